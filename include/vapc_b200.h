@@ -1,0 +1,259 @@
+/*
+ * vapc_b200.h — C ABI of libvapc_b200.so: the B200 (sm_100a) implementation of the
+ * voxelisation + per-voxel statistics path of 3dgeo-heidelberg/vapc.
+ *
+ * The reference has no FFI of its own (it is pure Python on pandas/numpy); the drop-in
+ * boundary is the method level of `vapc.Vapc` / `vapc.BiTemporalVapc`.  Each entry point
+ * below names the reference lines it replaces (paths relative to the reference repo).
+ * `vapc_b200/` (Python) mirrors the reference classes on top of exactly these calls;
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
+ *    parameter name ends in `_host`.  The library never allocates caller-visible memory;
+ *    scratch space is passed in (`ws`, `ws_bytes`) and sized by the `*_workspace_bytes`
+ *    queries.
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing
+ *    synchronises unless documented.
+ *  - return value: 0 = VAPC_OK, negative = VAPC_E_*; `vapc_last_error()` returns a
+ *    thread-local message.  Nothing throws.
+ *  - points are referred to by uint32 indices (N < 2^32 per GPU); voxel rows by uint32
+ *    too.  Voxel rows are always in lexicographic (voxel_x, voxel_y, voxel_z) order, the
+ *    order the reference emits (tests/test_voxel.py:217-229); points inside a voxel keep
+ *    their original order (stable sort), so "first point of a voxel" is the lowest index
+ *    (`drop_duplicates`, vapc.py:1208).
+ */
+#ifndef VAPC_B200_H
+#define VAPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAPC_OK 0
+#define VAPC_E_INVALID (-1)   /* bad argument */
+#define VAPC_E_CUDA (-2)      /* CUDA runtime error, see vapc_last_error() */
+#define VAPC_E_KEYSPACE (-3)  /* voxel bounding box needs more than 64 key bits */
+#define VAPC_E_WORKSPACE (-4) /* workspace too small */
+#define VAPC_E_RANGE (-5)     /* a point fell outside the grid given to vapc_pack_keys */
+
+#define VAPC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VAPC_API __attribute__((visibility("default")))
+#else
+#define VAPC_API
+#endif
+
+/* Voxel grid + packed-key layout.  key = ((vx-vmin[0]) << (bits[1]+bits[2])) |
+ * ((vy-vmin[1]) << bits[2]) | (vz-vmin[2]); x is most significant so that ascending key
+ * order is lexicographic (vx, vy, vz) order.  key_bytes is 4 when bits sum <= 32 else 8. */
+typedef struct vapc_grid {
+  double origin[3];   /* Vapc.origin        (vapc.py:60)  */
+  double voxel_size;  /* Vapc.voxel_size    (vapc.py:59)  */
+  int64_t vmin[3];    /* lowest voxel index per axis in the cloud */
+  int32_t bits[3];    /* key bits per axis */
+  int32_t key_bytes;  /* 4 or 8 */
+} vapc_grid_t;
+
+VAPC_API int vapc_abi_version(void);
+VAPC_API const char* vapc_last_error(void);
+
+/* ---- bounding box (feeds vapc_grid_t; also Vapc.compute_reduction_point, vapc.py:153-162,
+ * and the min/max of compute_percentage_occupied, vapc.py:761-763) ----------------------
+ * out6 = {min x, min y, min z, max x, max y, max z}; ws >= vapc_minmax_workspace_bytes(). */
+VAPC_API size_t vapc_minmax_workspace_bytes(void);
+VAPC_API int vapc_minmax_f64(const double* x, const double* y, const double* z, int64_t n, double* out6,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a2 Vapc.voxelize (vapc.py:188-207): v = floor((coord - origin) / voxel_size) as int64,
+ * IEEE subtract + IEEE divide + floor, bit-exact with numpy. --------------------------- */
+VAPC_API int vapc_voxel_coords_f64(const double* x, const double* y, const double* z, int64_t n,
+                          const vapc_grid_t* grid_host, int64_t* vx, int64_t* vy, int64_t* vz,
+                          void* stream);
+
+/* Host helper: fill vmin/bits/key_bytes of *grid_host from the cloud's coordinate bounding box
+ * minmax6_host (floor is monotone, so voxel(min) is the min voxel).  VAPC_E_KEYSPACE if the
+ * box needs more than 64 bits. */
+VAPC_API int vapc_grid_from_bounds(vapc_grid_t* grid_host, const double* minmax6_host);
+
+/* ---- packed keys (internal form of the voxel triple; the groupby key of vapc.py:724, :843,
+ * :877, :959, :1081).  keys: uint32 or uint64 per grid->key_bytes.  xyzw (nullable): 32-byte
+ * records {x, y, z, 0} written alongside so that later per-voxel gathers cost one sector per
+ * point.  status (int32, device, caller-zeroed): bit 0 set if a point fell outside the grid. */
+VAPC_API int vapc_pack_keys_f64(const double* x, const double* y, const double* z, int64_t n,
+                       const vapc_grid_t* grid_host, void* keys, double* xyzw, int32_t* status,
+                       void* stream);
+/* voxel triple back from keys (n keys -> 3 x int64) */
+VAPC_API int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* grid_host, int64_t* vx,
+                     int64_t* vy, int64_t* vz, void* stream);
+
+/* ---- stable LSD radix sort of (key, point index) pairs, 8-bit digits, in-house ---------
+ * Sorts bits [0, end_bit).  idx_is_iota != 0: the contents of idx are ignored and taken to be
+ * 0..n-1 (saves reading them in the first pass).  Buffers ping-pong; on return
+ * *result_in_alt_host is 1 when the sorted data are in (keys_alt, idx_alt), else 0 (in keys /
+ * idx).  key_bytes 4 or 8.  All four buffers must be distinct and hold n elements. */
+VAPC_API size_t vapc_sort_workspace_bytes(int64_t n);
+VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, uint32_t* idx, uint32_t* idx_alt,
+                    int32_t idx_is_iota, int64_t n, int32_t key_bytes, int32_t end_bit, void* ws,
+                    size_t ws_bytes, int32_t* result_in_alt_host, void* stream);
+
+/* ---- run-length segmentation of sorted keys into the voxel table ----------------------
+ * Step 1: count voxels.  Writes per-tile head counts + their exclusive scan into ws and the
+ * number of voxels into *nvoxels (device int64).  Step 2 (vapc_reduce_moments) needs the same
+ * ws untouched. */
+VAPC_API size_t vapc_segment_workspace_bytes(int64_t n);
+VAPC_API int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key_bytes, int64_t* nvoxels,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a4, a7, a8, a12 single-pass segmented reduction (vapc.py:715-726, 829-887, 929-1040)
+ * For every voxel v (row order = key order): count[v], first_idx[v] (lowest original index),
+ * start[v] (first sorted position; start[V] = n), voxel_keys[v], and the FP64 moments
+ *   mean3[a][v] = mean of (p_a - c_a(v)),   c(v) = origin + (v + 0.5) * voxel_size,
+ *   m2[k][v]    = SUM (p_a - mean_a)(p_b - mean_b)   (k over xx, xy, xz, yy, yz, zz).
+ * c(v) is an exact function of the key, so (count, mean3, m2) triples of the same voxel from
+ * different tiles or different GPUs combine with Chan's pairwise update without loss
+ * (vapc_merge_partials).  Inside a voxel, points are visited in original point order.
+ * point2voxel (nullable) gets the voxel row of every point.  Layout: mean3 is [3][V], m2 is
+ * [6][V] (column stride V = nvoxels_host).  xyzw = the records vapc_pack_keys wrote. */
+VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n,
+                        const vapc_grid_t* grid_host, const double* xyzw, int64_t nvoxels_host,
+                        void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
+                        double* mean3, double* m2, uint32_t* point2voxel, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---- a5, a7, a8, a12, a13, a14: per-voxel outputs from the moments ---------------------
+ * (vapc.py:730-741 density, 829-852 centroid, 856-887 std ddof=1, 929-1040 covariance,
+ *  1044-1090 eigenvalues — symmetric 3x3 cyclic Jacobi instead of LAPACK dgeev —, 1094-1146
+ *  the 8 features + the 3 normalised eigenvalues the reference leaves in the frame.)
+ * All outputs nullable; layouts [k][V].  cov6 order xx, xy, xz, yy, yz, zz; feat8 order
+ * Sum_of_Eigenvalues, Omnivariance, Eigenentropy, Anisotropy, Planarity, Linearity,
+ * Surface_Variation, Sphericity.  n == 1 voxels get NaN std/cov/eig/features as in the
+ * reference (vapc.py:977-1006, 1057-1058). */
+VAPC_API int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, const double* mean3,
+                     const double* m2, int64_t nvoxels, const vapc_grid_t* grid_host,
+                     double* density, double* cog3, double* std3, double* cov6, double* eig3,
+                     double* eign3, double* feat8, void* stream);
+
+/* ---- a11 centre / corner of voxel (vapc.py:891-925): ((v*vs) + vs/2) + origin and
+ * (v*vs) + origin, in the reference's operation order (bit-exact). out: [3][n]. */
+VAPC_API int vapc_voxel_center_corner(const void* voxel_keys, int64_t nvoxels, const vapc_grid_t* grid_host,
+                             double* center3, double* corner3, void* stream);
+
+/* ---- a9, a10, a15 closest-to-centroid (vapc.py:776-825, 1188-1195) ---------------------
+ * Per voxel: min over its points of sqrt((X-cog_x)^2 + (Y-cog_y)^2 + (Z-cog_z)^2) (plain
+ * products, left-to-right sum, no FMA — numpy's evaluation order) and the LOWEST original
+ * index attaining it. */
+VAPC_API int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n,
+                        int32_t key_bytes, const double* xyzw, const double* cog3,
+                        int64_t nvoxels_host, double* min_dist, uint32_t* argmin_idx, void* ws,
+                        size_t ws_bytes, void* stream);
+/* Per point (original order): distance to its voxel's centroid (vapc.py:790-794). */
+VAPC_API int vapc_point_distance(const double* x, const double* y, const double* z, int64_t n,
+                        const uint32_t* point2voxel, const double* cog3, int64_t nvoxels,
+                        double* distance, void* stream);
+
+/* ---- broadcast / gather helpers: out[i] = table[index[i]]  (the per-point broadcast of
+ * groupby.transform / merge(how="left"), vapc.py:724-726, 843-850, 1087-1089) ------------ */
+VAPC_API int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream);
+VAPC_API int vapc_gather_u32(const uint32_t* table, const uint32_t* index, int64_t n, uint32_t* out, void* stream);
+
+/* ---- a16 mode / mode_count of an integer attribute (vapc.py:407-433) --------------------
+ * vapc_mode_keys builds composite keys (voxel row << attr_bits) | int(attr) from the per-point
+ * attribute column (fp64 holding integers, truncated toward zero like astype(int),
+ * vapc.py:409, :423); status bit 1 = negative / NaN value (np.bincount would raise), bit 2 =
+ * value needs more than attr_bits.  After vapc_sort_pairs on those keys (8-byte keys,
+ * end_bit = voxel-row bits + attr_bits) the points are ordered by (voxel, value) and the voxel
+ * slices are the same [start[v], start[v+1]) as before.  vapc_mode_count then gives per voxel:
+ * mode = smallest most frequent value (np.argmax(np.bincount)), mode_count = number of distinct
+ * values whose share count / n >= threshold (fp64 division, as the reference).  Either output
+ * nullable. */
+VAPC_API int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, int64_t n, int32_t attr_bits,
+                   uint64_t* keys, int32_t* status, void* stream);
+VAPC_API int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t attr_bits, const uint32_t* start,
+                    int64_t nvoxels, double threshold, int64_t* mode, int64_t* mode_count,
+                    void* stream);
+
+/* ---- a16 (rest) mean / sum / min / max / var (ddof = 0) / median of an fp64 attribute
+ * (vapc.py:393-406).  order = point indices grouped by voxel ([start[v], start[v+1]) slices):
+ * idx_sorted for vapc_attr_stats (original order inside a voxel), and the (voxel, value) order
+ * produced by sorting vapc_f64_sort_keys by value, then stably by voxel row, for the median.
+ * std = sqrt(var).  All outputs nullable. */
+VAPC_API int vapc_attr_stats(const double* attr, const uint32_t* order, const uint32_t* start,
+                             int64_t nvoxels, double* sum, double* mean, double* vmin, double* vmax,
+                             double* var, void* stream);
+VAPC_API int vapc_f64_sort_keys(const double* attr, int64_t n, uint64_t* keys, void* stream);
+VAPC_API int vapc_attr_median(const double* attr, const uint32_t* order, const uint32_t* start,
+                              int64_t nvoxels, double* median, void* stream);
+
+/* ---- a18 mask membership by hashed key (MultiIndex.isin, vapc.py:594-598) ---------------
+ * The mask's voxel triples are packed to uint64 keys in the mask's own grid (needs <= 63 bits;
+ * triples outside the grid pack to the reserved key ~0 and status bit 0 is set) and inserted
+ * into an open-addressing table (uint64[capacity], capacity a power of two >= 2 * nmask,
+ * linear probing, multiplicative hash).  vapc_mask_lookup_points fuses voxelisation of the
+ * queried points (vapc.py:199-201, same origin / voxel_size as the mask grid) with the probe;
+ * vapc_mask_lookup_keys probes already packed keys.  member[i] = 1 / 0. */
+VAPC_API int vapc_pack_triples_i64(const int64_t* vx, const int64_t* vy, const int64_t* vz, int64_t n,
+                          const vapc_grid_t* grid_host, uint64_t* keys, int32_t* status, void* stream);
+VAPC_API size_t vapc_mask_table_bytes(int64_t nmask, int64_t* capacity_host);
+VAPC_API int vapc_mask_build(const uint64_t* mask_keys, int64_t nmask, void* table, int64_t capacity,
+                    void* stream);
+VAPC_API int vapc_mask_lookup_points(const double* x, const double* y, const double* z, int64_t n,
+                            const vapc_grid_t* grid_host, const void* table, int64_t capacity,
+                            uint8_t* member, void* stream);
+VAPC_API int vapc_mask_lookup_keys(const uint64_t* keys, int64_t n, const void* table, int64_t capacity,
+                          uint8_t* member, void* stream);
+
+/* ---- a17 voxel buffer (vapc.py:495-541): every triple + all (2b+1)^3 offsets, in the
+ * reference's expansion order (voxel-major, offsets in meshgrid 'ij' order); de-duplication is
+ * done by the caller with sort + segment.  out: [3][n * (2b+1)^3]. */
+VAPC_API int vapc_buffer_expand(const int64_t* vx, const int64_t* vy, const int64_t* vz, int64_t n,
+                       int32_t buffer_size, int64_t* out3, void* stream);
+
+/* ---- a22, a25 two-epoch voxel join (bi_vapc.py:78-84, 25-36) ----------------------------
+ * keys1 / keys2: sorted, unique uint64 keys packed with the SAME grid.  For each row of epoch
+ * 1: match1[i] = row in epoch 2 or 0xFFFFFFFF; likewise match2. */
+VAPC_API int vapc_join_sorted_keys(const uint64_t* keys1, int64_t n1, const uint64_t* keys2, int64_t n2,
+                          uint32_t* match1, uint32_t* match2, void* stream);
+
+/* ---- a23, a24 centroid distance + Mahalanobis change test (bi_vapc.py:86-138, 198-207) --
+ * For each pair r: rows i1[r], i2[r] of the two voxel tables (cog3 [3][V], cov6 [6][V]).
+ * distance = |cog1 - cog2|; C += 1e-10 I; d1 = diff' inv(C2) diff; d2 = diff' inv(C1) diff;
+ * p = 1 - chi2.cdf(d, 3) in closed form (1 - cdf, NOT a survival function: p == 0 must happen
+ * where the reference's does); significance = p1 < alpha or p2 < alpha; p_value = p1 if
+ * p1 < alpha else p2; change_type 1, 0 where not significant, 2 where p_value == 0.
+ * All outputs nullable. */
+VAPC_API int vapc_mahalanobis(const double* cog3_1, const double* cov6_1, int64_t v1, const double* cog3_2,
+                     const double* cov6_2, int64_t v2, const uint32_t* i1, const uint32_t* i2,
+                     int64_t npairs, double alpha, double* distance, double* d1, double* d2,
+                     double* p_value, int32_t* significance, int32_t* change_type, void* stream);
+
+/* ---- multi-GPU (north_star: partial accumulators exchanged by key range) ---------------
+ * Merge partial voxel rows that share a key: inputs are R partial rows (keys sorted, equal
+ * keys adjacent, in source-rank order), outputs the merged rows.  Same ws protocol as
+ * vapc_count_voxels (call it first on the received keys to get the merged row count). */
+VAPC_API int vapc_merge_partials(const void* keys_sorted, const uint32_t* order, int64_t nrows,
+                        int32_t key_bytes, const uint32_t* count_in, const double* mean3_in,
+                        const double* m2_in, int64_t in_stride, int64_t nvoxels_host,
+                        void* voxel_keys, uint32_t* count, double* mean3, double* m2, void* ws,
+                        size_t ws_bytes, void* stream);
+/* histogram of the top `hist_bits` key bits (splitter selection) */
+VAPC_API int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes, int32_t total_bits,
+                       int32_t hist_bits, uint32_t* hist, void* stream);
+
+/* ---- host-side self-tests of the fp64 helpers the kernels share (run on the CPU, no GPU
+ * needed): Jacobi eigenvalues of n symmetric 3x3 (cov6 rows xx xy xz yy yz zz -> 3 descending
+ * eigenvalues), Chan combination of n (count, mean3, m2) rows, and the Mahalanobis quadratic
+ * form + chi-square p of n (cov6, diff3) rows.  All pointers are HOST pointers. */
+VAPC_API int vapc_selftest_eig3_host(const double* cov6_host, int64_t n, double* eig3_host);
+VAPC_API int vapc_selftest_chan_host(const double* rows_host, int64_t n, double* out10_host);
+VAPC_API int vapc_selftest_mahalanobis_host(const double* cov6_host, const double* diff3_host, int64_t n,
+                                   double* d_host, double* p_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAPC_B200_H */

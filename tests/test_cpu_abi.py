@@ -1,0 +1,204 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/vapc_b200.h
+declares, the ctypes table matches the header, host-side helpers and the shared fp64 math (compiled
+for the host as self-test entry points) agree with numpy, and the facade validates its arguments
+like the reference.  No GPU compute is called here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "vapc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"VAPC_API\s+[\w\s\*]+?\b(vapc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    from vapc_b200 import _lib as L
+
+    decl = header_functions()
+    assert len(decl) >= 35
+    lib = C.CDLL(L.LIB_PATH)
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/vapc_b200.h but not exported"
+    # the ctypes table binds exactly the declared functions, with the declared number of arguments
+    assert set(L.SIGNATURES) == set(decl)
+    for name, (_, argtypes) in L.SIGNATURES.items():
+        assert len(argtypes) == decl[name], name
+    assert L.raw("vapc_abi_version")() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    from vapc_b200 import engine as E
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.VoxelCloud.build(np.zeros(4), np.zeros(4), np.zeros(4), 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.voxel_coords(np.zeros(4), np.zeros(4), np.zeros(4), 1.0, [0, 0, 0])
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vapc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_grid_from_bounds_matches_numpy_floor():
+    from vapc_b200 import engine as E
+    from vapc_b200._lib import VapcError
+
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        vs = float(rng.choice([0.05, 0.1, 0.25, 0.3, 1.0, 7.5]))
+        origin = rng.uniform(-10, 10, 3).tolist()
+        lo = rng.uniform(-1e4, 1e4, 3)
+        hi = lo + rng.uniform(0, 500, 3)
+        g = E.grid_from_bounds(vs, origin, list(lo) + list(hi))
+        vmin = np.floor((lo - origin) / vs).astype(np.int64)
+        vmax = np.floor((hi - origin) / vs).astype(np.int64)
+        assert list(g.vmin) == vmin.tolist()
+        for k in range(3):
+            assert g.bits[k] == int(vmax[k] - vmin[k]).bit_length()
+        assert g.key_bytes == (4 if g.total_bits <= 32 else 8)
+    g = E.grid_from_bounds(0.1, [0, 0, 0], [0.3, 0.6, 0.7, 0.3, 0.6, 0.7])  # KAT-1: 2, 5, 6 (not 3, 6, 7)
+    assert list(g.vmin) == [2, 5, 6] and g.total_bits == 0
+    with pytest.raises(VapcError):
+        E.grid_from_bounds(1e-9, [0, 0, 0], [0, 0, 0, 1e6, 1e6, 1e6])  # 3 x 50 bits
+    with pytest.raises(ValueError):
+        E.grid_from_bounds(-1.0, [0, 0, 0], [0, 0, 0, 1, 1, 1])
+    with pytest.raises(ValueError):
+        E.grid_from_bounds(1.0, [0, 0, 0], [0, 0, 0, np.nan, 1, 1])
+
+
+def test_host_selftest_eig3_matches_numpy():
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(1)
+    mats = []
+    for i in range(4000):
+        n = int(rng.integers(2, 12))
+        pts = rng.normal(0, 1, (n, 3)) * rng.uniform(1e-4, 1, 3)
+        if i % 7 == 0:
+            pts[:, 2] = pts[:, 0] * 0.5  # rank deficient
+        if i % 11 == 0:
+            pts = np.round(pts, 2)
+        mats.append(np.cov(pts.T))
+    mats += [np.zeros((3, 3)), np.eye(3), np.diag([3.0, 3.0, 1.0]), np.diag([1e-12, 5.0, 5.0]), np.full((3, 3), 2.0)]
+    mats = np.array(mats)
+    cov6 = np.ascontiguousarray(mats[:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]])
+    out = np.empty((len(mats), 3))
+    assert L.raw("vapc_selftest_eig3_host")(cov6.ctypes.data, len(mats), out.ctypes.data) == 0
+    ref = np.linalg.eigvalsh(mats)[:, ::-1]
+    scale = np.maximum(np.abs(ref[:, :1]), 1e-300)
+    assert np.max(np.abs(out - ref) / scale) < 1e-13
+    assert np.all(out[:, 0] >= out[:, 1]) and np.all(out[:, 1] >= out[:, 2])
+
+
+def test_host_selftest_chan_combination():
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(2)
+    pts = rng.normal(0, 0.02, (5000, 3)) + [0.21, -0.13, 0.4]
+    cuts = [0, 1, 2, 40, 41, 1000, 1001, 4999, 5000]
+    rows = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        c = pts[a:b]
+        m = c.mean(0)
+        d = c - m
+        M = d.T @ d
+        rows.append([b - a, *m, M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]])
+    rows = np.ascontiguousarray(np.array(rows, dtype=np.float64))
+    out = np.empty(10)
+    assert L.raw("vapc_selftest_chan_host")(rows.ctypes.data, len(rows), out.ctypes.data) == 0
+    m = pts.mean(0)
+    d = pts - m
+    M = d.T @ d
+    ref = np.array([5000, *m, M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]])
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-18)
+
+
+def test_host_selftest_mahalanobis_matches_scipy():
+    from scipy.stats import chi2
+
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(3)
+    n = 3000
+    covs, diffs = [], []
+    for _ in range(n):
+        pts = rng.normal(0, 1, (8, 3)) * rng.uniform(0.01, 0.3, 3)
+        covs.append(np.cov(pts.T))
+        diffs.append(rng.normal(0, 0.2, 3) * rng.choice([0.01, 0.1, 1.0, 10.0]))
+    covs, diffs = np.array(covs), np.ascontiguousarray(np.array(diffs))
+    cov6 = np.ascontiguousarray(covs[:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]])
+    d = np.empty(n)
+    p = np.empty(n)
+    assert L.raw("vapc_selftest_mahalanobis_host")(cov6.ctypes.data, diffs.ctypes.data, n, d.ctypes.data, p.ctypes.data) == 0
+    ce = covs + np.eye(3) * 1e-10
+    d_ref = np.einsum("ij,ijk,ik->i", diffs, np.linalg.inv(ce), diffs)
+    cond = np.linalg.cond(ce)
+    assert np.all(np.abs(d - d_ref) <= d_ref * (1e-12 + 1e-15 * cond))
+    p_ref = 1 - chi2.cdf(d_ref, df=3)
+    assert np.all(np.abs(p - p_ref) <= 1e-15 + 1e-9 * p_ref + 1e-12 * cond * p_ref)
+    # the tail: p is exactly 0 where scipy's 1 - cdf is (drives change_type 2, bi_vapc.py:135)
+    big = np.array([60.0, 75.0, 78.0, 79.0, 80.0, 100.0, 1e4, 1e12])
+    cov6 = np.tile(np.array([1.0 - 1e-10, 0, 0, 1.0 - 1e-10, 0, 1.0 - 1e-10]), (len(big), 1))
+    diffs = np.zeros((len(big), 3))
+    diffs[:, 0] = np.sqrt(big)
+    d = np.empty(len(big))
+    p = np.empty(len(big))
+    L.raw("vapc_selftest_mahalanobis_host")(np.ascontiguousarray(cov6).ctypes.data, np.ascontiguousarray(diffs).ctypes.data, len(big),
+                                            d.ctypes.data, p.ctypes.data)
+    p_ref = 1 - chi2.cdf(d, df=3)
+    assert np.array_equal(p == 0, p_ref == 0)
+    assert np.all(np.abs(p - p_ref) <= 4e-16)
+
+
+def test_facade_argument_validation_matches_reference():
+    import pandas as pd
+
+    import vapc_b200 as vapc
+
+    with pytest.raises(ValueError):
+        vapc.Vapc(0)
+    with pytest.raises(ValueError):
+        vapc.Vapc(-1.0)
+    with pytest.raises(ValueError):
+        vapc.Vapc(1.0, origin=[0, 0])
+    with pytest.raises(ValueError):
+        vapc.Vapc(1.0, origin=(0, 0, 0))  # the reference insists on a list (vapc.py:68)
+    v = vapc.Vapc(0.5)
+    assert v.origin == [0, 0, 0] and v.return_at == "closest_to_center_of_gravity" and v.compute == [] and v.attributes == {}
+    assert len(v.AVAILABLE_COMPUTATIONS) == 13
+    v.compute = ["point_count", "nonsense"]
+    with pytest.raises(ValueError):
+        v.compute_requested_attributes()
+    v.df = pd.DataFrame({"X": [0.0, 1.0], "Y": [0.0, 1.0], "Z": [0.0, 1.0], "point_count": [1, 5]})
+    with pytest.raises(ValueError):
+        v.filter_attributes("point_count", "leq", 3)
+    with pytest.raises(KeyError):
+        v.filter_attributes("attribute", "<=", 3)
+    v.filter_attributes("point_count", "Greater_Than", 3)  # case-insensitive long names
+    assert len(v.df) == 1
+    with pytest.raises(ValueError):
+        vapc.BiTemporalVapc([v])
+    with pytest.raises(AttributeError):
+        class DH:
+            df = None
+        vapc.Vapc(1.0).get_data_from_data_handler(DH())
+    assert callable(vapc.enable_trace) and callable(vapc.enable_timeit)

@@ -1,0 +1,309 @@
+"""GPU tests of the reference-shaped facade (vapc_b200.Vapc / BiTemporalVapc) against the golden
+fixtures the UNMODIFIED reference produced (tests/golden, oracle/make_golden.py), column by column,
+and a replay of the reference's own unit-test strategy (known 8-voxel grid, seeded plane, dispatch,
+filter known answer).  Tolerances: tests/parity.py."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+FULL = ["point_count", "point_density", "center_of_gravity", "std_of_cog", "covariance_matrix", "eigenvalues",
+        "geometric_features", "distance_to_center_of_gravity", "closest_to_center_of_gravity", "center_of_voxel", "corner_of_voxel"]
+MODES = ["center_of_voxel", "corner_of_voxel", "center_of_gravity", "closest_to_center_of_gravity"]
+
+
+@pytest.fixture(scope="module")
+def vapc():
+    import vapc_b200
+
+    return vapc_b200
+
+
+def input_frame(gold):
+    cols = [k[3:] for k in gold if k.startswith("in_") and gold[k].ndim == 1 and len(gold[k]) == len(gold["in_X"])
+            and not k.startswith(("in_mask_", "in_e1_", "in_e2_"))]
+    cols = ["X", "Y", "Z"] + [c for c in cols if c not in "XYZ"]
+    return pd.DataFrame({c: gold["in_" + c] for c in cols})
+
+
+def new(vapc, gold, df=None, **kw):
+    origin = gold["in_origin"].tolist()
+    v = vapc.Vapc(float(gold["in_voxel_size"]), origin=origin, **kw)
+    v.df = (input_frame(gold) if df is None else df).copy()
+    v.original_attributes = v.df.columns.tolist()
+    return v
+
+
+@pytest.mark.parametrize("name", P.cloud_cases())
+def test_full_attribute_set_matches_reference(vapc, name):
+    gold = P.load_golden(name)
+    v = new(vapc, gold)
+    v.compute = list(FULL)
+    v.compute_requested_attributes()
+    df = v.df
+    assert df.columns.tolist() == gold["pt__columns"].tolist(), "column names and order"
+    assert len(df) == len(gold["in_X"])
+    coords = np.stack([gold["in_X"], gold["in_Y"], gold["in_Z"]], 1)
+    cmax = np.abs(coords).max()
+    vs = float(gold["in_voxel_size"])
+    # integers: bit-exact, same dtype
+    for c in ("voxel_x", "voxel_y", "voxel_z", "point_count"):
+        assert df[c].dtype == np.int64
+        np.testing.assert_array_equal(df[c].to_numpy(), gold["pt_" + c], err_msg=c)
+    for c in ("center_x", "center_y", "center_z", "corner_x", "corner_y", "corner_z"):
+        np.testing.assert_array_equal(df[c].to_numpy(), gold["pt_" + c], err_msg=c)
+    P.assert_close_rel(df["point_density"].to_numpy(), gold["pt_point_density"], what="density")
+    for d in "xyz":
+        P.assert_close_rel(df[f"cog_{d}"].to_numpy(), gold[f"pt_cog_{d}"], what=f"cog_{d}")
+        P.assert_close_rel(df[f"std_{d}"].to_numpy(), gold[f"pt_std_{d}"], what=f"std_{d}", atol=8 * P.EPS * cmax)
+    # covariance, H1 rule, per point (all points of a voxel carry the voxel's value)
+    six = ("cov_xx", "cov_xy", "cov_xz", "cov_yy", "cov_yz", "cov_zz")
+    got6 = np.stack([df[c].to_numpy() for c in six], 1)
+    ref6 = np.stack([gold["pt_" + c] for c in six], 1)
+    cnt = gold["pt_point_count"]
+    grp = pd.DataFrame({"k0": gold["pt_voxel_x"], "k1": gold["pt_voxel_y"], "k2": gold["pt_voxel_z"],
+                        "s": (coords ** 2).sum(1)}).groupby(["k0", "k1", "k2"])["s"].transform("mean").to_numpy()
+    P.assert_cov_h1(got6, ref6, cnt, grp)
+    for a, b in (("cov_xy", "cov_yx"), ("cov_xz", "cov_zx"), ("cov_yz", "cov_zy")):
+        np.testing.assert_array_equal(df[a].to_numpy(), df[b].to_numpy())
+    ref_eig = np.stack([gold[f"pt_Eigenvalue_{i}"] for i in (1, 2, 3)], 1)
+    got_eig = np.stack([df[f"Eigenvalue_{i}"].to_numpy() for i in (1, 2, 3)], 1)
+    P.assert_eig_h7(got_eig, ref_eig, cnt)
+    P.assert_features_h7(np.stack([df[c].to_numpy() for c in P.FEATURES], 1), np.stack([gold["pt_" + c] for c in P.FEATURES], 1), ref_eig, cnt)
+    ok = cnt > 1
+    for i in (1, 2, 3):
+        assert np.all(np.abs(df[f"Eigenvalue_{i}_n"].to_numpy()[ok] - gold[f"pt_Eigenvalue_{i}_n"][ok]) <= 1e-9)
+    tol = 8 * P.EPS * max(vs, cmax)
+    assert np.all(np.abs(df["distance"].to_numpy() - gold["pt_distance"]) <= 1e-9 * gold["pt_distance"] + tol)
+    assert np.all(np.abs(df["min_distance"].to_numpy() - gold["pt_min_distance"]) <= 1e-9 * gold["pt_min_distance"] + tol)
+    v2 = new(vapc, gold)
+    v2.compute_percentage_occupied()
+    assert v2.percentage_occupied == float(gold["percentage_occupied"])
+
+
+@pytest.mark.parametrize("name", P.cloud_cases())
+@pytest.mark.parametrize("mode", MODES)
+def test_reduce_to_voxels_matches_reference(vapc, name, mode):
+    gold = P.load_golden(name)
+    v = new(vapc, gold, return_at=mode)
+    v.reduce_to_voxels()
+    assert v.reduced is True
+    assert v.df.columns.tolist() == gold[f"red_{mode}__columns"].tolist()
+    ref = np.stack([gold[f"red_{mode}_{c}"] for c in "XYZ"], 1)
+    got = v.df[["X", "Y", "Z"]].to_numpy()
+    if mode in ("center_of_voxel", "corner_of_voxel"):
+        np.testing.assert_array_equal(got, ref)  # exact values, exact (lexicographic voxel) order
+    elif mode == "center_of_gravity":
+        assert got.shape == ref.shape
+        # rows are sorted by the centroid floats; last-bit differences may swap equal-X neighbours, so compare sorted
+        np.testing.assert_allclose(got[np.lexsort(got.T[::-1])], ref[np.lexsort(ref.T[::-1])], rtol=1e-9, atol=0)
+    else:
+        ref_set, got_set = {tuple(r) for r in ref.tolist()}, {tuple(r) for r in got.tolist()}
+        assert len(ref_set ^ got_set) <= max(2, int(0.02 * len(ref_set))), "closest-point rows (H5 near-tie slack)"
+    others = [c for c in v.df.columns if c not in "XYZ"]
+    if mode != "closest_to_center_of_gravity" and others:
+        if mode == "center_of_gravity":
+            a = v.df.sort_values(["X", "Y", "Z"])[others].to_numpy()
+            o = np.lexsort(ref.T[::-1])
+            b = np.stack([gold[f"red_{mode}_{c}"] for c in others], 1)[o]
+            np.testing.assert_array_equal(a, b)
+        else:
+            np.testing.assert_array_equal(v.df[others].to_numpy(), np.stack([gold[f"red_{mode}_{c}"] for c in others], 1))
+
+
+@pytest.mark.parametrize("name", [n for n in P.cloud_cases() if any(k.startswith("stat_") for k in P.load_golden(n))])
+def test_attribute_statistics_match_reference(vapc, name):
+    gold = P.load_golden(name)
+    keys = [k for k in gold if k.startswith("stat_") and not k.startswith("stat_voxel_")]
+    attrs = sorted((k[3:] for k in gold if k.startswith("in_")), key=len, reverse=True)
+    spec = {}
+    for k in keys:
+        col = k[5:]
+        attr = next(a for a in attrs if col.startswith(a + "_"))
+        spec.setdefault(attr, []).append(col[len(attr) + 1:])
+    v = new(vapc, gold, attributes=spec)
+    v.compute_requested_statistics_per_attributes()
+    assert v.attributes_per_voxel is True
+    for k in keys:
+        col = k[5:]
+        got, ref = v.df[col].to_numpy(), gold[k]
+        if "mode" in col or col.endswith(("_min", "_max", "_median")):
+            np.testing.assert_array_equal(got, ref, err_msg=col)
+            if "mode" in col:
+                assert got.dtype == np.int64
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12, err_msg=col)
+
+
+@pytest.mark.parametrize("name", [n for n in P.cloud_cases() if "mask_in_rows" in P.load_golden(n)])
+def test_mask_and_buffer_match_reference(vapc, name):
+    gold = P.load_golden(name)
+    mask_df = pd.DataFrame({c: gold["in_mask_" + c] for c in "XYZ"})
+    for mode in ("in", "out"):
+        p = new(vapc, gold, df=input_frame(gold).assign(_row=np.arange(len(gold["in_X"]), dtype=np.float64)))
+        m = new(vapc, gold, df=mask_df)
+        p.select_by_mask(m, segment_in_or_out=mode)
+        np.testing.assert_array_equal(p.df["_row"].to_numpy().astype(np.int64), gold[f"mask_{mode}_rows"])
+        assert p.voxelized is False and "voxel_x" not in p.df.columns
+        assert list(p.df.index.names) == ["idx_voxel_x", "idx_voxel_y", "idx_voxel_z"]
+    m = new(vapc, gold, df=mask_df)
+    buf = m.compute_voxel_buffer(buffer_size=int(gold["in_mask_buffer_size"]))
+    np.testing.assert_array_equal(buf[["voxel_x", "voxel_y", "voxel_z"]].to_numpy(), gold["mask_buffer_voxels"])
+    np.testing.assert_array_equal(buf[["X", "Y", "Z"]].to_numpy(), gold["mask_buffer_xyz"])
+    p = new(vapc, gold, df=input_frame(gold).assign(_row=np.arange(len(gold["in_X"]), dtype=np.float64)))
+    m.voxel_index = False
+    m.df = m.buffer_df
+    p.select_by_mask(m, segment_in_or_out="in")
+    np.testing.assert_array_equal(p.df["_row"].to_numpy().astype(np.int64), gold["mask_buffer_in_rows"])
+    with pytest.raises(ValueError):
+        new(vapc, gold).select_by_mask(new(vapc, gold, df=mask_df), segment_in_or_out="sideways")
+
+
+@pytest.mark.parametrize("name", [n for n in P.cloud_cases() if "bi_merged_voxels" in P.load_golden(n)])
+def test_bitemporal_matches_reference(vapc, name):
+    gold = P.load_golden(name)
+    vs, alpha = float(gold["in_bi_voxel_size"]), float(gold["in_bi_alpha"])
+    eps = []
+    for k in "12":
+        v = vapc.Vapc(vs)
+        v.df = pd.DataFrame({c: gold[f"in_e{k}_{c}"] for c in "XYZ"})
+        v.original_attributes = v.df.columns.tolist()
+        eps.append(v)
+    bi = vapc.BiTemporalVapc(eps)
+    with pytest.raises(ValueError):
+        bi.compute_voxels_occupied_in_single_epoch()
+    bi.prepare_data_for_mahalanobis_distance()
+    bi.merge_vapcs_with_same_voxel_index()
+    bi.compute_distance()
+    bi.compute_mahalanobis_distance(alpha=alpha)
+    bi.compute_voxels_occupied_in_single_epoch()
+    bi.prepare_data_for_export()
+    md = bi.merged_df
+    ref_vox = gold["bi_merged_voxels"]
+    got_vox = np.array([list(t) for t in md.index.tolist()], np.int64).reshape(-1, 3)
+    # the merged rows follow the epoch-1 centroid sort; a last-bit centroid difference may swap equal-X
+    # neighbours, so align by voxel triple
+    def order(vox):
+        return np.lexsort((vox[:, 2], vox[:, 1], vox[:, 0]))
+    og, orf = order(got_vox), order(ref_vox)
+    np.testing.assert_array_equal(got_vox[og], ref_vox[orf])
+    assert (got_vox == ref_vox).mean() > 0.99
+    P.assert_close_rel(md["distance"].to_numpy()[og], gold["bi_merged_distance"][orf], rtol=1e-9, atol=1e-13, what="distance")
+    six = ("cov_xx", "cov_xy", "cov_xz", "cov_yy", "cov_yz", "cov_zz")
+    nine = ("cov_xx", "cov_xy", "cov_xz", "cov_yx", "cov_yy", "cov_yz", "cov_zx", "cov_zy", "cov_zz")
+    eye = np.eye(3) * 1e-10
+    d1, d2 = bi.mahalanobis_d
+    if "bi_d1" in gold:
+        # conditioning-aware rule: the reference's own raw-moment covariances carry (|x|/sigma)^2 eps
+        cov_y = np.stack([gold[f"bi_merged_{c}_y"] for c in nine], 1).reshape(-1, 3, 3)[orf] + eye
+        cov_x = np.stack([gold[f"bi_merged_{c}_x"] for c in nine], 1).reshape(-1, 3, 3)[orf] + eye
+        c1 = P.assert_mahalanobis(d1[og], gold["bi_d1"][orf], cov_y, cov_rel=1e-9, what="d1")
+        c2 = P.assert_mahalanobis(d2[og], gold["bi_d2"][orf], cov_x, cov_rel=1e-9, what="d2")
+    p, pr = md["p_value"].to_numpy()[og], gold["bi_merged_p_value"][orf]
+    assert np.array_equal(np.isnan(p), np.isnan(pr))
+    cond = np.full(len(p), np.inf)
+    okc = ~np.isnan(gold["bi_d1"][orf]) & ~np.isnan(gold["bi_d2"][orf])
+    cond[okc] = np.maximum(np.linalg.cond(cov_x[okc]), np.linalg.cond(cov_y[okc]))
+    well = cond < 1e2
+    assert np.all(np.abs(p[well] - pr[well]) <= 1e-15 + 1e-7 * np.abs(pr[well]))
+    stable = (well & (np.abs(pr - alpha) > 1e-6)) | (pr == 0)
+    sig, ct = md["mahalanobi_significance"].to_numpy()[og], md["change_type"].to_numpy()[og]
+    np.testing.assert_array_equal(sig[stable], gold["bi_merged_mahalanobi_significance"][orf][stable])
+    np.testing.assert_array_equal(ct[stable], gold["bi_merged_change_type"][orf][stable])
+    # appear / disappear rows and the export layout
+    ex = bi.df
+    assert ex.columns.tolist() == ["X", "Y", "Z", "distance", "mahalanobi_significance", "p_value", "change_type"]
+    n_m = len(md)
+    ex_vox = np.array([list(t) for t in ex.index.tolist()], np.int64).reshape(-1, 3)
+    np.testing.assert_array_equal(ex_vox[n_m:], gold["bi_export_voxels"][n_m:])
+    np.testing.assert_array_equal(ex["change_type"].to_numpy()[n_m:], gold["bi_export_change_type"][n_m:])
+    np.testing.assert_allclose(ex[["X", "Y", "Z"]].to_numpy()[n_m:], np.stack([gold[f"bi_export_{c}"] for c in "XYZ"], 1)[n_m:], rtol=1e-9)
+    assert np.isnan(ex["distance"].to_numpy()[n_m:]).all()
+
+
+# ---- the reference's own unit-test strategy, re-expressed against the new package ----
+def test_known_voxel_grid(vapc):
+    """tests/test_voxel.py:88-229 — 8 known voxels x 5 random points, mask of 4 voxels, voxel size 1."""
+    rng = np.random.default_rng(123)
+    vox = np.array([[0, 0, 0], [1, 1, 1], [1, 2, 0], [3, 3, 0], [4, 5, 1], [5, 2, 0], [6, 5, 2], [9, 7, 1]])
+    pts = np.repeat(vox, 5, axis=0) + rng.uniform(0, 1, (40, 3))
+    df = pd.DataFrame(pts, columns=["X", "Y", "Z"])
+
+    def mk(d=df):
+        v = vapc.Vapc(voxel_size=1)
+        v.df = d.copy()
+        v.original_attributes = v.df.columns.tolist()
+        return v
+
+    v = mk()
+    v.voxelize()
+    assert v.voxelized is True
+    np.testing.assert_array_equal(np.unique(v.df[["voxel_x", "voxel_y", "voxel_z"]].to_numpy(), axis=0), vox)
+    v = mk()
+    v.compute_voxel_index()
+    assert v.voxel_index is True
+    np.testing.assert_array_equal(v.df.index.to_frame(index=False).to_numpy(), np.repeat(vox, 5, axis=0))
+    v = mk()
+    v.compute_corner_of_voxel()
+    np.testing.assert_array_equal(v.df[["corner_x", "corner_y", "corner_z"]].to_numpy(), np.repeat(vox, 5, axis=0))
+    v = mk()
+    v.return_at = "center_of_voxel"
+    v.reduce_to_voxels()
+    np.testing.assert_array_equal(v.df[["X", "Y", "Z"]].to_numpy(), vox + 0.5)
+    v = mk()
+    v.return_at = "center_of_gravity"
+    v.reduce_to_voxels()
+    means = pts.reshape(8, 5, 3).mean(1)
+    got = v.df[["X", "Y", "Z"]].to_numpy()
+    np.testing.assert_allclose(got[np.lexsort(got.T[::-1])], means[np.lexsort(means.T[::-1])])
+    v = mk()
+    v.return_at = "closest_to_center_of_gravity"
+    v.reduce_to_voxels()
+    d = np.linalg.norm(pts.reshape(8, 5, 3) - means[:, None, :], axis=2)
+    want = pts.reshape(8, 5, 3)[np.arange(8), d.argmin(1)]
+    got = v.df[["X", "Y", "Z"]].to_numpy()
+    np.testing.assert_allclose(got[np.lexsort(got.T[::-1])], want[np.lexsort(want.T[::-1])])
+    # mask in / out
+    mvox = np.array([[0, 0, 0], [0, 1, 0], [1, 1, 1], [1, 2, 0]])
+    mdf = pd.DataFrame(np.repeat(mvox, 5, axis=0) + rng.uniform(0, 1, (20, 3)), columns=["X", "Y", "Z"])
+    inside = {tuple(r) for r in mvox.tolist()} & {tuple(r) for r in vox.tolist()}
+    for mode, expect in (("in", len(inside) * 5), ("out", (8 - len(inside)) * 5)):
+        p, m = mk(), mk(mdf)
+        p.select_by_mask(m, segment_in_or_out=mode)
+        assert len(p.df) == expect
+    from itertools import product
+    v = mk()
+    v.compute_voxel_buffer(buffer_size=1)
+    want = np.unique((vox[:, None] + np.array(list(product(range(-1, 2), repeat=3)))).reshape(-1, 3), axis=0)
+    np.testing.assert_array_equal(np.unique(v.buffer_df[["voxel_x", "voxel_y", "voxel_z"]].to_numpy(), axis=0), want)
+
+
+def test_seeded_plane_known_answers(vapc):
+    """tests/test_compute.py:202-232, 246-271, 336-351 on the seeded plane fixture (plane500 golden)."""
+    gold = P.load_golden("plane500_vs1.0")
+    v = new(vapc, gold, df=input_frame(gold)[["X", "Y", "Z"]])
+    v.compute_reduction_point()
+    assert v.reduction_point == [120, 200, 3]
+    assert v.offset_applied is False
+    v.compute_offset()
+    assert v.offset_applied is True and v.df["X"].min() == 0 and v.df["Y"].min() == 0 and v.df["Z"].min() == 0
+    v.compute_offset()
+    assert v.offset_applied is False and v.df["X"].min() == 120 and v.df["Z"].min() == 3
+    v = new(vapc, gold, df=input_frame(gold)[["X", "Y", "Z"]])
+    v.voxelize()
+    v.compute = ["point_count"]
+    v.compute_requested_attributes()
+    v.filter_attributes(filter_attribute="point_count", min_max_eq=">", filter_value=3)
+    assert v.df.shape[0] == 442
+    # dispatcher: each name calls compute_<name> exactly once
+    from unittest.mock import patch
+    for name in vapc.Vapc.AVAILABLE_COMPUTATIONS:
+        v = new(vapc, gold, df=input_frame(gold)[["X", "Y", "Z"]])
+        v.voxelize()
+        v.compute = [name]
+        with patch(f"vapc_b200.Vapc.compute_{name}") as mock:
+            v.compute_requested_attributes()
+            mock.assert_called_once()

@@ -1,0 +1,319 @@
+"""GPU parity tests of the CUDA path (through the C ABI, via vapc_b200.engine) against the CPU
+oracle on seeded inputs, plus size-independent properties at larger sizes.  Tolerances are the
+parity rules of tests/parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vapc_oracle as O
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    from vapc_b200 import engine
+
+    return engine
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _u32(t):
+    return _np(t).astype(np.int64) & 0xFFFFFFFF
+
+
+def make_cloud(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":  # LAS-like quantised uniform box
+        q = [rng.integers(0, hi, n) for hi in (200000, 150000, 30000)]
+        pts = np.stack(q, axis=1) * 1e-4
+    elif kind == "negative":  # negative coordinates, unquantised
+        pts = rng.uniform([-37.5, -12.25, -3.0], [12.5, 40.0, 9.0], (n, 3))
+    elif kind == "clustered":  # heavy-tailed voxel occupancy: tight blobs + sheet + sparse noise
+        centers = rng.uniform(0, 40, (60, 3)) * [1, 1, 0.2]
+        blob = centers[rng.integers(0, 60, n // 2)] + rng.normal(0, 0.05, (n // 2, 3))
+        sheet = np.stack([rng.uniform(0, 40, n // 4), rng.uniform(0, 40, n // 4), np.zeros(n // 4)], axis=1)
+        sheet[:, 2] = 0.3 * np.sin(sheet[:, 0] / 3) + rng.normal(0, 0.01, n // 4)
+        noise = rng.uniform(0, 40, (n - n // 2 - n // 4, 3))
+        pts = np.round(np.vstack([blob, sheet, noise]), 4)
+        pts = pts[rng.permutation(n)]
+    elif kind == "utm":  # large coordinates: 64-bit keys when the origin stays at 0
+        pts = rng.uniform(0, 25, (n, 3)) + [476850.0, 5429100.0, 312.0]
+        pts = np.round(pts, 3)
+    elif kind == "duplicates":  # many exactly identical points and n == 1 / n == 2 voxels
+        base = rng.integers(0, 50, (n // 4, 3)) * 0.37
+        pts = np.vstack([base, base, base[: n // 8], rng.uniform(0, 18.5, (n - 2 * (n // 4) - n // 8, 3))])
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1]), np.ascontiguousarray(pts[:, 2])
+
+
+# --------------------------------------------------------------------------------------
+def test_voxel_coords_bit_exact(E):
+    g = P.load_golden("kat_voxelize")
+    for tag in "abc":
+        vs, origin = float(g[f"{tag}_vs"]), g[f"{tag}_origin"].tolist()
+        got = E.voxel_coords(g["in_X"], g["in_Y"], g["in_Z"], vs, origin)
+        for t, d in zip(got, "xyz"):
+            np.testing.assert_array_equal(_np(t), g[f"{tag}_voxel_{d}"])
+    rng = np.random.default_rng(1)
+    for vs, origin in ((0.1, [0, 0, 0]), (0.3, [1.5, -2.25, 0.3]), (1.0, [0, 0, 0]), (0.05, [-7.0, 3.0, 0.0])):
+        # values exactly on and next to voxel faces, where a reciprocal multiply goes wrong
+        k = rng.integers(-5000, 5000, 20000)
+        x = k * vs + origin[0]
+        x = np.concatenate([x, np.nextafter(x, np.inf), np.nextafter(x, -np.inf), rng.uniform(-500, 500, 20000)])
+        ref = O.voxelize(x, x[::-1].copy(), x * 0.5, origin, vs)
+        got = E.voxel_coords(x, x[::-1].copy(), x * 0.5, vs, origin)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(_np(a), b)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 255, 4096, 4097, 12289, 1_000_003])
+@pytest.mark.parametrize("bits,dtype", [(1, np.uint32), (7, np.uint32), (8, np.uint32), (17, np.uint32), (32, np.uint32),
+                                        (33, np.uint64), (47, np.uint64), (64, np.uint64)])
+def test_sort_pairs_stable(E, n, bits, dtype):
+    rng = np.random.default_rng(n * 131 + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, hi, n, dtype=np.uint64, endpoint=True).astype(dtype)
+    if n > 100:  # skew: half of the keys share one digit pattern
+        keys[: n // 2] &= dtype(hi & 0xFF00FF00FF00FF00)
+    tk = torch.from_numpy(keys.view(np.int32 if dtype == np.uint32 else np.int64)).cuda()
+    ks, idx = E.sort_pairs(tk, bits)
+    order = np.argsort(keys, kind="stable")
+    got_keys = _np(ks).view(dtype)
+    np.testing.assert_array_equal(got_keys, keys[order])
+    np.testing.assert_array_equal(_u32(idx), order)
+
+
+def test_sort_pairs_with_payload_and_partial_bits(E):
+    rng = np.random.default_rng(5)
+    n = 50000
+    keys = rng.integers(0, 1 << 20, n, dtype=np.uint64).astype(np.uint32)
+    payload = rng.permutation(n).astype(np.uint32)
+    ks, idx = E.sort_pairs(torch.from_numpy(keys.view(np.int32)).cuda(), 12, idx=torch.from_numpy(payload.view(np.int32)).cuda())
+    order = np.argsort(keys & 0xFFF, kind="stable")  # only the low 12 bits are sorted
+    np.testing.assert_array_equal(_np(ks).view(np.uint32), keys[order])
+    np.testing.assert_array_equal(_u32(idx), payload[order])
+
+
+# --------------------------------------------------------------------------------------
+def check_cloud(E, x, y, z, vs, origin, eig_faithful=False):
+    cloud = E.VoxelCloud.build(x, y, z, vs, origin)
+    vx, vy, vz = O.voxelize(x, y, z, origin, vs)
+    g = O.group_by_voxel(vx, vy, vz)
+    V = g.nvoxels
+    assert cloud.nvoxels == V
+    # integer outputs: bit-exact
+    cvx, cvy, cvz = (_np(t) for t in cloud.voxel_coords())
+    np.testing.assert_array_equal(cvx, g.vx)
+    np.testing.assert_array_equal(cvy, g.vy)
+    np.testing.assert_array_equal(cvz, g.vz)
+    np.testing.assert_array_equal(_u32(cloud.count), g.counts)
+    np.testing.assert_array_equal(_u32(cloud.first_idx), g.first_index)
+    np.testing.assert_array_equal(_u32(cloud.point2voxel), g.point2voxel)
+    np.testing.assert_array_equal(_u32(cloud.idx_sorted), g.order)  # stable: original order inside a voxel
+    np.testing.assert_array_equal(_u32(cloud.start), np.append(g.starts, len(x)))
+    assert cloud.percentage_occupied() == O.percentage_occupied(g)
+    # floating point outputs
+    st = cloud.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+    P.assert_close_rel(_np(st.density), O.point_density(g, vs), what="density")
+    cog_ref = O.center_of_gravity(x, y, z, g)
+    P.assert_close_rel(_np(st.cog).T, cog_ref, what="cog")
+    std_ref = O.std_of_cog(x, y, z, g)
+    P.assert_close_rel(_np(st.std).T, std_ref, what="std", atol=1e-12 * vs)
+    cov_exact = O.covariance_exact(x, y, z, g)
+    ssq = np.zeros(V)  # vs the exact oracle no allowance for the raw-moment formula is needed
+    P.assert_cov_h1(_np(st.cov).T, cov_exact, g.counts, ssq, what="cov vs exact")
+    cov_ref = O.covariance_reference_formula(x, y, z, g)
+    ssq = (O._group_sum(x * x, g) + O._group_sum(y * y, g) + O._group_sum(z * z, g)) / g.counts
+    P.assert_cov_h1(_np(st.cov).T, cov_ref, g.counts, ssq, what="cov vs reference formula")
+    eig_ref = O.eigenvalues(x, y, z, g, faithful=eig_faithful)
+    P.assert_eig_h7(_np(st.eig).T, eig_ref, g.counts)
+    feat_ref, eign_ref = O.geometric_features(eig_ref)
+    P.assert_features_h7(_np(st.feat).T, feat_ref, eig_ref, g.counts)
+    ok = g.counts > 1
+    assert np.all(np.abs(_np(st.eig_n).T[ok] - eign_ref[ok]) <= 1e-9)
+    # centre / corner: bit-exact
+    center, corner = cloud.center_corner()
+    np.testing.assert_array_equal(_np(center).T, O.center_of_voxel(g, origin, vs))
+    np.testing.assert_array_equal(_np(corner).T, O.corner_of_voxel(g, origin, vs))
+    # closest to centroid (H5)
+    dist_ref = O.distance_to_center_of_gravity(x, y, z, g, cog_ref)
+    dmin_ref, winner_ref, _ = O.closest_to_center_of_gravity(dist_ref, g)
+    md, am = cloud.closest_to_cog()
+    am = _u32(am)
+    scale = 8 * P.EPS * max(vs, np.abs(cog_ref).max())
+    assert np.all(np.abs(_np(md) - dmin_ref) <= 1e-9 * dmin_ref + scale)
+    assert np.all(g.point2voxel[am] == np.arange(V)), "winner must belong to its voxel"
+    assert np.all(dist_ref[am] <= dmin_ref * (1 + 1e-12) + scale), "winner must be in the reference's tied set"
+    # voxels with a clear winner (runner-up separated from the minimum): exact match required
+    ds = dist_ref[g.order]
+    vid_sorted = g.point2voxel[g.order]
+    ds_in_voxel = ds[np.lexsort((ds, vid_sorted))]
+    second = np.full(V, np.inf)
+    multi = g.counts > 1
+    second[multi] = ds_in_voxel[g.starts[multi] + 1]
+    clear = second > dmin_ref * (1 + 1e-9) + 1e-12
+    np.testing.assert_array_equal(am[clear], winner_ref[clear])
+    pd_ = _np(cloud.point_distance())
+    assert np.all(np.abs(pd_ - dist_ref) <= 1e-9 * dist_ref + scale)
+    return cloud, g
+
+
+@pytest.mark.parametrize("kind,n,vs,origin", [
+    ("uniform", 60000, 0.5, [0, 0, 0]),
+    ("uniform", 200000, 0.1, [0, 0, 0]),
+    ("negative", 50000, 0.3, [1.5, -2.25, 0.3]),
+    ("clustered", 120000, 0.25, [0, 0, 0]),
+    ("clustered", 120000, 5.0, [0, 0, 0]),      # voxels far larger than a 1024-point tile: carry chains
+    ("uniform", 70000, 100.0, [0, 0, 0]),       # every point in one voxel
+    ("utm", 40000, 0.5, [0, 0, 0]),             # 64-bit keys
+    ("utm", 40000, 0.05, [476850.0, 5429100.0, 312.0]),
+    ("duplicates", 40000, 0.37, [0, 0, 0]),
+    ("uniform", 1, 1.0, [0, 0, 0]),
+    ("uniform", 3, 1000.0, [0, 0, 0]),
+])
+def test_voxel_table_vs_oracle(E, kind, n, vs, origin):
+    x, y, z = make_cloud(kind, n, seed=n + int(vs * 100))
+    check_cloud(E, x, y, z, vs, origin)
+
+
+def test_mode_count_vs_oracle(E):
+    x, y, z = make_cloud("clustered", 80000, 3)
+    rng = np.random.default_rng(4)
+    attr = rng.integers(0, 9, len(x)).astype(np.float64)
+    attr[rng.random(len(x)) < 0.5] = 2.0
+    for vs in (0.05, 0.2, 1.0, 50.0):
+        cloud = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+        g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], vs))
+        mode, counts = cloud.mode_count(attr, [0.1, 0.34, 0.5, 1.0])
+        np.testing.assert_array_equal(_np(mode), O.attribute_statistic(attr, g, "mode"))
+        for p, t in counts.items():
+            np.testing.assert_array_equal(_np(t), O.attribute_statistic(attr, g, f"mode_count,{p}"), err_msg=f"vs={vs} p={p}")
+    with pytest.raises(ValueError):
+        cloud.mode_count(attr - 3.0, [0.1])
+
+
+def test_attribute_statistics_vs_oracle(E):
+    x, y, z = make_cloud("uniform", 30000, 6)
+    rng = np.random.default_rng(7)
+    attr = rng.normal(-3, 5, len(x))
+    cloud = E.VoxelCloud.build(x, y, z, 0.7, [0, 0, 0])
+    g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], 0.7))
+    res = E.attribute_statistics(cloud, attr)
+    for stat in ("min", "max", "median"):
+        np.testing.assert_array_equal(_np(res[stat]), O.attribute_statistic(attr, g, stat), err_msg=stat)
+    for stat in ("mean", "sum", "var", "std"):
+        np.testing.assert_allclose(_np(res[stat]), O.attribute_statistic(attr, g, stat), rtol=1e-9, atol=1e-12, err_msg=stat)
+
+
+def test_mask_and_buffer_vs_oracle(E):
+    x, y, z = make_cloud("negative", 60000, 8)
+    mx, my, mz = make_cloud("negative", 300, 9)
+    vs, origin = 0.4, [0.1, 0.2, 0.3]
+    vx, vy, vz = O.voxelize(x, y, z, origin, vs)
+    mv = O.voxelize(mx, my, mz, origin, vs)
+    mask = E.VoxelMask(*mv, vs, origin)
+    ref = O.mask_membership(vx, vy, vz, *mv)
+    np.testing.assert_array_equal(_np(mask.contains_points(x, y, z)).astype(bool), ref)
+    np.testing.assert_array_equal(_np(mask.contains_voxels(vx, vy, vz)).astype(bool), ref)
+    for b in (1, 2):
+        want = O.voxel_buffer(*mv, buffer_size=b)
+        uniq = E.unique_voxels_first_occurrence(*mv)
+        exp = E.buffer_expand(uniq[0], uniq[1], uniq[2], b)
+        got = E.unique_voxels_first_occurrence(exp[0], exp[1], exp[2])
+        np.testing.assert_array_equal(np.stack([_np(t) for t in got], axis=1), want)  # same rows, same order
+        bm = E.VoxelMask(want[:, 0], want[:, 1], want[:, 2], vs, origin)
+        np.testing.assert_array_equal(_np(bm.contains_points(x, y, z)).astype(bool),
+                                      O.mask_membership(vx, vy, vz, want[:, 0], want[:, 1], want[:, 2]))
+    empty = E.VoxelMask(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), vs, origin)
+    assert not _np(empty.contains_points(x, y, z)).any()
+
+
+def test_two_epoch_join_and_mahalanobis_vs_oracle(E):
+    x1, y1, z1 = make_cloud("clustered", 60000, 10)
+    rng = np.random.default_rng(11)
+    keep = rng.random(len(x1)) < 0.85
+    x2, y2, z2 = x1[keep] + rng.normal(0, 0.01, keep.sum()), y1[keep] + 0.02, z1[keep] + rng.normal(0, 0.01, keep.sum())
+    ex, ey, ez = make_cloud("uniform", 3000, 12)
+    x2, y2, z2 = np.concatenate([x2, ex + 41]), np.concatenate([y2, ey]), np.concatenate([z2, ez])
+    vs = 0.5
+    c1 = E.VoxelCloud.build(x1, y1, z1, vs, [0, 0, 0])
+    c2 = E.VoxelCloud.build(x2, y2, z2, vs, [0, 0, 0])
+    g1 = O.group_by_voxel(*O.voxelize(x1, y1, z1, [0, 0, 0], vs))
+    g2 = O.group_by_voxel(*O.voxelize(x2, y2, z2, [0, 0, 0], vs))
+    i1, i2, only1, only2 = E.join_voxel_tables(c1.voxel_coords(), c2.voxel_coords())
+    r1, r2, ro1, ro2 = O.join_epochs(np.stack([g1.vx, g1.vy, g1.vz], 1), np.stack([g2.vx, g2.vy, g2.vz], 1))
+    np.testing.assert_array_equal(_np(i1), r1)
+    np.testing.assert_array_equal(_np(i2), r2)
+    np.testing.assert_array_equal(_np(only1), ro1)
+    np.testing.assert_array_equal(_np(only2), ro2)
+    s1, s2 = c1.stats(cog=True, cov=True), c2.stats(cog=True, cov=True)
+    for alpha in (0.005, 0.999):
+        res = E.mahalanobis(s1.cog, s1.cov, s2.cog, s2.cov, i1, i2, alpha=alpha)
+        cog1, cog2 = O.center_of_gravity(x1, y1, z1, g1)[r1], O.center_of_gravity(x2, y2, z2, g2)[r2]
+        cv1 = O.cov6_to_cov9(O.covariance_exact(x1, y1, z1, g1))[r1]
+        cv2 = O.cov6_to_cov9(O.covariance_exact(x2, y2, z2, g2))[r2]
+        ref = O.mahalanobis_change(cog1, cv1, cog2, cv2, alpha=alpha)
+        P.assert_close_rel(_np(res["distance"]), O.euclidean_distance(cog1, cog2), rtol=1e-9, atol=1e-13, what="distance")
+        eye = np.eye(3) * 1e-10
+        c_d1 = P.assert_mahalanobis(_np(res["d1"]), ref["d1"], cv2.reshape(-1, 3, 3) + eye, cov_rel=1e-9, what="d1")
+        c_d2 = P.assert_mahalanobis(_np(res["d2"]), ref["d2"], cv1.reshape(-1, 3, 3) + eye, cov_rel=1e-9, what="d2")
+        cond = np.full(len(r1), np.inf)
+        cond[~np.isnan(ref["d1"])] = c_d1
+        cond2 = np.full(len(r1), np.inf)
+        cond2[~np.isnan(ref["d2"])] = c_d2
+        well = (cond < 1e2) & (cond2 < 1e2)  # well-conditioned voxels: plain 1e-9-level agreement
+        p, pr = _np(res["p_value"]), ref["p_value"]
+        assert np.all(np.isnan(p) == np.isnan(pr))
+        assert np.all(np.abs(p[well] - pr[well]) <= 1e-15 + 1e-7 * np.abs(pr[well]))
+        stable = well & (np.abs(pr - alpha) > 1e-6)
+        np.testing.assert_array_equal(_np(res["significance"])[stable], ref["significance"][stable])
+        np.testing.assert_array_equal(_np(res["change_type"])[stable], ref["change_type"][stable])
+        nan_rows = np.isnan(pr)
+        assert np.all(_np(res["change_type"])[nan_rows] == 0)
+
+
+def test_reproducible_bitwise(E):
+    """No atomics in the reductions: two runs give bit-identical tables."""
+    x, y, z = make_cloud("clustered", 150000, 13)
+    a = E.VoxelCloud.build(x, y, z, 0.25, [0, 0, 0])
+    b = E.VoxelCloud.build(x, y, z, 0.25, [0, 0, 0])
+    for name in ("mean3", "m2", "count", "first_idx", "point2voxel", "idx_sorted"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+@pytest.mark.parametrize("n", [3_000_000])
+def test_properties_at_scale(E, n):
+    """Size-independent properties on a cloud too big for the per-voxel Python oracle."""
+    rng = np.random.default_rng(21)
+    x = rng.integers(0, 500000, n) * 1e-4
+    y = rng.integers(0, 500000, n) * 1e-4
+    z = rng.integers(0, 40000, n) * 1e-4
+    vs = 0.1
+    cloud = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+    ks = _np(cloud.keys_sorted).view(np.uint32 if cloud.grid.key_bytes == 4 else np.uint64)
+    assert np.all(ks[1:] >= ks[:-1]), "sortedness"
+    idx = _u32(cloud.idx_sorted)
+    assert np.array_equal(np.sort(idx), np.arange(n)), "permutation"
+    count = _u32(cloud.count)
+    assert count.sum() == n, "checksum of counts"
+    vx, vy, vz = O.voxelize(x, y, z, [0, 0, 0], vs)
+    packed = (vx * 1_000_000 + vy) * 1_000 + vz
+    uniq, inv, cnt = np.unique(packed, return_inverse=True, return_counts=True)
+    assert cloud.nvoxels == len(uniq)
+    np.testing.assert_array_equal(count, cnt)
+    np.testing.assert_array_equal(_u32(cloud.point2voxel), inv)
+    st = cloud.stats(cog=True, cov=True, eig=True)
+    cog = _np(st.cog).T
+    for k, c in enumerate((x, y, z)):  # centroid * count == sum (linearity)
+        s = np.bincount(inv, weights=c, minlength=len(uniq))
+        np.testing.assert_allclose(cog[:, k] * cnt, s, rtol=1e-12)
+    eig, cov = _np(st.eig), _np(st.cov)
+    ok = cnt > 1
+    np.testing.assert_allclose(eig[:, ok].sum(0), cov[0, ok] + cov[3, ok] + cov[5, ok], rtol=1e-9, atol=1e-15)  # trace
+    assert np.all(eig[0, ok] >= eig[1, ok]) and np.all(eig[1, ok] >= eig[2, ok]) and np.all(eig[2, ok] >= 0)

@@ -1,0 +1,160 @@
+"""`BiTemporalVapc` — drop-in for the reference's two-epoch change detection
+(src/vapc/bi_vapc.py:11-207) on top of the B200 engine.
+
+The voxel join (inner join + both anti-joins) and the centroid-delta / Mahalanobis / chi-square
+classification run on the GPU (vapc_join_sorted_keys, vapc_mahalanobis); the merged frame keeps
+the reference's column names (`*_x` = epoch 1, `*_y` = epoch 2, `distance`,
+`mahalanobi_significance`, `p_value`, `change_type`).  Additionally `d1` / `d2` (the two Mahalanobis
+distances, internal temporaries in the reference) are kept in `self.mahalanobis_d`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import engine as E
+from .utilities import timeit, trace
+
+_COV6 = ["cov_xx", "cov_xy", "cov_xz", "cov_yy", "cov_yz", "cov_zz"]
+
+
+class BiTemporalVapc:
+    def __init__(self, vapcs: list):
+        if len(vapcs) != 2:
+            raise ValueError("BiTemporalVapc requires exactly two dataframes.")
+        self.vapcs = vapcs
+        self.merged_df = None
+        self.final_df = None
+        self.distance_computed = False
+        self.mahalanobis_computed = False
+        self.prepared_for_bi_temporal_analysis = False
+        self.single_occupation_computed = False
+        self.mahalanobis_d = None
+        self._only = None
+
+    @trace
+    @timeit
+    def compute_voxels_occupied_in_single_epoch(self):
+        """Voxels only in epoch 1 -> change_type 3, only in epoch 2 -> 4 (bi_vapc.py:25-36)."""
+        if self.prepared_for_bi_temporal_analysis is False:
+            raise ValueError("Data should be prepared for bi_temporal analysis using 'prepare_data_for_mahalanobis_distance()'")
+        if self._only is None:
+            self._join()
+        only1, only2 = self._only
+        a = self.vapcs[0].df.iloc[only1].copy()
+        b = self.vapcs[1].df.iloc[only2].copy()
+        a["change_type"] = 3  # disappearing
+        b["change_type"] = 4  # appearing
+        self.df_appear_disappear = pd.concat([a, b])
+        self.single_occupation_computed = True
+
+    @trace
+    @timeit
+    def prepare_data_for_mahalanobis_distance(self):
+        """Per epoch: centroid + covariance, reduced to one centroid row per voxel (bi_vapc.py:40-47)."""
+        for vapc in self.vapcs:
+            vapc.return_at = "center_of_gravity"
+            vapc.compute_center_of_gravity()
+            vapc.compute_covariance_matrix()
+            vapc.reduce_to_voxels()
+        self.prepared_for_bi_temporal_analysis = True
+
+    def _join(self):
+        for vapc in self.vapcs:
+            vapc.voxelize()
+            vapc.compute_voxel_index()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tabs = []
+        for vapc in self.vapcs:
+            tabs.append([torch.from_numpy(vapc.df[c].to_numpy(np.int64)).to(dev) for c in ("voxel_x", "voxel_y", "voxel_z")])
+        i1, i2, only1, only2 = E.join_voxel_tables(tabs[0], tabs[1])
+        self._pairs = (i1.cpu().numpy(), i2.cpu().numpy())
+        self._only = (only1.cpu().numpy(), only2.cpu().numpy())
+
+    @trace
+    @timeit
+    def merge_vapcs_with_same_voxel_index(self):
+        """Inner join of the two voxel tables on the voxel triple, suffixes _x / _y, epoch-1 row order
+        (bi_vapc.py:78-84)."""
+        self._join()
+        i1, i2 = self._pairs
+        df1, df2 = self.vapcs[0].df, self.vapcs[1].df
+        left = df1.iloc[i1].add_suffix("_x")
+        right = df2.iloc[i2].add_suffix("_y")
+        right.index = left.index
+        self.merged_df = pd.concat([left, right], axis=1)
+
+    def merge_vapcs_with_closest_point(self):
+        """Mutual-nearest-neighbour pairing (bi_vapc.py:51-74) — KD-tree based, outside the voxel-join path
+        this package rebuilds."""
+        raise NotImplementedError("merge_vapcs_with_closest_point is outside the path rebuilt by vapc_b200")
+
+    def _device_tables(self):
+        df = self.merged_df
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def tab(cols):
+            return torch.from_numpy(np.ascontiguousarray(df[cols].to_numpy(np.float64).T)).to(dev)
+
+        cog1 = tab(["cog_x_x", "cog_y_x", "cog_z_x"])
+        cog2 = tab(["cog_x_y", "cog_y_y", "cog_z_y"])
+        cov_cols_x = sorted(c for c in df.columns if c.startswith("cov_") and c.endswith("_x"))
+        cov_cols_y = sorted(c for c in df.columns if c.startswith("cov_") and c.endswith("_y"))
+        has_cov = len(cov_cols_x) == 9 and len(cov_cols_y) == 9
+        cov1 = tab([c + "_x" for c in _COV6]) if has_cov else None
+        cov2 = tab([c + "_y" for c in _COV6]) if has_cov else None
+        rows = torch.arange(len(df), dtype=torch.int64, device=dev)
+        return cog1, cov1, cog2, cov2, rows, has_cov
+
+    def compute_distance(self):
+        """Euclidean distance of the joined centroids (bi_vapc.py:86-88, 198-207)."""
+        cog1, cov1, cog2, cov2, rows, has_cov = self._device_tables()
+        zeros = torch.zeros((6, len(self.merged_df)), dtype=torch.float64, device=cog1.device)
+        res = E.mahalanobis(cog1, cov1 if has_cov else zeros, cog2, cov2 if has_cov else zeros, rows, rows)
+        self.merged_df["distance"] = res["distance"].cpu().numpy()
+        self.distance_computed = True
+
+    @trace
+    @timeit
+    def compute_mahalanobis_distance(self, alpha: float = 0.005):
+        """Mahalanobis test of the centroid shift against either epoch's covariance (+1e-10 I), p = 1 - chi2
+        cdf (3 dof), significance, change_type 0 / 1 / 2 (bi_vapc.py:92-138)."""
+        if self.merged_df is None:
+            raise ValueError("Run compute_nearest_neighbors() before computing Mahalanobis test.")
+        cog1, cov1, cog2, cov2, rows, has_cov = self._device_tables()
+        if not has_cov:
+            raise ValueError("Incomplete covariance matrix columns.")
+        res = E.mahalanobis(cog1, cov1, cog2, cov2, rows, rows, alpha=alpha)
+        df = self.merged_df
+        df["mahalanobi_significance"] = res["significance"].cpu().numpy().astype(np.int64)
+        df["p_value"] = res["p_value"].cpu().numpy()
+        df["change_type"] = res["change_type"].cpu().numpy().astype(np.int64)
+        self.mahalanobis_d = (res["d1"].cpu().numpy(), res["d2"].cpu().numpy())
+        self.merged_df = df
+        self.mahalanobis_computed = True
+
+    @trace
+    @timeit
+    def prepare_data_for_export(self):
+        """X, Y, Z (= epoch-1 centroid) + computed columns, plus the appear / disappear rows (bi_vapc.py:142-161)."""
+        if self.merged_df is None:
+            raise ValueError("Run compute_mahalanobis_distance() before saving to LAS.")
+        cols = ["cog_x_x", "cog_y_x", "cog_z_x"]
+        if self.distance_computed:
+            cols.append("distance")
+        if self.mahalanobis_computed:
+            cols.extend(["mahalanobi_significance", "p_value", "change_type"])
+        self.df = self.merged_df[cols].rename(columns={"cog_x_x": "X", "cog_y_x": "Y", "cog_z_x": "Z"})
+        if self.single_occupation_computed is True:
+            self.df = pd.concat([self.df, self.df_appear_disappear[["X", "Y", "Z", "change_type"]]])
+
+    @trace
+    @timeit
+    def save_to_las(self, output_file: str):
+        """Save the exported frame to LAS through the DataHandler (bi_vapc.py:163-169)."""
+        from .datahandler import DataHandler
+
+        dh = DataHandler("")
+        dh.df = self.df
+        dh.save_as_las(output_file)

@@ -1,0 +1,101 @@
+// Shared device/host helpers for libvapc_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vapc_b200.h"
+
+// ---- error plumbing (thread-local message behind vapc_last_error) -----------------------
+int vapc_set_error(int code, const char* fmt, ...);
+int vapc_cuda_error(cudaError_t e, const char* file, int line);
+
+#define VAPC_RETURN_IF_CUDA(expr)                                        \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return vapc_cuda_error(_e, __FILE__, __LINE__); \
+  } while (0)
+#define VAPC_CHECK_LAUNCH() VAPC_RETURN_IF_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- packed-key layout, passed by value to kernels -------------------------------------
+struct Grid {
+  double ox, oy, oz, vs;
+  long long minx, miny, minz;
+  int bx, by, bz;
+};
+static inline Grid to_device_grid(const vapc_grid_t* g) {
+  Grid d;
+  d.ox = g->origin[0]; d.oy = g->origin[1]; d.oz = g->origin[2];
+  d.vs = g->voxel_size;
+  d.minx = g->vmin[0]; d.miny = g->vmin[1]; d.minz = g->vmin[2];
+  d.bx = g->bits[0]; d.by = g->bits[1]; d.bz = g->bits[2];
+  return d;
+}
+
+// v = floor((c - o) / vs): IEEE subtract, IEEE divide (no reciprocal, no FMA contraction),
+// floor, convert.  Bit-exact with numpy's np.floor((X - o) / vs).astype(int)  (vapc.py:199-201).
+__device__ __forceinline__ long long voxel_of(double c, double o, double vs) {
+  return __double2ll_rd(__ddiv_rn(__dsub_rn(c, o), vs));
+}
+
+__device__ __forceinline__ void unpack_key(unsigned long long key, const Grid& g, long long& vx,
+                                           long long& vy, long long& vz) {
+  const unsigned long long mz = g.bz >= 64 ? ~0ull : ((1ull << g.bz) - 1);
+  const unsigned long long my = g.by >= 64 ? ~0ull : ((1ull << g.by) - 1);
+  vz = (long long)(key & mz) + g.minz;
+  vy = (long long)((g.bz >= 64 ? 0ull : (key >> g.bz)) & my) + g.miny;
+  const int s = g.by + g.bz;
+  vx = (long long)(s >= 64 ? 0ull : (key >> s)) + g.minx;
+}
+
+// Shift point c(v) = origin + (v + 0.5) * vs used for the shifted moments.  It only has to be
+// the SAME value wherever a voxel's moments are formed or unshifted, so the operation order
+// is pinned with explicit round-to-nearest intrinsics (no contraction).
+__device__ __forceinline__ double shift_center(long long v, double o, double vs) {
+  return __dadd_rn(o, __dmul_rn(__dadd_rn((double)v, 0.5), vs));
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+
+// ---- block-wide exclusive scan of one unsigned per thread (blockDim.x multiple of 32, <= 1024)
+// smem33: 33 words of shared scratch.  Returns the exclusive prefix; *total = block sum (all
+// threads).  Ends with a barrier, so smem33 may be reused immediately.
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* smem33, unsigned* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem33[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    const unsigned w = lane < nw ? smem33[lane] : 0u;
+    unsigned winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem33[lane] = winc - w;  // exclusive prefix of the warp sums
+    if (lane == 31) smem33[32] = winc;
+  }
+  __syncthreads();
+  const unsigned res = inc - v + smem33[warp];
+  *total = smem33[32];
+  __syncthreads();
+  return res;
+}
+
+// ---- device-wide exclusive scan of uint32 (three launches; scan.cu) ---------------------
+size_t scan_u32_workspace_bytes(int64_t n);
+// out may alias in.  total (nullable, device uint64) receives the grand total.
+cudaError_t scan_u32_exclusive(const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* total,
+                               void* ws, cudaStream_t s);

@@ -1,0 +1,116 @@
+// Small fp64 3x3 helpers shared by device kernels and the host self-test entry points
+// (vapc_selftest_*_host): compiled for both sides so the arithmetic can be exercised without a GPU.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define VAPC_HD __host__ __device__ __forceinline__
+#else
+#define VAPC_HD inline
+#endif
+
+VAPC_HD double vapc_rsqrt(double v) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(v);
+#else
+  return 1.0 / sqrt(v);
+#endif
+}
+
+// One Jacobi rotation annihilating a_pq of a symmetric 3x3 held in scalars.
+// (app, aqq, apq) is the 2x2 pivot block, (arp, arq) the remaining off-diagonal pair.
+VAPC_HD void jacobi_rotate(double& app, double& aqq, double& apq, double& arp, double& arq, int sweep) {
+  if (apq == 0.0) return;
+  const double g = 100.0 * fabs(apq);
+  if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+    apq = 0.0;
+    return;
+  }
+  const double h = aqq - app;
+  double t;
+  if (fabs(h) + g == fabs(h)) {
+    t = apq / h;
+  } else {
+    const double theta = 0.5 * h / apq;
+    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+    if (theta < 0.0) t = -t;
+  }
+  const double c = vapc_rsqrt(1.0 + t * t);
+  const double s = t * c;
+  const double tau = s / (1.0 + c);
+  const double hh = t * apq;
+  app -= hh;
+  aqq += hh;
+  apq = 0.0;
+  const double gp = arp, hq = arq;
+  arp = gp - s * (hq + gp * tau);
+  arq = hq + s * (gp - hq * tau);
+}
+
+// Eigenvalues of the symmetric matrix [[a00 a01 a02][a01 a11 a12][a02 a12 a22]], descending.
+VAPC_HD void eig3_sym(double a00, double a01, double a02, double a11, double a12, double a22, double& l1,
+                                         double& l2, double& l3) {
+  // scale to O(1) so that the convergence tests never meet denormals
+  const double scale = fmax(fmax(fabs(a00), fabs(a11)), fmax(fabs(a22), fmax(fabs(a01), fmax(fabs(a02), fabs(a12)))));
+  if (scale == 0.0) { l1 = l2 = l3 = 0.0; return; }
+  const double inv = 1.0 / scale;
+  a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    if (fabs(a01) + fabs(a02) + fabs(a12) == 0.0) break;
+    jacobi_rotate(a00, a11, a01, a02, a12, sweep);  // (p, q) = (0, 1), r = 2
+    jacobi_rotate(a00, a22, a02, a01, a12, sweep);  // (0, 2), r = 1
+    jacobi_rotate(a11, a22, a12, a01, a02, sweep);  // (1, 2), r = 0
+  }
+  double x = a00 * scale, y = a11 * scale, z = a22 * scale;
+  double t;
+  if (x < y) { t = x; x = y; y = t; }
+  if (y < z) { t = y; y = z; z = t; }
+  if (x < y) { t = x; x = y; y = t; }
+  l1 = x; l2 = y; l3 = z;
+}
+
+VAPC_HD double safe_log(double v) { return v > 0.0 ? log(v) : 0.0; }  // vapc.py:1104-1106
+
+
+// ---- Chan / Welford pairwise combination of (n, mean, M2) -----------------------------------------
+// m: mean of (p - c(voxel)); M: xx xy xz yy yz zz central second moments.
+VAPC_HD void chan_combine(double& na, double (&ma)[3], double (&Ma)[6], double nb, const double (&mb)[3], const double (&Mb)[6]) {
+  if (nb == 0.0) return;
+  if (na == 0.0) {
+    na = nb;
+    for (int k = 0; k < 3; ++k) ma[k] = mb[k];
+    for (int k = 0; k < 6; ++k) Ma[k] = Mb[k];
+    return;
+  }
+  const double n = na + nb;
+  const double f = nb / n, w = na * f;
+  const double dx = mb[0] - ma[0], dy = mb[1] - ma[1], dz = mb[2] - ma[2];
+  ma[0] = fma(dx, f, ma[0]); ma[1] = fma(dy, f, ma[1]); ma[2] = fma(dz, f, ma[2]);
+  Ma[0] += fma(dx * dx, w, Mb[0]); Ma[1] += fma(dx * dy, w, Mb[1]); Ma[2] += fma(dx * dz, w, Mb[2]);
+  Ma[3] += fma(dy * dy, w, Mb[3]); Ma[4] += fma(dy * dz, w, Mb[4]); Ma[5] += fma(dz * dz, w, Mb[5]);
+  na = n;
+}
+
+// ---- inverse of a symmetric 3x3 (adjugate / determinant) applied as a quadratic form ---------------
+// q = d' inv(C) d with C = [[c0 c1 c2][c1 c3 c4][c2 c4 c5]]  (np.linalg.inv + einsum, bi_vapc.py:112-117)
+VAPC_HD double quad_form_inv3(const double (&c)[6], double dx, double dy, double dz) {
+  const double a00 = c[3] * c[5] - c[4] * c[4];
+  const double a01 = c[2] * c[4] - c[1] * c[5];
+  const double a02 = c[1] * c[4] - c[2] * c[3];
+  const double a11 = c[0] * c[5] - c[2] * c[2];
+  const double a12 = c[1] * c[2] - c[0] * c[4];
+  const double a22 = c[0] * c[3] - c[1] * c[1];
+  const double det = c[0] * a00 + c[1] * a01 + c[2] * a02;
+  const double q = dx * (a00 * dx + a01 * dy + a02 * dz) + dy * (a01 * dx + a11 * dy + a12 * dz) + dz * (a02 * dx + a12 * dy + a22 * dz);
+  return q / det;
+}
+
+// p = 1 - chi2.cdf(d, df = 3) (bi_vapc.py:118-119) in closed form:
+//   cdf = erf(sqrt(d / 2)) - sqrt(2 d / pi) * exp(-d / 2)
+// formed as 1 - cdf on purpose: the reference's p is exactly 0 for d >~ 79 and that drives change_type 2.
+VAPC_HD double chi2_df3_one_minus_cdf(double d) {
+  if (d != d) return d;
+  if (d <= 0.0) return 1.0;
+  const double cdf = erf(sqrt(0.5 * d)) - sqrt(d * 0.63661977236758134308 /* 2/pi */) * exp(-0.5 * d);
+  return 1.0 - cdf;
+}

@@ -1,0 +1,355 @@
+// mode / mode_count of an integer attribute, mask membership by hashed key, voxel buffer expansion.
+// Reference: vapc.py:407-433 (mode, mode_count), :594-598 (MultiIndex.isin), :495-541 (voxel buffer).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+constexpr unsigned long long kEmpty = ~0ull;
+
+inline int grid_for(int64_t n, int per_thread = 4) {
+  int64_t b = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+// ---- composite (voxel row, attribute value) keys ----------------------------------------------------
+// astype(int) truncates toward zero (vapc.py:409, :423); negative or too-large values are flagged
+// (np.bincount raises on negatives).
+__global__ void __launch_bounds__(kThreads) mode_keys_kernel(const uint32_t* __restrict__ p2v, const double* __restrict__ attr, int64_t n,
+                                                             int attr_bits, unsigned long long* __restrict__ keys, int* __restrict__ status) {
+  int bad = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double a = attr[i];
+    const long long v = (long long)a;  // trunc toward zero
+    if (!(a == a) || v < 0) bad |= 2;
+    else if ((unsigned long long)v >> attr_bits) bad |= 4;
+    keys[i] = ((unsigned long long)p2v[i] << attr_bits) | ((unsigned long long)v & ((1ull << attr_bits) - 1ull));
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// One thread per voxel walks the voxel's (value-sorted) slice: runs of equal keys are the bincount.
+__global__ void __launch_bounds__(kThreads) mode_count_kernel(const unsigned long long* __restrict__ keys, int attr_bits,
+                                                              const uint32_t* __restrict__ start, int64_t nvox, double threshold,
+                                                              long long* __restrict__ mode, long long* __restrict__ mode_count) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const int64_t a = start[v], b = start[v + 1];
+  const double total = (double)(b - a);
+  const unsigned long long mask = (1ull << attr_bits) - 1ull;
+  long long best_val = 0, best_cnt = 0, above = 0;
+  int64_t p = a;
+  while (p < b) {
+    const unsigned long long k = keys[p];
+    int64_t q = p + 1;
+    while (q < b && keys[q] == k) ++q;
+    const long long cnt = (long long)(q - p);
+    if (cnt > best_cnt) { best_cnt = cnt; best_val = (long long)(k & mask); }  // first maximum = smallest value (np.argmax)
+    if ((double)cnt / total >= threshold) ++above;                              // counts / counts_sum >= percentage
+    p = q;
+  }
+  if (mode) mode[v] = best_val;
+  if (mode_count) mode_count[v] = above;
+}
+
+// ---- per-voxel statistics of an fp64 attribute (vapc.py:393-406) -----------------------------------------
+// One thread per voxel walks the voxel's points in original order (order = idx_sorted).  mean / sum as a
+// running fp64 sum, var / std two-pass about the mean with ddof = 0 (numpy's .var() / .std()).
+__global__ void __launch_bounds__(kThreads) attr_stats_kernel(const double* __restrict__ attr, const uint32_t* __restrict__ order,
+                                                              const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ sum,
+                                                              double* __restrict__ mean, double* __restrict__ vmin, double* __restrict__ vmax,
+                                                              double* __restrict__ var) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const int64_t a = start[v], b = start[v + 1];
+  double s = 0.0, lo = INFINITY, hi = -INFINITY;
+  bool any_nan = false;
+  for (int64_t p = a; p < b; ++p) {
+    const double x = __ldg(attr + order[p]);
+    s += x;
+    any_nan |= (x != x);
+    lo = fmin(lo, x);
+    hi = fmax(hi, x);
+  }
+  const double n = (double)(b - a);
+  const double m = s / n;
+  if (any_nan) lo = hi = s;  // numpy min / max propagate NaN
+  if (sum) sum[v] = s;
+  if (mean) mean[v] = m;
+  if (vmin) vmin[v] = lo;
+  if (vmax) vmax[v] = hi;
+  if (var) {
+    double q = 0.0;
+    for (int64_t p = a; p < b; ++p) {
+      const double d = __ldg(attr + order[p]) - m;
+      q = fma(d, d, q);
+    }
+    var[v] = q / n;
+  }
+}
+
+// order-preserving map fp64 -> uint64 (for radix sorting by value); NaN sorts last like numpy
+__global__ void __launch_bounds__(kThreads) f64_sort_keys_kernel(const double* __restrict__ attr, int64_t n,
+                                                                 unsigned long long* __restrict__ keys) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double x = attr[i];
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    if (x != x) u = ~0ull;
+    else u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    keys[i] = u;
+  }
+}
+
+// median per voxel; order = points sorted by (voxel row, value)
+__global__ void __launch_bounds__(kThreads) attr_median_kernel(const double* __restrict__ attr, const uint32_t* __restrict__ order,
+                                                               const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ median) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const int64_t a = start[v], b = start[v + 1], n = b - a;
+  const double hi = attr[order[a + n / 2]];
+  if (n & 1) {
+    median[v] = hi;
+  } else {
+    const double lo = attr[order[a + n / 2 - 1]];
+    median[v] = (lo + hi) / 2.0;  // np.median: mean of the two middle values
+  }
+  const double last = attr[order[b - 1]];
+  if (last != last) median[v] = last;  // numpy: NaN anywhere -> NaN
+}
+
+// ---- generic packing of int64 voxel triples --------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pack_triples_kernel(const long long* __restrict__ vx, const long long* __restrict__ vy,
+                                                                const long long* __restrict__ vz, int64_t n, Grid g,
+                                                                unsigned long long* __restrict__ keys, int* __restrict__ status) {
+  int bad = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long rx = (unsigned long long)(vx[i] - g.minx), ry = (unsigned long long)(vy[i] - g.miny),
+                             rz = (unsigned long long)(vz[i] - g.minz);
+    const bool out = (g.bx < 64 && (rx >> g.bx)) || (g.by < 64 && (ry >> g.by)) || (g.bz < 64 && (rz >> g.bz));
+    bad |= out ? 1 : 0;
+    unsigned long long k = rz;
+    if (g.bz < 64) k |= ry << g.bz;
+    if (g.by + g.bz < 64) k |= rx << (g.by + g.bz);
+    keys[i] = out ? kEmpty : k;
+  }
+  if (bad) atomicOr(status, 1);
+}
+
+// ---- open-addressing hash set of packed keys -----------------------------------------------------------
+__device__ __forceinline__ unsigned long long hash_slot(unsigned long long k, int log2cap) {
+  return (k * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+__global__ void __launch_bounds__(kThreads) mask_build_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                              unsigned long long* __restrict__ table, int log2cap) {
+  const unsigned long long cap_mask = (1ull << log2cap) - 1ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long k = keys[i];
+    if (k == kEmpty) continue;
+    unsigned long long s = hash_slot(k, log2cap);
+    while (true) {
+      const unsigned long long old = atomicCAS(table + s, kEmpty, k);
+      if (old == kEmpty || old == k) break;
+      s = (s + 1) & cap_mask;
+    }
+  }
+}
+__device__ __forceinline__ bool mask_contains(const unsigned long long* __restrict__ table, int log2cap, unsigned long long k) {
+  const unsigned long long cap_mask = (1ull << log2cap) - 1ull;
+  unsigned long long s = hash_slot(k, log2cap);
+  while (true) {
+    const unsigned long long t = __ldg(table + s);
+    if (t == k) return true;
+    if (t == kEmpty) return false;
+    s = (s + 1) & cap_mask;
+  }
+}
+// membership of every POINT's voxel: fused voxelise (vapc.py:199-201) + pack in the mask's grid + probe
+__global__ void __launch_bounds__(kThreads) mask_lookup_points_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                      const double* __restrict__ z, int64_t n, Grid g,
+                                                                      const unsigned long long* __restrict__ table, int log2cap,
+                                                                      unsigned char* __restrict__ member) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long rx = (unsigned long long)(voxel_of(x[i], g.ox, g.vs) - g.minx);
+    const unsigned long long ry = (unsigned long long)(voxel_of(y[i], g.oy, g.vs) - g.miny);
+    const unsigned long long rz = (unsigned long long)(voxel_of(z[i], g.oz, g.vs) - g.minz);
+    const bool out = (g.bx < 64 && (rx >> g.bx)) || (g.by < 64 && (ry >> g.by)) || (g.bz < 64 && (rz >> g.bz));
+    unsigned long long k = rz;
+    if (g.bz < 64) k |= ry << g.bz;
+    if (g.by + g.bz < 64) k |= rx << (g.by + g.bz);
+    member[i] = (!out && mask_contains(table, log2cap, k)) ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(kThreads) mask_lookup_keys_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                    const unsigned long long* __restrict__ table, int log2cap,
+                                                                    unsigned char* __restrict__ member) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long k = keys[i];
+    member[i] = (k != kEmpty && mask_contains(table, log2cap, k)) ? 1 : 0;
+  }
+}
+
+// ---- voxel buffer: every triple + all (2b+1)^3 offsets, voxel-major, offsets in 'ij' meshgrid order ---
+__global__ void __launch_bounds__(kThreads) buffer_expand_kernel(const long long* __restrict__ vx, const long long* __restrict__ vy,
+                                                                 const long long* __restrict__ vz, int64_t n, int b,
+                                                                 long long* __restrict__ out) {
+  const int w = 2 * b + 1;
+  const int64_t per = (int64_t)w * w * w, total = n * per;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t v = i / per;
+    const int o = (int)(i - v * per);
+    const int dz = o % w - b, dy = (o / w) % w - b, dx = o / (w * w) - b;
+    out[i] = vx[v] + dx;
+    out[total + i] = vy[v] + dy;
+    out[2 * total + i] = vz[v] + dz;
+  }
+}
+
+inline int ilog2_ceil(int64_t v) {
+  int b = 0;
+  while (((int64_t)1 << b) < v) ++b;
+  return b;
+}
+}  // namespace
+
+extern "C" int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, int64_t n, int32_t attr_bits, uint64_t* keys,
+                              int32_t* status, void* stream) {
+  if (n < 0 || attr_bits < 1 || attr_bits > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_keys: bad arguments (attr_bits in 1..32)");
+  if (n == 0) return VAPC_OK;
+  mode_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(point2voxel, attr, n, attr_bits,
+                                                                    reinterpret_cast<unsigned long long*>(keys), status);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t attr_bits, const uint32_t* start, int64_t nvoxels,
+                               double threshold, int64_t* mode, int64_t* mode_count, void* stream) {
+  if (n < 0 || nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  mode_count_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(keys_sorted), attr_bits, start, nvoxels, threshold,
+      reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_attr_stats(const double* attr, const uint32_t* order, const uint32_t* start, int64_t nvoxels, double* sum,
+                               double* mean, double* vmin, double* vmax, double* var, void* stream) {
+  if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_attr_stats: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  attr_stats_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(attr, order, start, nvoxels, sum, mean,
+                                                                                                       vmin, vmax, var);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+extern "C" int vapc_f64_sort_keys(const double* attr, int64_t n, uint64_t* keys, void* stream) {
+  if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_f64_sort_keys: n < 0");
+  if (n == 0) return VAPC_OK;
+  f64_sort_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(attr, n, reinterpret_cast<unsigned long long*>(keys));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+extern "C" int vapc_attr_median(const double* attr, const uint32_t* order, const uint32_t* start, int64_t nvoxels, double* median,
+                                void* stream) {
+  if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_attr_median: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  attr_median_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(attr, order, start, nvoxels, median);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_pack_triples_i64(const int64_t* vx, const int64_t* vy, const int64_t* vz, int64_t n, const vapc_grid_t* grid_host,
+                                     uint64_t* keys, int32_t* status, void* stream) {
+  if (!grid_host || n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_triples_i64: bad arguments");
+  if (grid_host->bits[0] + grid_host->bits[1] + grid_host->bits[2] > 63)
+    return vapc_set_error(VAPC_E_KEYSPACE, "vapc_pack_triples_i64: needs at most 63 key bits");
+  if (n == 0) return VAPC_OK;
+  pack_triples_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(vx),
+      reinterpret_cast<const long long*>(vy), reinterpret_cast<const long long*>(vz), n, to_device_grid(grid_host),
+      reinterpret_cast<unsigned long long*>(keys), status);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" size_t vapc_mask_table_bytes(int64_t nmask, int64_t* capacity_host) {
+  const int lg = ilog2_ceil((nmask < 1 ? 1 : nmask) * 2);
+  const int64_t cap = (int64_t)1 << (lg < 4 ? 4 : lg);
+  if (capacity_host) *capacity_host = cap;
+  return (size_t)cap * sizeof(uint64_t);
+}
+
+extern "C" int vapc_mask_build(const uint64_t* mask_keys, int64_t nmask, void* table, int64_t capacity, void* stream) {
+  if (nmask < 0 || capacity < 16 || (capacity & (capacity - 1)) || capacity < 2 * nmask || !table)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_mask_build: capacity must be a power of two >= max(16, 2 * nmask)");
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(table, 0xff, (size_t)capacity * sizeof(uint64_t), as_stream(stream)));
+  if (nmask == 0) return VAPC_OK;
+  mask_build_kernel<<<grid_for(nmask, 1), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(mask_keys), nmask,
+                                                                            static_cast<unsigned long long*>(table), ilog2_ceil(capacity));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_mask_lookup_points(const double* x, const double* y, const double* z, int64_t n, const vapc_grid_t* grid_host,
+                                       const void* table, int64_t capacity, uint8_t* member, void* stream) {
+  if (!grid_host || n < 0 || capacity < 16 || (capacity & (capacity - 1))) return vapc_set_error(VAPC_E_INVALID, "vapc_mask_lookup_points: bad arguments");
+  if (n == 0) return VAPC_OK;
+  mask_lookup_points_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(x, y, z, n, to_device_grid(grid_host),
+      static_cast<const unsigned long long*>(table), ilog2_ceil(capacity), member);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_mask_lookup_keys(const uint64_t* keys, int64_t n, const void* table, int64_t capacity, uint8_t* member, void* stream) {
+  if (n < 0 || capacity < 16 || (capacity & (capacity - 1))) return vapc_set_error(VAPC_E_INVALID, "vapc_mask_lookup_keys: bad arguments");
+  if (n == 0) return VAPC_OK;
+  mask_lookup_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(keys), n,
+      static_cast<const unsigned long long*>(table), ilog2_ceil(capacity), member);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_buffer_expand(const int64_t* vx, const int64_t* vy, const int64_t* vz, int64_t n, int32_t buffer_size, int64_t* out3,
+                                  void* stream) {
+  if (n < 0 || buffer_size < 0 || buffer_size > 64) return vapc_set_error(VAPC_E_INVALID, "vapc_buffer_expand: bad arguments");
+  if (n == 0) return VAPC_OK;
+  const int w = 2 * buffer_size + 1;
+  buffer_expand_kernel<<<grid_for(n * w * w * w), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(vx),
+      reinterpret_cast<const long long*>(vy), reinterpret_cast<const long long*>(vz), n, buffer_size, reinterpret_cast<long long*>(out3));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+// histogram of the top hist_bits of the keys (multi-GPU splitter selection)
+namespace {
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) key_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd(hist + (unsigned)((unsigned long long)keys[i] >> shift), 1u);
+}
+}  // namespace
+extern "C" int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes, int32_t total_bits, int32_t hist_bits, uint32_t* hist,
+                                  void* stream) {
+  if (n < 0 || hist_bits < 1 || hist_bits > 24 || total_bits < 0 || total_bits > 64)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_key_histogram: bad arguments");
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) << hist_bits, as_stream(stream)));
+  if (n == 0) return VAPC_OK;
+  const int shift = total_bits > hist_bits ? total_bits - hist_bits : 0;
+  if (key_bytes == 4)
+    key_hist_kernel<uint32_t><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(keys), n, shift, hist);
+  else if (key_bytes == 8)
+    key_hist_kernel<unsigned long long><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(static_cast<const unsigned long long*>(keys), n, shift, hist);
+  else
+    return vapc_set_error(VAPC_E_INVALID, "vapc_key_histogram: key_bytes must be 4 or 8");
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}

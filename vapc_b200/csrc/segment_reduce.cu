@@ -1,0 +1,555 @@
+// Run-length segmentation of the sorted keys + single-pass segmented reductions.
+//
+// A tile is kSegTile = 1024 consecutive sorted positions handled by one CTA of 256 threads
+// (4 positions per thread, blocked, so key / index loads are 16-byte vectors).  In a tile:
+//   1. head flags (key differs from its predecessor), block scan -> local segment ids;
+//   2. every position gathers its 32-byte xyzw record (one sector per point, all loads issued
+//      up front) into shared memory; point->voxel ids are scattered out;
+//   3. one thread per segment walks its points in shared memory IN SORTED ORDER — which is
+//      original point order, the sort being stable — accumulating n, SUM d, SUM d d' with
+//      d = (p - c) - (p_first - c), c = c(voxel), i.e. shifted by the segment's first point so that
+//      the final M2 = SUM dd' - SUM d SUM d'/n loses nothing to cancellation even for a tight
+//      cluster in a large voxel; the segment leaves as (n, mean of p - c, M2 about the mean).
+//      Segments that start in the tile are stored to the voxel row, the leading partial segment
+//      (a voxel continued from the previous tile) goes to a per-tile carry slot;
+//   4. a fix-up kernel folds each voxel's carry chain in with Chan's pairwise update, in tile order.
+// (n, mean - c, M2) triples combine exactly the same way across GPUs (vapc_merge_partials).
+// No atomics: results are bit-reproducible run to run.
+//
+// Algorithmic bytes per point (u32 keys): 4 key + 4 idx + 32 record + 4 point2voxel write(+28 of
+// sector write-allocate on the scatter) ; per voxel: 8 key... see DESIGN.md.
+#include <math.h>
+
+#include "common.cuh"
+#include "math3.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+constexpr int kItems = 4;
+constexpr int kSegTile = kThreads * kItems;  // 1024
+
+struct SegWs {  // layout of the segmentation workspace
+  uint32_t* tile_heads;       // [ntiles]   heads per tile, then (in place) exclusive scan = first voxel row of the tile
+  unsigned long long* total;  // [1]        number of voxels
+  void* scan_ws;              // scan scratch
+  uint32_t* carry_cnt;        // [ntiles]   points in the leading partial segment (0 = none)
+  double* carry;              // [ntiles][10] its partial moments (or other per-op payload)
+};
+inline int64_t seg_tiles(int64_t n) { return (n + kSegTile - 1) / kSegTile; }
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline size_t seg_ws_bytes(int64_t n) {
+  const int64_t nt = seg_tiles(n < 1 ? 1 : n);
+  return align_up(nt * 4) + align_up(8) + align_up(scan_u32_workspace_bytes(nt)) + align_up(nt * 4) + align_up(nt * 10 * 8);
+}
+inline SegWs carve(void* ws, int64_t n) {
+  const int64_t nt = seg_tiles(n < 1 ? 1 : n);
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  SegWs w;
+  w.tile_heads = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
+  w.total = reinterpret_cast<unsigned long long*>(p); p += align_up(8);
+  w.scan_ws = p; p += align_up(scan_u32_workspace_bytes(nt));
+  w.carry_cnt = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
+  w.carry = reinterpret_cast<double*>(p);
+  return w;
+}
+
+// ---- load one tile's keys (blocked, 4 per thread) + the predecessor of the first ---------------
+template <typename KeyT>
+__device__ __forceinline__ void load_tile_keys(const KeyT* __restrict__ keys, int64_t n, int64_t base, KeyT (&key)[kItems],
+                                               KeyT& prev, bool (&valid)[kItems]) {
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+  if (p0 + kItems <= n) {
+    if (sizeof(KeyT) == 4) {
+      const uint4 v = *reinterpret_cast<const uint4*>(keys + p0);
+      key[0] = (KeyT)v.x; key[1] = (KeyT)v.y; key[2] = (KeyT)v.z; key[3] = (KeyT)v.w;
+    } else {
+      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys + p0);
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(keys + p0 + 2);
+      key[0] = (KeyT)a.x; key[1] = (KeyT)a.y; key[2] = (KeyT)b.x; key[3] = (KeyT)b.y;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) valid[j] = true;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      valid[j] = p0 + j < n;
+      key[j] = valid[j] ? keys[p0 + j] : (KeyT)0;
+    }
+  }
+  // predecessor of this thread's first position: previous thread's last key (via shuffle /
+  // shared memory would need a barrier; a global re-read of one L1-resident word is simpler)
+  prev = (p0 > 0 && p0 <= n) ? keys[p0 - 1] : (KeyT)0;
+}
+
+template <typename KeyT>
+__device__ __forceinline__ unsigned head_flags(const KeyT (&key)[kItems], KeyT prev, const bool (&valid)[kItems], int64_t p0,
+                                               bool (&head)[kItems]) {
+  unsigned cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const KeyT before = j == 0 ? prev : key[j - 1];
+    head[j] = valid[j] && ((p0 + j) == 0 || key[j] != before);
+    cnt += head[j] ? 1u : 0u;
+  }
+  return cnt;
+}
+
+// ---- step 1: heads per tile ---------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) count_heads_kernel(const KeyT* __restrict__ keys, int64_t n,
+                                                               uint32_t* __restrict__ tile_heads) {
+  __shared__ unsigned warp_cnt[kThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kSegTile;
+  KeyT key[kItems], prev;
+  bool valid[kItems], head[kItems];
+  load_tile_keys(keys, n, base, key, prev, valid);
+  unsigned c = head_flags(key, prev, valid, base + (int64_t)threadIdx.x * kItems, head);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += warp_cnt[w];
+    tile_heads[blockIdx.x] = t;
+  }
+}
+
+// ---- shared tile state ----------------------------------------------------------------------------
+template <typename KeyT>
+struct TileSmem {
+  unsigned scan_s[33];
+  unsigned short seg_start[kSegTile + 2];  // [s] first tile position of local segment s; [nheads+1] = tile_n
+  KeyT seg_key[kSegTile + 1];              // key of local segment s (s = 0: the continued voxel)
+  double x[kSegTile], y[kSegTile], z[kSegTile];
+};
+
+// Common prologue: flags, scan, segment tables, voxel-table bookkeeping.
+// On return inc[j] = number of heads at tile positions <= this one (local segment id; 0 = continuation).
+template <typename KeyT>
+__device__ __forceinline__ void tile_prologue(TileSmem<KeyT>& sm, const KeyT* __restrict__ keys, int64_t n, int64_t base,
+                                              KeyT (&key)[kItems], bool (&valid)[kItems], bool (&head)[kItems],
+                                              unsigned (&inc)[kItems], unsigned& nheads, int& tile_n) {
+  KeyT prev;
+  load_tile_keys(keys, n, base, key, prev, valid);
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+  const unsigned local = head_flags(key, prev, valid, p0, head);
+  const unsigned excl = block_exclusive_scan(local, sm.scan_s, &nheads);
+  unsigned run = excl;
+  tile_n = (int)min((int64_t)kSegTile, n - base);
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    run += head[j] ? 1u : 0u;
+    inc[j] = run;
+    if (head[j]) {
+      sm.seg_start[run] = (unsigned short)(threadIdx.x * kItems + j);
+      sm.seg_key[run] = key[j];
+    }
+  }
+  if (threadIdx.x == 0) {
+    sm.seg_start[0] = 0;
+    sm.seg_key[0] = key[0];  // position 0 belongs to segment 0 (continuation) or is head of segment 1
+    sm.seg_start[nheads + 1] = (unsigned short)tile_n;
+  }
+}
+
+// ---- step 2: moments ------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
+    const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
+    const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
+    uint32_t* __restrict__ count, uint32_t* __restrict__ first_idx, double* __restrict__ mean3, double* __restrict__ m2,
+    uint32_t* __restrict__ point2voxel, uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<KeyT>& sm = *reinterpret_cast<TileSmem<KeyT>*>(smem_raw);
+  const int64_t base = (int64_t)blockIdx.x * kSegTile;
+  KeyT key[kItems];
+  bool valid[kItems], head[kItems];
+  unsigned inc[kItems], nheads;
+  int tile_n;
+
+  // issue the index loads + gathers first so that they overlap the scan
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+  uint32_t idx[kItems];
+  if (p0 + kItems <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(idx_sorted + p0);
+    idx[0] = v.x; idx[1] = v.y; idx[2] = v.z; idx[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) idx[j] = (p0 + j < n) ? idx_sorted[p0 + j] : 0u;
+  }
+  double4 rec[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (p0 + j < n) {
+      const double2 lo = __ldg(reinterpret_cast<const double2*>(xyzw + idx[j]));
+      const double2 hi = __ldg(reinterpret_cast<const double2*>(xyzw + idx[j]) + 1);
+      rec[j] = make_double4(lo.x, lo.y, hi.x, 0.0);
+    } else {
+      rec[j] = make_double4(0, 0, 0, 0);
+    }
+  }
+
+  tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
+  const uint32_t first_row = tile_first[blockIdx.x];  // voxel row of the first head in this tile
+
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    sm.x[p] = rec[j].x; sm.y[p] = rec[j].y; sm.z[p] = rec[j].z;
+    if (valid[j]) {
+      const uint32_t row = first_row + inc[j] - 1u;  // inc == 0 -> first_row - 1: the continued voxel
+      if (point2voxel) point2voxel[idx[j]] = row;
+      if (head[j]) {
+        voxel_keys[row] = key[j];
+        start[row] = (uint32_t)(p0 + j);
+        first_idx[row] = idx[j];
+      }
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[nvox] = (uint32_t)n;
+  __syncthreads();
+
+  // one thread per local segment
+  for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
+    const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
+    if (b <= a) continue;  // only s == 0 can be empty (tile starts with a head)
+    long long vx, vy, vz;
+    unpack_key((unsigned long long)sm.seg_key[s], g, vx, vy, vz);
+    const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
+    const double q0x = sm.x[a] - cx, q0y = sm.y[a] - cy, q0z = sm.z[a] - cz;
+    double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+    for (int p = a + 1; p < b; ++p) {
+      const double dx = (sm.x[p] - cx) - q0x, dy = (sm.y[p] - cy) - q0y, dz = (sm.z[p] - cz) - q0z;
+      sx += dx; sy += dy; sz += dz;
+      xx = fma(dx, dx, xx); xy = fma(dx, dy, xy); xz = fma(dx, dz, xz);
+      yy = fma(dy, dy, yy); yz = fma(dy, dz, yz); zz = fma(dz, dz, zz);
+    }
+    const double inv = 1.0 / (double)(b - a);
+    const double mx = sx * inv, my = sy * inv, mz = sz * inv;  // mean of d
+    double out[9];
+    out[0] = q0x + mx; out[1] = q0y + my; out[2] = q0z + mz;
+    out[3] = fma(-sx, mx, xx); out[4] = fma(-sx, my, xy); out[5] = fma(-sx, mz, xz);
+    out[6] = fma(-sy, my, yy); out[7] = fma(-sy, mz, yz); out[8] = fma(-sz, mz, zz);
+    if (s >= 1) {
+      const int64_t row = (int64_t)first_row + s - 1;
+      count[row] = (uint32_t)(b - a);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = out[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = out[3 + k];
+    } else {
+      double* c = carry + (int64_t)blockIdx.x * 10;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] = out[k];
+      carry_cnt[blockIdx.x] = (uint32_t)(b - a);
+    }
+  }
+  // tiles that start with a head have no carry
+  if (threadIdx.x == 0 && sm.seg_start[1] == 0 && nheads > 0) carry_cnt[blockIdx.x] = 0;
+}
+
+// Fix-up: a voxel continued over tiles t, t+1, ... (carry_cnt > 0 and the same row) gets its carries
+// folded in, in tile order.  One warp per chain start; lane l folds tiles t+l, t+l+32, ... sequentially and
+// the 32 lane results are folded by lane 0 in lane order — a fixed association, so the result does not
+// depend on scheduling.
+__global__ void __launch_bounds__(kThreads) fixup_moments_kernel(const uint32_t* __restrict__ tile_first,
+                                                                 const uint32_t* __restrict__ carry_cnt, const double* __restrict__ carry,
+                                                                 int ntiles, int64_t nvox, uint32_t* __restrict__ count,
+                                                                 double* __restrict__ mean3, double* __restrict__ m2) {
+  const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= ntiles) return;
+  if (carry_cnt[t] == 0) return;
+  const uint32_t row = tile_first[t] - 1u;
+  if (t > 0 && carry_cnt[t - 1] != 0 && tile_first[t - 1] - 1u == row) return;  // not the chain start
+  double na = 0.0, ma[3] = {0, 0, 0}, Ma[6] = {0, 0, 0, 0, 0, 0};
+  for (int u0 = t; u0 < ntiles; u0 += 32) {
+    const int u = u0 + lane;
+    const bool mine = u < ntiles && carry_cnt[u] != 0 && tile_first[u] - 1u == row;
+    const unsigned ok = __ballot_sync(0xffffffffu, mine);
+    const unsigned run = (ok == 0xffffffffu) ? 32u : (unsigned)(__ffs(~ok) - 1);  // leading tiles of the chain
+    if ((unsigned)lane < run) {
+      const double* c = carry + (int64_t)u * 10;
+      const double mb[3] = {c[0], c[1], c[2]};
+      const double Mb[6] = {c[3], c[4], c[5], c[6], c[7], c[8]};
+      chan_combine(na, ma, Ma, (double)carry_cnt[u], mb, Mb);
+    }
+    if (run < 32u) break;
+  }
+  // lane 0 folds: head-tile partial, then lanes 0..31 in order
+  double nt = 0.0, mt[3] = {0, 0, 0}, Mt[6] = {0, 0, 0, 0, 0, 0};
+  if (lane == 0) {
+    nt = (double)count[row];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mt[k] = mean3[(int64_t)k * nvox + row];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Mt[k] = m2[(int64_t)k * nvox + row];
+  }
+  for (int l = 0; l < 32; ++l) {
+    const double nb = __shfl_sync(0xffffffffu, na, l);
+    double mb[3], Mb[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mb[k] = __shfl_sync(0xffffffffu, ma[k], l);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Mb[k] = __shfl_sync(0xffffffffu, Ma[k], l);
+    if (lane == 0) chan_combine(nt, mt, Mt, nb, mb, Mb);
+  }
+  if (lane == 0) {
+    count[row] = (uint32_t)nt;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = mt[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Mt[k];
+  }
+}
+
+// ---- closest to centroid ----------------------------------------------------------------------------
+// distance = sqrt((X-cog_x)^2 + (Y-cog_y)^2 + (Z-cog_z)^2), numpy evaluation order, no FMA.
+__device__ __forceinline__ double ref_distance(double px, double py, double pz, double cx, double cy, double cz) {
+  const double dx = __dsub_rn(px, cx), dy = __dsub_rn(py, cy), dz = __dsub_rn(pz, cz);
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx_sorted,
+                                                           int64_t n, const double4* __restrict__ xyzw, const double* __restrict__ cog3,
+                                                           const uint32_t* __restrict__ tile_first, int64_t nvox,
+                                                           double* __restrict__ min_dist, uint32_t* __restrict__ argmin_idx,
+                                                           uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<KeyT>& sm = *reinterpret_cast<TileSmem<KeyT>*>(smem_raw);
+  __shared__ uint32_t idx_s[kSegTile];
+  const int64_t base = (int64_t)blockIdx.x * kSegTile;
+  KeyT key[kItems];
+  bool valid[kItems], head[kItems];
+  unsigned inc[kItems], nheads;
+  int tile_n;
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    if (p0 + j < n) {
+      const uint32_t id = idx_sorted[p0 + j];
+      const double2 lo = __ldg(reinterpret_cast<const double2*>(xyzw + id));
+      const double2 hi = __ldg(reinterpret_cast<const double2*>(xyzw + id) + 1);
+      sm.x[p] = lo.x; sm.y[p] = lo.y; sm.z[p] = hi.x;
+      idx_s[p] = id;
+    }
+  }
+  tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
+  const uint32_t first_row = tile_first[blockIdx.x];
+  __syncthreads();
+  for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
+    const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
+    if (b <= a) continue;
+    const int64_t row = (int64_t)first_row + s - 1;  // s == 0: first_row - 1 (continued voxel)
+    const double cx = cog3[row], cy = cog3[nvox + row], cz = cog3[2 * nvox + row];
+    double best = INFINITY;
+    uint32_t best_i = 0xffffffffu;
+    for (int p = a; p < b; ++p) {
+      const double d = ref_distance(sm.x[p], sm.y[p], sm.z[p], cx, cy, cz);
+      if (d < best || best_i == 0xffffffffu) { best = d; best_i = idx_s[p]; }  // strict <: first (lowest index) wins ties
+    }
+    if (s >= 1) {
+      min_dist[row] = best;
+      argmin_idx[row] = best_i;
+    } else {
+      double* c = carry + (int64_t)blockIdx.x * 10;
+      c[0] = best;
+      c[1] = __longlong_as_double((long long)best_i);
+      carry_cnt[blockIdx.x] = (uint32_t)(b - a);
+    }
+  }
+  if (threadIdx.x == 0 && sm.seg_start[1] == 0 && nheads > 0) carry_cnt[blockIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) fixup_closest_kernel(const uint32_t* __restrict__ tile_first,
+                                                                 const uint32_t* __restrict__ carry_cnt, const double* __restrict__ carry,
+                                                                 int ntiles, double* __restrict__ min_dist, uint32_t* __restrict__ argmin_idx) {
+  const int t = (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= ntiles || carry_cnt[t] == 0) return;
+  const uint32_t row = tile_first[t] - 1u;
+  if (t > 0 && carry_cnt[t - 1] != 0 && tile_first[t - 1] - 1u == row) return;
+  double best = min_dist[row];
+  uint32_t best_i = argmin_idx[row];
+  for (int u = t; u < ntiles && carry_cnt[u] != 0 && tile_first[u] - 1u == row; ++u) {
+    const double d = carry[(int64_t)u * 10];
+    if (d < best) { best = d; best_i = (uint32_t)__double_as_longlong(carry[(int64_t)u * 10 + 1]); }
+  }
+  min_dist[row] = best;
+  argmin_idx[row] = best_i;
+}
+
+// ---- merge of partial voxel rows (multi-GPU) ----------------------------------------------------------
+// Rows with equal keys are adjacent (keys sorted, stable, so source-rank order is kept); order[p] is
+// the source row of sorted position p.  A key has at most one partial row per source rank, so the
+// thread at each run head simply walks its run in global memory (runs may cross tiles freely).
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) merge_partials_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ order,
+                                                                  int64_t n, const uint32_t* __restrict__ count_in,
+                                                                  const double* __restrict__ mean3_in, const double* __restrict__ m2_in,
+                                                                  int64_t in_stride, const uint32_t* __restrict__ tile_first, int64_t nvox,
+                                                                  KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ count,
+                                                                  double* __restrict__ mean3, double* __restrict__ m2) {
+  __shared__ unsigned scan_s[33];
+  const int64_t base = (int64_t)blockIdx.x * kSegTile;
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+  KeyT key[kItems], prev;
+  bool valid[kItems], head[kItems];
+  load_tile_keys(keys, n, base, key, prev, valid);
+  const unsigned local = head_flags(key, prev, valid, p0, head);
+  unsigned nheads;
+  unsigned run = block_exclusive_scan(local, scan_s, &nheads);
+  const uint32_t first_row = tile_first[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (!head[j]) continue;
+    const int64_t row = (int64_t)first_row + run;
+    ++run;
+    double na = 0.0, ma[3] = {0, 0, 0}, Ma[6] = {0, 0, 0, 0, 0, 0};
+    int64_t q = p0 + j;
+    do {
+      const int64_t src = order[q];
+      double mb[3], Mb[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mb[k] = mean3_in[(int64_t)k * in_stride + src];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Mb[k] = m2_in[(int64_t)k * in_stride + src];
+      chan_combine(na, ma, Ma, (double)count_in[src], mb, Mb);
+      ++q;
+    } while (q < n && keys[q] == key[j]);
+    voxel_keys[row] = key[j];
+    count[row] = (uint32_t)na;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = ma[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Ma[k];
+  }
+}
+
+template <typename KeyT>
+size_t tile_smem_bytes() { return sizeof(TileSmem<KeyT>); }
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" size_t vapc_segment_workspace_bytes(int64_t n) { return seg_ws_bytes(n); }
+
+extern "C" int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key_bytes, int64_t* nvoxels, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  if (n < 0 || !nvoxels) return vapc_set_error(VAPC_E_INVALID, "vapc_count_voxels: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (n == 0) {
+    VAPC_RETURN_IF_CUDA(cudaMemsetAsync(nvoxels, 0, sizeof(int64_t), s));
+    return VAPC_OK;
+  }
+  if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "vapc_count_voxels: n must be < 2^32 per GPU");
+  if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_count_voxels: workspace too small");
+  if (key_bytes != 4 && key_bytes != 8) return vapc_set_error(VAPC_E_INVALID, "vapc_count_voxels: key_bytes must be 4 or 8");
+  if ((uintptr_t)keys_sorted & 15u) return vapc_set_error(VAPC_E_INVALID, "vapc_count_voxels: keys must be 16-byte aligned");
+  const SegWs w = carve(ws, n);
+  const int64_t nt = seg_tiles(n);
+  if (key_bytes == 4)
+    count_heads_kernel<uint32_t><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const uint32_t*>(keys_sorted), n, w.tile_heads);
+  else
+    count_heads_kernel<unsigned long long><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const unsigned long long*>(keys_sorted), n, w.tile_heads);
+  VAPC_RETURN_IF_CUDA(scan_u32_exclusive(w.tile_heads, w.tile_heads, nt, w.total, w.scan_ws, s));
+  VAPC_RETURN_IF_CUDA(cudaMemcpyAsync(nvoxels, w.total, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  return VAPC_OK;
+}
+
+extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n, const vapc_grid_t* grid_host,
+                                   const double* xyzw, int64_t nvoxels_host, void* voxel_keys, uint32_t* start, uint32_t* count,
+                                   uint32_t* first_idx, double* mean3, double* m2, uint32_t* point2voxel, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  if (!grid_host || n < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: bad arguments");
+  if (n == 0) return VAPC_OK;
+  if (!keys_sorted || !idx_sorted || !xyzw || !voxel_keys || !start || !count || !first_idx || !mean3 || !m2)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: null buffer");
+  if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_reduce_moments: workspace too small");
+  if (((uintptr_t)keys_sorted | (uintptr_t)idx_sorted) & 15u || ((uintptr_t)xyzw & 31u))
+    return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: keys/idx must be 16-byte and xyzw 32-byte aligned");
+  const SegWs w = carve(ws, n);
+  const Grid g = to_device_grid(grid_host);
+  const int64_t nt = seg_tiles(n);
+  cudaStream_t s = as_stream(stream);
+  const double4* rec = reinterpret_cast<const double4*>(xyzw);
+  if (grid_host->key_bytes == 4) {
+    typedef uint32_t K;
+    const size_t smem = tile_smem_bytes<K>();
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reduce_moments_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
+  } else {
+    typedef unsigned long long K;
+    const size_t smem = tile_smem_bytes<K>();
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reduce_moments_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
+  }
+  const int64_t warps_per_block = kThreads / 32;
+  fixup_moments_kernel<<<(unsigned)((nt + warps_per_block - 1) / warps_per_block), kThreads, 0, s>>>(w.tile_heads, w.carry_cnt, w.carry,
+                                                                                                   (int)nt, nvoxels_host, count, mean3, m2);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n, int32_t key_bytes,
+                                   const double* xyzw, const double* cog3, int64_t nvoxels_host, double* min_dist,
+                                   uint32_t* argmin_idx, void* ws, size_t ws_bytes, void* stream) {
+  if (n < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: bad arguments");
+  if (n == 0) return VAPC_OK;
+  if (!keys_sorted || !idx_sorted || !xyzw || !cog3 || !min_dist || !argmin_idx)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: null buffer");
+  if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_closest_to_cog: workspace too small");
+  const SegWs w = carve(ws, n);
+  const int64_t nt = seg_tiles(n);
+  cudaStream_t s = as_stream(stream);
+  const double4* rec = reinterpret_cast<const double4*>(xyzw);
+  if (key_bytes == 4) {
+    typedef uint32_t K;
+    const size_t smem = tile_smem_bytes<K>();
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    closest_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+                                                          nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
+  } else if (key_bytes == 8) {
+    typedef unsigned long long K;
+    const size_t smem = tile_smem_bytes<K>();
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    closest_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+                                                          nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
+  } else {
+    return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: key_bytes must be 4 or 8");
+  }
+  fixup_closest_kernel<<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s>>>(w.tile_heads, w.carry_cnt, w.carry, (int)nt,
+                                                                                     min_dist, argmin_idx);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_merge_partials(const void* keys_sorted, const uint32_t* order, int64_t nrows, int32_t key_bytes,
+                                   const uint32_t* count_in, const double* mean3_in, const double* m2_in, int64_t in_stride,
+                                   int64_t nvoxels_host, void* voxel_keys, uint32_t* count, double* mean3, double* m2, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  if (nrows < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partials: bad arguments");
+  if (nrows == 0) return VAPC_OK;
+  if (!keys_sorted || !order || !count_in || !mean3_in || !m2_in || !voxel_keys || !count || !mean3 || !m2)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partials: null buffer");
+  if (!ws || ws_bytes < seg_ws_bytes(nrows)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_merge_partials: workspace too small");
+  const SegWs w = carve(ws, nrows);
+  const int64_t nt = seg_tiles(nrows);
+  cudaStream_t s = as_stream(stream);
+  if (key_bytes == 4)
+    merge_partials_kernel<uint32_t><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const uint32_t*>(keys_sorted), order, nrows, count_in,
+        mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<uint32_t*>(voxel_keys), count, mean3, m2);
+  else if (key_bytes == 8)
+    merge_partials_kernel<unsigned long long><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const unsigned long long*>(keys_sorted), order,
+        nrows, count_in, mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<unsigned long long*>(voxel_keys), count,
+        mean3, m2);
+  else
+    return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partials: key_bytes must be 4 or 8");
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}

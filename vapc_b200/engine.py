@@ -1,0 +1,483 @@
+"""Device-level pipeline over libvapc_b200: torch tensors are only the containers (device
+memory, streams); every computation is a call through the C ABI (include/vapc_b200.h).
+
+    VoxelCloud.build(x, y, z, voxel_size, origin)   keys -> radix sort -> segmentation -> moments
+    cloud.stats(...)                                density / centroid / std / cov / eig / features
+    cloud.closest_to_cog(), cloud.mode_count(...), mask_membership(...), join_epochs(...), ...
+
+This is what `vapc_b200.Vapc` / `BiTemporalVapc` (the reference-shaped facade) drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import Grid
+
+FEATURE_NAMES = (
+    "Sum_of_Eigenvalues", "Omnivariance", "Eigenentropy", "Anisotropy", "Planarity", "Linearity",
+    "Surface_Variation", "Sphericity",
+)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("vapc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f64(a, device) -> torch.Tensor:
+    """A contiguous fp64 CUDA tensor from a tensor / numpy array / pandas column."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    return t.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
+
+
+def _empty(n, dtype, device):
+    return torch.empty(int(n), dtype=dtype, device=device)
+
+
+def make_grid(voxel_size: float, origin: Sequence[float]) -> Grid:
+    if not voxel_size > 0:
+        raise ValueError("voxel_size must be a positive number.")
+    if len(origin) != 3:
+        raise ValueError("origin must be a list of three coordinates [x, y, z].")
+    g = Grid()
+    g.voxel_size = float(voxel_size)
+    for k in range(3):
+        g.origin[k] = float(origin[k])
+    return g
+
+
+def grid_from_bounds(voxel_size, origin, minmax6) -> Grid:
+    g = make_grid(voxel_size, origin)
+    mm = (C.c_double * 6)(*[float(v) for v in minmax6])
+    L.call("vapc_grid_from_bounds", C.byref(g), mm)
+    return g
+
+
+def grid_from_voxel_bounds(voxel_size, origin, vmin, vmax) -> Grid:
+    """Grid covering integer voxel bounds [vmin, vmax] per axis (used for masks / joins)."""
+    g = make_grid(voxel_size, origin)
+    total = 0
+    for k in range(3):
+        g.vmin[k] = int(vmin[k])
+        g.bits[k] = max(0, int(int(vmax[k]) - int(vmin[k])).bit_length())
+        total += g.bits[k]
+    if total > 64:
+        raise L.VapcError(L.VAPC_E_KEYSPACE, f"voxel bounding box needs {total} key bits (> 64)")
+    g.key_bytes = 4 if total <= 32 else 8
+    return g
+
+
+def coordinate_bounds(x, y, z) -> np.ndarray:
+    """[min x, min y, min z, max x, max y, max z] of device columns (one tiny D2H copy)."""
+    n = x.numel()
+    out = _empty(6, torch.float64, x.device)
+    ws_bytes = L.raw("vapc_minmax_workspace_bytes")()
+    ws = _empty(ws_bytes, torch.uint8, x.device)
+    L.call("vapc_minmax_f64", _ptr(x), _ptr(y), _ptr(z), n, _ptr(out), _ptr(ws), ws_bytes, _stream())
+    return out.cpu().numpy()
+
+
+def voxel_coords(x, y, z, voxel_size, origin):
+    """Vapc.voxelize (vapc.py:188-207): three int64 device columns, bit-exact with numpy."""
+    _require_cuda()
+    dev = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x, y, z = (_dev_f64(a, dev) for a in (x, y, z))
+    g = make_grid(voxel_size, origin)
+    n = x.numel()
+    out = [_empty(n, torch.int64, dev) for _ in range(3)]
+    L.call("vapc_voxel_coords_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream())
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = None):
+    """Stable LSD radix sort of (key, idx) by the low `end_bit` key bits.  keys: uint32-as-int32 or
+    uint64-as-int64 storage (torch has no unsigned 32/64 arithmetic; only the bytes matter).
+    Returns (keys_sorted, idx_sorted) — new tensors or the inputs, whichever holds the result."""
+    n = keys.numel()
+    dev = keys.device
+    key_bytes = keys.element_size()
+    keys_alt = torch.empty_like(keys)
+    iota = idx is None
+    if iota:
+        idx = _empty(n, torch.int32, dev)
+    idx_alt = torch.empty_like(idx)
+    ws_bytes = L.raw("vapc_sort_workspace_bytes")(n)
+    ws = _empty(ws_bytes, torch.uint8, dev)
+    in_alt = C.c_int32(0)
+    L.call("vapc_sort_pairs", _ptr(keys), _ptr(keys_alt), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, key_bytes, int(end_bit),
+           _ptr(ws), ws_bytes, C.byref(in_alt), _stream())
+    return (keys_alt, idx_alt) if in_alt.value else (keys, idx)
+
+
+@dataclass
+class VoxelStats:
+    density: Optional[torch.Tensor] = None  # [V]
+    cog: Optional[torch.Tensor] = None  # [3, V]
+    std: Optional[torch.Tensor] = None  # [3, V]
+    cov: Optional[torch.Tensor] = None  # [6, V]  xx xy xz yy yz zz
+    eig: Optional[torch.Tensor] = None  # [3, V]
+    eig_n: Optional[torch.Tensor] = None  # [3, V]
+    feat: Optional[torch.Tensor] = None  # [8, V]  FEATURE_NAMES order
+
+
+class VoxelCloud:
+    """A point cloud voxelised on the GPU: sorted (key, index) pairs, the voxel table in
+    lexicographic (vx, vy, vz) order, the (count, mean, M2) moments and the point->voxel map."""
+
+    def __init__(self):
+        self.grid: Grid = None
+        self.n = 0
+        self.nvoxels = 0
+        self.x = self.y = self.z = None
+        self.xyzw = None
+        self.keys_sorted = None
+        self.idx_sorted = None
+        self.voxel_keys = None
+        self.start = None
+        self.count = None
+        self.first_idx = None
+        self.mean3 = None
+        self.m2 = None
+        self.point2voxel = None
+        self._seg_ws = None
+        self._stats_cache: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------
+    @classmethod
+    def build(cls, x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), *, bounds=None, want_point2voxel=True,
+              keep_columns=True, device=None) -> "VoxelCloud":
+        """voxelize + groupby of the reference (vapc.py:188-207 and the groupby at :724, :843, :959)
+        as: bounds -> packed keys (+ xyzw records) -> stable radix sort -> segmentation -> moments."""
+        _require_cuda()
+        if device is None:
+            device = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x, y, z = (_dev_f64(a, device) for a in (x, y, z))
+        n = x.numel()
+        if y.numel() != n or z.numel() != n:
+            raise ValueError("X, Y, Z must have the same length")
+        if n == 0:
+            raise ValueError("empty point cloud")
+        if n >= 2 ** 32:
+            raise ValueError("at most 2**32 - 1 points per GPU")
+        self = cls()
+        self.n = n
+        if keep_columns:
+            self.x, self.y, self.z = x, y, z
+        if bounds is None:
+            bounds = coordinate_bounds(x, y, z)
+        self.grid = g = grid_from_bounds(voxel_size, origin, bounds)
+        kdtype = torch.int32 if g.key_bytes == 4 else torch.int64
+        keys = _empty(n, kdtype, device)
+        self.xyzw = torch.empty((n, 4), dtype=torch.float64, device=device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
+        self.keys_sorted, self.idx_sorted = sort_pairs(keys, g.total_bits)
+        del keys
+        ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
+        self._seg_ws = _empty(ws_bytes, torch.uint8, device)
+        nv = torch.zeros(2, dtype=torch.int64, device=device)
+        L.call("vapc_count_voxels", _ptr(self.keys_sorted), n, g.key_bytes, _ptr(nv), _ptr(self._seg_ws), ws_bytes, _stream())
+        host = torch.cat([nv[:1], status.to(torch.int64)]).cpu()  # the one sync of the pipeline
+        if int(host[1]) & 1:
+            raise L.VapcError(L.VAPC_E_RANGE, "a point fell outside the voxel grid bounds (NaN / inf coordinate or wrong bounds)")
+        self.nvoxels = V = int(host[0])
+        self.voxel_keys = _empty(V, kdtype, device)
+        self.start = _empty(V + 1, torch.int32, device)
+        self.count = _empty(V, torch.int32, device)
+        self.first_idx = _empty(V, torch.int32, device)
+        self.mean3 = torch.empty((3, V), dtype=torch.float64, device=device)
+        self.m2 = torch.empty((6, V), dtype=torch.float64, device=device)
+        self.point2voxel = _empty(n, torch.int32, device) if want_point2voxel else None
+        L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.idx_sorted), n, C.byref(g), _ptr(self.xyzw), V,
+               _ptr(self.voxel_keys), _ptr(self.start), _ptr(self.count), _ptr(self.first_idx), _ptr(self.mean3), _ptr(self.m2),
+               _ptr(self.point2voxel), _ptr(self._seg_ws), ws_bytes, _stream())
+        return self
+
+    @property
+    def device(self):
+        return self.voxel_keys.device
+
+    # ------------------------------------------------------------------------------------
+    def stats(self, density=False, cog=False, std=False, cov=False, eig=False, eig_n=False, feat=False) -> VoxelStats:
+        """One launch of vapc_voxel_stats for whatever is not cached yet."""
+        V, dev = self.nvoxels, self.device
+        want = dict(density=density, cog=cog, std=std, cov=cov, eig=eig, eig_n=eig_n, feat=feat)
+        shapes = dict(density=(V,), cog=(3, V), std=(3, V), cov=(6, V), eig=(3, V), eig_n=(3, V), feat=(8, V))
+        new = {k: torch.empty(shapes[k], dtype=torch.float64, device=dev) for k, w in want.items() if w and k not in self._stats_cache}
+        if new:
+            L.call("vapc_voxel_stats", _ptr(self.voxel_keys), _ptr(self.count), _ptr(self.mean3), _ptr(self.m2), V, C.byref(self.grid),
+                   *[_ptr(new.get(k)) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")], _stream())
+            self._stats_cache.update(new)
+        return VoxelStats(**{k: self._stats_cache[k] for k, w in want.items() if w})
+
+    def voxel_coords(self):
+        """(vx, vy, vz) int64 [V] of the voxel table rows."""
+        V, dev = self.nvoxels, self.device
+        out = [_empty(V, torch.int64, dev) for _ in range(3)]
+        L.call("vapc_unpack_keys", _ptr(self.voxel_keys), V, C.byref(self.grid), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream())
+        return out
+
+    def center_corner(self, center=True, corner=True):
+        V, dev = self.nvoxels, self.device
+        c = torch.empty((3, V), dtype=torch.float64, device=dev) if center else None
+        k = torch.empty((3, V), dtype=torch.float64, device=dev) if corner else None
+        L.call("vapc_voxel_center_corner", _ptr(self.voxel_keys), V, C.byref(self.grid), _ptr(c), _ptr(k), _stream())
+        return c, k
+
+    def closest_to_cog(self):
+        """(min_distance [V] f64, argmin original point index [V] int32-as-uint32)."""
+        V, dev = self.nvoxels, self.device
+        cog = self.stats(cog=True).cog
+        md = _empty(V, torch.float64, dev)
+        am = _empty(V, torch.int32, dev)
+        L.call("vapc_closest_to_cog", _ptr(self.keys_sorted), _ptr(self.idx_sorted), self.n, self.grid.key_bytes, _ptr(self.xyzw), _ptr(cog), V,
+               _ptr(md), _ptr(am), _ptr(self._seg_ws), self._seg_ws.numel(), _stream())
+        return md, am
+
+    def point_distance(self):
+        """distance of every point to its voxel's centroid, original point order (vapc.py:790-794)."""
+        cog = self.stats(cog=True).cog
+        out = _empty(self.n, torch.float64, self.device)
+        L.call("vapc_point_distance", _ptr(self.x), _ptr(self.y), _ptr(self.z), self.n, _ptr(self.point2voxel), _ptr(cog), self.nvoxels,
+               _ptr(out), _stream())
+        return out
+
+    def broadcast(self, table: torch.Tensor) -> torch.Tensor:
+        """table[point2voxel] for a [V] fp64 / int32 voxel column (the reference's per-point broadcast)."""
+        out = _empty(self.n, table.dtype, self.device)
+        if table.dtype == torch.float64:
+            L.call("vapc_gather_f64", _ptr(table), _ptr(self.point2voxel), self.n, _ptr(out), _stream())
+        elif table.dtype == torch.int32:
+            L.call("vapc_gather_u32", _ptr(table), _ptr(self.point2voxel), self.n, _ptr(out), _stream())
+        else:
+            raise TypeError(table.dtype)
+        return out
+
+    def mode_count(self, attr, thresholds: Sequence[float] = (), want_mode=True):
+        """mode and mode_count,p of an integer-valued attribute column (vapc.py:407-433).
+        Returns (mode [V] int64 or None, {p: mode_count [V] int64})."""
+        dev = self.device
+        a = _dev_f64(attr, dev)
+        if a.numel() != self.n:
+            raise ValueError("attribute length differs from the cloud")
+        amax = float(a.max().item()) if self.n else 0.0
+        attr_bits = max(1, int(max(amax, 0.0)).bit_length())
+        if attr_bits > 32:
+            raise ValueError("attribute values too large for mode / mode_count")
+        vbits = max(1, int(self.nvoxels - 1).bit_length())
+        keys = _empty(self.n, torch.int64, dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("vapc_mode_keys", _ptr(self.point2voxel), _ptr(a), self.n, attr_bits, _ptr(keys), _ptr(status), _stream())
+        ks, _ = sort_pairs(keys, vbits + attr_bits)
+        if int(status.item()) & 2:
+            raise ValueError("Cannot compute 'mode' / 'mode_count' for negative or non-finite attribute values")
+        mode = _empty(self.nvoxels, torch.int64, dev) if want_mode else None
+        counts = {}
+        todo = list(thresholds) or [None]
+        for i, p in enumerate(todo):
+            mc = _empty(self.nvoxels, torch.int64, dev) if p is not None else None
+            L.call("vapc_mode_count", _ptr(ks), self.n, attr_bits, _ptr(self.start), self.nvoxels, float(p if p is not None else 0.0),
+                   _ptr(mode if i == 0 else None), _ptr(mc), _stream())
+            if p is not None:
+                counts[p] = mc
+        return mode, counts
+
+    def percentage_occupied(self) -> float:
+        """round(V / bbox_cells * 100, 2)  (vapc.py:761-773)."""
+        vx, vy, vz = self.voxel_coords()
+        ext = [int(v.max().item()) - int(v.min().item()) + 1 for v in (vx, vy, vz)]
+        return round(self.nvoxels / (ext[0] * ext[1] * ext[2]) * 100, 2)
+
+
+def attribute_statistics(cloud: VoxelCloud, attr, median=True) -> Dict[str, torch.Tensor]:
+    """mean / sum / min / max / var / std (ddof = 0) / median of an fp64 attribute per voxel
+    (vapc.py:393-406); [V] device tensors."""
+    dev, V, n = cloud.device, cloud.nvoxels, cloud.n
+    a = _dev_f64(attr, dev)
+    if a.numel() != n:
+        raise ValueError("attribute length differs from the cloud")
+    out = {k: _empty(V, torch.float64, dev) for k in ("sum", "mean", "min", "max", "var")}
+    L.call("vapc_attr_stats", _ptr(a), _ptr(cloud.idx_sorted), _ptr(cloud.start), V, _ptr(out["sum"]), _ptr(out["mean"]), _ptr(out["min"]),
+           _ptr(out["max"]), _ptr(out["var"]), _stream())
+    out["std"] = torch.sqrt(out["var"])
+    if median:
+        keys = _empty(n, torch.int64, dev)
+        L.call("vapc_f64_sort_keys", _ptr(a), n, _ptr(keys), _stream())
+        _, by_value = sort_pairs(keys, 64)
+        rows = _empty(n, torch.int32, dev)
+        L.call("vapc_gather_u32", _ptr(cloud.point2voxel), _ptr(by_value), n, _ptr(rows), _stream())
+        _, by_voxel_value = sort_pairs(rows, max(1, int(V - 1).bit_length()), idx=by_value)
+        out["median"] = _empty(V, torch.float64, dev)
+        L.call("vapc_attr_median", _ptr(a), _ptr(by_voxel_value), _ptr(cloud.start), V, _ptr(out["median"]), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# masks
+# ----------------------------------------------------------------------------------------
+class VoxelMask:
+    """Hash set of voxel triples on the device (MultiIndex.isin, vapc.py:594-598)."""
+
+    def __init__(self, mvx, mvy, mvz, voxel_size, origin, device=None):
+        _require_cuda()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        mv = [torch.as_tensor(np.asarray(a, dtype=np.int64) if not isinstance(a, torch.Tensor) else a).to(device=device, dtype=torch.int64).contiguous()
+              for a in (mvx, mvy, mvz)]
+        self.n = mv[0].numel()
+        self.device = device
+        if self.n == 0:
+            self.grid = grid_from_voxel_bounds(voxel_size, origin, (0, 0, 0), (0, 0, 0))
+        else:
+            lo = [int(a.min().item()) for a in mv]
+            hi = [int(a.max().item()) for a in mv]
+            self.grid = grid_from_voxel_bounds(voxel_size, origin, lo, hi)
+        if self.grid.total_bits > 63:
+            raise L.VapcError(L.VAPC_E_KEYSPACE, "mask extent needs more than 63 key bits")
+        keys = _empty(self.n, torch.int64, device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        L.call("vapc_pack_triples_i64", _ptr(mv[0]), _ptr(mv[1]), _ptr(mv[2]), self.n, C.byref(self.grid), _ptr(keys), _ptr(status), _stream())
+        cap = C.c_int64(0)
+        nbytes = L.raw("vapc_mask_table_bytes")(self.n, C.byref(cap))
+        self.capacity = cap.value
+        self.table = _empty(nbytes, torch.uint8, device)
+        L.call("vapc_mask_build", _ptr(keys), self.n, _ptr(self.table), self.capacity, _stream())
+
+    def contains_points(self, x, y, z) -> torch.Tensor:
+        """uint8 [N]: 1 where the point's voxel (same voxel_size / origin as the mask) is in the set."""
+        x, y, z = (_dev_f64(a, self.device) for a in (x, y, z))
+        n = x.numel()
+        out = _empty(n, torch.uint8, self.device)
+        L.call("vapc_mask_lookup_points", _ptr(x), _ptr(y), _ptr(z), n, C.byref(self.grid), _ptr(self.table), self.capacity, _ptr(out), _stream())
+        return out
+
+    def contains_voxels(self, vx, vy, vz) -> torch.Tensor:
+        v = [torch.as_tensor(np.asarray(a, dtype=np.int64) if not isinstance(a, torch.Tensor) else a).to(device=self.device, dtype=torch.int64).contiguous()
+             for a in (vx, vy, vz)]
+        n = v[0].numel()
+        keys = _empty(n, torch.int64, self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        L.call("vapc_pack_triples_i64", _ptr(v[0]), _ptr(v[1]), _ptr(v[2]), n, C.byref(self.grid), _ptr(keys), _ptr(status), _stream())
+        out = _empty(n, torch.uint8, self.device)
+        L.call("vapc_mask_lookup_keys", _ptr(keys), n, _ptr(self.table), self.capacity, _ptr(out), _stream())
+        return out
+
+
+def unique_voxels_first_occurrence(vx, vy, vz, device=None):
+    """drop_duplicates() on voxel triples: unique rows in first-occurrence order (vapc.py:507-510,
+    :524-525).  Packs, stable-sorts (key, position), takes each run's first position, then sorts those
+    positions.  Returns three int64 device columns."""
+    _require_cuda()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    v = [torch.as_tensor(np.asarray(a, dtype=np.int64) if not isinstance(a, torch.Tensor) else a).to(device=device, dtype=torch.int64).contiguous()
+         for a in (vx, vy, vz)]
+    n = v[0].numel()
+    if n == 0:
+        return v
+    lo = [int(a.min().item()) for a in v]
+    hi = [int(a.max().item()) for a in v]
+    g = grid_from_voxel_bounds(1.0, (0.0, 0.0, 0.0), lo, hi)
+    if g.total_bits > 63:
+        raise L.VapcError(L.VAPC_E_KEYSPACE, "voxel extent needs more than 63 key bits")
+    keys = _empty(n, torch.int64, device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    L.call("vapc_pack_triples_i64", _ptr(v[0]), _ptr(v[1]), _ptr(v[2]), n, C.byref(g), _ptr(keys), _ptr(status), _stream())
+    ks, order = sort_pairs(keys, g.total_bits)
+    ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
+    ws = _empty(ws_bytes, torch.uint8, device)
+    nv = torch.zeros(1, dtype=torch.int64, device=device)
+    L.call("vapc_count_voxels", _ptr(ks), n, 8, _ptr(nv), _ptr(ws), ws_bytes, _stream())
+    # heads of runs: stable sort => the first element of each run is the first occurrence
+    head = torch.ones(n, dtype=torch.bool, device=device)
+    head[1:] = ks[1:] != ks[:-1]
+    first_pos = order[head]  # uint32 positions stored as int32
+    assert first_pos.numel() == int(nv.item())
+    pos_sorted, _ = sort_pairs(first_pos.clone(), max(1, int(n - 1).bit_length()))
+    sel = pos_sorted.to(torch.int64) & 0xFFFFFFFF
+    return [a[sel] for a in v]
+
+
+def buffer_expand(vx, vy, vz, buffer_size: int, device=None):
+    """Every triple + all (2b+1)^3 offsets in the reference's order (vapc.py:513-521); [3, n*(2b+1)^3]."""
+    _require_cuda()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    v = [torch.as_tensor(np.asarray(a, dtype=np.int64) if not isinstance(a, torch.Tensor) else a).to(device=device, dtype=torch.int64).contiguous()
+         for a in (vx, vy, vz)]
+    n = v[0].numel()
+    w = 2 * int(buffer_size) + 1
+    out = torch.empty((3, n * w ** 3), dtype=torch.int64, device=device)
+    L.call("vapc_buffer_expand", _ptr(v[0]), _ptr(v[1]), _ptr(v[2]), n, int(buffer_size), _ptr(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# two-epoch change detection
+# ----------------------------------------------------------------------------------------
+def join_voxel_tables(v1: Sequence[torch.Tensor], v2: Sequence[torch.Tensor]):
+    """Inner join + the two anti-joins of two voxel tables given as (vx, vy, vz) int64 device columns
+    whose rows are UNIQUE (bi_vapc.py:84, :30-31).  Returns (i1, i2, only1, only2) int64 index tensors:
+    pairs in epoch-1 row order; only1 / only2 in lexicographic voxel order (Index.difference sorts)."""
+    dev = v1[0].device
+    n1, n2 = v1[0].numel(), v2[0].numel()
+    lo = [min(int(a.min().item()) if n1 else 0, int(b.min().item()) if n2 else 0) for a, b in zip(v1, v2)]
+    hi = [max(int(a.max().item()) if n1 else 0, int(b.max().item()) if n2 else 0) for a, b in zip(v1, v2)]
+    g = grid_from_voxel_bounds(1.0, (0.0, 0.0, 0.0), lo, hi)
+    if g.total_bits > 63:
+        raise L.VapcError(L.VAPC_E_KEYSPACE, "joined voxel extent needs more than 63 key bits")
+    sorted_keys, orders = [], []
+    for v, n in ((v1, n1), (v2, n2)):
+        keys = _empty(n, torch.int64, dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("vapc_pack_triples_i64", _ptr(v[0]), _ptr(v[1]), _ptr(v[2]), n, C.byref(g), _ptr(keys), _ptr(status), _stream())
+        ks, order = sort_pairs(keys, g.total_bits)
+        sorted_keys.append(ks)
+        orders.append(order.to(torch.int64) & 0xFFFFFFFF)
+    m1 = _empty(n1, torch.int32, dev)
+    m2 = _empty(n2, torch.int32, dev)
+    L.call("vapc_join_sorted_keys", _ptr(sorted_keys[0]), n1, _ptr(sorted_keys[1]), n2, _ptr(m1), _ptr(m2), _stream())
+    m1 = m1.to(torch.int64) & 0xFFFFFFFF
+    m2 = m2.to(torch.int64) & 0xFFFFFFFF
+    miss = 0xFFFFFFFF
+    # back to original row numbering: sorted position p of table 1 is row orders[0][p]
+    match_row1 = torch.full((n1,), -1, dtype=torch.int64, device=dev)
+    hit = m1 != miss
+    match_row1[orders[0][hit]] = orders[1][m1[hit]]
+    i1 = torch.nonzero(match_row1 >= 0).flatten()
+    i2 = match_row1[i1]
+    only1 = orders[0][m1 == miss]  # already in key (lexicographic) order
+    only2 = orders[1][m2 == miss]
+    return i1, i2, only1, only2
+
+
+def mahalanobis(cog1, cov1, cog2, cov2, i1, i2, alpha=0.005):
+    """bi_vapc.py:86-138 on joined rows.  cog*: [3, V] f64, cov*: [6, V] f64, i1 / i2: int64 rows.
+    Returns dict of device tensors: distance, d1, d2, p_value, significance, change_type."""
+    dev = cog1.device
+    r = i1.numel()
+    a = i1.to(torch.int32).contiguous()
+    b = i2.to(torch.int32).contiguous()
+    out = dict(distance=_empty(r, torch.float64, dev), d1=_empty(r, torch.float64, dev), d2=_empty(r, torch.float64, dev),
+               p_value=_empty(r, torch.float64, dev), significance=_empty(r, torch.int32, dev), change_type=_empty(r, torch.int32, dev))
+    L.call("vapc_mahalanobis", _ptr(cog1.contiguous()), _ptr(cov1.contiguous()), cog1.shape[1], _ptr(cog2.contiguous()), _ptr(cov2.contiguous()),
+           cog2.shape[1], _ptr(a), _ptr(b), r, float(alpha), _ptr(out["distance"]), _ptr(out["d1"]), _ptr(out["d2"]), _ptr(out["p_value"]),
+           _ptr(out["significance"]), _ptr(out["change_type"]), _stream())
+    return out

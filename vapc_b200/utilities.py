@@ -1,0 +1,56 @@
+"""trace / timeit decorators with the reference's switches (src/vapc/utilities.py:51-111).
+
+Same names and printing behaviour, so notebooks calling `vapc.enable_trace(False)` keep working.
+`timeit` synchronises the CUDA device before reading the clock on both sides — kernels are
+asynchronous, and without it the printed time would only be the launch time.  Unlike the
+reference both switches default to off-by-environment: set VAPC_TRACE=1 / VAPC_TIMEIT=1 or call
+enable_trace() / enable_timeit() to get the reference's chatty default.
+"""
+import os
+import time
+from functools import wraps
+
+DECORATOR_CONFIG = {"trace": os.environ.get("VAPC_TRACE", "0") == "1", "timeit": os.environ.get("VAPC_TIMEIT", "0") == "1"}
+
+
+def enable_trace(enable=True):
+    DECORATOR_CONFIG["trace"] = enable
+
+
+def enable_timeit(enable=True):
+    DECORATOR_CONFIG["timeit"] = enable
+
+
+def _sync():
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    except Exception:  # pragma: no cover
+        pass
+
+
+def trace(func):
+    @wraps(func)
+    def wrapper(*args, **kwargs):
+        if DECORATOR_CONFIG["trace"]:
+            print(f"Calling {func.__name__}")
+        return func(*args, **kwargs)
+
+    return wrapper
+
+
+def timeit(func):
+    @wraps(func)
+    def wrapper(*args, **kwargs):
+        if not DECORATOR_CONFIG["timeit"]:
+            return func(*args, **kwargs)
+        _sync()
+        t0 = time.time()
+        result = func(*args, **kwargs)
+        _sync()
+        print(f"Function '{func.__name__}' executed in {time.time() - t0:.4f} seconds")
+        return result
+
+    return wrapper

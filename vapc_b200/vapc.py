@@ -1,0 +1,615 @@
+"""`Vapc` — drop-in for the reference's `vapc.Vapc` (src/vapc/vapc.py:8-1357) on top of the
+B200 engine.
+
+Same constructor, attributes, state flags, method names and DataFrame column names as the
+reference; `self.df` stays a host pandas DataFrame (callers read and assign it directly,
+tests/test_voxel.py:82-83) while every per-point computation runs on the GPU through
+`vapc_b200.engine` (C ABI calls) and only the resulting columns are copied back.
+
+Host-side work is limited to what the DataFrame container itself requires (adding / dropping /
+reordering columns, row selection with a mask computed on the GPU, and — on the V-row reduced
+frame only — the reference's final `drop_duplicates` + `groupby(XYZ).median()` formatting).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import engine as E
+from .utilities import timeit, trace
+
+_COV_NAMES = ["cov_xx", "cov_xy", "cov_xz", "cov_yx", "cov_yy", "cov_yz", "cov_zx", "cov_zy", "cov_zz"]
+_COV9_FROM6 = [0, 1, 2, 1, 3, 4, 2, 4, 5]
+
+
+def _u32(t: torch.Tensor) -> torch.Tensor:
+    """uint32 values stored in an int32 tensor -> int64."""
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+class Vapc:
+    AVAILABLE_COMPUTATIONS = [
+        "voxel_index",
+        "point_count",
+        "point_density",
+        "percentage_occupied",
+        "covariance_matrix",
+        "eigenvalues",
+        "geometric_features",
+        "center_of_gravity",
+        "distance_to_center_of_gravity",
+        "std_of_cog",
+        "closest_to_center_of_gravity",
+        "center_of_voxel",
+        "corner_of_voxel",
+    ]
+
+    def __init__(self, voxel_size: float, origin: list = None, attributes: dict = None, compute: list = None,
+                 return_at: str = "closest_to_center_of_gravity"):
+        """Same parameters and validation as the reference constructor (vapc.py:26-110)."""
+        self.voxel_size = voxel_size
+        self.origin = origin if origin is not None else [0, 0, 0]
+        self.attributes = attributes if attributes is not None else {}
+        self.compute = compute if compute is not None else []
+        self.return_at = return_at
+        if self.voxel_size <= 0:
+            raise ValueError("voxel_size must be a positive number.")
+        if not isinstance(self.origin, list) or len(self.origin) != 3:
+            raise ValueError("origin must be a list of three coordinates [x, y, z].")
+        self.AVAILABLE_COMPUTATIONS = list(Vapc.AVAILABLE_COMPUTATIONS)
+        self.df = None
+        self.original_attributes = None
+        # state flags of the lazy-dependency protocol (vapc.py:90-110)
+        self.attributes_up_to_data = False
+        self.voxelized = False
+        self.voxel_index = False
+        self.point_count = False
+        self.point_density = False
+        self.percentage_occupied = False
+        self.covariance_matrix = False
+        self.eigenvalues = False
+        self.geometric_features = False
+        self.center_of_gravity = False
+        self.distance_to_center_of_gravity = False
+        self.std_of_cog = False
+        self.closest_to_center_of_gravity = False
+        self.center_of_voxel = False
+        self.corner_of_voxel = False
+        self.attributes_per_voxel = False
+        self.drop_columns = []
+        self.new_column_names = {}
+        self.reduced = False
+        self.reduction_point = None
+        self.offset_applied = False
+        # closest-to-centroid reduction: "all" keeps every exactly tied point like the reference
+        # (vapc.py:1195); "first" keeps the lowest original index only (north_star tie-break).
+        self.closest_ties = "all"
+        self._cloud = None
+        self._cloud_sig = None
+
+    # ------------------------------------------------------------------------------------
+    # device cloud cache
+    # ------------------------------------------------------------------------------------
+    def _signature(self):
+        x = self.df["X"].to_numpy()
+        n = len(x)
+        sig = [id(self.df), n, float(self.voxel_size), tuple(float(o) for o in self.origin)]
+        for c in ("X", "Y", "Z"):
+            a = self.df[c].to_numpy()
+            sig.append(a.__array_interface__["data"][0])
+            if n:
+                sig += [float(a[0]), float(a[n // 2]), float(a[-1])]
+        return tuple(sig)
+
+    def _get_cloud(self) -> E.VoxelCloud:
+        """The device-side voxelisation of the current X, Y, Z columns (rebuilt when they change)."""
+        if self.df is None:
+            raise AttributeError("no point cloud loaded: assign `df` or call get_data_from_data_handler()")
+        sig = self._signature()
+        if self._cloud is None or sig != self._cloud_sig:
+            self._cloud = E.VoxelCloud.build(self.df["X"].to_numpy(np.float64), self.df["Y"].to_numpy(np.float64),
+                                             self.df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
+            self._cloud_sig = sig
+        return self._cloud
+
+    def _resign(self):
+        """Re-take the cache signature after this class itself touched the frame (added columns)."""
+        if self._cloud is not None:
+            self._cloud_sig = self._signature()
+
+    def _per_point(self, voxel_column: torch.Tensor) -> np.ndarray:
+        """Broadcast a [V] voxel column to the points on the device, copy the result to the host."""
+        return self._get_cloud().broadcast(voxel_column.contiguous()).cpu().numpy()
+
+    def _validate_compute_list(self):
+        invalid = [c for c in self.compute if c not in self.AVAILABLE_COMPUTATIONS]
+        if invalid:
+            raise ValueError(f"Invalid computation(s) requested: {invalid}. "
+                             f"Available computations are: {self.AVAILABLE_COMPUTATIONS}")
+
+    # ------------------------------------------------------------------------------------
+    @trace
+    @timeit
+    def get_data_from_data_handler(self, data_handler):
+        """Moves the DataFrame out of the data handler (vapc.py:132-149)."""
+        if data_handler.df is None:
+            raise AttributeError("The provided data_handler does not have a 'df' attribute.")
+        self.df = data_handler.df
+        data_handler.df = None
+        self.original_attributes = self.df.columns.tolist()
+
+    @trace
+    @timeit
+    def compute_reduction_point(self):
+        """[int(min X), int(min Y), int(min Z)] (vapc.py:153-162); the minima come from the GPU bbox kernel."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        E._require_cuda()
+        cols = [E._dev_f64(self.df[c].to_numpy(np.float64), dev) for c in ("X", "Y", "Z")]
+        mm = E.coordinate_bounds(*cols)
+        self.reduction_point = [int(mm[0]), int(mm[1]), int(mm[2])]
+
+    @trace
+    @timeit
+    def compute_offset(self):
+        """Toggle the subtraction of `reduction_point` from X, Y, Z (vapc.py:166-184)."""
+        if self.reduction_point is None:
+            self.compute_reduction_point()
+        sign = 1 if self.offset_applied else -1
+        for c, r in zip(("X", "Y", "Z"), self.reduction_point):
+            self.df[c] = self.df[c] + sign * r
+        self.offset_applied = not self.offset_applied
+
+    @trace
+    @timeit
+    def voxelize(self):
+        """voxel_x / voxel_y / voxel_z = floor((coord - origin) / voxel_size) as int64 (vapc.py:188-207)."""
+        vx, vy, vz = E.voxel_coords(self.df["X"].to_numpy(np.float64), self.df["Y"].to_numpy(np.float64),
+                                    self.df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
+        for name, col in zip(("voxel_x", "voxel_y", "voxel_z"), (vx, vy, vz)):
+            self.df[name] = col.cpu().numpy()
+        self.voxelized = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_requested_attributes(self):
+        """Dispatcher over `self.compute` (vapc.py:211-252)."""
+        self._validate_compute_list()
+        for name in self.compute:
+            if getattr(self, name) is True:
+                continue
+            method = getattr(self, f"compute_{name}", None)
+            if callable(method):
+                try:
+                    method()
+                except Exception as e:
+                    print(f"Error computing '{name}': {e}")
+                    raise e
+            else:
+                print(f"Invalid computation name: '{name}'")
+                raise ValueError(f"Invalid computation name: '{name}'")
+
+    def update_attribute_dictionary(self, remove_cols=None):
+        """Default statistic 'mean' for every original attribute unless specified (vapc.py:254-299)."""
+        if remove_cols is None:
+            remove_cols = ["X", "Y", "Z", "bit_fields", "raw_classification", "scan_angle_rank", "user_data", "point_source_id"]
+        original = [c for c in self.original_attributes if c not in remove_cols]
+        attributes = {c: "mean" for c in original}
+        attributes.update(self.attributes)
+        self.attributes = attributes
+        self.attributes_up_to_data = True
+
+    # ------------------------------------------------------------------------------------
+    @trace
+    @timeit
+    def compute_requested_statistics_per_attributes(self):
+        """Per-voxel statistics of attribute columns broadcast to the points, column f"{attr}_{stat}"
+        (vapc.py:303-472).  `mode` and `mode_count,<p>` (vapc.py:407-433) run on the GPU as a
+        sort by (voxel, value) + run lengths; mean / sum / min / max / std / var (ddof = 0) / median are
+        segmented reductions over the voxel-sorted attribute."""
+        if self.attributes == {}:
+            print("No attributes specified for computation. Skipping.")
+            return
+        if not self.voxelized:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        if not self.attributes_up_to_data:
+            self.update_attribute_dictionary()
+        required = ["voxel_x", "voxel_y", "voxel_z"] + list(self.attributes.keys())
+        missing = [c for c in required if c not in self.df.columns]
+        if missing:
+            raise KeyError(f"Missing columns in `self.df`: {missing}")
+        cloud = self._get_cloud()
+        new_cols = {}
+        for attr, stats_list in self.attributes.items():
+            if not isinstance(stats_list, list):
+                stats_list = [stats_list]
+            values = self.df[attr].to_numpy(np.float64)
+            thresholds, want_mode = [], False
+            for stat in stats_list:
+                if stat == "mode":
+                    want_mode = True
+                elif "mode_count" in stat:
+                    try:
+                        _, p = stat.split(",")
+                        thresholds.append((stat, float(p)))
+                    except ValueError as exc:
+                        raise ValueError(f"Invalid 'mode_count' specification for attribute '{attr}': '{stat}'") from exc
+            mode_res, count_res = (None, {})
+            if want_mode or thresholds:
+                try:
+                    mode_res, count_res = cloud.mode_count(values, [p for _, p in thresholds], want_mode=True)
+                except ValueError as exc:
+                    if thresholds:
+                        raise ValueError(f"Cannot compute 'mode_count' for continuous attribute '{attr}'") from exc
+                    raise
+            simple = None
+            for stat in stats_list:
+                col = f"{attr}_{stat}"
+                if stat == "mode":
+                    new_cols[col] = mode_res
+                elif "mode_count" in stat:
+                    new_cols[col] = count_res[dict(thresholds)[stat]]
+                elif stat in ("mean", "std", "var", "median", "min", "max", "sum"):
+                    if simple is None:
+                        simple = E.attribute_statistics(cloud, values)
+                    new_cols[col] = simple[stat]
+                else:
+                    print(f"Unknown aggregation type '{stat}' for attribute '{attr}'. Skipping.")
+        # the reference merges the aggregated frame back with how="left" (index reset, vapc.py:468-470)
+        self.df = self.df.reset_index(drop=True)
+        p2v = _u32(cloud.point2voxel)
+        for col, table in new_cols.items():
+            self.df[col] = table[p2v].cpu().numpy()
+        self.attributes_per_voxel = True
+        self._cloud_sig = self._signature()
+
+    # ------------------------------------------------------------------------------------
+    @trace
+    @timeit
+    def compute_voxel_index(self):
+        """3-level MultiIndex idx_voxel_{x,y,z} equal to the voxel triple, columns kept (vapc.py:476-491)."""
+        if self.voxel_index:
+            return
+        if not self.voxelized:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        self.df.set_index(["voxel_x", "voxel_y", "voxel_z"], inplace=True, drop=False)
+        self.df.index.set_names(["idx_voxel_x", "idx_voxel_y", "idx_voxel_z"], inplace=True)
+        self.voxel_index = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_voxel_buffer(self, buffer_size: int = 1):
+        """Unique voxels of this cloud, each expanded by all (2b+1)^3 offsets and de-duplicated in
+        first-occurrence order; overwrites `self.df` with that mask frame and returns it
+        (vapc.py:495-541, including its X/Y/Z = (v + vs/2) * vs quirk)."""
+        if not self.voxelized:
+            self.voxelize()
+        v = [self.df[c].to_numpy(np.int64) for c in ("voxel_x", "voxel_y", "voxel_z")]
+        uniq = E.unique_voxels_first_occurrence(*v)
+        expanded = E.buffer_expand(uniq[0], uniq[1], uniq[2], int(buffer_size))
+        buf = E.unique_voxels_first_occurrence(expanded[0], expanded[1], expanded[2])
+        self.df = pd.DataFrame({n: c.cpu().numpy() for n, c in zip(("voxel_x", "voxel_y", "voxel_z"), buf)})
+        self.voxelized = True
+        self.voxel_index = False
+        self.compute_voxel_index()
+        self.df["Y"] = (self.df["voxel_y"] + self.voxel_size / 2) * self.voxel_size
+        self.df["Z"] = (self.df["voxel_z"] + self.voxel_size / 2) * self.voxel_size
+        self.df["X"] = (self.df["voxel_x"] + self.voxel_size / 2) * self.voxel_size
+        self.buffer_df = self.df
+        self._cloud = None
+        return self.df
+
+    def _mask_voxels(self, vapc_mask):
+        if self.df is None or vapc_mask.df is None:
+            raise AttributeError("Both `self.df` and `vapc_mask.df` must exist.")
+        if self.voxelized is False:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        if vapc_mask.voxelized is False:
+            vapc_mask.voxelize()
+        if vapc_mask.voxel_index is False:
+            vapc_mask.compute_voxel_index()
+        if self.voxel_index is False:
+            self.compute_voxel_index()
+        idx = vapc_mask.df.index
+        return [np.asarray(idx.get_level_values(k), dtype=np.int64) for k in range(3)]
+
+    @trace
+    @timeit
+    def select_by_mask(self, vapc_mask, segment_in_or_out="in"):
+        """Keep ("in") or remove ("out") the points whose voxel triple is in the mask's voxel set
+        (vapc.py:545-609).  Membership is a GPU hash-set probe; original order is kept, the voxel
+        columns are dropped afterwards and `voxelized` is reset, as in the reference."""
+        mv = self._mask_voxels(vapc_mask)
+        if segment_in_or_out not in ("in", "out"):
+            raise ValueError("Parameter 'segment_in_or_out' must be either 'in' or 'out'.")
+        mask = E.VoxelMask(mv[0], mv[1], mv[2], float(self.voxel_size), self.origin)
+        own = [np.asarray(self.df.index.get_level_values(k), dtype=np.int64) for k in range(3)]
+        member = mask.contains_voxels(*own).cpu().numpy().astype(bool)
+        self.df = self.df.loc[member if segment_in_or_out == "in" else ~member]
+        for attr in ["voxel_x", "voxel_y", "voxel_z"]:
+            if attr in self.df.columns:
+                self.df = self.df.drop([attr], axis=1)
+        self.voxelized = False
+        self._cloud = None
+
+    @trace
+    @timeit
+    def label_by_mask(self, vapc_mask, label_attributes=["voxel_x", "voxel_y", "voxel_z"]):
+        """Left-join selected mask columns onto the points by voxel triple (vapc.py:614-677)."""
+        self._mask_voxels(vapc_mask)
+        common = [c for c in label_attributes if c in vapc_mask.df.columns]
+        if common:
+            self.df = self.df.join(vapc_mask.df[common], how="left")
+        for attr in ["voxel_x", "voxel_y", "voxel_z"]:
+            if attr in self.df.columns:
+                self.df = self.df.drop([attr], axis=1)
+        self.voxelized = False
+        self._cloud = None
+
+    # ------------------------------------------------------------------------------------
+    @trace
+    @timeit
+    def compute_point_count(self):
+        """point_count = points in the point's voxel, int64 (vapc.py:715-726)."""
+        if self.voxelized is False:
+            self.voxelize()
+        cloud = self._get_cloud()
+        self.df["point_count"] = _u32(cloud.broadcast(cloud.count)).cpu().numpy()
+        self.point_count = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_point_density(self):
+        """point_count / voxel_size**3 (vapc.py:730-741)."""
+        if self.point_count is False:
+            self.compute_point_count()
+            if "point_count" not in self.compute:
+                self.drop_columns += ["point_count"]
+        cloud = self._get_cloud()
+        self.df["point_density"] = self._per_point(cloud.stats(density=True).density)
+        self.point_density = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_percentage_occupied(self):
+        """Occupied share of the voxel bounding box, stored in `self.percentage_occupied` (vapc.py:745-773)."""
+        if self.voxel_index is False:
+            self.compute_voxel_index()
+        self.percentage_occupied = self._get_cloud().percentage_occupied()
+
+    def compute_distance_to_center_of_gravity(self):
+        """distance = |point - voxel centroid| per point (vapc.py:776-795)."""
+        if self.center_of_gravity is False:
+            self.compute_center_of_gravity()
+            if "center_of_gravity" not in self.compute:
+                self.drop_columns += ["cog_x", "cog_y", "cog_z"]
+        self.df["distance"] = self._get_cloud().point_distance().cpu().numpy()
+        self.distance_to_center_of_gravity = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_closest_to_center_of_gravity(self):
+        """min_distance = smallest distance in the point's voxel (vapc.py:799-825; the reference's
+        merge resets the index)."""
+        if not self.center_of_gravity:
+            self.compute_center_of_gravity()
+            if "center_of_gravity" not in self.compute:
+                self.drop_columns += ["cog_x", "cog_y", "cog_z"]
+        if not self.distance_to_center_of_gravity:
+            self.compute_distance_to_center_of_gravity()
+            if "distance_to_center_of_gravity" not in self.compute:
+                self.drop_columns += ["distance"]
+        cloud = self._get_cloud()
+        min_dist, argmin = cloud.closest_to_cog()
+        self._closest_argmin = _u32(argmin)
+        self.df = self.df.reset_index(drop=True)
+        self.df["min_distance"] = self._per_point(min_dist)
+        self.closest_to_center_of_gravity = True
+        self._cloud_sig = self._signature()
+
+    @trace
+    @timeit
+    def compute_center_of_gravity(self):
+        """cog_x / cog_y / cog_z = per-voxel mean of X, Y, Z (vapc.py:829-852)."""
+        if not self.voxelized:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        cloud = self._get_cloud()
+        cog = cloud.stats(cog=True).cog
+        for k, name in enumerate(("cog_x", "cog_y", "cog_z")):
+            self.df[name] = self._per_point(cog[k])
+        self.center_of_gravity = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_std_of_cog(self):
+        """std_x / std_y / std_z = per-voxel sample standard deviation, ddof = 1 (vapc.py:856-887)."""
+        if not self.voxelized:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        cloud = self._get_cloud()
+        std = cloud.stats(std=True).std
+        for k, name in enumerate(("std_x", "std_y", "std_z")):
+            self.df[name] = self._per_point(std[k])
+        self.std_of_cog = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_center_of_voxel(self):
+        """center_* = ((voxel * vs) + vs / 2) + origin (vapc.py:891-907)."""
+        if self.voxelized is False:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        center, _ = self._get_cloud().center_corner(center=True, corner=False)
+        for k, name in enumerate(("center_x", "center_y", "center_z")):
+            self.df[name] = self._per_point(center[k])
+        self.center_of_voxel = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_corner_of_voxel(self):
+        """corner_* = (voxel * vs) + origin (vapc.py:911-925)."""
+        if self.voxelized is False:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        _, corner = self._get_cloud().center_corner(center=False, corner=True)
+        for k, name in enumerate(("corner_x", "corner_y", "corner_z")):
+            self.df[name] = self._per_point(corner[k])
+        self.corner_of_voxel = True
+        self._resign()
+
+    @trace
+    @timeit
+    def compute_covariance_matrix(self):
+        """The 9 cov_* columns, moved to the front of the frame (vapc.py:929-1040); NaN for
+        single-point voxels.  Sets `covariance_matrix_computed` — like the reference it does NOT set
+        the `covariance_matrix` flag."""
+        if not self.voxelized:
+            self.voxelize()
+        cloud = self._get_cloud()
+        cov = cloud.stats(cov=True).cov
+        six = [self._per_point(cov[k]) for k in range(6)]
+        for name, k in zip(_COV_NAMES, _COV9_FROM6):
+            self.df[name] = six[k]
+        other = [c for c in self.df.columns if c not in _COV_NAMES]
+        self.df = self.df[_COV_NAMES + other]
+        self.covariance_matrix_computed = True
+        self._cloud_sig = self._signature()
+
+    @trace
+    @timeit
+    def compute_eigenvalues(self):
+        """Eigenvalue_1..3 of the per-voxel covariance, descending, NaN for single-point voxels
+        (vapc.py:1044-1090; the reference's merge resets the index)."""
+        if self.covariance_matrix is False:
+            self.compute_covariance_matrix()
+            if "covariance_matrix" not in self.compute:
+                self.drop_columns += list(_COV_NAMES)
+        cloud = self._get_cloud()
+        eig = cloud.stats(eig=True).eig
+        self.df = self.df.reset_index(drop=True)
+        for k, name in enumerate(("Eigenvalue_1", "Eigenvalue_2", "Eigenvalue_3")):
+            self.df[name] = self._per_point(eig[k])
+        self.eigenvalues = True
+        self._cloud_sig = self._signature()
+
+    @trace
+    @timeit
+    def compute_geometric_features(self):
+        """The 8 eigenvalue features plus the Eigenvalue_{1,2,3}_n columns the reference leaves behind
+        (vapc.py:1094-1146)."""
+        if self.eigenvalues is False:
+            self.compute_eigenvalues()
+            if "eigenvalues" not in self.compute:
+                self.drop_columns += ["Eigenvalue_1", "Eigenvalue_2", "Eigenvalue_3"]
+        cloud = self._get_cloud()
+        st = cloud.stats(eig_n=True, feat=True)
+        for k, name in enumerate(("Eigenvalue_1_n", "Eigenvalue_2_n", "Eigenvalue_3_n")):
+            self.df[name] = self._per_point(st.eig_n[k])
+        for k, name in enumerate(E.FEATURE_NAMES):
+            self.df[name] = self._per_point(st.feat[k])
+        self.geometric_features = True
+        self._resign()
+
+    # ------------------------------------------------------------------------------------
+    @trace
+    @timeit
+    def reduce_to_voxels(self):
+        """One row per voxel at the centre / corner / centroid / closest point(s) (vapc.py:1150-1210)."""
+        if self.return_at == "center_of_voxel":
+            if self.center_of_voxel is False or not hasattr(self.df, "center_x"):
+                self.compute_center_of_voxel()
+                self.drop_columns += ["center_x", "center_y", "center_z"]
+            self.new_column_names.update({"X": "center_x", "Y": "center_y", "Z": "center_z"})
+        elif self.return_at == "corner_of_voxel":
+            if self.corner_of_voxel is False:
+                self.compute_corner_of_voxel()
+                self.drop_columns += ["corner_x", "corner_y", "corner_z"]
+            self.new_column_names.update({"X": "corner_x", "Y": "corner_y", "Z": "corner_z"})
+        elif self.return_at == "center_of_gravity":
+            if not self.center_of_gravity:
+                self.compute_center_of_gravity()
+                self.drop_columns += ["cog_x", "cog_y", "cog_z"]
+            self.new_column_names.update({"X": "cog_x", "Y": "cog_y", "Z": "cog_z"})
+        elif self.return_at == "closest_to_center_of_gravity":
+            if not self.center_of_gravity:
+                self.compute_center_of_gravity()
+                self.drop_columns += ["cog_x", "cog_y", "cog_z"]
+            if not self.closest_to_center_of_gravity:
+                self.compute_closest_to_center_of_gravity()
+                self.drop_columns += ["min_distance"]
+            if self.closest_ties == "first" and getattr(self, "_closest_argmin", None) is not None:
+                rows = np.sort(self._closest_argmin.cpu().numpy())
+                self.df = self.df.iloc[rows]
+            else:
+                self.df = self.df[self.df["distance"] == self.df["min_distance"]]
+        else:
+            print(f"Voxels cannot be reduced to {self.return_at},\n \
+                    try 'center_of_gravity', 'center_of_voxel', 'closest_to_center_of_gravity', or 'corner_of_voxel'")
+            return
+        if self.return_at != "closest_to_center_of_gravity":
+            # one row per voxel: its first point (what drop_duplicates(subset=XYZ) keeps, vapc.py:1208);
+            # picking those V rows first is equivalent and avoids formatting N rows
+            cloud = self._get_cloud() if self._cloud is not None and len(self.df) == self._cloud.n else None
+            if cloud is not None:
+                rows = np.sort(_u32(cloud.first_idx).cpu().numpy())
+                self.df = self.df.iloc[rows].copy()
+        for col_name in self.new_column_names.keys():
+            self.df[col_name] = self.df[self.new_column_names[col_name]]
+        self.df = self.df.drop(set(self.drop_columns), axis=1)
+        # output formatting on the reduced frame, exactly as the reference does it (vapc.py:1208-1209)
+        self.df = self.df.drop_duplicates(subset=["X", "Y", "Z"])
+        self.df = self.df.groupby(["X", "Y", "Z"], as_index=False).median(numeric_only=True)
+        self.reduced = True
+        self._cloud = None
+
+    @trace
+    @timeit
+    def filter_attributes(self, filter_attribute: str, min_max_eq: str, filter_value):
+        """Row filter == != > >= < <= (long or symbol names, case-insensitive) (vapc.py:1214-1270)."""
+        valid_strings = ["equal_to", "==", "not_equal_to", "!=", "greater_than", ">", "greater_than_or_equal_to", ">=",
+                         "less_than", "<", "less_than_or_equal_to", "<="]
+        op = min_max_eq.lower()
+        col = self.df[filter_attribute]  # KeyError on a missing column, as in the reference
+        if op in ["equal_to", "=="]:
+            self.df = self.df[col == filter_value]
+        elif op in ["not_equal_to", "!="]:
+            self.df = self.df[col != filter_value]
+        elif op in ["greater_than", ">"]:
+            self.df = self.df[col > filter_value]
+        elif op in ["greater_than_or_equal_to", ">="]:
+            self.df = self.df[col >= filter_value]
+        elif op in ["less_than", "<"]:
+            self.df = self.df[col < filter_value]
+        elif op in ["less_than_or_equal_to", "<="]:
+            self.df = self.df[col <= filter_value]
+        else:
+            raise ValueError(f"Filter invalid, use only one of the following:\n\n{', '.join(valid_strings)}.")
+        self._cloud = None
+
+    def compute_mode_count(self, attribute: str, percentage: float):
+        """Convenience alias named by the north_star: the statistic string "mode_count,<p>" of the
+        reference (vapc.py:413-433) for one attribute."""
+        saved = self.attributes
+        self.attributes = {attribute: [f"mode_count,{percentage}"]}
+        self.attributes_up_to_data = True
+        try:
+            self.compute_requested_statistics_per_attributes()
+        finally:
+            self.attributes = saved
+
+    def compute_clusters(self, cluster_distance, cluster_by=None):
+        """KD-tree region growing of the reference (vapc.py:1274-1357) — not part of the voxel-statistics
+        hot path this package rebuilds (out of scope)."""
+        raise NotImplementedError("compute_clusters is outside the voxelisation / per-voxel statistics path rebuilt by vapc_b200")
