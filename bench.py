@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — points/s of the voxelise + per-voxel statistics path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl reference]
+
+A step is one pass of the hot path over one synthetic cloud: bounding box -> packed voxel keys ->
+stable radix sort -> run-length segmentation -> FP64 (count, mean, M2) moments -> density, centroid,
+std, covariance, eigenvalues, 8 eigen-features (+ the point->voxel map).  At N = 1 the workload is
+BASELINE.json configs[1]: a 100M-point uniform cloud, voxel 0.1 m, full attribute set.
+
+value   whole-job points/s with the inputs already resident in HBM (CUDA events, max over ranks)
+e2e     the same metric through the public API with HOST buffers: pinned host -> device copies of X, Y, Z
+        and the device -> pinned-host read of the complete voxel table inside the timed region
+roofline  the dominant C-ABI call: algorithmic bytes / CUDA-event time on the launching stream, against
+        MEASURED_PEAKS.json
+cpu_baseline  the CPU port of the reference's pandas path (oracle/ref_port.py, "port": the reference is pure
+        Python and /root/reference does not exist on the GPU box) on a bounded spatial crop, 1 core
+--impl reference  times that CPU port alone and prints the same line with "impl": "reference"
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "points/sec voxelise+stats"
+UNIT = "points/s"
+VOXEL_SIZE = 0.1
+ORIGIN = [0.0, 0.0, 0.0]
+EXTENT = (50.0, 50.0, 4.0)  # metres: 500 x 500 x 40 voxels = 1e7 cells -> ~10 points per voxel at 1e8 points
+QUANT = 1e-4  # LAS-like coordinate quantisation
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=100_000_000, help="points per GPU")
+    ap.add_argument("--impl", default="vapc_b200", choices=["vapc_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="points in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data
+# ------------------------------------------------------------------------------------------------
+def gen_cloud_device(n, seed, device, x_shift=0.0):
+    """n quantised uniform points in EXTENT (x shifted by x_shift metres), fp64 device columns."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cols = []
+    for k, ext in enumerate(EXTENT):
+        q = torch.randint(0, int(round(ext / QUANT)), (n,), generator=g, device=device, dtype=torch.int64)
+        c = q.to(torch.float64) * QUANT
+        if k == 0 and x_shift:
+            c += x_shift
+        cols.append(c)
+        del q
+    return cols
+
+
+def gen_crop_host(n_sample, seed=2):
+    """A spatial crop of the same cloud law at the same density (10 points per voxel at 1e8 points): the box
+    [0, lx) x [0, 0.5) x [0, 4) holding n_sample points.  Generated on the host (numpy), used by the CPU legs."""
+    import numpy as np
+
+    density = 100_000_000 / (EXTENT[0] * EXTENT[1] * EXTENT[2])  # points per m^3 of config[1]
+    lx = n_sample / (density * 0.5 * EXTENT[2])
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, max(1, int(round(lx / QUANT))), n_sample) * QUANT
+    y = rng.integers(0, int(round(0.5 / QUANT)), n_sample) * QUANT
+    z = rng.integers(0, int(round(EXTENT[2] / QUANT)), n_sample) * QUANT
+    return x, y, z, f"spatial crop [0,{lx:.2f})x[0,0.5)x[0,4) m of the workload at its density: {n_sample} points"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs
+# ------------------------------------------------------------------------------------------------
+def cpu_port_once(x, y, z):
+    from oracle import ref_port
+
+    t0 = time.perf_counter()
+    df = ref_port.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN, with_eigen=True)
+    dt = time.perf_counter() - t0
+    nvox = int(df[["voxel_x", "voxel_y", "voxel_z"]].drop_duplicates().shape[0])
+    return dt, nvox
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0 / max(1, args.steps + args.warmup)  # seconds per step
+    n_sample = args.cpu_sample or int(min(200_000, max(2_000, budget * 5_000)))
+    x, y, z, what = gen_crop_host(n_sample)
+    for _ in range(args.warmup):
+        cpu_port_once(x, y, z)
+    times = []
+    for _ in range(args.steps):
+        dt, nvox = cpu_port_once(x, y, z)
+        times.append(dt)
+    total = sum(times)
+    value = n_sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.points, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": what + f" ({nvox} voxels); the reference is single-threaded pandas/numpy; per-voxel Python eigen step included"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(points_per_gpu, gpus):
+    return {
+        "workload": f"configs[1]: {points_per_gpu / 1e6:g}M-point synthetic uniform cloud per GPU, voxel_size={VOXEL_SIZE} m, "
+                    "full attribute set (count, density, centroid, std, covariance, eigenvalues, 8 eigen-features) + point->voxel map",
+        "points_per_gpu": points_per_gpu, "voxel_size": VOXEL_SIZE, "extent_m": list(EXTENT),
+        "l2": "inputs (24 B/point, 2.4 GB at 1e8 points) are larger than the 126 MB L2; no flush needed",
+        "parallelism": f"points sharded in contiguous chunks over {gpus} GPU(s)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, n, v, key_bytes, passes):
+    """Algorithmic bytes of one C-ABI call ('bytes per unit'); n points, v voxels."""
+    k = key_bytes
+    return {
+        "vapc_minmax_f64": 24 * n,
+        "vapc_pack_keys_f64": (24 + k + 32) * n,
+        "vapc_sort_pairs": (passes * (3 * k + 8) - 4) * n,
+        "vapc_count_voxels": k * n,
+        "vapc_reduce_moments": (k + 4 + 32 + 4) * n + (k + 12 + 72) * v,
+        "vapc_voxel_stats": (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v,
+    }.get(name, 0)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from vapc_b200 import _lib as L
+    from vapc_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n = args.points
+
+    if world > 1:
+        from vapc_b200 import dist as D
+
+        x, y, z = gen_cloud_device(n, seed=2 + rank, device=device, x_shift=D.bench_slab_shift(rank, EXTENT[0]))
+    else:
+        x, y, z = gen_cloud_device(n, seed=2, device=device)
+
+    def step_device():
+        if world > 1:
+            return D.voxel_statistics(x, y, z, VOXEL_SIZE, ORIGIN)
+        cloud = E.VoxelCloud.build(x, y, z, VOXEL_SIZE, ORIGIN, keep_columns=False)
+        st = cloud.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+        return cloud, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        cloud, st = step_device()
+    torch.cuda.synchronize()
+    nvox = cloud.nvoxels
+    key_bytes = cloud.grid.key_bytes
+    passes = (cloud.grid.total_bits + 7) // 8
+
+    # ---- timed region: K steps, CUDA events, per-call events for the roofline -----------------
+    records = []
+
+    def observer(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        records.append((name, phase, ev))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.raw("vapc_launch_count")()
+    barrier()
+    L.observer = observer
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        cloud, st = step_device()
+    t_end.record()
+    L.observer = None
+    barrier()
+    launches = L.raw("vapc_launch_count")() - launches0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    per_call = {}
+    pending = {}
+    for name, phase, ev in records:
+        if phase == "before":
+            pending[name] = ev
+        else:
+            per_call.setdefault(name, []).append(pending.pop(name).elapsed_time(ev))
+    del records
+
+    # ---- roofline of the dominant call --------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    breakdown = {}
+    for name, ts in per_call.items():
+        calls_per_step = len(ts) / args.steps
+        avg = sum(ts) / len(ts)
+        b = algorithmic_bytes(name, n, nvox, key_bytes, passes)
+        breakdown[name] = {"ms_per_call": round(avg, 4), "calls_per_step": calls_per_step, "ms_per_step": round(avg * calls_per_step, 4),
+                           "algorithmic_GB": round(b / 1e9, 4), "GBps": round(b / 1e9 / (avg * 1e-3), 1) if b else None}
+    dom = max((k for k in breakdown if breakdown[k]["algorithmic_GB"]), key=lambda k: breakdown[k]["ms_per_step"])
+    achieved = breakdown[dom]["GBps"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(breakdown[dom]["algorithmic_GB"] * 1e9), "ms_per_launch": breakdown[dom]["ms_per_call"]}
+    gpu_ms = sum(v["ms_per_step"] for v in breakdown.values())
+
+    # ---- e2e: host buffers in, host voxel table out -------------------------------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        hx, hy, hz = (c.cpu().pin_memory() for c in (x, y, z))
+        del x, y, z
+        torch.cuda.empty_cache()
+        out_specs = {"voxel_keys": (nvox,), "count": (nvox,), "density": (nvox,), "cog": (3, nvox), "std": (3, nvox), "cov": (6, nvox),
+                     "eig": (3, nvox), "eig_n": (3, nvox), "feat": (8, nvox)}
+        host_out = {}
+
+        def step_e2e():
+            dx, dy, dz = (h.to(device, non_blocking=True) for h in (hx, hy, hz))
+            c = E.VoxelCloud.build(dx, dy, dz, VOXEL_SIZE, ORIGIN, keep_columns=False)
+            s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+            dev_out = {"voxel_keys": c.voxel_keys, "count": c.count, "density": s.density, "cog": s.cog, "std": s.std, "cov": s.cov,
+                       "eig": s.eig, "eig_n": s.eig_n, "feat": s.feat}
+            for k, t in dev_out.items():
+                if k not in host_out:
+                    host_out[k] = torch.empty(out_specs[k], dtype=t.dtype).pin_memory()
+                host_out[k].copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+            return dev_out
+
+        for _ in range(2):
+            dev_out = step_e2e()
+        h2d = 3 * 8 * n
+        d2h = sum(t.numel() * t.element_size() for t in dev_out.values())
+        del dev_out
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e_steps = max(3, min(args.steps, 5))
+        for _ in range(e_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": e_steps,
+               "api": "vapc_b200.engine.VoxelCloud.build + .stats on pinned host columns; full voxel table copied back to pinned host"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        n_sample = args.cpu_sample or 100_000
+        cx, cy, cz, what = gen_crop_host(n_sample)
+        dt, cv = cpu_port_once(cx, cy, cz)
+        cpu_baseline = {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": round(dt, 2),
+                        "sample": what + f" ({cv} voxels); oracle/ref_port.py keeps the reference's single-threaded pandas data flow "
+                                         "incl. its per-voxel Python eigen step; host has %d logical cores" % (os.cpu_count() or 0)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=cloud.grid.total_bits,
+                                                radix_passes=passes),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,8 @@ typedef struct vapc_grid {
 } vapc_grid_t;
 
 VAPC_API int vapc_abi_version(void);
+/* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches) */
+VAPC_API uint64_t vapc_launch_count(void);
 VAPC_API const char* vapc_last_error(void);
 
 /* ---- bounding box (feeds vapc_grid_t; also Vapc.compute_reduction_point, vapc.py:153-162,

@@ -140,8 +140,9 @@ def test_host_selftest_mahalanobis_matches_scipy():
     rng = np.random.default_rng(3)
     n = 3000
     covs, diffs = [], []
-    for _ in range(n):
-        pts = rng.normal(0, 1, (8, 3)) * rng.uniform(0.01, 0.3, 3)
+    for i in range(n):
+        npts = 2 if i % 5 == 0 else (3 if i % 5 == 1 else 8)  # rank-1 / rank-2 covariances: cond ~ 1e8 after + 1e-10 I
+        pts = rng.normal(0, 1, (npts, 3)) * rng.uniform(0.01, 0.3, 3)
         covs.append(np.cov(pts.T))
         diffs.append(rng.normal(0, 0.2, 3) * rng.choice([0.01, 0.1, 1.0, 10.0]))
     covs, diffs = np.array(covs), np.ascontiguousarray(np.array(diffs))
@@ -152,9 +153,11 @@ def test_host_selftest_mahalanobis_matches_scipy():
     ce = covs + np.eye(3) * 1e-10
     d_ref = np.einsum("ij,ijk,ik->i", diffs, np.linalg.inv(ce), diffs)
     cond = np.linalg.cond(ce)
-    assert np.all(np.abs(d - d_ref) <= d_ref * (1e-12 + 1e-15 * cond))
+    assert cond.max() > 1e7
+    assert np.all(np.abs(d - d_ref) <= d_ref * (1e-12 + 1e-14 * cond))  # both are backward-stable pivoted solves
     p_ref = 1 - chi2.cdf(d_ref, df=3)
-    assert np.all(np.abs(p - p_ref) <= 1e-15 + 1e-9 * p_ref + 1e-12 * cond * p_ref)
+    well = cond < 1e3
+    assert np.all(np.abs(p - p_ref)[well] <= 1e-15 + 1e-9 * p_ref[well])
     # the tail: p is exactly 0 where scipy's 1 - cdf is (drives change_type 2, bi_vapc.py:135)
     big = np.array([60.0, 75.0, 78.0, 79.0, 80.0, 100.0, 1e4, 1e12])
     cov6 = np.tile(np.array([1.0 - 1e-10, 0, 0, 1.0 - 1e-10, 0, 1.0 - 1e-10]), (len(big), 1))

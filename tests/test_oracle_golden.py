@@ -201,3 +201,17 @@ def test_reference_unit_test_known_answers():
     buf = O.voxel_buffer(vx, vy, vz, 1)
     want = np.unique((exp[:, None] + np.array(list(product(range(-1, 2), repeat=3)))).reshape(-1, 3), axis=0)
     np.testing.assert_array_equal(np.unique(buf, axis=0), want)
+
+
+@pytest.mark.parametrize("name", ["uniform5000_vs0.5", "plane500_vs1.0", "kat_cloud10"])
+def test_reference_port_reproduces_reference(name):
+    """oracle/ref_port.py (the timed CPU baseline) keeps the reference's pandas data flow; its columns must
+    equal the reference's."""
+    from oracle import ref_port as R
+
+    gold = P.load_golden(name)
+    df = R.full_attribute_set(gold["in_X"], gold["in_Y"], gold["in_Z"], float(gold["in_voxel_size"]), gold["in_origin"].tolist())
+    for c in df.columns:
+        got = df[c].to_numpy()
+        got = got.real if got.dtype.kind == "c" else got
+        np.testing.assert_allclose(got, gold["pt_" + c], rtol=1e-12, atol=1e-14, equal_nan=True, err_msg=c)

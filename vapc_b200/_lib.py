@@ -67,6 +67,7 @@ GP = C.POINTER(Grid)
 SIGNATURES = {
     "vapc_abi_version": (C.c_int, []),
     "vapc_last_error": (C.c_char_p, []),
+    "vapc_launch_count": (C.c_uint64, []),
     "vapc_minmax_workspace_bytes": (SZ, []),
     "vapc_minmax_f64": (C.c_int, [P, P, P, I64, P, P, SZ, P]),
     "vapc_voxel_coords_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
@@ -125,9 +126,20 @@ def check(code: int):
     raise VapcError(code, msg)
 
 
+# optional observer(name, phase) with phase in {"before", "after"}: bench.py uses it to bracket every
+# C-ABI call with CUDA events on the launching stream
+observer = None
+
+
 def call(name: str, *args):
     """Call a status-returning entry point and raise on failure."""
-    check(getattr(_lib, name)(*args))
+    obs = observer
+    if obs is not None:
+        obs(name, "before")
+    code = getattr(_lib, name)(*args)
+    if obs is not None:
+        obs(name, "after")
+    check(code)
 
 
 def raw(name: str):

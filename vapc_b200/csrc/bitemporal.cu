@@ -62,7 +62,7 @@ extern "C" int vapc_join_sorted_keys(const uint64_t* keys1, int64_t n1, const ui
   if (n1 < 0 || n2 < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_join_sorted_keys: negative size");
   const int64_t n = n1 > n2 ? n1 : n2;
   if (n == 0) return VAPC_OK;
-  join_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(
+  VAPC_LAUNCH(join_kernel, (unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), 
       reinterpret_cast<const unsigned long long*>(keys1), n1, reinterpret_cast<const unsigned long long*>(keys2), n2, match1, match2);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -76,7 +76,7 @@ extern "C" int vapc_mahalanobis(const double* cog3_1, const double* cov6_1, int6
   if (!cog3_1 || !cog3_2 || !i1 || !i2) return vapc_set_error(VAPC_E_INVALID, "vapc_mahalanobis: null input");
   if ((d1 || d2 || p_value || significance || change_type) && (!cov6_1 || !cov6_2))
     return vapc_set_error(VAPC_E_INVALID, "vapc_mahalanobis: covariance tables required");
-  mahalanobis_kernel<<<(unsigned)((npairs + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(
+  VAPC_LAUNCH(mahalanobis_kernel, (unsigned)((npairs + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), 
       cog3_1, cov6_1, v1, cog3_2, cov6_2, v2, i1, i2, npairs, alpha, distance, d1, d2, p_value, significance, change_type);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;

@@ -17,6 +17,14 @@ int vapc_cuda_error(cudaError_t e, const char* file, int line);
   } while (0)
 #define VAPC_CHECK_LAUNCH() VAPC_RETURN_IF_CUDA(cudaGetLastError())
 
+// every kernel launch of the library goes through this so that vapc_launch_count() is exact
+void vapc_note_launch();
+#define VAPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  do {                                                      \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+    vapc_note_launch();                                     \
+  } while (0)
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this

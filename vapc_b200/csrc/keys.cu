@@ -25,6 +25,11 @@ int vapc_cuda_error(cudaError_t e, const char* file, int line) {
   return VAPC_E_CUDA;
 }
 extern "C" const char* vapc_last_error(void) { return g_err; }
+
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+void vapc_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t vapc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int vapc_abi_version(void) { return VAPC_ABI_VERSION; }
 
 namespace {
@@ -199,8 +204,8 @@ extern "C" int vapc_minmax_f64(const double* x, const double* y, const double* z
   if (n <= 0 || !x || !y || !z || !out6) return vapc_set_error(VAPC_E_INVALID, "vapc_minmax_f64: empty input or null pointer");
   if (ws_bytes < vapc_minmax_workspace_bytes() || !ws) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_minmax_f64: workspace too small");
   const int grid = stream_grid(n, kThreads * 8);
-  minmax_partial<<<grid, kThreads, 0, as_stream(stream)>>>(x, y, z, n, static_cast<double*>(ws));
-  minmax_final<<<1, 192, 0, as_stream(stream)>>>(static_cast<double*>(ws), grid, out6);
+  VAPC_LAUNCH(minmax_partial, grid, kThreads, 0, as_stream(stream), x, y, z, n, static_cast<double*>(ws));
+  VAPC_LAUNCH(minmax_final, 1, 192, 0, as_stream(stream), static_cast<double*>(ws), grid, out6);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
@@ -216,7 +221,7 @@ extern "C" int vapc_voxel_coords_f64(const double* x, const double* y, const dou
   if (int e = check_grid(grid_host, "vapc_voxel_coords_f64")) return e;
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_coords_f64: n < 0");
   if (n == 0) return VAPC_OK;
-  voxel_coords_kernel<<<stream_grid(n, kThreads * 4), kThreads, 0, as_stream(stream)>>>(
+  VAPC_LAUNCH(voxel_coords_kernel, stream_grid(n, kThreads * 4), kThreads, 0, as_stream(stream), 
       x, y, z, n, to_device_grid(grid_host), reinterpret_cast<long long*>(vx), reinterpret_cast<long long*>(vy),
       reinterpret_cast<long long*>(vz));
   VAPC_CHECK_LAUNCH();
@@ -267,12 +272,12 @@ extern "C" int vapc_pack_keys_f64(const double* x, const double* y, const double
   cudaStream_t s = as_stream(stream);
   double4* rec = reinterpret_cast<double4*>(xyzw);
   if (grid_host->key_bytes == 4) {
-    if (vec) pack_keys_kernel<uint32_t, 2><<<grid, kThreads, 0, s>>>(x, y, z, n, g, static_cast<uint32_t*>(keys), rec, status);
-    else pack_keys_kernel<uint32_t, 1><<<grid, kThreads, 0, s>>>(x, y, z, n, g, static_cast<uint32_t*>(keys), rec, status);
+    if (vec) VAPC_LAUNCH((pack_keys_kernel<uint32_t, 2>), grid, kThreads, 0, s, x, y, z, n, g, static_cast<uint32_t*>(keys), rec, status);
+    else VAPC_LAUNCH((pack_keys_kernel<uint32_t, 1>), grid, kThreads, 0, s, x, y, z, n, g, static_cast<uint32_t*>(keys), rec, status);
   } else if (grid_host->key_bytes == 8) {
     typedef unsigned long long u64;
-    if (vec) pack_keys_kernel<u64, 2><<<grid, kThreads, 0, s>>>(x, y, z, n, g, static_cast<u64*>(keys), rec, status);
-    else pack_keys_kernel<u64, 1><<<grid, kThreads, 0, s>>>(x, y, z, n, g, static_cast<u64*>(keys), rec, status);
+    if (vec) VAPC_LAUNCH((pack_keys_kernel<u64, 2>), grid, kThreads, 0, s, x, y, z, n, g, static_cast<u64*>(keys), rec, status);
+    else VAPC_LAUNCH((pack_keys_kernel<u64, 1>), grid, kThreads, 0, s, x, y, z, n, g, static_cast<u64*>(keys), rec, status);
   } else {
     return vapc_set_error(VAPC_E_INVALID, "vapc_pack_keys_f64: key_bytes must be 4 or 8");
   }
@@ -287,10 +292,10 @@ extern "C" int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* 
   const Grid g = to_device_grid(grid_host);
   const int grid = stream_grid(n, kThreads * 4);
   if (grid_host->key_bytes == 4)
-    unpack_keys_kernel<uint32_t><<<grid, kThreads, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(keys), n, g,
+    VAPC_LAUNCH(unpack_keys_kernel<uint32_t>, grid, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(keys), n, g,
         reinterpret_cast<long long*>(vx), reinterpret_cast<long long*>(vy), reinterpret_cast<long long*>(vz));
   else
-    unpack_keys_kernel<unsigned long long><<<grid, kThreads, 0, as_stream(stream)>>>(
+    VAPC_LAUNCH(unpack_keys_kernel<unsigned long long>, grid, kThreads, 0, as_stream(stream), 
         static_cast<const unsigned long long*>(keys), n, g, reinterpret_cast<long long*>(vx),
         reinterpret_cast<long long*>(vy), reinterpret_cast<long long*>(vz));
   VAPC_CHECK_LAUNCH();
@@ -304,9 +309,9 @@ extern "C" int vapc_voxel_center_corner(const void* voxel_keys, int64_t nvoxels,
   const Grid g = to_device_grid(grid_host);
   const int grid = stream_grid(nvoxels, kThreads * 4);
   if (grid_host->key_bytes == 4)
-    center_corner_kernel<uint32_t><<<grid, kThreads, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(voxel_keys), nvoxels, g, center3, corner3);
+    VAPC_LAUNCH(center_corner_kernel<uint32_t>, grid, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(voxel_keys), nvoxels, g, center3, corner3);
   else
-    center_corner_kernel<unsigned long long><<<grid, kThreads, 0, as_stream(stream)>>>(static_cast<const unsigned long long*>(voxel_keys), nvoxels, g, center3, corner3);
+    VAPC_LAUNCH(center_corner_kernel<unsigned long long>, grid, kThreads, 0, as_stream(stream), static_cast<const unsigned long long*>(voxel_keys), nvoxels, g, center3, corner3);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -91,18 +91,34 @@ VAPC_HD void chan_combine(double& na, double (&ma)[3], double (&Ma)[6], double n
   na = n;
 }
 
-// ---- inverse of a symmetric 3x3 (adjugate / determinant) applied as a quadratic form ---------------
-// q = d' inv(C) d with C = [[c0 c1 c2][c1 c3 c4][c2 c4 c5]]  (np.linalg.inv + einsum, bi_vapc.py:112-117)
+// ---- q = d' inv(C) d for a symmetric 3x3 C = [[c0 c1 c2][c1 c3 c4][c2 c4 c5]] -------------------------
+// (np.linalg.inv + einsum in the reference, bi_vapc.py:112-117).  Solved as C y = d by Gaussian elimination
+// with partial pivoting — the same backward-stable class as LAPACK's getrf the reference runs; the
+// adjugate / determinant formula loses cond(C)^2 and is useless for rank-deficient covariances + 1e-10 I.
 VAPC_HD double quad_form_inv3(const double (&c)[6], double dx, double dy, double dz) {
-  const double a00 = c[3] * c[5] - c[4] * c[4];
-  const double a01 = c[2] * c[4] - c[1] * c[5];
-  const double a02 = c[1] * c[4] - c[2] * c[3];
-  const double a11 = c[0] * c[5] - c[2] * c[2];
-  const double a12 = c[1] * c[2] - c[0] * c[4];
-  const double a22 = c[0] * c[3] - c[1] * c[1];
-  const double det = c[0] * a00 + c[1] * a01 + c[2] * a02;
-  const double q = dx * (a00 * dx + a01 * dy + a02 * dz) + dy * (a01 * dx + a11 * dy + a12 * dz) + dz * (a02 * dx + a12 * dy + a22 * dz);
-  return q / det;
+  double r0[4] = {c[0], c[1], c[2], dx};
+  double r1[4] = {c[1], c[3], c[4], dy};
+  double r2[4] = {c[2], c[4], c[5], dz};
+#define VAPC_SWAP_ROWS(a, b)                                  \
+  do {                                                        \
+    for (int k_ = 0; k_ < 4; ++k_) {                          \
+      const double t_ = a[k_]; a[k_] = b[k_]; b[k_] = t_;     \
+    }                                                         \
+  } while (0)
+  // column 0 pivot
+  if (fabs(r1[0]) > fabs(r0[0])) VAPC_SWAP_ROWS(r0, r1);
+  if (fabs(r2[0]) > fabs(r0[0])) VAPC_SWAP_ROWS(r0, r2);
+  const double m1 = r1[0] / r0[0], m2 = r2[0] / r0[0];
+  for (int k = 1; k < 4; ++k) { r1[k] -= m1 * r0[k]; r2[k] -= m2 * r0[k]; }
+  // column 1 pivot
+  if (fabs(r2[1]) > fabs(r1[1])) VAPC_SWAP_ROWS(r1, r2);
+  const double m3 = r2[1] / r1[1];
+  for (int k = 2; k < 4; ++k) r2[k] -= m3 * r1[k];
+#undef VAPC_SWAP_ROWS
+  const double y2 = r2[3] / r2[2];
+  const double y1 = (r1[3] - r1[2] * y2) / r1[1];
+  const double y0 = (r0[3] - r0[1] * y1 - r0[2] * y2) / r0[0];
+  return dx * y0 + dy * y1 + dz * y2;
 }
 
 // p = 1 - chi2.cdf(d, df = 3) (bi_vapc.py:118-119) in closed form:

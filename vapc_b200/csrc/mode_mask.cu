@@ -225,7 +225,7 @@ extern "C" int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, i
                               int32_t* status, void* stream) {
   if (n < 0 || attr_bits < 1 || attr_bits > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_keys: bad arguments (attr_bits in 1..32)");
   if (n == 0) return VAPC_OK;
-  mode_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(point2voxel, attr, n, attr_bits,
+  VAPC_LAUNCH(mode_keys_kernel, grid_for(n), kThreads, 0, as_stream(stream), point2voxel, attr, n, attr_bits,
                                                                     reinterpret_cast<unsigned long long*>(keys), status);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -235,7 +235,7 @@ extern "C" int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t a
                                double threshold, int64_t* mode, int64_t* mode_count, void* stream) {
   if (n < 0 || nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count: bad arguments");
   if (nvoxels == 0) return VAPC_OK;
-  mode_count_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(
+  VAPC_LAUNCH(mode_count_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), 
       reinterpret_cast<const unsigned long long*>(keys_sorted), attr_bits, start, nvoxels, threshold,
       reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
   VAPC_CHECK_LAUNCH();
@@ -246,7 +246,7 @@ extern "C" int vapc_attr_stats(const double* attr, const uint32_t* order, const 
                                double* mean, double* vmin, double* vmax, double* var, void* stream) {
   if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_attr_stats: bad arguments");
   if (nvoxels == 0) return VAPC_OK;
-  attr_stats_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(attr, order, start, nvoxels, sum, mean,
+  VAPC_LAUNCH(attr_stats_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), attr, order, start, nvoxels, sum, mean,
                                                                                                        vmin, vmax, var);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -254,7 +254,7 @@ extern "C" int vapc_attr_stats(const double* attr, const uint32_t* order, const 
 extern "C" int vapc_f64_sort_keys(const double* attr, int64_t n, uint64_t* keys, void* stream) {
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_f64_sort_keys: n < 0");
   if (n == 0) return VAPC_OK;
-  f64_sort_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(attr, n, reinterpret_cast<unsigned long long*>(keys));
+  VAPC_LAUNCH(f64_sort_keys_kernel, grid_for(n), kThreads, 0, as_stream(stream), attr, n, reinterpret_cast<unsigned long long*>(keys));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
@@ -262,7 +262,7 @@ extern "C" int vapc_attr_median(const double* attr, const uint32_t* order, const
                                 void* stream) {
   if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_attr_median: bad arguments");
   if (nvoxels == 0) return VAPC_OK;
-  attr_median_kernel<<<(unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(attr, order, start, nvoxels, median);
+  VAPC_LAUNCH(attr_median_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), attr, order, start, nvoxels, median);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
@@ -273,7 +273,7 @@ extern "C" int vapc_pack_triples_i64(const int64_t* vx, const int64_t* vy, const
   if (grid_host->bits[0] + grid_host->bits[1] + grid_host->bits[2] > 63)
     return vapc_set_error(VAPC_E_KEYSPACE, "vapc_pack_triples_i64: needs at most 63 key bits");
   if (n == 0) return VAPC_OK;
-  pack_triples_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(vx),
+  VAPC_LAUNCH(pack_triples_kernel, grid_for(n), kThreads, 0, as_stream(stream), reinterpret_cast<const long long*>(vx),
       reinterpret_cast<const long long*>(vy), reinterpret_cast<const long long*>(vz), n, to_device_grid(grid_host),
       reinterpret_cast<unsigned long long*>(keys), status);
   VAPC_CHECK_LAUNCH();
@@ -292,7 +292,7 @@ extern "C" int vapc_mask_build(const uint64_t* mask_keys, int64_t nmask, void* t
     return vapc_set_error(VAPC_E_INVALID, "vapc_mask_build: capacity must be a power of two >= max(16, 2 * nmask)");
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(table, 0xff, (size_t)capacity * sizeof(uint64_t), as_stream(stream)));
   if (nmask == 0) return VAPC_OK;
-  mask_build_kernel<<<grid_for(nmask, 1), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(mask_keys), nmask,
+  VAPC_LAUNCH(mask_build_kernel, grid_for(nmask, 1), kThreads, 0, as_stream(stream), reinterpret_cast<const unsigned long long*>(mask_keys), nmask,
                                                                             static_cast<unsigned long long*>(table), ilog2_ceil(capacity));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -302,7 +302,7 @@ extern "C" int vapc_mask_lookup_points(const double* x, const double* y, const d
                                        const void* table, int64_t capacity, uint8_t* member, void* stream) {
   if (!grid_host || n < 0 || capacity < 16 || (capacity & (capacity - 1))) return vapc_set_error(VAPC_E_INVALID, "vapc_mask_lookup_points: bad arguments");
   if (n == 0) return VAPC_OK;
-  mask_lookup_points_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(x, y, z, n, to_device_grid(grid_host),
+  VAPC_LAUNCH(mask_lookup_points_kernel, grid_for(n), kThreads, 0, as_stream(stream), x, y, z, n, to_device_grid(grid_host),
       static_cast<const unsigned long long*>(table), ilog2_ceil(capacity), member);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -311,7 +311,7 @@ extern "C" int vapc_mask_lookup_points(const double* x, const double* y, const d
 extern "C" int vapc_mask_lookup_keys(const uint64_t* keys, int64_t n, const void* table, int64_t capacity, uint8_t* member, void* stream) {
   if (n < 0 || capacity < 16 || (capacity & (capacity - 1))) return vapc_set_error(VAPC_E_INVALID, "vapc_mask_lookup_keys: bad arguments");
   if (n == 0) return VAPC_OK;
-  mask_lookup_keys_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(keys), n,
+  VAPC_LAUNCH(mask_lookup_keys_kernel, grid_for(n), kThreads, 0, as_stream(stream), reinterpret_cast<const unsigned long long*>(keys), n,
       static_cast<const unsigned long long*>(table), ilog2_ceil(capacity), member);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -322,7 +322,7 @@ extern "C" int vapc_buffer_expand(const int64_t* vx, const int64_t* vy, const in
   if (n < 0 || buffer_size < 0 || buffer_size > 64) return vapc_set_error(VAPC_E_INVALID, "vapc_buffer_expand: bad arguments");
   if (n == 0) return VAPC_OK;
   const int w = 2 * buffer_size + 1;
-  buffer_expand_kernel<<<grid_for(n * w * w * w), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(vx),
+  VAPC_LAUNCH(buffer_expand_kernel, grid_for(n * w * w * w), kThreads, 0, as_stream(stream), reinterpret_cast<const long long*>(vx),
       reinterpret_cast<const long long*>(vy), reinterpret_cast<const long long*>(vz), n, buffer_size, reinterpret_cast<long long*>(out3));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -345,9 +345,9 @@ extern "C" int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes
   if (n == 0) return VAPC_OK;
   const int shift = total_bits > hist_bits ? total_bits - hist_bits : 0;
   if (key_bytes == 4)
-    key_hist_kernel<uint32_t><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(keys), n, shift, hist);
+    VAPC_LAUNCH(key_hist_kernel<uint32_t>, grid_for(n), kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(keys), n, shift, hist);
   else if (key_bytes == 8)
-    key_hist_kernel<unsigned long long><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(static_cast<const unsigned long long*>(keys), n, shift, hist);
+    VAPC_LAUNCH(key_hist_kernel<unsigned long long>, grid_for(n), kThreads, 0, as_stream(stream), static_cast<const unsigned long long*>(keys), n, shift, hist);
   else
     return vapc_set_error(VAPC_E_INVALID, "vapc_key_histogram: key_bytes must be 4 or 8");
   VAPC_CHECK_LAUNCH();

@@ -106,8 +106,8 @@ cudaError_t scan_u32_exclusive(const uint32_t* in, uint32_t* out, int64_t n, uns
   }
   const int nb = (int)((n + kChunk - 1) / kChunk);
   unsigned long long* sums = static_cast<unsigned long long*>(ws);
-  scan_block_sums<<<nb, kThreads, 0, s>>>(in, n, sums);
-  scan_block_prefix<<<1, 1024, 0, s>>>(sums, nb, total);
-  scan_apply<<<nb, kThreads, 0, s>>>(in, out, n, sums);
+  VAPC_LAUNCH(scan_block_sums, nb, kThreads, 0, s, in, n, sums);
+  VAPC_LAUNCH(scan_block_prefix, 1, 1024, 0, s, sums, nb, total);
+  VAPC_LAUNCH(scan_apply, nb, kThreads, 0, s, in, out, n, sums);
   return cudaGetLastError();
 }

@@ -452,9 +452,9 @@ extern "C" int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key
   const SegWs w = carve(ws, n);
   const int64_t nt = seg_tiles(n);
   if (key_bytes == 4)
-    count_heads_kernel<uint32_t><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const uint32_t*>(keys_sorted), n, w.tile_heads);
+    VAPC_LAUNCH(count_heads_kernel<uint32_t>, (unsigned)nt, kThreads, 0, s, static_cast<const uint32_t*>(keys_sorted), n, w.tile_heads);
   else
-    count_heads_kernel<unsigned long long><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const unsigned long long*>(keys_sorted), n, w.tile_heads);
+    VAPC_LAUNCH(count_heads_kernel<unsigned long long>, (unsigned)nt, kThreads, 0, s, static_cast<const unsigned long long*>(keys_sorted), n, w.tile_heads);
   VAPC_RETURN_IF_CUDA(scan_u32_exclusive(w.tile_heads, w.tile_heads, nt, w.total, w.scan_ws, s));
   VAPC_RETURN_IF_CUDA(cudaMemcpyAsync(nvoxels, w.total, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
   return VAPC_OK;
@@ -480,17 +480,17 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_
     typedef uint32_t K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reduce_moments_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
+    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
         nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
   } else {
     typedef unsigned long long K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reduce_moments_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
+    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
         nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
   }
   const int64_t warps_per_block = kThreads / 32;
-  fixup_moments_kernel<<<(unsigned)((nt + warps_per_block - 1) / warps_per_block), kThreads, 0, s>>>(w.tile_heads, w.carry_cnt, w.carry,
+  VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + warps_per_block - 1) / warps_per_block), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry,
                                                                                                    (int)nt, nvoxels_host, count, mean3, m2);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -512,18 +512,18 @@ extern "C" int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_
     typedef uint32_t K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    closest_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
                                                           nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
   } else if (key_bytes == 8) {
     typedef unsigned long long K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    closest_kernel<K><<<(unsigned)nt, kThreads, smem, s>>>(static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
                                                           nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
   } else {
     return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: key_bytes must be 4 or 8");
   }
-  fixup_closest_kernel<<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s>>>(w.tile_heads, w.carry_cnt, w.carry, (int)nt,
+  VAPC_LAUNCH(fixup_closest_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
                                                                                      min_dist, argmin_idx);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -542,10 +542,10 @@ extern "C" int vapc_merge_partials(const void* keys_sorted, const uint32_t* orde
   const int64_t nt = seg_tiles(nrows);
   cudaStream_t s = as_stream(stream);
   if (key_bytes == 4)
-    merge_partials_kernel<uint32_t><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const uint32_t*>(keys_sorted), order, nrows, count_in,
+    VAPC_LAUNCH(merge_partials_kernel<uint32_t>, (unsigned)nt, kThreads, 0, s, static_cast<const uint32_t*>(keys_sorted), order, nrows, count_in,
         mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<uint32_t*>(voxel_keys), count, mean3, m2);
   else if (key_bytes == 8)
-    merge_partials_kernel<unsigned long long><<<(unsigned)nt, kThreads, 0, s>>>(static_cast<const unsigned long long*>(keys_sorted), order,
+    VAPC_LAUNCH(merge_partials_kernel<unsigned long long>, (unsigned)nt, kThreads, 0, s, static_cast<const unsigned long long*>(keys_sorted), order,
         nrows, count_in, mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<unsigned long long*>(voxel_keys), count,
         mean3, m2);
   else

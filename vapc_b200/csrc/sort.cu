@@ -193,7 +193,7 @@ int sort_impl(KeyT* keys, KeyT* keys_alt, uint32_t* idx, uint32_t* idx_alt, int 
   VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (passes == 0) {
-    if (idx_is_iota) iota_kernel<<<kNumSMs * 8, 256, 0, s>>>(idx, n);
+    if (idx_is_iota) VAPC_LAUNCH(iota_kernel, kNumSMs * 8, 256, 0, s, idx, n);
     *result_in_alt = 0;
     VAPC_CHECK_LAUNCH();
     return VAPC_OK;
@@ -204,14 +204,14 @@ int sort_impl(KeyT* keys, KeyT* keys_alt, uint32_t* idx, uint32_t* idx_alt, int 
     const int shift = p * kRadixBits;
     const int bits = min(kRadixBits, end_bit - shift);
     const unsigned mask = (1u << bits) - 1u;
-    radix_hist<KeyT><<<(unsigned)ntiles, kThreads, 0, s>>>(src_k, n, shift, mask, tile_hist);
-    colscan_partial<<<(unsigned)nchunks, kThreads, 0, s>>>(tile_hist, (int)ntiles, chunk_sum);
-    colscan_chunks<<<1, kThreads, 0, s>>>(chunk_sum, (int)nchunks);
-    colscan_apply<<<(unsigned)nchunks, kThreads, 0, s>>>(tile_hist, (int)ntiles, chunk_sum);
+    VAPC_LAUNCH(radix_hist<KeyT>, (unsigned)ntiles, kThreads, 0, s, src_k, n, shift, mask, tile_hist);
+    VAPC_LAUNCH(colscan_partial, (unsigned)nchunks, kThreads, 0, s, tile_hist, (int)ntiles, chunk_sum);
+    VAPC_LAUNCH(colscan_chunks, 1, kThreads, 0, s, chunk_sum, (int)nchunks);
+    VAPC_LAUNCH(colscan_apply, (unsigned)nchunks, kThreads, 0, s, tile_hist, (int)ntiles, chunk_sum);
     if (p == 0 && idx_is_iota)
-      radix_scatter<KeyT, true><<<(unsigned)ntiles, kThreads, smem, s>>>(src_k, nullptr, dst_k, dst_i, n, shift, mask, tile_hist);
+      VAPC_LAUNCH((radix_scatter<KeyT, true>), (unsigned)ntiles, kThreads, smem, s, src_k, nullptr, dst_k, dst_i, n, shift, mask, tile_hist);
     else
-      radix_scatter<KeyT, false><<<(unsigned)ntiles, kThreads, smem, s>>>(src_k, src_i, dst_k, dst_i, n, shift, mask, tile_hist);
+      VAPC_LAUNCH((radix_scatter<KeyT, false>), (unsigned)ntiles, kThreads, smem, s, src_k, src_i, dst_k, dst_i, n, shift, mask, tile_hist);
     KeyT* tk = src_k; src_k = dst_k; dst_k = tk;
     uint32_t* ti = src_i; src_i = dst_i; dst_i = ti;
   }

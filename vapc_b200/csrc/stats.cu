@@ -115,10 +115,10 @@ extern "C" int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, c
   const Grid g = to_device_grid(grid_host);
   const unsigned blocks = (unsigned)((nvoxels + kThreads - 1) / kThreads);
   if (grid_host->key_bytes == 4)
-    voxel_stats_kernel<uint32_t><<<blocks, kThreads, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(voxel_keys), count, mean3, m2,
+    VAPC_LAUNCH(voxel_stats_kernel<uint32_t>, blocks, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(voxel_keys), count, mean3, m2,
                                                                              nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8);
   else
-    voxel_stats_kernel<unsigned long long><<<blocks, kThreads, 0, as_stream(stream)>>>(
+    VAPC_LAUNCH(voxel_stats_kernel<unsigned long long>, blocks, kThreads, 0, as_stream(stream), 
         static_cast<const unsigned long long*>(voxel_keys), count, mean3, m2, nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -127,14 +127,14 @@ extern "C" int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, c
 extern "C" int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream) {
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_gather_f64: n < 0");
   if (n == 0) return VAPC_OK;
-  gather_kernel<double><<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(table, index, n, out);
+  VAPC_LAUNCH(gather_kernel<double>, grid_for(n, 256, 4), 256, 0, as_stream(stream), table, index, n, out);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
 extern "C" int vapc_gather_u32(const uint32_t* table, const uint32_t* index, int64_t n, uint32_t* out, void* stream) {
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_gather_u32: n < 0");
   if (n == 0) return VAPC_OK;
-  gather_kernel<uint32_t><<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(table, index, n, out);
+  VAPC_LAUNCH(gather_kernel<uint32_t>, grid_for(n, 256, 4), 256, 0, as_stream(stream), table, index, n, out);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
@@ -143,7 +143,7 @@ extern "C" int vapc_point_distance(const double* x, const double* y, const doubl
                                    const double* cog3, int64_t nvoxels, double* distance, void* stream) {
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_point_distance: n < 0");
   if (n == 0) return VAPC_OK;
-  point_distance_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(x, y, z, n, point2voxel, cog3, nvoxels, distance);
+  VAPC_LAUNCH(point_distance_kernel, grid_for(n, 256, 4), 256, 0, as_stream(stream), x, y, z, n, point2voxel, cog3, nvoxels, distance);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
