@@ -149,7 +149,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -197,7 +197,8 @@ def algorithmic_bytes(name, n, v, key_bytes, passes):
         "vapc_pack_keys_f64": (24 + k + 32) * n,
         "vapc_sort_pairs": (passes * (3 * k + 8) - 4) * n,
         "vapc_count_voxels": k * n,
-        "vapc_reduce_moments": (k + 4 + 32 + 4) * n + (k + 12 + 72) * v,
+        "vapc_reduce_moments": (k + 4 + 32) * n + (k + 12 + 72) * v,
+        "vapc_point2voxel_dense": (k + 4) * n + k * v,
         "vapc_voxel_stats": (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v,
     }.get(name, 0)
 

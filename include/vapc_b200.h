@@ -62,6 +62,9 @@ typedef struct vapc_grid {
 VAPC_API int vapc_abi_version(void);
 /* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches) */
 VAPC_API uint64_t vapc_launch_count(void);
+/* cudaLimitMaxL2FetchGranularity for the current device (32, 64 or 128 bytes): the per-voxel gathers read
+ * one random 32-byte record per point, so 32 avoids fetching unused neighbour sectors from HBM. */
+VAPC_API int vapc_set_l2_fetch_granularity(int32_t bytes);
 VAPC_API const char* vapc_last_error(void);
 
 /* ---- bounding box (feeds vapc_grid_t; also Vapc.compute_reduction_point, vapc.py:153-162,
@@ -95,13 +98,16 @@ VAPC_API int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* gr
 
 /* ---- stable LSD radix sort of (key, point index) pairs, 8-bit digits, in-house ---------
  * Sorts bits [0, end_bit).  idx_is_iota != 0: the contents of idx are ignored and taken to be
- * 0..n-1 (saves reading them in the first pass).  Buffers ping-pong; on return
- * *result_in_alt_host is 1 when the sorted data are in (keys_alt, idx_alt), else 0 (in keys /
- * idx).  key_bytes 4 or 8.  All four buffers must be distinct and hold n elements. */
+ * 0..n-1 (saves reading them in the first pass).  Buffers ping-pong: keys -> keys_alt ->
+ * (keys_alt2 if given, else keys) -> keys_alt -> ...; pass a third buffer keys_alt2 to keep the
+ * caller's keys intact (NULL: they are overwritten when more than one pass runs).  On return
+ * *result_location_host: bits 0-1 = which key buffer holds the sorted keys (0 keys, 1 keys_alt,
+ * 2 keys_alt2), bit 2 = sorted indices are in idx_alt (else idx).  key_bytes 4 or 8. */
 VAPC_API size_t vapc_sort_workspace_bytes(int64_t n);
-VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, uint32_t* idx, uint32_t* idx_alt,
-                    int32_t idx_is_iota, int64_t n, int32_t key_bytes, int32_t end_bit, void* ws,
-                    size_t ws_bytes, int32_t* result_in_alt_host, void* stream);
+VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx,
+                    uint32_t* idx_alt, int32_t idx_is_iota, int64_t n, int32_t key_bytes,
+                    int32_t end_bit, void* ws, size_t ws_bytes, int32_t* result_location_host,
+                    void* stream);
 
 /* ---- run-length segmentation of sorted keys into the voxel table ----------------------
  * Step 1: count voxels.  Writes per-tile head counts + their exclusive scan into ws and the
@@ -126,6 +132,16 @@ VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_so
                         void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
                         double* mean3, double* m2, uint32_t* point2voxel, void* ws,
                         size_t ws_bytes, void* stream);
+
+/* point -> voxel map in ORIGINAL point order through a direct-address table over the packed key space
+ * (table[key] = voxel row).  For grids of <= 2^25 cells the table stays in the 126 MB L2 and this costs
+ * 8 B/point of HBM traffic instead of the 64 B/point of the scattered writes that vapc_reduce_moments
+ * does when given point2voxel.  keys_unsorted: the keys vapc_pack_keys_f64 wrote (keep them intact by
+ * giving vapc_sort_pairs a keys_alt2 buffer).  table: scratch of vapc_point2voxel_table_bytes(). */
+VAPC_API size_t vapc_point2voxel_table_bytes(int32_t total_bits);
+VAPC_API int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys,
+                           int64_t nvoxels, int32_t key_bytes, int32_t total_bits, void* table,
+                           size_t table_bytes, uint32_t* point2voxel, void* stream);
 
 /* ---- a5, a7, a8, a12, a13, a14: per-voxel outputs from the moments ---------------------
  * (vapc.py:730-741 density, 829-852 centroid, 856-887 std ddof=1, 929-1040 covariance,

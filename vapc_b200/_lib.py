@@ -68,6 +68,7 @@ SIGNATURES = {
     "vapc_abi_version": (C.c_int, []),
     "vapc_last_error": (C.c_char_p, []),
     "vapc_launch_count": (C.c_uint64, []),
+    "vapc_set_l2_fetch_granularity": (C.c_int, [I32]),
     "vapc_minmax_workspace_bytes": (SZ, []),
     "vapc_minmax_f64": (C.c_int, [P, P, P, I64, P, P, SZ, P]),
     "vapc_voxel_coords_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
@@ -75,10 +76,12 @@ SIGNATURES = {
     "vapc_pack_keys_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
     "vapc_unpack_keys": (C.c_int, [P, I64, GP, P, P, P, P]),
     "vapc_sort_workspace_bytes": (SZ, [I64]),
-    "vapc_sort_pairs": (C.c_int, [P, P, P, P, I32, I64, I32, I32, P, SZ, C.POINTER(I32), P]),
+    "vapc_sort_pairs": (C.c_int, [P, P, P, P, P, I32, I64, I32, I32, P, SZ, C.POINTER(I32), P]),
     "vapc_segment_workspace_bytes": (SZ, [I64]),
     "vapc_count_voxels": (C.c_int, [P, I64, I32, P, P, SZ, P]),
     "vapc_reduce_moments": (C.c_int, [P, P, I64, GP, P, I64, P, P, P, P, P, P, P, P, SZ, P]),
+    "vapc_point2voxel_table_bytes": (SZ, [I32]),
+    "vapc_point2voxel_dense": (C.c_int, [P, I64, P, I64, I32, I32, P, SZ, P, P]),
     "vapc_voxel_stats": (C.c_int, [P, P, P, P, I64, GP, P, P, P, P, P, P, P, P]),
     "vapc_voxel_center_corner": (C.c_int, [P, I64, GP, P, P, P]),
     "vapc_closest_to_cog": (C.c_int, [P, P, I64, I32, P, P, I64, P, P, P, SZ, P]),

@@ -70,6 +70,16 @@ __device__ __forceinline__ double shift_center(long long v, double o, double vs)
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 
+// One 32-byte xyzw record with a single 256-bit load (LDG.E.256 on sm_100a): one request, one sector.
+__device__ __forceinline__ double4 ld_record(const double4* p) {
+  double4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_record(double4* p, double x, double y, double z, double w) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
+}
+
 // ---- block-wide exclusive scan of one unsigned per thread (blockDim.x multiple of 32, <= 1024)
 // smem33: 33 words of shared scratch.  Returns the exclusive prefix; *total = block sum (all
 // threads).  Ends with a barrier, so smem33 may be reused immediately.

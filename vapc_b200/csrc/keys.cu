@@ -32,6 +32,14 @@ void vapc_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" uint64_t vapc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int vapc_abi_version(void) { return VAPC_ABI_VERSION; }
 
+// The per-voxel gathers read one 32-byte record per point at random; ask the L2 to fetch no more than that
+// from DRAM on a miss (the default fetch granularity pulls neighbouring sectors that are never used).
+extern "C" int vapc_set_l2_fetch_granularity(int32_t bytes) {
+  if (bytes != 32 && bytes != 64 && bytes != 128) return vapc_set_error(VAPC_E_INVALID, "vapc_set_l2_fetch_granularity: 32, 64 or 128");
+  VAPC_RETURN_IF_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return VAPC_OK;
+}
+
 namespace {
 constexpr int kThreads = 256;
 
@@ -138,13 +146,13 @@ __global__ void __launch_bounds__(kThreads) pack_keys_kernel(const double* __res
         reinterpret_cast<ulonglong2*>(keys)[v] = make_ulonglong2(k0, k1);
       }
       if (xyzw) {
-        xyzw[2 * v] = make_double4(a.x, b.x, c.x, 0.0);
-        xyzw[2 * v + 1] = make_double4(a.y, b.y, c.y, 0.0);
+        st_record(xyzw + 2 * v, a.x, b.x, c.x, 0.0);
+        st_record(xyzw + 2 * v + 1, a.y, b.y, c.y, 0.0);
       }
     } else {
       const double a = ld_stream(x + v), b = ld_stream(y + v), c = ld_stream(z + v);
       keys[v] = pack_one<KeyT>(a, b, c, g, bad);
-      if (xyzw) xyzw[v] = make_double4(a, b, c, 0.0);
+      if (xyzw) st_record(xyzw + v, a, b, c, 0.0);
     }
   }
   if (VEC == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {

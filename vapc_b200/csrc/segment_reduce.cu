@@ -20,6 +20,8 @@
 // sector write-allocate on the scatter) ; per voxel: 8 key... see DESIGN.md.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "math3.cuh"
 
@@ -34,12 +36,15 @@ struct SegWs {  // layout of the segmentation workspace
   void* scan_ws;              // scan scratch
   uint32_t* carry_cnt;        // [ntiles]   points in the leading partial segment (0 = none)
   double* carry;              // [ntiles][10] its partial moments (or other per-op payload)
+  uint32_t* long_chains;      // [ntiles]   first tile of every carry chain longer than one tile
+  uint32_t* n_long;           // [1]
 };
 inline int64_t seg_tiles(int64_t n) { return (n + kSegTile - 1) / kSegTile; }
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 inline size_t seg_ws_bytes(int64_t n) {
   const int64_t nt = seg_tiles(n < 1 ? 1 : n);
-  return align_up(nt * 4) + align_up(8) + align_up(scan_u32_workspace_bytes(nt)) + align_up(nt * 4) + align_up(nt * 10 * 8);
+  return align_up(nt * 4) + align_up(8) + align_up(scan_u32_workspace_bytes(nt)) + align_up(nt * 4) + align_up(nt * 10 * 8) +
+         align_up(nt * 4) + align_up(4);
 }
 inline SegWs carve(void* ws, int64_t n) {
   const int64_t nt = seg_tiles(n < 1 ? 1 : n);
@@ -49,7 +54,9 @@ inline SegWs carve(void* ws, int64_t n) {
   w.total = reinterpret_cast<unsigned long long*>(p); p += align_up(8);
   w.scan_ws = p; p += align_up(scan_u32_workspace_bytes(nt));
   w.carry_cnt = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
-  w.carry = reinterpret_cast<double*>(p);
+  w.carry = reinterpret_cast<double*>(p); p += align_up(nt * 10 * 8);
+  w.long_chains = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
+  w.n_long = reinterpret_cast<uint32_t*>(p);
   return w;
 }
 
@@ -182,9 +189,7 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
     if (p0 + j < n) {
-      const double2 lo = __ldg(reinterpret_cast<const double2*>(xyzw + idx[j]));
-      const double2 hi = __ldg(reinterpret_cast<const double2*>(xyzw + idx[j]) + 1);
-      rec[j] = make_double4(lo.x, lo.y, hi.x, 0.0);
+      rec[j] = ld_record(xyzw + idx[j]);
     } else {
       rec[j] = make_double4(0, 0, 0, 0);
     }
@@ -249,59 +254,105 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
   if (threadIdx.x == 0 && sm.seg_start[1] == 0 && nheads > 0) carry_cnt[blockIdx.x] = 0;
 }
 
-// Fix-up: a voxel continued over tiles t, t+1, ... (carry_cnt > 0 and the same row) gets its carries
-// folded in, in tile order.  One warp per chain start; lane l folds tiles t+l, t+l+32, ... sequentially and
-// the 32 lane results are folded by lane 0 in lane order — a fixed association, so the result does not
-// depend on scheduling.
+// Fix-up: a voxel continued over tiles t, t+1, ... (carry_cnt > 0 and the same row) gets its carries folded
+// in, in tile order.  Almost every chain is a single tile (a voxel simply straddles one tile boundary): that
+// case is one Chan update by one thread.  Longer chains (a voxel with more points than a tile) are handed to a
+// warp each: lane l folds tiles t+l, t+l+32, ... sequentially and lane 0 folds the 32 lane results in lane
+// order — a fixed association, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(kThreads) fixup_moments_kernel(const uint32_t* __restrict__ tile_first,
                                                                  const uint32_t* __restrict__ carry_cnt, const double* __restrict__ carry,
                                                                  int ntiles, int64_t nvox, uint32_t* __restrict__ count,
-                                                                 double* __restrict__ mean3, double* __restrict__ m2) {
-  const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+                                                                 double* __restrict__ mean3, double* __restrict__ m2,
+                                                                 uint32_t* __restrict__ long_chains, uint32_t* __restrict__ n_long) {
+  const int t = (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (t >= ntiles) return;
-  if (carry_cnt[t] == 0) return;
+  const uint32_t cc = carry_cnt[t];
+  if (cc == 0) return;
   const uint32_t row = tile_first[t] - 1u;
   if (t > 0 && carry_cnt[t - 1] != 0 && tile_first[t - 1] - 1u == row) return;  // not the chain start
-  double na = 0.0, ma[3] = {0, 0, 0}, Ma[6] = {0, 0, 0, 0, 0, 0};
-  for (int u0 = t; u0 < ntiles; u0 += 32) {
-    const int u = u0 + lane;
-    const bool mine = u < ntiles && carry_cnt[u] != 0 && tile_first[u] - 1u == row;
-    const unsigned ok = __ballot_sync(0xffffffffu, mine);
-    const unsigned run = (ok == 0xffffffffu) ? 32u : (unsigned)(__ffs(~ok) - 1);  // leading tiles of the chain
-    if ((unsigned)lane < run) {
-      const double* c = carry + (int64_t)u * 10;
-      const double mb[3] = {c[0], c[1], c[2]};
-      const double Mb[6] = {c[3], c[4], c[5], c[6], c[7], c[8]};
-      chan_combine(na, ma, Ma, (double)carry_cnt[u], mb, Mb);
+  if (t + 1 < ntiles && carry_cnt[t + 1] != 0 && tile_first[t + 1] - 1u == row) {  // chain of >= 2 tiles
+    long_chains[atomicAdd(n_long, 1u)] = (uint32_t)t;
+    return;
+  }
+  double na = (double)count[row], ma[3], Ma[6], mb[3], Mb[6];
+  const double* c = carry + (int64_t)t * 10;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ma[k] = mean3[(int64_t)k * nvox + row]; mb[k] = c[k]; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { Ma[k] = m2[(int64_t)k * nvox + row]; Mb[k] = c[3 + k]; }
+  chan_combine(na, ma, Ma, (double)cc, mb, Mb);
+  count[row] = (uint32_t)na;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = ma[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Ma[k];
+}
+
+__global__ void __launch_bounds__(kThreads) fixup_long_chains_kernel(const uint32_t* __restrict__ tile_first,
+                                                                     const uint32_t* __restrict__ carry_cnt, const double* __restrict__ carry,
+                                                                     int ntiles, int64_t nvox, uint32_t* __restrict__ count,
+                                                                     double* __restrict__ mean3, double* __restrict__ m2,
+                                                                     const uint32_t* __restrict__ long_chains, const uint32_t* __restrict__ n_long) {
+  const int lane = threadIdx.x & 31;
+  const unsigned nchains = *n_long;
+  for (unsigned w = (unsigned)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < nchains; w += (gridDim.x * blockDim.x) >> 5) {
+    const int t = (int)long_chains[w];
+    const uint32_t row = tile_first[t] - 1u;
+    double na = 0.0, ma[3] = {0, 0, 0}, Ma[6] = {0, 0, 0, 0, 0, 0};
+    for (int u0 = t; u0 < ntiles; u0 += 32) {
+      const int u = u0 + lane;
+      const bool mine = u < ntiles && carry_cnt[u] != 0 && tile_first[u] - 1u == row;
+      const unsigned ok = __ballot_sync(0xffffffffu, mine);
+      const unsigned run = (ok == 0xffffffffu) ? 32u : (unsigned)(__ffs(~ok) - 1);  // leading tiles of the chain
+      if ((unsigned)lane < run) {
+        const double* c = carry + (int64_t)u * 10;
+        const double mb[3] = {c[0], c[1], c[2]};
+        const double Mb[6] = {c[3], c[4], c[5], c[6], c[7], c[8]};
+        chan_combine(na, ma, Ma, (double)carry_cnt[u], mb, Mb);
+      }
+      if (run < 32u) break;
     }
-    if (run < 32u) break;
+    double nt = 0.0, mt[3] = {0, 0, 0}, Mt[6] = {0, 0, 0, 0, 0, 0};
+    if (lane == 0) {
+      nt = (double)count[row];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mt[k] = mean3[(int64_t)k * nvox + row];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Mt[k] = m2[(int64_t)k * nvox + row];
+    }
+    for (int l = 0; l < 32; ++l) {
+      const double nb = __shfl_sync(0xffffffffu, na, l);
+      double mb[3], Mb[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mb[k] = __shfl_sync(0xffffffffu, ma[k], l);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Mb[k] = __shfl_sync(0xffffffffu, Ma[k], l);
+      if (lane == 0) chan_combine(nt, mt, Mt, nb, mb, Mb);
+    }
+    if (lane == 0) {
+      count[row] = (uint32_t)nt;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = mt[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Mt[k];
+    }
   }
-  // lane 0 folds: head-tile partial, then lanes 0..31 in order
-  double nt = 0.0, mt[3] = {0, 0, 0}, Mt[6] = {0, 0, 0, 0, 0, 0};
-  if (lane == 0) {
-    nt = (double)count[row];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) mt[k] = mean3[(int64_t)k * nvox + row];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Mt[k] = m2[(int64_t)k * nvox + row];
-  }
-  for (int l = 0; l < 32; ++l) {
-    const double nb = __shfl_sync(0xffffffffu, na, l);
-    double mb[3], Mb[6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) mb[k] = __shfl_sync(0xffffffffu, ma[k], l);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Mb[k] = __shfl_sync(0xffffffffu, Ma[k], l);
-    if (lane == 0) chan_combine(nt, mt, Mt, nb, mb, Mb);
-  }
-  if (lane == 0) {
-    count[row] = (uint32_t)nt;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = mt[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Mt[k];
-  }
+}
+
+// ---- point -> voxel map through a direct-address table (dense key spaces) ------------------------------------
+// table[key] = voxel row for every occupied key; p2v[i] = table[key_i] in ORIGINAL point order.  For key spaces
+// of <= 2^25 cells the table (<= 128 MB) lives in the 126 MB L2, so the per-point lookups cost no DRAM traffic,
+// unlike the scattered 4-byte writes of the in-kernel path (one 32-byte sector read-modify-write per point).
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) p2v_fill_kernel(const KeyT* __restrict__ voxel_keys, int64_t nvox, uint32_t* __restrict__ table) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += stride) table[voxel_keys[v]] = (uint32_t)v;
+}
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) p2v_lookup_kernel(const KeyT* __restrict__ keys, int64_t n, const uint32_t* __restrict__ table,
+                                                              uint32_t* __restrict__ p2v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p2v[i] = __ldg(table + __ldcs(keys + i));
 }
 
 // ---- closest to centroid ----------------------------------------------------------------------------
@@ -331,9 +382,8 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
     const int p = threadIdx.x * kItems + j;
     if (p0 + j < n) {
       const uint32_t id = idx_sorted[p0 + j];
-      const double2 lo = __ldg(reinterpret_cast<const double2*>(xyzw + id));
-      const double2 hi = __ldg(reinterpret_cast<const double2*>(xyzw + id) + 1);
-      sm.x[p] = lo.x; sm.y[p] = lo.y; sm.z[p] = hi.x;
+      const double4 r = ld_record(xyzw + id);
+      sm.x[p] = r.x; sm.y[p] = r.y; sm.z[p] = r.z;
       idx_s[p] = id;
     }
   }
@@ -489,9 +539,39 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_
     VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
         nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
   }
-  const int64_t warps_per_block = kThreads / 32;
-  VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + warps_per_block - 1) / warps_per_block), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry,
-                                                                                                   (int)nt, nvoxels_host, count, mean3, m2);
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.n_long, 0, sizeof(uint32_t), s));
+  VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
+              nvoxels_host, count, mean3, m2, w.long_chains, w.n_long);
+  VAPC_LAUNCH(fixup_long_chains_kernel, kNumSMs, kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt, nvoxels_host, count, mean3, m2,
+              w.long_chains, w.n_long);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" size_t vapc_point2voxel_table_bytes(int32_t total_bits) {
+  return total_bits < 0 || total_bits > 32 ? 0 : (sizeof(uint32_t) << total_bits);
+}
+
+extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys, int64_t nvoxels, int32_t key_bytes,
+                                      int32_t total_bits, void* table, size_t table_bytes, uint32_t* point2voxel, void* stream) {
+  if (n < 0 || nvoxels < 0 || total_bits < 0 || total_bits > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_dense: bad arguments");
+  if (!table || table_bytes < vapc_point2voxel_table_bytes(total_bits)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_point2voxel_dense: table too small");
+  if (n == 0) return VAPC_OK;
+  cudaStream_t s = as_stream(stream);
+  const int g1 = (int)std::min<int64_t>((nvoxels + kThreads - 1) / kThreads, (int64_t)kNumSMs * 16);
+  const int g2 = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16);
+  if (key_bytes == 4) {
+    VAPC_LAUNCH(p2v_fill_kernel<uint32_t>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const uint32_t*>(voxel_keys), nvoxels, static_cast<uint32_t*>(table));
+    VAPC_LAUNCH(p2v_lookup_kernel<uint32_t>, g2 < 1 ? 1 : g2, kThreads, 0, s, static_cast<const uint32_t*>(keys_unsorted), n,
+                static_cast<const uint32_t*>(table), point2voxel);
+  } else if (key_bytes == 8) {
+    typedef unsigned long long K;
+    VAPC_LAUNCH(p2v_fill_kernel<K>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const K*>(voxel_keys), nvoxels, static_cast<uint32_t*>(table));
+    VAPC_LAUNCH(p2v_lookup_kernel<K>, g2 < 1 ? 1 : g2, kThreads, 0, s, static_cast<const K*>(keys_unsorted), n, static_cast<const uint32_t*>(table),
+                point2voxel);
+  } else {
+    return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_dense: key_bytes must be 4 or 8");
+  }
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

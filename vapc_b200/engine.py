@@ -106,24 +106,50 @@ def voxel_coords(x, y, z, voxel_size, origin):
     return out
 
 
-def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = None):
+def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = None, preserve_keys: bool = False):
     """Stable LSD radix sort of (key, idx) by the low `end_bit` key bits.  keys: uint32-as-int32 or
     uint64-as-int64 storage (torch has no unsigned 32/64 arithmetic; only the bytes matter).
-    Returns (keys_sorted, idx_sorted) — new tensors or the inputs, whichever holds the result."""
+    Returns (keys_sorted, idx_sorted) — new tensors or the inputs, whichever holds the result.
+    preserve_keys: sort through a third buffer so that `keys` keeps its contents."""
     n = keys.numel()
     dev = keys.device
     key_bytes = keys.element_size()
     keys_alt = torch.empty_like(keys)
+    passes = (int(end_bit) + 7) // 8
+    keys_alt2 = torch.empty_like(keys) if (preserve_keys and passes > 1) else None
     iota = idx is None
     if iota:
         idx = _empty(n, torch.int32, dev)
     idx_alt = torch.empty_like(idx)
     ws_bytes = L.raw("vapc_sort_workspace_bytes")(n)
     ws = _empty(ws_bytes, torch.uint8, dev)
-    in_alt = C.c_int32(0)
-    L.call("vapc_sort_pairs", _ptr(keys), _ptr(keys_alt), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, key_bytes, int(end_bit),
-           _ptr(ws), ws_bytes, C.byref(in_alt), _stream())
-    return (keys_alt, idx_alt) if in_alt.value else (keys, idx)
+    loc = C.c_int32(0)
+    L.call("vapc_sort_pairs", _ptr(keys), _ptr(keys_alt), _ptr(keys_alt2), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, key_bytes,
+           int(end_bit), _ptr(ws), ws_bytes, C.byref(loc), _stream())
+    out_keys = (keys, keys_alt, keys_alt2)[loc.value & 3]
+    if preserve_keys and out_keys is keys and passes > 0:  # cannot happen with a third buffer; guard the contract
+        raise AssertionError("sort overwrote preserved keys")
+    return out_keys, (idx_alt if loc.value & 4 else idx)
+
+
+_L2_FETCH_SET = set()
+
+
+def _tune_device(device):
+    """Once per device: ask the L2 for 32-byte fetch granularity (random 32-byte record gathers)."""
+    import os
+
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i in _L2_FETCH_SET:
+        return
+    _L2_FETCH_SET.add(i)
+    g = int(os.environ.get("VAPC_L2_FETCH", "32"))
+    if g:
+        with torch.cuda.device(i):
+            L.call("vapc_set_l2_fetch_granularity", g)
+
+
+DENSE_P2V_MAX_BITS = 25  # direct-address point->voxel table of <= 128 MB stays L2-resident on B200
 
 
 @dataclass
@@ -187,9 +213,12 @@ class VoxelCloud:
         keys = _empty(n, kdtype, device)
         self.xyzw = torch.empty((n, 4), dtype=torch.float64, device=device)
         status = torch.zeros(1, dtype=torch.int32, device=device)
+        _tune_device(device)
         L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
-        self.keys_sorted, self.idx_sorted = sort_pairs(keys, g.total_bits)
-        del keys
+        dense_p2v = want_point2voxel and g.total_bits <= DENSE_P2V_MAX_BITS
+        self.keys_sorted, self.idx_sorted = sort_pairs(keys, g.total_bits, preserve_keys=dense_p2v)
+        if not dense_p2v:
+            del keys
         ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
         self._seg_ws = _empty(ws_bytes, torch.uint8, device)
         nv = torch.zeros(2, dtype=torch.int64, device=device)
@@ -207,7 +236,13 @@ class VoxelCloud:
         self.point2voxel = _empty(n, torch.int32, device) if want_point2voxel else None
         L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.idx_sorted), n, C.byref(g), _ptr(self.xyzw), V,
                _ptr(self.voxel_keys), _ptr(self.start), _ptr(self.count), _ptr(self.first_idx), _ptr(self.mean3), _ptr(self.m2),
-               _ptr(self.point2voxel), _ptr(self._seg_ws), ws_bytes, _stream())
+               _ptr(None if dense_p2v else self.point2voxel), _ptr(self._seg_ws), ws_bytes, _stream())
+        if dense_p2v:
+            tbytes = L.raw("vapc_point2voxel_table_bytes")(g.total_bits)
+            table = _empty(tbytes, torch.uint8, device)
+            L.call("vapc_point2voxel_dense", _ptr(keys), n, _ptr(self.voxel_keys), V, g.key_bytes, g.total_bits, _ptr(table), tbytes,
+                   _ptr(self.point2voxel), _stream())
+            del keys, table
         return self
 
     @property
