@@ -130,7 +130,9 @@ def workload_config(points_per_gpu, gpus):
                     "full attribute set (count, density, centroid, std, covariance, eigenvalues, 8 eigen-features) + point->voxel map",
         "points_per_gpu": points_per_gpu, "voxel_size": VOXEL_SIZE, "extent_m": list(EXTENT),
         "l2": "inputs (24 B/point, 2.4 GB at 1e8 points) are larger than the 126 MB L2; no flush needed",
-        "parallelism": f"points sharded in contiguous chunks over {gpus} GPU(s)",
+        "parallelism": f"points sharded in contiguous chunks over {gpus} GPU(s)" + ("" if gpus == 1 else
+                       "; rank r holds the x-slab [0.9 r L, 0.9 r L + L) (10 % overlap with its neighbour); partial voxel tables "
+                       "exchanged by key range with one NCCL all-to-all, then merged"),
     }
 
 
@@ -252,7 +254,8 @@ def main():
     torch.cuda.synchronize()
     nvox = cloud.nvoxels
     key_bytes = cloud.grid.key_bytes
-    passes = (cloud.grid.total_bits + 7) // 8
+    total_bits = cloud.grid.total_bits
+    passes = (total_bits + 7) // 8
 
     # ---- timed region: K steps, CUDA events, per-call events for the roofline -----------------
     records = []
@@ -316,41 +319,48 @@ def main():
 
     # ---- e2e: host buffers in, host voxel table out -------------------------------------------
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         hx, hy, hz = (c.cpu().pin_memory() for c in (x, y, z))
-        del x, y, z
+        del x, y, z, cloud, st
         torch.cuda.empty_cache()
-        out_specs = {"voxel_keys": (nvox,), "count": (nvox,), "density": (nvox,), "cog": (3, nvox), "std": (3, nvox), "cov": (6, nvox),
-                     "eig": (3, nvox), "eig_n": (3, nvox), "feat": (8, nvox)}
         host_out = {}
 
         def step_e2e():
             dx, dy, dz = (h.to(device, non_blocking=True) for h in (hx, hy, hz))
-            c = E.VoxelCloud.build(dx, dy, dz, VOXEL_SIZE, ORIGIN, keep_columns=False)
-            s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+            if world > 1:
+                c, s = D.voxel_statistics(dx, dy, dz, VOXEL_SIZE, ORIGIN)
+            else:
+                c = E.VoxelCloud.build(dx, dy, dz, VOXEL_SIZE, ORIGIN, keep_columns=False)
+                s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
             dev_out = {"voxel_keys": c.voxel_keys, "count": c.count, "density": s.density, "cog": s.cog, "std": s.std, "cov": s.cov,
                        "eig": s.eig, "eig_n": s.eig_n, "feat": s.feat}
             for k, t in dev_out.items():
-                if k not in host_out:
-                    host_out[k] = torch.empty(out_specs[k], dtype=t.dtype).pin_memory()
+                if k not in host_out or host_out[k].shape != t.shape:
+                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
                 host_out[k].copy_(t, non_blocking=True)
             torch.cuda.synchronize()
-            return dev_out
+            return sum(t.numel() * t.element_size() for t in dev_out.values())
 
         for _ in range(2):
-            dev_out = step_e2e()
+            d2h = step_e2e()
         h2d = 3 * 8 * n
-        d2h = sum(t.numel() * t.element_size() for t in dev_out.values())
-        del dev_out
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         e_steps = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(e_steps):
             step_e2e()
-        torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / e_steps
-        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": e_steps,
-               "api": "vapc_b200.engine.VoxelCloud.build + .stats on pinned host columns; full voxel table copied back to pinned host"}
+        if world > 1:
+            t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=device)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt, h2d, d2h = float(tmax[0].item()), int(t[1].item()), int(t[2].item())
+        e2e = {"value": n * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+               "steps": e_steps,
+               "api": "vapc_b200.engine.VoxelCloud.build + .stats (N = 1) / vapc_b200.dist.voxel_statistics (N > 1) on pinned host columns; "
+                      "the complete voxel table is copied back to pinned host memory; wall clock between barriers, max over ranks"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu_baseline = None

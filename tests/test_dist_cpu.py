@@ -1,0 +1,142 @@
+"""CPU tests of the N > 1 host logic (vapc_b200/dist.py) with world_size-2 gloo process groups: splitter
+planning, destination partitioning and the all-to-all(v) row exchange, followed by a numpy Chan merge (the
+checker) and comparison with the single-process oracle.  No CUDA kernels run here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import vapc_oracle as O
+from vapc_b200 import dist as D
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def partial_table(x, y, z, vs, vmin, bits):
+    """numpy stand-in of the local GPU stage: key-sorted partial rows (key, n, mean - c, M2)."""
+    vx, vy, vz = O.voxelize(x, y, z, [0, 0, 0], vs)
+    g = O.group_by_voxel(vx, vy, vz)
+    key = ((g.vx - vmin[0]) << (bits[1] + bits[2])) | ((g.vy - vmin[1]) << bits[2]) | (g.vz - vmin[2])
+    pts = np.stack([x, y, z], 1)[g.order]
+    c = (np.stack([g.vx, g.vy, g.vz], 1) + 0.5) * vs
+    n = g.counts.astype(np.float64)
+    mean = np.add.reduceat(pts, g.starts, axis=0) / n[:, None]
+    dev = pts - np.repeat(mean, g.counts, axis=0)
+    prod = np.stack([dev[:, a] * dev[:, b] for a, b in ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))], 1)
+    m2 = np.add.reduceat(prod, g.starts, axis=0)
+    assert np.all(np.diff(key) > 0)
+    return key.astype(np.int64), g.counts.astype(np.int32), np.concatenate([mean - c, m2], axis=1)
+
+
+def chan_merge(keys, count, mom):
+    """Reference merge of partial rows with equal keys (source order), numpy."""
+    order = np.argsort(keys, kind="stable")
+    keys, count, mom = keys[order], count[order].astype(np.float64), mom[order]
+    out_k, out_n, out_m = [], [], []
+    i = 0
+    idx6 = ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))
+    while i < len(keys):
+        na, ma, Ma = count[i], mom[i, :3].copy(), mom[i, 3:].copy()
+        j = i + 1
+        while j < len(keys) and keys[j] == keys[i]:
+            nb, mb, Mb = count[j], mom[j, :3], mom[j, 3:]
+            n = na + nb
+            d = mb - ma
+            ma = ma + d * nb / n
+            Ma = Ma + Mb + np.array([d[a] * d[b] for a, b in idx6]) * na * nb / n
+            na = n
+            j += 1
+        out_k.append(keys[i]); out_n.append(na); out_m.append(np.concatenate([ma, Ma]))
+        i = j
+    return np.array(out_k), np.array(out_n), np.array(out_m)
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        n, vs = 40000, 0.5
+        pts = np.round(rng.uniform([0, 0, 0], [30, 20, 4], (n, 3)), 3)
+        # disjoint point sets whose x-ranges overlap by 20 %, like bench.py's slabs: the middle fifth of the points
+        # (sorted by x) is dealt alternately to the two ranks
+        order = np.argsort(pts[:, 0], kind="stable")
+        a, b = int(0.4 * n), int(0.6 * n)
+        mid = order[a:b]
+        mine = pts[np.concatenate([order[:a], mid[0::2]])] if rank == 0 else pts[np.concatenate([mid[1::2], order[b:]])]
+        vmin = np.floor(pts.min(0) / vs).astype(np.int64)
+        vmax = np.floor(pts.max(0) / vs).astype(np.int64)
+        bits = [int(int(b - a).bit_length()) for a, b in zip(vmin, vmax)]
+        total_bits = sum(bits)
+        key, cnt, mom = partial_table(mine[:, 0], mine[:, 1], mine[:, 2], vs, vmin, bits)
+        hb = min(D.HIST_BITS, total_bits)
+        hist = torch.from_numpy(np.bincount(key >> (total_bits - hb), minlength=1 << hb).astype(np.int64))
+        dist.all_reduce(hist)
+        thresholds = D.plan_splitters(hist.numpy(), world, total_bits, hb)
+        send = D.partition_counts(torch.from_numpy(key), thresholds)
+        assert sum(send) == len(key)
+        recv, recv_counts = D.exchange_rows({"keys": torch.from_numpy(key), "count": torch.from_numpy(cnt), "moments": torch.from_numpy(mom)},
+                                            send)
+        rk = recv["keys"].numpy()
+        # every received key is in this rank's range
+        t = [0] + thresholds + [1 << 62]
+        assert np.all((rk >= t[rank]) & (rk < t[rank + 1]))
+        mk, mn, mm = chan_merge(rk, recv["count"].numpy(), recv["moments"].numpy())
+        # compare with the single-process oracle restricted to this rank's key range
+        gk, gc, gm = partial_table(pts[:, 0], pts[:, 1], pts[:, 2], vs, vmin, bits)
+        sel = (gk >= t[rank]) & (gk < t[rank + 1])
+        assert np.array_equal(mk, gk[sel])
+        assert np.array_equal(mn.astype(np.int64), gc[sel].astype(np.int64))
+        np.testing.assert_allclose(mm[:, :3], gm[sel][:, :3], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(mm[:, 3:], gm[sel][:, 3:], rtol=1e-9, atol=1e-15)
+        ret[rank] = (len(mk), sum(send), sum(recv_counts), int(sel.sum()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_and_merge_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    owned = [ret[r][0] for r in range(world)]
+    assert all(o > 0 for o in owned)
+    assert abs(owned[0] - owned[1]) < 0.35 * sum(owned), f"unbalanced key ranges {owned}"
+    assert sum(ret[r][1] for r in range(world)) == sum(ret[r][2] for r in range(world))  # rows sent == rows received
+
+
+def test_plan_splitters_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        for total_bits in (5, 16, 24, 40):
+            hb = min(D.HIST_BITS, total_bits)
+            hist = rng.integers(0, 50, 1 << hb)
+            hist[rng.random(1 << hb) < 0.5] = 0
+            t = D.plan_splitters(hist, world, total_bits, hb)
+            assert len(t) == world - 1 and all(a <= b for a, b in zip(t, t[1:]))
+            edges = [0] + [x >> (total_bits - hb) for x in t] + [1 << hb]
+            loads = [hist[a:b].sum() for a, b in zip(edges[:-1], edges[1:])]
+            assert sum(loads) == hist.sum()
+            if world > 1 and hist.sum() > 0:
+                assert max(loads) <= hist.sum() / world + hist.max() + 1
+    assert D.plan_splitters(np.zeros(16, np.int64), 4, 4, 4) == sorted(D.plan_splitters(np.zeros(16, np.int64), 4, 4, 4))
+
+
+def test_partition_counts_unsigned_keys():
+    keys = torch.tensor([1, 5, 5, 9, 0x7FFFFFFF, 0x80000000, 0xFFFFFFF0], dtype=torch.int64).to(torch.int32)  # uint32 storage
+    assert D.partition_counts(keys, [5, 0x80000000]) == [1, 4, 2]
+    assert D.partition_counts(keys, []) == [7]
+    assert D.bench_slab_shift(0, 50.0) == 0.0 and D.bench_slab_shift(2, 50.0) == 90.0

@@ -1,0 +1,204 @@
+"""Multi-GPU voxel statistics: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
+
+Points are sharded in contiguous chunks (each rank holds its own slice, as it would come out of a
+file).  The path has exactly one real exchange step, as BASELINE.json's north_star prescribes:
+
+  1. bounding box: local min/max kernel -> all-reduce(min/max) of 6 doubles -> ONE grid for all ranks,
+     so packed keys mean the same voxel everywhere;
+  2. every rank builds its local PARTIAL voxel table (key, count, mean - c(key), M2): keys -> radix
+     sort -> segmentation -> moments, all local, no communication;
+  3. the key space is cut into `world` ranges balancing the number of partial rows: all-reduce(sum) of
+     a 2^16-bin histogram of the partial tables' keys -> splitters;
+  4. ONE all-to-all(v) sends every partial row to the owner of its key range (the local table is
+     sorted, so each destination's rows are a contiguous slice);
+  5. the owner merges the received rows (stable radix sort by key keeps source-rank order; equal
+     keys are combined with Chan's update in that fixed order) and finalises statistics.
+
+Because c(key) is an exact function of the key, partial (count, mean, M2) triples combine without
+loss; integer outputs do not depend on the number of ranks, floating point ones differ only by the
+association of the Chan updates (<< 1e-9).
+
+The host-side planning functions are pure (numpy / torch-CPU friendly) so that the N > 1 logic is
+covered by world_size-2 gloo tests on the CPU (tests/test_dist_cpu.py); kernels run only on CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HIST_BITS = 16
+
+
+# ------------------------------------------------------------------------------------------------
+# pure planning helpers (no CUDA)
+# ------------------------------------------------------------------------------------------------
+def bench_slab_shift(rank: int, extent_x: float) -> float:
+    """bench.py's N > 1 layout: rank r holds the slab x in [0.9 r L, 0.9 r L + L): neighbouring chunks overlap
+    by 10 %, like adjacent flight strips, so ~10 % of every rank's voxels are shared with a neighbour and the
+    all-to-all really carries data."""
+    return 0.9 * rank * extent_x
+
+
+def plan_splitters(global_hist: np.ndarray, world: int, total_bits: int, hist_bits: int = HIST_BITS) -> List[int]:
+    """Key thresholds t_1 <= ... <= t_{world-1}: rank g owns keys in [t_g, t_{g+1}) (t_0 = 0, t_world = inf).
+    Chosen on histogram-bin boundaries so that every range holds about the same number of partial rows."""
+    hist = np.asarray(global_hist, dtype=np.int64)
+    hb = min(hist_bits, max(total_bits, 1))
+    shift = max(total_bits - hb, 0)
+    cum = np.cumsum(hist)
+    total = int(cum[-1]) if len(cum) else 0
+    out = []
+    for g in range(1, world):
+        target = total * g / world
+        b = int(np.searchsorted(cum, target, side="left")) + 1  # first bin NOT in range g-1
+        b = min(b, len(hist))
+        out.append(b << shift)
+    for i in range(1, len(out)):
+        out[i] = max(out[i], out[i - 1])
+    return out
+
+
+def keys_as_int64(keys: torch.Tensor) -> torch.Tensor:
+    """uint32-in-int32 / uint64-in-int64 key storage as non-negative int64 (needs <= 63 key bits)."""
+    if keys.dtype == torch.int32:
+        return keys.to(torch.int64) & 0xFFFFFFFF
+    return keys
+
+
+def partition_counts(sorted_keys: torch.Tensor, thresholds: Sequence[int]) -> List[int]:
+    """Rows of a key-sorted table going to each rank."""
+    n = sorted_keys.numel()
+    if not thresholds:
+        return [n]
+    k = keys_as_int64(sorted_keys)
+    t = torch.tensor(list(thresholds), dtype=torch.int64, device=k.device)
+    cuts = torch.searchsorted(k, t, right=False).cpu().tolist()
+    edges = [0] + cuts + [n]
+    return [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+
+
+def exchange_rows(columns: Dict[str, torch.Tensor], send_counts: Sequence[int], group=None):
+    """all-to-all(v) of row-major columns ([rows] or [rows, k] tensors, rows already grouped by destination).
+    Returns (received columns, recv_counts).  One small all-to-all of the counts, then one per column."""
+    world = dist.get_world_size(group)
+    dev = next(iter(columns.values())).device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.cpu().tolist()
+    total = int(sum(recv_counts))
+    out = {}
+    for name, t in columns.items():
+        t = t.contiguous()
+        r = torch.empty((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(r, t, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+        out[name] = r
+    return out, recv_counts
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA path
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ShardedVoxelTable:
+    """This rank's key range of the global voxel table (rows in key order; ranks in rank order)."""
+
+    grid: object
+    nvoxels: int  # rows owned by this rank
+    voxel_keys: torch.Tensor
+    count: torch.Tensor
+    mean3: torch.Tensor  # [3, V]
+    m2: torch.Tensor  # [6, V]
+    thresholds: List[int]
+    partial_rows_sent: int
+    partial_rows_received: int
+
+    def stats(self, density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True):
+        from . import engine as E
+
+        c = E.VoxelCloud()
+        c.grid, c.nvoxels, c.voxel_keys, c.count, c.mean3, c.m2 = self.grid, self.nvoxels, self.voxel_keys, self.count, self.mean3, self.m2
+        return c.stats(density=density, cog=cog, std=std, cov=cov, eig=eig, eig_n=eig_n, feat=feat)
+
+    def voxel_coords(self):
+        from . import engine as E
+
+        c = E.VoxelCloud()
+        c.grid, c.nvoxels, c.voxel_keys = self.grid, self.nvoxels, self.voxel_keys
+        return c.voxel_coords()
+
+
+def global_bounds(x, y, z, group=None) -> np.ndarray:
+    """Global [min x, min y, min z, max x, max y, max z]: local bbox kernel + one 6-double all-reduce."""
+    from . import _lib as L
+    from . import engine as E
+
+    n = x.numel()
+    out = torch.empty(6, dtype=torch.float64, device=x.device)
+    ws_bytes = L.raw("vapc_minmax_workspace_bytes")()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.call("vapc_minmax_f64", E._ptr(x), E._ptr(y), E._ptr(z), n, E._ptr(out), E._ptr(ws), ws_bytes, E._stream())
+    out[3:] = -out[3:]  # min over (min, -max)
+    dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)
+    out[3:] = -out[3:]
+    return out.cpu().numpy()
+
+
+def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: torch.Tensor, m2: torch.Tensor):
+    """Combine partial rows with equal keys (vapc_merge_partials).  keys [R] (any order, runs per source sorted),
+    count [R], mean3 [3, R], m2 [6, R].  Returns (voxel_keys, count, mean3, m2) of the merged table."""
+    from . import _lib as L
+    from . import engine as E
+
+    dev = keys.device
+    r = keys.numel()
+    ks, order = E.sort_pairs(keys.clone(), grid.total_bits)
+    ws_bytes = L.raw("vapc_segment_workspace_bytes")(r)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nv = torch.zeros(1, dtype=torch.int64, device=dev)
+    L.call("vapc_count_voxels", E._ptr(ks), r, grid.key_bytes, E._ptr(nv), E._ptr(ws), ws_bytes, E._stream())
+    v = int(nv.item())
+    out_keys = torch.empty(v, dtype=keys.dtype, device=dev)
+    out_count = torch.empty(v, dtype=torch.int32, device=dev)
+    out_mean = torch.empty((3, v), dtype=torch.float64, device=dev)
+    out_m2 = torch.empty((6, v), dtype=torch.float64, device=dev)
+    if r:
+        L.call("vapc_merge_partials", E._ptr(ks), E._ptr(order), r, grid.key_bytes, E._ptr(count.contiguous()), E._ptr(mean3.contiguous()),
+               E._ptr(m2.contiguous()), r, v, E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), E._ptr(ws), ws_bytes,
+               E._stream())
+    return out_keys, out_count, out_mean, out_m2
+
+
+def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True):
+    """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats)."""
+    from . import _lib as L
+    from . import engine as E
+
+    world = dist.get_world_size(group)
+    dev = x.device
+    bounds = global_bounds(x, y, z, group)
+    local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=bounds, want_point2voxel=False, keep_columns=False)
+    g = local.grid
+    if g.total_bits > 63:
+        raise L.VapcError(L.VAPC_E_KEYSPACE, "multi-GPU key ranges need at most 63 key bits")
+    # splitters from the global histogram of partial-table keys
+    hb = min(HIST_BITS, max(g.total_bits, 1))
+    hist = torch.empty(1 << hb, dtype=torch.int32, device=dev)
+    L.call("vapc_key_histogram", E._ptr(local.voxel_keys), local.nvoxels, g.key_bytes, g.total_bits, hb, E._ptr(hist), E._stream())
+    hist64 = hist.to(torch.int64)
+    dist.all_reduce(hist64, op=dist.ReduceOp.SUM, group=group)
+    thresholds = plan_splitters(hist64.cpu().numpy(), world, g.total_bits, hb)
+    send_counts = partition_counts(local.voxel_keys, thresholds)
+    moments = torch.cat([local.mean3, local.m2], dim=0).t().contiguous()  # [V, 9] rows for the exchange
+    recv, recv_counts = exchange_rows({"keys": local.voxel_keys, "count": local.count, "moments": moments}, send_counts, group)
+    rm = recv["moments"].t().contiguous()  # [9, R]
+    keys, count, mean3, m2 = merge_partial_rows(g, recv["keys"], recv["count"], rm[:3].contiguous(), rm[3:].contiguous())
+    table = ShardedVoxelTable(grid=g, nvoxels=keys.numel(), voxel_keys=keys, count=count, mean3=mean3, m2=m2, thresholds=thresholds,
+                              partial_rows_sent=int(sum(send_counts)), partial_rows_received=int(sum(recv_counts)))
+    st = table.stats() if with_stats else None
+    return table, st
