@@ -376,8 +376,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=cloud.grid.total_bits,
-                                                radix_passes=passes),
+            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
         }
