@@ -323,34 +323,34 @@ def main():
         hx, hy, hz = (c.cpu().pin_memory() for c in (x, y, z))
         del x, y, z, cloud, st
         torch.cuda.empty_cache()
-        host_out = {}
+        from vapc_b200.pipeline import HostStreamPipeline, STAT_NAMES
 
-        def step_e2e():
-            dx, dy, dz = (h.to(device, non_blocking=True) for h in (hx, hy, hz))
+        def compute_fn(dx, dy, dz):
             if world > 1:
-                c, s = D.voxel_statistics(dx, dy, dz, VOXEL_SIZE, ORIGIN)
+                c, s_ = D.voxel_statistics(dx, dy, dz, VOXEL_SIZE, ORIGIN)
             else:
                 c = E.VoxelCloud.build(dx, dy, dz, VOXEL_SIZE, ORIGIN, keep_columns=False)
-                s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
-            dev_out = {"voxel_keys": c.voxel_keys, "count": c.count, "density": s.density, "cog": s.cog, "std": s.std, "cov": s.cov,
-                       "eig": s.eig, "eig_n": s.eig_n, "feat": s.feat}
-            for k, t in dev_out.items():
-                if k not in host_out or host_out[k].shape != t.shape:
-                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                host_out[k].copy_(t, non_blocking=True)
-            torch.cuda.synchronize()
-            return sum(t.numel() * t.element_size() for t in dev_out.values())
+                s_ = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+            out = {"voxel_keys": c.voxel_keys, "count": c.count}
+            out.update({k: getattr(s_, k) for k in STAT_NAMES})
+            return out
 
-        for _ in range(2):
-            d2h = step_e2e()
-        h2d = 3 * 8 * n
-        e_steps = max(3, min(args.steps, 5))
+        pipe = HostStreamPipeline(VOXEL_SIZE, ORIGIN, device, compute_fn=compute_fn)
+        for _res in pipe.run([(hx, hy, hz)] * 2):  # warm-up: allocates device / pinned buffers
+            pass
+        torch.cuda.synchronize()
+        e_steps = max(5, args.steps)
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e_steps):
-            step_e2e()
+        nres = 0
+        for _res in pipe.run([(hx, hy, hz)] * e_steps):
+            nres += 1
+        torch.cuda.synchronize()
         barrier()
         dt = (time.perf_counter() - t0) / e_steps
+        assert nres == e_steps
+        h2d, d2h = pipe.h2d_bytes // e_steps, pipe.d2h_bytes // e_steps
         if world > 1:
             t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=device)
             tmax = t.clone()
@@ -359,8 +359,10 @@ def main():
             dt, h2d, d2h = float(tmax[0].item()), int(t[1].item()), int(t[2].item())
         e2e = {"value": n * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                "steps": e_steps,
-               "api": "vapc_b200.engine.VoxelCloud.build + .stats (N = 1) / vapc_b200.dist.voxel_statistics (N > 1) on pinned host columns; "
-                      "the complete voxel table is copied back to pinned host memory; wall clock between barriers, max over ranks"}
+               "api": "vapc_b200.pipeline.HostStreamPipeline over VoxelCloud.build + .stats (N = 1) / dist.voxel_statistics (N > 1): every step "
+                      "copies its X, Y, Z from pinned host memory and its complete voxel table back to pinned host memory; H2D of step k+1, "
+                      "compute of step k and D2H of step k-1 overlap on three streams; wall clock over all steps incl. pipeline fill and "
+                      "drain, max over ranks"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu_baseline = None

@@ -318,3 +318,25 @@ def test_properties_at_scale(E, n):
     ok = cnt > 1
     np.testing.assert_allclose(eig[:, ok].sum(0), cov[0, ok] + cov[3, ok] + cov[5, ok], rtol=1e-9, atol=1e-15)  # trace
     assert np.all(eig[0, ok] >= eig[1, ok]) and np.all(eig[1, ok] >= eig[2, ok]) and np.all(eig[2, ok] >= 0)
+
+
+def test_host_stream_pipeline_matches_direct(E):
+    """The overlapped host-buffer pipeline returns, for every cloud, exactly the table of a direct call."""
+    from vapc_b200.pipeline import HostStreamPipeline
+
+    clouds = [make_cloud("uniform" if i % 2 else "clustered", 40000 + 7000 * i, seed=100 + i) for i in range(6)]
+    pinned = [tuple(torch.from_numpy(c).pin_memory() for c in cl) for cl in clouds]
+    pipe = HostStreamPipeline(0.3, [0.0, 0.0, 0.0])
+    results = []
+    for res in pipe.run(pinned):
+        results.append({k: v.clone() for k, v in res.items() if isinstance(v, torch.Tensor)})
+    assert len(results) == len(clouds)
+    for cl, res in zip(clouds, results):
+        direct = E.VoxelCloud.build(*cl, 0.3, [0.0, 0.0, 0.0])
+        st = direct.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+        assert torch.equal(res["voxel_keys"], direct.voxel_keys.cpu())
+        assert torch.equal(res["count"], direct.count.cpu())
+        for name in ("density", "cog", "std", "cov", "eig", "eig_n", "feat"):
+            a, b = res[name], getattr(st, name).cpu()
+            assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), name
+    assert pipe.h2d_bytes == sum(3 * 8 * len(c[0]) for c in clouds)
