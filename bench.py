@@ -140,6 +140,9 @@ def workload_config(points_per_gpu, gpus):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled in the background from program start; stop(windows) keeps the samples whose arrival time
+    falls inside the timed regions (nvidia-smi needs ~0.3 s to start, longer than one timed region)."""
+
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -151,7 +154,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -159,9 +162,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, windows):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -171,7 +174,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if not any(a - 0.03 <= ts <= b + 0.03 for a, b in windows):
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -185,7 +190,7 @@ class ClockSampler:
                     reasons.add(nme)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "windows": "timed region + e2e region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -225,6 +230,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     n = args.points
@@ -265,10 +272,9 @@ def main():
         ev.record()
         records.append((name, phase, ev))
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = L.raw("vapc_launch_count")()
     barrier()
+    windows = [[time.perf_counter(), None]]
     L.observer = observer
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -279,7 +285,7 @@ def main():
     L.observer = None
     barrier()
     launches = L.raw("vapc_launch_count")() - launches0
-    clocks = sampler.stop()
+    windows[0][1] = time.perf_counter()
     ms_total = t_start.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=device)
@@ -290,11 +296,17 @@ def main():
 
     per_call = {}
     pending = {}
+    gaps = {}
+    last_after = None
     for name, phase, ev in records:
         if phase == "before":
             pending[name] = ev
+            if last_after is not None:
+                gaps.setdefault(f"{last_after[0]} -> {name}", []).append(last_after[1].elapsed_time(ev))
         else:
             per_call.setdefault(name, []).append(pending.pop(name).elapsed_time(ev))
+            last_after = (name, ev)
+    gaps = {k: round(sum(v) / len(v), 4) for k, v in gaps.items()}
     del records
 
     # ---- roofline of the dominant call --------------------------------------------------------
@@ -348,7 +360,8 @@ def main():
             nres += 1
         torch.cuda.synchronize()
         barrier()
-        dt = (time.perf_counter() - t0) / e_steps
+        windows.append([t0, time.perf_counter()])
+        dt = (windows[-1][1] - t0) / e_steps
         assert nres == e_steps
         h2d, d2h = pipe.h2d_bytes // e_steps, pipe.d2h_bytes // e_steps
         if world > 1:
@@ -363,6 +376,8 @@ def main():
                       "copies its X, Y, Z from pinned host memory and its complete voxel table back to pinned host memory; H2D of step k+1, "
                       "compute of step k and D2H of step k-1 overlap on three streams; wall clock over all steps incl. pipeline fill and "
                       "drain, max over ranks"}
+
+    clocks = sampler.stop(windows)
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu_baseline = None
@@ -381,6 +396,7 @@ def main():
             "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
+            "gaps_between_calls_ms": gaps,
         }
         print(json.dumps(line))
     if world > 1:

@@ -1,0 +1,234 @@
+"""Native reader / writer for uncompressed LAS 1.0-1.4 (point formats 0-10), numpy structured views.
+
+This is the I/O feeding the hot path.  The reference delegates to `laspy[lazrs]`
+(`src/vapc/datahandler.py:54-165`), which is not available offline; this module covers what `DataHandler`
+needs from it for plain `.las` files and mirrors laspy's conventions:
+
+* dimension names and order of `las.point_format.dimension_names` (bit fields split into their sub-fields),
+* scaled coordinates `x = X * scale + offset` in fp64 as two rounded operations (multiply, then add),
+* extra-byte dimensions described by the LASF_Spec / 4 VLR,
+* writing LAS 1.4 point format 7 with offsets = coordinate minima and scale 2.5e-4 by default, extra
+  dimensions as float32 (`datahandler.py:99-165`).
+
+LAZ (LASzip-compressed) files need `laspy` with a LAZ backend; without it a clear error is raised.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+# core fields of the two families of point records (ASPRS LAS 1.4 R15, tables 7 and 13)
+_LEGACY = [("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("intensity", "<u2"), ("bit_fields", "u1"), ("raw_classification", "u1"),
+           ("scan_angle_rank", "i1"), ("user_data", "u1"), ("point_source_id", "<u2")]
+_MODERN = [("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("intensity", "<u2"), ("return_byte", "u1"), ("flag_byte", "u1"),
+           ("classification", "u1"), ("user_data", "u1"), ("scan_angle", "<i2"), ("point_source_id", "<u2"), ("gps_time", "<f8")]
+_GPS = [("gps_time", "<f8")]
+_RGB = [("red", "<u2"), ("green", "<u2"), ("blue", "<u2")]
+_NIR = [("nir", "<u2")]
+_WAVE = [("wavepacket_index", "u1"), ("wavepacket_offset", "<u8"), ("wavepacket_size", "<u4"), ("return_point_wave_location", "<f4"),
+         ("x_t", "<f4"), ("y_t", "<f4"), ("z_t", "<f4")]
+POINT_FORMATS = {
+    0: _LEGACY, 1: _LEGACY + _GPS, 2: _LEGACY + _RGB, 3: _LEGACY + _GPS + _RGB, 4: _LEGACY + _GPS + _WAVE,
+    5: _LEGACY + _GPS + _RGB + _WAVE, 6: _MODERN, 7: _MODERN + _RGB, 8: _MODERN + _RGB + _NIR, 9: _MODERN + _WAVE,
+    10: _MODERN + _RGB + _NIR + _WAVE,
+}
+# extra-bytes data types (LAS 1.4 table 24): type code -> numpy dtype
+_EXTRA_TYPES = {1: "u1", 2: "i1", 3: "<u2", 4: "<i2", 5: "<u4", 6: "<i4", 7: "<u8", 8: "<i8", 9: "<f4", 10: "<f8"}
+_EXTRA_CODES = {np.dtype(v).str.lstrip("<|"): k for k, v in _EXTRA_TYPES.items()}
+
+
+def _sub_fields(fmt: int):
+    """(name, source field, shift, mask) of the bit-packed sub-fields, in laspy's dimension order."""
+    if fmt <= 5:
+        return {"bit_fields": [("return_number", 0, 0x07), ("number_of_returns", 3, 0x07), ("scan_direction_flag", 6, 0x01),
+                               ("edge_of_flight_line", 7, 0x01)],
+                "raw_classification": [("classification", 0, 0x1F), ("synthetic", 5, 0x01), ("key_point", 6, 0x01), ("withheld", 7, 0x01)]}
+    return {"return_byte": [("return_number", 0, 0x0F), ("number_of_returns", 4, 0x0F)],
+            "flag_byte": [("synthetic", 0, 0x01), ("key_point", 1, 0x01), ("withheld", 2, 0x01), ("overlap", 3, 0x01),
+                          ("scanner_channel", 4, 0x03), ("scan_direction_flag", 6, 0x01), ("edge_of_flight_line", 7, 0x01)]}
+
+
+def dimension_names(fmt: int, extra: List[str] = ()) -> List[str]:
+    """laspy's `point_format.dimension_names` for a point format (+ extra dimensions)."""
+    subs = _sub_fields(fmt)
+    out = []
+    for name, _ in POINT_FORMATS[fmt]:
+        if name in subs:
+            out += [s[0] for s in subs[name]]
+        else:
+            out.append(name)
+    return out + list(extra)
+
+
+class LasHeader:
+    def __init__(self):
+        self.version = (1, 4)
+        self.point_format = 7
+        self.scales = np.array([0.00025, 0.00025, 0.00025])
+        self.offsets = np.zeros(3)
+        self.mins = np.zeros(3)
+        self.maxs = np.zeros(3)
+        self.point_count = 0
+        self.point_size = 0
+        self.offset_to_points = 0
+        self.generating_software = "vapc_b200"
+        self.system_identifier = ""
+        self.extra_dims: List[Tuple[str, str]] = []  # (name, numpy dtype string)
+        self.compressed = False
+
+
+def read_header(buf: bytes) -> LasHeader:
+    if buf[:4] != b"LASF":
+        raise ValueError("not a LAS file (missing LASF signature)")
+    h = LasHeader()
+    h.version = (buf[24], buf[25])
+    h.system_identifier = buf[26:58].split(b"\0")[0].decode("ascii", "replace")
+    h.generating_software = buf[58:90].split(b"\0")[0].decode("ascii", "replace")
+    header_size, h.offset_to_points, n_vlr = struct.unpack_from("<HII", buf, 94)
+    fmt_byte, h.point_size = struct.unpack_from("<BH", buf, 104)
+    h.compressed = bool(fmt_byte & 0x80)
+    h.point_format = fmt_byte & 0x3F
+    legacy_count = struct.unpack_from("<I", buf, 107)[0]
+    sx, sy, sz, ox, oy, oz, maxx, minx, maxy, miny, maxz, minz = struct.unpack_from("<12d", buf, 131)
+    h.scales, h.offsets = np.array([sx, sy, sz]), np.array([ox, oy, oz])
+    h.mins, h.maxs = np.array([minx, miny, minz]), np.array([maxx, maxy, maxz])
+    h.point_count = legacy_count
+    if h.version >= (1, 4) and header_size >= 375:
+        count64 = struct.unpack_from("<Q", buf, 247)[0]
+        if count64:
+            h.point_count = count64
+    # VLRs: look for the extra-bytes description (LASF_Spec, record id 4)
+    pos = header_size
+    for _ in range(n_vlr):
+        if pos + 54 > len(buf):
+            break
+        user = buf[pos + 2:pos + 18].split(b"\0")[0].decode("ascii", "replace")
+        rec_id, length = struct.unpack_from("<HH", buf, pos + 18)
+        body = buf[pos + 54:pos + 54 + length]
+        if user == "LASF_Spec" and rec_id == 4:
+            for k in range(len(body) // 192):
+                e = body[k * 192:(k + 1) * 192]
+                dtype_code, options = e[2], e[3]
+                name = e[4:36].split(b"\0")[0].decode("ascii", "replace")
+                if dtype_code == 0:  # undocumented bytes: `options` holds the size
+                    h.extra_dims.append((name or f"ExtraBytes{k}", f"V{options}"))
+                elif dtype_code in _EXTRA_TYPES:
+                    h.extra_dims.append((name, _EXTRA_TYPES[dtype_code]))
+        pos += 54 + length
+    return h
+
+
+def record_dtype(h: LasHeader) -> np.dtype:
+    fields = list(POINT_FORMATS[h.point_format])
+    names = {n for n, _ in fields}
+    for name, dt in h.extra_dims:
+        fields.append((name if name not in names else name + "_extra", dt))
+    core = np.dtype(fields)
+    if core.itemsize < h.point_size:  # undocumented trailing bytes
+        fields.append(("ExtraBytes", f"V{h.point_size - core.itemsize}"))
+    elif core.itemsize > h.point_size:
+        raise ValueError(f"point record length {h.point_size} smaller than format {h.point_format} needs ({core.itemsize})")
+    return np.dtype(fields)
+
+
+def read_las(path: str):
+    """Returns (header, dict of numpy columns keyed by laspy dimension names; 'x', 'y', 'z' are the scaled fp64
+    coordinates)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    h = read_header(buf)
+    if h.compressed or path.lower().endswith(".laz"):
+        raise NotImplementedError("LAZ-compressed input needs laspy with a LAZ backend (lazrs / laszip), which is not installed; "
+                                  "decompress to .las first")
+    if h.point_format not in POINT_FORMATS:
+        raise ValueError(f"unsupported point format {h.point_format}")
+    dt = record_dtype(h)
+    rec = np.frombuffer(buf, dtype=dt, count=int(h.point_count), offset=h.offset_to_points)
+    cols: Dict[str, np.ndarray] = {}
+    subs = _sub_fields(h.point_format)
+    for name in dt.names:
+        if name in subs:
+            for sub, shift, mask in subs[name]:
+                cols[sub] = (rec[name] >> shift) & mask
+        elif dt[name].kind == "V":
+            continue
+        else:
+            cols[name] = rec[name]
+    # two rounded fp64 operations, like laspy (no FMA): X * scale, then + offset
+    for k, (lo, up) in enumerate((("x", "X"), ("y", "Y"), ("z", "Z"))):
+        cols[lo] = rec[up].astype(np.float64) * h.scales[k] + h.offsets[k]
+    return h, cols
+
+
+def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
+              point_format: int = 7, generating_software: str = "vapc_b200"):
+    """LAS 1.4, point format 6 / 7 / 8.  `standard`: values for standard dimensions by laspy name (cast to the field
+    type); `extra`: extra-byte dimensions (float32 / int16 / ... arrays)."""
+    if point_format not in (6, 7, 8):
+        raise ValueError("writer supports point formats 6, 7 and 8 (LAS 1.4)")
+    x, y, z = (np.asarray(a, np.float64) for a in (x, y, z))
+    n = len(x)
+    scales = np.asarray([0.00025] * 3 if scales is None else scales, np.float64)
+    if offsets is None:
+        offsets = np.array([x.min(), y.min(), z.min()]) if n else np.zeros(3)
+    offsets = np.asarray(offsets, np.float64)
+    fields = list(POINT_FORMATS[point_format])
+    extra_fields = []
+    for name, arr in extra.items():
+        arr = np.asarray(arr)
+        code = _EXTRA_CODES.get(arr.dtype.str.lstrip("<|"))
+        if code is None:
+            arr = arr.astype(np.float32)
+            code = 9
+        extra_fields.append((name, arr, code))
+        fields.append((name, _EXTRA_TYPES[code]))
+    dt = np.dtype(fields)
+    rec = np.zeros(n, dtype=dt)
+    for k, (c, up) in enumerate(((x, "X"), (y, "Y"), (z, "Z"))):
+        rec[up] = np.round((c - offsets[k]) / scales[k]).astype(np.int64).astype(np.int32)
+    subs = _sub_fields(point_format)
+    sub_lookup = {s[0]: (byte, s[1], s[2]) for byte, lst in subs.items() for s in lst}
+    for name, arr in standard.items():
+        arr = np.asarray(arr)
+        if name in sub_lookup:
+            byte, shift, mask = sub_lookup[name]
+            rec[byte] |= ((arr.astype(np.int64) & mask) << shift).astype(np.uint8)
+        elif name in dt.names:
+            with np.errstate(invalid="ignore"):
+                rec[name] = arr.astype(dt[name])
+    for name, arr, _ in extra_fields:
+        rec[name] = arr
+    # extra-bytes VLR
+    vlr = b""
+    if extra_fields:
+        body = b""
+        for name, arr, code in extra_fields:
+            e = bytearray(192)
+            e[2] = code
+            e[4:4 + min(31, len(name))] = name.encode("ascii", "replace")[:31]
+            e[160:160 + min(31, len(name))] = name.encode("ascii", "replace")[:31]
+            body += bytes(e)
+        vlr = struct.pack("<H16sHH32s", 0, b"LASF_Spec", 4, len(body), b"extra bytes") + body
+    header = bytearray(375)
+    header[0:4] = b"LASF"
+    header[24], header[25] = 1, 4
+    header[26:26 + 5] = b"OTHER"
+    sw = generating_software.encode("ascii", "replace")[:31]
+    header[58:58 + len(sw)] = sw
+    struct.pack_into("<HH", header, 90, 1, 2026)  # creation day / year
+    struct.pack_into("<HII", header, 94, 375, 375 + len(vlr), 1 if vlr else 0)
+    struct.pack_into("<BH", header, 104, point_format, dt.itemsize)
+    struct.pack_into("<I", header, 107, 0)  # legacy counts are 0 for formats >= 6
+    mins = [float(c.min()) if n else 0.0 for c in (x, y, z)]
+    maxs = [float(c.max()) if n else 0.0 for c in (x, y, z)]
+    struct.pack_into("<12d", header, 131, *scales, *offsets, maxs[0], mins[0], maxs[1], mins[1], maxs[2], mins[2])
+    struct.pack_into("<Q", header, 247, n)
+    rn = (rec["return_byte"] & 0x0F).astype(np.int64)
+    by_return = np.bincount(rn[(rn >= 1) & (rn <= 15)] - 1, minlength=15)[:15] if n else np.zeros(15, np.int64)
+    struct.pack_into("<15Q", header, 255, *[int(v) for v in by_return])
+    with open(path, "wb") as f:
+        f.write(bytes(header))
+        f.write(vlr)
+        f.write(rec.tobytes())
