@@ -102,8 +102,12 @@ VAPC_API int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* gr
  * (keys_alt2 if given, else keys) -> keys_alt -> ...; pass a third buffer keys_alt2 to keep the
  * caller's keys intact (NULL: they are overwritten when more than one pass runs).  On return
  * *result_location_host: bits 0-1 = which key buffer holds the sorted keys (0 keys, 1 keys_alt,
- * 2 keys_alt2), bit 2 = sorted indices are in idx_alt (else idx).  key_bytes 4 or 8. */
+ * 2 keys_alt2), bit 2 = sorted indices are in idx_alt (else idx).  key_bytes 4 or 8.
+ * One read of the keys builds the digit histograms of all passes; each pass is then a single
+ * kernel (rank in the tile, decoupled look-back for the global offsets, coalesced scatter). */
 VAPC_API size_t vapc_sort_workspace_bytes(int64_t n);
+/* test hook: force the 64-bit look-back words that n >= 2^30 elements need (default: chosen by n) */
+VAPC_API int vapc_sort_debug_wide_lookback(int32_t on);
 VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx,
                     uint32_t* idx_alt, int32_t idx_is_iota, int64_t n, int32_t key_bytes,
                     int32_t end_bit, void* ws, size_t ws_bytes, int32_t* result_location_host,

@@ -89,6 +89,24 @@ def test_sort_pairs_stable(E, n, bits, dtype):
     np.testing.assert_array_equal(_u32(idx), order)
 
 
+def test_sort_pairs_wide_lookback_words(E):
+    """n >= 2^30 elements per GPU switch the look-back words to 64 bits; force that path at a small n."""
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(11)
+    n = 300_001
+    keys = rng.integers(0, 1 << 19, n, dtype=np.uint64).astype(np.uint32)
+    L.call("vapc_sort_debug_wide_lookback", 1)
+    try:
+        ks, idx = E.sort_pairs(torch.from_numpy(keys.view(np.int32)).cuda(), 19)
+        torch.cuda.synchronize()
+    finally:
+        L.call("vapc_sort_debug_wide_lookback", 0)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(_np(ks).view(np.uint32), keys[order])
+    np.testing.assert_array_equal(_u32(idx), order)
+
+
 def test_sort_pairs_with_payload_and_partial_bits(E):
     rng = np.random.default_rng(5)
     n = 50000

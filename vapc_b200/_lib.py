@@ -76,6 +76,7 @@ SIGNATURES = {
     "vapc_pack_keys_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
     "vapc_unpack_keys": (C.c_int, [P, I64, GP, P, P, P, P]),
     "vapc_sort_workspace_bytes": (SZ, [I64]),
+    "vapc_sort_debug_wide_lookback": (C.c_int, [I32]),
     "vapc_sort_pairs": (C.c_int, [P, P, P, P, P, I32, I64, I32, I32, P, SZ, C.POINTER(I32), P]),
     "vapc_segment_workspace_bytes": (SZ, [I64]),
     "vapc_count_voxels": (C.c_int, [P, I64, I32, P, P, SZ, P]),

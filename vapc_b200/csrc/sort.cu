@@ -1,17 +1,21 @@
-// In-house stable LSD radix sort of (key, point index) pairs — 8-bit digits.
+// In-house stable LSD radix sort of (key, point index) pairs — 8-bit digits, ONE sweep per pass.
 //
-// Per pass (tile = 4096 consecutive elements, one CTA of 256 threads per tile):
-//   radix_hist     per-tile digit histogram              reads keys                 K B/elt
-//   colscan_*      column-wise exclusive scan of the [ntiles][256] counters (tiny)
-//   radix_scatter  rank (ballot-built peer masks + per-warp smem digit counters), reorder the tile in
-//                  shared memory, write each digit's run coalesced   reads K+4, writes K+4 B/elt
-// Peer masks ("which lanes hold my digit") are built from 8 vote.ballot's, one per digit bit.  The
-// match.any instruction would do the same in one line, but it runs on the SM's single ADU pipe at a
-// cost proportional to the number of distinct values in the warp (~60 cycles for random 8-bit digits;
-// ncu showed both kernels 99 % ADU-bound with it, profiles/r1_ncu_summary.md).
+//   digit_hist_kernel   one read of the keys -> the global digit histogram of EVERY pass (shared-memory
+//                       atomics), digit_scan_kernel turns each into first-slot offsets          K B/elt
+//   onesweep_kernel     per pass; tile = 4096 consecutive elements, one CTA of 256 threads:
+//                       rank inside the tile, publish the tile's digit counts, decoupled look-back over
+//                       the tiles in front for the global offsets, reorder the tile in shared memory and
+//                       write each digit's run coalesced        reads K+4, writes K+4 B/elt, nothing else
+// Ranking: the lanes of a warp holding the same digit find each other through a shared-memory word per
+// (warp, digit) that they OR their lane bit into (one ATOMS + one LDS per key).  The two alternatives were
+// measured on B200 (profiles/): match.any runs on the SM's single ADU pipe at a cost proportional to the
+// distinct values in the warp (both sort kernels 99 % ADU-bound), and peer masks from 8 vote.ballot's cost
+// ~35 ALU instructions per key (sort kernels ALU-bound, 0.65 ms per pass at 1e8 keys).
 // Ranking keeps equal digits in input order, so every pass — and therefore the whole sort — is
 // stable: points of one voxel stay in original index order (tie-break "lowest original index"
 // and "first point of a voxel" fall out of that; see include/vapc_b200.h).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -21,160 +25,171 @@ constexpr int kThreads = 256;  // == kRadix: thread t owns digit t in the per-di
 constexpr int kWarps = kThreads / 32;
 constexpr int kItems = 16;
 constexpr int kTile = kThreads * kItems;  // 4096
-constexpr int kRowsPerChunk = 32;         // tiles per column-scan chunk
+constexpr int kMaxPasses = 8;             // 64-bit keys
 
 template <typename KeyT>
 __device__ __forceinline__ unsigned digit_of(KeyT k, int shift, unsigned mask) {
   return (unsigned)(k >> shift) & mask;
 }
 
-// lanes of the warp holding the same 8-bit digit as this lane (invalid lanes match nobody valid)
-__device__ __forceinline__ unsigned match_digit(unsigned d, bool valid) {
-  unsigned peers = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-  for (int b = 0; b < kRadixBits; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const unsigned m = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? m : ~m;
-  }
-  return peers;
-}
-
-// ---- per-tile digit histogram ---------------------------------------------------------------
-// Per-warp private counters updated by one leader lane per distinct digit (plain read-modify-write:
-// leaders of different digits touch different words), then summed over the warps.
+// ---- all digit histograms in one sweep over the keys ---------------------------------------------
+// ghist[p][d] = number of keys whose p-th 8-bit digit is d.  Shared-memory atomics (no return value
+// needed for counting), one flush of non-zero counters per CTA.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift, unsigned mask,
-                                                       uint32_t* __restrict__ tile_hist) {
-  __shared__ unsigned cnt[kWarps][kRadix];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int w = 0; w < kWarps; ++w) cnt[w][threadIdx.x] = 0;
+__global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int end_bit,
+                                                              uint32_t* __restrict__ ghist) {
+  __shared__ unsigned sh[kMaxPasses][kRadix];
+  for (int p = 0; p < passes; ++p) sh[p][threadIdx.x] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kTile;
-  KeyT key[kItems];
+  constexpr int kVec = 16 / sizeof(KeyT);  // keys per 16-byte load
+  const int64_t nvec = n / kVec;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const unsigned last_mask = (1u << (end_bit - (passes - 1) * kRadixBits)) - 1u;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    KeyT k[kVec];
+    if (sizeof(KeyT) == 4) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(keys) + v);
+      k[0] = (KeyT)q.x; k[1] = (KeyT)q.y; k[2] = (KeyT)q.z; k[3] = (KeyT)q.w;
+    } else {
+      const ulonglong2 q = __ldcs(reinterpret_cast<const ulonglong2*>(keys) + v);
+      k[0] = (KeyT)q.x; k[1] = (KeyT)q.y;
+    }
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const int64_t i = base + k * kThreads + threadIdx.x;
-    key[k] = i < n ? keys[i] : (KeyT)0;
+    for (int j = 0; j < kVec; ++j) {
+      for (int p = 0; p < passes; ++p) {
+        const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
+        atomicAdd(&sh[p][digit_of(k[j], p * kRadixBits, m)], 1u);
+      }
+    }
   }
-  unsigned* wc = cnt[warp];
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const bool valid = (base + k * kThreads + threadIdx.x) < n;
-    const unsigned d = digit_of(key[k], shift, mask);
-    const unsigned peers = match_digit(d, valid);
-    if (valid && lane == (__ffs(peers) - 1)) wc[d] += (unsigned)__popc(peers);
-    __syncwarp();
+  if (blockIdx.x == 0) {  // tail (n not a multiple of the vector width)
+    for (int64_t i = nvec * kVec + threadIdx.x; i < n; i += blockDim.x) {
+      const KeyT k = keys[i];
+      for (int p = 0; p < passes; ++p) {
+        const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
+        atomicAdd(&sh[p][digit_of(k, p * kRadixBits, m)], 1u);
+      }
+    }
   }
   __syncthreads();
-  unsigned t = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; ++w) t += cnt[w][threadIdx.x];
-  tile_hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = t;
+  for (int p = 0; p < passes; ++p) {
+    const unsigned c = sh[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * kRadix + threadIdx.x], c);
+  }
 }
 
-// ---- column scan: off[t][d] = SUM_{d'<d} total[d'] + SUM_{t'<t} hist[t'][d] ---------------------
-// Chunks of kRowsPerChunk tiles; every thread owns one digit column.  All loads of a chunk are issued
-// before the dependent running sum, so the passes are bandwidth- not latency-bound.
-__global__ void __launch_bounds__(kThreads) colscan_partial(const uint32_t* __restrict__ hist, int ntiles,
-                                                            uint32_t* __restrict__ chunk_sum) {
-  const int r0 = blockIdx.x * kRowsPerChunk;
-  uint32_t v[kRowsPerChunk];
-#pragma unroll
-  for (int r = 0; r < kRowsPerChunk; ++r) v[r] = (r0 + r) < ntiles ? hist[(int64_t)(r0 + r) * kRadix + threadIdx.x] : 0u;
-  uint32_t s = 0;
-#pragma unroll
-  for (int r = 0; r < kRowsPerChunk; ++r) s += v[r];
-  chunk_sum[(int64_t)blockIdx.x * kRadix + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(kThreads) colscan_chunks(const uint32_t* __restrict__ chunk_sum, uint32_t* __restrict__ chunk_base,
-                                                           int nchunks) {
+// ghist[p][.] -> exclusive scan over the digits (first output slot of each digit); one CTA per pass
+__global__ void __launch_bounds__(kThreads) digit_scan_kernel(uint32_t* __restrict__ ghist) {
   __shared__ unsigned warp_s[33];
-  uint32_t total_d = 0;
-#pragma unroll 8
-  for (int c = 0; c < nchunks; ++c) total_d += chunk_sum[(int64_t)c * kRadix + threadIdx.x];
   unsigned total;
-  uint32_t run = block_exclusive_scan(total_d, warp_s, &total);  // first slot of this digit
-#pragma unroll 8
-  for (int c = 0; c < nchunks; ++c) {
-    const uint32_t v = chunk_sum[(int64_t)c * kRadix + threadIdx.x];
-    chunk_base[(int64_t)c * kRadix + threadIdx.x] = run;
-    run += v;
-  }
-}
-__global__ void __launch_bounds__(kThreads) colscan_apply(uint32_t* __restrict__ hist, int ntiles,
-                                                          const uint32_t* __restrict__ chunk_base) {
-  const int r0 = blockIdx.x * kRowsPerChunk;
-  uint32_t v[kRowsPerChunk];
-#pragma unroll
-  for (int r = 0; r < kRowsPerChunk; ++r) v[r] = (r0 + r) < ntiles ? hist[(int64_t)(r0 + r) * kRadix + threadIdx.x] : 0u;
-  uint32_t run = chunk_base[(int64_t)blockIdx.x * kRadix + threadIdx.x];
-#pragma unroll
-  for (int r = 0; r < kRowsPerChunk; ++r) {
-    if ((r0 + r) < ntiles) hist[(int64_t)(r0 + r) * kRadix + threadIdx.x] = run;
-    run += v[r];
-  }
+  uint32_t* h = ghist + (int64_t)blockIdx.x * kRadix;
+  const unsigned v = h[threadIdx.x];
+  h[threadIdx.x] = block_exclusive_scan(v, warp_s, &total);
 }
 
-// ---- rank + scatter ---------------------------------------------------------------------------
-template <typename KeyT>
-struct ScatterSmem {
-  unsigned warp_cnt[kWarps][kRadix];  // per-warp digit counters -> per-warp exclusive prefixes
-  unsigned bin_start[kRadix];         // tile-local first slot of each digit
-  unsigned g_off[kRadix];             // global first slot of this tile's run of each digit
-  unsigned warp_s[33];
-  KeyT keys[kTile];
-  uint32_t idx[kTile];
+// ---- one radix pass in one sweep: rank + decoupled look-back + scatter --------------------------------
+// Tiles are handed out by an atomic ticket, so a tile's predecessors are always resident or done and the
+// look-back spin cannot starve.  look[tile][digit] packs a 2-bit status with the count:
+//   0 = not ready, 1 = this tile's own count, 2 = inclusive count of all tiles up to this one.
+template <typename LookT> struct Look;
+template <> struct Look<uint32_t> {
+  static constexpr int kShift = 30;
+  static __device__ __forceinline__ uint32_t load(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void store(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
+};
+template <> struct Look<unsigned long long> {
+  static constexpr int kShift = 62;
+  static __device__ __forceinline__ unsigned long long load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  }
 };
 
-template <typename KeyT, bool IOTA>
-__global__ void __launch_bounds__(kThreads, 3) radix_scatter(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
-                                                          KeyT* __restrict__ keys_out, uint32_t* __restrict__ idx_out, int64_t n,
-                                                          int shift, unsigned mask, const uint32_t* __restrict__ tile_off) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ScatterSmem<KeyT>& sm = *reinterpret_cast<ScatterSmem<KeyT>*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+template <typename KeyT>
+struct SweepSmem {
+  unsigned warp_cnt[kWarps][kRadix];  // per-warp digit counters -> per-warp exclusive prefixes
+  unsigned bin_start[kRadix];         // tile-local first slot of each digit
+  unsigned delta[kRadix];             // global slot of tile position p holding digit d = p + delta[d]
+  unsigned warp_s[33];
+  unsigned tile;
+  union {
+    unsigned masks[3][kWarps][kRadix];  // ranking: lanes of a warp holding each digit (triple-buffered)
+    struct {
+      KeyT keys[kTile];
+      uint32_t idx[kTile];
+    } out;  // the tile reordered by digit
+  } u;
+};
 
+template <typename KeyT, typename LookT, bool IOTA>
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
+                                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ idx_out, int64_t n,
+                                                               int shift, unsigned mask, const uint32_t* __restrict__ digit_base,
+                                                               LookT* __restrict__ look, unsigned* __restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SweepSmem<KeyT>& sm = *reinterpret_cast<SweepSmem<KeyT>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) sm.warp_cnt[w][tid] = 0;
-  sm.g_off[tid] = tile_off[(int64_t)blockIdx.x * kRadix + tid];
-
-  // warp-striped load: warp w owns elements [w*512, (w+1)*512) of the tile, lane l takes
-  // element k*32 + l in step k, so (warp, k, lane) order is input order.
-  KeyT key[kItems];
-  uint32_t idx[kItems];
-  const int64_t wbase = tile_base + (int64_t)warp * (32 * kItems) + lane;
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const int64_t i = wbase + k * 32;
-    const bool valid = i < n;
-    key[k] = valid ? keys_in[i] : (KeyT)0;
-    idx[k] = IOTA ? (uint32_t)i : (valid ? idx_in[i] : 0u);
-  }
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) sm.u.masks[b][w][tid] = 0;
   __syncthreads();
+  const unsigned tile = sm.tile;
+  const int64_t tile_base = (int64_t)tile * kTile;
 
-  // rank inside the warp: lanes holding the same digit find each other through the ballot-built peer
-  // mask; the per-warp counter carries the count from earlier steps.
-  unsigned rank[kItems];
+  // warp-striped load: warp w owns elements [w*512, (w+1)*512) of the tile, lane l takes element k*32 + l
+  // in step k, so (warp, k, lane) order is input order.
+  KeyT key[kItems];
+  const int64_t wbase = tile_base + (int64_t)warp * (32 * kItems) + lane;
+  const bool full = tile_base + kTile <= n;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys_in + wbase + k * 32) : (KeyT)0;
+
+  // rank inside the warp.  Lanes holding the same digit find each other by OR-ing their lane bit into a
+  // per-(warp, digit) shared word; the lowest such lane advances the warp's running digit counter.  The mask
+  // words are cleared by that leader one step later, hence three buffers and one warp barrier per step.
+  unsigned short rank[kItems];
   const unsigned lt = (1u << lane) - 1u;
   unsigned* wc = sm.warp_cnt[warp];
+  unsigned prev_d = 0;
+  bool prev_leader = false;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    const bool valid = (wbase + k * 32) < n;
+    unsigned* mk = sm.u.masks[k % 3][warp];
+    const bool valid = full || (wbase + k * 32) < n;
     const unsigned d = digit_of(key[k], shift, mask);
-    const unsigned peers = match_digit(d, valid);
-    unsigned prev = 0;
-    if (valid) prev = wc[d];
+    if (valid) atomicOr(&mk[d], 1u << lane);
     __syncwarp();
-    if (valid && lane == (__ffs(peers) - 1)) wc[d] = prev + (unsigned)__popc(peers);
-    __syncwarp();
-    rank[k] = prev + (unsigned)__popc(peers & lt);
+    if (k > 0 && prev_leader) sm.u.masks[(k + 2) % 3][warp][prev_d] = 0;
+    const unsigned peers = valid ? mk[d] : 0u;
+    const int leader = __ffs(peers) - 1;
+    const bool is_leader = valid && lane == leader;
+    unsigned before = 0;
+    if (is_leader) {
+      before = wc[d];
+      wc[d] = before + (unsigned)__popc(peers);
+    }
+    before = __shfl_sync(0xffffffffu, before, leader);
+    rank[k] = (unsigned short)(before + (unsigned)__popc(peers & lt));
+    prev_d = d;
+    prev_leader = is_leader;
   }
   __syncthreads();
 
-  // per digit (thread tid == digit): exclusive prefix over warps, then over digits
+  // per digit (thread tid == digit): exclusive prefix over warps -> tile count, published for the tiles behind
   unsigned run = 0;
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) {
@@ -182,31 +197,50 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter(const KeyT* __restr
     sm.warp_cnt[w][tid] = run;
     run += t;
   }
+  LookT* mine = look + (int64_t)tile * kRadix + tid;
+  Look<LookT>::store(mine, (LookT)run | ((LookT)(tile == 0 ? 2 : 1) << Look<LookT>::kShift));
   unsigned total;
-  sm.bin_start[tid] = block_exclusive_scan(run, sm.warp_s, &total);
+  const unsigned bstart = block_exclusive_scan(run, sm.warp_s, &total);
+  sm.bin_start[tid] = bstart;
   __syncthreads();
 
-  // reorder inside shared memory
+  // reorder inside shared memory (the mask words are dead: every warp passed the barrier above)
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    if ((wbase + k * 32) < n) {
+    if (full || (wbase + k * 32) < n) {
       const unsigned d = digit_of(key[k], shift, mask);
       const unsigned pos = sm.bin_start[d] + wc[d] + rank[k];
-      sm.keys[pos] = key[k];
-      sm.idx[pos] = idx[k];
+      sm.u.out.keys[pos] = key[k];
+      sm.u.out.idx[pos] = IOTA ? (uint32_t)(wbase + k * 32) : __ldcs(idx_in + wbase + k * 32);
     }
   }
+
+  // decoupled look-back: sum the counts of the tiles in front until one has published its inclusive count
+  LookT excl = 0;
+  if (tile > 0) {
+    const LookT vmask = ((LookT)1 << Look<LookT>::kShift) - 1;
+    const LookT* p = mine - kRadix;
+    while (true) {
+      const LookT w = Look<LookT>::load(p);
+      const unsigned st = (unsigned)(w >> Look<LookT>::kShift);
+      if (st == 0) continue;
+      excl += w & vmask;
+      if (st == 2) break;
+      p -= kRadix;
+    }
+    Look<LookT>::store(mine, (excl + run) | ((LookT)2 << Look<LookT>::kShift));
+  }
+  sm.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
   __syncthreads();
 
   // each digit's run goes out contiguously
   const int tile_n = (int)min((int64_t)kTile, n - tile_base);
 #pragma unroll 4
   for (int p = tid; p < tile_n; p += kThreads) {
-    const KeyT k = sm.keys[p];
-    const unsigned d = digit_of(k, shift, mask);
-    const unsigned dst = sm.g_off[d] + ((unsigned)p - sm.bin_start[d]);
+    const KeyT k = sm.u.out.keys[p];
+    const unsigned dst = (unsigned)p + sm.delta[digit_of(k, shift, mask)];
     keys_out[dst] = k;
-    idx_out[dst] = sm.idx[p];
+    idx_out[dst] = sm.u.out.idx[p];
   }
 }
 
@@ -216,42 +250,43 @@ __global__ void iota_kernel(uint32_t* __restrict__ out, int64_t n) {
 }
 
 inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
-inline int64_t num_chunks(int64_t ntiles) { return (ntiles + kRowsPerChunk - 1) / kRowsPerChunk; }
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+// workspace: [digit histograms kMaxPasses x 256 u32][ticket (256 B)][look-back ntiles x 256 x 8 B]
+inline size_t look_offset() { return align256(kMaxPasses * kRadix * sizeof(uint32_t)) + 256; }
 
-template <typename KeyT>
-int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int end_bit,
-              void* ws, int32_t* result_location, cudaStream_t s) {
-  const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
+bool g_force_wide_lookback = false;
+
+template <typename KeyT, typename LookT>
+int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int end_bit,
+                 int passes, void* ws, int32_t* result_location, cudaStream_t s) {
   const int64_t ntiles = num_tiles(n);
-  const int64_t nchunks = num_chunks(ntiles);
-  uint32_t* tile_hist = static_cast<uint32_t*>(ws);
-  uint32_t* chunk_sum = tile_hist + ntiles * kRadix;
-  uint32_t* chunk_base = chunk_sum + nchunks * kRadix;
-  const size_t smem = sizeof(ScatterSmem<KeyT>);
-  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (passes == 0) {
-    if (idx_is_iota) VAPC_LAUNCH(iota_kernel, kNumSMs * 8, 256, 0, s, idx, n);
-    *result_location = 0;
-    VAPC_CHECK_LAUNCH();
-    return VAPC_OK;
-  }
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  uint32_t* ghist = reinterpret_cast<uint32_t*>(base);
+  unsigned* ticket = reinterpret_cast<unsigned*>(base + align256(kMaxPasses * kRadix * sizeof(uint32_t)));
+  LookT* look = reinterpret_cast<LookT*>(base + look_offset());
+  const size_t look_bytes = (size_t)ntiles * kRadix * sizeof(LookT);
+  const size_t smem = sizeof(SweepSmem<KeyT>);
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT, LookT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT, LookT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(ghist, 0, kMaxPasses * kRadix * sizeof(uint32_t), s));
+  const int hgrid = (int)std::min<int64_t>((n + kThreads * 16 - 1) / (kThreads * 16), (int64_t)kNumSMs * 8);
+  VAPC_LAUNCH(digit_hist_kernel<KeyT>, hgrid < 1 ? 1 : hgrid, kThreads, 0, s, keys, n, passes, end_bit, ghist);
+  VAPC_LAUNCH(digit_scan_kernel, passes, kThreads, 0, s, ghist);
   // key buffers: keys -> alt -> (alt2 | keys) -> alt -> ...; with alt2 the caller's keys stay intact
   KeyT* src_k = keys; KeyT* dst_k = keys_alt;
   KeyT* spare = keys_alt2 ? keys_alt2 : keys;
   uint32_t* src_i = idx; uint32_t* dst_i = idx_alt;
   for (int p = 0; p < passes; ++p) {
     const int shift = p * kRadixBits;
-    const int bits = min(kRadixBits, end_bit - shift);
+    const int bits = std::min(kRadixBits, end_bit - shift);
     const unsigned mask = (1u << bits) - 1u;
-    VAPC_LAUNCH(radix_hist<KeyT>, (unsigned)ntiles, kThreads, 0, s, src_k, n, shift, mask, tile_hist);
-    VAPC_LAUNCH(colscan_partial, (unsigned)nchunks, kThreads, 0, s, tile_hist, (int)ntiles, chunk_sum);
-    VAPC_LAUNCH(colscan_chunks, 1, kThreads, 0, s, chunk_sum, chunk_base, (int)nchunks);
-    VAPC_LAUNCH(colscan_apply, (unsigned)nchunks, kThreads, 0, s, tile_hist, (int)ntiles, chunk_base);
+    VAPC_RETURN_IF_CUDA(cudaMemsetAsync(ticket, 0, 256 + look_bytes, s));  // ticket + look-back words (contiguous)
     if (p == 0 && idx_is_iota)
-      VAPC_LAUNCH((radix_scatter<KeyT, true>), (unsigned)ntiles, kThreads, smem, s, src_k, nullptr, dst_k, dst_i, n, shift, mask, tile_hist);
+      VAPC_LAUNCH((onesweep_kernel<KeyT, LookT, true>), (unsigned)ntiles, kThreads, smem, s, src_k, nullptr, dst_k, dst_i, n, shift, mask,
+                  ghist + p * kRadix, look, ticket);
     else
-      VAPC_LAUNCH((radix_scatter<KeyT, false>), (unsigned)ntiles, kThreads, smem, s, src_k, src_i, dst_k, dst_i, n, shift, mask, tile_hist);
+      VAPC_LAUNCH((onesweep_kernel<KeyT, LookT, false>), (unsigned)ntiles, kThreads, smem, s, src_k, src_i, dst_k, dst_i, n, shift, mask,
+                  ghist + p * kRadix, look, ticket);
     KeyT* next_dst = (p == 0) ? spare : src_k;
     src_k = dst_k; dst_k = next_dst;
     uint32_t* ti = src_i; src_i = dst_i; dst_i = ti;
@@ -261,12 +296,32 @@ int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32
   *result_location = key_loc | ((passes & 1) ? 4 : 0);
   return VAPC_OK;
 }
+
+template <typename KeyT>
+int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int end_bit,
+              void* ws, int32_t* result_location, cudaStream_t s) {
+  const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
+  if (passes == 0) {
+    if (idx_is_iota) VAPC_LAUNCH(iota_kernel, kNumSMs * 8, 256, 0, s, idx, n);
+    *result_location = 0;
+    VAPC_CHECK_LAUNCH();
+    return VAPC_OK;
+  }
+  // 30-bit counts in 32-bit look-back words cover n < 2^30; beyond that (or when a test asks) 64-bit words
+  if (n < ((int64_t)1 << 30) && !g_force_wide_lookback)
+    return sweep_passes<KeyT, uint32_t>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, ws, result_location, s);
+  return sweep_passes<KeyT, unsigned long long>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, ws, result_location, s);
+}
 }  // namespace
+
+extern "C" int vapc_sort_debug_wide_lookback(int32_t on) {
+  g_force_wide_lookback = on != 0;
+  return VAPC_OK;
+}
 
 extern "C" size_t vapc_sort_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
-  const int64_t ntiles = num_tiles(n);
-  return (size_t)(ntiles + 2 * num_chunks(ntiles)) * kRadix * sizeof(uint32_t);
+  return look_offset() + (size_t)num_tiles(n) * kRadix * sizeof(unsigned long long);
 }
 
 extern "C" int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int32_t idx_is_iota,
