@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvapc_b200.so")
+LIB_PATH = os.environ.get("VAPC_B200_LIB") or os.path.join(_HERE, "libvapc_b200.so")  # env: a development build
 
 VAPC_OK = 0
 VAPC_E_INVALID = -1

@@ -26,6 +26,10 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kItems = 16;
 constexpr int kTile = kThreads * kItems;  // 4096
 constexpr int kMaxPasses = 8;             // 64-bit keys
+#ifndef VAPC_SORT_LOOK
+#define VAPC_SORT_LOOK 4
+#endif
+constexpr int kLookWindow = VAPC_SORT_LOOK;  // look-back words fetched at once
 
 template <typename KeyT>
 __device__ __forceinline__ unsigned digit_of(KeyT k, int shift, unsigned mask) {
@@ -115,19 +119,20 @@ template <> struct Look<unsigned long long> {
   }
 };
 
+template <typename KeyT> struct PairOf;  // (key, payload) as stored in the reorder buffer
+template <> struct PairOf<uint32_t> { typedef uint2 type; };           // one 64-bit shared-memory access per element
+template <> struct PairOf<unsigned long long> { typedef ulonglong2 type; };  // key + zero-extended payload
+
 template <typename KeyT>
 struct SweepSmem {
-  unsigned warp_cnt[kWarps][kRadix];  // per-warp digit counters -> per-warp exclusive prefixes
+  unsigned warp_cnt[kWarps][kRadix];  // per-warp running digit counters -> tile position of each warp's first key of a digit
   unsigned bin_start[kRadix];         // tile-local first slot of each digit
   unsigned delta[kRadix];             // global slot of tile position p holding digit d = p + delta[d]
   unsigned warp_s[33];
   unsigned tile;
-  union {
+  alignas(16) union {
     unsigned masks[3][kWarps][kRadix];  // ranking: lanes of a warp holding each digit (triple-buffered)
-    struct {
-      KeyT keys[kTile];
-      uint32_t idx[kTile];
-    } out;  // the tile reordered by digit
+    typename PairOf<KeyT>::type out[kTile];  // the tile reordered by digit
   } u;
 };
 
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_
                                                                LookT* __restrict__ look, unsigned* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem<KeyT>& sm = *reinterpret_cast<SweepSmem<KeyT>*>(smem_raw);
+  typedef typename PairOf<KeyT>::type Pair;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
 #pragma unroll
@@ -149,19 +155,31 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_
   __syncthreads();
   const unsigned tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kTile;
+  const bool full = tile_base + kTile <= n;
 
   // warp-striped load: warp w owns elements [w*512, (w+1)*512) of the tile, lane l takes element k*32 + l
   // in step k, so (warp, k, lane) order is input order.
+  // Slots past the end of the input (last tile only) hold all-ones keys: they take the highest digit and, coming last
+  // in input order, the last ranks of it, i.e. tile positions >= tile_n, which are never written out.  Nothing below
+  // needs a validity test, and no tile looks back at the last one.
   KeyT key[kItems];
-  const int64_t wbase = tile_base + (int64_t)warp * (32 * kItems) + lane;
-  const bool full = tile_base + kTile <= n;
+  uint32_t idx[kItems];
+  const int slot0 = warp * (32 * kItems) + lane;
+  const int64_t wbase = tile_base + slot0;
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys_in + wbase + k * 32) : (KeyT)0;
+  for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys_in + wbase + k * 32) : (KeyT)~(KeyT)0;
+  // 64-bit keys leave no registers for the payload: it is fetched when the tile is reordered instead
+  constexpr bool kLatePayload = sizeof(KeyT) == 8;
+  if (!kLatePayload) {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) idx[k] = IOTA ? (uint32_t)(wbase + k * 32) : ((full || wbase + k * 32 < n) ? __ldcs(idx_in + wbase + k * 32) : 0u);
+  }
 
   // rank inside the warp.  Lanes holding the same digit find each other by OR-ing their lane bit into a
-  // per-(warp, digit) shared word; the lowest such lane advances the warp's running digit counter.  The mask
-  // words are cleared by that leader one step later, hence three buffers and one warp barrier per step.
-  unsigned short rank[kItems];
+  // per-(warp, digit) shared word; the lowest such lane advances the warp's running digit counter with one
+  // shared-memory atomic.  The mask words are cleared by that leader one step later, hence three buffers and one
+  // warp barrier per step.  (Shared-memory wavefronts bound this kernel: every access below is one per key.)
+  unsigned rank2[kItems / 2];  // two 16-bit ranks per register
   const unsigned lt = (1u << lane) - 1u;
   unsigned* wc = sm.warp_cnt[warp];
   unsigned prev_d = 0;
@@ -169,64 +187,77 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     unsigned* mk = sm.u.masks[k % 3][warp];
-    const bool valid = full || (wbase + k * 32) < n;
     const unsigned d = digit_of(key[k], shift, mask);
-    if (valid) atomicOr(&mk[d], 1u << lane);
+    atomicOr(&mk[d], 1u << lane);
     __syncwarp();
     if (k > 0 && prev_leader) sm.u.masks[(k + 2) % 3][warp][prev_d] = 0;
-    const unsigned peers = valid ? mk[d] : 0u;
+    const unsigned peers = mk[d];
     const int leader = __ffs(peers) - 1;
-    const bool is_leader = valid && lane == leader;
+    const bool is_leader = lane == leader;
     unsigned before = 0;
-    if (is_leader) {
-      before = wc[d];
-      wc[d] = before + (unsigned)__popc(peers);
-    }
+    if (is_leader) before = atomicAdd(&wc[d], (unsigned)__popc(peers));
     before = __shfl_sync(0xffffffffu, before, leader);
-    rank[k] = (unsigned short)(before + (unsigned)__popc(peers & lt));
+    const unsigned r = before + (unsigned)__popc(peers & lt);
+    rank2[k / 2] = (k & 1) ? (rank2[k / 2] | (r << 16)) : r;
     prev_d = d;
     prev_leader = is_leader;
   }
   __syncthreads();
 
-  // per digit (thread tid == digit): exclusive prefix over warps -> tile count, published for the tiles behind
+  // per digit (thread tid == digit): the tile's count, published for the tiles behind; first slot in the tile;
+  // each warp's first slot
+  unsigned cnt[kWarps];
   unsigned run = 0;
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) {
-    const unsigned t = sm.warp_cnt[w][tid];
-    sm.warp_cnt[w][tid] = run;
-    run += t;
+    cnt[w] = sm.warp_cnt[w][tid];
+    run += cnt[w];
   }
   LookT* mine = look + (int64_t)tile * kRadix + tid;
   Look<LookT>::store(mine, (LookT)run | ((LookT)(tile == 0 ? 2 : 1) << Look<LookT>::kShift));
   unsigned total;
   const unsigned bstart = block_exclusive_scan(run, sm.warp_s, &total);
   sm.bin_start[tid] = bstart;
+  unsigned acc = bstart;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    sm.warp_cnt[w][tid] = acc;
+    acc += cnt[w];
+  }
   __syncthreads();
 
-  // reorder inside shared memory (the mask words are dead: every warp passed the barrier above)
+  // reorder inside shared memory (the mask words are dead: every warp passed the barriers above)
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    if (full || (wbase + k * 32) < n) {
-      const unsigned d = digit_of(key[k], shift, mask);
-      const unsigned pos = sm.bin_start[d] + wc[d] + rank[k];
-      sm.u.out.keys[pos] = key[k];
-      sm.u.out.idx[pos] = IOTA ? (uint32_t)(wbase + k * 32) : __ldcs(idx_in + wbase + k * 32);
-    }
+    const unsigned d = digit_of(key[k], shift, mask);
+    const unsigned pos = wc[d] + ((k & 1) ? (rank2[k / 2] >> 16) : (rank2[k / 2] & 0xffffu));
+    Pair pr;
+    pr.x = key[k];
+    pr.y = !kLatePayload ? idx[k] : (IOTA ? (uint32_t)(wbase + k * 32) : ((full || wbase + k * 32 < n) ? __ldcs(idx_in + wbase + k * 32) : 0u));
+    sm.u.out[pos] = pr;
   }
 
-  // decoupled look-back: sum the counts of the tiles in front until one has published its inclusive count
+  // decoupled look-back: sum the counts of the tiles in front until one has published its inclusive count.
+  // kLookWindow words are fetched at once (a hop is an L2 round trip); words behind the first inclusive one are
+  // simply ignored, a word that is not ready yet is polled again.
   LookT excl = 0;
   if (tile > 0) {
     const LookT vmask = ((LookT)1 << Look<LookT>::kShift) - 1;
-    const LookT* p = mine - kRadix;
-    while (true) {
-      const LookT w = Look<LookT>::load(p);
-      const unsigned st = (unsigned)(w >> Look<LookT>::kShift);
-      if (st == 0) continue;
-      excl += w & vmask;
-      if (st == 2) break;
-      p -= kRadix;
+    int64_t t = (int64_t)tile - 1;
+    bool done = false;
+    while (!done) {
+      LookT w[kLookWindow];
+#pragma unroll
+      for (int j = 0; j < kLookWindow; ++j) w[j] = (t - j >= 0) ? Look<LookT>::load(mine - (int64_t)(tile - (t - j)) * kRadix) : ((LookT)2 << Look<LookT>::kShift);
+#pragma unroll
+      for (int j = 0; j < kLookWindow; ++j) {
+        if (done) break;
+        LookT v = w[j];
+        while ((v >> Look<LookT>::kShift) == 0) v = Look<LookT>::load(mine - (int64_t)(tile - (t - j)) * kRadix);
+        excl += v & vmask;
+        done = (v >> Look<LookT>::kShift) == 2;
+      }
+      t -= kLookWindow;
     }
     Look<LookT>::store(mine, (excl + run) | ((LookT)2 << Look<LookT>::kShift));
   }
@@ -237,10 +268,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_
   const int tile_n = (int)min((int64_t)kTile, n - tile_base);
 #pragma unroll 4
   for (int p = tid; p < tile_n; p += kThreads) {
-    const KeyT k = sm.u.out.keys[p];
-    const unsigned dst = (unsigned)p + sm.delta[digit_of(k, shift, mask)];
-    keys_out[dst] = k;
-    idx_out[dst] = sm.u.out.idx[p];
+    const Pair pr = sm.u.out[p];
+    const unsigned dst = (unsigned)p + sm.delta[digit_of((KeyT)pr.x, shift, mask)];
+    keys_out[dst] = (KeyT)pr.x;
+    idx_out[dst] = (uint32_t)pr.y;
   }
 }
 
