@@ -87,11 +87,26 @@ VAPC_API int vapc_grid_from_bounds(vapc_grid_t* grid_host, const double* minmax6
 
 /* ---- packed keys (internal form of the voxel triple; the groupby key of vapc.py:724, :843,
  * :877, :959, :1081).  keys: uint32 or uint64 per grid->key_bytes.  xyzw (nullable): 32-byte
- * records {x, y, z, 0} written alongside so that later per-voxel gathers cost one sector per
- * point.  status (int32, device, caller-zeroed): bit 0 set if a point fell outside the grid. */
+ * records {x, y, z, bit pattern of the point index} written alongside so that later per-voxel
+ * gathers cost one sector per point.  status (int32, device, caller-zeroed): bit 0 set if a point fell outside the grid. */
 VAPC_API int vapc_pack_keys_f64(const double* x, const double* y, const double* z, int64_t n,
                        const vapc_grid_t* grid_host, void* keys, double* xyzw, int32_t* status,
                        void* stream);
+/* Same keys and records, but written in KEY-PREFIX BUCKET order: bucket b = the leading
+ * *bucket_bits_host = min(8, bits[0]) bits of the key (high bits of the voxel x index); inside a
+ * bucket the points keep their input order (stable).  bucket_start (device, uint32[257]) receives
+ * the first slot of every bucket and n at [2^bucket_bits].  The record of a point carries its
+ * ORIGINAL index as a bit pattern in the fourth slot, so everything downstream that gathers records
+ * by bucketed position (vapc_reduce_moments, vapc_closest_to_cog) still reports original indices.
+ * Purpose: the per-voxel gathers then stay inside an L2-sized window of records instead of costing a
+ * 128-byte HBM line per random 32-byte record, and the buckets are the segments of
+ * vapc_sort_pairs_segmented, which only has to sort the remaining key bits.  keys_orig receives the
+ * keys in input order (the first step; vapc_point2voxel_dense wants them too). */
+VAPC_API size_t vapc_bucket_workspace_bytes(int64_t n);
+VAPC_API int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n,
+                               const vapc_grid_t* grid_host, void* keys_bucketed, double* xyzw_bucketed,
+                               void* keys_orig, uint32_t* bucket_start, int32_t* bucket_bits_host,
+                               int32_t* status, void* ws, size_t ws_bytes, void* stream);
 /* voxel triple back from keys (n keys -> 3 x int64) */
 VAPC_API int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* grid_host, int64_t* vx,
                      int64_t* vy, int64_t* vz, void* stream);
@@ -112,6 +127,14 @@ VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32
                     uint32_t* idx_alt, int32_t idx_is_iota, int64_t n, int32_t key_bytes,
                     int32_t end_bit, void* ws, size_t ws_bytes, int32_t* result_location_host,
                     void* stream);
+/* Segmented form: the array is nseg <= 256 consecutive segments [seg_start[s], seg_start[s+1])
+ * (device uint32[nseg+1], seg_start[nseg] = n), each sorted independently by bits [0, end_bit) in the
+ * same launches; idx_is_iota numbers the elements by their global position.  Two key buffers
+ * (keys is overwritten).  Same workspace size and result_location as vapc_sort_pairs. */
+VAPC_API int vapc_sort_pairs_segmented(void* keys, void* keys_alt, uint32_t* idx, uint32_t* idx_alt,
+                              int32_t idx_is_iota, int64_t n, int32_t key_bytes, int32_t end_bit,
+                              const uint32_t* seg_start, int32_t nseg, void* ws, size_t ws_bytes,
+                              int32_t* result_location_host, void* stream);
 
 /* ---- run-length segmentation of sorted keys into the voxel table ----------------------
  * Step 1: count voxels.  Writes per-tile head counts + their exclusive scan into ws and the
@@ -130,12 +153,15 @@ VAPC_API int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key_b
  * different tiles or different GPUs combine with Chan's pairwise update without loss
  * (vapc_merge_partials).  Inside a voxel, points are visited in original point order.
  * point2voxel (nullable) gets the voxel row of every point.  Layout: mean3 is [3][V], m2 is
- * [6][V] (column stride V = nvoxels_host).  xyzw = the records vapc_pack_keys wrote. */
-VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n,
+ * [6][V] (column stride V = nvoxels_host).  xyzw = the records vapc_pack_keys_f64 (input order) or
+ * vapc_pack_records_bucketed (bucket order) wrote, pos_sorted = the sorted payload = position of each
+ * point's record in xyzw; original point indices come from the records.  idx_sorted (nullable)
+ * receives the original point index of every sorted position. */
+VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n,
                         const vapc_grid_t* grid_host, const double* xyzw, int64_t nvoxels_host,
                         void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
-                        double* mean3, double* m2, uint32_t* point2voxel, void* ws,
-                        size_t ws_bytes, void* stream);
+                        double* mean3, double* m2, uint32_t* point2voxel, uint32_t* idx_sorted,
+                        void* ws, size_t ws_bytes, void* stream);
 
 /* point -> voxel map in ORIGINAL point order through a direct-address table over the packed key space
  * (table[key] = voxel row).  For grids of <= 2^25 cells the table stays in the 126 MB L2 and this costs
@@ -168,8 +194,8 @@ VAPC_API int vapc_voxel_center_corner(const void* voxel_keys, int64_t nvoxels, c
 /* ---- a9, a10, a15 closest-to-centroid (vapc.py:776-825, 1188-1195) ---------------------
  * Per voxel: min over its points of sqrt((X-cog_x)^2 + (Y-cog_y)^2 + (Z-cog_z)^2) (plain
  * products, left-to-right sum, no FMA — numpy's evaluation order) and the LOWEST original
- * index attaining it. */
-VAPC_API int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n,
+ * index attaining it.  pos_sorted / xyzw as in vapc_reduce_moments. */
+VAPC_API int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n,
                         int32_t key_bytes, const double* xyzw, const double* cog3,
                         int64_t nvoxels_host, double* min_dist, uint32_t* argmin_idx, void* ws,
                         size_t ws_bytes, void* stream);

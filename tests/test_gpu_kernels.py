@@ -107,6 +107,25 @@ def test_sort_pairs_wide_lookback_words(E):
     np.testing.assert_array_equal(_u32(idx), order)
 
 
+@pytest.mark.parametrize("n,nseg,bits,dtype", [(1, 1, 5, np.uint32), (5000, 3, 9, np.uint32), (300_000, 256, 16, np.uint32),
+                                                (300_000, 200, 24, np.uint64), (1_000_003, 37, 11, np.uint32), (70_000, 256, 40, np.uint64)])
+def test_sort_pairs_segmented(E, n, nseg, bits, dtype):
+    """Every segment sorted independently and stably by the low bits; empty, tiny and multi-tile segments mixed."""
+    rng = np.random.default_rng(n + nseg)
+    cuts = np.sort(rng.integers(0, n + 1, nseg - 1)) if nseg > 1 else np.zeros(0, np.int64)
+    if nseg > 4:
+        cuts[1] = cuts[0]  # an empty segment
+    seg_start = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+    keys = rng.integers(0, (1 << bits) - 1, n, dtype=np.uint64, endpoint=True).astype(dtype)
+    seg_of = np.searchsorted(seg_start, np.arange(n), side="right") - 1
+    order = np.lexsort((np.arange(n), keys, seg_of))  # by segment, then key, then position
+    tk = torch.from_numpy(keys.view(np.int32 if dtype == np.uint32 else np.int64)).cuda()
+    ss = torch.from_numpy(seg_start.astype(np.uint32).view(np.int32)).cuda()
+    ks, idx = E.sort_pairs_segmented(tk, bits, ss, nseg)
+    np.testing.assert_array_equal(_np(ks).view(dtype), keys[order])
+    np.testing.assert_array_equal(_u32(idx), order)
+
+
 def test_sort_pairs_with_payload_and_partial_bits(E):
     rng = np.random.default_rng(5)
     n = 50000
@@ -119,8 +138,8 @@ def test_sort_pairs_with_payload_and_partial_bits(E):
 
 
 # --------------------------------------------------------------------------------------
-def check_cloud(E, x, y, z, vs, origin, eig_faithful=False):
-    cloud = E.VoxelCloud.build(x, y, z, vs, origin)
+def check_cloud(E, x, y, z, vs, origin, eig_faithful=False, bucketed=True):
+    cloud = E.VoxelCloud.build(x, y, z, vs, origin, bucketed=bucketed)
     vx, vy, vz = O.voxelize(x, y, z, origin, vs)
     g = O.group_by_voxel(vx, vy, vz)
     V = g.nvoxels
@@ -198,6 +217,8 @@ def check_cloud(E, x, y, z, vs, origin, eig_faithful=False):
 ])
 def test_voxel_table_vs_oracle(E, kind, n, vs, origin):
     x, y, z = make_cloud(kind, n, seed=n + int(vs * 100))
+    if kind == "negative":  # the path with records in input order + full sort stays covered
+        check_cloud(E, x, y, z, vs, origin, bucketed=False)
     check_cloud(E, x, y, z, vs, origin)
 
 
@@ -298,12 +319,57 @@ def test_two_epoch_join_and_mahalanobis_vs_oracle(E):
 
 
 def test_reproducible_bitwise(E):
-    """No atomics in the reductions: two runs give bit-identical tables."""
+    """No atomics in the reductions: two runs give bit-identical tables — and so does the path that keeps the
+    records in input order and sorts all key bits (bucketed=False)."""
     x, y, z = make_cloud("clustered", 150000, 13)
     a = E.VoxelCloud.build(x, y, z, 0.25, [0, 0, 0])
     b = E.VoxelCloud.build(x, y, z, 0.25, [0, 0, 0])
-    for name in ("mean3", "m2", "count", "first_idx", "point2voxel", "idx_sorted"):
+    c = E.VoxelCloud.build(x, y, z, 0.25, [0, 0, 0], bucketed=False)
+    for name in ("mean3", "m2", "count", "first_idx", "point2voxel", "idx_sorted", "keys_sorted", "voxel_keys", "start"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+        assert torch.equal(getattr(a, name), getattr(c, name)), name + " (bucketed vs input-order records)"
+
+
+def test_bucketed_records(E):
+    """vapc_pack_records_bucketed: buckets are the leading key bits in order, stable inside a bucket, every record
+    carries its point and its original index."""
+    import ctypes as C
+    from vapc_b200 import _lib as L
+
+    for kind, n, vs in (("uniform", 100_003, 0.05), ("clustered", 50_000, 0.5), ("utm", 30_000, 0.05), ("uniform", 7, 10.0)):
+        x, y, z = make_cloud(kind, n, seed=n)
+        dx, dy, dz = (torch.from_numpy(a).cuda() for a in (x, y, z))
+        g = E.grid_from_bounds(vs, [0, 0, 0], E.coordinate_bounds(dx, dy, dz))
+        kd = torch.int32 if g.key_bytes == 4 else torch.int64
+        keys_b, keys_o = torch.empty(n, dtype=kd, device="cuda"), torch.empty(n, dtype=kd, device="cuda")
+        rec = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+        bstart = torch.empty(257, dtype=torch.int32, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        wsb = L.raw("vapc_bucket_workspace_bytes")(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        bits = C.c_int32(0)
+        L.call("vapc_pack_records_bucketed", E._ptr(dx), E._ptr(dy), E._ptr(dz), n, C.byref(g), E._ptr(keys_b), E._ptr(rec), E._ptr(keys_o),
+               E._ptr(bstart), C.byref(bits), E._ptr(status), E._ptr(ws), wsb, E._stream())
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        mb = bits.value
+        assert mb == min(8, g.bits[0])
+        ut = np.uint32 if g.key_bytes == 4 else np.uint64
+        ko = _np(keys_o).view(ut).astype(np.uint64)
+        vx, vy, vz = O.voxelize(x, y, z, [0, 0, 0], vs)
+        ref = ((vx - g.vmin[0]).astype(np.uint64) << np.uint64(g.bits[1] + g.bits[2])) | ((vy - g.vmin[1]).astype(np.uint64) << np.uint64(g.bits[2])) \
+            | (vz - g.vmin[2]).astype(np.uint64)
+        np.testing.assert_array_equal(ko, ref)
+        bucket = (ko >> np.uint64(g.total_bits - mb)).astype(np.int64)
+        order = np.argsort(bucket, kind="stable")
+        np.testing.assert_array_equal(_np(keys_b).view(ut).astype(np.uint64), ko[order])
+        r = _np(rec)
+        np.testing.assert_array_equal(r[:, 3].copy().view(np.int64) & 0xFFFFFFFF, order)  # (32-bit keys ride in the upper half)
+        np.testing.assert_array_equal(r[:, 0], x[order])
+        np.testing.assert_array_equal(r[:, 1], y[order])
+        np.testing.assert_array_equal(r[:, 2], z[order])
+        nb = 1 << mb
+        np.testing.assert_array_equal(_u32(bstart)[: nb + 1], np.concatenate([[0], np.cumsum(np.bincount(bucket, minlength=nb))]))
 
 
 @pytest.mark.parametrize("n", [3_000_000])

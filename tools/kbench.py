@@ -61,7 +61,7 @@ def bench_sort(n=100_000_000, bits=24):
     return ok
 
 
-def bench_build(n=100_000_000):
+def bench_build(n=100_000_000, bucketed=1):
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
     y = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
@@ -74,7 +74,7 @@ def bench_build(n=100_000_000):
         rec.append((name, phase, ev))
 
     def step():
-        c = E.VoxelCloud.build(x, y, z, 0.1, (0.0, 0.0, 0.0))
+        c = E.VoxelCloud.build(x, y, z, 0.1, (0.0, 0.0, 0.0), bucketed=bool(bucketed))
         c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
         return c
 
@@ -96,7 +96,7 @@ def bench_build(n=100_000_000):
             pend[name] = ev
         else:
             per.setdefault(name, []).append(pend.pop(name).elapsed_time(ev))
-    print(f"build+stats n={n} voxels={c.nvoxels}: {a.elapsed_time(b) / reps:.3f} ms/step = {n * reps / a.elapsed_time(b) / 1e6:.2f} Gpts/s")
+    print(f"build+stats bucketed={bucketed} n={n} voxels={c.nvoxels}: {a.elapsed_time(b) / reps:.3f} ms/step = {n * reps / a.elapsed_time(b) / 1e6:.2f} Gpts/s")
     for k, v in per.items():
         print(f"   {k:28s} {sum(v) / reps:.3f} ms/step ({len(v) // reps} calls)")
 

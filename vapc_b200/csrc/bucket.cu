@@ -1,0 +1,234 @@
+// Keys + 32-byte point records, written in KEY-PREFIX BUCKET order instead of input order.
+//
+// Why: the per-voxel reduction gathers one record per point in sorted-key order.  With the records in input
+// order those are random 32-byte reads over the whole array and every one of them costs a full 128-byte line
+// from HBM (measured: 13.4 GB of DRAM reads for 3.2 GB of records at 1e8 points, profiles/).  Here the
+// records are grouped by the leading bits of the packed key — the high bits of the voxel x index, <= 256
+// buckets — while they are produced, so that the later gathers of one bucket stay inside a window of
+// records that fits the 126 MB L2 and every line is fetched from HBM once.  The buckets are also exactly the
+// segments that vapc_sort_pairs_segmented sorts by the REMAINING key bits, which saves the radix pass over
+// the leading digit.
+//
+//   keys_hist_kernel      reads x, y, z; writes the packed keys in input order and counts the bucket digit
+//                         (shared-memory atomics)                                              24 + K B/pt
+//   bucket_scatter_kernel reads the keys of a 4096-point tile, ranks the bucket digit (radix_rank.cuh, stable),
+//                         decoupled look-back for the global offsets, then reads x, y, z and writes key and
+//                         record {x, y, z, index} at the bucketed position, records straight from registers as one
+//                         256-bit store each (a full sector)                              K + 24 + K + 32 B/pt
+// (One fused kernel was tried first: with the three IEEE divisions of the key in front of the count publication
+// every tile waited on its predecessors' look-back words — 34 % of all stall samples on that poll, 4.4 ms per 1e8
+// points.  Keys first, then a scatter pass whose tiles publish right after a 16 KB key load, is 2x faster.)
+// Stable: inside a bucket the points keep their input order, so after the (stable) segmented sort the points
+// of a voxel are still in original index order.
+#include <algorithm>
+
+#include "radix_rank.cuh"
+
+namespace {
+using namespace rr;
+#ifndef VAPC_BUCKET_ITEMS
+#define VAPC_BUCKET_ITEMS 6
+#endif
+#ifndef VAPC_BUCKET_MINB
+#define VAPC_BUCKET_MINB 3
+#endif
+constexpr int kItems = VAPC_BUCKET_ITEMS;
+constexpr int kTile = kThreads * kItems;  // 1536 points: the reordered records of a tile take 48 KB of shared memory (6 vs 8 items: 2.22 vs 2.42 ms)
+
+template <typename KeyT>
+__device__ __forceinline__ unsigned bucket_of(KeyT key, int shift, unsigned mask) { return (unsigned)(key >> shift) & mask; }
+
+// keys in input order + histogram of the bucket digit
+template <typename KeyT, int VEC>
+__global__ void __launch_bounds__(kThreads) keys_hist_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                             int64_t n, Grid g, int shift, unsigned mask, KeyT* __restrict__ keys,
+                                                             uint32_t* __restrict__ hist, int* __restrict__ status) {
+  __shared__ unsigned sh[kRadix];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  int bad = 0;
+  const int64_t nvec = n / VEC;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    if (VEC == 2) {
+      const double2 a = __ldcs(reinterpret_cast<const double2*>(x) + v);
+      const double2 b = __ldcs(reinterpret_cast<const double2*>(y) + v);
+      const double2 c = __ldcs(reinterpret_cast<const double2*>(z) + v);
+      const KeyT k0 = pack_one<KeyT>(a.x, b.x, c.x, g, bad);
+      const KeyT k1 = pack_one<KeyT>(a.y, b.y, c.y, g, bad);
+      if (sizeof(KeyT) == 4) {
+        reinterpret_cast<uint2*>(keys)[v] = make_uint2((unsigned)k0, (unsigned)k1);
+      } else {
+        reinterpret_cast<ulonglong2*>(keys)[v] = make_ulonglong2(k0, k1);
+      }
+      atomicAdd(&sh[bucket_of(k0, shift, mask)], 1u);
+      atomicAdd(&sh[bucket_of(k1, shift, mask)], 1u);
+    } else {
+      const KeyT k = pack_one<KeyT>(ld_stream(x + v), ld_stream(y + v), ld_stream(z + v), g, bad);
+      keys[v] = k;
+      atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
+    }
+  }
+  if (VEC == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const KeyT k = pack_one<KeyT>(x[n - 1], y[n - 1], z[n - 1], g, bad);
+    keys[n - 1] = k;
+    atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
+  }
+  __syncthreads();
+  const unsigned c = sh[threadIdx.x];
+  if (c) atomicAdd(&hist[threadIdx.x], c);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+}
+
+// bucket_start[b] = first slot of bucket b, [nb] = n   (digit_base = exclusive scan of the histogram)
+__global__ void bucket_start_kernel(const uint32_t* __restrict__ digit_base, int nb, uint32_t n, uint32_t* __restrict__ bucket_start) {
+  const int t = threadIdx.x;
+  if (t < nb) bucket_start[t] = digit_base[t];
+  if (t == 0) bucket_start[nb] = n;
+}
+
+// 32-bit keys ride in the upper half of the record's index slot while the tile is reordered (and stay there in
+// memory: readers only look at the lower half); 64-bit keys get their own array.
+template <typename KeyT> struct KeySlots { KeyT keys[kTile]; };
+template <> struct KeySlots<uint32_t> {};
+
+template <typename KeyT>
+struct BucketSmem {
+  RankSmem r;
+  KeySlots<KeyT> k;
+  alignas(32) union {
+    MaskBuffers masks;
+    double4 rec[kTile];  // the tile's records reordered by bucket
+  } u;
+};
+
+template <typename KeyT, typename LookT>
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 2) bucket_scatter_kernel(
+    const KeyT* __restrict__ keys, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n, int shift,
+    unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyT* __restrict__ keys_b,
+    double4* __restrict__ rec_b) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  BucketSmem<KeyT>& sm = *reinterpret_cast<BucketSmem<KeyT>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) sm.r.tile = atomicAdd(ticket, 1u);
+  rank_init(sm.r, sm.u.masks);
+  __syncthreads();
+  const unsigned tile = sm.r.tile;
+  const int64_t tile_base = (int64_t)tile * kTile;
+  const bool full = tile_base + kTile <= n;
+
+  // warp-striped: warp w owns points [w*256, (w+1)*256) of the tile, lane l takes point k*32 + l in step k.
+  // Slots past the end of the input (last tile) hold all-ones keys: highest bucket, last ranks, never written.
+  const int64_t wbase = tile_base + warp * (32 * kItems) + lane;
+  KeyT key[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys + wbase + k * 32) : (KeyT)~(KeyT)0;
+  // the coordinates are only needed once the positions are known; their loads overlap the ranking
+  double px[kItems], py[kItems], pz[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const bool valid = full || wbase + k * 32 < n;
+    px[k] = valid ? ld_stream(x + wbase + k * 32) : 0.0;
+    py[k] = valid ? ld_stream(y + wbase + k * 32) : 0.0;
+    pz[k] = valid ? ld_stream(z + wbase + k * 32) : 0.0;
+  }
+
+  unsigned rank2[kItems / 2];
+  warp_rank<kItems>([&](int k) { return bucket_of(key[k], shift, mask); }, sm.r, sm.u.masks, rank2);
+  __syncthreads();
+
+  LookT* mine = look + (int64_t)tile * kRadix + tid;
+  unsigned bstart;
+  const unsigned run = digit_offsets<LookT>(sm.r, mine, tile == 0, &bstart);
+
+  // reorder the records inside shared memory (the mask words are dead: every warp passed the barriers above), so
+  // that a bucket's run leaves as whole 128-byte lines: scattered single-sector stores were measured at a quarter of
+  // the HBM write bandwidth (profiles/).
+  const unsigned* wc = sm.r.warp_cnt[warp];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
+    unsigned long long w = (uint32_t)(wbase + k * 32);
+    if (sizeof(KeyT) == 4) w |= (unsigned long long)key[k] << 32;
+    else reinterpret_cast<KeyT*>(&sm.k)[pos] = key[k];
+    sm.u.rec[pos] = make_double4(px[k], py[k], pz[k], __longlong_as_double((long long)w));
+  }
+
+  const LookT excl = look_back<LookT>(mine, (int64_t)tile, run);
+  sm.r.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
+  __syncthreads();
+
+  const int tile_n = (int)min((int64_t)kTile, n - tile_base);
+#pragma unroll 4
+  for (int p = tid; p < tile_n; p += kThreads) {
+    const double4 r = sm.u.rec[p];
+    const KeyT k = sizeof(KeyT) == 4 ? (KeyT)((unsigned long long)__double_as_longlong(r.w) >> 32) : reinterpret_cast<const KeyT*>(&sm.k)[p];
+    const unsigned dst = (unsigned)p + sm.r.delta[bucket_of(k, shift, mask)];
+    st_record(rec_b + dst, r.x, r.y, r.z, r.w);
+    keys_b[dst] = k;
+  }
+}
+
+inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
+// workspace: [bucket histogram -> first slots, 256 u32][ticket (256 B)][look-back ntiles x 256 x 8 B]
+constexpr size_t kHistBytes = kRadix * sizeof(uint32_t);
+
+template <typename KeyT, typename LookT>
+int bucket_impl(const double* x, const double* y, const double* z, int64_t n, const Grid& g, int mb, KeyT* keys_b, double4* rec_b, KeyT* keys_orig,
+                uint32_t* bucket_start, int32_t* status, void* ws, cudaStream_t s) {
+  const int shift = g.bx + g.by + g.bz - mb;  // the bucket digit = the leading mb bits of the key
+  const unsigned mask = (1u << mb) - 1u;
+  const int64_t ntiles = num_tiles(n);
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base);
+  unsigned* ticket = reinterpret_cast<unsigned*>(base + kHistBytes);
+  LookT* look = reinterpret_cast<LookT*>(base + kHistBytes + 256);
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(base, 0, kHistBytes + 256 + (size_t)ntiles * kRadix * sizeof(LookT), s));
+  const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16));
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(keys_orig)) & 15u) == 0;
+  if (vec) VAPC_LAUNCH((keys_hist_kernel<KeyT, 2>), hgrid, kThreads, 0, s, x, y, z, n, g, shift, mask, keys_orig, hist, status);
+  else VAPC_LAUNCH((keys_hist_kernel<KeyT, 1>), hgrid, kThreads, 0, s, x, y, z, n, g, shift, mask, keys_orig, hist, status);
+  VAPC_LAUNCH(digit_scan_kernel, 1, kThreads, 0, s, hist, nullptr, 1);
+  VAPC_LAUNCH(bucket_start_kernel, 1, kThreads, 0, s, hist, 1 << mb, (uint32_t)n, bucket_start);
+  const size_t smem = sizeof(BucketSmem<KeyT>);
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, LookT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, LookT>), (unsigned)ntiles, kThreads, smem, s, keys_orig, x, y, z, n, shift, mask, hist, look, ticket, keys_b,
+              rec_b);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+}  // namespace
+
+extern "C" size_t vapc_bucket_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return kHistBytes + 256 + (size_t)num_tiles(n) * kRadix * sizeof(unsigned long long);
+}
+
+extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n, const vapc_grid_t* grid_host,
+                                          void* keys_bucketed, double* xyzw_bucketed, void* keys_orig, uint32_t* bucket_start,
+                                          int32_t* bucket_bits_host, int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+  if (!grid_host || !(grid_host->voxel_size > 0)) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad grid");
+  if (n < 0 || !bucket_bits_host) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad arguments");
+  const Grid g = to_device_grid(grid_host);
+  const int mb = g.bx < kRadixBits ? g.bx : kRadixBits;
+  *bucket_bits_host = mb;
+  if (n == 0) return VAPC_OK;
+  if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: n must be < 2^32 per GPU");
+  if (!x || !y || !z || !keys_bucketed || !xyzw_bucketed || !keys_orig || !bucket_start || !status)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: null buffer");
+  if (reinterpret_cast<uintptr_t>(xyzw_bucketed) & 31u) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: xyzw must be 32-byte aligned");
+  if (!ws || ws_bytes < vapc_bucket_workspace_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_pack_records_bucketed: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  double4* rec = reinterpret_cast<double4*>(xyzw_bucketed);
+  const bool wide = n >= ((int64_t)1 << 30);
+  typedef unsigned long long u64;
+  if (grid_host->key_bytes == 4) {
+    if (!wide) return bucket_impl<uint32_t, uint32_t>(x, y, z, n, g, mb, static_cast<uint32_t*>(keys_bucketed), rec, static_cast<uint32_t*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<uint32_t, u64>(x, y, z, n, g, mb, static_cast<uint32_t*>(keys_bucketed), rec, static_cast<uint32_t*>(keys_orig), bucket_start, status, ws, s);
+  }
+  if (grid_host->key_bytes == 8) {
+    if (!wide) return bucket_impl<u64, uint32_t>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u64, u64>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+  }
+  return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: key_bytes must be 4 or 8");
+}

@@ -67,6 +67,23 @@ __device__ __forceinline__ double shift_center(long long v, double o, double vs)
   return __dadd_rn(o, __dmul_rn(__dadd_rn((double)v, 0.5), vs));
 }
 
+// Packed key of one point (x most significant).  `bad` is OR-ed with 1 when a relative voxel coordinate does
+// not fit its bit field (NaN / out-of-box point).
+template <typename KeyT>
+__device__ __forceinline__ KeyT pack_one(double px, double py, double pz, const Grid& g, int& bad, unsigned long long* rx_out = nullptr) {
+  const unsigned long long rx = (unsigned long long)(voxel_of(px, g.ox, g.vs) - g.minx);
+  const unsigned long long ry = (unsigned long long)(voxel_of(py, g.oy, g.vs) - g.miny);
+  const unsigned long long rz = (unsigned long long)(voxel_of(pz, g.oz, g.vs) - g.minz);
+  // (unsigned) relative coordinates must fit their bit fields; NaN / out-of-box points do not
+  bad |= (g.bx < 64 && (rx >> g.bx)) || (g.by < 64 && (ry >> g.by)) || (g.bz < 64 && (rz >> g.bz));
+  const int sxy = g.by + g.bz;
+  unsigned long long k = rz;
+  if (g.bz < 64) k |= ry << g.bz;
+  if (sxy < 64) k |= rx << sxy;
+  if (rx_out) *rx_out = rx;
+  return (KeyT)k;
+}
+
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 
@@ -76,6 +93,9 @@ __device__ __forceinline__ double4 ld_record(const double4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
+// the original point index travels in the record's fourth slot as a bit pattern
+__device__ __forceinline__ double index_as_record_w(uint32_t i) { return __longlong_as_double((long long)i); }
+__device__ __forceinline__ uint32_t record_index(const double4& r) { return (uint32_t)__double_as_longlong(r.w); }
 __device__ __forceinline__ void st_record(double4* p, double x, double y, double z, double w) {
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
 }

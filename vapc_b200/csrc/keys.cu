@@ -111,20 +111,6 @@ __global__ void __launch_bounds__(kThreads) voxel_coords_kernel(const double* __
 // ---- packed keys (+ 32-byte xyzw records) ---------------------------------------------------
 // Each thread handles two consecutive points per iteration so that x/y/z loads are 16-byte
 // vector loads when the columns are 16-byte aligned (VEC=2); VEC=1 is the unaligned fallback.
-template <typename KeyT>
-__device__ __forceinline__ KeyT pack_one(double px, double py, double pz, const Grid& g, int& bad) {
-  const unsigned long long rx = (unsigned long long)(voxel_of(px, g.ox, g.vs) - g.minx);
-  const unsigned long long ry = (unsigned long long)(voxel_of(py, g.oy, g.vs) - g.miny);
-  const unsigned long long rz = (unsigned long long)(voxel_of(pz, g.oz, g.vs) - g.minz);
-  // (unsigned) relative coordinates must fit their bit fields; NaN / out-of-box points do not
-  bad |= (g.bx < 64 && (rx >> g.bx)) || (g.by < 64 && (ry >> g.by)) || (g.bz < 64 && (rz >> g.bz));
-  const int sxy = g.by + g.bz;
-  unsigned long long k = rz;
-  if (g.bz < 64) k |= ry << g.bz;
-  if (sxy < 64) k |= rx << sxy;
-  return (KeyT)k;
-}
-
 template <typename KeyT, int VEC>
 __global__ void __launch_bounds__(kThreads) pack_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                              const double* __restrict__ z, int64_t n, Grid g,
@@ -146,20 +132,20 @@ __global__ void __launch_bounds__(kThreads) pack_keys_kernel(const double* __res
         reinterpret_cast<ulonglong2*>(keys)[v] = make_ulonglong2(k0, k1);
       }
       if (xyzw) {
-        st_record(xyzw + 2 * v, a.x, b.x, c.x, 0.0);
-        st_record(xyzw + 2 * v + 1, a.y, b.y, c.y, 0.0);
+        st_record(xyzw + 2 * v, a.x, b.x, c.x, index_as_record_w((uint32_t)(2 * v)));
+        st_record(xyzw + 2 * v + 1, a.y, b.y, c.y, index_as_record_w((uint32_t)(2 * v + 1)));
       }
     } else {
       const double a = ld_stream(x + v), b = ld_stream(y + v), c = ld_stream(z + v);
       keys[v] = pack_one<KeyT>(a, b, c, g, bad);
-      if (xyzw) st_record(xyzw + v, a, b, c, 0.0);
+      if (xyzw) st_record(xyzw + v, a, b, c, index_as_record_w((uint32_t)v));
     }
   }
   if (VEC == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t i = n - 1;
     const double a = x[i], b = y[i], c = z[i];
     keys[i] = pack_one<KeyT>(a, b, c, g, bad);
-    if (xyzw) xyzw[i] = make_double4(a, b, c, 0.0);
+    if (xyzw) xyzw[i] = make_double4(a, b, c, index_as_record_w((uint32_t)i));
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
 }

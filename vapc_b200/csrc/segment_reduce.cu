@@ -163,10 +163,10 @@ __device__ __forceinline__ void tile_prologue(TileSmem<KeyT>& sm, const KeyT* __
 // ---- step 2: moments ------------------------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
-    const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
+    const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
     const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
     uint32_t* __restrict__ count, uint32_t* __restrict__ first_idx, double* __restrict__ mean3, double* __restrict__ m2,
-    uint32_t* __restrict__ point2voxel, uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
+    uint32_t* __restrict__ point2voxel, uint32_t* __restrict__ idx_sorted, uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<KeyT>& sm = *reinterpret_cast<TileSmem<KeyT>*>(smem_raw);
   const int64_t base = (int64_t)blockIdx.x * kSegTile;
@@ -175,15 +175,15 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
   unsigned inc[kItems], nheads;
   int tile_n;
 
-  // issue the index loads + gathers first so that they overlap the scan
+  // issue the record-position loads + gathers first so that they overlap the scan
   const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
   uint32_t idx[kItems];
   if (p0 + kItems <= n) {
-    const uint4 v = *reinterpret_cast<const uint4*>(idx_sorted + p0);
+    const uint4 v = *reinterpret_cast<const uint4*>(pos_sorted + p0);
     idx[0] = v.x; idx[1] = v.y; idx[2] = v.z; idx[3] = v.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < kItems; ++j) idx[j] = (p0 + j < n) ? idx_sorted[p0 + j] : 0u;
+    for (int j = 0; j < kItems; ++j) idx[j] = (p0 + j < n) ? pos_sorted[p0 + j] : 0u;
   }
   double4 rec[kItems];
 #pragma unroll
@@ -192,6 +192,18 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
       rec[j] = ld_record(xyzw + idx[j]);
     } else {
       rec[j] = make_double4(0, 0, 0, 0);
+    }
+  }
+  // the record carries the point's original index (bit pattern in w); from here on idx[] is that index
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) idx[j] = record_index(rec[j]);
+  if (idx_sorted) {
+    if (p0 + kItems <= n) {
+      *reinterpret_cast<uint4*>(idx_sorted + p0) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j)
+        if (p0 + j < n) idx_sorted[p0 + j] = idx[j];
     }
   }
 
@@ -363,7 +375,7 @@ __device__ __forceinline__ double ref_distance(double px, double py, double pz, 
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx_sorted,
+__global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted,
                                                            int64_t n, const double4* __restrict__ xyzw, const double* __restrict__ cog3,
                                                            const uint32_t* __restrict__ tile_first, int64_t nvox,
                                                            double* __restrict__ min_dist, uint32_t* __restrict__ argmin_idx,
@@ -381,10 +393,9 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
   for (int j = 0; j < kItems; ++j) {
     const int p = threadIdx.x * kItems + j;
     if (p0 + j < n) {
-      const uint32_t id = idx_sorted[p0 + j];
-      const double4 r = ld_record(xyzw + id);
+      const double4 r = ld_record(xyzw + pos_sorted[p0 + j]);
       sm.x[p] = r.x; sm.y[p] = r.y; sm.z[p] = r.z;
-      idx_s[p] = id;
+      idx_s[p] = record_index(r);
     }
   }
   tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
@@ -510,17 +521,17 @@ extern "C" int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key
   return VAPC_OK;
 }
 
-extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n, const vapc_grid_t* grid_host,
+extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n, const vapc_grid_t* grid_host,
                                    const double* xyzw, int64_t nvoxels_host, void* voxel_keys, uint32_t* start, uint32_t* count,
-                                   uint32_t* first_idx, double* mean3, double* m2, uint32_t* point2voxel, void* ws,
-                                   size_t ws_bytes, void* stream) {
+                                   uint32_t* first_idx, double* mean3, double* m2, uint32_t* point2voxel, uint32_t* idx_sorted,
+                                   void* ws, size_t ws_bytes, void* stream) {
   if (!grid_host || n < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: bad arguments");
   if (n == 0) return VAPC_OK;
-  if (!keys_sorted || !idx_sorted || !xyzw || !voxel_keys || !start || !count || !first_idx || !mean3 || !m2)
+  if (!keys_sorted || !pos_sorted || !xyzw || !voxel_keys || !start || !count || !first_idx || !mean3 || !m2)
     return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: null buffer");
   if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_reduce_moments: workspace too small");
-  if (((uintptr_t)keys_sorted | (uintptr_t)idx_sorted) & 15u || ((uintptr_t)xyzw & 31u))
-    return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: keys/idx must be 16-byte and xyzw 32-byte aligned");
+  if (((uintptr_t)keys_sorted | (uintptr_t)pos_sorted | (uintptr_t)idx_sorted) & 15u || ((uintptr_t)xyzw & 31u))
+    return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: keys / positions / indices must be 16-byte and xyzw 32-byte aligned");
   const SegWs w = carve(ws, n);
   const Grid g = to_device_grid(grid_host);
   const int64_t nt = seg_tiles(n);
@@ -530,14 +541,14 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* idx_
     typedef uint32_t K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
+    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, idx_sorted, w.carry_cnt, w.carry);
   } else {
     typedef unsigned long long K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, w.carry_cnt, w.carry);
+    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, idx_sorted, w.carry_cnt, w.carry);
   }
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.n_long, 0, sizeof(uint32_t), s));
   VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
@@ -576,12 +587,12 @@ extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, cons
   return VAPC_OK;
 }
 
-extern "C" int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_sorted, int64_t n, int32_t key_bytes,
+extern "C" int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n, int32_t key_bytes,
                                    const double* xyzw, const double* cog3, int64_t nvoxels_host, double* min_dist,
                                    uint32_t* argmin_idx, void* ws, size_t ws_bytes, void* stream) {
   if (n < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: bad arguments");
   if (n == 0) return VAPC_OK;
-  if (!keys_sorted || !idx_sorted || !xyzw || !cog3 || !min_dist || !argmin_idx)
+  if (!keys_sorted || !pos_sorted || !xyzw || !cog3 || !min_dist || !argmin_idx)
     return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: null buffer");
   if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_closest_to_cog: workspace too small");
   const SegWs w = carve(ws, n);
@@ -592,13 +603,13 @@ extern "C" int vapc_closest_to_cog(const void* keys_sorted, const uint32_t* idx_
     typedef uint32_t K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, rec, cog3, w.tile_heads,
                                                           nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
   } else if (key_bytes == 8) {
     typedef unsigned long long K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(closest_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), idx_sorted, n, rec, cog3, w.tile_heads,
+    VAPC_LAUNCH(closest_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, rec, cog3, w.tile_heads,
                                                           nvoxels_host, min_dist, argmin_idx, w.carry_cnt, w.carry);
   } else {
     return vapc_set_error(VAPC_E_INVALID, "vapc_closest_to_cog: key_bytes must be 4 or 8");

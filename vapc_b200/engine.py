@@ -132,6 +132,25 @@ def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = N
     return out_keys, (idx_alt if loc.value & 4 else idx)
 
 
+def sort_pairs_segmented(keys: torch.Tensor, end_bit: int, seg_start: torch.Tensor, nseg: int, idx: Optional[torch.Tensor] = None):
+    """Stable sort of every segment [seg_start[s], seg_start[s+1]) by the low `end_bit` key bits, all segments in
+    the same launches (`keys` is overwritten).  Returns (keys_sorted, idx_sorted); idx defaults to the global
+    position of every element."""
+    n = keys.numel()
+    dev = keys.device
+    keys_alt = torch.empty_like(keys)
+    iota = idx is None
+    if iota:
+        idx = _empty(n, torch.int32, dev)
+    idx_alt = torch.empty_like(idx)
+    ws_bytes = L.raw("vapc_sort_workspace_bytes")(n)
+    ws = _empty(ws_bytes, torch.uint8, dev)
+    loc = C.c_int32(0)
+    L.call("vapc_sort_pairs_segmented", _ptr(keys), _ptr(keys_alt), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, keys.element_size(), int(end_bit),
+           _ptr(seg_start), int(nseg), _ptr(ws), ws_bytes, C.byref(loc), _stream())
+    return (keys, keys_alt)[loc.value & 3], (idx_alt if loc.value & 4 else idx)
+
+
 _L2_FETCH_SET = set()
 
 
@@ -172,9 +191,10 @@ class VoxelCloud:
         self.n = 0
         self.nvoxels = 0
         self.x = self.y = self.z = None
-        self.xyzw = None
+        self.xyzw = None  # 32-byte records {x, y, z, original index}, in bucket order (or input order)
         self.keys_sorted = None
-        self.idx_sorted = None
+        self.pos_sorted = None  # position of each sorted point's record in xyzw
+        self.idx_sorted = None  # original index of each sorted point
         self.voxel_keys = None
         self.start = None
         self.count = None
@@ -188,9 +208,11 @@ class VoxelCloud:
     # ------------------------------------------------------------------------------------
     @classmethod
     def build(cls, x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), *, bounds=None, want_point2voxel=True,
-              keep_columns=True, device=None) -> "VoxelCloud":
+              keep_columns=True, device=None, bucketed=True) -> "VoxelCloud":
         """voxelize + groupby of the reference (vapc.py:188-207 and the groupby at :724, :843, :959)
-        as: bounds -> packed keys (+ xyzw records) -> stable radix sort -> segmentation -> moments."""
+        as: bounds -> packed keys + xyzw records in key-prefix bucket order -> stable radix sort of the remaining key
+        bits inside the buckets -> segmentation -> moments.  bucketed=False keeps the records in input order and
+        sorts all key bits (same results; the per-voxel gathers then miss the L2)."""
         _require_cuda()
         if device is None:
             device = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -210,15 +232,30 @@ class VoxelCloud:
             bounds = coordinate_bounds(x, y, z)
         self.grid = g = grid_from_bounds(voxel_size, origin, bounds)
         kdtype = torch.int32 if g.key_bytes == 4 else torch.int64
-        keys = _empty(n, kdtype, device)
         self.xyzw = torch.empty((n, 4), dtype=torch.float64, device=device)
         status = torch.zeros(1, dtype=torch.int32, device=device)
         _tune_device(device)
-        L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
         dense_p2v = want_point2voxel and g.total_bits <= DENSE_P2V_MAX_BITS
-        self.keys_sorted, self.idx_sorted = sort_pairs(keys, g.total_bits, preserve_keys=dense_p2v)
-        if not dense_p2v:
-            del keys
+        if bucketed:
+            keys = _empty(n, kdtype, device)  # keys in input order
+            keys_b = _empty(n, kdtype, device)
+            bucket_start = _empty(257, torch.int32, device)
+            bws_bytes = L.raw("vapc_bucket_workspace_bytes")(n)
+            bws = _empty(bws_bytes, torch.uint8, device)
+            bucket_bits = C.c_int32(0)
+            L.call("vapc_pack_records_bucketed", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys_b), _ptr(self.xyzw), _ptr(keys), _ptr(bucket_start),
+                   C.byref(bucket_bits), _ptr(status), _ptr(bws), bws_bytes, _stream())
+            del bws
+            self.keys_sorted, self.pos_sorted = sort_pairs_segmented(keys_b, g.total_bits - bucket_bits.value, bucket_start, 1 << bucket_bits.value)
+            del keys_b
+            if not dense_p2v:
+                del keys
+        else:
+            keys = _empty(n, kdtype, device)
+            L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
+            self.keys_sorted, self.pos_sorted = sort_pairs(keys, g.total_bits, preserve_keys=dense_p2v)
+            if not dense_p2v:
+                del keys
         ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
         self._seg_ws = _empty(ws_bytes, torch.uint8, device)
         nv = torch.zeros(2, dtype=torch.int64, device=device)
@@ -234,9 +271,10 @@ class VoxelCloud:
         self.mean3 = torch.empty((3, V), dtype=torch.float64, device=device)
         self.m2 = torch.empty((6, V), dtype=torch.float64, device=device)
         self.point2voxel = _empty(n, torch.int32, device) if want_point2voxel else None
-        L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.idx_sorted), n, C.byref(g), _ptr(self.xyzw), V,
+        self.idx_sorted = _empty(n, torch.int32, device)
+        L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.pos_sorted), n, C.byref(g), _ptr(self.xyzw), V,
                _ptr(self.voxel_keys), _ptr(self.start), _ptr(self.count), _ptr(self.first_idx), _ptr(self.mean3), _ptr(self.m2),
-               _ptr(None if dense_p2v else self.point2voxel), _ptr(self._seg_ws), ws_bytes, _stream())
+               _ptr(None if dense_p2v else self.point2voxel), _ptr(self.idx_sorted), _ptr(self._seg_ws), ws_bytes, _stream())
         if dense_p2v:
             tbytes = L.raw("vapc_point2voxel_table_bytes")(g.total_bits)
             table = _empty(tbytes, torch.uint8, device)
@@ -282,7 +320,7 @@ class VoxelCloud:
         cog = self.stats(cog=True).cog
         md = _empty(V, torch.float64, dev)
         am = _empty(V, torch.int32, dev)
-        L.call("vapc_closest_to_cog", _ptr(self.keys_sorted), _ptr(self.idx_sorted), self.n, self.grid.key_bytes, _ptr(self.xyzw), _ptr(cog), V,
+        L.call("vapc_closest_to_cog", _ptr(self.keys_sorted), _ptr(self.pos_sorted), self.n, self.grid.key_bytes, _ptr(self.xyzw), _ptr(cog), V,
                _ptr(md), _ptr(am), _ptr(self._seg_ws), self._seg_ws.numel(), _stream())
         return md, am
 
