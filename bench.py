@@ -34,6 +34,9 @@ VOXEL_SIZE = 0.1
 ORIGIN = [0.0, 0.0, 0.0]
 EXTENT = (50.0, 50.0, 4.0)  # metres: 500 x 500 x 40 voxels = 1e7 cells -> ~10 points per voxel at 1e8 points
 QUANT = 1e-4  # LAS-like coordinate quantisation
+# DRAM traffic per launch of the big kernels at the default workload, from the committed `ncu --set full` capture
+# (profiles/README.md says which file); reported next to the algorithmic bytes of the dominant kernel
+NCU_TRAFFIC_GB = {}
 
 
 def parse():
@@ -196,18 +199,44 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(name, n, v, key_bytes, passes):
-    """Algorithmic bytes of one C-ABI call ('bytes per unit'); n points, v voxels."""
+def algorithmic_bytes(name, n, v, key_bytes, passes, low_passes):
+    """Algorithmic bytes of one C-ABI call ('bytes per unit'); n points, v voxels, `passes` radix passes for
+    all key bits, `low_passes` for the key bits below the bucket digit."""
     k = key_bytes
     return {
         "vapc_minmax_f64": 24 * n,
         "vapc_pack_keys_f64": (24 + k + 32) * n,
-        "vapc_sort_pairs": (passes * (3 * k + 8) - 4) * n,
+        "vapc_pack_records_bucketed": (24 + k) * n + (k + 24 + k + 32) * n,
+        "vapc_sort_pairs": (k + passes * (2 * k + 8) - 4) * n,
+        "vapc_sort_pairs_segmented": (k + low_passes * (2 * k + 8) - 4) * n,
         "vapc_count_voxels": k * n,
-        "vapc_reduce_moments": (k + 4 + 32) * n + (k + 12 + 72) * v,
-        "vapc_point2voxel_dense": (k + 4) * n + k * v,
+        "vapc_reduce_moments": (k + 4 + 32 + 4) * n + (k + 12 + 72) * v,
+        "vapc_point2voxel_dense": (k + 4) * n + (k + 4) * v,
         "vapc_voxel_stats": (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v,
     }.get(name, 0)
+
+
+def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
+    """Algorithmic bytes of ONE launch of a kernel (name as recorded by the library's launch macro)."""
+    k = key_bytes
+    table = [
+        ("minmax_partial", 24 * n),
+        ("keys_hist_kernel", (24 + k) * n),                      # x, y, z in; keys in input order out
+        ("bucket_scatter_kernel", (k + 24 + k + 32) * n),        # keys + x, y, z in; bucketed keys + records out
+        ("pack_keys_kernel", (24 + k + 32) * n),
+        ("digit_hist_kernel", k * n),
+        # one radix pass: keys + payload in and out; the first pass of a sort takes the payload from the position
+        ("onesweep_kernel", (2 * k + 8) * n - (4 * n) / max(1.0, launches_per_step)),
+        ("count_heads_kernel", k * n),
+        ("reduce_moments_kernel", (k + 4 + 32 + 4) * n + (k + 12 + 72) * v),
+        ("p2v_lookup_kernel", (k + 4) * n),
+        ("p2v_fill_kernel", (k + 4) * v),
+        ("voxel_stats_kernel", (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v),
+    ]
+    for key, b in table:
+        if key in kernel:
+            return key, float(b)
+    return kernel, 0.0
 
 
 def main():
@@ -263,6 +292,7 @@ def main():
     key_bytes = cloud.grid.key_bytes
     total_bits = cloud.grid.total_bits
     passes = (total_bits + 7) // 8
+    low_passes = (total_bits - min(8, cloud.grid.bits[0]) + 7) // 8  # inside the key-prefix buckets
 
     # ---- timed region: K steps, CUDA events, per-call events for the roofline -----------------
     records = []
@@ -276,6 +306,7 @@ def main():
     barrier()
     windows = [[time.perf_counter(), None]]
     L.observer = observer
+    L.call("vapc_profile_enable", 1)  # CUDA events around every kernel launch, on the launching stream
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -283,7 +314,9 @@ def main():
         cloud, st = step_device()
     t_end.record()
     L.observer = None
+    L.call("vapc_profile_enable", 0)
     barrier()
+    kernel_times = L.profile_collect()
     launches = L.raw("vapc_launch_count")() - launches0
     windows[0][1] = time.perf_counter()
     ms_total = t_start.elapsed_time(t_end)
@@ -319,14 +352,27 @@ def main():
     for name, ts in per_call.items():
         calls_per_step = len(ts) / args.steps
         avg = sum(ts) / len(ts)
-        b = algorithmic_bytes(name, n, nvox, key_bytes, passes)
+        b = algorithmic_bytes(name, n, nvox, key_bytes, passes, low_passes)
         breakdown[name] = {"ms_per_call": round(avg, 4), "calls_per_step": calls_per_step, "ms_per_step": round(avg * calls_per_step, 4),
                            "algorithmic_GB": round(b / 1e9, 4), "GBps": round(b / 1e9 / (avg * 1e-3), 1) if b else None}
-    dom = max((k for k in breakdown if breakdown[k]["algorithmic_GB"]), key=lambda k: breakdown[k]["ms_per_step"])
-    achieved = breakdown[dom]["GBps"]
+    # per kernel (CUDA events around every launch inside the timed region): the dominant one gives the roofline
+    per_kernel = {}
+    for kname, (cnt, ms) in kernel_times.items():
+        short, b = kernel_algorithmic_bytes(kname, n, nvox, key_bytes, cnt / args.steps)
+        e = per_kernel.setdefault(short, {"launches_per_step": 0.0, "ms_per_step": 0.0, "algorithmic_GB_per_launch": round(b / 1e9, 4)})
+        e["launches_per_step"] += cnt / args.steps
+        e["ms_per_step"] += ms / args.steps
+    for e in per_kernel.values():
+        e["ms_per_launch"] = round(e["ms_per_step"] / e["launches_per_step"], 4)
+        e["ms_per_step"] = round(e["ms_per_step"], 4)
+        e["GBps"] = round(e["algorithmic_GB_per_launch"] / (e["ms_per_launch"] * 1e-3), 1) if e["algorithmic_GB_per_launch"] and e["ms_per_launch"] else None
+    dom = max((k for k in per_kernel if per_kernel[k]["GBps"]), key=lambda k: per_kernel[k]["ms_per_step"])
+    achieved = per_kernel[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(breakdown[dom]["algorithmic_GB"] * 1e9), "ms_per_launch": breakdown[dom]["ms_per_call"]}
+                "traffic": NCU_TRAFFIC_GB.get(dom), "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_kernel[dom]["algorithmic_GB_per_launch"] * 1e9),
+                "ms_per_launch": per_kernel[dom]["ms_per_launch"], "launches_per_step": per_kernel[dom]["launches_per_step"],
+                "share_of_step": round(per_kernel[dom]["ms_per_step"] / ms_per_step, 3)}
     gpu_ms = sum(v["ms_per_step"] for v in breakdown.values())
 
     # ---- e2e: host buffers in, host voxel table out -------------------------------------------
@@ -395,7 +441,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": per_kernel, "abi_calls": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
             "gaps_between_calls_ms": gaps,
         }
         print(json.dumps(line))

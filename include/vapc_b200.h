@@ -66,6 +66,12 @@ VAPC_API uint64_t vapc_launch_count(void);
  * one random 32-byte record per point, so 32 avoids fetching unused neighbour sectors from HBM. */
 VAPC_API int vapc_set_l2_fetch_granularity(int32_t bytes);
 VAPC_API const char* vapc_last_error(void);
+/* Per-kernel timing for bench.py: while enabled, every kernel launch of the library is bracketed by CUDA
+ * events on its own stream.  vapc_profile_collect waits for them and writes one line
+ * "kernel<TAB>launches<TAB>total_ms" per kernel since the previous collect into out (NUL-terminated,
+ * truncated to cap); returns the full text length. */
+VAPC_API int vapc_profile_enable(int32_t on);
+VAPC_API int64_t vapc_profile_collect(char* out, int64_t cap);
 
 /* ---- bounding box (feeds vapc_grid_t; also Vapc.compute_reduction_point, vapc.py:153-162,
  * and the min/max of compute_percentage_occupied, vapc.py:761-763) ----------------------

@@ -69,6 +69,8 @@ SIGNATURES = {
     "vapc_last_error": (C.c_char_p, []),
     "vapc_launch_count": (C.c_uint64, []),
     "vapc_set_l2_fetch_granularity": (C.c_int, [I32]),
+    "vapc_profile_enable": (C.c_int, [I32]),
+    "vapc_profile_collect": (C.c_int64, [C.c_char_p, I64]),
     "vapc_minmax_workspace_bytes": (SZ, []),
     "vapc_minmax_f64": (C.c_int, [P, P, P, I64, P, P, SZ, P]),
     "vapc_voxel_coords_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
@@ -147,6 +149,17 @@ def call(name: str, *args):
     if obs is not None:
         obs(name, "after")
     check(code)
+
+
+def profile_collect():
+    """{kernel: (launches, total_ms)} of the launches recorded since vapc_profile_enable(1) / the last collect."""
+    buf = C.create_string_buffer(1 << 16)
+    _lib.vapc_profile_collect(buf, len(buf))
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, ms = ln.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def raw(name: str):

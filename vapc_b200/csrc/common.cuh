@@ -17,12 +17,18 @@ int vapc_cuda_error(cudaError_t e, const char* file, int line);
   } while (0)
 #define VAPC_CHECK_LAUNCH() VAPC_RETURN_IF_CUDA(cudaGetLastError())
 
-// every kernel launch of the library goes through this so that vapc_launch_count() is exact
+// every kernel launch of the library goes through this so that vapc_launch_count() is exact; with
+// vapc_profile_enable(1) every launch is also bracketed by CUDA events on its own stream (bench.py's per-kernel roofline)
 void vapc_note_launch();
-#define VAPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  do {                                                      \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
-    vapc_note_launch();                                     \
+extern bool g_vapc_profile;
+void vapc_profile_begin(const char* name, cudaStream_t s);
+void vapc_profile_end(cudaStream_t s);
+#define VAPC_LAUNCH(kernel, grid, block, smem, stream, ...)      \
+  do {                                                           \
+    if (g_vapc_profile) vapc_profile_begin(#kernel, (stream));   \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
+    if (g_vapc_profile) vapc_profile_end((stream));              \
+    vapc_note_launch();                                          \
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

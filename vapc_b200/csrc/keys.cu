@@ -4,6 +4,7 @@
 //   vapc_pack_keys_f64     24 B/pt read + key (4|8) + 32 B/pt xyzw record write
 #include <math.h>
 #include <stdarg.h>
+#include <algorithm>
 #include <string.h>
 
 #include "common.cuh"
@@ -31,6 +32,57 @@ static std::atomic<unsigned long long> g_launches{0};
 void vapc_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" uint64_t vapc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int vapc_abi_version(void) { return VAPC_ABI_VERSION; }
+
+// ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------------------
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+bool g_vapc_profile = false;
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+void vapc_profile_begin(const char* name, cudaStream_t s) {
+  ProfRec r{name, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+void vapc_profile_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s);
+}
+extern "C" int vapc_profile_enable(int32_t on) {
+  g_vapc_profile = on != 0;
+  return VAPC_OK;
+}
+// "name<TAB>launches<TAB>total_ms\n" per kernel since the last call; synchronises on the recorded events.
+extern "C" int64_t vapc_profile_collect(char* out, int64_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (r.a && r.b && cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    if (r.a) cudaEventDestroy(r.a);
+    if (r.b) cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string text;
+  for (auto& kv : agg) text += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+  if (out && cap > 0) {
+    const int64_t m = std::min<int64_t>((int64_t)text.size(), cap - 1);
+    memcpy(out, text.data(), (size_t)m);
+    out[m] = 0;
+  }
+  return (int64_t)text.size();
+}
 
 // The per-voxel gathers read one 32-byte record per point at random; ask the L2 to fetch no more than that
 // from DRAM on a miss (the default fetch granularity pulls neighbouring sectors that are never used).
