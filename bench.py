@@ -244,6 +244,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -444,7 +448,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": per_kernel, "abi_calls": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
             "gaps_between_calls_ms": gaps,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

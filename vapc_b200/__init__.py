@@ -13,5 +13,10 @@ from .engine import VoxelCloud, VoxelMask, FEATURE_NAMES  # noqa: F401
 from .utilities import enable_trace, enable_timeit, trace, timeit, DECORATOR_CONFIG  # noqa: F401
 from .vapc import Vapc  # noqa: F401
 from .bi_vapc import BiTemporalVapc  # noqa: F401
+from .datahandler import DataHandler  # noqa: F401
+from . import vapc_tools  # noqa: F401
+from .vapc_tools import use_tool  # noqa: F401
+from .main import do_vapc_on_files, main, get_version  # noqa: F401
 
-__all__ = ["Vapc", "BiTemporalVapc", "VoxelCloud", "VoxelMask", "enable_trace", "enable_timeit", "trace", "timeit"]
+__all__ = ["Vapc", "BiTemporalVapc", "DataHandler", "use_tool", "do_vapc_on_files", "main", "get_version", "VoxelCloud", "VoxelMask",
+           "enable_trace", "enable_timeit", "trace", "timeit"]
