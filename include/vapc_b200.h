@@ -294,6 +294,26 @@ VAPC_API int vapc_merge_partials(const void* keys_sorted, const uint32_t* order,
                         const double* m2_in, int64_t in_stride, int64_t nvoxels_host,
                         void* voxel_keys, uint32_t* count, double* mean3, double* m2, void* ws,
                         size_t ws_bytes, void* stream);
+/* Multi-GPU exchange of partial voxel rows.  Every rank builds its local table with its OWN grid (keys relative
+ * to its own lowest voxel: fewer key bits, fewer radix passes, and no dependence on the global bounds);
+ * vapc_global_keys re-expresses the (sorted) local voxel keys in the global layout (same lexicographic
+ * order) and counts the leading hist_bits bits of them into hist (zeroed here; the splitters come from the
+ * all-reduced histogram).  vapc_pack_partial_rows writes the rows [begin, end) that leave this rank as
+ * row-major records of 11 x 8 bytes {key (uint64), count (int64), mean[3], M2[6]}.  vapc_merge_partial_rows
+ * merges like vapc_merge_partials over two sources: order values < n_local address this rank's own rows
+ * local_first + value of the SOA columns (never copied), the others the received `rows`[value - n_local]. */
+VAPC_API int vapc_global_keys(const void* voxel_keys, int64_t nvoxels, const vapc_grid_t* local_grid_host,
+                     const vapc_grid_t* global_grid_host, int32_t hist_bits, uint64_t* keys_out,
+                     uint32_t* hist, void* stream);
+VAPC_API int vapc_pack_partial_rows(const uint64_t* global_keys, const uint32_t* count, const double* mean3,
+                           const double* m2, int64_t nvoxels, int64_t begin, int64_t end, double* rows_out,
+                           void* stream);
+VAPC_API int vapc_merge_partial_rows(const void* keys_sorted, const uint32_t* order, int64_t nrows,
+                            int32_t key_bytes, const double* rows, const uint32_t* local_count,
+                            const double* local_mean3, const double* local_m2, int64_t local_stride,
+                            int64_t local_first, int64_t n_local, int64_t nvoxels_host, void* voxel_keys,
+                            uint32_t* count, double* mean3, double* m2, void* ws, size_t ws_bytes,
+                            void* stream);
 /* histogram of the top `hist_bits` key bits (splitter selection) */
 VAPC_API int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes, int32_t total_bits,
                        int32_t hist_bits, uint32_t* hist, void* stream);

@@ -140,3 +140,20 @@ def test_partition_counts_unsigned_keys():
     assert D.partition_counts(keys, [5, 0x80000000]) == [1, 4, 2]
     assert D.partition_counts(keys, []) == [7]
     assert D.bench_slab_shift(0, 50.0) == 0.0 and D.bench_slab_shift(2, 50.0) == 90.0
+
+
+def test_device_side_planning_matches_host_planning():
+    """voxel_statistics plans splitters and destinations with tensor ops on the device; on CPU tensors they must give
+    exactly what the (numpy) host planner gives."""
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 4, 8):
+        for total_bits in (5, 16, 24, 40, 63):
+            hb = min(D.HIST_BITS, total_bits)
+            hist = rng.integers(0, 50, 1 << hb)
+            hist[rng.random(1 << hb) < 0.5] = 0
+            t_host = D.plan_splitters(hist, world, total_bits, hb)
+            t_dev = D.plan_splitters_tensor(torch.from_numpy(hist), world, total_bits, hb)
+            assert t_dev.tolist() == t_host
+            keys = np.sort(rng.integers(0, 1 << min(total_bits, 62), 5000))
+            assert D.destination_counts(torch.from_numpy(keys), t_dev).tolist() == D.partition_counts(torch.from_numpy(keys), t_host)
+    assert D.plan_splitters_tensor(torch.zeros(16, dtype=torch.int64), 4, 4, 4).tolist() == D.plan_splitters(np.zeros(16, np.int64), 4, 4, 4)

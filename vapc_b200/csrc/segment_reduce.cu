@@ -29,6 +29,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kItems = 4;
 constexpr int kSegTile = kThreads * kItems;  // 1024
+constexpr int kPartialRowWords = 11;         // exchanged partial voxel row: key, count, mean[3], M2[6] (8 bytes each)
 
 struct SegWs {  // layout of the segmentation workspace
   uint32_t* tile_heads;       // [ntiles]   heads per tile, then (in place) exclusive scan = first voxel row of the tile
@@ -446,11 +447,16 @@ __global__ void __launch_bounds__(kThreads) fixup_closest_kernel(const uint32_t*
 // Rows with equal keys are adjacent (keys sorted, stable, so source-rank order is kept); order[p] is
 // the source row of sorted position p.  A key has at most one partial row per source rank, so the
 // thread at each run head simply walks its run in global memory (runs may cross tiles freely).
-template <typename KeyT>
+// Sources of the partial rows.  SOA: columns count_in / mean3_in / m2_in (column stride in_stride).  ROWS: row-major
+// {key, count, mean[3], M2[6]} of 11 x 8 bytes as exchanged between GPUs (`rows`).  MIXED: source index < n_local is row
+// local_first + index of the SOA columns (this GPU's own rows, never copied), the others are `rows`[index - n_local].
+enum { kSrcSoa = 0, kSrcRows = 1, kSrcMixed = 2 };
+template <typename KeyT, int SRC>
 __global__ void __launch_bounds__(kThreads) merge_partials_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ order,
                                                                   int64_t n, const uint32_t* __restrict__ count_in,
                                                                   const double* __restrict__ mean3_in, const double* __restrict__ m2_in,
-                                                                  int64_t in_stride, const uint32_t* __restrict__ tile_first, int64_t nvox,
+                                                                  int64_t in_stride, const double* __restrict__ rows, int64_t n_local,
+                                                                  int64_t local_first, const uint32_t* __restrict__ tile_first, int64_t nvox,
                                                                   KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ count,
                                                                   double* __restrict__ mean3, double* __restrict__ m2) {
   __shared__ unsigned scan_s[33];
@@ -471,13 +477,25 @@ __global__ void __launch_bounds__(kThreads) merge_partials_kernel(const KeyT* __
     double na = 0.0, ma[3] = {0, 0, 0}, Ma[6] = {0, 0, 0, 0, 0, 0};
     int64_t q = p0 + j;
     do {
-      const int64_t src = order[q];
-      double mb[3], Mb[6];
+      int64_t src = order[q];
+      double mb[3], Mb[6], nb;
+      const bool from_rows = SRC == kSrcRows || (SRC == kSrcMixed && src >= n_local);
+      if (SRC == kSrcMixed) src = from_rows ? src - n_local : src + local_first;
+      if (from_rows) {
+        const double* row = rows + src * kPartialRowWords;
+        nb = (double)__double_as_longlong(row[1]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) mb[k] = mean3_in[(int64_t)k * in_stride + src];
+        for (int k = 0; k < 3; ++k) mb[k] = row[2 + k];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) Mb[k] = m2_in[(int64_t)k * in_stride + src];
-      chan_combine(na, ma, Ma, (double)count_in[src], mb, Mb);
+        for (int k = 0; k < 6; ++k) Mb[k] = row[5 + k];
+      } else {
+        nb = (double)count_in[src];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mb[k] = mean3_in[(int64_t)k * in_stride + src];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Mb[k] = m2_in[(int64_t)k * in_stride + src];
+      }
+      chan_combine(na, ma, Ma, nb, mb, Mb);
       ++q;
     } while (q < n && keys[q] == key[j]);
     voxel_keys[row] = key[j];
@@ -486,6 +504,57 @@ __global__ void __launch_bounds__(kThreads) merge_partials_kernel(const KeyT* __
     for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = ma[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = Ma[k];
+  }
+}
+
+// local voxel keys -> keys in the GLOBAL layout (unpack with the local grid, repack with the global one) + the histogram of
+// their leading bits.  The table is key-sorted, so neighbouring rows share a bin: one atomic per run of equal bins in a warp.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) global_keys_kernel(const KeyT* __restrict__ voxel_keys, int64_t nvox, Grid lg, Grid gg, int hist_shift,
+                                                               unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ hist) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (nvox + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t v = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = v < nvox;
+    unsigned bin = 0xffffffffu;
+    if (valid) {
+      long long vx, vy, vz;
+      unpack_key((unsigned long long)voxel_keys[v], lg, vx, vy, vz);
+      const int sxy = gg.by + gg.bz;
+      unsigned long long k = (unsigned long long)(vz - gg.minz);
+      if (gg.bz < 64) k |= (unsigned long long)(vy - gg.miny) << gg.bz;
+      if (sxy < 64) k |= (unsigned long long)(vx - gg.minx) << sxy;
+      keys_out[v] = k;
+      bin = (unsigned)(k >> hist_shift);
+    }
+    // head of a run of equal bins inside the warp adds the run length
+    const unsigned prev = __shfl_up_sync(0xffffffffu, bin, 1);
+    const bool head = valid && (lane == 0 || prev != bin);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+    if (head) {
+      const unsigned after = heads & ~((2u << lane) - 1u);  // heads in higher lanes
+      const int end = after ? __ffs(after) - 1 : 32 - __clz(valid_mask);
+      atomicAdd(hist + bin, (unsigned)(end - lane));
+    }
+  }
+}
+
+// rows [begin, end) of a partial table (SOA, column stride nvox) -> exchange rows (row-major, 11 x 8 bytes) at rows_out
+__global__ void __launch_bounds__(kThreads) pack_partial_rows_kernel(const unsigned long long* __restrict__ gkeys, const uint32_t* __restrict__ count,
+                                                                     const double* __restrict__ mean3, const double* __restrict__ m2, int64_t nvox,
+                                                                     int64_t begin, int64_t end, double* __restrict__ rows_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < end; v += stride) {
+    double* row = rows_out + (v - begin) * kPartialRowWords;
+    row[0] = __longlong_as_double((long long)gkeys[v]);
+    row[1] = __longlong_as_double((long long)count[v]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) row[2 + k] = mean3[(int64_t)k * nvox + v];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[5 + k] = m2[(int64_t)k * nvox + v];
   }
 }
 
@@ -633,14 +702,77 @@ extern "C" int vapc_merge_partials(const void* keys_sorted, const uint32_t* orde
   const int64_t nt = seg_tiles(nrows);
   cudaStream_t s = as_stream(stream);
   if (key_bytes == 4)
-    VAPC_LAUNCH(merge_partials_kernel<uint32_t>, (unsigned)nt, kThreads, 0, s, static_cast<const uint32_t*>(keys_sorted), order, nrows, count_in,
-        mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<uint32_t*>(voxel_keys), count, mean3, m2);
+    VAPC_LAUNCH((merge_partials_kernel<uint32_t, kSrcSoa>), (unsigned)nt, kThreads, 0, s, static_cast<const uint32_t*>(keys_sorted), order, nrows, count_in,
+        mean3_in, m2_in, in_stride, nullptr, 0, 0, w.tile_heads, nvoxels_host, static_cast<uint32_t*>(voxel_keys), count, mean3, m2);
   else if (key_bytes == 8)
-    VAPC_LAUNCH(merge_partials_kernel<unsigned long long>, (unsigned)nt, kThreads, 0, s, static_cast<const unsigned long long*>(keys_sorted), order,
-        nrows, count_in, mean3_in, m2_in, in_stride, w.tile_heads, nvoxels_host, static_cast<unsigned long long*>(voxel_keys), count,
+    VAPC_LAUNCH((merge_partials_kernel<unsigned long long, kSrcSoa>), (unsigned)nt, kThreads, 0, s, static_cast<const unsigned long long*>(keys_sorted), order,
+        nrows, count_in, mean3_in, m2_in, in_stride, nullptr, 0, 0, w.tile_heads, nvoxels_host, static_cast<unsigned long long*>(voxel_keys), count,
         mean3, m2);
   else
     return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partials: key_bytes must be 4 or 8");
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_global_keys(const void* voxel_keys, int64_t nvoxels, const vapc_grid_t* local_grid_host, const vapc_grid_t* global_grid_host,
+                               int32_t hist_bits, uint64_t* keys_out, uint32_t* hist, void* stream) {
+  if (nvoxels < 0 || !local_grid_host || !global_grid_host || hist_bits < 1 || hist_bits > 24 || !hist)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_global_keys: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) << hist_bits, s));
+  if (nvoxels == 0) return VAPC_OK;
+  if (!voxel_keys || !keys_out) return vapc_set_error(VAPC_E_INVALID, "vapc_global_keys: null buffer");
+  const Grid lg = to_device_grid(local_grid_host), gg = to_device_grid(global_grid_host);
+  const int global_bits = gg.bx + gg.by + gg.bz;
+  if (global_bits > 64) return vapc_set_error(VAPC_E_KEYSPACE, "vapc_global_keys: global layout needs more than 64 bits");
+  const int shift = global_bits > hist_bits ? global_bits - hist_bits : 0;
+  const int grid = (int)std::min<int64_t>((nvoxels + kThreads - 1) / kThreads, (int64_t)kNumSMs * 16);
+  unsigned long long* ko = reinterpret_cast<unsigned long long*>(keys_out);
+  if (local_grid_host->key_bytes == 4)
+    VAPC_LAUNCH(global_keys_kernel<uint32_t>, grid, kThreads, 0, s, static_cast<const uint32_t*>(voxel_keys), nvoxels, lg, gg, shift, ko, hist);
+  else if (local_grid_host->key_bytes == 8)
+    VAPC_LAUNCH(global_keys_kernel<unsigned long long>, grid, kThreads, 0, s, static_cast<const unsigned long long*>(voxel_keys), nvoxels, lg, gg, shift, ko, hist);
+  else
+    return vapc_set_error(VAPC_E_INVALID, "vapc_global_keys: key_bytes must be 4 or 8");
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_pack_partial_rows(const uint64_t* global_keys, const uint32_t* count, const double* mean3, const double* m2, int64_t nvoxels,
+                                      int64_t begin, int64_t end, double* rows_out, void* stream) {
+  if (nvoxels < 0 || begin < 0 || end > nvoxels || begin > end) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_partial_rows: bad range");
+  if (begin == end) return VAPC_OK;
+  if (!global_keys || !count || !mean3 || !m2 || !rows_out) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_partial_rows: null buffer");
+  const int grid = (int)std::min<int64_t>((end - begin + kThreads - 1) / kThreads, (int64_t)kNumSMs * 16);
+  VAPC_LAUNCH(pack_partial_rows_kernel, grid, kThreads, 0, as_stream(stream), reinterpret_cast<const unsigned long long*>(global_keys), count, mean3, m2,
+              nvoxels, begin, end, rows_out);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_merge_partial_rows(const void* keys_sorted, const uint32_t* order, int64_t nrows, int32_t key_bytes, const double* rows,
+                                       const uint32_t* local_count, const double* local_mean3, const double* local_m2, int64_t local_stride,
+                                       int64_t local_first, int64_t n_local, int64_t nvoxels_host, void* voxel_keys, uint32_t* count,
+                                       double* mean3, double* m2, void* ws, size_t ws_bytes, void* stream) {
+  if (nrows < 0 || nvoxels_host < 0 || n_local < 0 || n_local > nrows) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partial_rows: bad arguments");
+  if (nrows == 0) return VAPC_OK;
+  if (!keys_sorted || !order || !voxel_keys || !count || !mean3 || !m2 || (nrows > n_local && !rows) ||
+      (n_local > 0 && (!local_count || !local_mean3 || !local_m2)))
+    return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partial_rows: null buffer");
+  if (!ws || ws_bytes < seg_ws_bytes(nrows)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_merge_partial_rows: workspace too small");
+  const SegWs w = carve(ws, nrows);
+  const int64_t nt = seg_tiles(nrows);
+  cudaStream_t s = as_stream(stream);
+  if (key_bytes == 4)
+    VAPC_LAUNCH((merge_partials_kernel<uint32_t, kSrcMixed>), (unsigned)nt, kThreads, 0, s, static_cast<const uint32_t*>(keys_sorted), order, nrows,
+                local_count, local_mean3, local_m2, local_stride, rows, n_local, local_first, w.tile_heads, nvoxels_host,
+                static_cast<uint32_t*>(voxel_keys), count, mean3, m2);
+  else if (key_bytes == 8)
+    VAPC_LAUNCH((merge_partials_kernel<unsigned long long, kSrcMixed>), (unsigned)nt, kThreads, 0, s, static_cast<const unsigned long long*>(keys_sorted),
+                order, nrows, local_count, local_mean3, local_m2, local_stride, rows, n_local, local_first, w.tile_heads, nvoxels_host,
+                static_cast<unsigned long long*>(voxel_keys), count, mean3, m2);
+  else
+    return vapc_set_error(VAPC_E_INVALID, "vapc_merge_partial_rows: key_bytes must be 4 or 8");
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

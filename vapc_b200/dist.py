@@ -3,16 +3,19 @@
 Points are sharded in contiguous chunks (each rank holds its own slice, as it would come out of a
 file).  The path has exactly one real exchange step, as BASELINE.json's north_star prescribes:
 
-  1. bounding box: local min/max kernel -> all-reduce(min/max) of 6 doubles -> ONE grid for all ranks,
-     so packed keys mean the same voxel everywhere;
-  2. every rank builds its local PARTIAL voxel table (key, count, mean - c(key), M2): keys -> radix
-     sort -> segmentation -> moments, all local, no communication;
-  3. the key space is cut into `world` ranges balancing the number of partial rows: all-reduce(sum) of
-     a 2^16-bin histogram of the partial tables' keys -> splitters;
-  4. ONE all-to-all(v) sends every partial row to the owner of its key range (the local table is
-     sorted, so each destination's rows are a contiguous slice);
-  5. the owner merges the received rows (stable radix sort by key keeps source-rank order; equal
-     keys are combined with Chan's update in that fixed order) and finalises statistics.
+  1. bounding boxes: local min/max kernel; the all-reduce(min/max) of 6 doubles that gives the GLOBAL key layout is
+     started asynchronously — nothing local depends on it;
+  2. every rank builds its local PARTIAL voxel table (key, count, mean - c(key), M2) with its OWN grid (keys
+     relative to its own lowest voxel: fewer key bits and radix passes than the global layout): keys + records in
+     bucket order -> segmented radix sort -> segmentation -> moments, all local, no communication;
+  3. the sorted local voxel keys are re-expressed in the global layout (same lexicographic order) and the key space
+     is cut into `world` ranges balancing the number of partial rows: all-reduce(sum) of a 2^16-bin histogram of
+     the keys -> splitters -> destinations, all planned on the device; one all-gather of the send counts;
+  4. ONE all-to-all(v) moves the rows that leave their rank, packed row-major, to the owner of their key range (the
+     local table is sorted, so each destination's rows are a contiguous slice); the rows a rank owns itself are
+     never copied;
+  5. the owner merges its own rows with the received ones (stable radix sort by key keeps source order; equal keys
+     are combined with Chan's update in that fixed order) and finalises statistics.
 
 Because c(key) is an exact function of the key, partial (count, mean, M2) triples combine without
 loss; integer outputs do not depend on the number of ranks, floating point ones differ only by the
@@ -133,8 +136,32 @@ class ShardedVoxelTable:
         return c.voxel_coords()
 
 
-def global_bounds(x, y, z, group=None) -> np.ndarray:
-    """Global [min x, min y, min z, max x, max y, max z]: local bbox kernel + one 6-double all-reduce."""
+def plan_splitters_tensor(global_hist: torch.Tensor, world: int, total_bits: int, hist_bits: int = HIST_BITS) -> torch.Tensor:
+    """plan_splitters on a tensor, on whatever device the histogram lives (no host round trip): int64 [world - 1]."""
+    hb = min(hist_bits, max(total_bits, 1))
+    shift = max(total_bits - hb, 0)
+    cum = torch.cumsum(global_hist.to(torch.int64), 0)
+    if world <= 1:
+        return torch.empty(0, dtype=torch.int64, device=cum.device)
+    g = torch.arange(1, world, dtype=torch.float64, device=cum.device)
+    target = cum[-1].to(torch.float64) * g / world
+    b = torch.searchsorted(cum.to(torch.float64), target, right=False) + 1  # first bin NOT in range g-1
+    b = torch.clamp(b, max=cum.numel())
+    return torch.cummax(b << shift, 0).values
+
+
+def destination_counts(sorted_keys_i64: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
+    """Rows of a key-sorted table (non-negative int64 keys) going to each rank: int64 [world], same device."""
+    n = sorted_keys_i64.numel()
+    cuts = torch.searchsorted(sorted_keys_i64, thresholds, right=False)
+    edges = torch.cat([cuts.new_zeros(1), cuts, cuts.new_full((1,), n)])
+    return edges[1:] - edges[:-1]
+
+
+def start_bounds(x, y, z, group=None):
+    """Local bbox kernel + the 6-double all-reduce started asynchronously.  Returns (local bounds on the host, finish) where
+    finish() waits for the collective and returns the global bounds — the local pipeline does not need them, so it runs
+    while the all-reduce is in flight."""
     from . import _lib as L
     from . import engine as E
 
@@ -143,10 +170,22 @@ def global_bounds(x, y, z, group=None) -> np.ndarray:
     ws_bytes = L.raw("vapc_minmax_workspace_bytes")()
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     L.call("vapc_minmax_f64", E._ptr(x), E._ptr(y), E._ptr(z), n, E._ptr(out), E._ptr(ws), ws_bytes, E._stream())
-    out[3:] = -out[3:]  # min over (min, -max)
-    dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)
-    out[3:] = -out[3:]
-    return out.cpu().numpy()
+    red = torch.cat([out[:3], -out[3:]])  # min over (min, -max)
+    work = dist.all_reduce(red, op=dist.ReduceOp.MIN, group=group, async_op=True)
+    local = out.cpu().numpy()
+
+    def finish():
+        work.wait()
+        glob = red.cpu().numpy()
+        glob[3:] = -glob[3:]
+        return glob
+
+    return local, finish
+
+
+def global_bounds(x, y, z, group=None) -> np.ndarray:
+    """Global [min x, min y, min z, max x, max y, max z]."""
+    return start_bounds(x, y, z, group)[1]()
 
 
 def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: torch.Tensor, m2: torch.Tensor):
@@ -175,30 +214,77 @@ def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: tor
 
 
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True):
-    """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats)."""
+    """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
+
+    Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
+    than the global layout, and no dependence on the global bounds, whose all-reduce overlaps the local pipeline).  The
+    sorted local table is then re-keyed in the global layout (same order), splitters and destinations are planned on the
+    device, only the rows that leave the rank are packed and exchanged (ONE all-to-all), and the owner merges its own rows
+    (in place) with the received ones.  Five small device -> host copies synchronise the host: local bounds, local voxel
+    count, global bounds, the all-gathered send-count matrix, the merged voxel count."""
     from . import _lib as L
     from . import engine as E
 
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     dev = x.device
-    bounds = global_bounds(x, y, z, group)
-    local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=bounds, want_point2voxel=False, keep_columns=False)
-    g = local.grid
+    local_b, finish_bounds = start_bounds(x, y, z, group)
+    local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=local_b, want_point2voxel=False, keep_columns=False)
+    lg = local.grid
+    g = E.grid_from_bounds(voxel_size, origin, finish_bounds())  # the key layout every rank agrees on
     if g.total_bits > 63:
         raise L.VapcError(L.VAPC_E_KEYSPACE, "multi-GPU key ranges need at most 63 key bits")
-    # splitters from the global histogram of partial-table keys
+    v = local.nvoxels
     hb = min(HIST_BITS, max(g.total_bits, 1))
+    gkeys = torch.empty(v, dtype=torch.int64, device=dev)
     hist = torch.empty(1 << hb, dtype=torch.int32, device=dev)
-    L.call("vapc_key_histogram", E._ptr(local.voxel_keys), local.nvoxels, g.key_bytes, g.total_bits, hb, E._ptr(hist), E._stream())
+    L.call("vapc_global_keys", E._ptr(local.voxel_keys), v, C.byref(lg), C.byref(g), hb, E._ptr(gkeys), E._ptr(hist), E._stream())
     hist64 = hist.to(torch.int64)
     dist.all_reduce(hist64, op=dist.ReduceOp.SUM, group=group)
-    thresholds = plan_splitters(hist64.cpu().numpy(), world, g.total_bits, hb)
-    send_counts = partition_counts(local.voxel_keys, thresholds)
-    moments = torch.cat([local.mean3, local.m2], dim=0).t().contiguous()  # [V, 9] rows for the exchange
-    recv, recv_counts = exchange_rows({"keys": local.voxel_keys, "count": local.count, "moments": moments}, send_counts, group)
-    rm = recv["moments"].t().contiguous()  # [9, R]
-    keys, count, mean3, m2 = merge_partial_rows(g, recv["keys"], recv["count"], rm[:3].contiguous(), rm[3:].contiguous())
-    table = ShardedVoxelTable(grid=g, nvoxels=keys.numel(), voxel_keys=keys, count=count, mean3=mean3, m2=m2, thresholds=thresholds,
-                              partial_rows_sent=int(sum(send_counts)), partial_rows_received=int(sum(recv_counts)))
+    thresholds = plan_splitters_tensor(hist64, world, g.total_bits, hb)
+    send = destination_counts(gkeys, thresholds)
+    matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(matrix, send, group=group)
+    host = torch.cat([matrix, thresholds]).cpu()  # one synchronisation for everything the host has to know
+    matrix_h = host[: world * world].view(world, world)
+    send_counts = matrix_h[rank].tolist()
+    recv_counts = matrix_h[:, rank].tolist()
+    # rows [lo, hi) of the local table stay here; the rest leaves, packed row-major, grouped by destination (= key order)
+    lo = int(sum(send_counts[:rank]))
+    n_own = int(send_counts[rank])
+    hi = lo + n_own
+    out_rows = torch.empty((v - n_own, 11), dtype=torch.float64, device=dev)
+    for begin, end, at in ((0, lo, 0), (hi, v, lo)):
+        if end > begin:
+            L.call("vapc_pack_partial_rows", E._ptr(gkeys), E._ptr(local.count), E._ptr(local.mean3), E._ptr(local.m2), v, begin, end,
+                   C.c_void_p(out_rows.data_ptr() + at * 88), E._stream())
+    send_remote = list(send_counts)
+    recv_remote = list(recv_counts)
+    send_remote[rank] = recv_remote[rank] = 0
+    n_in = int(sum(recv_remote))
+    in_rows = torch.empty((n_in, 11), dtype=torch.float64, device=dev)
+    dist.all_to_all_single(in_rows, out_rows, output_split_sizes=recv_remote, input_split_sizes=send_remote, group=group)
+    # merge: own rows (sources 0 .. n_own-1, read in place from the local table) + received rows (sources n_own ..)
+    keys = torch.cat([gkeys[lo:hi], in_rows.view(torch.int64)[:, 0]])
+    if g.key_bytes == 4:
+        keys = keys.to(torch.int32)
+    r = keys.numel()
+    ks, order = E.sort_pairs(keys, g.total_bits)
+    ws_bytes = L.raw("vapc_segment_workspace_bytes")(r)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nv = torch.zeros(1, dtype=torch.int64, device=dev)
+    L.call("vapc_count_voxels", E._ptr(ks), r, g.key_bytes, E._ptr(nv), E._ptr(ws), ws_bytes, E._stream())
+    vm = int(nv.item())
+    out_keys = torch.empty(vm, dtype=ks.dtype, device=dev)
+    out_count = torch.empty(vm, dtype=torch.int32, device=dev)
+    out_mean = torch.empty((3, vm), dtype=torch.float64, device=dev)
+    out_m2 = torch.empty((6, vm), dtype=torch.float64, device=dev)
+    if r:
+        L.call("vapc_merge_partial_rows", E._ptr(ks), E._ptr(order), r, g.key_bytes, E._ptr(in_rows), E._ptr(local.count), E._ptr(local.mean3),
+               E._ptr(local.m2), v, lo, n_own, vm, E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), E._ptr(ws), ws_bytes,
+               E._stream())
+    table = ShardedVoxelTable(grid=g, nvoxels=vm, voxel_keys=out_keys, count=out_count, mean3=out_mean, m2=out_m2,
+                              thresholds=host[world * world:].tolist(), partial_rows_sent=int(sum(send_remote)),
+                              partial_rows_received=n_in)
     st = table.stats() if with_stats else None
     return table, st
