@@ -35,9 +35,9 @@ __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __res
   if (!(std3 || cov6 || eig3 || eign3 || feat8)) return;
   double c[6];
   if (n > 1) {
-    const double d = (double)(n - 1);
+    const double d = 1.0 / (double)(n - 1);  // one reciprocal instead of six divisions (<= 1 ulp apart)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c[k] = m2[(int64_t)k * nvox + v] / d;
+    for (int k = 0; k < 6; ++k) c[k] = m2[(int64_t)k * nvox + v] * d;
   } else {
 #pragma unroll
     for (int k = 0; k < 6; ++k) c[k] = nan;
@@ -64,17 +64,18 @@ __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __res
   if (eig3) { eig3[v] = l1; eig3[nvox + v] = l2; eig3[2 * nvox + v] = l3; }
   if (!(eign3 || feat8)) return;
   const double total = l1 + l2 + l3;
-  const double e1 = l1 / total, e2 = l2 / total, e3 = l3 / total;
+  const double inv_total = 1.0 / total, inv_l1 = 1.0 / l1;  // 0 / 0 = NaN and x / 0 = inf behave the same through the reciprocal
+  const double e1 = l1 * inv_total, e2 = l2 * inv_total, e3 = l3 * inv_total;
   if (eign3) { eign3[v] = e1; eign3[nvox + v] = e2; eign3[2 * nvox + v] = e3; }
   if (feat8) {
     feat8[v] = total;                                                                       // Sum_of_Eigenvalues
-    feat8[nvox + v] = pow(l1 * l2 * l3, 1.0 / 3.0);                                         // Omnivariance
+    feat8[nvox + v] = cbrt(l1 * l2 * l3);                                                   // Omnivariance ((.) ** (1/3), non-negative argument)
     feat8[2 * nvox + v] = -(e1 * safe_log(e1) + e2 * safe_log(e2) + e3 * safe_log(e3));     // Eigenentropy
-    feat8[3 * nvox + v] = (l1 - l3) / l1;                                                   // Anisotropy
-    feat8[4 * nvox + v] = (l2 - l3) / l1;                                                   // Planarity
-    feat8[5 * nvox + v] = (l1 - l2) / l1;                                                   // Linearity
-    feat8[6 * nvox + v] = l3 / total;                                                       // Surface_Variation
-    feat8[7 * nvox + v] = l3 / l1;                                                          // Sphericity
+    feat8[3 * nvox + v] = (l1 - l3) * inv_l1;                                               // Anisotropy
+    feat8[4 * nvox + v] = (l2 - l3) * inv_l1;                                               // Planarity
+    feat8[5 * nvox + v] = (l1 - l2) * inv_l1;                                               // Linearity
+    feat8[6 * nvox + v] = e3;                                                               // Surface_Variation
+    feat8[7 * nvox + v] = l3 * inv_l1;                                                      // Sphericity
   }
 }
 
