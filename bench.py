@@ -36,7 +36,10 @@ EXTENT = (50.0, 50.0, 4.0)  # metres: 500 x 500 x 40 voxels = 1e7 cells -> ~10 p
 QUANT = 1e-4  # LAS-like coordinate quantisation
 # DRAM traffic per launch of the big kernels at the default workload, from the committed `ncu --set full` capture
 # (profiles/README.md says which file); reported next to the algorithmic bytes of the dominant kernel
-NCU_TRAFFIC_GB = {}
+NCU_TRAFFIC_GB = {  # profiles/r1_c_ncu_full.csv (1e8 points, 9 999 543 voxels, 24-bit keys)
+    "bucket_scatter_kernel": 6.46, "reduce_moments_kernel": 5.28, "onesweep_kernel": 1.40, "voxel_stats_kernel": 2.90,
+    "keys_hist_kernel": 2.75, "p2v_lookup_kernel": 1.24, "minmax_partial": 2.41, "digit_hist_kernel": 0.41, "count_heads_kernel": 0.40,
+}
 
 
 def parse():
@@ -373,7 +376,7 @@ def main():
     dom = max((k for k in per_kernel if per_kernel[k]["GBps"]), key=lambda k: per_kernel[k]["ms_per_step"])
     achieved = per_kernel[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": NCU_TRAFFIC_GB.get(dom), "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
+                "traffic": NCU_TRAFFIC_GB.get(dom) if (n == 100_000_000 and world == 1) else None, "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_kernel[dom]["algorithmic_GB_per_launch"] * 1e9),
                 "ms_per_launch": per_kernel[dom]["ms_per_launch"], "launches_per_step": per_kernel[dom]["launches_per_step"],
                 "share_of_step": round(per_kernel[dom]["ms_per_step"] / ms_per_step, 3)}
