@@ -133,6 +133,10 @@ VAPC_API int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32
                     uint32_t* idx_alt, int32_t idx_is_iota, int64_t n, int32_t key_bytes,
                     int32_t end_bit, void* ws, size_t ws_bytes, int32_t* result_location_host,
                     void* stream);
+/* The same over the key bits [begin_bit, end_bit) only (e.g. one pass over the leading byte of 32-bit indices). */
+VAPC_API int vapc_sort_pairs_bits(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx, uint32_t* idx_alt,
+                         int32_t idx_is_iota, int64_t n, int32_t key_bytes, int32_t begin_bit, int32_t end_bit,
+                         void* ws, size_t ws_bytes, int32_t* result_location_host, void* stream);
 /* Segmented form: the array is nseg <= 256 consecutive segments [seg_start[s], seg_start[s+1])
  * (device uint32[nseg+1], seg_start[nseg] = n), each sorted independently by bits [0, end_bit) in the
  * same launches; idx_is_iota numbers the elements by their global position.  Two key buffers
@@ -158,16 +162,22 @@ VAPC_API int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key_b
  * c(v) is an exact function of the key, so (count, mean3, m2) triples of the same voxel from
  * different tiles or different GPUs combine with Chan's pairwise update without loss
  * (vapc_merge_partials).  Inside a voxel, points are visited in original point order.
- * point2voxel (nullable) gets the voxel row of every point.  Layout: mean3 is [3][V], m2 is
+ * Layout: mean3 is [3][V], m2 is
  * [6][V] (column stride V = nvoxels_host).  xyzw = the records vapc_pack_keys_f64 (input order) or
  * vapc_pack_records_bucketed (bucket order) wrote, pos_sorted = the sorted payload = position of each
  * point's record in xyzw; original point indices come from the records.  idx_sorted (nullable)
- * receives the original point index of every sorted position. */
+ * receives the original point index of every sorted position, row_sorted (nullable) its voxel row:
+ * together they are the point -> voxel map in sorted order.  To get it in ORIGINAL point order
+ * (point2voxel[idx_sorted[p]] = row_sorted[p]) without 1e8 random 4-byte writes to HBM, group the pairs
+ * by the leading byte of the index (vapc_sort_pairs_bits, one pass) and vapc_scatter_u32 them: the writes
+ * of a group then stay inside an L2-sized window.  Small grids: vapc_point2voxel_dense is cheaper. */
 VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n,
                         const vapc_grid_t* grid_host, const double* xyzw, int64_t nvoxels_host,
                         void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
-                        double* mean3, double* m2, uint32_t* point2voxel, uint32_t* idx_sorted,
+                        double* mean3, double* m2, uint32_t* row_sorted, uint32_t* idx_sorted,
                         void* ws, size_t ws_bytes, void* stream);
+/* out[index[i]] = values[i] */
+VAPC_API int vapc_scatter_u32(const uint32_t* index, const uint32_t* values, int64_t n, uint32_t* out, void* stream);
 
 /* point -> voxel map in ORIGINAL point order through a direct-address table over the packed key space
  * (table[key] = voxel row).  For grids of <= 2^25 cells the table stays in the 126 MB L2 and this costs

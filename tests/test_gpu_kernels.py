@@ -126,6 +126,21 @@ def test_sort_pairs_segmented(E, n, nseg, bits, dtype):
     np.testing.assert_array_equal(_u32(idx), order)
 
 
+def test_sort_pairs_bit_range(E):
+    """Only the bits [begin_bit, end_bit) are sorted (stable in everything else): one pass over the leading byte of an index."""
+    rng = np.random.default_rng(9)
+    for n, begin, end, dtype in ((200_000, 10, 18, np.uint32), (50_000, 3, 27, np.uint32), (70_000, 40, 61, np.uint64)):
+        keys = rng.integers(0, (1 << end) - 1, n, dtype=np.uint64, endpoint=True).astype(dtype)
+        payload = rng.permutation(n).astype(np.uint32)
+        tk = torch.from_numpy(keys.view(np.int32 if dtype == np.uint32 else np.int64)).cuda()
+        ks, idx = E.sort_pairs(tk, end, idx=torch.from_numpy(payload.view(np.int32)).cuda(), begin_bit=begin, preserve_keys=True)
+        field = (keys.astype(np.uint64) >> np.uint64(begin)) & np.uint64((1 << (end - begin)) - 1)
+        order = np.argsort(field, kind="stable")
+        np.testing.assert_array_equal(_np(ks).view(dtype), keys[order])
+        np.testing.assert_array_equal(_u32(idx), payload[order])
+        np.testing.assert_array_equal(_np(tk).view(dtype), keys)  # preserved
+
+
 def test_sort_pairs_with_payload_and_partial_bits(E):
     rng = np.random.default_rng(5)
     n = 50000

@@ -61,11 +61,48 @@ def bench_sort(n=100_000_000, bits=24):
     return ok
 
 
-def bench_build(n=100_000_000, bucketed=1):
+def clustered_cloud(n, seed=3, extent=500.0, scan_order=True):
+    """C3-like cloud: 60 % of the points on a terrain sheet z = f(x, y) + noise, 40 % in tree-like
+    blobs (stems + crowns); quantised to 1e-4 m; emitted in scan-line order (sorted by a coarse y strip, then x) or shuffled."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    nt = int(0.6 * n)
+    tx = torch.rand(nt, device="cuda", generator=g, dtype=torch.float64) * extent
+    ty = torch.rand(nt, device="cuda", generator=g, dtype=torch.float64) * extent
+    tz = 5.0 * torch.sin(tx / 37.0) * torch.cos(ty / 53.0) + 0.02 * tx + (torch.rand(nt, device="cuda", generator=g, dtype=torch.float64) - 0.5) * 0.1
+    nb = n - nt
+    ntrees = max(1, int(2e5 * (extent / 1000.0) ** 2))
+    cx = torch.rand(ntrees, device="cuda", generator=g, dtype=torch.float64) * extent
+    cy = torch.rand(ntrees, device="cuda", generator=g, dtype=torch.float64) * extent
+    ch = 5.0 + 20.0 * torch.rand(ntrees, device="cuda", generator=g, dtype=torch.float64)
+    t = torch.randint(0, ntrees, (nb,), device="cuda", generator=g)
+    r = torch.randn(nb, 3, device="cuda", generator=g, dtype=torch.float64)
+    crown = torch.rand(nb, device="cuda", generator=g) < 0.8
+    bx = cx[t] + torch.where(crown, r[:, 0] * 1.5, r[:, 0] * 0.1)
+    by = cy[t] + torch.where(crown, r[:, 1] * 1.5, r[:, 1] * 0.1)
+    h = torch.rand(nb, device="cuda", generator=g, dtype=torch.float64)
+    ground = 5.0 * torch.sin(cx[t] / 37.0) * torch.cos(cy[t] / 53.0) + 0.02 * cx[t]
+    bz = ground + torch.where(crown, ch[t] * (0.6 + 0.4 * h) + r[:, 2] * 0.8, ch[t] * 0.6 * h)
+    x, y, z = torch.cat([tx, bx]), torch.cat([ty, by]), torch.cat([tz, bz])
+    del tx, ty, tz, bx, by, bz, r, t, h, crown, ground
+    x, y, z = (torch.round(c * 1e4) * 1e-4 for c in (x, y, z))
+    if scan_order:
+        key = torch.floor(y / 2.0) * 1e6 + x
+        perm = torch.argsort(key)
+    else:
+        perm = torch.randperm(n, device="cuda", generator=g)
+    return x[perm].contiguous(), y[perm].contiguous(), z[perm].contiguous()
+
+
+def bench_build(n=100_000_000, bucketed=1, workload=0, vs_mm=100):
+    """workload 0: uniform box of bench.py; 1: clustered, scan-line order; 2: clustered, shuffled.  vs_mm: voxel size in mm."""
     g = torch.Generator(device="cuda").manual_seed(2)
-    x = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
-    y = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
-    z = torch.randint(0, 40_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
+    if workload == 0:
+        x = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
+        y = torch.randint(0, 500_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
+        z = torch.randint(0, 40_000, (n,), device="cuda", generator=g).to(torch.float64) * 1e-4
+    else:
+        x, y, z = clustered_cloud(n, scan_order=workload == 1)
+    vs = vs_mm / 1000.0
     rec = []
 
     def obs(name, phase):
@@ -74,7 +111,7 @@ def bench_build(n=100_000_000, bucketed=1):
         rec.append((name, phase, ev))
 
     def step():
-        c = E.VoxelCloud.build(x, y, z, 0.1, (0.0, 0.0, 0.0), bucketed=bool(bucketed))
+        c = E.VoxelCloud.build(x, y, z, vs, (0.0, 0.0, 0.0), bucketed=bool(bucketed))
         c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
         return c
 
@@ -96,7 +133,7 @@ def bench_build(n=100_000_000, bucketed=1):
             pend[name] = ev
         else:
             per.setdefault(name, []).append(pend.pop(name).elapsed_time(ev))
-    print(f"build+stats bucketed={bucketed} n={n} voxels={c.nvoxels}: {a.elapsed_time(b) / reps:.3f} ms/step = {n * reps / a.elapsed_time(b) / 1e6:.2f} Gpts/s")
+    print(f"build+stats workload={workload} vs={vs} key_bits={c.grid.total_bits} bucketed={bucketed} n={n} voxels={c.nvoxels}: {a.elapsed_time(b) / reps:.3f} ms/step = {n * reps / a.elapsed_time(b) / 1e6:.2f} Gpts/s")
     for k, v in per.items():
         print(f"   {k:28s} {sum(v) / reps:.3f} ms/step ({len(v) // reps} calls)")
 

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
     const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
     const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
     uint32_t* __restrict__ count, uint32_t* __restrict__ first_idx, double* __restrict__ mean3, double* __restrict__ m2,
-    uint32_t* __restrict__ point2voxel, uint32_t* __restrict__ idx_sorted, uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
+    uint32_t* __restrict__ row_sorted, uint32_t* __restrict__ idx_sorted, uint32_t* __restrict__ carry_cnt, double* __restrict__ carry) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<KeyT>& sm = *reinterpret_cast<TileSmem<KeyT>*>(smem_raw);
   const int64_t base = (int64_t)blockIdx.x * kSegTile;
@@ -211,18 +211,25 @@ __global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
   tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
   const uint32_t first_row = tile_first[blockIdx.x];  // voxel row of the first head in this tile
 
+  uint32_t rows[kItems];
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
     const int p = threadIdx.x * kItems + j;
     sm.x[p] = rec[j].x; sm.y[p] = rec[j].y; sm.z[p] = rec[j].z;
-    if (valid[j]) {
-      const uint32_t row = first_row + inc[j] - 1u;  // inc == 0 -> first_row - 1: the continued voxel
-      if (point2voxel) point2voxel[idx[j]] = row;
-      if (head[j]) {
-        voxel_keys[row] = key[j];
-        start[row] = (uint32_t)(p0 + j);
-        first_idx[row] = idx[j];
-      }
+    rows[j] = first_row + inc[j] - 1u;  // inc == 0 -> first_row - 1: the continued voxel
+    if (valid[j] && head[j]) {
+      voxel_keys[rows[j]] = key[j];
+      start[rows[j]] = (uint32_t)(p0 + j);
+      first_idx[rows[j]] = idx[j];
+    }
+  }
+  if (row_sorted) {  // voxel row of every sorted position (vapc_point2voxel_sorted turns it into the point -> voxel map)
+    if (p0 + kItems <= n) {
+      *reinterpret_cast<uint4*>(row_sorted + p0) = make_uint4(rows[0], rows[1], rows[2], rows[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j)
+        if (valid[j]) row_sorted[p0 + j] = rows[j];
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[nvox] = (uint32_t)n;
@@ -376,6 +383,14 @@ __global__ void __launch_bounds__(kThreads) p2v_lookup_kernel(const KeyT* __rest
     __stcs(reinterpret_cast<uint4*>(p2v) + q, r);
   }
   for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p2v[i] = __ldg(table + __ldcs(keys + i));
+}
+
+// point2voxel[index[i]] = row[i].  Called with (index, row) pairs grouped by the leading bits of the index, so that the writes
+// of a group stay inside a window of the output that the L2 holds and leave for HBM as whole lines.
+__global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const uint32_t* __restrict__ index, const uint32_t* __restrict__ row, int64_t n,
+                                                                uint32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[__ldcs(index + i)] = __ldcs(row + i);
 }
 
 // ---- closest to centroid ----------------------------------------------------------------------------
@@ -602,14 +617,14 @@ extern "C" int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key
 
 extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n, const vapc_grid_t* grid_host,
                                    const double* xyzw, int64_t nvoxels_host, void* voxel_keys, uint32_t* start, uint32_t* count,
-                                   uint32_t* first_idx, double* mean3, double* m2, uint32_t* point2voxel, uint32_t* idx_sorted,
+                                   uint32_t* first_idx, double* mean3, double* m2, uint32_t* row_sorted, uint32_t* idx_sorted,
                                    void* ws, size_t ws_bytes, void* stream) {
   if (!grid_host || n < 0 || nvoxels_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: bad arguments");
   if (n == 0) return VAPC_OK;
   if (!keys_sorted || !pos_sorted || !xyzw || !voxel_keys || !start || !count || !first_idx || !mean3 || !m2)
     return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: null buffer");
   if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_reduce_moments: workspace too small");
-  if (((uintptr_t)keys_sorted | (uintptr_t)pos_sorted | (uintptr_t)idx_sorted) & 15u || ((uintptr_t)xyzw & 31u))
+  if (((uintptr_t)keys_sorted | (uintptr_t)pos_sorted | (uintptr_t)idx_sorted | (uintptr_t)row_sorted) & 15u || ((uintptr_t)xyzw & 31u))
     return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_moments: keys / positions / indices must be 16-byte and xyzw 32-byte aligned");
   const SegWs w = carve(ws, n);
   const Grid g = to_device_grid(grid_host);
@@ -621,19 +636,29 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, idx_sorted, w.carry_cnt, w.carry);
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted, w.carry_cnt, w.carry);
   } else {
     typedef unsigned long long K;
     const size_t smem = tile_smem_bytes<K>();
     VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, point2voxel, idx_sorted, w.carry_cnt, w.carry);
+        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted, w.carry_cnt, w.carry);
   }
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.n_long, 0, sizeof(uint32_t), s));
   VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
               nvoxels_host, count, mean3, m2, w.long_chains, w.n_long);
   VAPC_LAUNCH(fixup_long_chains_kernel, kNumSMs, kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt, nvoxels_host, count, mean3, m2,
               w.long_chains, w.n_long);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_scatter_u32(const uint32_t* index, const uint32_t* values, int64_t n, uint32_t* out, void* stream) {
+  if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_scatter_u32: n < 0");
+  if (n == 0) return VAPC_OK;
+  if (!index || !values || !out) return vapc_set_error(VAPC_E_INVALID, "vapc_scatter_u32: null buffer");
+  const int grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16);
+  VAPC_LAUNCH(scatter_rows_kernel, grid, kThreads, 0, as_stream(stream), index, values, n, out);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

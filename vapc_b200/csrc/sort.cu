@@ -56,7 +56,7 @@ __device__ __forceinline__ int segment_of_tile(const unsigned* first, int nseg, 
 // return value needed for counting); a CTA walks a contiguous range of tiles and flushes its non-zero
 // counters when the segment changes.
 template <typename KeyT, bool SEG>
-__global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int end_bit,
+__global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int begin_bit, int end_bit,
                                                               uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_start,
                                                               const uint32_t* __restrict__ seg_first_tile, int nseg, int tiles_per_cta) {
   __shared__ unsigned sh[kMaxPasses][kRadix];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __rest
     if (threadIdx.x == 0 && nseg == kMaxSegments) first[kMaxSegments] = seg_first_tile[kMaxSegments];
   }
   __syncthreads();
-  const unsigned last_mask = (1u << (end_bit - (passes - 1) * kRadixBits)) - 1u;
+  const unsigned last_mask = (1u << (end_bit - begin_bit - (passes - 1) * kRadixBits)) - 1u;
   const int64_t ntiles = SEG ? (int64_t)first[nseg] : (n + kTile - 1) / kTile;
   const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;
   const int64_t t1 = min(ntiles, t0 + tiles_per_cta);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __rest
       const KeyT k = __ldcs(keys + i);
       for (int p = 0; p < passes; ++p) {
         const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
-        atomicAdd(&sh[p][digit_of(k, p * kRadixBits, m)], 1u);
+        atomicAdd(&sh[p][digit_of(k, begin_bit + p * kRadixBits, m)], 1u);
       }
     }
   }
@@ -229,8 +229,8 @@ inline size_t look_offset() { return hist_bytes() + segtab_bytes() + 256; }
 bool g_force_wide_lookback = false;
 
 template <typename KeyT, typename LookT, bool SEG>
-int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int end_bit,
-                 int passes, const uint32_t* seg_start, int nseg, void* ws, int32_t* result_location, cudaStream_t s) {
+int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int begin_bit,
+                 int end_bit, int passes, const uint32_t* seg_start, int nseg, void* ws, int32_t* result_location, cudaStream_t s) {
   const int64_t ntiles = num_tiles(n) + (SEG ? nseg : 0);  // segmented: upper bound, surplus CTAs exit
   unsigned char* base = static_cast<unsigned char*>(ws);
   uint32_t* ghist = reinterpret_cast<uint32_t*>(base);
@@ -246,14 +246,14 @@ int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uin
   if (SEG) VAPC_LAUNCH(seg_tiles_kernel, 1, kThreads, 0, s, seg_start, nseg, seg_first_tile);
   const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * 8));
   const int tiles_per_cta = (int)((ntiles + hgrid - 1) / hgrid);
-  VAPC_LAUNCH((digit_hist_kernel<KeyT, SEG>), hgrid, kThreads, 0, s, keys, n, passes, end_bit, ghist, seg_start, seg_first_tile, hseg, tiles_per_cta);
+  VAPC_LAUNCH((digit_hist_kernel<KeyT, SEG>), hgrid, kThreads, 0, s, keys, n, passes, begin_bit, end_bit, ghist, seg_start, seg_first_tile, hseg, tiles_per_cta);
   VAPC_LAUNCH(digit_scan_kernel, passes * hseg, kThreads, 0, s, ghist, SEG ? seg_start : nullptr, hseg);
   // key buffers: keys -> alt -> (alt2 | keys) -> alt -> ...; with alt2 the caller's keys stay intact
   KeyT* src_k = keys; KeyT* dst_k = keys_alt;
   KeyT* spare = keys_alt2 ? keys_alt2 : keys;
   uint32_t* src_i = idx; uint32_t* dst_i = idx_alt;
   for (int p = 0; p < passes; ++p) {
-    const int shift = p * kRadixBits;
+    const int shift = begin_bit + p * kRadixBits;
     const int bits = std::min(kRadixBits, end_bit - shift);
     const unsigned mask = (1u << bits) - 1u;
     VAPC_RETURN_IF_CUDA(cudaMemsetAsync(ticket, 0, 256 + look_bytes, s));  // ticket + look-back words (contiguous)
@@ -275,9 +275,9 @@ int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uin
 }
 
 template <typename KeyT>
-int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int end_bit,
-              const uint32_t* seg_start, int nseg, void* ws, int32_t* result_location, cudaStream_t s) {
-  const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
+int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int idx_is_iota, int64_t n, int begin_bit,
+              int end_bit, const uint32_t* seg_start, int nseg, void* ws, int32_t* result_location, cudaStream_t s) {
+  const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
   if (passes == 0) {
     if (idx_is_iota) VAPC_LAUNCH(iota_kernel, kNumSMs * 8, 256, 0, s, idx, n);
     *result_location = 0;
@@ -287,29 +287,29 @@ int sort_impl(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uint32
   // 30-bit counts in 32-bit look-back words cover n < 2^30; beyond that (or when a test asks) 64-bit words
   const bool wide = n >= ((int64_t)1 << 30) || g_force_wide_lookback;
   if (seg_start) {
-    if (!wide) return sweep_passes<KeyT, uint32_t, true>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, seg_start, nseg, ws, result_location, s);
-    return sweep_passes<KeyT, unsigned long long, true>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, seg_start, nseg, ws, result_location, s);
+    if (!wide) return sweep_passes<KeyT, uint32_t, true>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, begin_bit, end_bit, passes, seg_start, nseg, ws, result_location, s);
+    return sweep_passes<KeyT, unsigned long long, true>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, begin_bit, end_bit, passes, seg_start, nseg, ws, result_location, s);
   }
-  if (!wide) return sweep_passes<KeyT, uint32_t, false>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, nullptr, 1, ws, result_location, s);
-  return sweep_passes<KeyT, unsigned long long, false>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, end_bit, passes, nullptr, 1, ws, result_location, s);
+  if (!wide) return sweep_passes<KeyT, uint32_t, false>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, begin_bit, end_bit, passes, nullptr, 1, ws, result_location, s);
+  return sweep_passes<KeyT, unsigned long long, false>(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, begin_bit, end_bit, passes, nullptr, 1, ws, result_location, s);
 }
 
 int sort_entry(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int32_t idx_is_iota, int64_t n, int32_t key_bytes,
-               int32_t end_bit, const uint32_t* seg_start, int32_t nseg, void* ws, size_t ws_bytes, int32_t* result_location_host, void* stream,
+               int32_t begin_bit, int32_t end_bit, const uint32_t* seg_start, int32_t nseg, void* ws, size_t ws_bytes, int32_t* result_location_host, void* stream,
                const char* who) {
   if (n < 0 || !result_location_host) return vapc_set_error(VAPC_E_INVALID, "%s: bad arguments", who);
   if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "%s: n must be < 2^32 per GPU", who);
   *result_location_host = 0;
   if (n == 0) return VAPC_OK;
   if (!keys || !keys_alt || !idx || !idx_alt) return vapc_set_error(VAPC_E_INVALID, "%s: null buffer", who);
-  if (end_bit < 0 || end_bit > key_bytes * 8) return vapc_set_error(VAPC_E_INVALID, "%s: end_bit out of range", who);
+  if (begin_bit < 0 || end_bit < begin_bit || end_bit > key_bytes * 8) return vapc_set_error(VAPC_E_INVALID, "%s: bit range out of bounds", who);
   if (ws_bytes < vapc_sort_workspace_bytes(n) || !ws) return vapc_set_error(VAPC_E_WORKSPACE, "%s: workspace too small", who);
   if (key_bytes == 4)
     return sort_impl<uint32_t>(static_cast<uint32_t*>(keys), static_cast<uint32_t*>(keys_alt), static_cast<uint32_t*>(keys_alt2), idx, idx_alt,
-                               idx_is_iota, n, end_bit, seg_start, nseg, ws, result_location_host, as_stream(stream));
+                               idx_is_iota, n, begin_bit, end_bit, seg_start, nseg, ws, result_location_host, as_stream(stream));
   if (key_bytes == 8)
     return sort_impl<unsigned long long>(static_cast<unsigned long long*>(keys), static_cast<unsigned long long*>(keys_alt),
-                                         static_cast<unsigned long long*>(keys_alt2), idx, idx_alt, idx_is_iota, n, end_bit, seg_start, nseg, ws,
+                                         static_cast<unsigned long long*>(keys_alt2), idx, idx_alt, idx_is_iota, n, begin_bit, end_bit, seg_start, nseg, ws,
                                          result_location_host, as_stream(stream));
   return vapc_set_error(VAPC_E_INVALID, "%s: key_bytes must be 4 or 8", who);
 }
@@ -328,8 +328,15 @@ extern "C" size_t vapc_sort_workspace_bytes(int64_t n) {
 extern "C" int vapc_sort_pairs(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int32_t idx_is_iota,
                                int64_t n, int32_t key_bytes, int32_t end_bit, void* ws, size_t ws_bytes, int32_t* result_location_host,
                                void* stream) {
-  return sort_entry(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, key_bytes, end_bit, nullptr, 1, ws, ws_bytes, result_location_host,
+  return sort_entry(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, key_bytes, 0, end_bit, nullptr, 1, ws, ws_bytes, result_location_host,
                     stream, "vapc_sort_pairs");
+}
+
+extern "C" int vapc_sort_pairs_bits(void* keys, void* keys_alt, void* keys_alt2, uint32_t* idx, uint32_t* idx_alt, int32_t idx_is_iota,
+                                    int64_t n, int32_t key_bytes, int32_t begin_bit, int32_t end_bit, void* ws, size_t ws_bytes,
+                                    int32_t* result_location_host, void* stream) {
+  return sort_entry(keys, keys_alt, keys_alt2, idx, idx_alt, idx_is_iota, n, key_bytes, begin_bit, end_bit, nullptr, 1, ws, ws_bytes,
+                    result_location_host, stream, "vapc_sort_pairs_bits");
 }
 
 extern "C" int vapc_sort_pairs_segmented(void* keys, void* keys_alt, uint32_t* idx, uint32_t* idx_alt, int32_t idx_is_iota, int64_t n,
@@ -337,6 +344,6 @@ extern "C" int vapc_sort_pairs_segmented(void* keys, void* keys_alt, uint32_t* i
                                          int32_t* result_location_host, void* stream) {
   if (!seg_start || nseg < 1 || nseg > kMaxSegments)
     return vapc_set_error(VAPC_E_INVALID, "vapc_sort_pairs_segmented: 1..%d segments", kMaxSegments);
-  return sort_entry(keys, keys_alt, nullptr, idx, idx_alt, idx_is_iota, n, key_bytes, end_bit, seg_start, nseg, ws, ws_bytes, result_location_host,
+  return sort_entry(keys, keys_alt, nullptr, idx, idx_alt, idx_is_iota, n, key_bytes, 0, end_bit, seg_start, nseg, ws, ws_bytes, result_location_host,
                     stream, "vapc_sort_pairs_segmented");
 }

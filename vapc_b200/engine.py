@@ -106,7 +106,7 @@ def voxel_coords(x, y, z, voxel_size, origin):
     return out
 
 
-def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = None, preserve_keys: bool = False):
+def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = None, preserve_keys: bool = False, begin_bit: int = 0):
     """Stable LSD radix sort of (key, idx) by the low `end_bit` key bits.  keys: uint32-as-int32 or
     uint64-as-int64 storage (torch has no unsigned 32/64 arithmetic; only the bytes matter).
     Returns (keys_sorted, idx_sorted) — new tensors or the inputs, whichever holds the result.
@@ -115,7 +115,7 @@ def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = N
     dev = keys.device
     key_bytes = keys.element_size()
     keys_alt = torch.empty_like(keys)
-    passes = (int(end_bit) + 7) // 8
+    passes = (int(end_bit) - int(begin_bit) + 7) // 8
     keys_alt2 = torch.empty_like(keys) if (preserve_keys and passes > 1) else None
     iota = idx is None
     if iota:
@@ -124,8 +124,8 @@ def sort_pairs(keys: torch.Tensor, end_bit: int, idx: Optional[torch.Tensor] = N
     ws_bytes = L.raw("vapc_sort_workspace_bytes")(n)
     ws = _empty(ws_bytes, torch.uint8, dev)
     loc = C.c_int32(0)
-    L.call("vapc_sort_pairs", _ptr(keys), _ptr(keys_alt), _ptr(keys_alt2), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, key_bytes,
-           int(end_bit), _ptr(ws), ws_bytes, C.byref(loc), _stream())
+    L.call("vapc_sort_pairs_bits", _ptr(keys), _ptr(keys_alt), _ptr(keys_alt2), _ptr(idx), _ptr(idx_alt), 1 if iota else 0, n, key_bytes,
+           int(begin_bit), int(end_bit), _ptr(ws), ws_bytes, C.byref(loc), _stream())
     out_keys = (keys, keys_alt, keys_alt2)[loc.value & 3]
     if preserve_keys and out_keys is keys and passes > 0:  # cannot happen with a third buffer; guard the contract
         raise AssertionError("sort overwrote preserved keys")
@@ -272,9 +272,16 @@ class VoxelCloud:
         self.m2 = torch.empty((6, V), dtype=torch.float64, device=device)
         self.point2voxel = _empty(n, torch.int32, device) if want_point2voxel else None
         self.idx_sorted = _empty(n, torch.int32, device)
+        row_sorted = _empty(n, torch.int32, device) if (want_point2voxel and not dense_p2v) else None
         L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.pos_sorted), n, C.byref(g), _ptr(self.xyzw), V,
                _ptr(self.voxel_keys), _ptr(self.start), _ptr(self.count), _ptr(self.first_idx), _ptr(self.mean3), _ptr(self.m2),
-               _ptr(None if dense_p2v else self.point2voxel), _ptr(self.idx_sorted), _ptr(self._seg_ws), ws_bytes, _stream())
+               _ptr(row_sorted), _ptr(self.idx_sorted), _ptr(self._seg_ws), ws_bytes, _stream())
+        if row_sorted is not None:
+            # (index, row) pairs grouped by the leading byte of the index, then scattered inside L2-sized windows
+            nbits = max(1, int(n - 1).bit_length())
+            grouped_idx, grouped_row = sort_pairs(self.idx_sorted, nbits, idx=row_sorted, preserve_keys=True, begin_bit=max(0, nbits - 8))
+            L.call("vapc_scatter_u32", _ptr(grouped_idx), _ptr(grouped_row), n, _ptr(self.point2voxel), _stream())
+            del grouped_idx, grouped_row, row_sorted
         if dense_p2v:
             tbytes = L.raw("vapc_point2voxel_table_bytes")(g.total_bits)
             table = _empty(tbytes, torch.uint8, device)
