@@ -1,0 +1,180 @@
+"""Parity at the sizes of BASELINE.json's configs, where the per-voxel Python oracle cannot follow: the CUDA path is
+cross-checked against an INDEPENDENT torch implementation (torch.unique(return_inverse) + index_add_ in fp64,
+SURVEY.md section 8(d) "parity at scale") and through size-independent properties (sortedness, permutation, checksums
+of counts, linearity, trace = sum of eigenvalues, join consistency)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    from vapc_b200 import engine
+
+    return engine
+
+
+def _u32(t):
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+def torch_voxel_table(x, y, z, vs, origin=(0.0, 0.0, 0.0)):
+    """Independent device implementation: (unique voxel triples in lexicographic order, inverse, counts, centroid, cov6)."""
+    # a TENSOR divisor: torch turns division by a Python scalar into a multiplication by its reciprocal on CUDA, which
+    # puts points that lie exactly on a voxel face into the wrong voxel (1 voxel in 1e7 differed in this very test)
+    vs_t = torch.full((1,), vs, dtype=torch.float64, device=x.device)
+    v = [torch.floor((c - o) / vs_t).to(torch.int64) for c, o in zip((x, y, z), origin)]
+    lo = [int(a.min()) for a in v]
+    ext = [int(a.max()) - l + 1 for a, l in zip(v, lo)]
+    packed = ((v[0] - lo[0]) * ext[1] + (v[1] - lo[1])) * ext[2] + (v[2] - lo[2])
+    uniq, inv, cnt = torch.unique(packed, return_inverse=True, return_counts=True)
+    V = uniq.numel()
+    vz = uniq % ext[2] + lo[2]
+    vy = (uniq // ext[2]) % ext[1] + lo[1]
+    vx = uniq // (ext[2] * ext[1]) + lo[0]
+    n = cnt.to(torch.float64)
+    cog = torch.stack([torch.zeros(V, dtype=torch.float64, device=x.device).index_add_(0, inv, c) / n for c in (x, y, z)])
+    d = [c - cog[k][inv] for k, c in enumerate((x, y, z))]
+    cov = []
+    for a, b in ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)):
+        s = torch.zeros(V, dtype=torch.float64, device=x.device).index_add_(0, inv, d[a] * d[b])
+        cov.append(s / (n - 1))
+    return (vx, vy, vz), inv, cnt, cog, torch.stack(cov)
+
+
+def check_against_torch(E, x, y, z, vs, full_stats=True):
+    cloud = E.VoxelCloud.build(x, y, z, vs, [0.0, 0.0, 0.0])
+    n = x.numel()
+    (vx, vy, vz), inv, cnt, cog, cov = torch_voxel_table(x, y, z, vs)
+    assert cloud.nvoxels == cnt.numel()
+    for a, b in zip(cloud.voxel_coords(), (vx, vy, vz)):
+        assert torch.equal(a, b), "voxel triples, lexicographic order"
+    assert torch.equal(_u32(cloud.count), cnt), "point counts are exact"
+    assert torch.equal(_u32(cloud.point2voxel), inv), "point -> voxel map is exact"
+    ks = cloud.keys_sorted
+    ks = _u32(ks) if ks.dtype == torch.int32 else ks
+    assert bool((ks[1:] >= ks[:-1]).all()), "sortedness"
+    idx = _u32(cloud.idx_sorted)
+    seen = torch.zeros(n, dtype=torch.bool, device=x.device)
+    seen[idx] = True
+    assert bool(seen.all()), "sorted indices are a permutation"
+    assert torch.equal(inv[idx], torch.repeat_interleave(torch.arange(cnt.numel(), device=x.device), cnt)), "every sorted point sits in its voxel's slice"
+    first = _u32(cloud.first_idx)
+    lowest = torch.full((cnt.numel(),), n, dtype=torch.int64, device=x.device).scatter_reduce_(0, inv, torch.arange(n, device=x.device), reduce="amin")
+    assert torch.equal(first, lowest), "first point of a voxel = lowest original index (stable sort)"
+    st = cloud.stats(cog=True, cov=True, eig=True, feat=full_stats)
+    scale = torch.stack([c.abs().max() for c in (x, y, z)])[:, None]
+    assert bool(((st.cog - cog).abs() <= 1e-9 * scale).all()), "centroid within 1e-9"
+    multi = cnt > 1
+    cmax = cov[:, multi].abs().amax(0)
+    # H1: 1e-9 of the voxel's largest covariance entry + the rounding floor of the two-pass checker itself
+    floor = 16 * 2.2e-16 * (scale.max() ** 2)
+    assert bool(((st.cov[:, multi] - cov[:, multi]).abs() <= 1e-9 * cmax + floor).all()), "covariance within 1e-9 (norm-wise)"
+    assert bool(torch.isnan(st.cov[:, ~multi]).all()), "n = 1 voxels have NaN covariance"
+    eig = st.eig[:, multi]
+    trace = st.cov[0, multi] + st.cov[3, multi] + st.cov[5, multi]
+    assert bool(((eig.sum(0) - trace).abs() <= 1e-9 * trace.abs() + 1e-18).all()), "sum of eigenvalues = trace"
+    assert bool((eig[0] >= eig[1]).all()) and bool((eig[1] >= eig[2]).all()) and bool((eig[2] >= 0).all())
+    return cloud
+
+
+def quantised_uniform(n, extent, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return [torch.randint(0, int(round(e / 1e-4)), (n,), device="cuda", generator=g).to(torch.float64) * 1e-4 for e in extent]
+
+
+def test_config2_full_size_100M_uniform(E):
+    """BASELINE configs[1] at its full size: 1e8 uniform points, voxel 0.1 m (bench.py's workload)."""
+    x, y, z = quantised_uniform(100_000_000, (50.0, 50.0, 4.0), 2)
+    cloud = check_against_torch(E, x, y, z, 0.1)
+    assert cloud.grid.total_bits == 24 and 9_990_000 < cloud.nvoxels <= 10_000_000
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("scan_order,vs", [(True, 0.25), (False, 0.1)])
+def test_config3_clustered(E, scan_order, vs):
+    """C3-like clustered cloud (terrain sheet + trees), scan-line order and shuffled; large grids (> 32 key bits at 0.1 m)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from kbench import clustered_cloud
+
+    x, y, z = clustered_cloud(30_000_000, seed=3, extent=400.0, scan_order=scan_order)
+    z = z - z.min()
+    cloud = check_against_torch(E, x, y, z, vs, full_stats=False)
+    assert cloud.grid.total_bits > 25  # the generic point -> voxel path
+    torch.cuda.empty_cache()
+
+
+def test_config4_two_epoch_join_and_change(E):
+    """Two epochs of 1e7 points: voxel join, centroid distance, Mahalanobis significance."""
+    n, vs = 10_000_000, 0.5
+    x, y, _ = quantised_uniform(n, (200.0, 200.0, 10.0), 4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # a thin surface (sigma 1 cm) inside the voxel layer [2.0, 2.5): a 15 cm lift of one quarter of the scene moves the
+    # voxel centroids without moving points to other voxels; a strip disappears in epoch 2
+    z = torch.round((2.2 + 0.01 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)) * 1e4) * 1e-4
+    moved = x > 150.0
+    x2, y2 = x.clone(), y.clone()
+    z2 = z + torch.where(moved, 0.15, 0.0) + torch.randn(n, device="cuda", generator=g, dtype=torch.float64) * 0.002
+    keep = ~((y2 > 90.0) & (y2 < 95.0))
+    c1 = E.VoxelCloud.build(x, y, z, vs, [0.0, 0.0, 0.0], want_point2voxel=False)
+    c2 = E.VoxelCloud.build(x2[keep], y2[keep], z2[keep], vs, [0.0, 0.0, 0.0], want_point2voxel=False)
+    v1, v2 = c1.voxel_coords(), c2.voxel_coords()
+    i1, i2, only1, only2 = E.join_voxel_tables(v1, v2)
+    assert i1.numel() + only1.numel() == c1.nvoxels and i2.numel() + only2.numel() == c2.nvoxels
+    for a, b in zip(v1, v2):
+        assert torch.equal(a[i1], b[i2]), "joined rows are the same voxel"
+    assert bool((i1[1:] > i1[:-1]).all()), "pairs in epoch-1 row order"
+    # every voxel of the removed strip that epoch 1 occupies and epoch 2 does not is in only1
+    strip = (v1[1][only1].to(torch.float64) * vs > 89.0) & (v1[1][only1].to(torch.float64) * vs < 96.0)
+    assert int(strip.sum()) > 0.5 * only1.numel()
+    s1 = c1.stats(cog=True, cov=True)
+    s2 = c2.stats(cog=True, cov=True)
+    out = E.mahalanobis(s1.cog, s1.cov, s2.cog, s2.cov, i1, i2, alpha=0.005)
+    d = (s1.cog[:, i1] - s2.cog[:, i2])
+    assert bool(((out["distance"] - d.pow(2).sum(0).sqrt()).abs() <= 1e-12).all())
+    p = out["p_value"]
+    ok = ~torch.isnan(p)
+    assert bool(((p[ok] >= 0) & (p[ok] <= 1)).all())
+    sig = out["significance"].bool()
+    in_moved = (v1[0][i1].to(torch.float64) * vs > 151.0)
+    dense = (_u32(c1.count)[i1] >= 8) & (_u32(c2.count)[i2] >= 8)
+    assert float(sig[in_moved & dense].float().mean()) > 0.95, "the shifted part is detected"
+    assert float(sig[~in_moved & dense & (v1[0][i1].to(torch.float64) * vs < 149.0)].float().mean()) < 0.05, "the static part is not"
+    ct = out["change_type"]
+    assert bool((ct[~sig] == 0).all()) and bool(((ct[sig] == 1) | (ct[sig] == 2)).all())
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("vs", [0.05, 0.2, 1.0])
+def test_config5_mode_count_and_subsample_sweep(E, vs):
+    """mode / mode_count,0.1 of an integer classification and closest-to-centroid subsampling at three voxel sizes."""
+    n = 10_000_000
+    x, y, z = quantised_uniform(n, (40.0, 40.0, 4.0), 6)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cls = (torch.floor(x / 5.0) + torch.floor(y / 5.0)).to(torch.int64) % 8 + 1  # blocks of one class ...
+    noise = torch.rand(n, device="cuda", generator=g) < 0.1  # ... with 10 % label noise
+    cls = torch.where(noise, torch.randint(1, 9, (n,), device="cuda", generator=g), cls)
+    cloud = E.VoxelCloud.build(x, y, z, vs, [0.0, 0.0, 0.0])
+    V = cloud.nvoxels
+    mode, counts = cloud.mode_count(cls.to(torch.float64), thresholds=(0.1,))
+    inv = _u32(cloud.point2voxel)
+    table = torch.zeros((V, 9), dtype=torch.int64, device="cuda")
+    table.view(-1).index_add_(0, inv * 9 + cls, torch.ones(n, dtype=torch.int64, device="cuda"))
+    assert torch.equal(table.sum(1), _u32(cloud.count))
+    assert torch.equal(mode, table.argmax(1)), "mode = smallest most frequent value"
+    share = table.to(torch.float64) / table.sum(1, keepdim=True).to(torch.float64)
+    assert torch.equal(counts[0.1], ((table > 0) & (share >= 0.1)).sum(1)), "mode_count,0.1"
+    md, am = cloud.closest_to_cog()
+    am = _u32(am)
+    assert torch.equal(inv[am], torch.arange(V, device="cuda")), "the selected point belongs to its voxel"
+    cog = cloud.stats(cog=True).cog
+    dist = ((x - cog[0][inv]) ** 2 + (y - cog[1][inv]) ** 2 + (z - cog[2][inv]) ** 2).sqrt()
+    best = torch.full((V,), float("inf"), dtype=torch.float64, device="cuda").scatter_reduce_(0, inv, dist, reduce="amin")
+    assert bool(((md - best).abs() <= 1e-9 * best + 1e-12).all()), "minimum distance per voxel"
+    assert bool((dist[am] <= best * (1 + 1e-9) + 1e-12).all()), "the selected point attains it"
+    torch.cuda.empty_cache()
