@@ -333,6 +333,27 @@ def test_two_epoch_join_and_mahalanobis_vs_oracle(E):
         assert np.all(_np(res["change_type"])[nan_rows] == 0)
 
 
+def test_lexsort_unique_rows_matches_pandas(E):
+    """The GPU replacement of the reference's final drop_duplicates + groupby(XYZ) formatting visits the same rows in the
+    same order as pandas (duplicates, -0.0 / 0.0, NaN coordinates, ties in X and Y)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 5000, 200_000):
+        x = rng.integers(-20, 20, n) * 0.25
+        y = rng.integers(-5, 5, n) * 0.5
+        z = np.round(rng.normal(0, 1, n), 1)
+        if n > 100:
+            x[::97] = -0.0
+            x[1::97] = 0.0
+            z[5::211] = np.nan
+            y[7::313] = np.nan
+        df = pd.DataFrame({"X": x, "Y": y, "Z": z, "row": np.arange(n, dtype=np.float64)})
+        ref = df.drop_duplicates(subset=["X", "Y", "Z"]).groupby(["X", "Y", "Z"], as_index=False).median(numeric_only=True)
+        rows = E.lexsort_unique_rows(x, y, z)
+        np.testing.assert_array_equal(rows, ref["row"].to_numpy().astype(np.int64))
+
+
 def test_reproducible_bitwise(E):
     """No atomics in the reductions: two runs give bit-identical tables — and so does the path that keeps the
     records in input order and sorts all key bits (bucketed=False)."""

@@ -30,6 +30,9 @@ constexpr int kThreads = 256;
 constexpr int kItems = 4;
 constexpr int kSegTile = kThreads * kItems;  // 1024
 constexpr int kPartialRowWords = 11;         // exchanged partial voxel row: key, count, mean[3], M2[6] (8 bytes each)
+#ifndef VAPC_REDUCE_MINB
+#define VAPC_REDUCE_MINB 4
+#endif
 
 struct SegWs {  // layout of the segmentation workspace
   uint32_t* tile_heads;       // [ntiles]   heads per tile, then (in place) exclusive scan = first voxel row of the tile
@@ -163,7 +166,7 @@ __device__ __forceinline__ void tile_prologue(TileSmem<KeyT>& sm, const KeyT* __
 
 // ---- step 2: moments ------------------------------------------------------------------------------
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) reduce_moments_kernel(
+__global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_kernel(
     const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
     const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
     uint32_t* __restrict__ count, uint32_t* __restrict__ first_idx, double* __restrict__ mean3, double* __restrict__ m2,

@@ -409,6 +409,32 @@ def attribute_statistics(cloud: VoxelCloud, attr, median=True) -> Dict[str, torc
     return out
 
 
+def lexsort_unique_rows(x, y, z, device=None) -> np.ndarray:
+    """Row numbers that `df.drop_duplicates(subset=[X, Y, Z])` followed by `df.groupby([X, Y, Z]).<agg>()` visits, in the
+    order of the result (vapc.py:1208-1209): rows sorted lexicographically by (X, Y, Z), of rows with identical coordinates only
+    the first (lowest row number), rows with a NaN coordinate dropped.  Three stable 64-bit radix sorts on the GPU (Z, then
+    Y, then X) instead of pandas' hash + sort on the host."""
+    _require_cuda()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    cols = [_dev_f64(a, device) + 0.0 for a in (x, y, z)]  # + 0.0: -0.0 and 0.0 are one group, as in pandas
+    n = cols[0].numel()
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    order = None
+    for c in reversed(cols):
+        keys = _empty(n, torch.int64, device)
+        src = c if order is None else c[order.to(torch.int64) & 0xFFFFFFFF]
+        L.call("vapc_f64_sort_keys", _ptr(src.contiguous()), n, _ptr(keys), _stream())
+        _, order = sort_pairs(keys, 64, idx=order)
+    rows = order.to(torch.int64) & 0xFFFFFFFF
+    sx, sy, sz = (c[rows] for c in cols)
+    keep = torch.ones(n, dtype=torch.bool, device=device)
+    keep[1:] = (sx[1:] != sx[:-1]) | (sy[1:] != sy[:-1]) | (sz[1:] != sz[:-1])
+    keep &= ~(torch.isnan(sx) | torch.isnan(sy) | torch.isnan(sz))
+    return rows[keep].cpu().numpy()
+
+
 # ----------------------------------------------------------------------------------------
 # masks
 # ----------------------------------------------------------------------------------------
