@@ -278,7 +278,32 @@ def grid8():
     save("grid8_vs1", store)
 
 
+def real_file():
+    """BASELINE configs[0]: the reference's own sample file tests/test_data/vapc_in.laz (LAS 1.2, point format 2,
+    LASzip-compressed), voxel 0.25 m.  laspy is not installable offline, so the points are decoded with this
+    repository's LAZ reader (vapc_b200/las.py -> vapc_laz_decode), which tests/test_laz.py pins against the file
+    header's bounding box and the reference's own known answer for this file ("13.43 percent of the voxel space is
+    occupied" at voxel 0.5, tests/integration_tests/test_main.py:216-218).  Every 50th point (10 954 points) keeps the
+    fixture small and the reference's per-voxel Python eigen step short; tests/test_data/small_mask.laz is the mask."""
+    from vapc_b200 import las
+
+    root = "/root/reference/tests/test_data/"
+    _, c = las.read_las(root + "vapc_in.laz")
+    sel = slice(0, None, 50)
+    df = pd.DataFrame({"X": c["x"][sel], "Y": c["y"][sel], "Z": c["z"][sel], "red": c["red"][sel].astype(np.float64),
+                       "classification": (c["red"][sel] // 8000).astype(np.float64)})
+    _, m = las.read_las(root + "small_mask.laz")
+    mask = pd.DataFrame({"X": m["x"], "Y": m["y"], "Z": m["z"]})
+    store = {}
+    run_cloud(store, df, 0.25, stats={"red": ["mean", "min", "max", "median"], "classification": ["mode", "mode_count,0.1"]}, mask_df=mask,
+              buffer_size=1)
+    save("vapc_in_every50th_vs0.25", store)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "real_file":
+        real_file()
+        sys.exit(0)
     kat_voxelize()
     kat_cloud10()
     plane500()
@@ -286,3 +311,4 @@ if __name__ == "__main__":
     shifted_origin()
     utm_offset()
     grid8()
+    real_file()

@@ -109,9 +109,8 @@ def test_save_as_las_roundtrip(tmp_path):
     with pytest.raises(NotImplementedError):
         dh.save_as_las(str(tmp_path / "out.laz"))
     laz = out.replace(".las", ".laz")
-    os.rename(out, laz)  # an uncompressed file under a .laz name is refused, like a really compressed one
-    with pytest.raises(NotImplementedError):
-        las.read_las(laz)
+    os.rename(out, laz)  # an uncompressed file under a .laz name is read as what it is
+    assert las.read_las(laz)[0].point_count == n
 
 
 def test_extra_bytes_vlr_types_and_empty_cloud(tmp_path):

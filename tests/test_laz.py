@@ -1,0 +1,81 @@
+"""The LASzip decoder (vapc_laz_decode, host code in libvapc_b200.so) against the reference's own LAZ fixtures.
+
+The fixtures are read where the reference lies (/root/reference/tests/test_data, build container only); nothing is
+copied.  On a box without the reference these tests skip — the decoded real data still travels as the golden fixture
+tests/golden/vapc_in_every50th_vs0.25.npz (oracle/make_golden.py real_file), which the GPU parity tests use.
+
+Pins: (1) the file headers' own bounding boxes, which the decoded points must reproduce exactly; (2) the reference's
+known answers for vapc_in.laz — frame shape and dimension names (tests/integration_tests/test_io.py:63-80) and "13.43
+percent of the voxel space is occupied" at voxel 0.5 (tests/integration_tests/test_main.py:216-218); (3) digests of the
+decoded integer records, so that any later change of the decoder shows."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vapc_oracle as O
+from vapc_b200 import DataHandler, las
+
+DATA = "/root/reference/tests/test_data"
+needs_fixtures = pytest.mark.skipif(not os.path.exists(os.path.join(DATA, "vapc_in.laz")), reason="reference fixtures not on this box")
+
+FMT2_ATTRS = ['intensity', 'return_number', 'number_of_returns', 'scan_direction_flag', 'edge_of_flight_line', 'classification', 'synthetic',
+              'key_point', 'withheld', 'scan_angle_rank', 'user_data', 'point_source_id', 'red', 'green', 'blue']
+
+
+@needs_fixtures
+def test_small_mask_single_chunk():
+    h, c = las.read_las(os.path.join(DATA, "small_mask.laz"))
+    assert h.compressed and h.point_format == 2 and h.point_count == 3065 and h.laszip["compressor"] == 2
+    assert h.laszip["items"] == [(6, 20, 2), (8, 6, 2)]  # POINT10 v2 + RGB12 v2
+    for k, d in enumerate("xyz"):
+        assert c[d].min() == h.mins[k] and c[d].max() == h.maxs[k], "decoded bounding box == header bounding box"
+    raw = np.stack([c["X"], c["Y"], c["Z"]], 1).astype(np.int32)
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == "c13b5310baa5f2a3322e3f444e6291d5494c7944b5a061d56b3d34e22410c5e9"
+
+
+@needs_fixtures
+def test_vapc_in_multi_chunk_known_answers():
+    path = os.path.join(DATA, "vapc_in.laz")
+    dh = DataHandler(path)
+    dh.load_las_files()
+    assert dh.df.shape == (547662, 18)  # test_io.py:74
+    assert dh.attributes == FMT2_ATTRS  # test_io.py:79
+    assert list(dh.df.columns[:3]) == ["X", "Y", "Z"] and dh.las_header is not None
+    h = dh.las_header
+    assert h.laszip["chunk_size"] == 50000  # 11 chunks: the chunk table is decoded too
+    for k, d in enumerate("XYZ"):
+        assert dh.df[d].min() == h.mins[k] and dh.df[d].max() == h.maxs[k]
+    x, y, z = (dh.df[d].to_numpy() for d in "XYZ")
+    g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], 0.5))
+    assert O.percentage_occupied(g) == 13.43  # test_main.py:216-218
+    _, c = las.read_las(path)
+    raw = np.stack([c["X"], c["Y"], c["Z"], c["red"], c["green"], c["blue"]], 1).astype(np.int64)
+    assert raw.sum(0).tolist() == [7819251612, 8861305537, 6141071598314, 19648548864, 19063821312, 17777984512]
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == "313f0062c201ad4891ef0058c109c8e7716a777232e935a31aa2316de29761f7"
+
+
+@needs_fixtures
+def test_golden_fixture_is_the_decoded_file():
+    """tests/golden/vapc_in_every50th_vs0.25.npz holds every 50th decoded point."""
+    from tests import parity as P
+
+    g = P.load_golden("vapc_in_every50th_vs0.25")
+    _, c = las.read_las(os.path.join(DATA, "vapc_in.laz"))
+    for d in "xyz":
+        np.testing.assert_array_equal(g["in_" + d.upper()], c[d][::50])
+    _, m = las.read_las(os.path.join(DATA, "small_mask.laz"))
+    np.testing.assert_array_equal(g["in_mask_X"], m["x"])
+
+
+@needs_fixtures
+def test_unsupported_and_damaged_files(tmp_path):
+    for name in ("tree_wind_condition.laz", "als_multichannel_leg000_points.laz"):  # LAS 1.4 layered items (compressor 3)
+        with pytest.raises(NotImplementedError, match="not supported"):
+            las.read_las(os.path.join(DATA, name))
+    buf = open(os.path.join(DATA, "small_mask.laz"), "rb").read()
+    cut = str(tmp_path / "cut.laz")
+    open(cut, "wb").write(buf[: len(buf) // 2])  # truncated inside the only chunk
+    with pytest.raises(ValueError):
+        las.read_las(cut)

@@ -1,0 +1,535 @@
+// LASzip decoder for the point layout of the reference's fixtures (tests/test_data/vapc_in.laz, small_mask.laz):
+// "pointwise chunked" compression (compressor 2) of POINT10 (version 2) + RGB12 (version 2) items, i.e. LAS point
+// format 2 written by LASzip 2.x / 3.x without layering.  Host code (file decoding sits in front of the hot path,
+// SURVEY.md section 8(f) row 1): the reference gets this from laspy[lazrs] (src/vapc/datahandler.py:72-73), which is
+// not installable offline.  Written from the published LASzip format description (Isenburg, "LASzip: lossless
+// compression of LiDAR data", PE&RS 2013) — an adaptive arithmetic coder (Said's FastAC scheme), integer
+// "corrector" coders with k-bit contexts, and the per-item predictors of version 2.
+//
+// Other items (GPSTIME11, WAVEPACKET13, the layered POINT14 family of LAS 1.4) are reported as unsupported.
+#include <stdint.h>
+#include <string.h>
+
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+// ---- byte source --------------------------------------------------------------------------------------------
+struct ByteReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool overrun = false;
+  uint8_t byte() {
+    if (p < end) return *p++;
+    overrun = true;
+    return 0;
+  }
+};
+
+// ---- adaptive arithmetic decoder ------------------------------------------------------------------------------
+constexpr uint32_t kAcMinLength = 0x01000000u, kAcMaxLength = 0xFFFFFFFFu;
+constexpr int kBmLengthShift = 13, kDmLengthShift = 15;
+constexpr uint32_t kBmMaxCount = 1u << kBmLengthShift, kDmMaxCount = 1u << kDmLengthShift;
+
+struct BitModel {
+  uint32_t update_cycle, bits_until_update, bit_0_prob, bit_0_count, bit_count;
+  void init() {
+    bit_0_count = 1;
+    bit_count = 2;
+    bit_0_prob = 1u << (kBmLengthShift - 1);
+    update_cycle = bits_until_update = 4;
+  }
+  void update() {
+    if ((bit_count += update_cycle) > kBmMaxCount) {
+      bit_count = (bit_count + 1) >> 1;
+      bit_0_count = (bit_0_count + 1) >> 1;
+      if (bit_0_count == bit_count) ++bit_count;
+    }
+    const uint32_t scale = 0x80000000u / bit_count;
+    bit_0_prob = (bit_0_count * scale) >> (31 - kBmLengthShift);
+    update_cycle = (5 * update_cycle) >> 2;
+    if (update_cycle > 64) update_cycle = 64;
+    bits_until_update = update_cycle;
+  }
+};
+
+struct SymbolModel {
+  uint32_t symbols = 0, last_symbol = 0, table_size = 0, table_shift = 0;
+  uint32_t total_count = 0, update_cycle = 0, symbols_until_update = 0;
+  std::vector<uint32_t> distribution, symbol_count, decoder_table;
+  explicit SymbolModel(uint32_t n) : symbols(n) {
+    last_symbol = n - 1;
+    if (n > 16) {
+      uint32_t table_bits = 3;
+      while (n > (1u << (table_bits + 2))) ++table_bits;
+      table_size = 1u << table_bits;
+      table_shift = kDmLengthShift - table_bits;
+      decoder_table.assign(table_size + 2, 0);
+    }
+    distribution.assign(n, 0);
+    symbol_count.assign(n, 0);
+    init();
+  }
+  void init() {
+    total_count = 0;
+    update_cycle = symbols;
+    for (uint32_t k = 0; k < symbols; ++k) symbol_count[k] = 1;
+    update();
+    symbols_until_update = update_cycle = (symbols + 6) >> 1;
+  }
+  void update() {
+    if ((total_count += update_cycle) > kDmMaxCount) {
+      total_count = 0;
+      for (uint32_t n = 0; n < symbols; ++n) total_count += (symbol_count[n] = (symbol_count[n] + 1) >> 1);
+    }
+    uint32_t sum = 0, s = 0;
+    const uint32_t scale = 0x80000000u / total_count;
+    if (table_size == 0) {
+      for (uint32_t k = 0; k < symbols; ++k) {
+        distribution[k] = (scale * sum) >> (31 - kDmLengthShift);
+        sum += symbol_count[k];
+      }
+    } else {
+      for (uint32_t k = 0; k < symbols; ++k) {
+        distribution[k] = (scale * sum) >> (31 - kDmLengthShift);
+        sum += symbol_count[k];
+        const uint32_t w = distribution[k] >> table_shift;
+        while (s < w) decoder_table[++s] = k - 1;
+      }
+      decoder_table[0] = 0;
+      while (s <= table_size) decoder_table[++s] = symbols - 1;
+    }
+    update_cycle = (5 * update_cycle) >> 2;
+    const uint32_t max_cycle = (symbols + 6) << 3;
+    if (update_cycle > max_cycle) update_cycle = max_cycle;
+    symbols_until_update = update_cycle;
+  }
+};
+
+struct ArithmeticDecoder {
+  ByteReader* in = nullptr;
+  uint32_t value = 0, length = 0;
+  void init(ByteReader* src) {
+    in = src;
+    length = kAcMaxLength;
+    value = (uint32_t)in->byte() << 24;
+    value |= (uint32_t)in->byte() << 16;
+    value |= (uint32_t)in->byte() << 8;
+    value |= (uint32_t)in->byte();
+  }
+  void renorm() {
+    do {
+      value = (value << 8) | in->byte();
+    } while ((length <<= 8) < kAcMinLength);
+  }
+  uint32_t bit(BitModel& m) {
+    const uint32_t x = m.bit_0_prob * (length >> kBmLengthShift);
+    const uint32_t sym = value >= x;
+    if (sym == 0) {
+      length = x;
+      ++m.bit_0_count;
+    } else {
+      value -= x;
+      length -= x;
+    }
+    if (length < kAcMinLength) renorm();
+    if (--m.bits_until_update == 0) m.update();
+    return sym;
+  }
+  uint32_t symbol(SymbolModel& m) {
+    uint32_t n, sym, x, y = length;
+    if (m.table_size) {
+      const uint32_t dv = value / (length >>= kDmLengthShift);
+      const uint32_t t = dv >> m.table_shift;
+      sym = m.decoder_table[t];
+      n = m.decoder_table[t + 1] + 1;
+      while (n > sym + 1) {
+        const uint32_t k = (sym + n) >> 1;
+        if (m.distribution[k] > dv) n = k; else sym = k;
+      }
+      x = m.distribution[sym] * length;
+      if (sym != m.last_symbol) y = m.distribution[sym + 1] * length;
+    } else {
+      x = sym = 0;
+      length >>= kDmLengthShift;
+      uint32_t k = (n = m.symbols) >> 1;
+      do {
+        const uint32_t z = length * m.distribution[k];
+        if (z > value) {
+          n = k;
+          y = z;
+        } else {
+          sym = k;
+          x = z;
+        }
+      } while ((k = (sym + n) >> 1) != sym);
+    }
+    value -= x;
+    length = y - x;
+    if (length < kAcMinLength) renorm();
+    ++m.symbol_count[sym];
+    if (--m.symbols_until_update == 0) m.update();
+    return sym;
+  }
+  uint32_t read_short() {
+    const uint32_t sym = value / (length >>= 16);
+    value -= length * sym;
+    if (length < kAcMinLength) renorm();
+    return sym;
+  }
+  uint32_t read_bits(uint32_t bits) {
+    if (bits > 19) {
+      const uint32_t lower = read_short();
+      return (read_bits(bits - 16) << 16) | lower;
+    }
+    const uint32_t sym = value / (length >>= bits);
+    value -= length * sym;
+    if (length < kAcMinLength) renorm();
+    return sym;
+  }
+};
+
+// ---- integer corrector coder -------------------------------------------------------------------------------------
+struct IntegerDecompressor {
+  ArithmeticDecoder* dec;
+  uint32_t k = 0, contexts, bits_high = 8, corr_bits, corr_range;
+  int32_t corr_min;
+  std::vector<std::unique_ptr<SymbolModel>> m_bits, m_corrector;  // m_corrector[0] unused: the 1-bit case is a BitModel
+  BitModel corrector0;
+  IntegerDecompressor(ArithmeticDecoder* d, uint32_t bits, uint32_t ctx) : dec(d), contexts(ctx) {
+    if (bits && bits < 32) {
+      corr_bits = bits;
+      corr_range = 1u << bits;
+      corr_min = -(int32_t)(corr_range / 2);
+    } else {
+      corr_bits = 32;
+      corr_range = 0;
+      corr_min = INT32_MIN;
+    }
+    for (uint32_t i = 0; i < contexts; ++i) m_bits.emplace_back(new SymbolModel(corr_bits + 1));
+    m_corrector.emplace_back(nullptr);
+    for (uint32_t i = 1; i <= corr_bits; ++i) m_corrector.emplace_back(new SymbolModel(i <= bits_high ? (1u << i) : (1u << bits_high)));
+    init();
+  }
+  void init() {
+    for (auto& m : m_bits) m->init();
+    corrector0.init();
+    for (uint32_t i = 1; i <= corr_bits; ++i) m_corrector[i]->init();
+  }
+  int32_t corrector(SymbolModel& bits_model) {
+    int32_t c;
+    k = dec->symbol(bits_model);
+    if (k) {
+      if (k < 32) {
+        if (k <= bits_high) {
+          c = (int32_t)dec->symbol(*m_corrector[k]);
+        } else {
+          const uint32_t k1 = k - bits_high;
+          c = (int32_t)dec->symbol(*m_corrector[k]);
+          const int32_t c1 = (int32_t)dec->read_bits(k1);
+          c = (int32_t)(((uint32_t)c << k1) | (uint32_t)c1);
+        }
+        if (c >= (1 << (k - 1))) c += 1; else c -= ((1 << k) - 1);
+      } else {
+        c = corr_min;
+      }
+    } else {
+      c = (int32_t)dec->bit(corrector0);
+    }
+    return c;
+  }
+  int32_t decompress(int32_t pred, uint32_t context) {
+    int32_t real = (int32_t)((uint32_t)pred + (uint32_t)corrector(*m_bits[context]));
+    if (real < 0) real = (int32_t)((uint32_t)real + corr_range);
+    else if ((uint32_t)real >= corr_range) real = (int32_t)((uint32_t)real - corr_range);
+    return real;
+  }
+};
+
+// ---- streaming median of the last five values ----------------------------------------------------------------------
+struct Median5 {
+  int32_t v[5];
+  bool high;
+  void init() {
+    v[0] = v[1] = v[2] = v[3] = v[4] = 0;
+    high = true;
+  }
+  int32_t get() const { return v[2]; }
+  void add(int32_t x) {
+    if (high) {
+      if (x < v[2]) {
+        v[4] = v[3];
+        v[3] = v[2];
+        if (x < v[0]) { v[2] = v[1]; v[1] = v[0]; v[0] = x; }
+        else if (x < v[1]) { v[2] = v[1]; v[1] = x; }
+        else v[2] = x;
+      } else {
+        if (x < v[3]) { v[4] = v[3]; v[3] = x; } else v[4] = x;
+        high = false;
+      }
+    } else {
+      if (v[2] < x) {
+        v[0] = v[1];
+        v[1] = v[2];
+        if (v[4] < x) { v[2] = v[3]; v[3] = v[4]; v[4] = x; }
+        else if (v[3] < x) { v[2] = v[3]; v[3] = x; }
+        else v[2] = x;
+      } else {
+        if (v[1] < x) { v[0] = v[1]; v[1] = x; } else v[0] = x;
+        high = true;
+      }
+    }
+  }
+};
+
+// return-number context tables of LASzip version 2 (indexed [number_of_returns][return_number])
+const uint8_t kReturnMap[8][8] = {{15, 14, 13, 12, 11, 10, 9, 8}, {14, 0, 1, 3, 6, 10, 10, 9},  {13, 1, 2, 4, 7, 11, 11, 10}, {12, 3, 4, 5, 8, 12, 12, 11},
+                                  {11, 6, 7, 8, 9, 13, 13, 12},   {10, 10, 11, 12, 13, 14, 14, 13}, {9, 10, 11, 12, 13, 14, 15, 14}, {8, 9, 10, 11, 12, 13, 14, 15}};
+const uint8_t kReturnLevel[8][8] = {{0, 1, 2, 3, 4, 5, 6, 7}, {1, 0, 1, 2, 3, 4, 5, 6}, {2, 1, 0, 1, 2, 3, 4, 5}, {3, 2, 1, 0, 1, 2, 3, 4},
+                                    {4, 3, 2, 1, 0, 1, 2, 3}, {5, 4, 3, 2, 1, 0, 1, 2}, {6, 5, 4, 3, 2, 1, 0, 1}, {7, 6, 5, 4, 3, 2, 1, 0}};
+
+inline int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd_u16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline void wr_i32(uint8_t* p, int32_t v) { memcpy(p, &v, 4); }
+inline void wr_u16(uint8_t* p, uint16_t v) { memcpy(p, &v, 2); }
+inline uint8_t u8_fold(int v) { return (uint8_t)(v & 0xFF); }
+inline int u8_clamp(int v) { return v <= 0 ? 0 : (v >= 255 ? 255 : v); }
+
+struct ItemReader {
+  virtual ~ItemReader() {}
+  virtual void init(const uint8_t* first) = 0;
+  virtual void read(uint8_t* out) = 0;
+};
+
+// POINT10 version 2: X, Y, Z, intensity, return byte, classification, scan angle rank, user data, point source id
+struct Point10V2 : ItemReader {
+  ArithmeticDecoder* dec;
+  uint8_t last[20];
+  uint16_t last_intensity[16];
+  Median5 mx[16], my[16];
+  int32_t last_height[8];
+  SymbolModel changed{64};
+  SymbolModel scan_angle[2] = {SymbolModel(256), SymbolModel(256)};
+  std::unique_ptr<SymbolModel> bit_byte[256], classification[256], user_data[256];
+  IntegerDecompressor ic_intensity, ic_source, ic_dx, ic_dy, ic_z;
+  explicit Point10V2(ArithmeticDecoder* d) : dec(d), ic_intensity(d, 16, 4), ic_source(d, 16, 1), ic_dx(d, 32, 2), ic_dy(d, 32, 22), ic_z(d, 32, 20) {}
+  void init(const uint8_t* first) override {
+    for (int i = 0; i < 16; ++i) {
+      mx[i].init();
+      my[i].init();
+      last_intensity[i] = 0;
+      last_height[i / 2] = 0;
+    }
+    changed.init();
+    ic_intensity.init();
+    scan_angle[0].init();
+    scan_angle[1].init();
+    ic_source.init();
+    for (int i = 0; i < 256; ++i) {
+      if (bit_byte[i]) bit_byte[i]->init();
+      if (classification[i]) classification[i]->init();
+      if (user_data[i]) user_data[i]->init();
+    }
+    ic_dx.init();
+    ic_dy.init();
+    ic_z.init();
+    memcpy(last, first, 20);
+    last[12] = last[13] = 0;  // the intensity context starts from zero
+  }
+  static SymbolModel& lazy(std::unique_ptr<SymbolModel>& m) {
+    if (!m) m.reset(new SymbolModel(256));
+    return *m;
+  }
+  void read(uint8_t* out) override {
+    uint32_t r, n, m, l;
+    const uint32_t ch = dec->symbol(changed);
+    if (ch) {
+      if (ch & 32) last[14] = (uint8_t)dec->symbol(lazy(bit_byte[last[14]]));
+      r = last[14] & 7;
+      n = (last[14] >> 3) & 7;
+      m = kReturnMap[n][r];
+      l = kReturnLevel[n][r];
+      if (ch & 16) {
+        const uint16_t v = (uint16_t)ic_intensity.decompress(last_intensity[m], m < 3 ? m : 3);
+        wr_u16(last + 12, v);
+        last_intensity[m] = v;
+      } else {
+        wr_u16(last + 12, last_intensity[m]);
+      }
+      if (ch & 8) last[15] = (uint8_t)dec->symbol(lazy(classification[last[15]]));
+      if (ch & 4) {
+        const int val = (int)dec->symbol(scan_angle[(last[14] >> 6) & 1]);
+        last[16] = u8_fold(val + last[16]);
+      }
+      if (ch & 2) last[17] = (uint8_t)dec->symbol(lazy(user_data[last[17]]));
+      if (ch & 1) wr_u16(last + 18, (uint16_t)ic_source.decompress(rd_u16(last + 18), 0));
+    } else {
+      r = last[14] & 7;
+      n = (last[14] >> 3) & 7;
+      m = kReturnMap[n][r];
+      l = kReturnLevel[n][r];
+    }
+    // x, y from the median of the last five differences of the same return type; z from the last height of its level
+    int32_t diff = ic_dx.decompress(mx[m].get(), n == 1);
+    wr_i32(last, (int32_t)((uint32_t)rd_i32(last) + (uint32_t)diff));
+    mx[m].add(diff);
+    uint32_t kb = ic_dx.k;
+    diff = ic_dy.decompress(my[m].get(), (n == 1) + (kb < 20 ? (kb & ~1u) : 20));
+    wr_i32(last + 4, (int32_t)((uint32_t)rd_i32(last + 4) + (uint32_t)diff));
+    my[m].add(diff);
+    kb = (ic_dx.k + ic_dy.k) / 2;
+    const int32_t zz = ic_z.decompress(last_height[l], (n == 1) + (kb < 18 ? (kb & ~1u) : 18));
+    wr_i32(last + 8, zz);
+    last_height[l] = zz;
+    memcpy(out, last, 20);
+  }
+};
+
+// RGB12 version 2: three 16-bit colours, coded byte-wise as differences; green and blue predicted from the red change
+struct Rgb12V2 : ItemReader {
+  ArithmeticDecoder* dec;
+  uint16_t last[3];
+  SymbolModel used{128};
+  SymbolModel d0{256}, d1{256}, d2{256}, d3{256}, d4{256}, d5{256};
+  explicit Rgb12V2(ArithmeticDecoder* d) : dec(d) {}
+  void init(const uint8_t* first) override {
+    used.init();
+    d0.init(); d1.init(); d2.init(); d3.init(); d4.init(); d5.init();
+    memcpy(last, first, 6);
+  }
+  void read(uint8_t* out) override {
+    uint16_t c[3];
+    int corr, diff;
+    const uint32_t sym = dec->symbol(used);
+    if (sym & 1) {
+      corr = (int)dec->symbol(d0);
+      c[0] = u8_fold(corr + (last[0] & 255));
+    } else {
+      c[0] = last[0] & 0xFF;
+    }
+    if (sym & 2) {
+      corr = (int)dec->symbol(d1);
+      c[0] |= (uint16_t)u8_fold(corr + (last[0] >> 8)) << 8;
+    } else {
+      c[0] |= last[0] & 0xFF00;
+    }
+    if (sym & 64) {
+      diff = (c[0] & 0xFF) - (last[0] & 0xFF);
+      if (sym & 4) {
+        corr = (int)dec->symbol(d2);
+        c[1] = u8_fold(corr + u8_clamp(diff + (last[1] & 255)));
+      } else {
+        c[1] = last[1] & 0xFF;
+      }
+      if (sym & 16) {
+        corr = (int)dec->symbol(d4);
+        diff = (diff + ((c[1] & 0xFF) - (last[1] & 0xFF))) / 2;
+        c[2] = u8_fold(corr + u8_clamp(diff + (last[2] & 255)));
+      } else {
+        c[2] = last[2] & 0xFF;
+      }
+      diff = (c[0] >> 8) - (last[0] >> 8);
+      if (sym & 8) {
+        corr = (int)dec->symbol(d3);
+        c[1] |= (uint16_t)u8_fold(corr + u8_clamp(diff + (last[1] >> 8))) << 8;
+      } else {
+        c[1] |= last[1] & 0xFF00;
+      }
+      if (sym & 32) {
+        corr = (int)dec->symbol(d5);
+        diff = (diff + ((c[1] >> 8) - (last[1] >> 8))) / 2;
+        c[2] |= (uint16_t)u8_fold(corr + u8_clamp(diff + (last[2] >> 8))) << 8;
+      } else {
+        c[2] |= last[2] & 0xFF00;
+      }
+    } else {
+      c[1] = c[0];
+      c[2] = c[0];
+    }
+    memcpy(last, c, 6);
+    memcpy(out, c, 6);
+  }
+};
+}  // namespace
+
+// Decode `npoints` records of `point_size` bytes into records_out_host.  items_host: nitems triples (type, size,
+// version) from the laszip VLR (user id "laszip encoded", record id 22204).  Everything is host memory.
+extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64_t offset_to_points, int64_t npoints, int32_t point_size,
+                               int32_t compressor, uint32_t chunk_size, const uint16_t* items_host, int32_t nitems, uint8_t* records_out_host) {
+  if (!file_host || !items_host || !records_out_host || file_bytes < 0 || npoints < 0 || nitems < 1)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: bad arguments");
+  if (compressor != 2) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip compressor %d is not supported (only 2 = pointwise chunked)", compressor);
+  int total = 0;
+  for (int i = 0; i < nitems; ++i) {
+    const int type = items_host[3 * i], size = items_host[3 * i + 1], version = items_host[3 * i + 2];
+    const bool ok = (type == 6 && size == 20 && version == 2) || (type == 8 && size == 6 && version == 2);
+    if (!ok) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip item type %d (size %d, version %d) is not supported (POINT10 v2 and RGB12 v2 are)", type, size, version);
+    total += size;
+  }
+  if (total != point_size) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: item sizes (%d) do not add up to the point size (%d)", total, point_size);
+  if (npoints == 0) return VAPC_OK;
+  if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: variable chunk sizes are not supported");
+  if (offset_to_points + 8 > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: truncated file");
+  int64_t table_pos;
+  memcpy(&table_pos, file_host + offset_to_points, 8);
+  if (table_pos == -1) memcpy(&table_pos, file_host + file_bytes - 8, 8);  // written at the end when the stream was not seekable
+  const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
+  std::vector<int64_t> chunk_start((size_t)nchunks + 1);
+  chunk_start[0] = offset_to_points + 8;
+  if (nchunks > 1) {
+    // chunk table: u32 version, u32 count, then the arithmetic-coded byte sizes of the chunks
+    if (table_pos < chunk_start[0] || table_pos + 8 > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk table missing");
+    uint32_t version, count;
+    memcpy(&version, file_host + table_pos, 4);
+    memcpy(&count, file_host + table_pos + 4, 4);
+    if (version != 0 || (int64_t)count < nchunks) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: unexpected chunk table (version %u, %u chunks)", version, count);
+    ByteReader br{file_host + table_pos + 8, file_host + file_bytes};
+    ArithmeticDecoder dec;
+    dec.init(&br);
+    IntegerDecompressor ic(&dec, 32, 2);
+    int32_t prev = 0;
+    for (int64_t i = 0; i < nchunks; ++i) {
+      prev = ic.decompress(prev, 1);
+      chunk_start[(size_t)i + 1] = chunk_start[(size_t)i] + (uint32_t)prev;
+    }
+    if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk table truncated");
+  }
+  ArithmeticDecoder dec;
+  std::vector<std::unique_ptr<ItemReader>> readers;
+  std::vector<int> sizes;
+  for (int i = 0; i < nitems; ++i) {
+    if (items_host[3 * i] == 6) readers.emplace_back(new Point10V2(&dec));
+    else readers.emplace_back(new Rgb12V2(&dec));
+    sizes.push_back(items_host[3 * i + 1]);
+  }
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t first = c * (int64_t)chunk_size;
+    const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
+    const int64_t begin = chunk_start[(size_t)c];
+    const int64_t limit = nchunks > 1 && c + 1 < nchunks ? chunk_start[(size_t)c + 1] : file_bytes;
+    if (begin + point_size > file_bytes || limit > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld outside the file", (long long)c);
+    uint8_t* out = records_out_host + first * point_size;
+    memcpy(out, file_host + begin, (size_t)point_size);  // the first point of a chunk is stored raw
+    int off = 0;
+    for (size_t i = 0; i < readers.size(); ++i) {
+      readers[i]->init(out + off);
+      off += sizes[i];
+    }
+    if (count > 1) {
+      ByteReader br{file_host + begin + point_size, file_host + limit};
+      dec.init(&br);
+      for (int64_t p = 1; p < count; ++p) {
+        uint8_t* rec = out + p * point_size;
+        off = 0;
+        for (size_t i = 0; i < readers.size(); ++i) {
+          readers[i]->read(rec + off);
+          off += sizes[i];
+        }
+      }
+      if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld is truncated or corrupt", (long long)c);
+    }
+  }
+  return VAPC_OK;
+}

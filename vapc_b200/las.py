@@ -10,7 +10,10 @@ needs from it for plain `.las` files and mirrors laspy's conventions:
 * writing LAS 1.4 point format 7 with offsets = coordinate minima and scale 2.5e-4 by default, extra
   dimensions as float32 (`datahandler.py:99-165`).
 
-LAZ (LASzip-compressed) files need `laspy` with a LAZ backend; without it a clear error is raised.
+LAZ: files compressed with LASzip's "pointwise chunked" scheme whose items are POINT10 v2 (+ RGB12 v2) — point formats
+0 and 2, the layout of the reference's `vapc_in.laz` / `small_mask.laz` fixtures — are decoded by the library's host
+entry point `vapc_laz_decode` (vapc_b200/csrc/laz.cu).  Other LAZ layouts (GPS time, LAS 1.4 layered items) raise
+NotImplementedError naming the item; `laspy` with a LAZ backend reads them when it is installed.
 """
 from __future__ import annotations
 
@@ -77,6 +80,7 @@ class LasHeader:
         self.system_identifier = ""
         self.extra_dims: List[Tuple[str, str]] = []  # (name, numpy dtype string)
         self.compressed = False
+        self.laszip = None  # dict(compressor, chunk_size, items=[(type, size, version), ...]) of a LAZ file
 
 
 def read_header(buf: bytes) -> LasHeader:
@@ -107,6 +111,9 @@ def read_header(buf: bytes) -> LasHeader:
         user = buf[pos + 2:pos + 18].split(b"\0")[0].decode("ascii", "replace")
         rec_id, length = struct.unpack_from("<HH", buf, pos + 18)
         body = buf[pos + 54:pos + 54 + length]
+        if rec_id == 22204 and user.startswith("laszip") and len(body) >= 34:
+            comp, _coder, _vmaj, _vmin, _vrev, _opt, chunk, _nse, _ose, nitems = struct.unpack_from("<HHBBHIIqqH", body, 0)
+            h.laszip = {"compressor": comp, "chunk_size": chunk, "items": [struct.unpack_from("<HHH", body, 34 + 6 * k) for k in range(nitems)]}
         if user == "LASF_Spec" and rec_id == 4:
             for k in range(len(body) // 192):
                 e = body[k * 192:(k + 1) * 192]
@@ -133,19 +140,41 @@ def record_dtype(h: LasHeader) -> np.dtype:
     return np.dtype(fields)
 
 
+def _decode_laz(buf: bytes, h: LasHeader) -> np.ndarray:
+    """LASzip-compressed point records -> uint8 [npoints * point_size] through the library's host decoder."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    if h.laszip is None:
+        raise ValueError("the point format byte says LASzip-compressed, but the file has no laszip VLR")
+    items = np.array(h.laszip["items"], dtype=np.uint16).reshape(-1)
+    n = int(h.point_count)
+    out = np.empty(n * h.point_size, dtype=np.uint8)
+    src = np.frombuffer(buf, dtype=np.uint8)
+    rc = L.raw("vapc_laz_decode")(src.ctypes.data_as(C.c_void_p), len(buf), int(h.offset_to_points), n, int(h.point_size), int(h.laszip["compressor"]),
+                                  int(h.laszip["chunk_size"]), items.ctypes.data_as(C.c_void_p), len(h.laszip["items"]), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        msg = L.last_error()
+        if "not supported" in msg:
+            raise NotImplementedError(msg + "; install laspy with a LAZ backend (lazrs / laszip) for this file")
+        raise ValueError(msg)
+    return out
+
+
 def read_las(path: str):
     """Returns (header, dict of numpy columns keyed by laspy dimension names; 'x', 'y', 'z' are the scaled fp64
     coordinates)."""
     with open(path, "rb") as f:
         buf = f.read()
     h = read_header(buf)
-    if h.compressed or path.lower().endswith(".laz"):
-        raise NotImplementedError("LAZ-compressed input needs laspy with a LAZ backend (lazrs / laszip), which is not installed; "
-                                  "decompress to .las first")
     if h.point_format not in POINT_FORMATS:
         raise ValueError(f"unsupported point format {h.point_format}")
     dt = record_dtype(h)
-    rec = np.frombuffer(buf, dtype=dt, count=int(h.point_count), offset=h.offset_to_points)
+    if h.compressed:
+        rec = _decode_laz(buf, h).view(dt).reshape(-1)
+    else:  # (an uncompressed file under a .laz name is read as what it is)
+        rec = np.frombuffer(buf, dtype=dt, count=int(h.point_count), offset=h.offset_to_points)
     cols: Dict[str, np.ndarray] = {}
     subs = _sub_fields(h.point_format)
     for name in dt.names:
