@@ -312,6 +312,17 @@ VAPC_API int vapc_merge_partials(const void* keys_sorted, const uint32_t* order,
  * row-major records of 11 x 8 bytes {key (uint64), count (int64), mean[3], M2[6]}.  vapc_merge_partial_rows
  * merges like vapc_merge_partials over two sources: order values < n_local address this rank's own rows
  * local_first + value of the SOA columns (never copied), the others the received `rows`[value - n_local]. */
+/* Exchange planning on the device.  hist_all = the all-gathered per-rank histograms [world][2^hist_bits] of
+ * vapc_global_keys.  out (int64 [world * world + world - 1]) = every rank's send counts to every destination (row r
+ * = rank r) followed by the world - 1 key thresholds: destination g owns keys in [t_g, t_{g+1}).  Thresholds lie on
+ * histogram-bin boundaries and balance the global number of partial rows per range.  vapc_merge_keys gathers the sort keys
+ * of the rows a rank then merges: its own rows [own_first, own_first + n_own) followed by the received rows' keys. */
+VAPC_API int vapc_plan_exchange(const uint32_t* hist_all, int32_t world, int32_t hist_bits, int32_t global_bits,
+                       int64_t* out, void* stream);
+VAPC_API int vapc_merge_keys(const uint64_t* global_keys, int64_t own_first, int64_t n_own, const double* rows,
+                    int64_t n_in, int32_t key_bytes, void* keys_out, void* stream);
+VAPC_API int vapc_selftest_plan_exchange_host(const uint32_t* hist_all_host, int32_t world, int32_t nbins,
+                                     int32_t shift, int64_t* out_host);
 VAPC_API int vapc_global_keys(const void* voxel_keys, int64_t nvoxels, const vapc_grid_t* local_grid_host,
                      const vapc_grid_t* global_grid_host, int32_t hist_bits, uint64_t* keys_out,
                      uint32_t* hist, void* stream);

@@ -157,3 +157,25 @@ def test_device_side_planning_matches_host_planning():
             keys = np.sort(rng.integers(0, 1 << min(total_bits, 62), 5000))
             assert D.destination_counts(torch.from_numpy(keys), t_dev).tolist() == D.partition_counts(torch.from_numpy(keys), t_host)
     assert D.plan_splitters_tensor(torch.zeros(16, dtype=torch.int64), 4, 4, 4).tolist() == D.plan_splitters(np.zeros(16, np.int64), 4, 4, 4)
+
+
+def test_plan_exchange_arithmetic_matches_host_planner():
+    """The planning kernel's arithmetic (host mirror in the library) == plan_splitters + partition of every rank's rows."""
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(4)
+    for world in (1, 2, 3, 8, 16):
+        for hb, total_bits in ((4, 4), (10, 24), (16, 27), (16, 40)):
+            nb = 1 << hb
+            hist_all = rng.integers(0, 40, (world, nb)).astype(np.uint32)
+            hist_all[rng.random((world, nb)) < 0.6] = 0
+            if world > 2:
+                hist_all[1] = 0  # a rank without rows
+            shift = max(total_bits - hb, 0)
+            out = np.zeros(world * world + world - 1, dtype=np.int64)
+            assert L.raw("vapc_selftest_plan_exchange_host")(hist_all.ctypes.data, world, nb, shift, out.ctypes.data) == 0
+            thresholds = D.plan_splitters(hist_all.sum(0), world, total_bits, hb)
+            assert out[world * world:].tolist() == thresholds
+            edges = [0] + [t >> shift for t in thresholds] + [nb]
+            for r in range(world):
+                assert out[r * world:(r + 1) * world].tolist() == [int(hist_all[r, a:b].sum()) for a, b in zip(edges[:-1], edges[1:])]

@@ -354,6 +354,35 @@ def test_lexsort_unique_rows_matches_pandas(E):
         np.testing.assert_array_equal(rows, ref["row"].to_numpy().astype(np.int64))
 
 
+def test_plan_exchange_kernel_matches_host_mirror(E):
+    """Multi-GPU exchange planning kernel (splitters + send-count matrix from the all-gathered histograms) == its host mirror
+    (which tests/test_dist_cpu.py checks against the pure-Python planner)."""
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(8)
+    for world, hb, total_bits in ((1, 16, 24), (2, 16, 24), (3, 10, 10), (8, 16, 27), (8, 4, 4), (64, 16, 40), (5, 12, 63)):
+        nb = 1 << hb
+        hist = rng.integers(0, 1000, (world, nb)).astype(np.uint32)
+        hist[rng.random((world, nb)) < 0.5] = 0
+        if world > 2:
+            hist[1] = 0
+            hist[2, : nb // 2] = 0  # a rank whose rows all lie in the upper half of the key space
+        ref = np.zeros(world * world + world - 1, dtype=np.int64)
+        assert L.raw("vapc_selftest_plan_exchange_host")(hist.ctypes.data, world, nb, max(total_bits - hb, 0), ref.ctypes.data) == 0
+        out = torch.empty(world * world + world - 1, dtype=torch.int64, device="cuda")
+        L.call("vapc_plan_exchange", E._ptr(torch.from_numpy(hist.view(np.int32)).cuda()), world, hb, total_bits, E._ptr(out), E._stream())
+        np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    # merge keys: own slice + first word of every received row
+    gk = torch.arange(100, 200, dtype=torch.int64, device="cuda")
+    rows = torch.zeros((7, 11), dtype=torch.float64, device="cuda")
+    rows.view(torch.int64)[:, 0] = torch.arange(7, device="cuda") + (1 << 33)
+    for kb, dt in ((4, torch.int32), (8, torch.int64)):
+        out = torch.empty(30 + 7, dtype=dt, device="cuda")
+        L.call("vapc_merge_keys", E._ptr(gk), 10, 30, E._ptr(rows), 7, kb, E._ptr(out), E._stream())
+        expect = torch.cat([gk[10:40], torch.arange(7, device="cuda") + (1 << 33)])
+        assert torch.equal(out.to(torch.int64) & (0xFFFFFFFF if kb == 4 else -1), expect & (0xFFFFFFFF if kb == 4 else -1))
+
+
 def test_reproducible_bitwise(E):
     """No atomics in the reductions: two runs give bit-identical tables — and so does the path that keeps the
     records in input order and sorts all key bits (bucketed=False)."""

@@ -110,6 +110,9 @@ SIGNATURES = {
     "vapc_join_sorted_keys": (C.c_int, [P, I64, P, I64, P, P, P]),
     "vapc_mahalanobis": (C.c_int, [P, P, I64, P, P, I64, P, P, I64, F64, P, P, P, P, P, P, P]),
     "vapc_merge_partials": (C.c_int, [P, P, I64, I32, P, P, P, I64, I64, P, P, P, P, P, SZ, P]),
+    "vapc_plan_exchange": (C.c_int, [P, I32, I32, I32, P, P]),
+    "vapc_merge_keys": (C.c_int, [P, I64, I64, P, I64, I32, P, P]),
+    "vapc_selftest_plan_exchange_host": (C.c_int, [P, I32, I32, I32, P]),
     "vapc_global_keys": (C.c_int, [P, I64, GP, GP, I32, P, P, P]),
     "vapc_pack_partial_rows": (C.c_int, [P, P, P, P, I64, I64, I64, P, P]),
     "vapc_merge_partial_rows": (C.c_int, [P, P, I64, I32, P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, SZ, P]),

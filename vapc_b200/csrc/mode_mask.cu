@@ -2,6 +2,9 @@
 // Reference: vapc.py:407-433 (mode, mode_count), :594-598 (MultiIndex.isin), :495-541 (voxel buffer).
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -351,5 +354,184 @@ extern "C" int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes
   else
     return vapc_set_error(VAPC_E_INVALID, "vapc_key_histogram: key_bytes must be 4 or 8");
   VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+// ---- multi-GPU exchange planning on the device --------------------------------------------------------------------------
+// hist_all[r][b]: rank r's histogram of the leading key bits of its partial voxel rows (all-gathered).  One CTA finds the
+// world - 1 splitters that balance the GLOBAL number of rows per key range — b_g = (first bin whose cumulative count reaches
+// total * g / world) + 1, exactly vapc_b200.dist.plan_splitters — and, because splitters lie on bin boundaries, every rank's
+// send counts to every destination as sums over bin ranges.  out = [matrix world x world (row r = rank r's send counts)]
+// [thresholds world - 1] as int64, so that the host learns everything with one copy.
+namespace {
+constexpr int kPlanThreads = 1024;
+constexpr int kMaxWorld = 64;
+// block-wide inclusive scan of one u64 per thread; returns the inclusive prefix, *total = block sum.  Ends with a barrier.
+__device__ __forceinline__ unsigned long long plan_block_scan(unsigned long long v, unsigned long long* warp_sums, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = warp_sums[lane];
+    unsigned long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  const unsigned long long res = inc + warp_sums[warp];
+  *total = warp_sums[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(kPlanThreads) plan_exchange_kernel(const uint32_t* __restrict__ hist_all, int world, int nbins, int shift,
+                                                                     long long* __restrict__ out) {
+  __shared__ unsigned long long warp_sums[33];
+  __shared__ unsigned long long matrix[kMaxWorld * kMaxWorld];
+  __shared__ int edges[kMaxWorld + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < world * world; i += kPlanThreads) matrix[i] = 0;
+  if (tid == 0) { edges[0] = 0; edges[world] = nbins; }
+  // pass 1: total number of rows (bins are visited 1024 at a time, thread t takes bin round * 1024 + t: coalesced)
+  unsigned long long mine = 0;
+  for (int b = tid; b < nbins; b += kPlanThreads)
+    for (int r = 0; r < world; ++r) mine += hist_all[(int64_t)r * nbins + b];
+  unsigned long long total;
+  plan_block_scan(mine, warp_sums, &total);
+  // pass 2: running cumulative count; the thread whose bin is the first to reach a target sets that splitter
+  unsigned long long carry = 0;
+  for (int b0 = 0; b0 < nbins; b0 += kPlanThreads) {
+    const int b = b0 + tid;
+    unsigned long long gb = 0;
+    if (b < nbins)
+      for (int r = 0; r < world; ++r) gb += hist_all[(int64_t)r * nbins + b];
+    unsigned long long round_total;
+    const unsigned long long cum = carry + plan_block_scan(gb, warp_sums, &round_total);
+    if (b < nbins) {
+      const unsigned long long before = cum - gb;
+      for (int g = 1; g < world; ++g) {
+        const double target = (double)total * (double)g / (double)world;
+        if ((double)cum >= target && (b == 0 || !((double)before >= target))) edges[g] = min(b + 1, nbins);
+      }
+    }
+    carry += round_total;
+  }
+  __syncthreads();
+  if (tid == 0)  // monotone (cummax), as the host planner does
+    for (int g = 1; g < world; ++g) edges[g] = max(edges[g], edges[g - 1]);
+  __syncthreads();
+  // pass 3: send counts = every rank's rows in the bins of every destination.  A warp walks a contiguous range of bins 32 at
+  // a time (coalesced); the destination changes at most world - 1 times over all bins, so lanes accumulate in a register and
+  // only flush (warp reduction + one shared-memory atomic) when it does.
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = kPlanThreads / 32;
+    const int per_warp = ((nbins + nwarps - 1) / nwarps + 31) / 32 * 32;
+    const int w0 = warp * per_warp, w1 = min(nbins, w0 + per_warp);
+    for (int r = 0; r < world; ++r) {
+      const uint32_t* h = hist_all + (int64_t)r * nbins;
+      int g = 0;
+      unsigned long long acc = 0;
+      for (int s0 = w0; s0 < w1; s0 += 32) {
+        const int b = s0 + lane;
+        const unsigned long long c = b < w1 ? h[b] : 0u;
+        const int last = min(s0 + 31, w1 - 1);
+        while (s0 >= edges[g + 1]) {  // the whole step lies beyond destination g: flush and advance (warp-uniform)
+          unsigned long long t = acc;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0 && t) atomicAdd(&matrix[r * world + g], t);
+          acc = 0;
+          ++g;
+        }
+        if (last < edges[g + 1]) {
+          acc += c;  // every bin of the step belongs to g
+        } else if (b < w1 && c) {  // a step that straddles a splitter: per-lane destination, direct atomics
+          int gg = g;
+          while (b >= edges[gg + 1]) ++gg;
+          atomicAdd(&matrix[r * world + gg], c);
+        }
+      }
+      unsigned long long t = acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0 && t) atomicAdd(&matrix[r * world + g], t);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < world * world; i += kPlanThreads) out[i] = (long long)matrix[i];
+  for (int g = tid + 1; g < world; g += kPlanThreads) out[world * world + g - 1] = (long long)edges[g] << shift;
+}
+
+// keys of the rows a rank merges: its own rows [own_first, own_first + n_own) of the global-key array, then the keys of the
+// received exchange rows (first word of each 11-word row), as 32- or 64-bit sort keys
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) merge_keys_kernel(const unsigned long long* __restrict__ gkeys, int64_t own_first, int64_t n_own,
+                                                              const double* __restrict__ rows, int64_t n_in, KeyT* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, n = n_own + n_in;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (KeyT)(i < n_own ? gkeys[own_first + i] : (unsigned long long)__double_as_longlong(rows[(i - n_own) * 11]));
+}
+}  // namespace
+
+extern "C" int vapc_plan_exchange(const uint32_t* hist_all, int32_t world, int32_t hist_bits, int32_t global_bits, int64_t* out, void* stream) {
+  if (!hist_all || !out || world < 1 || world > kMaxWorld || hist_bits < 1 || hist_bits > 24)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_plan_exchange: bad arguments (1 <= world <= %d)", kMaxWorld);
+  const int shift = global_bits > hist_bits ? global_bits - hist_bits : 0;
+  VAPC_LAUNCH(plan_exchange_kernel, 1, kPlanThreads, 0, as_stream(stream), hist_all, world, 1 << hist_bits, shift, reinterpret_cast<long long*>(out));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_merge_keys(const uint64_t* global_keys, int64_t own_first, int64_t n_own, const double* rows, int64_t n_in, int32_t key_bytes,
+                               void* keys_out, void* stream) {
+  if (n_own < 0 || n_in < 0 || own_first < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_keys: bad arguments");
+  if (n_own + n_in == 0) return VAPC_OK;
+  if (!keys_out || (n_own && !global_keys) || (n_in && !rows)) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_keys: null buffer");
+  const unsigned long long* gk = reinterpret_cast<const unsigned long long*>(global_keys);
+  if (key_bytes == 4)
+    VAPC_LAUNCH(merge_keys_kernel<uint32_t>, grid_for(n_own + n_in), kThreads, 0, as_stream(stream), gk, own_first, n_own, rows, n_in, static_cast<uint32_t*>(keys_out));
+  else if (key_bytes == 8)
+    VAPC_LAUNCH(merge_keys_kernel<unsigned long long>, grid_for(n_own + n_in), kThreads, 0, as_stream(stream), gk, own_first, n_own, rows, n_in,
+                static_cast<unsigned long long*>(keys_out));
+  else
+    return vapc_set_error(VAPC_E_INVALID, "vapc_merge_keys: key_bytes must be 4 or 8");
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+// host mirror of the planning kernel's arithmetic for the CPU tests (no GPU needed)
+extern "C" int vapc_selftest_plan_exchange_host(const uint32_t* hist_all_host, int32_t world, int32_t nbins, int32_t shift, int64_t* out_host) {
+  std::vector<unsigned long long> cum(nbins);
+  unsigned long long run = 0;
+  for (int b = 0; b < nbins; ++b) {
+    for (int r = 0; r < world; ++r) run += hist_all_host[(int64_t)r * nbins + b];
+    cum[b] = run;
+  }
+  std::vector<int> edges(world + 1, 0);
+  edges[world] = nbins;
+  for (int g = 1; g < world; ++g) {
+    const double target = (double)run * (double)g / (double)world;
+    int b = 0;
+    while (b < nbins && !((double)cum[b] >= target)) ++b;
+    edges[g] = std::max(std::min(b + 1, nbins), edges[g - 1]);
+  }
+  for (int r = 0; r < world; ++r)
+    for (int g = 0; g < world; ++g) {
+      unsigned long long acc = 0;
+      for (int b = edges[g]; b < edges[g + 1]; ++b) acc += hist_all_host[(int64_t)r * nbins + b];
+      out_host[r * world + g] = (long long)acc;
+    }
+  for (int g = 1; g < world; ++g) out_host[world * world + g - 1] = (long long)edges[g] << shift;
   return VAPC_OK;
 }

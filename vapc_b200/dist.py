@@ -9,8 +9,8 @@ file).  The path has exactly one real exchange step, as BASELINE.json's north_st
      relative to its own lowest voxel: fewer key bits and radix passes than the global layout): keys + records in
      bucket order -> segmented radix sort -> segmentation -> moments, all local, no communication;
   3. the sorted local voxel keys are re-expressed in the global layout (same lexicographic order) and the key space
-     is cut into `world` ranges balancing the number of partial rows: all-reduce(sum) of a 2^16-bin histogram of
-     the keys -> splitters -> destinations, all planned on the device; one all-gather of the send counts;
+     is cut into `world` ranges balancing the number of partial rows: ONE all-gather of the ranks' 2^16-bin key
+     histograms, from which a single kernel derives the splitters and the complete send-count matrix;
   4. ONE all-to-all(v) moves the rows that leave their rank, packed row-major, to the owner of their key range (the
      local table is sorted, so each destination's rows are a contiguous slice); the rows a rank owns itself are
      never copied;
@@ -239,13 +239,13 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     gkeys = torch.empty(v, dtype=torch.int64, device=dev)
     hist = torch.empty(1 << hb, dtype=torch.int32, device=dev)
     L.call("vapc_global_keys", E._ptr(local.voxel_keys), v, C.byref(lg), C.byref(g), hb, E._ptr(gkeys), E._ptr(hist), E._stream())
-    hist64 = hist.to(torch.int64)
-    dist.all_reduce(hist64, op=dist.ReduceOp.SUM, group=group)
-    thresholds = plan_splitters_tensor(hist64, world, g.total_bits, hb)
-    send = destination_counts(gkeys, thresholds)
-    matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(matrix, send, group=group)
-    host = torch.cat([matrix, thresholds]).cpu()  # one synchronisation for everything the host has to know
+    # ONE collective for the planning: with everybody's histogram every rank derives the splitters (global sum) AND the
+    # complete send-count matrix (splitters lie on bin boundaries) in one small kernel; one copy tells the host
+    hist_all = torch.empty(world << hb, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(hist_all, hist, group=group)
+    plan = torch.empty(world * world + world - 1, dtype=torch.int64, device=dev)
+    L.call("vapc_plan_exchange", E._ptr(hist_all), world, hb, g.total_bits, E._ptr(plan), E._stream())
+    host = plan.cpu()
     matrix_h = host[: world * world].view(world, world)
     send_counts = matrix_h[rank].tolist()
     recv_counts = matrix_h[:, rank].tolist()
@@ -265,10 +265,9 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     in_rows = torch.empty((n_in, 11), dtype=torch.float64, device=dev)
     dist.all_to_all_single(in_rows, out_rows, output_split_sizes=recv_remote, input_split_sizes=send_remote, group=group)
     # merge: own rows (sources 0 .. n_own-1, read in place from the local table) + received rows (sources n_own ..)
-    keys = torch.cat([gkeys[lo:hi], in_rows.view(torch.int64)[:, 0]])
-    if g.key_bytes == 4:
-        keys = keys.to(torch.int32)
-    r = keys.numel()
+    r = n_own + n_in
+    keys = torch.empty(r, dtype=torch.int32 if g.key_bytes == 4 else torch.int64, device=dev)
+    L.call("vapc_merge_keys", E._ptr(gkeys), lo, n_own, E._ptr(in_rows), n_in, g.key_bytes, E._ptr(keys), E._stream())
     ks, order = E.sort_pairs(keys, g.total_bits)
     ws_bytes = L.raw("vapc_segment_workspace_bytes")(r)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
