@@ -87,27 +87,28 @@ __global__ void bucket_start_kernel(const uint32_t* __restrict__ digit_base, int
   if (t == 0) bucket_start[nb] = n;
 }
 
-// 32-bit keys ride in the upper half of the record's index slot while the tile is reordered (and stay there in
-// memory: readers only look at the lower half); 64-bit keys get their own array.
-template <typename KeyT> struct KeySlots { KeyT keys[kTile]; };
-template <> struct KeySlots<uint32_t> {};
-
+// The tile's records reordered by bucket, as columns: coordinates, key and the 16-bit input slot of every point (64-bit
+// shared-memory stores per column measured 4 % faster than one 32-byte record store; a fourth CTA per SM — 55 KB each —
+// needs 64 registers per thread and loses more to spills than it gains).
 template <typename KeyT>
 struct BucketSmem {
   RankSmem r;
-  KeySlots<KeyT> k;
-  alignas(32) union {
+  alignas(16) union {
     MaskBuffers masks;
-    double4 rec[kTile];  // the tile's records reordered by bucket
+    struct {
+      double x[kTile], y[kTile], z[kTile];
+      KeyT key[kTile];
+      unsigned short slot[kTile];
+    } rec;
   } u;
 };
 
 template <typename KeyT, typename LookT>
-__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 2) bucket_scatter_kernel(
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) bucket_scatter_kernel(
     const KeyT* __restrict__ keys, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n, int shift,
     unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyT* __restrict__ keys_b,
     double4* __restrict__ rec_b) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   BucketSmem<KeyT>& sm = *reinterpret_cast<BucketSmem<KeyT>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) sm.r.tile = atomicAdd(ticket, 1u);
@@ -117,9 +118,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
   const int64_t tile_base = (int64_t)tile * kTile;
   const bool full = tile_base + kTile <= n;
 
-  // warp-striped: warp w owns points [w*256, (w+1)*256) of the tile, lane l takes point k*32 + l in step k.
+  // warp-striped: warp w owns points [w*32*kItems, (w+1)*32*kItems) of the tile, lane l takes point k*32 + l in step k.
   // Slots past the end of the input (last tile) hold all-ones keys: highest bucket, last ranks, never written.
-  const int64_t wbase = tile_base + warp * (32 * kItems) + lane;
+  const int slot0 = warp * (32 * kItems) + lane;
+  const int64_t wbase = tile_base + slot0;
   KeyT key[kItems];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys + wbase + k * 32) : (KeyT)~(KeyT)0;
@@ -148,23 +150,26 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
-    unsigned long long w = (uint32_t)(wbase + k * 32);
-    if (sizeof(KeyT) == 4) w |= (unsigned long long)key[k] << 32;
-    else reinterpret_cast<KeyT*>(&sm.k)[pos] = key[k];
-    sm.u.rec[pos] = make_double4(px[k], py[k], pz[k], __longlong_as_double((long long)w));
+    sm.u.rec.x[pos] = px[k];
+    sm.u.rec.y[pos] = py[k];
+    sm.u.rec.z[pos] = pz[k];
+    sm.u.rec.key[pos] = key[k];
+    sm.u.rec.slot[pos] = (unsigned short)(slot0 + k * 32);
   }
 
   const LookT excl = look_back<LookT>(mine, (int64_t)tile, run);
   sm.r.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
   __syncthreads();
 
+  // 32-bit keys also ride in the upper half of the record's index slot (readers only look at the lower half)
   const int tile_n = (int)min((int64_t)kTile, n - tile_base);
-#pragma unroll 4
+#pragma unroll 3
   for (int p = tid; p < tile_n; p += kThreads) {
-    const double4 r = sm.u.rec[p];
-    const KeyT k = sizeof(KeyT) == 4 ? (KeyT)((unsigned long long)__double_as_longlong(r.w) >> 32) : reinterpret_cast<const KeyT*>(&sm.k)[p];
+    const KeyT k = sm.u.rec.key[p];
+    unsigned long long w = (uint32_t)tile_base + (uint32_t)sm.u.rec.slot[p];
+    if (sizeof(KeyT) == 4) w |= (unsigned long long)k << 32;
     const unsigned dst = (unsigned)p + sm.r.delta[bucket_of(k, shift, mask)];
-    st_record(rec_b + dst, r.x, r.y, r.z, r.w);
+    st_record(rec_b + dst, sm.u.rec.x[p], sm.u.rec.y[p], sm.u.rec.z[p], __longlong_as_double((long long)w));
     keys_b[dst] = k;
   }
 }

@@ -95,12 +95,20 @@ __global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __rest
       base = t * kTile;
       end = min(n, base + kTile);
     }
-#pragma unroll 4
-    for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
-      const KeyT k = __ldcs(keys + i);
-      for (int p = 0; p < passes; ++p) {
-        const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
-        atomicAdd(&sh[p][digit_of(k, begin_bit + p * kRadixBits, m)], 1u);
+    // a tile is at most kItems keys per thread: all loads of the tile are issued before the first atomic
+    KeyT k[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int64_t i = base + j * kThreads + threadIdx.x;
+      k[j] = i < end ? __ldcs(keys + i) : (KeyT)0;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      if (base + j * kThreads + threadIdx.x < end) {
+        for (int p = 0; p < passes; ++p) {
+          const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
+          atomicAdd(&sh[p][digit_of(k[j], begin_bit + p * kRadixBits, m)], 1u);
+        }
       }
     }
   }
