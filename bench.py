@@ -296,6 +296,7 @@ def main():
         cloud, st = step_device()
     torch.cuda.synchronize()
     nvox = cloud.nvoxels
+    exchange_kind = getattr(cloud, "exchange", None)
     key_bytes = cloud.grid.key_bytes
     total_bits = cloud.grid.total_bits
     passes = (total_bits + 7) // 8
@@ -446,7 +447,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes),
+            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes,
+                                                 **({"exchange": exchange_kind} if world > 1 else {})),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": per_kernel, "abi_calls": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
             "gaps_between_calls_ms": gaps,
