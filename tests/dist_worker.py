@@ -24,11 +24,12 @@ def main():
     n, vs, origin = 600_000, 0.2, [0.5, -1.0, 0.25]
     pts = np.round(np.concatenate([rng.uniform([-20, -5, 0], [60, 45, 6], (n // 2, 3)),
                                    rng.normal([20, 20, 3], [3, 3, 0.5], (n - n // 2, 3))]), 3)
-    for mode in ("coherent", "shuffled"):
+    for mode, exchange in (("coherent", "peer"), ("shuffled", "peer"), ("coherent", "nccl")):
         order = np.argsort(pts[:, 0], kind="stable") if mode == "coherent" else rng.permutation(n)
         chunk = pts[order[rank * n // world:(rank + 1) * n // world]]
         x, y, z = (torch.from_numpy(np.ascontiguousarray(chunk[:, k])).to(dev) for k in range(3))
-        table, st = D.voxel_statistics(x, y, z, vs, origin)
+        table, st = D.voxel_statistics(x, y, z, vs, origin, exchange=exchange)
+        assert table.exchange == exchange, f"asked for the {exchange} exchange, got {table.exchange}"
         # single-GPU reference of the whole cloud on every rank
         ref = E.VoxelCloud.build(pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), vs, origin)
         rs = ref.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
@@ -55,7 +56,7 @@ def main():
                 continue  # ratios of noise on rank-deficient voxels; covered through eig
             assert np.all(err <= 1e-9 * scale + 1e-18), (mode, name, float(np.max(err / scale)))
         if rank == 0:
-            print(f"[{mode}] world={world}: owned voxels {allc}, partial rows sent by rank 0: {table.partial_rows_sent}", flush=True)
+            print(f"[{mode}, {exchange}] world={world}: owned voxels {allc}, partial rows sent by rank 0: {table.partial_rows_sent}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
