@@ -112,7 +112,14 @@ VAPC_API size_t vapc_bucket_workspace_bytes(int64_t n);
 VAPC_API int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n,
                                const vapc_grid_t* grid_host, void* keys_bucketed, double* xyzw_bucketed,
                                void* keys_orig, uint32_t* bucket_start, int32_t* bucket_bits_host,
-                               int32_t* status, void* ws, size_t ws_bytes, void* stream);
+                               int32_t* bucketed_key_bytes_host, int32_t* status, void* ws, size_t ws_bytes,
+                               void* stream);
+/* *bucketed_key_bytes_host = width of the keys written to keys_bucketed (allocate it for grid->key_bytes): 4 when the grid has
+ * 64-bit keys but the key bits BELOW the bucket digit fit 32 bits (grids of up to 40 key bits) — keys_bucketed then holds
+ * only those low bits as uint32, vapc_sort_pairs_segmented moves 4-byte keys, and vapc_expand_bucket_keys rebuilds the full
+ * sorted 64-bit keys (bucket of a sorted position from bucket_start) for the kernels downstream. */
+VAPC_API int vapc_expand_bucket_keys(const uint32_t* low_sorted, int64_t n, const uint32_t* bucket_start,
+                            int32_t bucket_bits, int32_t low_bits, uint64_t* keys_out, void* stream);
 /* voxel triple back from keys (n keys -> 3 x int64) */
 VAPC_API int vapc_unpack_keys(const void* keys, int64_t n, const vapc_grid_t* grid_host, int64_t* vx,
                      int64_t* vy, int64_t* vz, void* stream);

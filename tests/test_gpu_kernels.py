@@ -44,6 +44,10 @@ def make_cloud(kind, n, seed):
     elif kind == "utm":  # large coordinates: 64-bit keys when the origin stays at 0
         pts = rng.uniform(0, 25, (n, 3)) + [476850.0, 5429100.0, 312.0]
         pts = np.round(pts, 3)
+    elif kind == "wide":  # a few dense patches spread over 2 km x 2 km x 50 m: a grid of ~40 key bits with populated voxels
+        centers = rng.uniform([0, 0, 0], [2000, 2000, 50], (40, 3))
+        pts = np.round(centers[rng.integers(0, 40, n)] + rng.uniform(-0.6, 0.6, (n, 3)), 4)
+        pts[:2] = [[0.0, 0.0, 0.0], [2000.0, 2000.0, 50.0]]
     elif kind == "duplicates":  # many exactly identical points and n == 1 / n == 2 voxels
         base = rng.integers(0, 50, (n // 4, 3)) * 0.37
         pts = np.vstack([base, base, base[: n // 8], rng.uniform(0, 18.5, (n - 2 * (n // 4) - n // 8, 3))])
@@ -229,6 +233,7 @@ def check_cloud(E, x, y, z, vs, origin, eig_faithful=False, bucketed=True):
     ("duplicates", 40000, 0.37, [0, 0, 0]),
     ("uniform", 1, 1.0, [0, 0, 0]),
     ("uniform", 3, 1000.0, [0, 0, 0]),
+    ("wide", 50000, 0.05, [0, 0, 0]),           # 2 km extent at 5 cm: 40 key bits -> 32-bit low keys inside the buckets
 ])
 def test_voxel_table_vs_oracle(E, kind, n, vs, origin):
     x, y, z = make_cloud(kind, n, seed=n + int(vs * 100))
@@ -401,8 +406,13 @@ def test_bucketed_records(E):
     import ctypes as C
     from vapc_b200 import _lib as L
 
-    for kind, n, vs in (("uniform", 100_003, 0.05), ("clustered", 50_000, 0.5), ("utm", 30_000, 0.05), ("uniform", 7, 10.0)):
-        x, y, z = make_cloud(kind, n, seed=n)
+    for kind, n, vs in (("uniform", 100_003, 0.05), ("clustered", 50_000, 0.5), ("utm", 30_000, 0.05), ("uniform", 7, 10.0), ("wide", 60_000, 0.1),
+                        ("huge", 20_000, 0.001)):
+        if kind in ("wide", "huge"):  # 2 km x 2 km x 50 m: 39 key bits at 0.1 m (32-bit low keys inside the buckets), 59 at 1 mm
+            rng = np.random.default_rng(n)
+            x, y, z = (rng.integers(0, int(e / 1e-4), n) * 1e-4 for e in (2000.0, 2000.0, 50.0))
+        else:
+            x, y, z = make_cloud(kind, n, seed=n)
         dx, dy, dz = (torch.from_numpy(a).cuda() for a in (x, y, z))
         g = E.grid_from_bounds(vs, [0, 0, 0], E.coordinate_bounds(dx, dy, dz))
         kd = torch.int32 if g.key_bytes == 4 else torch.int64
@@ -412,9 +422,9 @@ def test_bucketed_records(E):
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         wsb = L.raw("vapc_bucket_workspace_bytes")(n)
         ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-        bits = C.c_int32(0)
+        bits, bkb = C.c_int32(0), C.c_int32(0)
         L.call("vapc_pack_records_bucketed", E._ptr(dx), E._ptr(dy), E._ptr(dz), n, C.byref(g), E._ptr(keys_b), E._ptr(rec), E._ptr(keys_o),
-               E._ptr(bstart), C.byref(bits), E._ptr(status), E._ptr(ws), wsb, E._stream())
+               E._ptr(bstart), C.byref(bits), C.byref(bkb), E._ptr(status), E._ptr(ws), wsb, E._stream())
         torch.cuda.synchronize()
         assert int(status.item()) == 0
         mb = bits.value
@@ -427,7 +437,20 @@ def test_bucketed_records(E):
         np.testing.assert_array_equal(ko, ref)
         bucket = (ko >> np.uint64(g.total_bits - mb)).astype(np.int64)
         order = np.argsort(bucket, kind="stable")
-        np.testing.assert_array_equal(_np(keys_b).view(ut).astype(np.uint64), ko[order])
+        low_bits = g.total_bits - mb
+        if kind == "wide":
+            assert g.key_bytes == 8 and bkb.value == 4, "39-bit grid: the bucketed keys are the 31 low bits as 32-bit words"
+        if kind == "huge":
+            assert g.key_bytes == 8 and bkb.value == 8
+        if bkb.value == 4 and g.key_bytes == 8:
+            got = _np(keys_b).view(np.uint32)[:n].astype(np.uint64)
+            np.testing.assert_array_equal(got, ko[order] & np.uint64((1 << low_bits) - 1))
+            full = torch.empty(n, dtype=torch.int64, device="cuda")  # low parts are still in bucket order: expansion restores the keys
+            L.call("vapc_expand_bucket_keys", E._ptr(keys_b), n, E._ptr(bstart), mb, low_bits, E._ptr(full), E._stream())
+            np.testing.assert_array_equal(_np(full).view(np.uint64), ko[order])
+        else:
+            assert bkb.value == g.key_bytes
+            np.testing.assert_array_equal(_np(keys_b).view(ut).astype(np.uint64), ko[order])
         r = _np(rec)
         np.testing.assert_array_equal(r[:, 3].copy().view(np.int64) & 0xFFFFFFFF, order)  # (32-bit keys ride in the upper half)
         np.testing.assert_array_equal(r[:, 0], x[order])

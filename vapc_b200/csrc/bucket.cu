@@ -103,10 +103,12 @@ struct BucketSmem {
   } u;
 };
 
-template <typename KeyT, typename LookT>
+// KeyOutT: the bucketed keys are written as 32-bit words holding the key bits BELOW the bucket digit when those fit
+// (64-bit keys of up to 40 bits): the segmented sort then moves 4-byte keys; vapc_expand_bucket_keys restores the full keys.
+template <typename KeyT, typename KeyOutT, typename LookT>
 __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) bucket_scatter_kernel(
     const KeyT* __restrict__ keys, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n, int shift,
-    unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyT* __restrict__ keys_b,
+    unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyOutT* __restrict__ keys_b,
     double4* __restrict__ rec_b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BucketSmem<KeyT>& sm = *reinterpret_cast<BucketSmem<KeyT>*>(smem_raw);
@@ -170,7 +172,24 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
     if (sizeof(KeyT) == 4) w |= (unsigned long long)k << 32;
     const unsigned dst = (unsigned)p + sm.r.delta[bucket_of(k, shift, mask)];
     st_record(rec_b + dst, sm.u.rec.x[p], sm.u.rec.y[p], sm.u.rec.z[p], __longlong_as_double((long long)w));
-    keys_b[dst] = k;
+    keys_b[dst] = sizeof(KeyOutT) < sizeof(KeyT) ? (KeyOutT)(k & (((KeyT)1 << shift) - 1)) : (KeyOutT)k;
+  }
+}
+
+// full sorted keys from the sorted low parts: key = bucket << low_bits | low, the bucket of a position from bucket_start
+__global__ void __launch_bounds__(kThreads) expand_keys_kernel(const uint32_t* __restrict__ low, int64_t n, const uint32_t* __restrict__ bucket_start,
+                                                               int nb, int low_bits, unsigned long long* __restrict__ out) {
+  __shared__ unsigned start[kRadix + 1];
+  for (int i = threadIdx.x; i <= nb; i += blockDim.x) start[i] = bucket_start[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    int lo = 0, hi = nb;  // start[lo] <= p < start[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (start[mid] <= (unsigned)p) lo = mid; else hi = mid;
+    }
+    out[p] = ((unsigned long long)lo << low_bits) | low[p];
   }
 }
 
@@ -178,8 +197,8 @@ inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
 // workspace: [bucket histogram -> first slots, 256 u32][ticket (256 B)][look-back ntiles x 256 x 8 B]
 constexpr size_t kHistBytes = kRadix * sizeof(uint32_t);
 
-template <typename KeyT, typename LookT>
-int bucket_impl(const double* x, const double* y, const double* z, int64_t n, const Grid& g, int mb, KeyT* keys_b, double4* rec_b, KeyT* keys_orig,
+template <typename KeyT, typename KeyOutT, typename LookT>
+int bucket_impl(const double* x, const double* y, const double* z, int64_t n, const Grid& g, int mb, KeyOutT* keys_b, double4* rec_b, KeyT* keys_orig,
                 uint32_t* bucket_start, int32_t* status, void* ws, cudaStream_t s) {
   const int shift = g.bx + g.by + g.bz - mb;  // the bucket digit = the leading mb bits of the key
   const unsigned mask = (1u << mb) - 1u;
@@ -196,8 +215,8 @@ int bucket_impl(const double* x, const double* y, const double* z, int64_t n, co
   VAPC_LAUNCH(digit_scan_kernel, 1, kThreads, 0, s, hist, nullptr, 1);
   VAPC_LAUNCH(bucket_start_kernel, 1, kThreads, 0, s, hist, 1 << mb, (uint32_t)n, bucket_start);
   const size_t smem = sizeof(BucketSmem<KeyT>);
-  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, LookT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, LookT>), (unsigned)ntiles, kThreads, smem, s, keys_orig, x, y, z, n, shift, mask, hist, look, ticket, keys_b,
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, KeyOutT, LookT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, KeyOutT, LookT>), (unsigned)ntiles, kThreads, smem, s, keys_orig, x, y, z, n, shift, mask, hist, look, ticket, keys_b,
               rec_b);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -211,12 +230,16 @@ extern "C" size_t vapc_bucket_workspace_bytes(int64_t n) {
 
 extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n, const vapc_grid_t* grid_host,
                                           void* keys_bucketed, double* xyzw_bucketed, void* keys_orig, uint32_t* bucket_start,
-                                          int32_t* bucket_bits_host, int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+                                          int32_t* bucket_bits_host, int32_t* bucketed_key_bytes_host, int32_t* status, void* ws, size_t ws_bytes,
+                                          void* stream) {
   if (!grid_host || !(grid_host->voxel_size > 0)) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad grid");
-  if (n < 0 || !bucket_bits_host) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad arguments");
+  if (n < 0 || !bucket_bits_host || !bucketed_key_bytes_host) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad arguments");
   const Grid g = to_device_grid(grid_host);
   const int mb = g.bx < kRadixBits ? g.bx : kRadixBits;
+  const int low_bits = g.bx + g.by + g.bz - mb;
+  const bool narrow = grid_host->key_bytes == 8 && low_bits <= 32;  // the bits below the bucket digit fit a 32-bit word
   *bucket_bits_host = mb;
+  *bucketed_key_bytes_host = narrow ? 4 : grid_host->key_bytes;
   if (n == 0) return VAPC_OK;
   if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: n must be < 2^32 per GPU");
   if (!x || !y || !z || !keys_bucketed || !xyzw_bucketed || !keys_orig || !bucket_start || !status)
@@ -227,13 +250,31 @@ extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, cons
   double4* rec = reinterpret_cast<double4*>(xyzw_bucketed);
   const bool wide = n >= ((int64_t)1 << 30);
   typedef unsigned long long u64;
+  typedef uint32_t u32;
   if (grid_host->key_bytes == 4) {
-    if (!wide) return bucket_impl<uint32_t, uint32_t>(x, y, z, n, g, mb, static_cast<uint32_t*>(keys_bucketed), rec, static_cast<uint32_t*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<uint32_t, u64>(x, y, z, n, g, mb, static_cast<uint32_t*>(keys_bucketed), rec, static_cast<uint32_t*>(keys_orig), bucket_start, status, ws, s);
+    if (!wide) return bucket_impl<u32, u32, u32>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u32, u32, u64>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
   }
   if (grid_host->key_bytes == 8) {
-    if (!wide) return bucket_impl<u64, uint32_t>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<u64, u64>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    if (narrow) {
+      if (!wide) return bucket_impl<u64, u32, u32>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+      return bucket_impl<u64, u32, u64>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    }
+    if (!wide) return bucket_impl<u64, u64, u32>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u64, u64, u64>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
   }
   return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: key_bytes must be 4 or 8");
+}
+
+extern "C" int vapc_expand_bucket_keys(const uint32_t* low_sorted, int64_t n, const uint32_t* bucket_start, int32_t bucket_bits, int32_t low_bits,
+                                       uint64_t* keys_out, void* stream) {
+  if (n < 0 || bucket_bits < 0 || bucket_bits > kRadixBits || low_bits < 0 || low_bits > 32)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_expand_bucket_keys: bad arguments");
+  if (n == 0) return VAPC_OK;
+  if (!low_sorted || !bucket_start || !keys_out) return vapc_set_error(VAPC_E_INVALID, "vapc_expand_bucket_keys: null buffer");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16));
+  VAPC_LAUNCH(expand_keys_kernel, grid, kThreads, 0, as_stream(stream), low_sorted, n, bucket_start, 1 << bucket_bits, low_bits,
+              reinterpret_cast<unsigned long long*>(keys_out));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
 }

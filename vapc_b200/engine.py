@@ -242,11 +242,19 @@ class VoxelCloud:
             bucket_start = _empty(257, torch.int32, device)
             bws_bytes = L.raw("vapc_bucket_workspace_bytes")(n)
             bws = _empty(bws_bytes, torch.uint8, device)
-            bucket_bits = C.c_int32(0)
+            bucket_bits, bkey_bytes = C.c_int32(0), C.c_int32(0)
             L.call("vapc_pack_records_bucketed", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys_b), _ptr(self.xyzw), _ptr(keys), _ptr(bucket_start),
-                   C.byref(bucket_bits), _ptr(status), _ptr(bws), bws_bytes, _stream())
+                   C.byref(bucket_bits), C.byref(bkey_bytes), _ptr(status), _ptr(bws), bws_bytes, _stream())
             del bws
-            self.keys_sorted, self.pos_sorted = sort_pairs_segmented(keys_b, g.total_bits - bucket_bits.value, bucket_start, 1 << bucket_bits.value)
+            low_bits = g.total_bits - bucket_bits.value
+            if bkey_bytes.value == 4 and g.key_bytes == 8:
+                # 64-bit grid, but the bits below the bucket digit fit 32: sort 4-byte keys, then rebuild the full sorted keys
+                low_sorted, self.pos_sorted = sort_pairs_segmented(keys_b.view(torch.int32)[:n], low_bits, bucket_start, 1 << bucket_bits.value)
+                self.keys_sorted = _empty(n, torch.int64, device)
+                L.call("vapc_expand_bucket_keys", _ptr(low_sorted), n, _ptr(bucket_start), bucket_bits.value, low_bits, _ptr(self.keys_sorted), _stream())
+                del low_sorted
+            else:
+                self.keys_sorted, self.pos_sorted = sort_pairs_segmented(keys_b, low_bits, bucket_start, 1 << bucket_bits.value)
             del keys_b
             if not dense_p2v:
                 del keys
