@@ -302,6 +302,41 @@ VAPC_API int vapc_mahalanobis(const double* cog3_1, const double* cov6_1, int64_
                      int64_t npairs, double alpha, double* distance, double* d1, double* d2,
                      double* p_value, int32_t* significance, int32_t* change_type, void* stream);
 
+/* ---- (f)4 neighbour queries on a voxelised point set used as a cell list ------------------
+ * The searched set is described by what a voxelisation of it with cell size grid->voxel_size produced: cell_keys
+ * (sorted packed keys, ncells), start[ncells + 1], pos_sorted[n] and the 32-byte records xyzw[n] (vapc_pack_keys_f64 /
+ * vapc_pack_records_bucketed + sort + vapc_reduce_moments).
+ *
+ * vapc_cell_nn: exact nearest neighbour of every query point (bi_vapc.py:173-186 mutual_nearest_neighbors and
+ * :51-74 merge_vapcs_with_closest_point: the KDTree.query(k=1) calls).  nn_idx = original index of the nearest point
+ * of the set (lowest index among exactly equidistant ones), nn_dist = sqrt(dx*dx + dy*dy + dz*dz) formed like scipy's
+ * KD-tree forms it (plain products, left-to-right sum).  Queries may lie outside the set's bounding box.
+ *
+ * vapc_cluster_components: connected components of the graph "distance <= cluster_distance" between the n units of
+ * the set (vapc.py:1274-1357 compute_clusters: KD-tree region growing, labels merged to the lowest).  Needs
+ * grid->voxel_size >= distance (a 3x3x3 block of cells then holds every neighbour).  first (nullable = unit
+ * index): the lowest original point index a unit stands for, weight (nullable = 1): its number of points — units are
+ * single points, or occupied voxels standing for all their points.  Outputs per unit: root = lowest unit index of its
+ * component; hop2_first = lowest `first` within two hops (a unit opens a new label in the reference's sequential sweep
+ * iff hop2_first == first, which yields the reference's cluster ids: see vapc_b200/engine.py:cluster_components);
+ * and at index root: comp_first = lowest `first` of the component, comp_size = its number of points. */
+VAPC_API int vapc_cell_nn(const double* qx, const double* qy, const double* qz, int64_t nq, const vapc_grid_t* grid_host,
+                 const void* cell_keys, int64_t ncells, const uint32_t* start, const uint32_t* pos_sorted,
+                 const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist, void* stream);
+VAPC_API size_t vapc_cluster_workspace_bytes(int64_t n);
+VAPC_API int vapc_cluster_components(const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
+                            const uint32_t* pos_sorted, const double* xyzw, int64_t n, double distance,
+                            const uint32_t* first, const uint32_t* weight, uint32_t* root, uint32_t* hop2_first,
+                            uint32_t* comp_first, int64_t* comp_size, void* ws, size_t ws_bytes, void* stream);
+/* the same code run serially on HOST arrays (CPU tests of the traversal logic) */
+VAPC_API int vapc_selftest_cell_nn_host(const double* qx, const double* qy, const double* qz, int64_t nq,
+                               const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
+                               const uint32_t* pos_sorted, const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist);
+VAPC_API int vapc_selftest_cluster_host(const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
+                               const uint32_t* pos_sorted, const double* xyzw, int64_t n, double distance,
+                               const uint32_t* first, const uint32_t* weight, uint32_t* root, uint32_t* hop2_first,
+                               uint32_t* comp_first, int64_t* comp_size);
+
 /* ---- multi-GPU (north_star: partial accumulators exchanged by key range) ---------------
  * Merge partial voxel rows that share a key: inputs are R partial rows (keys sorted, equal
  * keys adjacent, in source-rank order), outputs the merged rows.  Same ws protocol as

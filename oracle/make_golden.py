@@ -300,7 +300,69 @@ def real_file():
     save("vapc_in_every50th_vs0.25", store)
 
 
+def clusters_nn():
+    """compute_clusters (vapc.py:1274-1357) and merge_vapcs_with_closest_point
+    (bi_vapc.py:51-74) of the unmodified reference.
+      cl_sparse_*   sparse cloud, default cluster_by (voxel triple), distances 1.0 / 1.8 / 2.0 voxels: every KD-tree query
+                    finds fewer than 50 rows within the distance, i.e. the regime where the sweep is not truncated;
+      cl_xyz_*      cluster_by = X, Y, Z (float rows), distance 0.3 m;
+      cl_blobs_*    the reference's own unit-test fixture (tests/test_compute.py:128-160, 235-242): 3 blobs of 100
+                    points, voxel 0.2, distance 10 voxels — the truncated regime (every query returns 50 rows);
+      nn_*          two epochs of 4000 / 4300 points, voxel 0.5: prepare_data_for_mahalanobis_distance,
+                    merge_vapcs_with_closest_point, compute_mahalanobis_distance."""
+    from sklearn.datasets import make_blobs
+
+    store = {}
+    rng = np.random.default_rng(77)
+    pts = np.round(rng.random((900, 3)) * [12.0, 12.0, 6.0], 4)
+    df = pd.DataFrame({"X": pts[:, 0], "Y": pts[:, 1], "Z": pts[:, 2]})
+    for c in "XYZ":
+        store[f"in_sparse_{c}"] = df[c].to_numpy()
+    store["in_sparse_voxel_size"] = np.float64(0.5)
+    for d in (1.0, 1.8, 2.0):
+        v = new_vapc(df, 0.5)
+        v.compute_clusters(cluster_distance=d)
+        store[f"cl_sparse_d{d}_cluster_id"] = v.df["cluster_id"].to_numpy()
+        store[f"cl_sparse_d{d}_cluster_size"] = v.df["cluster_size"].to_numpy()
+        store[f"cl_sparse_d{d}__columns"] = np.array(v.df.columns.tolist())
+    v = new_vapc(df, 0.5)
+    v.compute_clusters(cluster_distance=0.3, cluster_by=["X", "Y", "Z"])
+    store["cl_xyz_d0.3_cluster_id"] = v.df["cluster_id"].to_numpy()
+    store["cl_xyz_d0.3_cluster_size"] = v.df["cluster_size"].to_numpy()
+    store["cl_xyz_d0.3__columns"] = np.array(v.df.columns.tolist())
+    bp, bid = make_blobs(n_samples=300, n_features=3, centers=3, cluster_std=1.0, random_state=42)
+    bdf = pd.DataFrame({"X": bp[:, 0], "Y": bp[:, 1], "Z": bp[:, 2], "cluster_id": bid})
+    for c in "XYZ":
+        store[f"in_blobs_{c}"] = bdf[c].to_numpy()
+    store["in_blobs_true_id"] = bid
+    v = new_vapc(bdf, 0.2)
+    v.compute_clusters(cluster_distance=10.0)
+    store["cl_blobs_cluster_id"] = v.df["cluster_id"].to_numpy()
+    store["cl_blobs_cluster_size"] = v.df["cluster_size"].to_numpy()
+    # two epochs
+    e1 = np.round(rng.random((4000, 3)) * [10.0, 10.0, 3.0], 4)
+    e2 = np.concatenate([np.round(e1[:3500] + rng.normal(0, 0.03, (3500, 3)), 4), np.round(rng.random((800, 3)) * [10.0, 10.0, 3.0] + [4.0, 0, 0], 4)])
+    for k, e in (("1", e1), ("2", e2)):
+        for j, c in enumerate("XYZ"):
+            store[f"in_nn_e{k}_{c}"] = e[:, j]
+    store["in_nn_voxel_size"] = np.float64(0.5)
+    a = new_vapc(pd.DataFrame(e1, columns=list("XYZ")), 0.5)
+    b = new_vapc(pd.DataFrame(e2, columns=list("XYZ")), 0.5)
+    bi = vapc.BiTemporalVapc([a, b])
+    bi.prepare_data_for_mahalanobis_distance()
+    bi.merge_vapcs_with_closest_point()
+    bi.compute_mahalanobis_distance(alpha=0.005)
+    md = bi.merged_df
+    store["nn__columns"] = np.array(md.columns.tolist())
+    for c in md.columns:
+        store[f"nn_{c}"] = md[c].to_numpy()
+    save("clusters_nn", store)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "clusters_nn":
+        clusters_nn()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "real_file":
         real_file()
         sys.exit(0)
@@ -312,3 +374,4 @@ if __name__ == "__main__":
     utm_offset()
     grid8()
     real_file()
+    clusters_nn()

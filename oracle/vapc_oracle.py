@@ -514,6 +514,94 @@ def euclidean_distance(cog1, cog2):
 
 
 # --------------------------------------------------------------------------------------
+# (f)4  Vapc.compute_clusters                                   src/vapc/vapc.py:1274-1357
+# --------------------------------------------------------------------------------------
+def compute_clusters(pts, cluster_distance, nr_of_neighbours=50, dtype=None):
+    """The reference's region growing restated literally (vapc.py:1336-1357): one KD-tree query of the
+    `nr_of_neighbours` nearest rows per row, in row order; rows within `cluster_distance` that carry no label yet
+    open label `objectCounter`; otherwise every label met is rewritten to the lowest one (frame-wide) and the rows
+    of the query take it.  pts: [n, k] rows of df[cluster_by].  Returns (cluster_id [n], cluster_size [n]); dtype
+    follows the reference: that of the first cluster_by column (np.zeros_like, vapc.py:1338)."""
+    from scipy.spatial import KDTree
+
+    pts = np.asarray(pts)
+    n = len(pts)
+    oc = np.zeros(n, dtype=dtype if dtype is not None else pts.dtype)
+    tree = KDTree(pts)
+    counter = 1.0
+    for point in pts:
+        distances, indices = tree.query(point, nr_of_neighbours)
+        rel = indices[np.where(distances <= cluster_distance)]
+        if oc[rel].max() < 1:
+            oc[rel] = counter
+            counter += 1
+        else:
+            obj = np.unique(oc[rel])
+            existing = obj[obj > 0]
+            for e in existing:
+                oc[oc == e] = existing.min()
+            oc[rel] = existing.min()
+    oids, cts = np.unique(oc, return_counts=True)
+    size = cts[np.searchsorted(oids, oc)]
+    return oc, size.astype(np.result_type(oc.dtype, np.int64))
+
+
+def cluster_components(pts, cluster_distance, dtype=None):
+    """What compute_clusters amounts to whenever no row has more than `nr_of_neighbours` rows (itself included)
+    within `cluster_distance` — stated without the sequential sweep, as the GPU computes it:
+      * the partition is the connected components of the graph "distance <= cluster_distance";
+      * row i opens a new label iff no earlier row lies within two hops of it (the rows of query j and of query i
+        intersect iff j is within two hops of i), labels are numbered 1, 2, ... in row order of those openings;
+      * merging always keeps the lowest label, so a component ends with the label opened by its lowest row.
+    Returns (cluster_id, cluster_size) like compute_clusters."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import KDTree
+
+    pts = np.asarray(pts)
+    n = len(pts)
+    tree = KDTree(pts.astype(np.float64))
+    pairs = tree.query_pairs(cluster_distance * (1 + 1e-12), output_type="ndarray")
+    if len(pairs):
+        d = pts[pairs[:, 0]].astype(np.float64) - pts[pairs[:, 1]].astype(np.float64)
+        pairs = pairs[np.sqrt((d * d).sum(axis=1)) <= cluster_distance]
+    a = np.concatenate([pairs[:, 0], pairs[:, 1], np.arange(n)])
+    b = np.concatenate([pairs[:, 1], pairs[:, 0], np.arange(n)])
+    adj = coo_matrix((np.ones(len(a), np.int64), (a, b)), shape=(n, n)).tocsr()
+    _, comp = connected_components(adj, directed=False)
+    m1 = np.full(n, n, np.int64)
+    np.minimum.at(m1, a, b)                      # lowest row in the closed neighbourhood
+    m2 = np.full(n, n, np.int64)
+    np.minimum.at(m2, a, m1[b])                  # lowest row within two hops
+    opens = np.flatnonzero(m2 == np.arange(n))   # rows that open a label, ascending
+    comp_first = np.full(comp.max() + 1, n, np.int64)
+    np.minimum.at(comp_first, comp, np.arange(n))
+    label = np.searchsorted(opens, comp_first[comp]) + 1
+    oc = label.astype(dtype if dtype is not None else pts.dtype)
+    size = np.bincount(comp)[comp]
+    return oc, size.astype(np.result_type(oc.dtype, np.int64))
+
+
+# --------------------------------------------------------------------------------------
+# (f)4  mutual nearest neighbours of two centroid sets           src/vapc/bi_vapc.py:51-74, 173-186
+# --------------------------------------------------------------------------------------
+def mutual_nearest_neighbors(coords1, coords2):
+    """bi_vapc.py:173-186: nearest row of set 2 for every row of set 1, kept where that row's nearest row of set 1
+    is the row itself.  Returns (idx1, idx2, distance) of the mutual pairs in set-1 order; distance as
+    merge_vapcs_with_closest_point recomputes it (bi_vapc.py:62-64)."""
+    from scipy.spatial import KDTree
+
+    coords1 = np.asarray(coords1, np.float64)
+    coords2 = np.asarray(coords2, np.float64)
+    _, indices = KDTree(coords2).query(coords1, k=1)
+    _, back = KDTree(coords1).query(coords2[indices], k=1)
+    mutual = np.arange(len(coords1)) == back
+    idx1, idx2 = np.arange(len(coords1))[mutual], indices[mutual]
+    dist, _ = KDTree(coords2[idx2]).query(coords1[idx1], k=1)
+    return idx1, idx2, dist
+
+
+# --------------------------------------------------------------------------------------
 # convenience: the whole per-voxel table for one cloud
 # --------------------------------------------------------------------------------------
 def voxel_table(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), faithful_eig=True):

@@ -215,3 +215,57 @@ def test_reference_port_reproduces_reference(name):
         got = df[c].to_numpy()
         got = got.real if got.dtype.kind == "c" else got
         np.testing.assert_allclose(got, gold["pt_" + c], rtol=1e-12, atol=1e-14, equal_nan=True, err_msg=c)
+
+
+# ---- compute_clusters / merge_vapcs_with_closest_point ---------------------------------
+CLUSTER_CASES = [("sparse_d1.0", 1.0, None), ("sparse_d1.8", 1.8, None), ("sparse_d2.0", 2.0, None), ("xyz_d0.3", 0.3, "XYZ")]
+
+
+def cluster_rows(gold, case, by):
+    x, y, z = (gold[f"in_sparse_{c}"] for c in "XYZ")
+    if by == "XYZ":
+        return np.stack([x, y, z], 1)
+    return np.stack(O.voxelize(x, y, z, (0.0, 0.0, 0.0), float(gold["in_sparse_voxel_size"])), 1)
+
+
+@pytest.mark.parametrize("case,d,by", CLUSTER_CASES)
+def test_clusters(case, d, by):
+    """The literal restatement of the sweep AND its closed form (components + opening rule) reproduce the reference."""
+    gold = P.load_golden("clusters_nn")
+    rows = cluster_rows(gold, case, by)
+    for fn in (O.compute_clusters, O.cluster_components):
+        cid, size = fn(rows, d)
+        assert cid.dtype == gold[f"cl_{case}_cluster_id"].dtype and size.dtype == gold[f"cl_{case}_cluster_size"].dtype
+        np.testing.assert_array_equal(cid, gold[f"cl_{case}_cluster_id"])
+        np.testing.assert_array_equal(size, gold[f"cl_{case}_cluster_size"])
+
+
+def test_clusters_reference_unit_test_fixture():
+    """tests/test_compute.py:235-242: three blobs -> three clusters (every KD-tree query is truncated to 50 rows here)."""
+    gold = P.load_golden("clusters_nn")
+    rows = np.stack(O.voxelize(*(gold[f"in_blobs_{c}"] for c in "XYZ"), (0.0, 0.0, 0.0), 0.2), 1)
+    cid, size = O.compute_clusters(rows, 10.0)
+    np.testing.assert_array_equal(cid, gold["cl_blobs_cluster_id"])
+    np.testing.assert_array_equal(size, gold["cl_blobs_cluster_size"])
+    assert len(np.unique(cid)) == 3
+    comp, _ = O.cluster_components(rows, 10.0)
+    assert len(set(zip(comp.tolist(), cid.tolist()))) == 3  # same partition
+
+
+def epoch_centroid_rows(gold, k):
+    """reduce_to_voxels(center_of_gravity) of one epoch: centroid rows sorted by (X, Y, Z) (vapc.py:1150-1210)."""
+    x, y, z = (gold[f"in_nn_e{k}_{c}"] for c in "XYZ")
+    g = O.group_by_voxel(*O.voxelize(x, y, z, (0.0, 0.0, 0.0), float(gold["in_nn_voxel_size"])))
+    cog = O.center_of_gravity(x, y, z, g)
+    return cog[np.lexsort((cog[:, 2], cog[:, 1], cog[:, 0]))]
+
+
+def test_mutual_nearest_neighbours():
+    gold = P.load_golden("clusters_nn")
+    c1, c2 = epoch_centroid_rows(gold, 1), epoch_centroid_rows(gold, 2)
+    i1, i2, dist = O.mutual_nearest_neighbors(c1, c2)
+    assert len(i1) == len(gold["nn_distance"])
+    for k, c in enumerate("xyz"):
+        P.assert_close_rel(c1[i1, k], gold[f"nn_cog_{c}_x"], rtol=1e-12, atol=1e-13, what=f"cog_{c}_x")
+        P.assert_close_rel(c2[i2, k], gold[f"nn_cog_{c}_y"], rtol=1e-12, atol=1e-13, what=f"cog_{c}_y")
+    P.assert_close_rel(dist, gold["nn_distance"], rtol=1e-9, atol=1e-13, what="distance")

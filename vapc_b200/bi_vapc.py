@@ -85,10 +85,26 @@ class BiTemporalVapc:
         right.index = left.index
         self.merged_df = pd.concat([left, right], axis=1)
 
+    @trace
+    @timeit
     def merge_vapcs_with_closest_point(self):
-        """Mutual-nearest-neighbour pairing (bi_vapc.py:51-74) — KD-tree based, outside the voxel-join path
-        this package rebuilds."""
-        raise NotImplementedError("merge_vapcs_with_closest_point is outside the path rebuilt by vapc_b200")
+        """Pairs every epoch-1 row with its nearest epoch-2 centroid where the two are MUTUAL nearest neighbours
+        (bi_vapc.py:51-74, 173-186), side by side with suffixes _x / _y and the pair `distance`.  The three KD-tree
+        queries of the reference are exact grid searches on the GPU (vapc_cell_nn) over the epochs' own voxel grids
+        (one centroid per cell)."""
+        df1, df2 = self.vapcs[0].df, self.vapcs[1].df
+        cols = ["cog_x", "cog_y", "cog_z"]
+        sets = [[d[c].to_numpy(np.float64) for c in cols] for d in (df1, df2)]
+        idx1, idx2, dist = E.mutual_nearest_neighbors(sets[0], sets[1], cell_sizes=[float(v.voxel_size) for v in self.vapcs],
+                                                      origins=[[float(o) for o in v.origin] for v in self.vapcs])
+        df1_reduced = df1.iloc[idx1.cpu().numpy()].copy()
+        df2_reduced = df2.iloc[idx2.cpu().numpy()].copy()
+        df1_reduced["distance"] = dist.cpu().numpy()
+        df1_reduced.reset_index(drop=True, inplace=True)
+        df2_reduced.reset_index(drop=True, inplace=True)
+        self.merged_df = pd.concat([df1_reduced.add_suffix("_x"), df2_reduced.add_suffix("_y")], axis=1)
+        self.merged_df.rename(columns={"distance_x": "distance"}, inplace=True)
+        self.distance_computed = True
 
     def _device_tables(self):
         df = self.merged_df

@@ -595,3 +595,93 @@ def mahalanobis(cog1, cov1, cog2, cov2, i1, i2, alpha=0.005):
            cog2.shape[1], _ptr(a), _ptr(b), r, float(alpha), _ptr(out["distance"]), _ptr(out["d1"]), _ptr(out["d2"]), _ptr(out["p_value"]),
            _ptr(out["significance"]), _ptr(out["change_type"]), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# neighbour queries on a voxelised point set
+# ----------------------------------------------------------------------------------------
+_MAX_AXIS_CELLS = float(1 << 20)  # cell size floor: three axes of <= 20 bits keep the packed key within 63 bits
+
+
+def _cell_cloud(x, y, z, cell_size, origin=(0.0, 0.0, 0.0)) -> VoxelCloud:
+    """The searched set voxelised with `cell_size`: its voxel table is the cell list of vapc_cell_nn /
+    vapc_cluster_components.  The cell size is raised when the extent would need more than 2^20 cells per axis."""
+    _require_cuda()
+    dev = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x, y, z = (_dev_f64(a, dev) for a in (x, y, z))
+    bounds = coordinate_bounds(x, y, z)
+    extent = float(max(bounds[3] - bounds[0], bounds[4] - bounds[1], bounds[5] - bounds[2]))
+    h = max(float(cell_size), extent / _MAX_AXIS_CELLS * 1.0000001)
+    return VoxelCloud.build(x, y, z, h, origin, bounds=bounds, want_point2voxel=False, keep_columns=False)
+
+
+def nearest_neighbors(qx, qy, qz, cells: VoxelCloud):
+    """Exact nearest point of the voxelised set `cells` for every query point (KDTree(set).query(q, k=1),
+    bi_vapc.py:179-184).  Returns (index int64 [nq], distance f64 [nq]) device tensors."""
+    dev = cells.device
+    qx, qy, qz = (_dev_f64(a, dev) for a in (qx, qy, qz))
+    nq = qx.numel()
+    idx = _empty(nq, torch.int32, dev)
+    dist = _empty(nq, torch.float64, dev)
+    L.call("vapc_cell_nn", _ptr(qx), _ptr(qy), _ptr(qz), nq, C.byref(cells.grid), _ptr(cells.voxel_keys), cells.nvoxels, _ptr(cells.start),
+           _ptr(cells.pos_sorted), _ptr(cells.xyzw), cells.n, _ptr(idx), _ptr(dist), _stream())
+    return idx.to(torch.int64) & 0xFFFFFFFF, dist
+
+
+def mutual_nearest_neighbors(c1: Sequence, c2: Sequence, cell_sizes=(None, None), origins=((0.0, 0.0, 0.0), (0.0, 0.0, 0.0))):
+    """bi_vapc.py:173-186 + :62-64: rows of set 1 whose nearest row of set 2 has them as ITS nearest row of set 1.
+    c1 / c2: (x, y, z) columns.  cell_sizes: cell size of the search grid over set 1 / set 2 (None: about two points
+    per cell of the bounding box).  Returns (idx1, idx2, distance) device tensors in set-1 order."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sets = [[_dev_f64(a, dev) for a in c] for c in (c1, c2)]
+    clouds = []
+    for s, h, o in zip(sets, cell_sizes, origins):
+        if h is None:
+            b = coordinate_bounds(*s)
+            ext = np.maximum(np.asarray(b[3:]) - np.asarray(b[:3]), 1e-12)
+            h = float(np.cbrt(2.0 * np.prod(ext) / s[0].numel()))
+        clouds.append(_cell_cloud(*s, h, o))
+    fwd, dist = nearest_neighbors(*sets[0], clouds[1])
+    back, _ = nearest_neighbors(*sets[1], clouds[0])
+    n1 = sets[0][0].numel()
+    idx1 = torch.nonzero(back[fwd] == torch.arange(n1, device=dev)).flatten()
+    return idx1, fwd[idx1], dist[idx1]
+
+
+def cluster_components(cx, cy, cz, cluster_distance: float, integer_rows: bool = False):
+    """compute_clusters of the reference (vapc.py:1324-1357) as connected components of the graph "row distance <=
+    cluster_distance", with the reference's label numbering: in its sequential sweep a row opens a new label iff no
+    earlier row lies within two hops (vapc_cluster_components' hop2_first), labels merge to the lowest, so a component
+    carries the label opened by its lowest row.  Identical to the reference whenever no row has more than 50 rows
+    (its `nr_of_neighbours`, itself included) within cluster_distance; beyond that the reference truncates its
+    neighbourhoods to a KD-tree dependent subset and may split what is connected here.
+    integer_rows: the columns hold integers (voxel indices): identical rows are collapsed into one unit standing for
+    all its points first.  Returns (cluster_id int64 [n], cluster_size int64 [n], openings) on the device."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cols = [_dev_f64(a, dev) for a in (cx, cy, cz)]
+    d = float(cluster_distance)
+    first = weight = p2v = None
+    if integer_rows:
+        units = VoxelCloud.build(*cols, 1.0, (0.0, 0.0, 0.0), keep_columns=False)
+        cols = [v.to(torch.float64) for v in units.voxel_coords()]
+        first, weight, p2v = units.first_idx, units.count, units.point2voxel.to(torch.int64) & 0xFFFFFFFF
+        del units
+    n = cols[0].numel()
+    cells = _cell_cloud(*cols, d * (1.0 + 2.0 ** -30) if d > 0 else 1.0)
+    root, hop2, comp_first = (_empty(n, torch.int32, dev) for _ in range(3))
+    comp_size = _empty(n, torch.int64, dev)
+    ws_bytes = L.raw("vapc_cluster_workspace_bytes")(n)
+    ws = _empty(ws_bytes, torch.uint8, dev)
+    L.call("vapc_cluster_components", C.byref(cells.grid), _ptr(cells.voxel_keys), cells.nvoxels, _ptr(cells.start), _ptr(cells.pos_sorted),
+           _ptr(cells.xyzw), n, d, _ptr(first), _ptr(weight), _ptr(root), _ptr(hop2), _ptr(comp_first), _ptr(comp_size), _ptr(ws), ws_bytes, _stream())
+    u32 = lambda t: t.to(torch.int64) & 0xFFFFFFFF  # noqa: E731
+    first64 = u32(first) if first is not None else torch.arange(n, device=dev)
+    root = u32(root)
+    opens = torch.sort(first64[u32(hop2) == first64]).values
+    label = torch.searchsorted(opens, u32(comp_first)[root]) + 1
+    size = comp_size[root]
+    if p2v is not None:
+        label, size = label[p2v], size[p2v]
+    return label, size, int(opens.numel())

@@ -656,7 +656,30 @@ class Vapc:
         finally:
             self.attributes = saved
 
+    @trace
+    @timeit
     def compute_clusters(self, cluster_distance, cluster_by=None):
-        """KD-tree region growing of the reference (vapc.py:1274-1357) — not part of the voxel-statistics
-        hot path this package rebuilds (out of scope)."""
-        raise NotImplementedError("compute_clusters is outside the voxelisation / per-voxel statistics path rebuilt by vapc_b200")
+        """cluster_id / cluster_size: rows within `cluster_distance` of each other (in the `cluster_by` columns,
+        default the voxel triple) share a cluster (vapc.py:1274-1357).  The reference grows regions with one KD-tree
+        query per row in a Python loop; here the rows' connected components come from a union-find over a cell list
+        on the GPU (engine.cluster_components), numbered like the reference's sweep numbers them.  Equal to the
+        reference whenever no row has more than its `nr_of_neighbours` = 50 rows within the distance."""
+        if cluster_by is None:
+            cluster_by = ["voxel_x", "voxel_y", "voxel_z"]
+        if not self.voxelized:
+            self.voxelize()
+            self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
+        cols = self.df[cluster_by]  # KeyError for unknown columns, like the reference
+        if not 1 <= cols.shape[1] <= 3:
+            raise NotImplementedError("compute_clusters: one to three cluster_by columns")
+        dtype0 = cols.dtypes.iloc[0]
+        integer = all(np.issubdtype(t, np.integer) for t in cols.dtypes)
+        arrays = [cols.iloc[:, k].to_numpy(np.float64) for k in range(cols.shape[1])]
+        arrays += [np.zeros(len(cols))] * (3 - len(arrays))
+        label, size, openings = E.cluster_components(*arrays, cluster_distance, integer_rows=integer)
+        self.objectCounter = float(openings + 1)
+        # np.zeros_like(df[cluster_by[0]]) holds the ids; the sizes come back through a merge (index reset)
+        self.df["cluster_id"] = self._host(label).astype(dtype0)
+        self.df = self.df.reset_index(drop=True)
+        self.df["cluster_size"] = self._host(size).astype(np.result_type(dtype0, np.int64))
+        self._resign()
