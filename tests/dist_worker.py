@@ -12,6 +12,59 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def gather_cat(a):
+    """Concatenate a per-rank numpy array over the ranks, in rank order (= global key order)."""
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, a)
+    return np.concatenate(parts, axis=-1)
+
+
+def two_epoch(rank, world, dev, pts, rng, vs, origin):
+    """Multi-GPU change detection (shared grid + shared key ranges, owner-local join) == the single-GPU flow."""
+    from vapc_b200 import dist as D
+    from vapc_b200 import engine as E
+
+    n = len(pts)
+    e2 = np.round(np.concatenate([pts[: n * 3 // 4] + rng.normal(0, 0.02, (n * 3 // 4, 3)), rng.uniform([40, 30, 0], [75, 50, 6], (n // 8, 3))]), 3)
+    chunks = []
+    for e, order in ((pts, np.argsort(pts[:, 0], kind="stable")), (e2, rng.permutation(len(e2)))):  # epoch 1 coherent, epoch 2 shuffled
+        c = e[order[rank * len(e) // world:(rank + 1) * len(e) // world]]
+        chunks.append([torch.from_numpy(np.ascontiguousarray(c[:, k])).to(dev) for k in range(3)])
+    res = D.two_epoch_change(chunks[0], chunks[1], vs, origin, alpha=0.005)
+    # single-GPU flow on every rank
+    only = dict(cog=True, cov=True)
+    refs = [E.VoxelCloud.build(e[:, 0].copy(), e[:, 1].copy(), e[:, 2].copy(), vs, origin) for e in (pts, e2)]
+    i1, i2, only1, only2 = E.join_voxel_tables(refs[0].voxel_coords(), refs[1].voxel_coords())
+    s1, s2 = refs[0].stats(**only), refs[1].stats(**only)
+    ref = E.mahalanobis(s1.cog, s1.cov, s2.cog, s2.cov, i1, i2, alpha=0.005)
+    vox = lambda cloud, rows: torch.stack(cloud.voxel_coords())[:, rows].cpu().numpy()  # noqa: E731
+    got_pairs = gather_cat(torch.stack(res["table1"].voxel_coords())[:, res["i1"]].cpu().numpy())
+    assert np.array_equal(got_pairs, vox(refs[0], i1)), "joined voxels"
+    assert np.array_equal(gather_cat(torch.stack(res["table2"].voxel_coords())[:, res["i2"]].cpu().numpy()), vox(refs[1], i2)), "joined voxels (epoch 2)"
+    assert np.array_equal(gather_cat(torch.stack(res["table1"].voxel_coords())[:, res["only1"]].cpu().numpy()), vox(refs[0], only1)), "disappeared"
+    assert np.array_equal(gather_cat(torch.stack(res["table2"].voxel_coords())[:, res["only2"]].cpu().numpy()), vox(refs[1], only2)), "appeared"
+    empty = torch.empty(0, dtype=torch.float64, device=dev)
+    dd = gather_cat(res.get("distance", empty).cpu().numpy())
+    rd = ref["distance"].cpu().numpy()
+    assert np.all(np.abs(dd - rd) <= 1e-9 * np.abs(rd) + 1e-12), "distance"
+    p, pr = gather_cat(res.get("p_value", empty).cpu().numpy()), ref["p_value"].cpu().numpy()
+    assert np.array_equal(np.isnan(p), np.isnan(pr))
+    ct = gather_cat(res.get("change_type", torch.empty(0, dtype=torch.int32, device=dev)).cpu().numpy())
+    rct = ref["change_type"].cpu().numpy()
+    # classes are exact away from the alpha threshold and from p == 0 (covariances agree to 1e-9 only)
+    d1, r1 = gather_cat(res.get("d1", empty).cpu().numpy()), ref["d1"].cpu().numpy()
+    d2, r2 = gather_cat(res.get("d2", empty).cpu().numpy()), ref["d2"].cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        stable = (~np.isnan(pr) & (np.abs(pr - 0.005) > 1e-4) & (pr > 1e-300) & (np.abs(d1 - r1) <= 1e-6 * np.abs(r1))
+                  & (np.abs(d2 - r2) <= 1e-6 * np.abs(r2)))
+    assert stable.sum() > 1000, int(stable.sum())
+    assert np.array_equal(ct[stable], rct[stable]), "change_type"
+    assert np.all(np.abs(p[stable] - pr[stable]) <= 1e-5 * pr[stable] + 1e-12), "p_value"
+    if rank == 0:
+        print(f"[two-epoch] world={world}: {len(rd)} joined voxels, {len(only1)} disappeared, {len(only2)} appeared, "
+              f"{int((rct == 1).sum() + (rct == 2).sum())} significant", flush=True)
+
+
 def main():
     from vapc_b200 import dist as D
     from vapc_b200 import engine as E
@@ -57,6 +110,7 @@ def main():
             assert np.all(err <= 1e-9 * scale + 1e-18), (mode, name, float(np.max(err / scale)))
         if rank == 0:
             print(f"[{mode}, {exchange}] world={world}: owned voxels {allc}, partial rows sent by rank 0: {table.partial_rows_sent}", flush=True)
+    two_epoch(rank, world, dev, pts, rng, vs, origin)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

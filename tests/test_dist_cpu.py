@@ -100,6 +100,26 @@ def _worker(rank, world, port, ret):
         assert np.array_equal(mn.astype(np.int64), gc[sel].astype(np.int64))
         np.testing.assert_allclose(mm[:, :3], gm[sel][:, :3], rtol=0, atol=1e-12)
         np.testing.assert_allclose(mm[:, 3:], gm[sel][:, 3:], rtol=1e-9, atol=1e-15)
+        # second epoch over the SAME key ranges (D.two_epoch_change): destination counts from the given thresholds, the
+        # send-count matrix by one all-gather; afterwards the voxel join is local to the owner
+        pts2 = np.round(np.concatenate([pts[: n // 2] + rng.normal(0, 0.05, (n // 2, 3)), rng.uniform([10, 0, 0], [30, 20, 4], (n // 8, 3))]), 3)
+        pts2 = np.clip(pts2, pts.min(0), pts.max(0))  # same grid as epoch 1
+        mine2 = pts2[rank::world]
+        key2, cnt2, mom2 = partial_table(mine2[:, 0], mine2[:, 1], mine2[:, 2], vs, vmin, bits)
+        counts = D.destination_counts(torch.from_numpy(key2), torch.tensor(thresholds, dtype=torch.int64))
+        matrix = torch.empty(world * world, dtype=torch.int64)
+        dist.all_gather_into_tensor(matrix, counts)
+        matrix = matrix.view(world, world)
+        assert matrix[rank].tolist() == D.partition_counts(torch.from_numpy(key2), thresholds)
+        recv2, rc2 = D.exchange_rows({"keys": torch.from_numpy(key2), "count": torch.from_numpy(cnt2), "moments": torch.from_numpy(mom2)},
+                                     matrix[rank].tolist())
+        assert rc2 == matrix[:, rank].tolist()
+        k2, _, _ = chan_merge(recv2["keys"].numpy(), recv2["count"].numpy(), recv2["moments"].numpy())
+        assert np.all((k2 >= t[rank]) & (k2 < t[rank + 1]))
+        g2, _, _ = partial_table(pts2[:, 0], pts2[:, 1], pts2[:, 2], vs, vmin, bits)
+        joined_here = np.intersect1d(mk, k2)
+        joined_global = np.intersect1d(gk, g2)
+        assert np.array_equal(joined_here, joined_global[(joined_global >= t[rank]) & (joined_global < t[rank + 1])])
         ret[rank] = (len(mk), sum(send), sum(recv_counts), int(sel.sum()))
     finally:
         dist.destroy_process_group()

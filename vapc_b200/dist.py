@@ -268,7 +268,8 @@ def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: tor
     return out_keys, out_count, out_mean, out_m2
 
 
-def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer"):
+def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
+                     thresholds=None):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
@@ -276,14 +277,21 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     sorted local table is then re-keyed in the global layout (same order), splitters and destinations are planned on the
     device, only the rows that leave the rank are packed and exchanged (ONE all-to-all), and the owner merges its own rows
     (in place) with the received ones.  Five small device -> host copies synchronise the host: local bounds, local voxel
-    count, global bounds, the all-gathered send-count matrix, the merged voxel count."""
+    count, global bounds, the all-gathered send-count matrix, the merged voxel count.
+
+    bounds (optional): global coordinate bounds every rank already agrees on (no all-reduce); thresholds (optional): the
+    world - 1 key thresholds of an earlier table over the SAME grid — the rows are then sent to the owners of those key
+    ranges instead of re-balancing, so that two tables (two epochs) are range-aligned rank by rank (two_epoch_change)."""
     from . import _lib as L
     from . import engine as E
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = x.device
-    local_b, finish_bounds = start_bounds(x, y, z, group)
+    if bounds is None:
+        local_b, finish_bounds = start_bounds(x, y, z, group)
+    else:
+        local_b, finish_bounds = None, (lambda: bounds)
     local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=local_b, want_point2voxel=False, keep_columns=False)
     lg = local.grid
     g = E.grid_from_bounds(voxel_size, origin, finish_bounds())  # the key layout every rank agrees on
@@ -296,10 +304,20 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     L.call("vapc_global_keys", E._ptr(local.voxel_keys), v, C.byref(lg), C.byref(g), hb, E._ptr(gkeys), E._ptr(hist), E._stream())
     # ONE collective for the planning: with everybody's histogram every rank derives the splitters (global sum) AND the
     # complete send-count matrix (splitters lie on bin boundaries) in one small kernel; one copy tells the host
-    hist_all = torch.empty(world << hb, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(hist_all, hist, group=group)
-    plan = torch.empty(world * world + world - 1, dtype=torch.int64, device=dev)
-    L.call("vapc_plan_exchange", E._ptr(hist_all), world, hb, g.total_bits, E._ptr(plan), E._stream())
+    if thresholds is None:
+        hist_all = torch.empty(world << hb, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(hist_all, hist, group=group)
+        plan = torch.empty(world * world + world - 1, dtype=torch.int64, device=dev)
+        L.call("vapc_plan_exchange", E._ptr(hist_all), world, hb, g.total_bits, E._ptr(plan), E._stream())
+    else:
+        # given key ranges: this rank's destination counts from its sorted keys, all-gathered into the same matrix
+        th = torch.as_tensor(list(thresholds), dtype=torch.int64, device=dev)
+        if th.numel() != world - 1:
+            raise ValueError("thresholds must hold world - 1 keys")
+        counts = destination_counts(gkeys, th)
+        matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(matrix, counts, group=group)
+        plan = torch.cat([matrix, th])
     host = plan.cpu()
     matrix_h = host[: world * world].view(world, world)
     send_counts = matrix_h[rank].tolist()
@@ -358,3 +376,39 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
                               partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl")
     st = table.stats() if with_stats else None
     return table, st
+
+
+def two_epoch_change(epoch1: Sequence[torch.Tensor], epoch2: Sequence[torch.Tensor], voxel_size, origin=(0.0, 0.0, 0.0), alpha: float = 0.005,
+                     group=None, exchange="peer"):
+    """Multi-GPU form of the reference's two-epoch change detection (bi_vapc.py:40-47 centroid + covariance per voxel and
+    epoch, :78-84 inner join on the voxel triple, :25-36 anti-joins, :86-138 centroid distance + Mahalanobis test).
+
+    epoch1 / epoch2: this rank's (x, y, z) chunk of each epoch.  Both epochs are voxelised over ONE global grid (bounds
+    of both) and share ONE set of key ranges (planned on epoch 1), so every voxel of either epoch ends on the same owner:
+    the join and the test are local to the owner, no further communication.  Returns a dict for this rank's key range:
+    table1 / table2 (ShardedVoxelTable), i1 / i2 (rows of the joined voxels in the two tables, key order), only1 / only2
+    (rows occupied in one epoch only: change_type 3 / 4) and the joined rows' distance, d1, d2, p_value, significance,
+    change_type."""
+    from . import _lib as L
+    from . import engine as E
+
+    (_, fin1), (_, fin2) = start_bounds(*epoch1, group), start_bounds(*epoch2, group)
+    b1, b2 = fin1(), fin2()
+    gb = np.concatenate([np.minimum(b1[:3], b2[:3]), np.maximum(b1[3:], b2[3:])])
+    t1, _ = voxel_statistics(*epoch1, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb)
+    t2, _ = voxel_statistics(*epoch2, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb, thresholds=t1.thresholds)
+    dev = t1.voxel_keys.device
+    k1, k2 = keys_as_int64(t1.voxel_keys).contiguous(), keys_as_int64(t2.voxel_keys).contiguous()
+    m1 = torch.empty(t1.nvoxels, dtype=torch.int32, device=dev)
+    m2 = torch.empty(t2.nvoxels, dtype=torch.int32, device=dev)
+    L.call("vapc_join_sorted_keys", E._ptr(k1), t1.nvoxels, E._ptr(k2), t2.nvoxels, E._ptr(m1), E._ptr(m2), E._stream())
+    m1 = m1.to(torch.int64) & 0xFFFFFFFF
+    m2 = m2.to(torch.int64) & 0xFFFFFFFF
+    i1 = torch.nonzero(m1 != 0xFFFFFFFF).flatten()
+    out = dict(table1=t1, table2=t2, i1=i1, i2=m1[i1], only1=torch.nonzero(m1 == 0xFFFFFFFF).flatten(), only2=torch.nonzero(m2 == 0xFFFFFFFF).flatten())
+    only = dict(density=False, cog=True, std=False, cov=True, eig=False, eig_n=False, feat=False)
+    s1, s2 = t1.stats(**only), t2.stats(**only)
+    out["stats1"], out["stats2"] = s1, s2
+    if i1.numel():
+        out.update(E.mahalanobis(s1.cog, s1.cov, s2.cog, s2.cov, i1, out["i2"], alpha=alpha))
+    return out
