@@ -377,6 +377,12 @@ VAPC_API int vapc_merge_partial_rows(const void* keys_sorted, const uint32_t* or
                             int64_t local_first, int64_t n_local, int64_t nvoxels_host, void* voxel_keys,
                             uint32_t* count, double* mean3, double* m2, void* ws, size_t ws_bytes,
                             void* stream);
+/* Multi-GPU closest-to-centroid: every rank proposes, per partial voxel row, its nearest point to the FINAL
+ * centroid; the owner reduces the n candidates (rows[i] = merged voxel row, dist[i] >= 0, idx[i] = global point index >= 0)
+ * to the lexicographic minimum (distance, index) per row — the single-GPU tie-break "lowest original index".  Rows without a
+ * candidate keep best_dist = NaN (all-ones pattern) and best_idx = -1. */
+VAPC_API int vapc_reduce_candidates(const int64_t* rows, const double* dist, const int64_t* idx, int64_t n, int64_t nrows,
+                           double* best_dist, int64_t* best_idx, void* stream);
 /* histogram of the top `hist_bits` key bits (splitter selection) */
 VAPC_API int vapc_key_histogram(const void* keys, int64_t n, int32_t key_bytes, int32_t total_bits,
                        int32_t hist_bits, uint32_t* hist, void* stream);

@@ -65,6 +65,40 @@ def two_epoch(rank, world, dev, pts, rng, vs, origin):
               f"{int((rct == 1).sum() + (rct == 2).sum())} significant", flush=True)
 
 
+def per_point_outputs(rank, world, dev, pts, rng, vs, origin):
+    """Reverse exchange: per-point distance to the GLOBAL centroid, per-point broadcast of the global point count, and the
+    closest-to-centroid subsample over all ranks == the single-GPU results."""
+    from vapc_b200 import dist as D
+    from vapc_b200 import engine as E
+
+    n = len(pts)
+    cloud = pts[rng.permutation(n)]  # chunks of a shuffled cloud: every voxel is shared by several ranks
+    a, b = rank * n // world, (rank + 1) * n // world
+    x, y, z = (torch.from_numpy(np.ascontiguousarray(cloud[a:b, k])).to(dev) for k in range(3))
+    table, st, shard = D.voxel_statistics(x, y, z, vs, origin, keep_local=True)
+    ref = E.VoxelCloud.build(cloud[:, 0].copy(), cloud[:, 1].copy(), cloud[:, 2].copy(), vs, origin)
+    # per-point columns
+    dist_pt = D.point_distance(table, shard, st.cog).cpu().numpy()
+    ref_pt = ref.point_distance().cpu().numpy()[a:b]
+    assert np.all(np.abs(dist_pt - ref_pt) <= 1e-9 * ref_pt + 1e-12), "distance to the global centroid"
+    cnt_pt = D.broadcast_to_points(table, shard, table.count.to(torch.float64)[None, :])[0].cpu().numpy()
+    ref_cnt = ref.broadcast(ref.count).cpu().numpy()[a:b]
+    assert np.array_equal(cnt_pt.astype(np.int64), ref_cnt.astype(np.int64)), "global point_count per point"
+    # closest-to-centroid subsample
+    md, gi = D.closest_to_cog(table, shard, st.cog)
+    md, gi = gather_cat(md.cpu().numpy()), gather_cat(gi.cpu().numpy())
+    rmd, ram = ref.closest_to_cog()
+    rmd, ram = rmd.cpu().numpy(), (ram.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    assert len(md) == ref.nvoxels
+    assert np.all(np.abs(md - rmd) <= 1e-9 * rmd + 1e-12), "min_distance"
+    same = gi == ram
+    assert same.mean() > 0.999, float(same.mean())  # a last-bit centroid difference may flip an exact tie
+    cog = st.cog.cpu().numpy()
+    if rank == 0:
+        print(f"[per-point] world={world}: {len(md)} voxels, subsample identical for {int(same.sum())}, "
+              f"partial rows answered by owners: {sum(shard.send_remote)}", flush=True)
+
+
 def main():
     from vapc_b200 import dist as D
     from vapc_b200 import engine as E
@@ -111,6 +145,7 @@ def main():
         if rank == 0:
             print(f"[{mode}, {exchange}] world={world}: owned voxels {allc}, partial rows sent by rank 0: {table.partial_rows_sent}", flush=True)
     two_epoch(rank, world, dev, pts, rng, vs, origin)
+    per_point_outputs(rank, world, dev, pts, rng, vs, origin)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

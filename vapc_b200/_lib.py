@@ -122,6 +122,7 @@ SIGNATURES = {
     "vapc_global_keys": (C.c_int, [P, I64, GP, GP, I32, P, P, P]),
     "vapc_pack_partial_rows": (C.c_int, [P, P, P, P, I64, I64, I64, P, P]),
     "vapc_merge_partial_rows": (C.c_int, [P, P, I64, I32, P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, SZ, P]),
+    "vapc_reduce_candidates": (C.c_int, [P, P, P, I64, I64, P, P, P]),
     "vapc_key_histogram": (C.c_int, [P, I64, I32, I32, I32, P, P]),
     "vapc_laz_decode": (C.c_int, [P, I64, I64, I64, I32, I32, C.c_uint32, P, I32, P]),
     "vapc_selftest_eig3_host": (C.c_int, [P, I64, P]),

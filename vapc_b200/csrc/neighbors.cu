@@ -264,6 +264,27 @@ __global__ void __launch_bounds__(256) cluster_finish_kernel(uint32_t* parent, c
   atomicAdd(comp_size + r, (unsigned long long)(weight ? weight[i] : 1u));
 }
 
+
+// ---- (dist, index) candidates reduced per row: lexicographic minimum -------------------------------------------
+// Distances are >= 0, so their bit patterns order like the values: pass 1 atomicMin of the distance bits, pass 2
+// atomicMin of the index among the candidates that attain it.  Integer atomics only: the result does not depend
+// on the order of arrival.
+__global__ void __launch_bounds__(256) cand_init_kernel(unsigned long long* best_dist, unsigned long long* best_idx, long long nrows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) { best_dist[i] = ~0ull; best_idx[i] = ~0ull; }
+}
+__global__ void __launch_bounds__(256) cand_min_dist_kernel(const long long* __restrict__ rows, const double* __restrict__ dist, long long n,
+                                                            unsigned long long* best_dist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(best_dist + rows[i], (unsigned long long)__double_as_longlong(dist[i]));
+}
+__global__ void __launch_bounds__(256) cand_min_idx_kernel(const long long* __restrict__ rows, const double* __restrict__ dist,
+                                                           const long long* __restrict__ idx, long long n, const unsigned long long* __restrict__ best_dist,
+                                                           unsigned long long* best_idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (unsigned long long)__double_as_longlong(dist[i]) == best_dist[rows[i]]) atomicMin(best_idx + rows[i], (unsigned long long)idx[i]);
+}
+
 template <typename KeyT>
 CellList<KeyT> make_list(const vapc_grid_t* grid, const void* keys, int64_t ncells, const uint32_t* start, const uint32_t* pos,
                          const double* xyzw, int64_t n) {
@@ -385,5 +406,24 @@ extern "C" int vapc_selftest_cluster_host(const vapc_grid_t* grid_host, const vo
     cluster_host(make_list<unsigned long long>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n), distance, first, weight, root, hop2_first,
                  comp_first, comp_size, scratch, scratch + n);
   delete[] scratch;
+  return VAPC_OK;
+}
+
+extern "C" int vapc_reduce_candidates(const int64_t* rows, const double* dist, const int64_t* idx, int64_t n, int64_t nrows, double* best_dist,
+                                      int64_t* best_idx, void* stream) {
+  if (n < 0 || nrows < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_candidates: negative size");
+  if (nrows == 0) return VAPC_OK;
+  if (!best_dist || !best_idx || (n > 0 && (!rows || !dist || !idx))) return vapc_set_error(VAPC_E_INVALID, "vapc_reduce_candidates: null buffer");
+  cudaStream_t s = as_stream(stream);
+  unsigned long long* bd = reinterpret_cast<unsigned long long*>(best_dist);
+  unsigned long long* bi = reinterpret_cast<unsigned long long*>(best_idx);
+  VAPC_LAUNCH(cand_init_kernel, (unsigned)((nrows + 255) / 256), 256, 0, s, bd, bi, (long long)nrows);
+  VAPC_CHECK_LAUNCH();
+  if (n == 0) return VAPC_OK;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  VAPC_LAUNCH(cand_min_dist_kernel, blocks, 256, 0, s, reinterpret_cast<const long long*>(rows), dist, (long long)n, bd);
+  VAPC_CHECK_LAUNCH();
+  VAPC_LAUNCH(cand_min_idx_kernel, blocks, 256, 0, s, reinterpret_cast<const long long*>(rows), dist, reinterpret_cast<const long long*>(idx), (long long)n, bd, bi);
+  VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

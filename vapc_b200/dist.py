@@ -137,6 +137,21 @@ class ShardedVoxelTable:
         return c.voxel_coords()
 
 
+@dataclass
+class LocalShard:
+    """What a rank keeps of its own chunk so that columns of the merged table can be brought back to its partial rows and
+    points (voxel_statistics(..., keep_local=True))."""
+
+    cloud: object  # the rank's own VoxelCloud (own grid) incl. x, y, z and point2voxel
+    gkeys: torch.Tensor  # int64 [v]: global keys of the local partial rows (sorted)
+    lo: int  # local rows [lo, lo + n_own) are owned by this rank itself
+    n_own: int
+    send_remote: List[int]  # partial rows sent to every rank (0 for itself)
+    recv_remote: List[int]  # partial rows received from every rank (0 for itself)
+    recv_keys: torch.Tensor  # int64 [n_in]: keys of the received rows, grouped by source
+    group: object = None
+
+
 def plan_splitters_tensor(global_hist: torch.Tensor, world: int, total_bits: int, hist_bits: int = HIST_BITS) -> torch.Tensor:
     """plan_splitters on a tensor, on whatever device the histogram lives (no host round trip): int64 [world - 1]."""
     hb = min(hist_bits, max(total_bits, 1))
@@ -269,7 +284,7 @@ def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: tor
 
 
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
-                     thresholds=None):
+                     thresholds=None, keep_local=False):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
@@ -292,7 +307,7 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
         local_b, finish_bounds = start_bounds(x, y, z, group)
     else:
         local_b, finish_bounds = None, (lambda: bounds)
-    local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=local_b, want_point2voxel=False, keep_columns=False)
+    local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=local_b, want_point2voxel=keep_local, keep_columns=keep_local)
     lg = local.grid
     g = E.grid_from_bounds(voxel_size, origin, finish_bounds())  # the key layout every rank agrees on
     if g.total_bits > 63:
@@ -375,6 +390,11 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
                               thresholds=host[world * world:].tolist(), partial_rows_sent=int(sum(send_remote)),
                               partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl")
     st = table.stats() if with_stats else None
+    if keep_local:
+        # keep_local: a third value, the LocalShard for rows_from_owner / point_distance / closest_to_cog below
+        recv_keys = in_rows[:, 0].contiguous().view(torch.int64).clone() if n_in else torch.empty(0, dtype=torch.int64, device=dev)
+        return table, st, LocalShard(cloud=local, gkeys=gkeys, lo=lo, n_own=n_own, send_remote=send_remote, recv_remote=recv_remote,
+                                     recv_keys=recv_keys, group=group)
     return table, st
 
 
@@ -412,3 +432,79 @@ def two_epoch_change(epoch1: Sequence[torch.Tensor], epoch2: Sequence[torch.Tens
     if i1.numel():
         out.update(E.mahalanobis(s1.cog, s1.cov, s2.cog, s2.cov, i1, out["i2"], alpha=alpha))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# results of the merged table brought back to the ranks' own rows and points (the reverse exchange)
+# ------------------------------------------------------------------------------------------------
+def _owner_rows(table: ShardedVoxelTable, keys_i64: torch.Tensor) -> torch.Tensor:
+    """Rows of this rank's merged table holding the given (present) global keys."""
+    return torch.searchsorted(keys_as_int64(table.voxel_keys).contiguous(), keys_i64.contiguous())
+
+
+def rows_from_owner(table: ShardedVoxelTable, shard: LocalShard, columns: torch.Tensor) -> torch.Tensor:
+    """columns: [k, V_owned] fp64 columns of this rank's merged table (centroids, counts as fp64, ...).  Returns [k, v_local]:
+    the same columns for every LOCAL partial row, i.e. the values of the voxel the row was merged into.  Rows a rank owns
+    itself are looked up locally; for the rows it sent away the owners answer in ONE all-to-all of k doubles per partial
+    row — the reverse of the accumulator exchange."""
+    k = columns.shape[0]
+    dev = columns.device
+    reply = columns[:, _owner_rows(table, shard.recv_keys)].t().contiguous()  # [n_in, k], grouped by source
+    v = shard.gkeys.numel()
+    back = torch.empty((v - shard.n_own, k), dtype=torch.float64, device=dev)
+    dist.all_to_all_single(back, reply, output_split_sizes=shard.send_remote, input_split_sizes=shard.recv_remote, group=shard.group)
+    lo, hi = shard.lo, shard.lo + shard.n_own
+    own = columns[:, _owner_rows(table, shard.gkeys[lo:hi])]
+    return torch.cat([back[:lo].t(), own, back[lo:].t()], dim=1).contiguous()
+
+
+def broadcast_to_points(table: ShardedVoxelTable, shard: LocalShard, columns: torch.Tensor) -> torch.Tensor:
+    """[k, n_local_points]: merged-table columns for every point of this rank's chunk, original point order (the reference's
+    per-point broadcast, vapc.py:724-726, 843-850)."""
+    per_row = rows_from_owner(table, shard, columns)
+    return torch.stack([shard.cloud.broadcast(per_row[j].contiguous()) for j in range(per_row.shape[0])])
+
+
+def point_distance(table: ShardedVoxelTable, shard: LocalShard, cog: torch.Tensor) -> torch.Tensor:
+    """distance of every local point to the GLOBAL centroid of its voxel (vapc.py:776-795)."""
+    from . import _lib as L
+    from . import engine as E
+
+    c = shard.cloud
+    per_row = rows_from_owner(table, shard, cog)
+    out = torch.empty(c.n, dtype=torch.float64, device=cog.device)
+    L.call("vapc_point_distance", E._ptr(c.x), E._ptr(c.y), E._ptr(c.z), c.n, E._ptr(c.point2voxel), E._ptr(per_row), c.nvoxels, E._ptr(out), E._stream())
+    return out
+
+
+def closest_to_cog(table: ShardedVoxelTable, shard: LocalShard, cog: torch.Tensor, point_offset: Optional[int] = None):
+    """Closest-to-centroid subsample over all ranks (vapc.py:799-825, 1188-1195).  Every rank proposes, per partial row, its
+    nearest point to the voxel's FINAL centroid (vapc_closest_to_cog against the centroids rows_from_owner brought back);
+    ONE all-to-all sends the (distance, global point index) candidates of the rows that left to their owners, which keep the
+    lexicographic minimum (vapc_reduce_candidates): lowest global index among exactly tied points, as on one GPU.
+    point_offset: global index of this rank's first point (default: chunks numbered in rank order).
+    Returns (min_distance [V_owned] f64, global point index [V_owned] int64)."""
+    from . import _lib as L
+    from . import engine as E
+
+    c = shard.cloud
+    dev = cog.device
+    if point_offset is None:
+        sizes = torch.zeros(dist.get_world_size(shard.group), dtype=torch.int64, device=dev)
+        sizes[dist.get_rank(shard.group)] = c.n
+        dist.all_reduce(sizes, group=shard.group)
+        point_offset = int(sizes[: dist.get_rank(shard.group)].sum().item())
+    md, am = c.closest_to_cog(cog=rows_from_owner(table, shard, cog))
+    gidx = (am.to(torch.int64) & 0xFFFFFFFF) + point_offset
+    lo, hi = shard.lo, shard.lo + shard.n_own
+    cand = torch.stack([md, gidx.view(torch.float64)], dim=1)  # the index travels as a bit pattern
+    out_c = torch.cat([cand[:lo], cand[hi:]]).contiguous()
+    in_c = torch.empty((shard.recv_keys.numel(), 2), dtype=torch.float64, device=dev)
+    dist.all_to_all_single(in_c, out_c, output_split_sizes=shard.recv_remote, input_split_sizes=shard.send_remote, group=shard.group)
+    rows = torch.cat([_owner_rows(table, shard.gkeys[lo:hi]), _owner_rows(table, shard.recv_keys)]).contiguous()
+    d = torch.cat([md[lo:hi], in_c[:, 0]]).contiguous()
+    g = torch.cat([gidx[lo:hi], in_c[:, 1].contiguous().view(torch.int64)]).contiguous()
+    best_d = torch.empty(table.nvoxels, dtype=torch.float64, device=dev)
+    best_i = torch.empty(table.nvoxels, dtype=torch.int64, device=dev)
+    L.call("vapc_reduce_candidates", E._ptr(rows), E._ptr(d), E._ptr(g), rows.numel(), table.nvoxels, E._ptr(best_d), E._ptr(best_i), E._stream())
+    return best_d, best_i

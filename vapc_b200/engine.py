@@ -329,10 +329,11 @@ class VoxelCloud:
         L.call("vapc_voxel_center_corner", _ptr(self.voxel_keys), V, C.byref(self.grid), _ptr(c), _ptr(k), _stream())
         return c, k
 
-    def closest_to_cog(self):
-        """(min_distance [V] f64, argmin original point index [V] int32-as-uint32)."""
+    def closest_to_cog(self, cog: Optional[torch.Tensor] = None):
+        """(min_distance [V] f64, argmin original point index [V] int32-as-uint32).  cog ([3, V], optional): centroids to
+        measure against instead of this cloud's own (multi-GPU: the merged table's centroids of the rank's partial rows)."""
         V, dev = self.nvoxels, self.device
-        cog = self.stats(cog=True).cog
+        cog = self.stats(cog=True).cog if cog is None else cog.contiguous()
         md = _empty(V, torch.float64, dev)
         am = _empty(V, torch.int32, dev)
         L.call("vapc_closest_to_cog", _ptr(self.keys_sorted), _ptr(self.pos_sorted), self.n, self.grid.key_bytes, _ptr(self.xyzw), _ptr(cog), V,
