@@ -186,11 +186,13 @@ VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_so
 /* out[index[i]] = values[i] */
 VAPC_API int vapc_scatter_u32(const uint32_t* index, const uint32_t* values, int64_t n, uint32_t* out, void* stream);
 
-/* point -> voxel map in ORIGINAL point order through a direct-address table over the packed key space
- * (table[key] = voxel row).  For grids of <= 2^25 cells the table stays in the 126 MB L2 and this costs
- * 8 B/point of HBM traffic instead of the 64 B/point of the scattered writes that vapc_reduce_moments
- * does when given point2voxel.  keys_unsorted: the keys vapc_pack_keys_f64 wrote (keep them intact by
- * giving vapc_sort_pairs a keys_alt2 buffer).  table: scratch of vapc_point2voxel_table_bytes(). */
+/* point -> voxel map in ORIGINAL point order through a rank bitmap over the packed key space: per 32 cells
+ * {occupancy bits, row of the first occupied cell}, row(key) = first + popc(bits below the key's bit) — the rows
+ * are in key order, so a voxel's row is its rank among the occupied keys.  2^total_bits / 4 bytes (4 MB for 2^24
+ * cells): the lookups are cache hits and the pass costs 8 B/point of HBM traffic instead of the 64 B/point of the
+ * scattered writes that vapc_reduce_moments does when given point2voxel.  keys_unsorted: the keys vapc_pack_keys_f64
+ * wrote (keep them intact by giving vapc_sort_pairs a keys_alt2 buffer).  table: scratch of
+ * vapc_point2voxel_table_bytes() (zeroed by the call); 8-byte aligned; total_bits <= 32. */
 VAPC_API size_t vapc_point2voxel_table_bytes(int32_t total_bits);
 VAPC_API int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys,
                            int64_t nvoxels, int32_t key_bytes, int32_t total_bits, void* table,

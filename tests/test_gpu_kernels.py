@@ -224,6 +224,8 @@ def check_cloud(E, x, y, z, vs, origin, eig_faithful=False, bucketed=True):
 @pytest.mark.parametrize("kind,n,vs,origin", [
     ("uniform", 60000, 0.5, [0, 0, 0]),
     ("uniform", 200000, 0.1, [0, 0, 0]),
+    ("uniform", 150000, 0.02, [0, 0, 0]),       # 28 key bits: the largest grids that take the rank-bitmap point->voxel path
+    ("uniform", 150000, 0.01, [0, 0, 0]),       # 31 key bits in 32-bit keys: point->voxel by grouped scatter
     ("negative", 50000, 0.3, [1.5, -2.25, 0.3]),
     ("clustered", 120000, 0.25, [0, 0, 0]),
     ("clustered", 120000, 5.0, [0, 0, 0]),      # voxels far larger than a 1024-point tile: carry chains

@@ -132,8 +132,13 @@ struct TileSmem {
   unsigned scan_s[33];
   unsigned short seg_start[kSegTile + 2];  // [s] first tile position of local segment s; [nheads+1] = tile_n
   KeyT seg_key[kSegTile + 1];              // key of local segment s (s = 0: the continued voxel)
-  double x[kSegTile], y[kSegTile], z[kSegTile];
+  // coordinates of tile position p live at slot sw(p): threads store 4 consecutive positions each, i.e. lane l writes
+  // position 4 l + j — unpadded, a half-warp's 64-bit stores hit only 4 of the 16 bank pairs (4-way conflict, 8 wavefronts
+  // per store instead of 2: 5.6e7 of the kernel's 1.6e8 shared-memory wavefronts at 1e8 points, profiles/r1_d).  One pad
+  // slot per 16 positions makes 4 l + j + l / 4 distinct mod 16.
+  double x[kSegTile + kSegTile / 16], y[kSegTile + kSegTile / 16], z[kSegTile + kSegTile / 16];
 };
+__device__ __forceinline__ int sw(int p) { return p + (p >> 4); }
 
 // Common prologue: flags, scan, segment tables, voxel-table bookkeeping.
 // On return inc[j] = number of heads at tile positions <= this one (local segment id; 0 = continuation).
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
     const int p = threadIdx.x * kItems + j;
-    sm.x[p] = rec[j].x; sm.y[p] = rec[j].y; sm.z[p] = rec[j].z;
+    sm.x[sw(p)] = rec[j].x; sm.y[sw(p)] = rec[j].y; sm.z[sw(p)] = rec[j].z;
     rows[j] = first_row + inc[j] - 1u;  // inc == 0 -> first_row - 1: the continued voxel
     if (valid[j] && head[j]) {
       voxel_keys[rows[j]] = key[j];
@@ -245,10 +250,11 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     long long vx, vy, vz;
     unpack_key((unsigned long long)sm.seg_key[s], g, vx, vy, vz);
     const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
-    const double q0x = sm.x[a] - cx, q0y = sm.y[a] - cy, q0z = sm.z[a] - cz;
+    const double q0x = sm.x[sw(a)] - cx, q0y = sm.y[sw(a)] - cy, q0z = sm.z[sw(a)] - cz;
     double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
     for (int p = a + 1; p < b; ++p) {
-      const double dx = (sm.x[p] - cx) - q0x, dy = (sm.y[p] - cy) - q0y, dz = (sm.z[p] - cz) - q0z;
+      const int q = sw(p);
+      const double dx = (sm.x[q] - cx) - q0x, dy = (sm.y[q] - cy) - q0y, dz = (sm.z[q] - cz) - q0z;
       sx += dx; sy += dy; sz += dz;
       xx = fma(dx, dx, xx); xy = fma(dx, dy, xy); xz = fma(dx, dz, xz);
       yy = fma(dy, dy, yy); yz = fma(dy, dz, yz); zz = fma(dz, dz, zz);
@@ -362,30 +368,58 @@ __global__ void __launch_bounds__(kThreads) fixup_long_chains_kernel(const uint3
   }
 }
 
-// ---- point -> voxel map through a direct-address table (dense key spaces) ------------------------------------
-// table[key] = voxel row for every occupied key; p2v[i] = table[key_i] in ORIGINAL point order.  For key spaces
-// of <= 2^25 cells the table (<= 128 MB) lives in the 126 MB L2, so the per-point lookups cost no DRAM traffic,
-// unlike the scattered 4-byte writes of the in-kernel path (one 32-byte sector read-modify-write per point).
+// ---- point -> voxel map through a rank bitmap over the key space (dense key spaces) -------------------------
+// Voxel rows are in key order, so the row of an occupied key is its RANK among the occupied keys.  The table holds, per
+// 32 cells of the key space, {occupancy bits, row of the word's first occupied cell}: row(key) = first + popc(bits below
+// the key's bit).  8 bytes per 32 cells = 2^total_bits / 4 bytes — 4 MB for the 2^24 cells of the benchmark grid against
+// 64 MB for a row per cell (which fell out of the L2: 61 % hit rate, profiles/r1_d) — so the per-point lookups are cache
+// hits and the kernel streams keys in, rows out.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) p2v_fill_kernel(const KeyT* __restrict__ voxel_keys, int64_t nvox, uint32_t* __restrict__ table) {
+__global__ void __launch_bounds__(kThreads) p2v_fill_kernel(const KeyT* __restrict__ voxel_keys, int64_t nvox, uint2* __restrict__ table) {
+  const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += stride) table[voxel_keys[v]] = (uint32_t)v;
+  const int64_t rounds = (nvox + stride - 1) / stride;
+  for (int64_t it = 0; it < rounds; ++it) {  // whole warps iterate together (shuffles below)
+    const int64_t v = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = v < nvox;
+    const KeyT k = valid ? voxel_keys[v] : (KeyT)0;
+    const KeyT w = valid ? (KeyT)(k >> 5) : (KeyT)~(KeyT)0;  // no valid word is all ones
+    unsigned bits = valid ? 1u << ((unsigned)k & 31u) : 0u;
+    // the keys are sorted: the voxels of a word are neighbouring lanes.  Segmented OR scan, one atomic per run.
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned b2 = __shfl_up_sync(0xffffffffu, bits, o);
+      const KeyT w2 = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o && w2 == w) bits |= b2;
+    }
+    const KeyT wn = __shfl_down_sync(0xffffffffu, w, 1);
+    if (valid && (lane == 31 || wn != w)) atomicOr(&table[w].x, bits);      // the occupancy words are zeroed by the caller
+    if (valid && (v == 0 || (voxel_keys[v - 1] >> 5) != w)) table[w].y = (unsigned)v;  // the first voxel of a word names its row
+  }
 }
-// Four keys per thread and iteration: the table lookups are L2 hits (~300 cycles), so what matters is how many are in
-// flight.
+__device__ __forceinline__ uint32_t p2v_row(const uint2* __restrict__ table, unsigned long long key) {
+  const uint2 t = __ldg(table + (key >> 5));
+  return t.y + (uint32_t)__popc(t.x & ((1u << ((unsigned)key & 31u)) - 1u));
+}
+// Four keys per thread and iteration: what matters is how many lookups are in flight.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) p2v_lookup_kernel(const KeyT* __restrict__ keys, int64_t n, const uint32_t* __restrict__ table,
+__global__ void __launch_bounds__(kThreads) p2v_lookup_kernel(const KeyT* __restrict__ keys, int64_t n, const uint2* __restrict__ table,
                                                               uint32_t* __restrict__ p2v) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(p2v)) & 15u) == 0 && sizeof(KeyT) == 4;
   const int64_t nvec = vec ? n / 4 : 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += stride) {
     const uint4 k = __ldcs(reinterpret_cast<const uint4*>(keys) + q);
+    const uint2 a = __ldg(table + (k.x >> 5)), b = __ldg(table + (k.y >> 5)), c = __ldg(table + (k.z >> 5)), d = __ldg(table + (k.w >> 5));
     uint4 r;
-    r.x = __ldg(table + k.x); r.y = __ldg(table + k.y); r.z = __ldg(table + k.z); r.w = __ldg(table + k.w);
+    r.x = a.y + (uint32_t)__popc(a.x & ((1u << (k.x & 31u)) - 1u));
+    r.y = b.y + (uint32_t)__popc(b.x & ((1u << (k.y & 31u)) - 1u));
+    r.z = c.y + (uint32_t)__popc(c.x & ((1u << (k.z & 31u)) - 1u));
+    r.w = d.y + (uint32_t)__popc(d.x & ((1u << (k.w & 31u)) - 1u));
     __stcs(reinterpret_cast<uint4*>(p2v) + q, r);
   }
-  for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p2v[i] = __ldg(table + __ldcs(keys + i));
+  for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    p2v[i] = p2v_row(table, (unsigned long long)__ldcs(keys + i));
 }
 
 // point2voxel[index[i]] = row[i].  Called with (index, row) pairs grouped by the leading bits of the index, so that the writes
@@ -423,7 +457,7 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
     const int p = threadIdx.x * kItems + j;
     if (p0 + j < n) {
       const double4 r = ld_record(xyzw + pos_sorted[p0 + j]);
-      sm.x[p] = r.x; sm.y[p] = r.y; sm.z[p] = r.z;
+      sm.x[sw(p)] = r.x; sm.y[sw(p)] = r.y; sm.z[sw(p)] = r.z;
       idx_s[p] = record_index(r);
     }
   }
@@ -438,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
     double best = INFINITY;
     uint32_t best_i = 0xffffffffu;
     for (int p = a; p < b; ++p) {
-      const double d = ref_distance(sm.x[p], sm.y[p], sm.z[p], cx, cy, cz);
+      const double d = ref_distance(sm.x[sw(p)], sm.y[sw(p)], sm.z[sw(p)], cx, cy, cz);
       if (d < best || best_i == 0xffffffffu) { best = d; best_i = idx_s[p]; }  // strict <: first (lowest index) wins ties
     }
     if (s >= 1) {
@@ -678,7 +712,7 @@ extern "C" int vapc_scatter_u32(const uint32_t* index, const uint32_t* values, i
 }
 
 extern "C" size_t vapc_point2voxel_table_bytes(int32_t total_bits) {
-  return total_bits < 0 || total_bits > 32 ? 0 : (sizeof(uint32_t) << total_bits);
+  return total_bits < 0 || total_bits > 32 ? 0 : (sizeof(uint2) << (total_bits > 5 ? total_bits - 5 : 0));
 }
 
 extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys, int64_t nvoxels, int32_t key_bytes,
@@ -689,14 +723,15 @@ extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, cons
   cudaStream_t s = as_stream(stream);
   const int g1 = (int)std::min<int64_t>((nvoxels + kThreads - 1) / kThreads, (int64_t)kNumSMs * 16);
   const int g2 = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16);
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(table, 0, vapc_point2voxel_table_bytes(total_bits), s));
   if (key_bytes == 4) {
-    VAPC_LAUNCH(p2v_fill_kernel<uint32_t>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const uint32_t*>(voxel_keys), nvoxels, static_cast<uint32_t*>(table));
+    VAPC_LAUNCH(p2v_fill_kernel<uint32_t>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const uint32_t*>(voxel_keys), nvoxels, static_cast<uint2*>(table));
     VAPC_LAUNCH(p2v_lookup_kernel<uint32_t>, g2 < 1 ? 1 : g2, kThreads, 0, s, static_cast<const uint32_t*>(keys_unsorted), n,
-                static_cast<const uint32_t*>(table), point2voxel);
+                static_cast<const uint2*>(table), point2voxel);
   } else if (key_bytes == 8) {
     typedef unsigned long long K;
-    VAPC_LAUNCH(p2v_fill_kernel<K>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const K*>(voxel_keys), nvoxels, static_cast<uint32_t*>(table));
-    VAPC_LAUNCH(p2v_lookup_kernel<K>, g2 < 1 ? 1 : g2, kThreads, 0, s, static_cast<const K*>(keys_unsorted), n, static_cast<const uint32_t*>(table),
+    VAPC_LAUNCH(p2v_fill_kernel<K>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const K*>(voxel_keys), nvoxels, static_cast<uint2*>(table));
+    VAPC_LAUNCH(p2v_lookup_kernel<K>, g2 < 1 ? 1 : g2, kThreads, 0, s, static_cast<const K*>(keys_unsorted), n, static_cast<const uint2*>(table),
                 point2voxel);
   } else {
     return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_dense: key_bytes must be 4 or 8");

@@ -168,7 +168,7 @@ def _tune_device(device):
             L.call("vapc_set_l2_fetch_granularity", g)
 
 
-DENSE_P2V_MAX_BITS = 25  # direct-address point->voxel table of <= 128 MB stays L2-resident on B200
+DENSE_P2V_MAX_BITS = 29  # rank-bitmap point->voxel table: 2^bits / 4 bytes, <= 128 MB stays L2-resident on B200
 
 
 @dataclass
