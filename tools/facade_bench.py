@@ -38,7 +38,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "profile":
     pr = cProfile.Profile()
     pr.enable()
     v.compute_requested_attributes()
-    v.return_at = "center_of_voxel"
+    v.return_at = sys.argv[3] if len(sys.argv) > 3 else "center_of_voxel"
+    pr.disable()
+    pr = cProfile.Profile()  # profile the reduction alone
+    pr.enable()
     v.reduce_to_voxels()
     torch.cuda.synchronize()
     pr.disable()

@@ -89,6 +89,9 @@ class Vapc:
         self.closest_ties = "all"
         self._cloud = None
         self._cloud_sig = None
+        # name -> ([V] device column, cloud it belongs to): per-voxel columns this class broadcast into the frame itself;
+        # reduce_to_voxels takes them from the device instead of gathering N-row host columns
+        self._voxel_cols = {}
 
     # ------------------------------------------------------------------------------------
     # device cloud cache
@@ -110,6 +113,7 @@ class Vapc:
             raise AttributeError("no point cloud loaded: assign `df` or call get_data_from_data_handler()")
         sig = self._signature()
         if self._cloud is None or sig != self._cloud_sig:
+            self._voxel_cols = {}
             self._cloud = E.VoxelCloud.build(self.df["X"].to_numpy(np.float64), self.df["Y"].to_numpy(np.float64),
                                              self.df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
             self._cloud_sig = sig
@@ -126,7 +130,26 @@ class Vapc:
 
     def _set_per_point(self, name: str, voxel_column: torch.Tensor):
         """df[name] = the [V] voxel column broadcast to the points."""
-        self._set_col(name, self._get_cloud().broadcast(voxel_column.contiguous()))
+        cloud = self._get_cloud()
+        self._set_col(name, cloud.broadcast(voxel_column.contiguous()))
+        self._voxel_cols[name] = (voxel_column, cloud)
+
+    def _voxel_column(self, name: str, cloud, probe_rows: np.ndarray, probe_voxels: torch.Tensor):
+        """The [V] device column behind the per-point frame column `name`, if this class put it there for `cloud` and the
+        frame still shows it (a few probed rows are compared bit for bit: callers own `df` and may have rewritten it)."""
+        hit = self._voxel_cols.get(name)
+        if hit is None or hit[1] is not cloud or cloud is None:
+            return None
+        col = hit[0]
+        if col.dtype != torch.float64 or col.numel() != cloud.nvoxels:
+            return None
+        a = self.df[name].to_numpy()
+        if a.dtype != np.float64 or len(a) != cloud.n:
+            return None
+        want = col[probe_voxels].cpu().numpy()
+        if not np.array_equal(a[probe_rows].view(np.int64), want.view(np.int64)):
+            return None
+        return col
 
     _pinned = {}  # (dtype, device index) -> reusable pinned staging buffer
 
@@ -287,9 +310,12 @@ class Vapc:
                     print(f"Unknown aggregation type '{stat}' for attribute '{attr}'. Skipping.")
         # the reference merges the aggregated frame back with how="left" (index reset, vapc.py:468-470)
         self.df = self.df.reset_index(drop=True)
+        self._resign()  # same points in a new frame object: keep the device cloud
         p2v = _u32(cloud.point2voxel)
         for col, table in new_cols.items():
             self.df[col] = table[p2v].cpu().numpy()
+            if table.dtype == torch.float64:
+                self._voxel_cols[col] = (table, cloud)
         self.attributes_per_voxel = True
         self._cloud_sig = self._signature()
 
@@ -329,6 +355,7 @@ class Vapc:
         self.df["X"] = (self.df["voxel_x"] + self.voxel_size / 2) * self.voxel_size
         self.buffer_df = self.df
         self._cloud = None
+        self._voxel_cols = {}
         return self.df
 
     def _mask_voxels(self, vapc_mask):
@@ -364,6 +391,7 @@ class Vapc:
                 self.df = self.df.drop([attr], axis=1)
         self.voxelized = False
         self._cloud = None
+        self._voxel_cols = {}
 
     @trace
     @timeit
@@ -378,6 +406,7 @@ class Vapc:
                 self.df = self.df.drop([attr], axis=1)
         self.voxelized = False
         self._cloud = None
+        self._voxel_cols = {}
 
     # ------------------------------------------------------------------------------------
     @trace
@@ -439,6 +468,7 @@ class Vapc:
         min_dist, argmin = cloud.closest_to_cog()
         self._closest_argmin = _u32(argmin)
         self.df = self.df.reset_index(drop=True)
+        self._resign()  # same points in a new frame object: keep the device cloud
         self._set_per_point("min_distance", min_dist)
         self.closest_to_center_of_gravity = True
         self._cloud_sig = self._signature()
@@ -510,6 +540,7 @@ class Vapc:
         six = [self._per_point(cov[k]) for k in range(6)]
         for name, k in zip(_COV_NAMES, _COV9_FROM6):
             self.df[name] = six[k]
+            self._voxel_cols[name] = (cov[k], cloud)
         other = [c for c in self.df.columns if c not in _COV_NAMES]
         self.df = self.df[_COV_NAMES + other]
         self.covariance_matrix_computed = True
@@ -527,6 +558,7 @@ class Vapc:
         cloud = self._get_cloud()
         eig = cloud.stats(eig=True).eig
         self.df = self.df.reset_index(drop=True)
+        self._resign()  # same points in a new frame object: keep the device cloud
         for k, name in enumerate(("Eigenvalue_1", "Eigenvalue_2", "Eigenvalue_3")):
             self._set_per_point(name, eig[k])
         self.eigenvalues = True
@@ -604,22 +636,42 @@ class Vapc:
             return a if sel is None else a[sel]
 
         rows = E.lexsort_unique_rows(xyz("X"), xyz("Y"), xyz("Z"))
-        final = torch.from_numpy(rows if sel is None else sel[rows])  # source row of every output row
-        out = {}
-        for c in ["X", "Y", "Z"] + [c for c in self.df.columns if c not in ("X", "Y", "Z")]:
-            if c in dropped:
-                continue
+        final_np = rows if sel is None else sel[rows]  # source row of every output row
+        final = torch.from_numpy(final_np)
+        names = [c for c in ["X", "Y", "Z"] + [c for c in self.df.columns if c not in ("X", "Y", "Z")] if c not in dropped]
+        keep = []
+        for c in names:
             src = self.df[self.new_column_names.get(c, c)]
             if c in ("X", "Y", "Z") or pd.api.types.is_bool_dtype(src.dtype) or pd.api.types.is_numeric_dtype(src.dtype):
-                a = np.ascontiguousarray(src.to_numpy())
-                if a.dtype not in (np.float64, np.float32, np.int64, np.int32, np.int16, np.int8, np.uint8):
-                    a = a.astype(np.float64)  # bool, unsigned 16 / 32 / 64 bit: not gatherable through torch
-                with warnings.catch_warnings():
-                    warnings.simplefilter("ignore")  # read-only numpy views are only read here
-                    out[c] = torch.from_numpy(a).index_select(0, final).numpy().astype(np.float64, copy=False)  # multi-threaded gather
-        self.df = pd.DataFrame(out)
+                keep.append(c)
+        # columns this class broadcast from the voxel table come straight from the device ([V] column -> output rows); the
+        # others (original attributes: the value of the voxel's first point) are gathered from the N-row host columns.  All
+        # outputs are float64, written into one block that the frame wraps without the copy pandas makes when it
+        # consolidates 39 separate columns.
+        cloud = self._cloud if self._cloud is not None and len(self.df) == self._cloud.n and self._cloud.point2voxel is not None else None
+        out_voxel = probe_rows = probe_voxels = None
+        if cloud is not None and len(final_np):
+            p2v = _u32(cloud.point2voxel)
+            out_voxel = p2v[final.to(p2v.device)]
+            probe_rows = final_np[np.linspace(0, len(final_np) - 1, num=min(256, len(final_np)), dtype=np.int64)]
+            probe_voxels = p2v[torch.from_numpy(probe_rows).to(p2v.device)]
+        block = np.empty((len(keep), len(final_np)), dtype=np.float64)
+        for i, c in enumerate(keep):
+            srcname = self.new_column_names.get(c, c)
+            vcol = self._voxel_column(srcname, cloud, probe_rows, probe_voxels) if out_voxel is not None else None
+            if vcol is not None:
+                block[i] = self._host(vcol[out_voxel])
+                continue
+            a = np.ascontiguousarray(self.df[srcname].to_numpy())
+            if a.dtype not in (np.float64, np.float32, np.int64, np.int32, np.int16, np.int8, np.uint8):
+                a = a.astype(np.float64)  # bool, unsigned 16 / 32 / 64 bit: not gatherable through torch
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # read-only numpy views are only read here
+                block[i] = torch.from_numpy(a).index_select(0, final).numpy()  # multi-threaded gather
+        self.df = pd.DataFrame(block.T, columns=keep, copy=False)
         self.reduced = True
         self._cloud = None
+        self._voxel_cols = {}
 
     @trace
     @timeit
@@ -644,6 +696,7 @@ class Vapc:
         else:
             raise ValueError(f"Filter invalid, use only one of the following:\n\n{', '.join(valid_strings)}.")
         self._cloud = None
+        self._voxel_cols = {}
 
     def compute_mode_count(self, attribute: str, percentage: float):
         """Convenience alias named by the north_star: the statistic string "mode_count,<p>" of the
@@ -681,5 +734,6 @@ class Vapc:
         # np.zeros_like(df[cluster_by[0]]) holds the ids; the sizes come back through a merge (index reset)
         self.df["cluster_id"] = self._host(label).astype(dtype0)
         self.df = self.df.reset_index(drop=True)
+        self._resign()  # same points in a new frame object: keep the device cloud
         self.df["cluster_size"] = self._host(size).astype(np.result_type(dtype0, np.int64))
         self._resign()
