@@ -137,7 +137,11 @@ struct TileSmem {
   // per store instead of 2: 5.6e7 of the kernel's 1.6e8 shared-memory wavefronts at 1e8 points, profiles/r1_d).  One pad
   // slot per 16 positions makes 4 l + j + l / 4 distinct mod 16.
   double x[kSegTile + kSegTile / 16], y[kSegTile + kSegTile / 16], z[kSegTile + kSegTile / 16];
+  // local segments of >= kLongSeg points are not walked by one thread but handed to a warp each
+  unsigned n_long;
+  unsigned short long_seg[kSegTile / 64 + 2];
 };
+constexpr int kLongSeg = 64;
 __device__ __forceinline__ int sw(int p) { return p + (p >> 4); }
 
 // Common prologue: flags, scan, segment tables, voxel-table bookkeeping.
@@ -241,12 +245,40 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[nvox] = (uint32_t)n;
+  if (threadIdx.x == 0) sm.n_long = 0;
   __syncthreads();
 
-  // one thread per local segment
+  // sums about the segment's first point q0 -> (n, mean of p - c, M2) -> voxel row, or the tile's carry slot for s == 0
+  auto emit = [&](unsigned s, int cnt, double q0x, double q0y, double q0z, double sx, double sy, double sz, double xx, double xy, double xz,
+                  double yy, double yz, double zz) {
+    const double inv = 1.0 / (double)cnt;
+    const double mx = sx * inv, my = sy * inv, mz = sz * inv;  // mean of d
+    double out[9];
+    out[0] = q0x + mx; out[1] = q0y + my; out[2] = q0z + mz;
+    out[3] = fma(-sx, mx, xx); out[4] = fma(-sx, my, xy); out[5] = fma(-sx, mz, xz);
+    out[6] = fma(-sy, my, yy); out[7] = fma(-sy, mz, yz); out[8] = fma(-sz, mz, zz);
+    if (s >= 1) {
+      const int64_t row = (int64_t)first_row + s - 1;
+      count[row] = (uint32_t)cnt;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = out[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = out[3 + k];
+    } else {
+      double* c = carry + (int64_t)blockIdx.x * 10;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] = out[k];
+      carry_cnt[blockIdx.x] = (uint32_t)cnt;
+    }
+  };
+  // one thread per local segment; segments of >= kLongSeg points (large voxels) are queued for a warp each
   for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
     const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
     if (b <= a) continue;  // only s == 0 can be empty (tile starts with a head)
+    if (b - a >= kLongSeg) {
+      sm.long_seg[atomicAdd(&sm.n_long, 1u)] = (unsigned short)s;
+      continue;
+    }
     long long vx, vy, vz;
     unpack_key((unsigned long long)sm.seg_key[s], g, vx, vy, vz);
     const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
@@ -259,24 +291,35 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
       xx = fma(dx, dx, xx); xy = fma(dx, dy, xy); xz = fma(dx, dz, xz);
       yy = fma(dy, dy, yy); yz = fma(dy, dz, yz); zz = fma(dz, dz, zz);
     }
-    const double inv = 1.0 / (double)(b - a);
-    const double mx = sx * inv, my = sy * inv, mz = sz * inv;  // mean of d
-    double out[9];
-    out[0] = q0x + mx; out[1] = q0y + my; out[2] = q0z + mz;
-    out[3] = fma(-sx, mx, xx); out[4] = fma(-sx, my, xy); out[5] = fma(-sx, mz, xz);
-    out[6] = fma(-sy, my, yy); out[7] = fma(-sy, mz, yz); out[8] = fma(-sz, mz, zz);
-    if (s >= 1) {
-      const int64_t row = (int64_t)first_row + s - 1;
-      count[row] = (uint32_t)(b - a);
+    emit(s, b - a, q0x, q0y, q0z, sx, sy, sz, xx, xy, xz, yy, yz, zz);
+  }
+  __syncthreads();
+  // long segments: lane l sums points a + 1 + l, a + 1 + l + 32, ...; the nine sums are folded with a fixed xor butterfly
+  // (every lane ends with the same bits), so the result does not depend on scheduling
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nl = sm.n_long;
+    for (unsigned i = warp; i < nl; i += kThreads / 32) {
+      const unsigned s = sm.long_seg[i];
+      const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
+      long long vx, vy, vz;
+      unpack_key((unsigned long long)sm.seg_key[s], g, vx, vy, vz);
+      const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
+      const double q0x = sm.x[sw(a)] - cx, q0y = sm.y[sw(a)] - cy, q0z = sm.z[sw(a)] - cz;
+      double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = a + 1 + lane; p < b; p += 32) {
+        const int q = sw(p);
+        const double dx = (sm.x[q] - cx) - q0x, dy = (sm.y[q] - cy) - q0y, dz = (sm.z[q] - cz) - q0z;
+        v[0] += dx; v[1] += dy; v[2] += dz;
+        v[3] = fma(dx, dx, v[3]); v[4] = fma(dx, dy, v[4]); v[5] = fma(dx, dz, v[5]);
+        v[6] = fma(dy, dy, v[6]); v[7] = fma(dy, dz, v[7]); v[8] = fma(dz, dz, v[8]);
+      }
 #pragma unroll
-      for (int k = 0; k < 3; ++k) mean3[(int64_t)k * nvox + row] = out[k];
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) m2[(int64_t)k * nvox + row] = out[3 + k];
-    } else {
-      double* c = carry + (int64_t)blockIdx.x * 10;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) c[k] = out[k];
-      carry_cnt[blockIdx.x] = (uint32_t)(b - a);
+        for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      }
+      if (lane == 0) emit(s, b - a, q0x, q0y, q0z, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
     }
   }
   // tiles that start with a head have no carry
@@ -463,10 +506,27 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
   }
   tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
   const uint32_t first_row = tile_first[blockIdx.x];
+  if (threadIdx.x == 0) sm.n_long = 0;
   __syncthreads();
+  auto emit = [&](unsigned s, int cnt, double best, uint32_t best_i) {
+    if (s >= 1) {
+      const int64_t row = (int64_t)first_row + s - 1;
+      min_dist[row] = best;
+      argmin_idx[row] = best_i;
+    } else {
+      double* c = carry + (int64_t)blockIdx.x * 10;
+      c[0] = best;
+      c[1] = __longlong_as_double((long long)best_i);
+      carry_cnt[blockIdx.x] = (uint32_t)cnt;
+    }
+  };
   for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
     const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
     if (b <= a) continue;
+    if (b - a >= kLongSeg) {  // large voxels: a warp each, below
+      sm.long_seg[atomicAdd(&sm.n_long, 1u)] = (unsigned short)s;
+      continue;
+    }
     const int64_t row = (int64_t)first_row + s - 1;  // s == 0: first_row - 1 (continued voxel)
     const double cx = cog3[row], cy = cog3[nvox + row], cz = cog3[2 * nvox + row];
     double best = INFINITY;
@@ -475,14 +535,31 @@ __global__ void __launch_bounds__(kThreads) closest_kernel(const KeyT* __restric
       const double d = ref_distance(sm.x[sw(p)], sm.y[sw(p)], sm.z[sw(p)], cx, cy, cz);
       if (d < best || best_i == 0xffffffffu) { best = d; best_i = idx_s[p]; }  // strict <: first (lowest index) wins ties
     }
-    if (s >= 1) {
-      min_dist[row] = best;
-      argmin_idx[row] = best_i;
-    } else {
-      double* c = carry + (int64_t)blockIdx.x * 10;
-      c[0] = best;
-      c[1] = __longlong_as_double((long long)best_i);
-      carry_cnt[blockIdx.x] = (uint32_t)(b - a);
+    emit(s, b - a, best, best_i);
+  }
+  __syncthreads();
+  {
+    // lexicographic minimum of (distance, tile position) over the lanes: the same winner as the sequential walk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nl = sm.n_long;
+    for (unsigned i = warp; i < nl; i += kThreads / 32) {
+      const unsigned s = sm.long_seg[i];
+      const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
+      const int64_t row = (int64_t)first_row + s - 1;
+      const double cx = cog3[row], cy = cog3[nvox + row], cz = cog3[2 * nvox + row];
+      double best = INFINITY;
+      int best_p = 0x7fffffff;
+      for (int p = a + lane; p < b; p += 32) {
+        const double d = ref_distance(sm.x[sw(p)], sm.y[sw(p)], sm.z[sw(p)], cx, cy, cz);
+        if (d < best || best_p == 0x7fffffff) { best = d; best_p = p; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, best_p, o);
+        if (op != 0x7fffffff && (best_p == 0x7fffffff || od < best || (od == best && op < best_p))) { best = od; best_p = op; }
+      }
+      if (lane == 0) emit(s, b - a, best, idx_s[best_p]);
     }
   }
   if (threadIdx.x == 0 && sm.seg_start[1] == 0 && nheads > 0) carry_cnt[blockIdx.x] = 0;
