@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=100_000_000, help="points per GPU")
+    ap.add_argument("--no-las-e2e", action="store_true", help="skip the LAS-integer-input variant of the e2e measurement")
     ap.add_argument("--impl", default="vapc_b200", choices=["vapc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -447,6 +448,28 @@ def main():
                       "copies its X, Y, Z from pinned host memory and its complete voxel table back to pinned host memory; H2D of step k+1, "
                       "compute of step k and D2H of step k-1 overlap on three streams; wall clock over all steps incl. pipeline fill and "
                       "drain, max over ranks"}
+
+        # the same cloud as the int32 coordinates of a LAS file (scale 1e-4, offset 0): 12 B/point over PCIe; reported next to e2e
+        if world == 1 and not args.no_las_e2e:
+            lasq = [torch.round(c / QUANT).to(torch.int32) for c in (hx, hy, hz)]
+            assert all(bool((q.to(torch.float64) * QUANT + 0.0 == c).all()) for q, c in zip(lasq, (hx, hy, hz))), "not the same cloud"
+            lasq = [q.pin_memory() for q in lasq]
+            del hx, hy, hz
+            lpipe = HostStreamPipeline(VOXEL_SIZE, ORIGIN, device, las=([QUANT] * 3, [0.0] * 3))
+            for _res in lpipe.run([tuple(lasq)] * 2):
+                pass
+            torch.cuda.synchronize()
+            lpipe.h2d_bytes = lpipe.d2h_bytes = 0
+            t0 = time.perf_counter()
+            for _res in lpipe.run([tuple(lasq)] * e_steps):
+                pass
+            torch.cuda.synchronize()
+            windows.append([t0, time.perf_counter()])
+            ldt = (windows[-1][1] - t0) / e_steps
+            e2e["las_int32"] = {"value": n / ldt, "unit": UNIT, "ms_per_step": ldt * 1e3, "h2d_bytes_per_step": lpipe.h2d_bytes // e_steps,
+                                "d2h_bytes_per_step": lpipe.d2h_bytes // e_steps,
+                                "what": "the same cloud entering as the int32 X, Y, Z of a LAS file (scale 1e-4, offset 0; identical doubles, "
+                                        "identical voxel table): vapc_pack_records_bucketed_i32 forms X * scale + offset in the key kernels"}
 
     clocks = sampler.stop(windows)
 

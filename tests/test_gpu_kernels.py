@@ -514,3 +514,30 @@ def test_host_stream_pipeline_matches_direct(E):
             a, b = res[name], getattr(st, name).cpu()
             assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), name
     assert pipe.h2d_bytes == sum(3 * 8 * len(c[0]) for c in clouds)
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,scales,offsets,vs", [(200_000, [1e-4, 1e-4, 1e-4], [0.0, 0.0, 0.0], 0.1),
+                                                 (150_001, [0.00025, 0.00025, 0.001], [476850.0, 5429100.0, 312.0], 0.25),
+                                                 (70_000, [0.01, 0.01, 0.01], [-500.0, 20.0, -3.0], 0.05)])
+def test_las_integer_input_is_bit_identical(E, n, scales, offsets, vs):
+    """The cloud as int32 LAS coordinates (12 B/point) gives the same bits as its float64 columns X * scale + offset
+    (what laspy hands the reference, datahandler.py:72-95): coordinates, keys, every row and moment of the voxel table."""
+    rng = np.random.default_rng(n)
+    q = [rng.integers(-2_000_000, 2_000_000, n).astype(np.int32), rng.integers(0, 1_500_000, n).astype(np.int32),
+         rng.integers(-30_000, 90_000, n).astype(np.int32)]
+    cols = [a.astype(np.float64) * s + o for a, s, o in zip(q, scales, offsets)]  # numpy: two rounded operations
+    dev = [_np(t) for t in E.las_coordinates(*q, scales, offsets)]
+    for a, b in zip(dev, cols):
+        np.testing.assert_array_equal(a.view(np.int64), b.view(np.int64))
+    origin = [offsets[0], offsets[1] - 1.0, 0.0]
+    ref = E.VoxelCloud.build(*cols, vs, origin)
+    got = E.VoxelCloud.build(None, None, None, vs, origin, las=(*q, scales, offsets))
+    assert got.nvoxels == ref.nvoxels and got.grid.total_bits == ref.grid.total_bits and list(got.grid.vmin) == list(ref.grid.vmin)
+    for name in ("voxel_keys", "start", "count", "first_idx", "mean3", "m2", "point2voxel", "idx_sorted", "x", "y", "z"):
+        a, b = getattr(got, name), getattr(ref, name)
+        assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b), name
+    lean = E.VoxelCloud.build(None, None, None, vs, origin, las=(*q, scales, offsets), keep_columns=False, want_point2voxel=False)
+    assert torch.equal(lean.m2.view(torch.int64), ref.m2.view(torch.int64)) and lean.x is None
+    with pytest.raises(TypeError):
+        E.VoxelCloud.build(None, None, None, vs, origin, las=(q[0].astype(np.int64), q[1], q[2], scales, offsets))

@@ -65,6 +65,17 @@ def test_read_las12_format2_matches_laspy_conventions(tmp_path):
     np.testing.assert_allclose(dh.las_header.mins, [truth[c].min() for c in "XYZ"])
 
 
+def test_read_las_ints_are_the_stored_coordinates(tmp_path):
+    """las.read_las_ints: the int32 X, Y, Z as stored + the header transform reproduce the DataHandler's float64 columns bit for
+    bit with one multiply and one add (the contract of the 12 B/point input path)."""
+    path = str(tmp_path / "in.las")
+    truth = _las12_fmt2(path)
+    header, X, Y, Z = las.read_las_ints(path)
+    assert X.dtype == np.int32 and X.flags.c_contiguous and len(X) == 300
+    for q, k, name in ((X, 0, "X"), (Y, 1, "Y"), (Z, 2, "Z")):
+        np.testing.assert_array_equal(q.astype(np.float64) * header.scales[k] + header.offsets[k], truth[name])
+
+
 def test_load_several_files_and_append(tmp_path):
     a, b = str(tmp_path / "a.las"), str(tmp_path / "b.las")
     _las12_fmt2(a, 120, 1)

@@ -48,6 +48,12 @@ class Grid(C.Structure):
         return g
 
 
+class LasTransform(C.Structure):
+    """vapc_las_transform_t (include/vapc_b200.h): coordinate = X * scale + offset."""
+
+    _fields_ = [("scale", C.c_double * 3), ("offset", C.c_double * 3)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with vapc_b200/csrc/build.sh (nvcc, sm_100a). "
@@ -62,6 +68,7 @@ I32 = C.c_int32
 F64 = C.c_double
 SZ = C.c_size_t
 GP = C.POINTER(Grid)
+TP = C.POINTER(LasTransform)
 
 # name -> (restype, argtypes).  Order and meaning exactly as in include/vapc_b200.h.
 SIGNATURES = {
@@ -73,6 +80,9 @@ SIGNATURES = {
     "vapc_profile_collect": (C.c_int64, [C.c_char_p, I64]),
     "vapc_minmax_workspace_bytes": (SZ, []),
     "vapc_minmax_f64": (C.c_int, [P, P, P, I64, P, P, SZ, P]),
+    "vapc_minmax_i32": (C.c_int, [P, P, P, I64, TP, P, P, SZ, P]),
+    "vapc_las_coords_i32": (C.c_int, [P, P, P, I64, TP, P, P, P, P]),
+    "vapc_pack_records_bucketed_i32": (C.c_int, [P, P, P, I64, TP, GP, P, P, P, P, C.POINTER(I32), C.POINTER(I32), P, P, SZ, P]),
     "vapc_voxel_coords_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),
     "vapc_grid_from_bounds": (C.c_int, [GP, C.POINTER(F64)]),
     "vapc_pack_keys_f64": (C.c_int, [P, P, P, I64, GP, P, P, P, P]),

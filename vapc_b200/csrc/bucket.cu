@@ -39,9 +39,8 @@ template <typename KeyT>
 __device__ __forceinline__ unsigned bucket_of(KeyT key, int shift, unsigned mask) { return (unsigned)(key >> shift) & mask; }
 
 // keys in input order + histogram of the bucket digit
-template <typename KeyT, int VEC>
-__global__ void __launch_bounds__(kThreads) keys_hist_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                                                             int64_t n, Grid g, int shift, unsigned mask, KeyT* __restrict__ keys,
+template <typename KeyT, int VEC, typename Src>
+__global__ void __launch_bounds__(kThreads) keys_hist_kernel(Src src, int64_t n, Grid g, int shift, unsigned mask, KeyT* __restrict__ keys,
                                                              uint32_t* __restrict__ hist, int* __restrict__ status) {
   __shared__ unsigned sh[kRadix];
   sh[threadIdx.x] = 0;
@@ -51,11 +50,10 @@ __global__ void __launch_bounds__(kThreads) keys_hist_kernel(const double* __res
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     if (VEC == 2) {
-      const double2 a = __ldcs(reinterpret_cast<const double2*>(x) + v);
-      const double2 b = __ldcs(reinterpret_cast<const double2*>(y) + v);
-      const double2 c = __ldcs(reinterpret_cast<const double2*>(z) + v);
-      const KeyT k0 = pack_one<KeyT>(a.x, b.x, c.x, g, bad);
-      const KeyT k1 = pack_one<KeyT>(a.y, b.y, c.y, g, bad);
+      double a[2], b[2], c[2];
+      src.pair(v, a, b, c);
+      const KeyT k0 = pack_one<KeyT>(a[0], b[0], c[0], g, bad);
+      const KeyT k1 = pack_one<KeyT>(a[1], b[1], c[1], g, bad);
       if (sizeof(KeyT) == 4) {
         reinterpret_cast<uint2*>(keys)[v] = make_uint2((unsigned)k0, (unsigned)k1);
       } else {
@@ -64,13 +62,13 @@ __global__ void __launch_bounds__(kThreads) keys_hist_kernel(const double* __res
       atomicAdd(&sh[bucket_of(k0, shift, mask)], 1u);
       atomicAdd(&sh[bucket_of(k1, shift, mask)], 1u);
     } else {
-      const KeyT k = pack_one<KeyT>(ld_stream(x + v), ld_stream(y + v), ld_stream(z + v), g, bad);
+      const KeyT k = pack_one<KeyT>(src.cx(v), src.cy(v), src.cz(v), g, bad);
       keys[v] = k;
       atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
     }
   }
   if (VEC == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const KeyT k = pack_one<KeyT>(x[n - 1], y[n - 1], z[n - 1], g, bad);
+    const KeyT k = pack_one<KeyT>(src.cx(n - 1), src.cy(n - 1), src.cz(n - 1), g, bad);
     keys[n - 1] = k;
     atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
   }
@@ -105,9 +103,9 @@ struct BucketSmem {
 
 // KeyOutT: the bucketed keys are written as 32-bit words holding the key bits BELOW the bucket digit when those fit
 // (64-bit keys of up to 40 bits): the segmented sort then moves 4-byte keys; vapc_expand_bucket_keys restores the full keys.
-template <typename KeyT, typename KeyOutT, typename LookT>
+template <typename KeyT, typename KeyOutT, typename LookT, typename Src>
 __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) bucket_scatter_kernel(
-    const KeyT* __restrict__ keys, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n, int shift,
+    const KeyT* __restrict__ keys, Src src, int64_t n, int shift,
     unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyOutT* __restrict__ keys_b,
     double4* __restrict__ rec_b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -132,9 +130,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const bool valid = full || wbase + k * 32 < n;
-    px[k] = valid ? ld_stream(x + wbase + k * 32) : 0.0;
-    py[k] = valid ? ld_stream(y + wbase + k * 32) : 0.0;
-    pz[k] = valid ? ld_stream(z + wbase + k * 32) : 0.0;
+    px[k] = valid ? src.cx(wbase + k * 32) : 0.0;
+    py[k] = valid ? src.cy(wbase + k * 32) : 0.0;
+    pz[k] = valid ? src.cz(wbase + k * 32) : 0.0;
   }
 
   unsigned rank2[kItems / 2];
@@ -197,8 +195,8 @@ inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
 // workspace: [bucket histogram -> first slots, 256 u32][ticket (256 B)][look-back ntiles x 256 x 8 B]
 constexpr size_t kHistBytes = kRadix * sizeof(uint32_t);
 
-template <typename KeyT, typename KeyOutT, typename LookT>
-int bucket_impl(const double* x, const double* y, const double* z, int64_t n, const Grid& g, int mb, KeyOutT* keys_b, double4* rec_b, KeyT* keys_orig,
+template <typename KeyT, typename KeyOutT, typename LookT, typename Src>
+int bucket_impl(const Src& src, int64_t n, const Grid& g, int mb, KeyOutT* keys_b, double4* rec_b, KeyT* keys_orig,
                 uint32_t* bucket_start, int32_t* status, void* ws, cudaStream_t s) {
   const int shift = g.bx + g.by + g.bz - mb;  // the bucket digit = the leading mb bits of the key
   const unsigned mask = (1u << mb) - 1u;
@@ -209,14 +207,14 @@ int bucket_impl(const double* x, const double* y, const double* z, int64_t n, co
   LookT* look = reinterpret_cast<LookT*>(base + kHistBytes + 256);
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(base, 0, kHistBytes + 256 + (size_t)ntiles * kRadix * sizeof(LookT), s));
   const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16));
-  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(keys_orig)) & 15u) == 0;
-  if (vec) VAPC_LAUNCH((keys_hist_kernel<KeyT, 2>), hgrid, kThreads, 0, s, x, y, z, n, g, shift, mask, keys_orig, hist, status);
-  else VAPC_LAUNCH((keys_hist_kernel<KeyT, 1>), hgrid, kThreads, 0, s, x, y, z, n, g, shift, mask, keys_orig, hist, status);
+  const bool vec = src.aligned() && (reinterpret_cast<uintptr_t>(keys_orig) & 15u) == 0;
+  if (vec) VAPC_LAUNCH((keys_hist_kernel<KeyT, 2, Src>), hgrid, kThreads, 0, s, src, n, g, shift, mask, keys_orig, hist, status);
+  else VAPC_LAUNCH((keys_hist_kernel<KeyT, 1, Src>), hgrid, kThreads, 0, s, src, n, g, shift, mask, keys_orig, hist, status);
   VAPC_LAUNCH(digit_scan_kernel, 1, kThreads, 0, s, hist, nullptr, 1);
   VAPC_LAUNCH(bucket_start_kernel, 1, kThreads, 0, s, hist, 1 << mb, (uint32_t)n, bucket_start);
   const size_t smem = sizeof(BucketSmem<KeyT>);
-  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, KeyOutT, LookT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, KeyOutT, LookT>), (unsigned)ntiles, kThreads, smem, s, keys_orig, x, y, z, n, shift, mask, hist, look, ticket, keys_b,
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, KeyOutT, LookT, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, KeyOutT, LookT, Src>), (unsigned)ntiles, kThreads, smem, s, keys_orig, src, n, shift, mask, hist, look, ticket, keys_b,
               rec_b);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
@@ -228,12 +226,13 @@ extern "C" size_t vapc_bucket_workspace_bytes(int64_t n) {
   return kHistBytes + 256 + (size_t)num_tiles(n) * kRadix * sizeof(unsigned long long);
 }
 
-extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n, const vapc_grid_t* grid_host,
-                                          void* keys_bucketed, double* xyzw_bucketed, void* keys_orig, uint32_t* bucket_start,
-                                          int32_t* bucket_bits_host, int32_t* bucketed_key_bytes_host, int32_t* status, void* ws, size_t ws_bytes,
-                                          void* stream) {
-  if (!grid_host || !(grid_host->voxel_size > 0)) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad grid");
-  if (n < 0 || !bucket_bits_host || !bucketed_key_bytes_host) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: bad arguments");
+namespace {
+template <typename Src>
+int pack_bucketed(const char* who, const Src& src, int64_t n, const vapc_grid_t* grid_host, void* keys_bucketed, double* xyzw_bucketed, void* keys_orig,
+                  uint32_t* bucket_start, int32_t* bucket_bits_host, int32_t* bucketed_key_bytes_host, int32_t* status, void* ws, size_t ws_bytes,
+                  void* stream) {
+  if (!grid_host || !(grid_host->voxel_size > 0)) return vapc_set_error(VAPC_E_INVALID, "%s: bad grid", who);
+  if (n < 0 || !bucket_bits_host || !bucketed_key_bytes_host) return vapc_set_error(VAPC_E_INVALID, "%s: bad arguments", who);
   const Grid g = to_device_grid(grid_host);
   const int mb = g.bx < kRadixBits ? g.bx : kRadixBits;
   const int low_bits = g.bx + g.by + g.bz - mb;
@@ -241,29 +240,46 @@ extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, cons
   *bucket_bits_host = mb;
   *bucketed_key_bytes_host = narrow ? 4 : grid_host->key_bytes;
   if (n == 0) return VAPC_OK;
-  if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: n must be < 2^32 per GPU");
-  if (!x || !y || !z || !keys_bucketed || !xyzw_bucketed || !keys_orig || !bucket_start || !status)
-    return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: null buffer");
-  if (reinterpret_cast<uintptr_t>(xyzw_bucketed) & 31u) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: xyzw must be 32-byte aligned");
-  if (!ws || ws_bytes < vapc_bucket_workspace_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_pack_records_bucketed: workspace too small");
+  if (n >= (int64_t)1 << 32) return vapc_set_error(VAPC_E_INVALID, "%s: n must be < 2^32 per GPU", who);
+  if (src.null() || !keys_bucketed || !xyzw_bucketed || !keys_orig || !bucket_start || !status) return vapc_set_error(VAPC_E_INVALID, "%s: null buffer", who);
+  if (reinterpret_cast<uintptr_t>(xyzw_bucketed) & 31u) return vapc_set_error(VAPC_E_INVALID, "%s: xyzw must be 32-byte aligned", who);
+  if (!ws || ws_bytes < vapc_bucket_workspace_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "%s: workspace too small", who);
   cudaStream_t s = as_stream(stream);
   double4* rec = reinterpret_cast<double4*>(xyzw_bucketed);
   const bool wide = n >= ((int64_t)1 << 30);
   typedef unsigned long long u64;
   typedef uint32_t u32;
   if (grid_host->key_bytes == 4) {
-    if (!wide) return bucket_impl<u32, u32, u32>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<u32, u32, u64>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
+    if (!wide) return bucket_impl<u32, u32, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u32, u32, u64>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
   }
   if (grid_host->key_bytes == 8) {
     if (narrow) {
-      if (!wide) return bucket_impl<u64, u32, u32>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
-      return bucket_impl<u64, u32, u64>(x, y, z, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+      if (!wide) return bucket_impl<u64, u32, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+      return bucket_impl<u64, u32, u64>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
     }
-    if (!wide) return bucket_impl<u64, u64, u32>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<u64, u64, u64>(x, y, z, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    if (!wide) return bucket_impl<u64, u64, u32>(src, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u64, u64, u64>(src, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
   }
-  return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed: key_bytes must be 4 or 8");
+  return vapc_set_error(VAPC_E_INVALID, "%s: key_bytes must be 4 or 8", who);
+}
+}  // namespace
+
+extern "C" int vapc_pack_records_bucketed(const double* x, const double* y, const double* z, int64_t n, const vapc_grid_t* grid_host,
+                                          void* keys_bucketed, double* xyzw_bucketed, void* keys_orig, uint32_t* bucket_start,
+                                          int32_t* bucket_bits_host, int32_t* bucketed_key_bytes_host, int32_t* status, void* ws, size_t ws_bytes,
+                                          void* stream) {
+  return pack_bucketed("vapc_pack_records_bucketed", SrcF64{x, y, z}, n, grid_host, keys_bucketed, xyzw_bucketed, keys_orig, bucket_start, bucket_bits_host,
+                       bucketed_key_bytes_host, status, ws, ws_bytes, stream);
+}
+
+extern "C" int vapc_pack_records_bucketed_i32(const int32_t* X, const int32_t* Y, const int32_t* Z, int64_t n, const vapc_las_transform_t* t_host,
+                                              const vapc_grid_t* grid_host, void* keys_bucketed, double* xyzw_bucketed, void* keys_orig,
+                                              uint32_t* bucket_start, int32_t* bucket_bits_host, int32_t* bucketed_key_bytes_host, int32_t* status,
+                                              void* ws, size_t ws_bytes, void* stream) {
+  if (!t_host) return vapc_set_error(VAPC_E_INVALID, "vapc_pack_records_bucketed_i32: null transform");
+  return pack_bucketed("vapc_pack_records_bucketed_i32", make_src_i32(X, Y, Z, t_host), n, grid_host, keys_bucketed, xyzw_bucketed, keys_orig, bucket_start,
+                       bucket_bits_host, bucketed_key_bytes_host, status, ws, ws_bytes, stream);
 }
 
 extern "C" int vapc_expand_bucket_keys(const uint32_t* low_sorted, int64_t n, const uint32_t* bucket_start, int32_t bucket_bits, int32_t low_bits,

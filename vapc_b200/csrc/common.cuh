@@ -106,6 +106,45 @@ __device__ __forceinline__ void st_record(double4* p, double x, double y, double
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
 }
 
+// ---- coordinate sources of the key kernels ------------------------------------------------------------------
+// SrcF64: the fp64 columns of the frame.  SrcI32: the integer coordinates of a LAS file with the header's scale / offset,
+// coordinate = X * scale + offset evaluated like laspy / numpy evaluate it (one IEEE multiply, one IEEE add, no FMA;
+// datahandler.py:72-95 receives exactly these doubles): 12 B/point over PCIe and from HBM instead of 24.
+struct SrcF64 {
+  const double *x, *y, *z;
+  static constexpr unsigned kPairAlign = 15u;  // a pair of points is one 16-byte load
+  __device__ __forceinline__ double cx(int64_t i) const { return ld_stream(x + i); }
+  __device__ __forceinline__ double cy(int64_t i) const { return ld_stream(y + i); }
+  __device__ __forceinline__ double cz(int64_t i) const { return ld_stream(z + i); }
+  __device__ __forceinline__ void pair(int64_t v, double (&a)[2], double (&b)[2], double (&c)[2]) const {
+    const double2 p = __ldcs(reinterpret_cast<const double2*>(x) + v), q = __ldcs(reinterpret_cast<const double2*>(y) + v),
+                  r = __ldcs(reinterpret_cast<const double2*>(z) + v);
+    a[0] = p.x; a[1] = p.y; b[0] = q.x; b[1] = q.y; c[0] = r.x; c[1] = r.y;
+  }
+  bool aligned() const { return ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & kPairAlign) == 0; }
+  bool null() const { return !x || !y || !z; }
+};
+struct SrcI32 {
+  const int32_t *x, *y, *z;
+  double sx, sy, sz, ox, oy, oz;
+  static constexpr unsigned kPairAlign = 7u;
+  static __device__ __forceinline__ double conv(int32_t q, double s, double o) { return __dadd_rn(__dmul_rn((double)q, s), o); }
+  __device__ __forceinline__ double cx(int64_t i) const { return conv(__ldcs(x + i), sx, ox); }
+  __device__ __forceinline__ double cy(int64_t i) const { return conv(__ldcs(y + i), sy, oy); }
+  __device__ __forceinline__ double cz(int64_t i) const { return conv(__ldcs(z + i), sz, oz); }
+  __device__ __forceinline__ void pair(int64_t v, double (&a)[2], double (&b)[2], double (&c)[2]) const {
+    const int2 p = __ldcs(reinterpret_cast<const int2*>(x) + v), q = __ldcs(reinterpret_cast<const int2*>(y) + v),
+               r = __ldcs(reinterpret_cast<const int2*>(z) + v);
+    a[0] = conv(p.x, sx, ox); a[1] = conv(p.y, sx, ox); b[0] = conv(q.x, sy, oy); b[1] = conv(q.y, sy, oy);
+    c[0] = conv(r.x, sz, oz); c[1] = conv(r.y, sz, oz);
+  }
+  bool aligned() const { return ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & kPairAlign) == 0; }
+  bool null() const { return !x || !y || !z; }
+};
+static inline SrcI32 make_src_i32(const int32_t* x, const int32_t* y, const int32_t* z, const vapc_las_transform_t* t) {
+  return SrcI32{x, y, z, t->scale[0], t->scale[1], t->scale[2], t->offset[0], t->offset[1], t->offset[2]};
+}
+
 // ---- block-wide exclusive scan of one unsigned per thread (blockDim.x multiple of 32, <= 1024)
 // smem33: 33 words of shared scratch.  Returns the exclusive prefix; *total = block sum (all
 // threads).  Ends with a barrier, so smem33 may be reused immediately.

@@ -103,13 +103,12 @@ inline int stream_grid(int64_t n, int per_block) {
 }
 
 // ---- min / max -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) minmax_partial(const double* __restrict__ x, const double* __restrict__ y,
-                                                           const double* __restrict__ z, int64_t n,
-                                                           double* __restrict__ partial /*[grid][6]*/) {
+template <typename Src>
+__global__ void __launch_bounds__(kThreads) minmax_partial(Src src, int64_t n, double* __restrict__ partial /*[grid][6]*/) {
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double a = ld_stream(x + i), b = ld_stream(y + i), c = ld_stream(z + i);
+    const double a = src.cx(i), b = src.cy(i), c = src.cz(i);
     mn[0] = fmin(mn[0], a); mx[0] = fmax(mx[0], a);
     mn[1] = fmin(mn[1], b); mx[1] = fmax(mx[1], b);
     mn[2] = fmin(mn[2], c); mx[2] = fmax(mx[2], c);
@@ -250,8 +249,41 @@ extern "C" int vapc_minmax_f64(const double* x, const double* y, const double* z
   if (n <= 0 || !x || !y || !z || !out6) return vapc_set_error(VAPC_E_INVALID, "vapc_minmax_f64: empty input or null pointer");
   if (ws_bytes < vapc_minmax_workspace_bytes() || !ws) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_minmax_f64: workspace too small");
   const int grid = stream_grid(n, kThreads * 8);
-  VAPC_LAUNCH(minmax_partial, grid, kThreads, 0, as_stream(stream), x, y, z, n, static_cast<double*>(ws));
+  VAPC_LAUNCH(minmax_partial<SrcF64>, grid, kThreads, 0, as_stream(stream), SrcF64{x, y, z}, n, static_cast<double*>(ws));
   VAPC_LAUNCH(minmax_final, 1, 192, 0, as_stream(stream), static_cast<double*>(ws), grid, out6);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(kThreads) las_coords_kernel(SrcI32 src, int64_t n, double* __restrict__ x, double* __restrict__ y,
+                                                              double* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    __stcs(x + i, src.cx(i));
+    __stcs(y + i, src.cy(i));
+    __stcs(z + i, src.cz(i));
+  }
+}
+}  // namespace
+
+extern "C" int vapc_minmax_i32(const int32_t* X, const int32_t* Y, const int32_t* Z, int64_t n, const vapc_las_transform_t* t_host, double* out6,
+                               void* ws, size_t ws_bytes, void* stream) {
+  if (n <= 0 || !X || !Y || !Z || !out6 || !t_host) return vapc_set_error(VAPC_E_INVALID, "vapc_minmax_i32: empty input or null pointer");
+  if (ws_bytes < vapc_minmax_workspace_bytes() || !ws) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_minmax_i32: workspace too small");
+  const int grid = stream_grid(n, kThreads * 8);
+  VAPC_LAUNCH(minmax_partial<SrcI32>, grid, kThreads, 0, as_stream(stream), make_src_i32(X, Y, Z, t_host), n, static_cast<double*>(ws));
+  VAPC_LAUNCH(minmax_final, 1, 192, 0, as_stream(stream), static_cast<double*>(ws), grid, out6);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_las_coords_i32(const int32_t* X, const int32_t* Y, const int32_t* Z, int64_t n, const vapc_las_transform_t* t_host, double* x,
+                                   double* y, double* z, void* stream) {
+  if (n < 0 || !t_host) return vapc_set_error(VAPC_E_INVALID, "vapc_las_coords_i32: bad arguments");
+  if (n == 0) return VAPC_OK;
+  if (!X || !Y || !Z || !x || !y || !z) return vapc_set_error(VAPC_E_INVALID, "vapc_las_coords_i32: null buffer");
+  VAPC_LAUNCH(las_coords_kernel, stream_grid(n, kThreads * 4), kThreads, 0, as_stream(stream), make_src_i32(X, Y, Z, t_host), n, x, y, z);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from ._lib import Grid
+from ._lib import Grid, LasTransform
 
 FEATURE_NAMES = (
     "Sum_of_Eigenvalues", "Omnivariance", "Eigenentropy", "Anisotropy", "Planarity", "Linearity",
@@ -92,6 +92,49 @@ def coordinate_bounds(x, y, z) -> np.ndarray:
     ws = _empty(ws_bytes, torch.uint8, x.device)
     L.call("vapc_minmax_f64", _ptr(x), _ptr(y), _ptr(z), n, _ptr(out), _ptr(ws), ws_bytes, _stream())
     return out.cpu().numpy()
+
+
+def las_transform(scales: Sequence[float], offsets: Sequence[float]) -> LasTransform:
+    t = LasTransform()
+    for k in range(3):
+        t.scale[k] = float(scales[k])
+        t.offset[k] = float(offsets[k])
+    return t
+
+
+def _dev_i32(a, device) -> torch.Tensor:
+    """A contiguous int32 CUDA tensor from a tensor / numpy array (LAS integer coordinates)."""
+    if not isinstance(a, torch.Tensor):
+        a = np.asarray(a)
+        if a.dtype != np.int32:
+            raise TypeError("LAS integer coordinates must be int32")
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    t = a
+    if t.dtype != torch.int32:
+        raise TypeError("LAS integer coordinates must be int32")
+    return t.to(device=device, non_blocking=True).contiguous()
+
+
+def coordinate_bounds_i32(X, Y, Z, t: LasTransform) -> np.ndarray:
+    """coordinate_bounds of the doubles X * scale + offset that int32 LAS coordinates stand for (12 B/point read)."""
+    out = _empty(6, torch.float64, X.device)
+    ws_bytes = L.raw("vapc_minmax_workspace_bytes")()
+    ws = _empty(ws_bytes, torch.uint8, X.device)
+    L.call("vapc_minmax_i32", _ptr(X), _ptr(Y), _ptr(Z), X.numel(), C.byref(t), _ptr(out), _ptr(ws), ws_bytes, _stream())
+    return out.cpu().numpy()
+
+
+def las_coordinates(X, Y, Z, scales, offsets, device=None):
+    """The fp64 x, y, z columns of int32 LAS coordinates, X * scale + offset (what laspy hands the reference's DataHandler,
+    datahandler.py:72-95), computed on the device; bit-identical to numpy's X * scale + offset."""
+    _require_cuda()
+    if device is None:
+        device = X.device if isinstance(X, torch.Tensor) and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    X, Y, Z = (_dev_i32(a, device) for a in (X, Y, Z))
+    t = las_transform(scales, offsets)
+    out = [_empty(X.numel(), torch.float64, device) for _ in range(3)]
+    L.call("vapc_las_coords_i32", _ptr(X), _ptr(Y), _ptr(Z), X.numel(), C.byref(t), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream())
+    return out
 
 
 def voxel_coords(x, y, z, voxel_size, origin):
@@ -208,18 +251,36 @@ class VoxelCloud:
     # ------------------------------------------------------------------------------------
     @classmethod
     def build(cls, x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), *, bounds=None, want_point2voxel=True,
-              keep_columns=True, device=None, bucketed=True) -> "VoxelCloud":
+              keep_columns=True, device=None, bucketed=True, las=None) -> "VoxelCloud":
         """voxelize + groupby of the reference (vapc.py:188-207 and the groupby at :724, :843, :959)
         as: bounds -> packed keys + xyzw records in key-prefix bucket order -> stable radix sort of the remaining key
         bits inside the buckets -> segmentation -> moments.  bucketed=False keeps the records in input order and
-        sorts all key bits (same results; the per-voxel gathers then miss the L2)."""
+        sorts all key bits (same results; the per-voxel gathers then miss the L2).
+        las = (X, Y, Z, scales, offsets): the cloud as the int32 coordinates of a LAS file (x, y, z are then ignored and may be
+        None): the key kernels read 12 B/point and form X * scale + offset themselves — the same doubles, the same results."""
         _require_cuda()
-        if device is None:
-            device = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        x, y, z = (_dev_f64(a, device) for a in (x, y, z))
-        n = x.numel()
-        if y.numel() != n or z.numel() != n:
-            raise ValueError("X, Y, Z must have the same length")
+        if las is not None:
+            if not bucketed:
+                raise ValueError("LAS integer input needs the bucketed path")
+            X0 = las[0]
+            if device is None:
+                device = X0.device if isinstance(X0, torch.Tensor) and X0.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            lX, lY, lZ = (_dev_i32(a, device) for a in las[:3])
+            lt = las_transform(las[3], las[4])
+            n = lX.numel()
+            if lY.numel() != n or lZ.numel() != n:
+                raise ValueError("X, Y, Z must have the same length")
+            if keep_columns:
+                x, y, z = las_coordinates(lX, lY, lZ, las[3], las[4], device)
+            if bounds is None and n:
+                bounds = coordinate_bounds_i32(lX, lY, lZ, lt)
+        else:
+            if device is None:
+                device = x.device if isinstance(x, torch.Tensor) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            x, y, z = (_dev_f64(a, device) for a in (x, y, z))
+            n = x.numel()
+            if y.numel() != n or z.numel() != n:
+                raise ValueError("X, Y, Z must have the same length")
         if n == 0:
             raise ValueError("empty point cloud")
         if n >= 2 ** 32:
@@ -243,8 +304,12 @@ class VoxelCloud:
             bws_bytes = L.raw("vapc_bucket_workspace_bytes")(n)
             bws = _empty(bws_bytes, torch.uint8, device)
             bucket_bits, bkey_bytes = C.c_int32(0), C.c_int32(0)
-            L.call("vapc_pack_records_bucketed", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys_b), _ptr(self.xyzw), _ptr(keys), _ptr(bucket_start),
-                   C.byref(bucket_bits), C.byref(bkey_bytes), _ptr(status), _ptr(bws), bws_bytes, _stream())
+            if las is not None:
+                L.call("vapc_pack_records_bucketed_i32", _ptr(lX), _ptr(lY), _ptr(lZ), n, C.byref(lt), C.byref(g), _ptr(keys_b), _ptr(self.xyzw), _ptr(keys),
+                       _ptr(bucket_start), C.byref(bucket_bits), C.byref(bkey_bytes), _ptr(status), _ptr(bws), bws_bytes, _stream())
+            else:
+                L.call("vapc_pack_records_bucketed", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys_b), _ptr(self.xyzw), _ptr(keys), _ptr(bucket_start),
+                       C.byref(bucket_bits), C.byref(bkey_bytes), _ptr(status), _ptr(bws), bws_bytes, _stream())
             del bws
             low_bits = g.total_bits - bucket_bits.value
             if bkey_bytes.value == 4 and g.key_bytes == 8:

@@ -191,6 +191,14 @@ def read_las(path: str):
     return h, cols
 
 
+def read_las_ints(path: str):
+    """(header, X, Y, Z): the int32 coordinates of the file as stored, contiguous; coordinate = X * header.scales[k] +
+    header.offsets[k].  Input of the 12 B/point path (vapc_b200.engine.VoxelCloud.build(..., las=...),
+    vapc_b200.pipeline.HostStreamPipeline(..., las=...))."""
+    header, cols = read_las(path)
+    return header, np.ascontiguousarray(cols["X"], dtype=np.int32), np.ascontiguousarray(cols["Y"], dtype=np.int32), np.ascontiguousarray(cols["Z"], dtype=np.int32)
+
+
 def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
               point_format: int = 7, generating_software: str = "vapc_b200"):
     """LAS 1.4, point format 6 / 7 / 8.  `standard`: values for standard dimensions by laspy name (cast to the field

@@ -12,6 +12,9 @@ clouds is what the hardware allows.  Used by `bench.py` for the `e2e` figure and
     pipe = HostStreamPipeline(voxel_size, origin, device)
     for result in pipe.run(iterable_of_(hx, hy, hz)_pinned_tensors):
         result["cog"], result["cov"], ...   # pinned host tensors, valid until the next result is requested
+
+With `las=(scales, offsets)` the clouds are the int32 X, Y, Z of LAS files (`vapc_b200.las.read_las_ints`): 12 B/point over
+PCIe instead of 24, the key kernels form X * scale + offset themselves (same doubles, same results).
 """
 from __future__ import annotations
 
@@ -24,9 +27,13 @@ from . import engine as E
 STAT_NAMES = ("density", "cog", "std", "cov", "eig", "eig_n", "feat")
 
 
-def full_statistics(dx, dy, dz, voxel_size, origin) -> Dict[str, torch.Tensor]:
-    """The whole single-GPU hot path on device columns -> dict of device tensors (the voxel table)."""
-    c = E.VoxelCloud.build(dx, dy, dz, voxel_size, origin, keep_columns=False)
+def full_statistics(dx, dy, dz, voxel_size, origin, las=None) -> Dict[str, torch.Tensor]:
+    """The whole single-GPU hot path on device columns -> dict of device tensors (the voxel table).  las = (scales, offsets):
+    dx, dy, dz are int32 LAS coordinates."""
+    if las is not None:
+        c = E.VoxelCloud.build(None, None, None, voxel_size, origin, keep_columns=False, las=(dx, dy, dz, las[0], las[1]))
+    else:
+        c = E.VoxelCloud.build(dx, dy, dz, voxel_size, origin, keep_columns=False)
     s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
     out = {"voxel_keys": c.voxel_keys, "count": c.count}
     out.update({k: getattr(s, k) for k in STAT_NAMES})
@@ -35,11 +42,11 @@ def full_statistics(dx, dy, dz, voxel_size, origin) -> Dict[str, torch.Tensor]:
 
 
 class HostStreamPipeline:
-    def __init__(self, voxel_size, origin, device=None, compute_fn: Optional[Callable] = None, depth: int = 2):
+    def __init__(self, voxel_size, origin, device=None, compute_fn: Optional[Callable] = None, depth: int = 2, las=None):
         E._require_cuda()
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.voxel_size, self.origin = voxel_size, list(origin)
-        self.compute_fn = compute_fn or (lambda x, y, z: full_statistics(x, y, z, self.voxel_size, self.origin))
+        self.compute_fn = compute_fn or (lambda x, y, z: full_statistics(x, y, z, self.voxel_size, self.origin, las=las))
         self.depth = depth
         self.s_in = torch.cuda.Stream(self.device)
         self.s_compute = torch.cuda.Stream(self.device)
@@ -55,8 +62,8 @@ class HostStreamPipeline:
             if after is not None:
                 self.s_in.wait_event(after)
             bufs = self._dev_in[slot]
-            if bufs is None or bufs[0].numel() != cols[0].numel():
-                bufs = [torch.empty(c.numel(), dtype=torch.float64, device=self.device) for c in cols]
+            if bufs is None or bufs[0].numel() != cols[0].numel() or bufs[0].dtype != cols[0].dtype:
+                bufs = [torch.empty(c.numel(), dtype=c.dtype, device=self.device) for c in cols]
                 self._dev_in[slot] = bufs
             for b, c in zip(bufs, cols):
                 b.copy_(c, non_blocking=True)
