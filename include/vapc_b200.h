@@ -272,6 +272,15 @@ VAPC_API int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t att
                     int64_t nvoxels, double threshold, int64_t* mode, int64_t* mode_count,
                     void* stream);
 
+/* mode / mode_count over N GPUs ("(key, value, count) runs instead of moments").  vapc_run_lengths: run-length
+ * encoding of sorted 64-bit keys with optional weights (NULL = 1 each): run_keys[r] = r-th distinct key, run_weight[r] = sum of
+ * the weights of its elements; call vapc_count_voxels(keys_sorted, n, 8, ...) first for the number of runs and pass the same
+ * ws.  vapc_mode_count_runs: vapc_mode_count on such runs, keys = voxel row << attr_bits | value, sorted and distinct. */
+VAPC_API int vapc_run_lengths(const uint64_t* keys_sorted, const uint32_t* weights, int64_t n, int64_t nruns_host, uint64_t* run_keys,
+                     int64_t* run_weight, void* ws, size_t ws_bytes, void* stream);
+VAPC_API int vapc_mode_count_runs(const uint64_t* run_keys, const int64_t* run_weight, int64_t nruns, int32_t attr_bits,
+                         int64_t nvoxels, double threshold, int64_t* mode, int64_t* mode_count, void* stream);
+
 /* ---- a16 (rest) mean / sum / min / max / var (ddof = 0) / median of an fp64 attribute
  * (vapc.py:393-406).  order = point indices grouped by voxel ([start[v], start[v+1]) slices):
  * idx_sorted for vapc_attr_stats (original order inside a voxel), and the (voxel, value) order

@@ -93,7 +93,14 @@ def per_point_outputs(rank, world, dev, pts, rng, vs, origin):
     assert np.all(np.abs(md - rmd) <= 1e-9 * rmd + 1e-12), "min_distance"
     same = gi == ram
     assert same.mean() > 0.999, float(same.mean())  # a last-bit centroid difference may flip an exact tie
-    cog = st.cog.cpu().numpy()
+    # mode / mode_count of an integer attribute: (voxel, value, count) runs merged at the owners == one GPU, exactly
+    cls_all = rng.integers(0, 9, n).astype(np.float64)
+    cls_all[cloud[:, 0] > 20] = np.minimum(cls_all[cloud[:, 0] > 20], 3)  # skewed classes in half of the scene
+    mode, counts = D.mode_count(table, shard, torch.from_numpy(cls_all[a:b]).to(dev), thresholds=[0.1, 0.3], want_mode=True)
+    rmode, rcounts = ref.mode_count(cls_all, [0.1, 0.3], want_mode=True)
+    assert np.array_equal(gather_cat(mode.cpu().numpy()), rmode.cpu().numpy()), "mode"
+    for p in (0.1, 0.3):
+        assert np.array_equal(gather_cat(counts[p].cpu().numpy()), rcounts[p].cpu().numpy()), f"mode_count,{p}"
     if rank == 0:
         print(f"[per-point] world={world}: {len(md)} voxels, subsample identical for {int(same.sum())}, "
               f"partial rows answered by owners: {sum(shard.send_remote)}", flush=True)

@@ -541,3 +541,35 @@ def test_las_integer_input_is_bit_identical(E, n, scales, offsets, vs):
     assert torch.equal(lean.m2.view(torch.int64), ref.m2.view(torch.int64)) and lean.x is None
     with pytest.raises(TypeError):
         E.VoxelCloud.build(None, None, None, vs, origin, las=(q[0].astype(np.int64), q[1], q[2], scales, offsets))
+
+
+def test_run_lengths_and_mode_from_runs(E):
+    """vapc_run_lengths (weighted run-length encoding of sorted keys) and vapc_mode_count_runs against numpy, and the runs
+    route == the per-point route of mode / mode_count."""
+    import ctypes as C
+
+    from vapc_b200 import _lib as L
+
+    rng = np.random.default_rng(21)
+    for n, hi in ((1, 5), (5000, 40), (300_000, 20_000), (1_000_003, 7)):
+        keys = np.sort(rng.integers(0, hi, n)).astype(np.int64)
+        w = rng.integers(1, 1000, n).astype(np.int32)
+        for weights in (None, w):
+            rk, rw = E.run_lengths(torch.from_numpy(keys).cuda(), None if weights is None else torch.from_numpy(weights).cuda())
+            uk, inv = np.unique(keys, return_inverse=True)
+            np.testing.assert_array_equal(_np(rk), uk)
+            np.testing.assert_array_equal(_np(rw), np.bincount(inv, weights=None if weights is None else weights.astype(np.float64)).astype(np.int64))
+    # mode / mode_count from runs == from points
+    x, y, z = make_cloud("clustered", 120000, 3)
+    cloud = E.VoxelCloud.build(x, y, z, 0.5, [0, 0, 0])
+    attr = rng.integers(0, 12, len(x)).astype(np.float64)
+    mode, counts = cloud.mode_count(attr, [0.2], want_mode=True)
+    attr_bits = 4
+    comp = (_u32(cloud.point2voxel) << attr_bits) | attr.astype(np.int64)
+    ks, _ = E.sort_pairs(torch.from_numpy(comp).cuda(), int(cloud.nvoxels - 1).bit_length() + attr_bits)
+    rk, rw = E.run_lengths(ks)
+    m2 = torch.empty(cloud.nvoxels, dtype=torch.int64, device="cuda")
+    c2 = torch.empty(cloud.nvoxels, dtype=torch.int64, device="cuda")
+    L.call("vapc_mode_count_runs", C.c_void_p(rk.data_ptr()), C.c_void_p(rw.data_ptr()), rk.numel(), attr_bits, cloud.nvoxels, 0.2,
+           C.c_void_p(m2.data_ptr()), C.c_void_p(c2.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(m2, mode) and torch.equal(c2, counts[0.2])

@@ -59,6 +59,34 @@ __global__ void __launch_bounds__(kThreads) mode_count_kernel(const unsigned lon
   if (mode_count) mode_count[v] = above;
 }
 
+// The same from (voxel row << attr_bits | value, weight) runs: sorted distinct keys with the number of points behind each —
+// what the owners of a multi-GPU table hold after merging the ranks' runs.  One thread per voxel finds its runs by
+// binary search.
+__global__ void __launch_bounds__(kThreads) mode_count_runs_kernel(const unsigned long long* __restrict__ run_keys, const long long* __restrict__ run_weight,
+                                                                   int64_t nruns, int attr_bits, int64_t nvox, double threshold,
+                                                                   long long* __restrict__ mode, long long* __restrict__ mode_count) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const unsigned long long first = (unsigned long long)v << attr_bits;
+  int64_t lo = 0, hi = nruns;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (run_keys[mid] < first) lo = mid + 1; else hi = mid;
+  }
+  const unsigned long long mask = (1ull << attr_bits) - 1ull;
+  long long total = 0;
+  int64_t e = lo;
+  while (e < nruns && (run_keys[e] >> attr_bits) == (unsigned long long)v) total += run_weight[e++];
+  long long best_val = 0, best_cnt = 0, above = 0;
+  for (int64_t p = lo; p < e; ++p) {
+    const long long cnt = run_weight[p];
+    if (cnt > best_cnt) { best_cnt = cnt; best_val = (long long)(run_keys[p] & mask); }
+    if ((double)cnt / (double)total >= threshold) ++above;
+  }
+  if (mode) mode[v] = best_val;
+  if (mode_count) mode_count[v] = above;
+}
+
 // ---- per-voxel statistics of an fp64 attribute (vapc.py:393-406) -----------------------------------------
 // One thread per voxel walks the voxel's points in original order (order = idx_sorted).  mean / sum as a
 // running fp64 sum, var / std two-pass about the mean with ddof = 0 (numpy's .var() / .std()).
@@ -241,6 +269,18 @@ extern "C" int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t a
   VAPC_LAUNCH(mode_count_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), 
       reinterpret_cast<const unsigned long long*>(keys_sorted), attr_bits, start, nvoxels, threshold,
       reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_mode_count_runs(const uint64_t* run_keys, const int64_t* run_weight, int64_t nruns, int32_t attr_bits, int64_t nvoxels,
+                                    double threshold, int64_t* mode, int64_t* mode_count, void* stream) {
+  if (nruns < 0 || nvoxels < 0 || attr_bits < 1 || attr_bits > 40) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count_runs: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  if (nruns > 0 && (!run_keys || !run_weight)) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count_runs: null buffer");
+  VAPC_LAUNCH(mode_count_runs_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream),
+              reinterpret_cast<const unsigned long long*>(run_keys), reinterpret_cast<const long long*>(run_weight), nruns, attr_bits, nvoxels, threshold,
+              reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -173,6 +173,40 @@ __device__ __forceinline__ void tile_prologue(TileSmem<KeyT>& sm, const KeyT* __
   }
 }
 
+// ---- weighted run lengths of sorted keys (multi-GPU mode / mode_count: (voxel, value) runs instead of points) -------
+// run_keys[r] = the r-th distinct key, run_weight[r] += the weights of its elements.  64-bit integer atomics: exact and
+// independent of the order of arrival.  tile_first = the workspace vapc_count_voxels left behind.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) run_lengths_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ weights, int64_t n,
+                                                               const uint32_t* __restrict__ tile_first, KeyT* __restrict__ run_keys,
+                                                               unsigned long long* __restrict__ run_weight) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<KeyT>& sm = *reinterpret_cast<TileSmem<KeyT>*>(smem_raw);
+  const int64_t base = (int64_t)blockIdx.x * kSegTile;
+  KeyT key[kItems];
+  bool valid[kItems], head[kItems];
+  unsigned inc[kItems], nheads;
+  int tile_n;
+  tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
+  const uint32_t first_row = tile_first[blockIdx.x];
+  const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
+  unsigned long long acc = 0;
+  uint32_t cur = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (!valid[j]) continue;
+    const uint32_t row = first_row + inc[j] - 1u;
+    if (head[j]) run_keys[row] = key[j];
+    if (row != cur) {
+      if (cur != 0xffffffffu) atomicAdd(run_weight + cur, acc);
+      cur = row;
+      acc = 0;
+    }
+    acc += weights ? weights[p0 + j] : 1u;
+  }
+  if (cur != 0xffffffffu) atomicAdd(run_weight + cur, acc);
+}
+
 // ---- step 2: moments ------------------------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_kernel(
@@ -813,6 +847,24 @@ extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, cons
   } else {
     return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_dense: key_bytes must be 4 or 8");
   }
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_run_lengths(const uint64_t* keys_sorted, const uint32_t* weights, int64_t n, int64_t nruns_host, uint64_t* run_keys,
+                                int64_t* run_weight, void* ws, size_t ws_bytes, void* stream) {
+  if (n < 0 || nruns_host < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_run_lengths: bad arguments");
+  if (n == 0) return VAPC_OK;
+  if (!keys_sorted || !run_keys || !run_weight) return vapc_set_error(VAPC_E_INVALID, "vapc_run_lengths: null buffer");
+  if (!ws || ws_bytes < seg_ws_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_run_lengths: workspace too small");
+  const SegWs w = carve(ws, n);
+  cudaStream_t s = as_stream(stream);
+  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(run_weight, 0, (size_t)nruns_host * sizeof(int64_t), s));
+  typedef unsigned long long K;
+  const size_t smem = tile_smem_bytes<K>();
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(run_lengths_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_LAUNCH(run_lengths_kernel<K>, (unsigned)seg_tiles(n), kThreads, smem, s, reinterpret_cast<const K*>(keys_sorted), weights, n, w.tile_heads,
+              reinterpret_cast<K*>(run_keys), reinterpret_cast<unsigned long long*>(run_weight));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -508,3 +508,67 @@ def closest_to_cog(table: ShardedVoxelTable, shard: LocalShard, cog: torch.Tenso
     best_i = torch.empty(table.nvoxels, dtype=torch.int64, device=dev)
     L.call("vapc_reduce_candidates", E._ptr(rows), E._ptr(d), E._ptr(g), rows.numel(), table.nvoxels, E._ptr(best_d), E._ptr(best_i), E._stream())
     return best_d, best_i
+
+
+def mode_count(table: ShardedVoxelTable, shard: LocalShard, attr, thresholds: Sequence[float] = (), want_mode=True):
+    """mode and mode_count,p of an integer attribute over all ranks (vapc.py:407-433).  Every rank sorts its points by (partial
+    row, value) and run-length encodes them (vapc_run_lengths); the (key, value, count) runs of the rows that left the rank go to
+    their owners in ONE all-to-all (24 B per run instead of moments), the owner adds the counts of equal (voxel, value) pairs
+    (sort + weighted run lengths) and evaluates mode / mode_count on the merged runs (vapc_mode_count_runs).  Counts are
+    integers: the result is identical to one GPU.  Returns (mode [V_owned] int64 or None, {p: mode_count [V_owned] int64})."""
+    from . import _lib as L
+    from . import engine as E
+
+    c = shard.cloud
+    dev = c.device
+    group = shard.group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    a = E._dev_f64(attr, dev)
+    if a.numel() != c.n:
+        raise ValueError("attribute length differs from the chunk")
+    amax = a.max().reshape(1).clone() if c.n else torch.zeros(1, dtype=torch.float64, device=dev)
+    dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=group)
+    attr_bits = max(1, int(max(float(amax.item()), 0.0)).bit_length())  # every rank must pack the values alike
+    if attr_bits > 32:
+        raise ValueError("attribute values too large for mode / mode_count")
+    keys = torch.empty(c.n, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("vapc_mode_keys", E._ptr(c.point2voxel), E._ptr(a), c.n, attr_bits, E._ptr(keys), E._ptr(status), E._stream())
+    ks, _ = E.sort_pairs(keys, max(1, int(c.nvoxels - 1).bit_length()) + attr_bits)
+    bad = status.to(torch.int64)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+    if int(bad.item()) & 2:
+        raise ValueError("Cannot compute 'mode' / 'mode_count' for negative or non-finite attribute values")
+    run_keys, run_w = E.run_lengths(ks)
+    rows = run_keys >> attr_bits  # partial row of every run; runs are in row order = destination order
+    payload = torch.stack([shard.gkeys[rows], run_keys & ((1 << attr_bits) - 1), run_w], dim=1).contiguous()  # [R, 3] int64
+    row_edges = [0]
+    for d in range(world):
+        row_edges.append(row_edges[-1] + (shard.n_own if d == rank else shard.send_remote[d]))
+    cuts = torch.searchsorted(rows.contiguous(), torch.tensor(row_edges, dtype=torch.int64, device=dev)).cpu().tolist()
+    send = [cuts[d + 1] - cuts[d] for d in range(world)]
+    own = payload[cuts[rank]:cuts[rank + 1]]
+    send[rank] = 0
+    send_t = torch.tensor(send, dtype=torch.int64, device=dev)
+    recv_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_t, send_t, group=group)
+    recv = recv_t.cpu().tolist()
+    out_p = torch.cat([payload[: cuts[rank]], payload[cuts[rank + 1]:]]).contiguous()
+    in_p = torch.empty((int(sum(recv)), 3), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(in_p, out_p, output_split_sizes=recv, input_split_sizes=send, group=group)
+    runs = torch.cat([own, in_p])
+    merged_row = _owner_rows(table, runs[:, 0])
+    comp = ((merged_row << attr_bits) | runs[:, 1]).contiguous()
+    cs, order = E.sort_pairs(comp, max(1, int(table.nvoxels - 1).bit_length()) + attr_bits)
+    weights = runs[:, 2][order.to(torch.int64) & 0xFFFFFFFF].to(torch.int32).contiguous()
+    mk, mw = E.run_lengths(cs, weights)
+    mode = torch.empty(table.nvoxels, dtype=torch.int64, device=dev) if want_mode else None
+    counts = {}
+    todo = list(thresholds) or [None]
+    for i, p in enumerate(todo):
+        mc = torch.empty(table.nvoxels, dtype=torch.int64, device=dev) if p is not None else None
+        L.call("vapc_mode_count_runs", E._ptr(mk), E._ptr(mw), mk.numel(), attr_bits, table.nvoxels, float(p if p is not None else 0.0),
+               E._ptr(mode if i == 0 else None), E._ptr(mc), E._stream())
+        if p is not None:
+            counts[p] = mc
+    return mode, counts

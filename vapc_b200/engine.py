@@ -460,6 +460,23 @@ class VoxelCloud:
         return round(self.nvoxels / (ext[0] * ext[1] * ext[2]) * 100, 2)
 
 
+def run_lengths(keys_sorted: torch.Tensor, weights: Optional[torch.Tensor] = None):
+    """(distinct keys, summed weights) of sorted 64-bit keys (vapc_run_lengths); weights: int32 per element or None = 1."""
+    dev = keys_sorted.device
+    n = keys_sorted.numel()
+    if n == 0:
+        return _empty(0, torch.int64, dev), _empty(0, torch.int64, dev)
+    ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
+    ws = _empty(ws_bytes, torch.uint8, dev)
+    nv = torch.zeros(1, dtype=torch.int64, device=dev)
+    L.call("vapc_count_voxels", _ptr(keys_sorted), n, 8, _ptr(nv), _ptr(ws), ws_bytes, _stream())
+    r = int(nv.item())
+    run_keys = _empty(r, torch.int64, dev)
+    run_weight = _empty(r, torch.int64, dev)
+    L.call("vapc_run_lengths", _ptr(keys_sorted), _ptr(weights), n, r, _ptr(run_keys), _ptr(run_weight), _ptr(ws), ws_bytes, _stream())
+    return run_keys, run_weight
+
+
 def attribute_statistics(cloud: VoxelCloud, attr, median=True) -> Dict[str, torch.Tensor]:
     """mean / sum / min / max / var / std (ddof = 0) / median of an fp64 attribute per voxel
     (vapc.py:393-406); [V] device tensors."""
