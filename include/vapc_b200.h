@@ -265,12 +265,12 @@ VAPC_API int vapc_gather_u32(const uint32_t* table, const uint32_t* index, int64
  * slices are the same [start[v], start[v+1]) as before.  vapc_mode_count then gives per voxel:
  * mode = smallest most frequent value (np.argmax(np.bincount)), mode_count = number of distinct
  * values whose share count / n >= threshold (fp64 division, as the reference).  Either output
- * nullable. */
+ * nullable.  key_bytes: 4 when voxel-row bits + attr_bits <= 32 (half the sort traffic), else 8. */
 VAPC_API int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, int64_t n, int32_t attr_bits,
-                   uint64_t* keys, int32_t* status, void* stream);
-VAPC_API int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t attr_bits, const uint32_t* start,
-                    int64_t nvoxels, double threshold, int64_t* mode, int64_t* mode_count,
-                    void* stream);
+                   int32_t key_bytes, void* keys, int32_t* status, void* stream);
+VAPC_API int vapc_mode_count(const void* keys_sorted, int64_t n, int32_t attr_bits, int32_t key_bytes,
+                    const uint32_t* start, int64_t nvoxels, double threshold, int64_t* mode,
+                    int64_t* mode_count, void* stream);
 
 /* mode / mode_count over N GPUs ("(key, value, count) runs instead of moments").  vapc_run_lengths: run-length
  * encoding of sorted 64-bit keys with optional weights (NULL = 1 each): run_keys[r] = r-th distinct key, run_weight[r] = sum of

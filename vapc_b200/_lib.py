@@ -107,8 +107,8 @@ SIGNATURES = {
     "vapc_point_distance": (C.c_int, [P, P, P, I64, P, P, I64, P, P]),
     "vapc_gather_f64": (C.c_int, [P, P, I64, P, P]),
     "vapc_gather_u32": (C.c_int, [P, P, I64, P, P]),
-    "vapc_mode_keys": (C.c_int, [P, P, I64, I32, P, P, P]),
-    "vapc_mode_count": (C.c_int, [P, I64, I32, P, I64, F64, P, P, P]),
+    "vapc_mode_keys": (C.c_int, [P, P, I64, I32, I32, P, P, P]),
+    "vapc_mode_count": (C.c_int, [P, I64, I32, I32, P, I64, F64, P, P, P]),
     "vapc_run_lengths": (C.c_int, [P, P, I64, I64, P, P, P, SZ, P]),
     "vapc_mode_count_runs": (C.c_int, [P, P, I64, I32, I64, F64, P, P, P]),
     "vapc_attr_stats": (C.c_int, [P, P, P, I64, P, P, P, P, P, P]),

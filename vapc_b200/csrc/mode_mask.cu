@@ -21,8 +21,9 @@ inline int grid_for(int64_t n, int per_thread = 4) {
 // ---- composite (voxel row, attribute value) keys ----------------------------------------------------
 // astype(int) truncates toward zero (vapc.py:409, :423); negative or too-large values are flagged
 // (np.bincount raises on negatives).
+template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) mode_keys_kernel(const uint32_t* __restrict__ p2v, const double* __restrict__ attr, int64_t n,
-                                                             int attr_bits, unsigned long long* __restrict__ keys, int* __restrict__ status) {
+                                                             int attr_bits, KeyT* __restrict__ keys, int* __restrict__ status) {
   int bad = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -30,13 +31,14 @@ __global__ void __launch_bounds__(kThreads) mode_keys_kernel(const uint32_t* __r
     const long long v = (long long)a;  // trunc toward zero
     if (!(a == a) || v < 0) bad |= 2;
     else if ((unsigned long long)v >> attr_bits) bad |= 4;
-    keys[i] = ((unsigned long long)p2v[i] << attr_bits) | ((unsigned long long)v & ((1ull << attr_bits) - 1ull));
+    keys[i] = (KeyT)(((unsigned long long)p2v[i] << attr_bits) | ((unsigned long long)v & ((1ull << attr_bits) - 1ull)));
   }
   if (bad) atomicOr(status, bad);
 }
 
 // One thread per voxel walks the voxel's (value-sorted) slice: runs of equal keys are the bincount.
-__global__ void __launch_bounds__(kThreads) mode_count_kernel(const unsigned long long* __restrict__ keys, int attr_bits,
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) mode_count_kernel(const KeyT* __restrict__ keys, int attr_bits,
                                                               const uint32_t* __restrict__ start, int64_t nvox, double threshold,
                                                               long long* __restrict__ mode, long long* __restrict__ mode_count) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,11 +49,11 @@ __global__ void __launch_bounds__(kThreads) mode_count_kernel(const unsigned lon
   long long best_val = 0, best_cnt = 0, above = 0;
   int64_t p = a;
   while (p < b) {
-    const unsigned long long k = keys[p];
+    const KeyT k = keys[p];
     int64_t q = p + 1;
     while (q < b && keys[q] == k) ++q;
     const long long cnt = (long long)(q - p);
-    if (cnt > best_cnt) { best_cnt = cnt; best_val = (long long)(k & mask); }  // first maximum = smallest value (np.argmax)
+    if (cnt > best_cnt) { best_cnt = cnt; best_val = (long long)((unsigned long long)k & mask); }  // first maximum = smallest value (np.argmax)
     if ((double)cnt / total >= threshold) ++above;                              // counts / counts_sum >= percentage
     p = q;
   }
@@ -252,23 +254,31 @@ inline int ilog2_ceil(int64_t v) {
 }
 }  // namespace
 
-extern "C" int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, int64_t n, int32_t attr_bits, uint64_t* keys,
+extern "C" int vapc_mode_keys(const uint32_t* point2voxel, const double* attr, int64_t n, int32_t attr_bits, int32_t key_bytes, void* keys,
                               int32_t* status, void* stream) {
-  if (n < 0 || attr_bits < 1 || attr_bits > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_keys: bad arguments (attr_bits in 1..32)");
+  if (n < 0 || attr_bits < 1 || attr_bits > 32 || (key_bytes != 4 && key_bytes != 8))
+    return vapc_set_error(VAPC_E_INVALID, "vapc_mode_keys: bad arguments (attr_bits in 1..32, key_bytes 4 or 8)");
   if (n == 0) return VAPC_OK;
-  VAPC_LAUNCH(mode_keys_kernel, grid_for(n), kThreads, 0, as_stream(stream), point2voxel, attr, n, attr_bits,
-                                                                    reinterpret_cast<unsigned long long*>(keys), status);
+  if (key_bytes == 4)
+    VAPC_LAUNCH(mode_keys_kernel<uint32_t>, grid_for(n), kThreads, 0, as_stream(stream), point2voxel, attr, n, attr_bits, static_cast<uint32_t*>(keys), status);
+  else
+    VAPC_LAUNCH(mode_keys_kernel<unsigned long long>, grid_for(n), kThreads, 0, as_stream(stream), point2voxel, attr, n, attr_bits,
+                static_cast<unsigned long long*>(keys), status);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
 
-extern "C" int vapc_mode_count(const uint64_t* keys_sorted, int64_t n, int32_t attr_bits, const uint32_t* start, int64_t nvoxels,
+extern "C" int vapc_mode_count(const void* keys_sorted, int64_t n, int32_t attr_bits, int32_t key_bytes, const uint32_t* start, int64_t nvoxels,
                                double threshold, int64_t* mode, int64_t* mode_count, void* stream) {
-  if (n < 0 || nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count: bad arguments");
+  if (n < 0 || nvoxels < 0 || (key_bytes != 4 && key_bytes != 8)) return vapc_set_error(VAPC_E_INVALID, "vapc_mode_count: bad arguments");
   if (nvoxels == 0) return VAPC_OK;
-  VAPC_LAUNCH(mode_count_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), 
-      reinterpret_cast<const unsigned long long*>(keys_sorted), attr_bits, start, nvoxels, threshold,
-      reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
+  const unsigned blocks = (unsigned)((nvoxels + kThreads - 1) / kThreads);
+  if (key_bytes == 4)
+    VAPC_LAUNCH(mode_count_kernel<uint32_t>, blocks, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(keys_sorted), attr_bits, start, nvoxels,
+                threshold, reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
+  else
+    VAPC_LAUNCH(mode_count_kernel<unsigned long long>, blocks, kThreads, 0, as_stream(stream), static_cast<const unsigned long long*>(keys_sorted), attr_bits,
+                start, nvoxels, threshold, reinterpret_cast<long long*>(mode), reinterpret_cast<long long*>(mode_count));
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

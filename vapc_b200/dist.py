@@ -533,7 +533,7 @@ def mode_count(table: ShardedVoxelTable, shard: LocalShard, attr, thresholds: Se
         raise ValueError("attribute values too large for mode / mode_count")
     keys = torch.empty(c.n, dtype=torch.int64, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    L.call("vapc_mode_keys", E._ptr(c.point2voxel), E._ptr(a), c.n, attr_bits, E._ptr(keys), E._ptr(status), E._stream())
+    L.call("vapc_mode_keys", E._ptr(c.point2voxel), E._ptr(a), c.n, attr_bits, 8, E._ptr(keys), E._ptr(status), E._stream())
     ks, _ = E.sort_pairs(keys, max(1, int(c.nvoxels - 1).bit_length()) + attr_bits)
     bad = status.to(torch.int64)
     dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)

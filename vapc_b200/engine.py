@@ -436,9 +436,10 @@ class VoxelCloud:
         if attr_bits > 32:
             raise ValueError("attribute values too large for mode / mode_count")
         vbits = max(1, int(self.nvoxels - 1).bit_length())
-        keys = _empty(self.n, torch.int64, dev)
+        kb = 4 if vbits + attr_bits <= 32 else 8  # (voxel row, value) keys of <= 32 bits: half the sort traffic
+        keys = _empty(self.n, torch.int32 if kb == 4 else torch.int64, dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.call("vapc_mode_keys", _ptr(self.point2voxel), _ptr(a), self.n, attr_bits, _ptr(keys), _ptr(status), _stream())
+        L.call("vapc_mode_keys", _ptr(self.point2voxel), _ptr(a), self.n, attr_bits, kb, _ptr(keys), _ptr(status), _stream())
         ks, _ = sort_pairs(keys, vbits + attr_bits)
         if int(status.item()) & 2:
             raise ValueError("Cannot compute 'mode' / 'mode_count' for negative or non-finite attribute values")
@@ -447,7 +448,7 @@ class VoxelCloud:
         todo = list(thresholds) or [None]
         for i, p in enumerate(todo):
             mc = _empty(self.nvoxels, torch.int64, dev) if p is not None else None
-            L.call("vapc_mode_count", _ptr(ks), self.n, attr_bits, _ptr(self.start), self.nvoxels, float(p if p is not None else 0.0),
+            L.call("vapc_mode_count", _ptr(ks), self.n, attr_bits, kb, _ptr(self.start), self.nvoxels, float(p if p is not None else 0.0),
                    _ptr(mode if i == 0 else None), _ptr(mc), _stream())
             if p is not None:
                 counts[p] = mc
