@@ -88,16 +88,26 @@ __global__ void bucket_start_kernel(const uint32_t* __restrict__ digit_base, int
 // The tile's records reordered by bucket, as columns: coordinates, key and the 16-bit input slot of every point (64-bit
 // shared-memory stores per column measured 4 % faster than one 32-byte record store; a fourth CTA per SM — 55 KB each —
 // needs 64 registers per thread and loses more to spills than it gains).
+#ifndef VAPC_BUCKET_TMA
+#define VAPC_BUCKET_TMA 0
+#endif
 template <typename KeyT>
 struct BucketSmem {
   RankSmem r;
-  alignas(16) union {
+  alignas(32) union {
     MaskBuffers masks;
+#if VAPC_BUCKET_TMA
+    struct {
+      double4 rec[kTile];  // whole records in bucket order: a bucket's run leaves as ONE bulk copy (TMA) instead of 32-byte stores
+      KeyT key[kTile];
+    } rec;
+#else
     struct {
       double x[kTile], y[kTile], z[kTile];
       KeyT key[kTile];
       unsigned short slot[kTile];
     } rec;
+#endif
   } u;
 };
 
@@ -147,6 +157,40 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
   // that a bucket's run leaves as whole 128-byte lines: scattered single-sector stores were measured at a quarter of
   // the HBM write bandwidth (profiles/).
   const unsigned* wc = sm.r.warp_cnt[warp];
+#if VAPC_BUCKET_TMA
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
+    unsigned long long w = (uint32_t)tile_base + (uint32_t)(slot0 + k * 32);
+    if (sizeof(KeyT) == 4) w |= (unsigned long long)key[k] << 32;
+    sm.u.rec.rec[pos] = make_double4(px[k], py[k], pz[k], __longlong_as_double((long long)w));
+    sm.u.rec.key[pos] = key[k];
+  }
+  const LookT excl = look_back<LookT>(mine, (int64_t)tile, run);
+  sm.r.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
+  // the records were written through the generic proxy; the bulk copies read them through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int tile_n = (int)min((int64_t)kTile, n - tile_base);
+  {
+    // thread == bucket: its run [bstart, bstart + run) of the tile goes to rec_b[digit_base + excl ...] as one bulk copy
+    const int end = min((int)(bstart + run), tile_n);
+    if (end > (int)bstart) {
+      const unsigned bytes = (unsigned)(end - (int)bstart) * 32u;
+      const unsigned src = (unsigned)__cvta_generic_to_shared(&sm.u.rec.rec[bstart]);
+      double4* dst = rec_b + (digit_base[tid] + (unsigned)excl);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+#pragma unroll 3
+  for (int p = tid; p < tile_n; p += kThreads) {
+    const KeyT k = sm.u.rec.key[p];
+    const unsigned dst = (unsigned)p + sm.r.delta[bucket_of(k, shift, mask)];
+    keys_b[dst] = sizeof(KeyOutT) < sizeof(KeyT) ? (KeyOutT)(k & (((KeyT)1 << shift) - 1)) : (KeyOutT)k;
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the copies
+#else
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
@@ -172,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
     st_record(rec_b + dst, sm.u.rec.x[p], sm.u.rec.y[p], sm.u.rec.z[p], __longlong_as_double((long long)w));
     keys_b[dst] = sizeof(KeyOutT) < sizeof(KeyT) ? (KeyOutT)(k & (((KeyT)1 << shift) - 1)) : (KeyOutT)k;
   }
+#endif
 }
 
 // full sorted keys from the sorted low parts: key = bucket << low_bits | low, the bucket of a position from bucket_start
