@@ -436,7 +436,10 @@ class VoxelCloud:
         if attr_bits > 32:
             raise ValueError("attribute values too large for mode / mode_count")
         vbits = max(1, int(self.nvoxels - 1).bit_length())
-        kb = 4 if vbits + attr_bits <= 32 else 8  # (voxel row, value) keys of <= 32 bits: half the sort traffic
+        # large voxels (hundreds of points each): the one-thread-per-voxel run scan of vapc_mode_count would walk them serially;
+        # the (voxel, value) runs are encoded by a point-parallel pass instead and evaluated per voxel (vapc_mode_count_runs)
+        by_runs = self.n > 256 * self.nvoxels
+        kb = 4 if vbits + attr_bits <= 32 and not by_runs else 8  # (voxel row, value) keys of <= 32 bits: half the sort traffic
         keys = _empty(self.n, torch.int32 if kb == 4 else torch.int64, dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         L.call("vapc_mode_keys", _ptr(self.point2voxel), _ptr(a), self.n, attr_bits, kb, _ptr(keys), _ptr(status), _stream())
@@ -446,8 +449,16 @@ class VoxelCloud:
         mode = _empty(self.nvoxels, torch.int64, dev) if want_mode else None
         counts = {}
         todo = list(thresholds) or [None]
+        if by_runs:
+            run_keys, run_weight = run_lengths(ks)
         for i, p in enumerate(todo):
             mc = _empty(self.nvoxels, torch.int64, dev) if p is not None else None
+            if by_runs:
+                L.call("vapc_mode_count_runs", _ptr(run_keys), _ptr(run_weight), run_keys.numel(), attr_bits, self.nvoxels,
+                       float(p if p is not None else 0.0), _ptr(mode if i == 0 else None), _ptr(mc), _stream())
+                if p is not None:
+                    counts[p] = mc
+                continue
             L.call("vapc_mode_count", _ptr(ks), self.n, attr_bits, kb, _ptr(self.start), self.nvoxels, float(p if p is not None else 0.0),
                    _ptr(mode if i == 0 else None), _ptr(mc), _stream())
             if p is not None:
