@@ -36,8 +36,8 @@ EXTENT = (50.0, 50.0, 4.0)  # metres: 500 x 500 x 40 voxels = 1e7 cells -> ~10 p
 QUANT = 1e-4  # LAS-like coordinate quantisation
 # DRAM traffic per launch of the big kernels at the default workload, from the committed `ncu --set full` capture
 # (profiles/README.md says which file); reported next to the algorithmic bytes of the dominant kernel
-NCU_TRAFFIC_GB = {  # profiles/r1_e_ncu_full.csv (1e8 points, 9 999 543 voxels, 24-bit keys)
-    "bucket_scatter_kernel": 6.41, "reduce_moments_kernel": 5.27, "onesweep_kernel": 1.40, "voxel_stats_kernel": 2.90,
+NCU_TRAFFIC_GB = {  # profiles/r1_f_ncu_full.csv (1e8 points, 9 999 543 voxels, 24-bit keys)
+    "bucket_scatter_kernel": 6.42, "reduce_moments_kernel": 5.27, "onesweep_kernel": 1.40, "voxel_stats_kernel": 2.90,
     "keys_hist_kernel": 2.75, "p2v_lookup_kernel": 0.76, "minmax_partial": 2.40, "digit_hist_kernel": 0.40, "count_heads_kernel": 0.40,
 }
 
