@@ -100,6 +100,22 @@ def _worker(rank, world, port, ret):
         assert np.array_equal(mn.astype(np.int64), gc[sel].astype(np.int64))
         np.testing.assert_allclose(mm[:, :3], gm[sel][:, :3], rtol=0, atol=1e-12)
         np.testing.assert_allclose(mm[:, 3:], gm[sel][:, 3:], rtol=1e-9, atol=1e-15)
+        # reverse exchange (D.rows_from_owner): a column of the merged table comes back to every local partial row — the rows a
+        # rank owns itself locally, the rows it sent away answered by their owners in one all-to-all
+        off = np.concatenate([[0], np.cumsum(recv_counts)])
+        remote = np.concatenate([rk[off[s]:off[s + 1]] for s in range(world) if s != rank]) if world > 1 else rk[:0]
+        table = D.ShardedVoxelTable(grid=None, nvoxels=len(mk), voxel_keys=torch.from_numpy(mk.astype(np.int64)), count=None, mean3=None, m2=None,
+                                    thresholds=thresholds, partial_rows_sent=0, partial_rows_received=len(remote))
+        shard = D.LocalShard(cloud=None, gkeys=torch.from_numpy(key), lo=int(sum(send[:rank])), n_own=int(send[rank]),
+                             send_remote=[0 if d == rank else int(c) for d, c in enumerate(send)],
+                             recv_remote=[0 if d == rank else int(c) for d, c in enumerate(recv_counts)],
+                             recv_keys=torch.from_numpy(remote.astype(np.int64)), group=None)
+        cols = torch.from_numpy(np.stack([mn.astype(np.float64), mm[:, 0]]))  # merged count and mean_x of every owned voxel
+        per_row = D.rows_from_owner(table, shard, cols).numpy()
+        where = np.searchsorted(gk, key)
+        assert np.array_equal(gk[where], key)
+        assert np.array_equal(per_row[0].astype(np.int64), gc[where].astype(np.int64)), "every partial row sees its voxel's global count"
+        np.testing.assert_allclose(per_row[1], gm[where, 0], rtol=0, atol=1e-12)
         # second epoch over the SAME key ranges (D.two_epoch_change): destination counts from the given thresholds, the
         # send-count matrix by one all-gather; afterwards the voxel join is local to the owner
         pts2 = np.round(np.concatenate([pts[: n // 2] + rng.normal(0, 0.05, (n // 2, 3)), rng.uniform([10, 0, 0], [30, 20, 4], (n // 8, 3))]), 3)
