@@ -122,8 +122,8 @@ def run_reference_arm(args):
     cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     budget = 150.0 / max(1, args.steps + args.warmup)  # seconds per step
     n_sample = args.cpu_sample or int(min(200_000, max(2_000, budget * 5_000)))
-    _, _, _, what = gen_crop_host(1000)
-    what = what.replace("1000 points", f"{n_sample} points per core")
+    _, _, _, what = gen_crop_host(n_sample)
+    what = what.replace(f"{n_sample} points", f"{n_sample} points per core")
     nvox = 0
     with ProcessPoolExecutor(max_workers=cores) as pool:
         for _ in range(args.warmup):
