@@ -178,3 +178,49 @@ def test_config5_mode_count_and_subsample_sweep(E, vs):
     assert bool(((md - best).abs() <= 1e-9 * best + 1e-12).all()), "minimum distance per voxel"
     assert bool((dist[am] <= best * (1 + 1e-9) + 1e-12).all()), "the selected point attains it"
     torch.cuda.empty_cache()
+
+
+def test_one_billion_points_on_one_gpu(E):
+    """north_star: "on 1e9 synthetic points".  One B200 holds the whole cloud (98 GiB peak): the n >= 2^30 paths (64-bit
+    look-back words, 28-bit rank-bitmap point->voxel map) at full size, checked through size-independent properties and a
+    sample of voxels recomputed from their points."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 130 * 2 ** 30:
+        pytest.skip("needs 130 GiB of free device memory")
+    n, vs = 1_000_000_000, 0.1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cols = []
+    for hi in (5_000_000, 500_000, 40_000):  # 500 m x 50 m x 4 m: the density of the bench line
+        q = torch.randint(0, hi, (n,), device="cuda", generator=g, dtype=torch.int32)
+        cols.append(q.to(torch.float64) * 1e-4)
+        del q
+    cloud = E.VoxelCloud.build(*cols, vs, (0.0, 0.0, 0.0))
+    V = cloud.nvoxels
+    assert 9.9e7 < V < 1.0e8 and cloud.grid.total_bits == 28
+    assert int(_u32(cloud.count).sum().item()) == n, "checksum of the counts"
+    keys = _u32(cloud.voxel_keys)
+    assert bool((keys[1:] > keys[:-1]).all()), "voxel rows strictly ascending"
+    start = _u32(cloud.start)
+    assert int(start[0]) == 0 and int(start[-1]) == n and torch.equal(start[1:] - start[:-1], _u32(cloud.count))
+    # every point's voxel row holds the point: its voxel triple equals the row's triple (1e6 sampled points)
+    sample = torch.randint(0, n, (1_000_000,), device="cuda", generator=g)
+    rows = _u32(cloud.point2voxel[sample])
+    vs_t = torch.full((1,), vs, dtype=torch.float64, device="cuda")
+    for c, v in zip(cols, cloud.voxel_coords()):
+        assert torch.equal(torch.floor(c[sample] / vs_t).to(torch.int64), v[rows])
+    st = cloud.stats(cog=True, cov=True, eig=True)
+    # 64 voxels recomputed from all their points (found through the point -> voxel map)
+    pick = torch.randint(0, V, (64,), device="cuda", generator=g).unique()
+    member = torch.isin(cloud.point2voxel, pick.to(torch.int32))
+    idx = torch.nonzero(member).flatten()
+    r = _u32(cloud.point2voxel[idx])
+    for k, c in enumerate(cols):
+        pts = c[idx]
+        for row in pick.tolist():
+            sel = pts[r == row]
+            assert sel.numel() == int(_u32(cloud.count[row:row + 1]))
+            assert abs(float(sel.mean()) - float(st.cog[k, row])) <= 1e-9 * max(1.0, abs(float(sel.mean())))
+    multi = _u32(cloud.count) > 1
+    eig = st.eig[:, multi]
+    trace = st.cov[0, multi] + st.cov[3, multi] + st.cov[5, multi]
+    assert bool(((eig.sum(0) - trace).abs() <= 1e-9 * trace.abs() + 1e-18).all()), "sum of eigenvalues = trace"
