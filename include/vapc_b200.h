@@ -343,7 +343,10 @@ VAPC_API int vapc_mahalanobis(const double* cog3_1, const double* cov6_1, int64_
  * vapc_cell_nn: exact nearest neighbour of every query point (bi_vapc.py:173-186 mutual_nearest_neighbors and
  * :51-74 merge_vapcs_with_closest_point: the KDTree.query(k=1) calls).  nn_idx = original index of the nearest point
  * of the set (lowest index among exactly equidistant ones), nn_dist = sqrt(dx*dx + dy*dy + dz*dz) formed like scipy's
- * KD-tree forms it (plain products, left-to-right sum).  Queries may lie outside the set's bounding box.
+ * KD-tree forms it (plain products, left-to-right sum).  Queries may lie outside the set's bounding box.  bounded != 0: a
+ * query whose neighbour is farther than ~8 cells is given up (nn_idx = 0xFFFFFFFF, nn_dist = inf) instead of scanning ever
+ * larger cubes — a grid degenerates to a scan of the whole set per query there; vapc_nn_all_pairs (tiled all-pairs search
+ * over the listed queries `which`, same distances and tie rule) finishes those with a bounded cost.
  *
  * vapc_cluster_components: connected components of the graph "distance <= cluster_distance" between the n units of
  * the set (vapc.py:1274-1357 compute_clusters: KD-tree region growing, labels merged to the lowest).  Needs
@@ -355,7 +358,9 @@ VAPC_API int vapc_mahalanobis(const double* cog3_1, const double* cov6_1, int64_
  * and at index root: comp_first = lowest `first` of the component, comp_size = its number of points. */
 VAPC_API int vapc_cell_nn(const double* qx, const double* qy, const double* qz, int64_t nq, const vapc_grid_t* grid_host,
                  const void* cell_keys, int64_t ncells, const uint32_t* start, const uint32_t* pos_sorted,
-                 const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist, void* stream);
+                 const double* xyzw, int64_t n, int32_t bounded, uint32_t* nn_idx, double* nn_dist, void* stream);
+VAPC_API int vapc_nn_all_pairs(const double* qx, const double* qy, const double* qz, const int64_t* which, int64_t nwhich,
+                      const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist, void* stream);
 VAPC_API size_t vapc_cluster_workspace_bytes(int64_t n);
 VAPC_API int vapc_cluster_components(const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
                             const uint32_t* pos_sorted, const double* xyzw, int64_t n, double distance,
@@ -364,7 +369,8 @@ VAPC_API int vapc_cluster_components(const vapc_grid_t* grid_host, const void* c
 /* the same code run serially on HOST arrays (CPU tests of the traversal logic) */
 VAPC_API int vapc_selftest_cell_nn_host(const double* qx, const double* qy, const double* qz, int64_t nq,
                                const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
-                               const uint32_t* pos_sorted, const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist);
+                               const uint32_t* pos_sorted, const double* xyzw, int64_t n, int32_t bounded, uint32_t* nn_idx,
+                               double* nn_dist);
 VAPC_API int vapc_selftest_cluster_host(const vapc_grid_t* grid_host, const void* cell_keys, int64_t ncells, const uint32_t* start,
                                const uint32_t* pos_sorted, const double* xyzw, int64_t n, double distance,
                                const uint32_t* first, const uint32_t* weight, uint32_t* root, uint32_t* hop2_first,

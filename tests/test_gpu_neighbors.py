@@ -137,3 +137,21 @@ def test_clusters_equal_components_at_scale(kind, n, d):
     # run-to-run identical (the union-find is order-free: roots are component minima)
     label2, size2, _ = E.cluster_components(rows[:, 0].copy(), rows[:, 1].copy(), rows[:, 2].copy(), d, integer_rows=(kind == "grid"))
     assert bool((label == label2).all()) and bool((size == size2).all())
+
+
+def test_nearest_neighbours_of_sets_far_apart():
+    """Two clouds 500 m apart (2000 cells): the grid search gives every query up, the tiled all-pairs kernel answers — still the
+    KD-tree's indices and distances, at a bounded cost (a pure grid search would scan the whole set per query)."""
+    from scipy.spatial import KDTree
+
+    from vapc_b200 import engine as E
+
+    rng = np.random.default_rng(12)
+    a = rng.random((30_000, 3)) * [20.0, 20.0, 3.0]
+    b = rng.random((25_000, 3)) * [20.0, 20.0, 3.0] + [520.0, 0.0, 0.0]
+    b[:50] = a[:50] + 0.01  # a few genuine neighbours inside the other cloud
+    cells = E._cell_cloud(b[:, 0].copy(), b[:, 1].copy(), b[:, 2].copy(), 0.25)
+    idx, dist = E.nearest_neighbors(a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy(), cells)
+    d_ref, i_ref = KDTree(b).query(a, k=1, workers=-1)
+    np.testing.assert_array_equal(idx.cpu().numpy(), i_ref)
+    np.testing.assert_array_equal(dist.cpu().numpy(), d_ref)

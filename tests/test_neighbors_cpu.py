@@ -36,14 +36,15 @@ def P(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def host_nn(q, pts, h):
+def host_nn(q, pts, h, bounded=False):
     from vapc_b200 import _lib as L
 
     g, keys, start, pos, rec = build_cell_list(pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), h)
     qx, qy, qz = (np.ascontiguousarray(q[:, k]) for k in range(3))
     idx = np.empty(len(q), np.uint32)
     dist = np.empty(len(q), np.float64)
-    L.call("vapc_selftest_cell_nn_host", P(qx), P(qy), P(qz), len(q), C.byref(g), P(keys), len(keys), P(start), P(pos), P(rec), len(pts), P(idx), P(dist))
+    L.call("vapc_selftest_cell_nn_host", P(qx), P(qy), P(qz), len(q), C.byref(g), P(keys), len(keys), P(start), P(pos), P(rec), len(pts), int(bounded),
+           P(idx), P(dist))
     return idx.astype(np.int64), dist
 
 
@@ -132,3 +133,21 @@ def test_clusters_over_weighted_units_equal_clusters_over_their_points():
     cid, csz = labels_from(root, hop2, cfirst, csize, first=first)
     np.testing.assert_array_equal(cid[inv.ravel()], ref_id.astype(np.int64))
     np.testing.assert_array_equal(csz[inv.ravel()], ref_size.astype(np.int64))
+
+
+def test_bounded_search_gives_up_only_on_far_neighbours():
+    """bounded mode (what the GPU path runs first): near queries get the exact answer, queries whose neighbour is many cells away
+    are handed back (index 0xFFFFFFFF) for the all-pairs kernel — never a wrong answer."""
+    from scipy.spatial import KDTree
+
+    rng = np.random.default_rng(8)
+    pts = rng.random((20000, 3)) * [20.0, 10.0, 2.0]
+    q = np.concatenate([rng.random((3000, 3)) * [20.0, 10.0, 2.0], rng.random((500, 3)) * [20.0, 10.0, 2.0] + [60.0, 0.0, 0.0]])
+    h = 0.25
+    idx, dist = host_nn(q, pts, h, bounded=True)
+    d_ref, i_ref = KDTree(pts).query(q, k=1)
+    given_up = idx == 0xFFFFFFFF
+    assert given_up[3000:].all() and not given_up[:3000].any()  # 40 m = 160 cells away / inside the cloud
+    np.testing.assert_array_equal(idx[~given_up], i_ref[~given_up])
+    np.testing.assert_array_equal(dist[~given_up], d_ref[~given_up])
+    assert np.isinf(dist[given_up]).all()

@@ -122,10 +122,11 @@ SIGNATURES = {
     "vapc_buffer_expand": (C.c_int, [P, P, P, I64, I32, P, P]),
     "vapc_join_sorted_keys": (C.c_int, [P, I64, P, I64, P, P, P]),
     "vapc_mahalanobis": (C.c_int, [P, P, I64, P, P, I64, P, P, I64, F64, P, P, P, P, P, P, P]),
-    "vapc_cell_nn": (C.c_int, [P, P, P, I64, GP, P, I64, P, P, P, I64, P, P, P]),
+    "vapc_cell_nn": (C.c_int, [P, P, P, I64, GP, P, I64, P, P, P, I64, I32, P, P, P]),
+    "vapc_nn_all_pairs": (C.c_int, [P, P, P, P, I64, P, I64, P, P, P]),
     "vapc_cluster_workspace_bytes": (SZ, [I64]),
     "vapc_cluster_components": (C.c_int, [GP, P, I64, P, P, P, I64, F64, P, P, P, P, P, P, P, SZ, P]),
-    "vapc_selftest_cell_nn_host": (C.c_int, [P, P, P, I64, GP, P, I64, P, P, P, I64, P, P]),
+    "vapc_selftest_cell_nn_host": (C.c_int, [P, P, P, I64, GP, P, I64, P, P, P, I64, I32, P, P]),
     "vapc_selftest_cluster_host": (C.c_int, [GP, P, I64, P, P, P, I64, F64, P, P, P, P, P, P]),
     "vapc_merge_partials": (C.c_int, [P, P, I64, I32, P, P, P, I64, I64, P, P, P, P, P, SZ, P]),
     "vapc_plan_exchange": (C.c_int, [P, I32, I32, I32, P, P]),

@@ -82,11 +82,13 @@ HD long long lower_bound_key(const KeyT* keys, long long n, KeyT k) {
   return lo;
 }
 
-// Calls f(record) for every point whose cell lies in the cube [c - r, c + r]^3 (clipped to the grid).  Falls back to
-// a linear pass over all records when the cube has more columns than that pass costs.  Returns true when every point
-// of the set has been visited (linear pass, or the cube covers the whole grid).
+// Calls f(record) for every point whose cell lies in the cube [c - r, c + r]^3 (clipped to the grid).  When the cube has
+// more columns than a linear pass over all records costs, that pass is made instead — or, with allow_linear == false,
+// nothing is visited and kRefused is returned (the caller hands the query to the tiled all-pairs kernel).  kAll: every
+// point of the set has been visited (linear pass, or the cube covers the whole grid).
+enum { kVisited = 0, kAll = 1, kRefused = 2 };
 template <typename KeyT, typename F>
-HD bool visit_cube(const CellList<KeyT>& cl, long long cx, long long cy, long long cz, long long r, F&& f) {
+HD int visit_cube(const CellList<KeyT>& cl, long long cx, long long cy, long long cz, long long r, F&& f, bool allow_linear = true) {
   const Grid& g = cl.g;
   const long long ex = axis_cells(g.bx), ey = axis_cells(g.by), ez = axis_cells(g.bz);
   long long x0 = cx - r - g.minx, x1 = cx + r - g.minx;
@@ -95,11 +97,12 @@ HD bool visit_cube(const CellList<KeyT>& cl, long long cx, long long cy, long lo
   const bool all = x0 <= 0 && y0 <= 0 && z0 <= 0 && x1 >= ex - 1 && y1 >= ey - 1 && z1 >= ez - 1;
   x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0; z0 = z0 < 0 ? 0 : z0;
   x1 = x1 > ex - 1 ? ex - 1 : x1; y1 = y1 > ey - 1 ? ey - 1 : y1; z1 = z1 > ez - 1 ? ez - 1 : z1;
-  if (x0 > x1 || y0 > y1 || z0 > z1) return all;
+  if (x0 > x1 || y0 > y1 || z0 > z1) return all ? kAll : kVisited;
   const double columns = (double)(x1 - x0 + 1) * (double)(y1 - y0 + 1);
   if (all || columns * 24.0 > (double)cl.n) {
+    if (!allow_linear && cl.n > 4096) return kRefused;
     for (long long p = 0; p < cl.n; ++p) f(cl.rec[p]);
-    return true;
+    return kAll;
   }
   for (long long x = x0; x <= x1; ++x) {
     for (long long y = y0; y <= y1; ++y) {
@@ -112,15 +115,18 @@ HD bool visit_cube(const CellList<KeyT>& cl, long long cx, long long cy, long lo
       for (uint32_t p = p0; p < p1; ++p) f(cl.rec[cl.pos[p]]);
     }
   }
-  return false;
+  return kVisited;
 }
 
 // ---- exact nearest neighbour ------------------------------------------------------------------------------
 // Cube of radius 1 first; a candidate at distance <= r h is final (everything outside the cube is farther than
 // r h); otherwise one more cube of radius ceil(best / h) holds the true neighbour.  Nothing found: double r.
 // Ties: the lowest original index (a KD-tree's choice among exactly equidistant points is traversal order).
+// bounded: the grid search gives up (index 0xffffffff) when the neighbour is farther than ~8 cells — a grid degenerates
+// to a scan of the whole set per query there; those queries go to the tiled all-pairs kernel, whose cost is bounded.
+constexpr long long kMaxEmptyRadius = 4, kMaxFinalRadius = 8;
 template <typename KeyT>
-HD void cell_nn_one(const CellList<KeyT>& cl, double qx, double qy, double qz, uint32_t* idx_out, double* dist_out) {
+HD void cell_nn_one(const CellList<KeyT>& cl, double qx, double qy, double qz, bool bounded, uint32_t* idx_out, double* dist_out) {
   const Grid& g = cl.g;
   const long long cx = cell_of(qx, g.ox, g.vs), cy = cell_of(qy, g.oy, g.vs), cz = cell_of(qz, g.oz, g.vs);
   double best2 = INFINITY;
@@ -130,21 +136,26 @@ HD void cell_nn_one(const CellList<KeyT>& cl, double qx, double qy, double qz, u
     const uint32_t j = rec_index(b);
     if (d2 < best2 || (d2 == best2 && j < besti)) { best2 = d2; besti = j; }
   };
+  bool refused = false;
   long long r = 1;
   for (int guard = 0; guard < 64; ++guard) {
-    if (visit_cube(cl, cx, cy, cz, r, f)) break;
+    const int st = visit_cube(cl, cx, cy, cz, r, f, !bounded);
+    if (st == kRefused) { refused = true; break; }
+    if (st == kAll) break;
     if (best2 < INFINITY) {
       const double bound = (double)r * g.vs;
       if (best2 <= bound * bound * (1.0 - 1e-9)) break;
       long long big = (long long)ceil(root_of(best2) / g.vs * (1.0 + 1e-9));
       if (big <= r) big = r + 1;
-      visit_cube(cl, cx, cy, cz, big, f);
+      if (bounded && big > kMaxFinalRadius) { refused = true; break; }
+      if (visit_cube(cl, cx, cy, cz, big, f, !bounded) == kRefused) refused = true;
       break;
     }
+    if (bounded && r >= kMaxEmptyRadius) { refused = true; break; }
     r = r < (1ll << 40) ? r * 2 : r;
   }
-  *idx_out = besti;
-  *dist_out = root_of(best2);
+  *idx_out = refused ? 0xffffffffu : besti;
+  *dist_out = refused ? INFINITY : root_of(best2);
 }
 
 // ---- connected components -----------------------------------------------------------------------------------
@@ -224,15 +235,47 @@ HD void cluster_hop2_one(const CellList<KeyT>& cl, long long p, double dist, con
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) cell_nn_kernel(CellList<KeyT> cl, const double* __restrict__ qx, const double* __restrict__ qy,
-                                                           const double* __restrict__ qz, long long nq, uint32_t* __restrict__ nn_idx,
-                                                           double* __restrict__ nn_dist) {
+                                                           const double* __restrict__ qz, long long nq, bool bounded,
+                                                           uint32_t* __restrict__ nn_idx, double* __restrict__ nn_dist) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   uint32_t idx;
   double d;
-  cell_nn_one(cl, qx[i], qy[i], qz[i], &idx, &d);
+  cell_nn_one(cl, qx[i], qy[i], qz[i], bounded, &idx, &d);
   nn_idx[i] = idx;
   nn_dist[i] = d;
+}
+
+// Tiled all-pairs search for the queries the grid search gave up on (which[] lists them): every thread keeps one query,
+// the CTA streams the records through shared memory.  Same distance formula, same tie rule.
+__global__ void __launch_bounds__(kThreads) nn_brute_kernel(const double4* __restrict__ rec, long long n, const double* __restrict__ qx,
+                                                            const double* __restrict__ qy, const double* __restrict__ qz,
+                                                            const long long* __restrict__ which, long long nwhich, uint32_t* __restrict__ nn_idx,
+                                                            double* __restrict__ nn_dist) {
+  __shared__ double4 tile[kThreads];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < nwhich;
+  const long long q = active ? which[t] : 0;
+  const double ax = active ? qx[q] : 0.0, ay = active ? qy[q] : 0.0, az = active ? qz[q] : 0.0;
+  double best2 = INFINITY;
+  uint32_t besti = 0xffffffffu;
+  for (long long base = 0; base < n; base += kThreads) {
+    const long long p = base + threadIdx.x;
+    if (p < n) tile[threadIdx.x] = rec[p];
+    __syncthreads();
+    const int m = (int)min((long long)kThreads, n - base);
+    for (int k = 0; k < m; ++k) {
+      const double4 b = tile[k];
+      const double d2 = dist2(ax, ay, az, b);
+      const uint32_t j = rec_index(b);
+      if (d2 < best2 || (d2 == best2 && j < besti)) { best2 = d2; besti = j; }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    nn_idx[q] = besti;
+    nn_dist[q] = root_of(best2);
+  }
 }
 
 __global__ void __launch_bounds__(256) cluster_init_kernel(uint32_t* parent, uint32_t* comp_first, unsigned long long* comp_size, long long n) {
@@ -326,7 +369,7 @@ void cluster_host(const CellList<KeyT>& cl, double dist, const uint32_t* first, 
 
 extern "C" int vapc_cell_nn(const double* qx, const double* qy, const double* qz, int64_t nq, const vapc_grid_t* grid_host,
                             const void* cell_keys, int64_t ncells, const uint32_t* start, const uint32_t* pos_sorted, const double* xyzw,
-                            int64_t n, uint32_t* nn_idx, double* nn_dist, void* stream) {
+                            int64_t n, int32_t bounded, uint32_t* nn_idx, double* nn_dist, void* stream) {
   if (nq < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_cell_nn: negative size");
   if (nq == 0) return VAPC_OK;
   if (const int rc = check_list("vapc_cell_nn", grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n)) return rc;
@@ -334,26 +377,38 @@ extern "C" int vapc_cell_nn(const double* qx, const double* qy, const double* qz
   const unsigned blocks = (unsigned)((nq + kThreads - 1) / kThreads);
   if (grid_host->key_bytes == 4) {
     VAPC_LAUNCH(cell_nn_kernel<uint32_t>, blocks, kThreads, 0, as_stream(stream), make_list<uint32_t>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n),
-                qx, qy, qz, (long long)nq, nn_idx, nn_dist);
+                qx, qy, qz, (long long)nq, bounded != 0, nn_idx, nn_dist);
   } else {
     VAPC_LAUNCH(cell_nn_kernel<unsigned long long>, blocks, kThreads, 0, as_stream(stream),
-                make_list<unsigned long long>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n), qx, qy, qz, (long long)nq, nn_idx, nn_dist);
+                make_list<unsigned long long>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n), qx, qy, qz, (long long)nq, bounded != 0, nn_idx,
+                nn_dist);
   }
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_nn_all_pairs(const double* qx, const double* qy, const double* qz, const int64_t* which, int64_t nwhich, const double* xyzw,
+                                 int64_t n, uint32_t* nn_idx, double* nn_dist, void* stream) {
+  if (nwhich < 0 || n <= 0) return vapc_set_error(VAPC_E_INVALID, "vapc_nn_all_pairs: bad sizes");
+  if (nwhich == 0) return VAPC_OK;
+  if (!qx || !qy || !qz || !which || !xyzw || !nn_idx || !nn_dist) return vapc_set_error(VAPC_E_INVALID, "vapc_nn_all_pairs: null argument");
+  VAPC_LAUNCH(nn_brute_kernel, (unsigned)((nwhich + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream), reinterpret_cast<const double4*>(xyzw),
+              (long long)n, qx, qy, qz, reinterpret_cast<const long long*>(which), (long long)nwhich, nn_idx, nn_dist);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
 
 extern "C" int vapc_selftest_cell_nn_host(const double* qx, const double* qy, const double* qz, int64_t nq, const vapc_grid_t* grid_host,
                                           const void* cell_keys, int64_t ncells, const uint32_t* start, const uint32_t* pos_sorted,
-                                          const double* xyzw, int64_t n, uint32_t* nn_idx, double* nn_dist) {
+                                          const double* xyzw, int64_t n, int32_t bounded, uint32_t* nn_idx, double* nn_dist) {
   if (nq < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_selftest_cell_nn_host: negative size");
   if (const int rc = check_list("vapc_selftest_cell_nn_host", grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n)) return rc;
   if (grid_host->key_bytes == 4) {
     const auto cl = make_list<uint32_t>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n);
-    for (int64_t i = 0; i < nq; ++i) cell_nn_one(cl, qx[i], qy[i], qz[i], nn_idx + i, nn_dist + i);
+    for (int64_t i = 0; i < nq; ++i) cell_nn_one(cl, qx[i], qy[i], qz[i], bounded != 0, nn_idx + i, nn_dist + i);
   } else {
     const auto cl = make_list<unsigned long long>(grid_host, cell_keys, ncells, start, pos_sorted, xyzw, n);
-    for (int64_t i = 0; i < nq; ++i) cell_nn_one(cl, qx[i], qy[i], qz[i], nn_idx + i, nn_dist + i);
+    for (int64_t i = 0; i < nq; ++i) cell_nn_one(cl, qx[i], qy[i], qz[i], bounded != 0, nn_idx + i, nn_dist + i);
   }
   return VAPC_OK;
 }

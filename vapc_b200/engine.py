@@ -719,7 +719,12 @@ def nearest_neighbors(qx, qy, qz, cells: VoxelCloud):
     idx = _empty(nq, torch.int32, dev)
     dist = _empty(nq, torch.float64, dev)
     L.call("vapc_cell_nn", _ptr(qx), _ptr(qy), _ptr(qz), nq, C.byref(cells.grid), _ptr(cells.voxel_keys), cells.nvoxels, _ptr(cells.start),
-           _ptr(cells.pos_sorted), _ptr(cells.xyzw), cells.n, _ptr(idx), _ptr(dist), _stream())
+           _ptr(cells.pos_sorted), _ptr(cells.xyzw), cells.n, 1, _ptr(idx), _ptr(dist), _stream())
+    # queries whose neighbour is many cells away (sets far apart, isolated outliers): a grid search degenerates there, a tiled
+    # all-pairs pass over just those queries has a bounded cost
+    far = torch.nonzero(idx == -1).flatten()
+    if far.numel():
+        L.call("vapc_nn_all_pairs", _ptr(qx), _ptr(qy), _ptr(qz), _ptr(far), far.numel(), _ptr(cells.xyzw), cells.n, _ptr(idx), _ptr(dist), _stream())
     return idx.to(torch.int64) & 0xFFFFFFFF, dist
 
 
