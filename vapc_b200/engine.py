@@ -770,6 +770,11 @@ def cluster_components(cx, cy, cz, cluster_distance: float, integer_rows: bool =
         del units
     n = cols[0].numel()
     cells = _cell_cloud(*cols, d * (1.0 + 2.0 ** -30) if d > 0 else 1.0)
+    # every unit visits the units of its 27 cells: ~27 n^2 / cells distance tests.  A cluster distance that spans most of the cloud
+    # makes that quadratic (the reference's sweep is slower still); refuse instead of occupying the GPU for hours
+    if 27.0 * n * n / max(cells.nvoxels, 1) > 2e13:
+        raise ValueError(f"compute_clusters: cluster_distance {d} spans too much of the cloud ({n} rows in {cells.nvoxels} cells of that size): "
+                         "the neighbourhood search would be quadratic")
     root, hop2, comp_first = (_empty(n, torch.int32, dev) for _ in range(3))
     comp_size = _empty(n, torch.int64, dev)
     ws_bytes = L.raw("vapc_cluster_workspace_bytes")(n)
