@@ -132,20 +132,17 @@ def test_do_vapc_on_files_and_main(V, tmp_path, save_as, capsys):
            "tile": 20, "reduce_to": "center_of_voxel", "save_as": save_as}
     cfg_path = str(tmp_path / "cfg.json")
     json.dump(cfg, open(cfg_path, "w"))
-    if save_as == ".laz":
-        with pytest.warns(UserWarning):
-            written = V.main([cfg_path])
-        assert written.endswith(".las")  # no LAZ backend in this image: stays uncompressed, with a warning
-    else:
-        written = V.main([cfg_path])
-        assert written.endswith(save_as)
+    written = V.main([cfg_path])
+    assert written.endswith(save_as)  # .laz: compressed by the library's own LASzip encoder (LAS 1.2 + extra bytes)
     assert os.path.exists(written) and os.path.basename(written).startswith("compute_")
     docs = glob.glob(os.path.join(outdir, "compute_*_cfg.json"))
     assert len(docs) == 1
     doc = json.load(open(docs[0]))
     assert doc["tool"] == "compute" and doc["voxel_size"] == 1.0 and doc["reduce_to"] == "center_of_voxel" and doc["tile"] == 20 and "vapc_version" in doc
     g = O.group_by_voxel(*O.voxelize(*(df[c].to_numpy() for c in "XYZ"), [0, 0, 0], 1.0))
-    if written.endswith(".las"):
+    if written.endswith((".las", ".laz")):
+        if save_as == ".laz":
+            assert V.las.read_las(written)[0].compressed and not os.path.exists(written.replace(".laz", ".las"))
         res = _read(V, written)
         assert len(res) == g.nvoxels and {"point_count", "cog_x", "cog_y", "cog_z"} <= set(res.columns)
     else:

@@ -117,11 +117,24 @@ def test_save_as_las_roundtrip(tmp_path):
     for c in ("point_count", "cov_xx"):  # extra dimensions are float32 (datahandler.py:157)
         np.testing.assert_array_equal(back.df[c].to_numpy(), df[c].to_numpy().astype(np.float32).astype(np.float64))
     assert back.df["scanner_channel"].eq(0).all() and back.df["overlap"].eq(0).all()  # not written (datahandler.py:152)
-    with pytest.raises(NotImplementedError):
-        dh.save_as_las(str(tmp_path / "out.laz"))
-    laz = out.replace(".las", ".laz")
-    os.rename(out, laz)  # an uncompressed file under a .laz name is read as what it is
-    assert las.read_las(laz)[0].point_count == n
+    # .laz: the library's own LASzip encoder (LAS 1.2, point format 0 / 2, the rest as extra bytes) and decoder
+    laz = str(tmp_path / "out.laz")
+    dh.save_as_las(laz)
+    assert os.path.getsize(laz) < os.path.getsize(out)
+    hz, _ = las.read_las(laz)
+    assert hz.compressed and hz.version == (1, 2) and hz.point_count == n and hz.laszip["items"][0] == (6, 20, 2) and hz.laszip["items"][-1][0] == 0
+    again = DataHandler(laz)
+    again.load_las_files()
+    for c in "XYZ":
+        assert np.abs(again.df[c].to_numpy() - df[c].to_numpy()).max() <= 0.000125 + 1e-9
+    for c in ("intensity", "classification", "return_number"):
+        np.testing.assert_array_equal(again.df[c].to_numpy(), df[c].to_numpy())
+    np.testing.assert_array_equal(again.df["gps_time"].to_numpy(), df["gps_time"].to_numpy())  # a float64 extra dimension
+    for c in ("point_count", "cov_xx"):
+        np.testing.assert_array_equal(again.df[c].to_numpy(), df[c].to_numpy().astype(np.float32).astype(np.float64))
+    plain = str(tmp_path / "plain.laz")
+    os.rename(out, plain)  # an uncompressed file under a .laz name is read as what it is
+    assert las.read_las(plain)[0].point_count == n
 
 
 def test_extra_bytes_vlr_types_and_empty_cloud(tmp_path):

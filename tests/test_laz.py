@@ -1,4 +1,4 @@
-"""The LASzip decoder (vapc_laz_decode, host code in libvapc_b200.so) against the reference's own LAZ fixtures.
+"""The LASzip codec (vapc_laz_decode / vapc_laz_encode, host code in libvapc_b200.so) against the reference's own LAZ fixtures.
 
 The fixtures are read where the reference lies (/root/reference/tests/test_data, build container only); nothing is
 copied.  On a box without the reference these tests skip — the decoded real data still travels as the golden fixture
@@ -54,6 +54,54 @@ def test_vapc_in_multi_chunk_known_answers():
     raw = np.stack([c["X"], c["Y"], c["Z"], c["red"], c["green"], c["blue"]], 1).astype(np.int64)
     assert raw.sum(0).tolist() == [7819251612, 8861305537, 6141071598314, 19648548864, 19063821312, 17777984512]
     assert hashlib.sha256(raw.tobytes()).hexdigest() == "313f0062c201ad4891ef0058c109c8e7716a777232e935a31aa2316de29761f7"
+
+
+@needs_fixtures
+@pytest.mark.parametrize("name", ["small_mask.laz", "vapc_in.laz"])
+def test_encoder_reproduces_laszip_byte_for_byte(name):
+    """Decode the reference's file, encode the records again: the point data of the file — 1 and 11 chunks of arithmetic-coded
+    POINT10 v2 + RGB12 v2 items and the chunk table — comes out identical to what LASzip wrote, byte for byte."""
+    import ctypes as C
+
+    from vapc_b200 import _lib as L
+
+    buf = open(os.path.join(DATA, name), "rb").read()
+    h = las.read_header(buf)
+    rec = las._decode_laz(buf, h)
+    items = np.array(h.laszip["items"], dtype=np.uint16).reshape(-1)
+    out = np.empty(len(buf), np.uint8)
+    nbytes = C.c_int64(0)
+    L.check(L.raw("vapc_laz_encode")(rec.ctypes.data_as(C.c_void_p), int(h.point_count), int(h.point_size), int(h.laszip["chunk_size"]),
+                                     items.ctypes.data_as(C.c_void_p), len(h.laszip["items"]), int(h.offset_to_points), out.ctypes.data_as(C.c_void_p),
+                                     len(out), C.byref(nbytes)))
+    assert nbytes.value == len(buf) - h.offset_to_points
+    assert out[: nbytes.value].tobytes() == buf[h.offset_to_points:]
+
+
+@pytest.mark.parametrize("n,chunk", [(0, 50000), (1, 50000), (2, 50000), (1000, 100), (1001, 100), (120_001, 50000)])
+@pytest.mark.parametrize("rgb", [False, True])
+def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb):
+    """write_laz -> read_las on synthetic clouds (runs anywhere): single points, exact chunk multiples, several chunks, with and
+    without colours, extra bytes of four types; constant and incompressible columns."""
+    rng = np.random.default_rng(n + chunk + rgb)
+    x, y, z = (np.round(rng.random(n) * s, 3) for s in (100.0, 50.0, 10.0))
+    std = dict(intensity=rng.integers(0, 65536, n), return_number=rng.integers(1, 4, n), number_of_returns=rng.integers(3, 8, n),
+               scan_direction_flag=rng.integers(0, 2, n), edge_of_flight_line=rng.integers(0, 2, n), classification=rng.integers(0, 32, n),
+               withheld=rng.integers(0, 2, n), scan_angle_rank=rng.integers(-90, 91, n), user_data=np.full(n, 7), point_source_id=rng.integers(0, 65536, n))
+    if rgb:
+        std.update(red=rng.integers(0, 65536, n), green=rng.integers(0, 256, n) * 256, blue=np.zeros(n, np.int64))
+    extra = dict(point_count=rng.integers(1, 60, n).astype(np.float32), noise=rng.random(n), small=rng.integers(-100, 100, n).astype(np.int16),
+                 big=rng.integers(0, 2 ** 62, n).astype(np.int64))
+    path = str(tmp_path / "t.laz")
+    las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk)
+    h, c = las.read_las(path)
+    assert h.compressed and h.point_format == (2 if rgb else 0) and h.point_count == n and h.laszip["chunk_size"] == chunk
+    for k, v in (("x", x), ("y", y), ("z", z)):
+        assert n == 0 or np.abs(c[k] - v).max() < 1e-9
+    for k, v in std.items():
+        np.testing.assert_array_equal(np.asarray(c[k]).astype(np.int64), np.asarray(v).astype(np.int64), err_msg=k)
+    for k, v in extra.items():
+        np.testing.assert_array_equal(c[k], v, err_msg=k)
 
 
 @needs_fixtures

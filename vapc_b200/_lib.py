@@ -138,6 +138,7 @@ SIGNATURES = {
     "vapc_reduce_candidates": (C.c_int, [P, P, P, I64, I64, P, P, P]),
     "vapc_key_histogram": (C.c_int, [P, I64, I32, I32, I32, P, P]),
     "vapc_laz_decode": (C.c_int, [P, I64, I64, I64, I32, I32, C.c_uint32, P, I32, P]),
+    "vapc_laz_encode": (C.c_int, [P, I64, I32, C.c_uint32, P, I32, I64, P, I64, C.POINTER(I64)]),
     "vapc_selftest_eig3_host": (C.c_int, [P, I64, P]),
     "vapc_selftest_chan_host": (C.c_int, [P, I64, P]),
     "vapc_selftest_mahalanobis_host": (C.c_int, [P, P, I64, P, P]),

@@ -452,6 +452,329 @@ struct Rgb12V2 : ItemReader {
     memcpy(out, c, 6);
   }
 };
+
+// BYTE version 2 (extra bytes): every byte coded as the difference to the same byte of the previous point
+struct ByteV2 : ItemReader {
+  ArithmeticDecoder* dec;
+  int number;
+  std::vector<uint8_t> last;
+  std::vector<std::unique_ptr<SymbolModel>> m_byte;
+  ByteV2(ArithmeticDecoder* d, int n) : dec(d), number(n), last((size_t)n) {
+    for (int i = 0; i < n; ++i) m_byte.emplace_back(new SymbolModel(256));
+  }
+  void init(const uint8_t* first) override {
+    for (auto& m : m_byte) m->init();
+    memcpy(last.data(), first, (size_t)number);
+  }
+  void read(uint8_t* out) override {
+    for (int i = 0; i < number; ++i) last[(size_t)i] = u8_fold((int)last[(size_t)i] + (int)dec->symbol(*m_byte[(size_t)i]));
+    memcpy(out, last.data(), (size_t)number);
+  }
+};
+
+// ================================================================================================================
+// Encoder: the exact mirror of the decoder above (same models, same contexts, same update schedule), so that the
+// streams it writes are the ones LASzip writes: tests/test_laz.py re-encodes the decoded records of the reference's
+// vapc_in.laz and compares the result with the file byte for byte, chunk table included.
+// ================================================================================================================
+struct ArithmeticEncoder {
+  std::vector<uint8_t>* out = nullptr;
+  size_t begin = 0;  // first byte of this coder's stream inside *out (carries never travel in front of it)
+  uint32_t base = 0, length = kAcMaxLength;
+  void init(std::vector<uint8_t>* dst) {
+    out = dst;
+    begin = dst->size();
+    base = 0;
+    length = kAcMaxLength;
+  }
+  void propagate_carry() {
+    size_t i = out->size();
+    while (i > begin && (*out)[i - 1] == 0xFFu) (*out)[--i] = 0;
+    if (i > begin) ++(*out)[i - 1];
+  }
+  void renorm() {
+    do {
+      out->push_back((uint8_t)(base >> 24));
+      base <<= 8;
+    } while ((length <<= 8) < kAcMinLength);
+  }
+  void bit(BitModel& m, uint32_t sym) {
+    const uint32_t x = m.bit_0_prob * (length >> kBmLengthShift);
+    if (sym == 0) {
+      length = x;
+      ++m.bit_0_count;
+    } else {
+      const uint32_t init_base = base;
+      base += x;
+      length -= x;
+      if (init_base > base) propagate_carry();
+    }
+    if (length < kAcMinLength) renorm();
+    if (--m.bits_until_update == 0) m.update();
+  }
+  void symbol(SymbolModel& m, uint32_t sym) {
+    uint32_t x;
+    const uint32_t init_base = base;
+    if (sym == m.last_symbol) {
+      x = m.distribution[sym] * (length >> kDmLengthShift);
+      base += x;
+      length -= x;
+    } else {
+      x = m.distribution[sym] * (length >>= kDmLengthShift);
+      base += x;
+      length = m.distribution[sym + 1] * length - x;
+    }
+    if (init_base > base) propagate_carry();
+    if (length < kAcMinLength) renorm();
+    ++m.symbol_count[sym];
+    if (--m.symbols_until_update == 0) m.update();
+  }
+  void write_short(uint32_t sym) {
+    const uint32_t init_base = base;
+    base += sym * (length >>= 16);
+    if (init_base > base) propagate_carry();
+    if (length < kAcMinLength) renorm();
+  }
+  void write_bits(uint32_t bits, uint32_t sym) {
+    if (bits > 19) {
+      write_short(sym & 0xFFFFu);
+      sym >>= 16;
+      bits -= 16;
+    }
+    const uint32_t init_base = base;
+    base += sym * (length >>= bits);
+    if (init_base > base) propagate_carry();
+    if (length < kAcMinLength) renorm();
+  }
+  void done() {
+    const uint32_t init_base = base;
+    bool another_byte = true;
+    if (length > 2 * kAcMinLength) {
+      base += kAcMinLength;
+      length = kAcMinLength >> 1;
+    } else {
+      base += kAcMinLength >> 1;
+      length = kAcMinLength >> 9;
+      another_byte = false;
+    }
+    if (init_base > base) propagate_carry();
+    renorm();
+    out->push_back(0);  // the decoder reads ahead: keep its byte reads inside the stream
+    out->push_back(0);
+    if (another_byte) out->push_back(0);
+  }
+};
+
+struct IntegerCompressor {
+  ArithmeticEncoder* enc;
+  uint32_t k = 0, contexts, bits_high = 8, corr_bits, corr_range;
+  int32_t corr_min, corr_max;
+  std::vector<std::unique_ptr<SymbolModel>> m_bits, m_corrector;
+  BitModel corrector0;
+  IntegerCompressor(ArithmeticEncoder* e, uint32_t bits, uint32_t ctx) : enc(e), contexts(ctx) {
+    if (bits && bits < 32) {
+      corr_bits = bits;
+      corr_range = 1u << bits;
+      corr_min = -(int32_t)(corr_range / 2);
+      corr_max = corr_min + (int32_t)corr_range - 1;
+    } else {
+      corr_bits = 32;
+      corr_range = 0;
+      corr_min = INT32_MIN;
+      corr_max = INT32_MAX;
+    }
+    for (uint32_t i = 0; i < contexts; ++i) m_bits.emplace_back(new SymbolModel(corr_bits + 1));
+    m_corrector.emplace_back(nullptr);
+    for (uint32_t i = 1; i <= corr_bits; ++i) m_corrector.emplace_back(new SymbolModel(i <= bits_high ? (1u << i) : (1u << bits_high)));
+    init();
+  }
+  void init() {
+    for (auto& m : m_bits) m->init();
+    corrector0.init();
+    for (uint32_t i = 1; i <= corr_bits; ++i) m_corrector[i]->init();
+  }
+  void corrector(int32_t c, SymbolModel& bits_model) {
+    uint32_t c1 = c <= 0 ? (uint32_t)0 - (uint32_t)c : (uint32_t)c - 1u;  // the tightest [-(2^k - 1), 2^k] holding c
+    for (k = 0; c1; ++k) c1 >>= 1;
+    enc->symbol(bits_model, k);
+    if (k) {
+      if (k < 32) {
+        if (c < 0) c += (int32_t)((1u << k) - 1u); else c -= 1;  // -> [0, 2^k - 1]
+        if (k <= bits_high) {
+          enc->symbol(*m_corrector[k], (uint32_t)c);
+        } else {
+          const uint32_t k1 = k - bits_high;
+          const uint32_t low = (uint32_t)c & ((1u << k1) - 1u);
+          enc->symbol(*m_corrector[k], (uint32_t)c >> k1);
+          enc->write_bits(k1, low);
+        }
+      }
+    } else {
+      enc->bit(corrector0, (uint32_t)c);
+    }
+  }
+  void compress(int32_t pred, int32_t real, uint32_t context) {
+    int32_t corr = (int32_t)((uint32_t)real - (uint32_t)pred);
+    if (corr < corr_min) corr = (int32_t)((uint32_t)corr + corr_range);
+    else if (corr > corr_max) corr = (int32_t)((uint32_t)corr - corr_range);
+    corrector(corr, *m_bits[context]);
+  }
+};
+
+struct ItemWriter {
+  virtual ~ItemWriter() {}
+  virtual void init(const uint8_t* first) = 0;
+  virtual void write(const uint8_t* item) = 0;
+};
+
+struct Point10V2Writer : ItemWriter {
+  ArithmeticEncoder* enc;
+  uint8_t last[20];
+  uint16_t last_intensity[16];
+  Median5 mx[16], my[16];
+  int32_t last_height[8];
+  SymbolModel changed{64};
+  SymbolModel scan_angle[2] = {SymbolModel(256), SymbolModel(256)};
+  std::unique_ptr<SymbolModel> bit_byte[256], classification[256], user_data[256];
+  IntegerCompressor ic_intensity, ic_source, ic_dx, ic_dy, ic_z;
+  explicit Point10V2Writer(ArithmeticEncoder* e) : enc(e), ic_intensity(e, 16, 4), ic_source(e, 16, 1), ic_dx(e, 32, 2), ic_dy(e, 32, 22), ic_z(e, 32, 20) {}
+  void init(const uint8_t* first) override {
+    for (int i = 0; i < 16; ++i) {
+      mx[i].init();
+      my[i].init();
+      last_intensity[i] = 0;
+      last_height[i / 2] = 0;
+    }
+    changed.init();
+    ic_intensity.init();
+    scan_angle[0].init();
+    scan_angle[1].init();
+    ic_source.init();
+    for (int i = 0; i < 256; ++i) {
+      if (bit_byte[i]) bit_byte[i]->init();
+      if (classification[i]) classification[i]->init();
+      if (user_data[i]) user_data[i]->init();
+    }
+    ic_dx.init();
+    ic_dy.init();
+    ic_z.init();
+    memcpy(last, first, 20);
+    last[12] = last[13] = 0;
+  }
+  void write(const uint8_t* item) override {
+    const uint32_t r = item[14] & 7, n = (item[14] >> 3) & 7;
+    const uint32_t m = kReturnMap[n][r], l = kReturnLevel[n][r];
+    const uint16_t intensity = rd_u16(item + 12);
+    const uint32_t ch = ((uint32_t)(last[14] != item[14]) << 5) | ((uint32_t)(last_intensity[m] != intensity) << 4) | ((uint32_t)(last[15] != item[15]) << 3) |
+                        ((uint32_t)(last[16] != item[16]) << 2) | ((uint32_t)(last[17] != item[17]) << 1) | (uint32_t)(rd_u16(last + 18) != rd_u16(item + 18));
+    enc->symbol(changed, ch);
+    if (ch & 32) enc->symbol(Point10V2::lazy(bit_byte[last[14]]), item[14]);
+    if (ch & 16) {
+      ic_intensity.compress(last_intensity[m], intensity, m < 3 ? m : 3);
+      last_intensity[m] = intensity;
+    }
+    if (ch & 8) enc->symbol(Point10V2::lazy(classification[last[15]]), item[15]);
+    if (ch & 4) enc->symbol(scan_angle[(item[14] >> 6) & 1], u8_fold((int)item[16] - (int)last[16]));
+    if (ch & 2) enc->symbol(Point10V2::lazy(user_data[last[17]]), item[17]);
+    if (ch & 1) ic_source.compress(rd_u16(last + 18), rd_u16(item + 18), 0);
+    int32_t diff = (int32_t)((uint32_t)rd_i32(item) - (uint32_t)rd_i32(last));
+    ic_dx.compress(mx[m].get(), diff, n == 1);
+    mx[m].add(diff);
+    uint32_t kb = ic_dx.k;
+    diff = (int32_t)((uint32_t)rd_i32(item + 4) - (uint32_t)rd_i32(last + 4));
+    ic_dy.compress(my[m].get(), diff, (n == 1) + (kb < 20 ? (kb & ~1u) : 20));
+    my[m].add(diff);
+    kb = (ic_dx.k + ic_dy.k) / 2;
+    ic_z.compress(last_height[l], rd_i32(item + 8), (n == 1) + (kb < 18 ? (kb & ~1u) : 18));
+    last_height[l] = rd_i32(item + 8);
+    memcpy(last, item, 20);
+  }
+};
+
+struct Rgb12V2Writer : ItemWriter {
+  ArithmeticEncoder* enc;
+  uint16_t last[3];
+  SymbolModel used{128};
+  SymbolModel d0{256}, d1{256}, d2{256}, d3{256}, d4{256}, d5{256};
+  explicit Rgb12V2Writer(ArithmeticEncoder* e) : enc(e) {}
+  void init(const uint8_t* first) override {
+    used.init();
+    d0.init(); d1.init(); d2.init(); d3.init(); d4.init(); d5.init();
+    memcpy(last, first, 6);
+  }
+  void write(const uint8_t* item) override {
+    uint16_t c[3];
+    memcpy(c, item, 6);
+    int diff_l = 0, diff_h = 0, corr;
+    const uint32_t sym = ((uint32_t)((last[0] & 0x00FF) != (c[0] & 0x00FF)) << 0) | ((uint32_t)((last[0] & 0xFF00) != (c[0] & 0xFF00)) << 1) |
+                         ((uint32_t)((last[1] & 0x00FF) != (c[1] & 0x00FF)) << 2) | ((uint32_t)((last[1] & 0xFF00) != (c[1] & 0xFF00)) << 3) |
+                         ((uint32_t)((last[2] & 0x00FF) != (c[2] & 0x00FF)) << 4) | ((uint32_t)((last[2] & 0xFF00) != (c[2] & 0xFF00)) << 5) |
+                         ((uint32_t)(((c[0] & 0x00FF) != (c[1] & 0x00FF)) || ((c[0] & 0x00FF) != (c[2] & 0x00FF)) || ((c[0] & 0xFF00) != (c[1] & 0xFF00)) ||
+                                     ((c[0] & 0xFF00) != (c[2] & 0xFF00))) << 6);
+    enc->symbol(used, sym);
+    if (sym & 1) {
+      diff_l = (int)(c[0] & 255) - (int)(last[0] & 255);
+      enc->symbol(d0, u8_fold(diff_l));
+    }
+    if (sym & 2) {
+      diff_h = (int)(c[0] >> 8) - (int)(last[0] >> 8);
+      enc->symbol(d1, u8_fold(diff_h));
+    }
+    if (sym & 64) {
+      if (sym & 4) {
+        corr = (int)(c[1] & 255) - u8_clamp(diff_l + (int)(last[1] & 255));
+        enc->symbol(d2, u8_fold(corr));
+      }
+      if (sym & 16) {
+        diff_l = (diff_l + (int)(c[1] & 255) - (int)(last[1] & 255)) / 2;
+        corr = (int)(c[2] & 255) - u8_clamp(diff_l + (int)(last[2] & 255));
+        enc->symbol(d4, u8_fold(corr));
+      }
+      if (sym & 8) {
+        corr = (int)(c[1] >> 8) - u8_clamp(diff_h + (int)(last[1] >> 8));
+        enc->symbol(d3, u8_fold(corr));
+      }
+      if (sym & 32) {
+        diff_h = (diff_h + (int)(c[1] >> 8) - (int)(last[1] >> 8)) / 2;
+        corr = (int)(c[2] >> 8) - u8_clamp(diff_h + (int)(last[2] >> 8));
+        enc->symbol(d5, u8_fold(corr));
+      }
+    }
+    memcpy(last, c, 6);
+  }
+};
+
+struct ByteV2Writer : ItemWriter {
+  ArithmeticEncoder* enc;
+  int number;
+  std::vector<uint8_t> last;
+  std::vector<std::unique_ptr<SymbolModel>> m_byte;
+  ByteV2Writer(ArithmeticEncoder* e, int n) : enc(e), number(n), last((size_t)n) {
+    for (int i = 0; i < n; ++i) m_byte.emplace_back(new SymbolModel(256));
+  }
+  void init(const uint8_t* first) override {
+    for (auto& m : m_byte) m->init();
+    memcpy(last.data(), first, (size_t)number);
+  }
+  void write(const uint8_t* item) override {
+    for (int i = 0; i < number; ++i) enc->symbol(*m_byte[(size_t)i], u8_fold((int)item[i] - (int)last[(size_t)i]));
+    memcpy(last.data(), item, (size_t)number);
+  }
+};
+
+int check_items(const char* who, const uint16_t* items, int nitems, int point_size) {
+  int total = 0;
+  for (int i = 0; i < nitems; ++i) {
+    const int type = items[3 * i], size = items[3 * i + 1], version = items[3 * i + 2];
+    const bool ok = (type == 6 && size == 20 && version == 2) || (type == 8 && size == 6 && version == 2) || (type == 0 && size > 0 && version == 2);
+    if (!ok)
+      return vapc_set_error(VAPC_E_INVALID, "%s: LASzip item type %d (size %d, version %d) is not supported (POINT10 v2, RGB12 v2 and BYTE v2 are)", who, type,
+                            size, version);
+    total += size;
+  }
+  if (total != point_size) return vapc_set_error(VAPC_E_INVALID, "%s: item sizes (%d) do not add up to the point size (%d)", who, total, point_size);
+  return VAPC_OK;
+}
 }  // namespace
 
 // Decode `npoints` records of `point_size` bytes into records_out_host.  items_host: nitems triples (type, size,
@@ -461,14 +784,7 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
   if (!file_host || !items_host || !records_out_host || file_bytes < 0 || npoints < 0 || nitems < 1)
     return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: bad arguments");
   if (compressor != 2) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip compressor %d is not supported (only 2 = pointwise chunked)", compressor);
-  int total = 0;
-  for (int i = 0; i < nitems; ++i) {
-    const int type = items_host[3 * i], size = items_host[3 * i + 1], version = items_host[3 * i + 2];
-    const bool ok = (type == 6 && size == 20 && version == 2) || (type == 8 && size == 6 && version == 2);
-    if (!ok) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip item type %d (size %d, version %d) is not supported (POINT10 v2 and RGB12 v2 are)", type, size, version);
-    total += size;
-  }
-  if (total != point_size) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: item sizes (%d) do not add up to the point size (%d)", total, point_size);
+  if (const int rc = check_items("vapc_laz_decode", items_host, nitems, point_size)) return rc;
   if (npoints == 0) return VAPC_OK;
   if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: variable chunk sizes are not supported");
   if (offset_to_points + 8 > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: truncated file");
@@ -501,7 +817,8 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
   std::vector<int> sizes;
   for (int i = 0; i < nitems; ++i) {
     if (items_host[3 * i] == 6) readers.emplace_back(new Point10V2(&dec));
-    else readers.emplace_back(new Rgb12V2(&dec));
+    else if (items_host[3 * i] == 8) readers.emplace_back(new Rgb12V2(&dec));
+    else readers.emplace_back(new ByteV2(&dec, items_host[3 * i + 1]));
     sizes.push_back(items_host[3 * i + 1]);
   }
   for (int64_t c = 0; c < nchunks; ++c) {
@@ -531,5 +848,76 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
       if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld is truncated or corrupt", (long long)c);
     }
   }
+  return VAPC_OK;
+}
+
+// Encode `npoints` records into a LASzip "pointwise chunked" stream (compressor 2): [int64 position of the chunk table,
+// relative to the start of the stream + stream_offset_host][chunks: first point raw, the rest arithmetic-coded]
+// [chunk table: u32 version 0, u32 count, arithmetic-coded chunk byte sizes].  stream_offset_host = file position at which the
+// caller will place the stream (= the header's offset to point data).  Returns the stream length in *out_bytes_host;
+// VAPC_E_WORKSPACE (with the needed size in *out_bytes_host) when out_cap is too small.
+extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int32_t point_size, uint32_t chunk_size, const uint16_t* items_host,
+                               int32_t nitems, int64_t stream_offset_host, uint8_t* out_host, int64_t out_cap, int64_t* out_bytes_host) {
+  if (!items_host || !out_bytes_host || npoints < 0 || nitems < 1 || point_size < 1 || (npoints > 0 && !records_host))
+    return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: bad arguments");
+  if (const int rc = check_items("vapc_laz_encode", items_host, nitems, point_size)) return rc;
+  if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: a fixed chunk size is required");
+  std::vector<uint8_t> out(8, 0);
+  ArithmeticEncoder enc;
+  std::vector<std::unique_ptr<ItemWriter>> writers;
+  std::vector<int> sizes;
+  for (int i = 0; i < nitems; ++i) {
+    if (items_host[3 * i] == 6) writers.emplace_back(new Point10V2Writer(&enc));
+    else if (items_host[3 * i] == 8) writers.emplace_back(new Rgb12V2Writer(&enc));
+    else writers.emplace_back(new ByteV2Writer(&enc, items_host[3 * i + 1]));
+    sizes.push_back(items_host[3 * i + 1]);
+  }
+  const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
+  std::vector<uint32_t> chunk_bytes;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t first = c * (int64_t)chunk_size;
+    const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
+    const size_t begin = out.size();
+    const uint8_t* rec = records_host + first * point_size;
+    out.insert(out.end(), rec, rec + point_size);  // the first point of a chunk is stored raw
+    int off = 0;
+    for (size_t i = 0; i < writers.size(); ++i) {
+      writers[i]->init(rec + off);
+      off += sizes[i];
+    }
+    enc.init(&out);
+    for (int64_t p = 1; p < count; ++p) {
+      const uint8_t* r = rec + p * point_size;
+      off = 0;
+      for (size_t i = 0; i < writers.size(); ++i) {
+        writers[i]->write(r + off);
+        off += sizes[i];
+      }
+    }
+    enc.done();
+    chunk_bytes.push_back((uint32_t)(out.size() - begin));
+  }
+  const int64_t table_pos = stream_offset_host + (int64_t)out.size();
+  memcpy(out.data(), &table_pos, 8);
+  {
+    const uint32_t version = 0, count = (uint32_t)nchunks;
+    const uint8_t* v = reinterpret_cast<const uint8_t*>(&version);
+    const uint8_t* n = reinterpret_cast<const uint8_t*>(&count);
+    out.insert(out.end(), v, v + 4);
+    out.insert(out.end(), n, n + 4);
+    if (nchunks > 0) {
+      enc.init(&out);
+      IntegerCompressor ic(&enc, 32, 2);
+      int32_t prev = 0;
+      for (int64_t i = 0; i < nchunks; ++i) {
+        ic.compress(prev, (int32_t)chunk_bytes[(size_t)i], 1);
+        prev = (int32_t)chunk_bytes[(size_t)i];
+      }
+      enc.done();
+    }
+  }
+  *out_bytes_host = (int64_t)out.size();
+  if (!out_host || out_cap < (int64_t)out.size()) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_laz_encode: output buffer too small (%lld bytes needed)", (long long)out.size());
+  memcpy(out_host, out.data(), out.size());
   return VAPC_OK;
 }

@@ -5,7 +5,8 @@ LAS dimension, all float64, ExtraBytes dropped; datahandler.py:54-95).
 
 File decoding / encoding is host work next to the hot path.  `laspy` is used when it
 is importable (then LAZ works as in the reference); otherwise the native LAS 1.0-1.4 reader / writer in
-`vapc_b200.las` handles uncompressed `.las`, and LAZ raises a clear error.  PLY export needs no third-party
+`vapc_b200.las` handles `.las` and, through the library's own LASzip codec (vapc_laz_decode / vapc_laz_encode), the LAZ
+layout of point formats 0 and 2 (+ extra bytes): reading the reference's fixtures, writing `.laz` results.  PLY export needs no third-party
 package: the voxel cubes are written as a binary little-endian PLY directly.
 """
 from __future__ import annotations
@@ -108,7 +109,21 @@ class DataHandler:
             out.write(outfile)
             return
         if outfile.lower().endswith(".laz"):
-            raise NotImplementedError("writing LAZ needs laspy with a LAZ backend (lazrs / laszip), which is not installed; write .las")
+            # native LASzip encoder: LAS 1.2, point format 0 / 2, everything without a legacy field as float32 extra bytes
+            legacy = set(_las.dimension_names(2))
+            standard, extra = {}, {}
+            for name in self.df.columns:
+                if name in _SKIP_ON_SAVE:
+                    continue
+                col = self.df[name].to_numpy()
+                if name in legacy:
+                    standard[name] = col
+                elif name == "gps_time":
+                    extra[name] = np.asarray(col, dtype=np.float64)  # seconds of a GPS week need all 53 bits
+                else:
+                    extra[name] = np.asarray(col, dtype=np.float64).astype(np.float32)
+            _las.write_laz(outfile, xyz[:, 0], xyz[:, 1], xyz[:, 2], standard, extra, scales=las_scales, offsets=las_offset)
+            return
         if str(las_version) != "1.4" or int(las_point_format) not in (6, 7, 8):
             raise NotImplementedError("the native writer produces LAS 1.4 point formats 6, 7, 8 (the reference's default is 1.4 / 7)")
         known = set(_las.dimension_names(int(las_point_format)))

@@ -269,3 +269,104 @@ def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
         f.write(bytes(header))
         f.write(vlr)
         f.write(rec.tobytes())
+
+
+def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
+              chunk_size: int = 50000, generating_software: str = "vapc_b200"):
+    """LASzip-compressed LAS 1.2 through the library's own encoder (vapc_laz_encode): point format 2 when red / green / blue are
+    given, else 0, every other dimension as extra bytes; "pointwise chunked" compression of the items POINT10 v2 (+ RGB12 v2)
+    (+ BYTE v2) — the layout of the reference's vapc_in.laz fixture, whose point data the encoder reproduces byte for byte
+    (tests/test_laz.py).  Values that do not fit the legacy fields (return numbers above 7, classes above 31) are masked as
+    in any point-format-0 file; pass them as extra dimensions to keep them."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    x, y, z = (np.asarray(a, np.float64) for a in (x, y, z))
+    n = len(x)
+    scales = np.asarray([0.00025] * 3 if scales is None else scales, np.float64)
+    if offsets is None:
+        offsets = np.array([x.min(), y.min(), z.min()]) if n else np.zeros(3)
+    offsets = np.asarray(offsets, np.float64)
+    point_format = 2 if any(c in standard for c in ("red", "green", "blue")) else 0
+    fields = list(POINT_FORMATS[point_format])
+    core_size = np.dtype(fields).itemsize
+    known = set(dimension_names(point_format))
+    extra = dict(extra)
+    for name in list(standard):
+        if name not in known:  # a LAS 1.4 dimension without a legacy field (gps_time, scan_angle, ...): kept as extra bytes
+            extra.setdefault(name, np.asarray(standard[name], np.float64).astype(np.float32))
+    extra_fields = []
+    taken = {f for f, _ in fields}
+    for name, arr in extra.items():
+        arr = np.asarray(arr)
+        code = _EXTRA_CODES.get(arr.dtype.str.lstrip("<|"))
+        if code is None:
+            arr = arr.astype(np.float32)
+            code = 9
+        extra_fields.append((name, arr, code))
+        fields.append((name if name not in taken else name + "_extra", _EXTRA_TYPES[code]))
+    dt = np.dtype(fields)
+    rec = np.zeros(n, dtype=dt)
+    for k, (c, up) in enumerate(((x, "X"), (y, "Y"), (z, "Z"))):
+        rec[up] = np.round((c - offsets[k]) / scales[k]).astype(np.int64).astype(np.int32)
+    sub_lookup = {s_[0]: (byte, s_[1], s_[2]) for byte, lst in _sub_fields(point_format).items() for s_ in lst}
+    for name, arr in standard.items():
+        arr = np.asarray(arr)
+        if name in sub_lookup:
+            byte, shift, mask = sub_lookup[name]
+            with np.errstate(invalid="ignore"):
+                rec[byte] |= ((arr.astype(np.int64) & mask) << shift).astype(np.uint8)
+        elif name in known and name in dt.names:
+            with np.errstate(invalid="ignore"):
+                rec[name] = arr.astype(dt[name])
+    for (name, arr, _), field in zip(extra_fields, dt.names[len(POINT_FORMATS[point_format]):]):
+        rec[field] = arr
+    items = [(6, 20, 2)] + ([(8, 6, 2)] if point_format == 2 else []) + ([(0, dt.itemsize - core_size, 2)] if dt.itemsize > core_size else [])
+    # VLRs: laszip description, extra-bytes description
+    body = struct.pack("<HHBBHIIqqH", 2, 0, 3, 4, 3, 0, int(chunk_size), -1, -1, len(items)) + b"".join(struct.pack("<HHH", *it) for it in items)
+    vlrs = struct.pack("<H16sHH32s", 0, b"laszip encoded", 22204, len(body), b"vapc_b200 LASzip-compatible") + body
+    nvlr = 1
+    if extra_fields:
+        eb = b""
+        for (name, arr, code), field in zip(extra_fields, dt.names[len(POINT_FORMATS[point_format]):]):
+            e = bytearray(192)
+            e[2] = code
+            e[4:4 + min(31, len(name))] = name.encode("ascii", "replace")[:31]
+            e[160:160 + min(31, len(name))] = name.encode("ascii", "replace")[:31]
+            eb += bytes(e)
+        vlrs += struct.pack("<H16sHH32s", 0, b"LASF_Spec", 4, len(eb), b"extra bytes") + eb
+        nvlr += 1
+    header = bytearray(227)
+    header[0:4] = b"LASF"
+    header[24], header[25] = 1, 2
+    header[26:26 + 5] = b"OTHER"
+    sw = generating_software.encode("ascii", "replace")[:31]
+    header[58:58 + len(sw)] = sw
+    struct.pack_into("<HH", header, 90, 1, 2026)
+    offset_to_points = 227 + len(vlrs)
+    struct.pack_into("<HII", header, 94, 227, offset_to_points, nvlr)
+    struct.pack_into("<BH", header, 104, point_format | 0x80, dt.itemsize)
+    rn = (rec["bit_fields"] & 0x07).astype(np.int64)
+    by_return = np.bincount(rn[(rn >= 1) & (rn <= 5)] - 1, minlength=5)[:5] if n else np.zeros(5, np.int64)
+    struct.pack_into("<I5I", header, 107, n, *[int(v) for v in by_return])
+    mins = [float(c.min()) if n else 0.0 for c in (x, y, z)]
+    maxs = [float(c.max()) if n else 0.0 for c in (x, y, z)]
+    struct.pack_into("<12d", header, 131, *scales, *offsets, maxs[0], mins[0], maxs[1], mins[1], maxs[2], mins[2])
+    raw = np.frombuffer(rec.tobytes(), dtype=np.uint8)
+    item_arr = np.array(items, dtype=np.uint16).reshape(-1)
+    cap = int(raw.size + raw.size // 8 + 64 * (n // max(1, chunk_size) + 2) + 1024)
+    out = np.empty(cap, dtype=np.uint8)
+    nbytes = C.c_int64(0)
+    rc = L.raw("vapc_laz_encode")(raw.ctypes.data_as(C.c_void_p), n, dt.itemsize, int(chunk_size), item_arr.ctypes.data_as(C.c_void_p), len(items),
+                                  offset_to_points, out.ctypes.data_as(C.c_void_p), cap, C.byref(nbytes))
+    if rc == L.VAPC_E_WORKSPACE:  # incompressible data: retry with the size the encoder asked for
+        cap = int(nbytes.value)
+        out = np.empty(cap, dtype=np.uint8)
+        rc = L.raw("vapc_laz_encode")(raw.ctypes.data_as(C.c_void_p), n, dt.itemsize, int(chunk_size), item_arr.ctypes.data_as(C.c_void_p), len(items),
+                                      offset_to_points, out.ctypes.data_as(C.c_void_p), cap, C.byref(nbytes))
+    L.check(rc)
+    with open(path, "wb") as f:
+        f.write(bytes(header))
+        f.write(vlrs)
+        f.write(out[: nbytes.value].tobytes())
