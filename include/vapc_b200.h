@@ -438,9 +438,11 @@ VAPC_API int vapc_selftest_mahalanobis_host(const double* cov6_host, const doubl
 /* ---- (f)1 LASzip decoding on the host (file I/O in front of the hot path; datahandler.py:72-73 gets it from
  * laspy[lazrs]).  Decodes npoints records of point_size bytes from a LAZ file image in host memory into
  * records_out_host.  compressor / chunk_size / items (nitems triples type, size, version) come from the
- * "laszip encoded" VLR (record id 22204).  Supported: compressor 2 (pointwise chunked) with POINT10 v2 and
- * RGB12 v2 items, i.e. LAS point formats 0 and 2 — the layout of the reference's vapc_in.laz / small_mask.laz
- * fixtures; anything else returns VAPC_E_INVALID with a message naming the item. */
+ * "laszip encoded" VLR (record id 22204).  Supported: compressor 2 (pointwise chunked) with POINT10 v2, RGB12 v2 and BYTE v2
+ * items, i.e. LAS point formats 0 and 2 (+ extra bytes) — the layout of the reference's vapc_in.laz / small_mask.laz — and
+ * compressor 3 (layered chunked) with POINT14 v3 (+ BYTE14 v3), i.e. LAS 1.4 point format 6 (+ extra bytes) — the layout of its
+ * tree_wind_condition.laz / als_multichannel_leg000_points.laz; anything else returns VAPC_E_INVALID with a message naming
+ * the item.  A layered chunk whose layer decoders do not end exactly on their streams' last bytes is reported as corrupt. */
 VAPC_API int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64_t offset_to_points, int64_t npoints,
                     int32_t point_size, int32_t compressor, uint32_t chunk_size, const uint16_t* items_host,
                     int32_t nitems, uint8_t* records_out_host);

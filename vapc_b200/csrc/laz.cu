@@ -6,7 +6,8 @@
 // compression of LiDAR data", PE&RS 2013) — an adaptive arithmetic coder (Said's FastAC scheme), integer
 // "corrector" coders with k-bit contexts, and the per-item predictors of version 2.
 //
-// Other items (GPSTIME11, WAVEPACKET13, the layered POINT14 family of LAS 1.4) are reported as unsupported.
+// LAS 1.4: the layered POINT14 v3 + BYTE14 v3 items (compressor 3) of the reference's other two fixtures are decoded as well
+// (second half of this file).  Other items (GPSTIME11, WAVEPACKET13, RGB14, ...) are reported as unsupported.
 #include <stdint.h>
 #include <string.h>
 
@@ -762,6 +763,410 @@ struct ByteV2Writer : ItemWriter {
   }
 };
 
+
+// ================================================================================================================
+// LAS 1.4: "layered chunked" compression (compressor 3) of POINT14 v3 (+ BYTE14 v3 extra bytes) — the layout of the
+// reference's tree_wind_condition.laz and als_multichannel_leg000_points.laz.  A chunk is: first point raw, u32 point
+// count, the byte size of every layer, then the layers, each an arithmetic-coded stream of its own (channel / returns /
+// XY, Z, classification, flags, intensity, scan angle, user data, point source, GPS time; one layer per extra byte).
+// Up to four contexts (one per scanner channel) keep their own models and predictors.
+// ================================================================================================================
+// XY context of a return: single (0), first / last of two (1 / 2), first / intermediate / last of three or more (3 / 4 / 5).
+// Pinned for every valid pair 1 <= r <= n by the reference's fixtures (decoded bounding boxes and by-return counts equal the
+// headers, every layer's decoder ends on the last byte of its stream).  Points with r = 0 or r > n use the neighbouring class
+// (not pinned by any fixture: such pairs only select which median predicts X and Y, they cannot desynchronise a stream).
+inline uint32_t return_map6(uint32_t n, uint32_t r) {
+  if (n <= 1) return 0;
+  if (n == 2) return r <= 1 ? 1 : 2;
+  return r <= 1 ? 3 : (r >= n ? 5 : 4);
+}
+inline uint32_t return_level8(uint32_t n, uint32_t r) {
+  const uint32_t d = n > r ? n - r : r - n;
+  return d < 7 ? d : 7;
+}
+constexpr int kGpsMulti = 500, kGpsMultiMinus = -10, kGpsMultiCodeFull = kGpsMulti - kGpsMultiMinus + 1, kGpsMultiTotal = kGpsMulti - kGpsMultiMinus + 5;
+
+struct P14 {  // LAS point format 6 core, unpacked
+  int32_t X, Y, Z;
+  uint16_t intensity;
+  uint8_t return_number, number_of_returns, class_flags, scanner_channel, scan_dir, edge, classification, user_data;
+  int16_t scan_angle;
+  uint16_t psid;
+  double gps_time;
+  bool gps_time_change;
+  void unpack(const uint8_t* p) {
+    X = rd_i32(p); Y = rd_i32(p + 4); Z = rd_i32(p + 8);
+    intensity = rd_u16(p + 12);
+    return_number = p[14] & 15; number_of_returns = p[14] >> 4;
+    class_flags = p[15] & 15; scanner_channel = (p[15] >> 4) & 3; scan_dir = (p[15] >> 6) & 1; edge = p[15] >> 7;
+    classification = p[16]; user_data = p[17];
+    memcpy(&scan_angle, p + 18, 2);
+    psid = rd_u16(p + 20);
+    memcpy(&gps_time, p + 22, 8);
+    gps_time_change = false;
+  }
+  void pack(uint8_t* p) const {
+    wr_i32(p, X); wr_i32(p + 4, Y); wr_i32(p + 8, Z);
+    wr_u16(p + 12, intensity);
+    p[14] = (uint8_t)(return_number | (number_of_returns << 4));
+    p[15] = (uint8_t)(class_flags | (scanner_channel << 4) | (scan_dir << 6) | (edge << 7));
+    p[16] = classification; p[17] = user_data;
+    memcpy(p + 18, &scan_angle, 2);
+    wr_u16(p + 20, psid);
+    memcpy(p + 22, &gps_time, 8);
+  }
+};
+
+enum { kLayerXY = 0, kLayerZ, kLayerClass, kLayerFlags, kLayerIntensity, kLayerScanAngle, kLayerUserData, kLayerSource, kLayerGps, kLayers14 };
+
+struct Point14V3 {
+  struct Ctx {
+    bool unused = true;
+    P14 last;
+    uint16_t last_intensity[8];
+    Median5 mx[12], my[12];
+    int32_t last_Z[8];
+    std::unique_ptr<SymbolModel> changed_values[8], scanner_channel, number_of_returns[16], return_number_gps_same, return_number[16];
+    std::unique_ptr<SymbolModel> classification[64], flags[64], user_data[64], gps_multi, gps_0diff;
+    std::unique_ptr<IntegerDecompressor> ic_dx, ic_dy, ic_z, ic_intensity, ic_scan_angle, ic_source, ic_gps;
+    uint32_t gps_last = 0, gps_next = 0;
+    uint64_t last_gps[4];
+    int32_t last_gps_diff[4], multi_extreme[4];
+  };
+  ByteReader br[kLayers14];
+  ArithmeticDecoder dec[kLayers14];
+  bool changed[kLayers14];
+  Ctx ctx[4];
+  uint32_t current = 0;
+
+  static SymbolModel& lazy(std::unique_ptr<SymbolModel>& m, uint32_t n) {
+    if (!m) m.reset(new SymbolModel(n));
+    return *m;
+  }
+  void create_and_init(uint32_t c, const P14& item) {
+    Ctx& x = ctx[c];
+    for (int i = 0; i < 8; ++i) lazy(x.changed_values[i], 128).init();
+    lazy(x.scanner_channel, 3).init();
+    for (int i = 0; i < 16; ++i) {
+      if (x.number_of_returns[i]) x.number_of_returns[i]->init();
+      if (x.return_number[i]) x.return_number[i]->init();
+    }
+    lazy(x.return_number_gps_same, 13).init();
+    if (!x.ic_dx) {
+      x.ic_dx.reset(new IntegerDecompressor(&dec[kLayerXY], 32, 2));
+      x.ic_dy.reset(new IntegerDecompressor(&dec[kLayerXY], 32, 22));
+      x.ic_z.reset(new IntegerDecompressor(&dec[kLayerZ], 32, 20));
+      x.ic_intensity.reset(new IntegerDecompressor(&dec[kLayerIntensity], 16, 4));
+      x.ic_scan_angle.reset(new IntegerDecompressor(&dec[kLayerScanAngle], 16, 2));
+      x.ic_source.reset(new IntegerDecompressor(&dec[kLayerSource], 16, 1));
+      x.ic_gps.reset(new IntegerDecompressor(&dec[kLayerGps], 32, 9));
+    }
+    x.ic_dx->init(); x.ic_dy->init(); x.ic_z->init(); x.ic_intensity->init(); x.ic_scan_angle->init(); x.ic_source->init(); x.ic_gps->init();
+    for (int i = 0; i < 12; ++i) { x.mx[i].init(); x.my[i].init(); }
+    for (int i = 0; i < 8; ++i) { x.last_Z[i] = item.Z; x.last_intensity[i] = item.intensity; }
+    for (int i = 0; i < 64; ++i) {
+      if (x.classification[i]) x.classification[i]->init();
+      if (x.flags[i]) x.flags[i]->init();
+      if (x.user_data[i]) x.user_data[i]->init();
+    }
+    lazy(x.gps_multi, kGpsMultiTotal).init();
+    lazy(x.gps_0diff, 5).init();
+    x.gps_last = x.gps_next = 0;
+    for (int i = 0; i < 4; ++i) { x.last_gps[i] = 0; x.last_gps_diff[i] = 0; x.multi_extreme[i] = 0; }
+    memcpy(&x.last_gps[0], &item.gps_time, 8);
+    x.last = item;
+    x.last.gps_time_change = false;
+    x.unused = false;
+  }
+  // layer sizes follow the chunk's point count; returns the number of bytes of all layers
+  int64_t begin_chunk(const uint8_t* first_raw, const uint8_t* sizes, const uint8_t* layers, const uint8_t* limit) {
+    uint32_t nbytes[kLayers14];
+    memcpy(nbytes, sizes, sizeof(nbytes));
+    const uint8_t* p = layers;
+    for (int l = 0; l < kLayers14; ++l) {
+      br[l] = ByteReader{p, p + nbytes[l] <= limit ? p + nbytes[l] : limit};
+      changed[l] = nbytes[l] > 0;
+      if (changed[l]) dec[l].init(&br[l]);
+      p += nbytes[l];
+    }
+    for (auto& c : ctx) c.unused = true;
+    P14 item;
+    item.unpack(first_raw);
+    current = item.scanner_channel;
+    create_and_init(current, item);
+    return p - layers;
+  }
+  void read_gps(Ctx& x) {
+    ArithmeticDecoder& d = dec[kLayerGps];
+    if (x.last_gps_diff[x.gps_last] == 0) {
+      const int multi = (int)d.symbol(*x.gps_0diff);
+      if (multi == 0) {  // the difference fits 32 bits
+        x.last_gps_diff[x.gps_last] = x.ic_gps->decompress(0, 0);
+        x.last_gps[x.gps_last] += (uint64_t)(int64_t)x.last_gps_diff[x.gps_last];
+        x.multi_extreme[x.gps_last] = 0;
+      } else if (multi == 1) {  // a huge difference: start another sequence
+        x.gps_next = (x.gps_next + 1) & 3;
+        uint64_t v = (uint64_t)(uint32_t)x.ic_gps->decompress((int32_t)(x.last_gps[x.gps_last] >> 32), 8);
+        v = (v << 32) | d.read_bits(32);
+        x.last_gps[x.gps_next] = v;
+        x.gps_last = x.gps_next;
+        x.last_gps_diff[x.gps_last] = 0;
+        x.multi_extreme[x.gps_last] = 0;
+      } else {  // switch to another sequence
+        x.gps_last = (x.gps_last + (uint32_t)multi - 1) & 3;
+        read_gps(x);
+      }
+    } else {
+      int multi = (int)d.symbol(*x.gps_multi);
+      if (multi == 1) {
+        x.last_gps[x.gps_last] += (uint64_t)(int64_t)x.ic_gps->decompress(x.last_gps_diff[x.gps_last], 1);
+        x.multi_extreme[x.gps_last] = 0;
+      } else if (multi < kGpsMultiCodeFull) {
+        int32_t diff;
+        const int32_t ld = x.last_gps_diff[x.gps_last];
+        if (multi == 0) {
+          diff = x.ic_gps->decompress(0, 7);
+          if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = diff; x.multi_extreme[x.gps_last] = 0; }
+        } else if (multi < kGpsMulti) {
+          diff = x.ic_gps->decompress((int32_t)((uint32_t)multi * (uint32_t)ld), multi < 10 ? 2 : 3);
+        } else if (multi == kGpsMulti) {
+          diff = x.ic_gps->decompress((int32_t)((uint32_t)kGpsMulti * (uint32_t)ld), 4);
+          if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = diff; x.multi_extreme[x.gps_last] = 0; }
+        } else {
+          multi = kGpsMulti - multi;
+          if (multi > kGpsMultiMinus) {
+            diff = x.ic_gps->decompress((int32_t)((uint32_t)multi * (uint32_t)ld), 5);
+          } else {
+            diff = x.ic_gps->decompress((int32_t)((uint32_t)kGpsMultiMinus * (uint32_t)ld), 6);
+            if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = diff; x.multi_extreme[x.gps_last] = 0; }
+          }
+        }
+        x.last_gps[x.gps_last] += (uint64_t)(int64_t)diff;
+      } else if (multi == kGpsMultiCodeFull) {
+        x.gps_next = (x.gps_next + 1) & 3;
+        uint64_t v = (uint64_t)(uint32_t)x.ic_gps->decompress((int32_t)(x.last_gps[x.gps_last] >> 32), 8);
+        v = (v << 32) | d.read_bits(32);
+        x.last_gps[x.gps_next] = v;
+        x.gps_last = x.gps_next;
+        x.last_gps_diff[x.gps_last] = 0;
+        x.multi_extreme[x.gps_last] = 0;
+      } else {
+        x.gps_last = (x.gps_last + (uint32_t)multi - (uint32_t)kGpsMultiCodeFull) & 3;
+        read_gps(x);
+      }
+    }
+  }
+  // decodes the next point into out (30 bytes); returns the context (scanner channel) for the extra-byte item
+  uint32_t read(uint8_t* out) {
+    Ctx* x = &ctx[current];
+    int lpr = (x->last.return_number == 1 ? 1 : 0) + (x->last.return_number >= x->last.number_of_returns ? 2 : 0) + (x->last.gps_time_change ? 4 : 0);
+    const uint32_t cv = dec[kLayerXY].symbol(*x->changed_values[lpr]);
+    if (cv & 64) {
+      const uint32_t diff = dec[kLayerXY].symbol(*x->scanner_channel);
+      const uint32_t sc = (current + diff + 1) % 4;
+      if (ctx[sc].unused) create_and_init(sc, x->last);
+      current = sc;
+      x = &ctx[current];
+      x->last.scanner_channel = (uint8_t)sc;
+    }
+    const bool source_change = cv & 32, gps_change = cv & 16, angle_change = cv & 8;
+    const uint32_t last_n = x->last.number_of_returns, last_r = x->last.return_number;
+    uint32_t n = last_n, r;
+    if (cv & 4) {
+      n = dec[kLayerXY].symbol(lazy(x->number_of_returns[last_n], 16));
+      x->last.number_of_returns = (uint8_t)n;
+    }
+    switch (cv & 3) {
+      case 0: r = last_r; break;
+      case 1: r = (last_r + 1) % 16; break;
+      case 2: r = (last_r + 15) % 16; break;
+      default:
+        if (gps_change) r = dec[kLayerXY].symbol(lazy(x->return_number[last_r], 16));
+        else r = (last_r + dec[kLayerXY].symbol(*x->return_number_gps_same) + 2) % 16;
+    }
+    x->last.return_number = (uint8_t)r;
+    const uint32_t m = return_map6(n, r);
+    const uint32_t l = return_level8(n, r);
+    const int cpr = (r == 1 ? 2 : 0) + (r >= n ? 1 : 0);
+    const uint32_t mi = (m << 1) | (gps_change ? 1u : 0u);
+    int32_t diff = x->ic_dx->decompress(x->mx[mi].get(), n == 1);
+    x->last.X = (int32_t)((uint32_t)x->last.X + (uint32_t)diff);
+    x->mx[mi].add(diff);
+    uint32_t kb = x->ic_dx->k;
+    diff = x->ic_dy->decompress(x->my[mi].get(), (n == 1) + (kb < 20 ? (kb & ~1u) : 20));
+    x->last.Y = (int32_t)((uint32_t)x->last.Y + (uint32_t)diff);
+    x->my[mi].add(diff);
+    if (changed[kLayerZ]) {
+      kb = (x->ic_dx->k + x->ic_dy->k) / 2;
+      x->last.Z = x->ic_z->decompress(x->last_Z[l], (n == 1) + (kb < 18 ? (kb & ~1u) : 18));
+      x->last_Z[l] = x->last.Z;
+    }
+    if (changed[kLayerClass]) {
+      const int ccc = ((x->last.classification & 0x1F) << 1) + (cpr == 3 ? 1 : 0);
+      x->last.classification = (uint8_t)dec[kLayerClass].symbol(lazy(x->classification[ccc], 256));
+    }
+    if (changed[kLayerFlags]) {
+      const uint32_t lf = ((uint32_t)x->last.edge << 5) | ((uint32_t)x->last.scan_dir << 4) | x->last.class_flags;
+      const uint32_t f = dec[kLayerFlags].symbol(lazy(x->flags[lf], 64));
+      x->last.edge = (f >> 5) & 1;
+      x->last.scan_dir = (f >> 4) & 1;
+      x->last.class_flags = f & 15;
+    }
+    if (changed[kLayerIntensity]) {
+      const uint32_t ii = ((uint32_t)cpr << 1) | (gps_change ? 1u : 0u);
+      const uint16_t v = (uint16_t)x->ic_intensity->decompress(x->last_intensity[ii], (uint32_t)cpr);
+      x->last_intensity[ii] = v;
+      x->last.intensity = v;
+    }
+    if (changed[kLayerScanAngle] && angle_change)
+      x->last.scan_angle = (int16_t)x->ic_scan_angle->decompress((int32_t)(uint16_t)x->last.scan_angle, gps_change ? 1 : 0);
+    if (changed[kLayerUserData]) x->last.user_data = (uint8_t)dec[kLayerUserData].symbol(lazy(x->user_data[x->last.user_data / 4], 256));
+    if (changed[kLayerSource] && source_change) x->last.psid = (uint16_t)x->ic_source->decompress(x->last.psid, 0);
+    if (changed[kLayerGps] && gps_change) {
+      read_gps(*x);
+      memcpy(&x->last.gps_time, &x->last_gps[x->gps_last], 8);
+    }
+    x->last.pack(out);
+    x->last.gps_time_change = gps_change;
+    return current;
+  }
+  bool overrun() const {
+    for (int l = 0; l < kLayers14; ++l)
+      if (changed[l] && br[l].overrun) return true;
+    return false;
+  }
+};
+
+struct Byte14V3 {
+  int number;
+  struct Ctx {
+    bool unused = true;
+    std::vector<uint8_t> last;
+    std::vector<std::unique_ptr<SymbolModel>> m;
+  };
+  std::vector<ByteReader> br;
+  std::vector<ArithmeticDecoder> dec;
+  std::vector<char> changed;
+  Ctx ctx[4];
+  uint32_t current = 0;
+  explicit Byte14V3(int n) : number(n), br((size_t)n), dec((size_t)n), changed((size_t)n) {}
+  void create_and_init(uint32_t c, const uint8_t* item) {
+    Ctx& x = ctx[c];
+    if (x.m.empty())
+      for (int i = 0; i < number; ++i) x.m.emplace_back(new SymbolModel(256));
+    for (auto& m : x.m) m->init();
+    x.last.assign(item, item + number);
+    x.unused = false;
+  }
+  int64_t begin_chunk(const uint8_t* first_raw, uint32_t context, const uint8_t* sizes, const uint8_t* layers, const uint8_t* limit) {
+    const uint8_t* p = layers;
+    for (int i = 0; i < number; ++i) {
+      uint32_t nb;
+      memcpy(&nb, sizes + 4 * i, 4);
+      br[(size_t)i] = ByteReader{p, p + nb <= limit ? p + nb : limit};
+      changed[(size_t)i] = nb > 0;
+      if (nb) dec[(size_t)i].init(&br[(size_t)i]);
+      p += nb;
+    }
+    for (auto& c : ctx) c.unused = true;
+    current = context;
+    create_and_init(current, first_raw);
+    return p - layers;
+  }
+  void read(uint8_t* out, uint32_t context) {
+    if (context != current) {
+      if (ctx[context].unused) create_and_init(context, ctx[current].last.data());
+      current = context;
+    }
+    Ctx& x = ctx[current];
+    for (int i = 0; i < number; ++i) {
+      if (changed[(size_t)i]) x.last[(size_t)i] = u8_fold((int)x.last[(size_t)i] + (int)dec[(size_t)i].symbol(*x.m[(size_t)i]));
+      out[i] = x.last[(size_t)i];
+    }
+  }
+  bool overrun() const {
+    for (int i = 0; i < number; ++i)
+      if (changed[(size_t)i] && br[(size_t)i].overrun) return true;
+    return false;
+  }
+};
+
+// chunk start positions from the chunk table (both compressors write the same table)
+int read_chunk_table(const char* who, const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t nchunks, std::vector<int64_t>& chunk_start) {
+  int64_t table_pos;
+  memcpy(&table_pos, file + offset_to_points, 8);
+  if (table_pos == -1) memcpy(&table_pos, file + file_bytes - 8, 8);
+  chunk_start.assign((size_t)nchunks + 1, 0);
+  chunk_start[0] = offset_to_points + 8;
+  if (table_pos < chunk_start[0] || table_pos + 8 > file_bytes) return vapc_set_error(VAPC_E_INVALID, "%s: chunk table missing", who);
+  uint32_t version, count;
+  memcpy(&version, file + table_pos, 4);
+  memcpy(&count, file + table_pos + 4, 4);
+  if (version != 0 || (int64_t)count < nchunks) return vapc_set_error(VAPC_E_INVALID, "%s: unexpected chunk table (version %u, %u chunks)", who, version, count);
+  ByteReader br{file + table_pos + 8, file + file_bytes};
+  ArithmeticDecoder dec;
+  dec.init(&br);
+  IntegerDecompressor ic(&dec, 32, 2);
+  int32_t prev = 0;
+  for (int64_t i = 0; i < nchunks; ++i) {
+    prev = ic.decompress(prev, 1);
+    chunk_start[(size_t)i + 1] = chunk_start[(size_t)i] + (uint32_t)prev;
+  }
+  if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "%s: chunk table truncated", who);
+  return VAPC_OK;
+}
+
+int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t npoints, int32_t point_size, uint32_t chunk_size,
+                   const uint16_t* items, int32_t nitems, uint8_t* out) {
+  const char* who = "vapc_laz_decode";
+  int extra = 0;
+  if (nitems < 1 || items[0] != 10 || items[1] != 30 || items[2] != 3)
+    return vapc_set_error(VAPC_E_INVALID, "%s: layered LASzip item type %d (size %d, version %d) is not supported (POINT14 v3 + BYTE14 v3 are)", who, items[0],
+                          items[1], items[2]);
+  if (nitems == 2 && items[3] == 14 && items[5] == 3) extra = items[4];
+  else if (nitems != 1)
+    return vapc_set_error(VAPC_E_INVALID, "%s: layered LASzip item type %d (size %d, version %d) is not supported (POINT14 v3 + BYTE14 v3 are)", who, items[3],
+                          items[4], items[5]);
+  if (30 + extra != point_size) return vapc_set_error(VAPC_E_INVALID, "%s: item sizes (%d) do not add up to the point size (%d)", who, 30 + extra, point_size);
+  if (npoints == 0) return VAPC_OK;
+  if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "%s: variable chunk sizes are not supported", who);
+  const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
+  std::vector<int64_t> chunk_start;
+  if (const int rc = read_chunk_table(who, file, file_bytes, offset_to_points, nchunks, chunk_start)) return rc;
+  std::unique_ptr<Point14V3> p14(new Point14V3());
+  std::unique_ptr<Byte14V3> b14(extra ? new Byte14V3(extra) : nullptr);
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t first = c * (int64_t)chunk_size;
+    const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
+    const int64_t begin = chunk_start[(size_t)c], limit = chunk_start[(size_t)c + 1];
+    const int64_t head = point_size + 4 + 4 * (kLayers14 + extra);
+    if (limit > file_bytes || begin + head > limit) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld outside the file", who, (long long)c);
+    uint8_t* rec = out + first * point_size;
+    memcpy(rec, file + begin, (size_t)point_size);  // the first point of a chunk is stored raw
+    uint32_t stored;
+    memcpy(&stored, file + begin + point_size, 4);
+    if ((int64_t)stored != count) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld holds %u points, expected %lld", who, (long long)c, stored, (long long)count);
+    const uint8_t* sizes = file + begin + point_size + 4;
+    const uint8_t* layers = file + begin + head;
+    const int64_t used = p14->begin_chunk(rec, sizes, layers, file + limit);
+    if (b14) b14->begin_chunk(rec + 30, p14->current, sizes + 4 * kLayers14, layers + used, file + limit);
+    for (int64_t p = 1; p < count; ++p) {
+      uint8_t* r = rec + p * point_size;
+      const uint32_t context = p14->read(r);
+      if (b14) b14->read(r + 30, context);
+    }
+    // a correct decode ends every layer on the last byte of its stream
+    bool exact = !p14->overrun();
+    for (int l = 0; l < kLayers14 && exact; ++l) exact = !p14->changed[l] || p14->br[l].p == p14->br[l].end;
+    if (b14) {
+      exact = exact && !b14->overrun();
+      for (int i = 0; i < b14->number && exact; ++i) exact = !b14->changed[(size_t)i] || b14->br[(size_t)i].p == b14->br[(size_t)i].end;
+    }
+    if (!exact) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld is truncated or corrupt (a layer's decoder did not end with its stream)", who, (long long)c);
+  }
+  return VAPC_OK;
+}
+
 int check_items(const char* who, const uint16_t* items, int nitems, int point_size) {
   int total = 0;
   for (int i = 0; i < nitems; ++i) {
@@ -783,7 +1188,9 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
                                int32_t compressor, uint32_t chunk_size, const uint16_t* items_host, int32_t nitems, uint8_t* records_out_host) {
   if (!file_host || !items_host || !records_out_host || file_bytes < 0 || npoints < 0 || nitems < 1)
     return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: bad arguments");
-  if (compressor != 2) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip compressor %d is not supported (only 2 = pointwise chunked)", compressor);
+  if (compressor == 3) return decode_layered(file_host, file_bytes, offset_to_points, npoints, point_size, chunk_size, items_host, nitems, records_out_host);
+  if (compressor != 2)
+    return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: LASzip compressor %d is not supported (2 = pointwise chunked and 3 = layered chunked are)", compressor);
   if (const int rc = check_items("vapc_laz_decode", items_host, nitems, point_size)) return rc;
   if (npoints == 0) return VAPC_OK;
   if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: variable chunk sizes are not supported");

@@ -10,10 +10,12 @@ needs from it for plain `.las` files and mirrors laspy's conventions:
 * writing LAS 1.4 point format 7 with offsets = coordinate minima and scale 2.5e-4 by default, extra
   dimensions as float32 (`datahandler.py:99-165`).
 
-LAZ: files compressed with LASzip's "pointwise chunked" scheme whose items are POINT10 v2 (+ RGB12 v2) — point formats
-0 and 2, the layout of the reference's `vapc_in.laz` / `small_mask.laz` fixtures — are decoded by the library's host
-entry point `vapc_laz_decode` (vapc_b200/csrc/laz.cu).  Other LAZ layouts (GPS time, LAS 1.4 layered items) raise
-NotImplementedError naming the item; `laspy` with a LAZ backend reads them when it is installed.
+LAZ: the library's own LASzip codec (vapc_b200/csrc/laz.cu, host entry points `vapc_laz_decode` / `vapc_laz_encode`) reads
+all four fixtures of the reference — "pointwise chunked" POINT10 v2 (+ RGB12 v2, + BYTE v2 extra bytes): point formats 0 and 2
+(`vapc_in.laz`, `small_mask.laz`), and the "layered chunked" POINT14 v3 (+ BYTE14 v3) of LAS 1.4 point format 6
+(`tree_wind_condition.laz`, `als_multichannel_leg000_points.laz`) — and writes `.laz` as LAS 1.2 point format 0 / 2 + extra bytes
+(`write_laz`).  Other items (GPSTIME11, RGB14, wave packets) raise NotImplementedError naming the item; `laspy` with a LAZ
+backend reads them when it is installed.
 """
 from __future__ import annotations
 
