@@ -447,11 +447,12 @@ VAPC_API int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64
                     int32_t point_size, int32_t compressor, uint32_t chunk_size, const uint16_t* items_host,
                     int32_t nitems, uint8_t* records_out_host);
 
-/* The mirror: npoints records -> LASzip stream (compressor 2, fixed chunk_size; items POINT10 v2, RGB12 v2, BYTE v2).  The
- * stream starts with the 8-byte position of its chunk table, counted from the start of the file: stream_offset_host = the
- * header's offset to point data.  *out_bytes_host receives the stream length (also when out_cap is too small:
- * VAPC_E_WORKSPACE).  Pinned: re-encoding the decoded records of the reference's vapc_in.laz reproduces the file's point
- * data byte for byte, chunk table included (tests/test_laz.py).  vapc_laz_decode reads BYTE v2 items as well. */
+/* The mirror: npoints records -> LASzip stream with a fixed chunk_size; items POINT10 v2 / RGB12 v2 / BYTE v2 (compressor 2,
+ * pointwise chunked) or POINT14 v3 (+ BYTE14 v3) (compressor 3, layered chunked: layers that never change inside a chunk are
+ * omitted).  The stream starts with the 8-byte position of its chunk table, counted from the start of the file:
+ * stream_offset_host = the header's offset to point data.  *out_bytes_host receives the stream length (also when out_cap is too
+ * small: VAPC_E_WORKSPACE).  Pinned: re-encoding the decoded records of each of the reference's four LAZ fixtures reproduces the
+ * file's point data byte for byte, layer sizes and chunk table included (tests/test_laz.py). */
 VAPC_API int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int32_t point_size, uint32_t chunk_size,
                     const uint16_t* items_host, int32_t nitems, int64_t stream_offset_host, uint8_t* out_host, int64_t out_cap,
                     int64_t* out_bytes_host);

@@ -117,19 +117,20 @@ def test_save_as_las_roundtrip(tmp_path):
     for c in ("point_count", "cov_xx"):  # extra dimensions are float32 (datahandler.py:157)
         np.testing.assert_array_equal(back.df[c].to_numpy(), df[c].to_numpy().astype(np.float32).astype(np.float64))
     assert back.df["scanner_channel"].eq(0).all() and back.df["overlap"].eq(0).all()  # not written (datahandler.py:152)
-    # .laz: the library's own LASzip encoder (LAS 1.2, point format 0 / 2, the rest as extra bytes) and decoder
+    # .laz: the library's own LASzip encoder and decoder (no colours here: LAS 1.4 point format 6 + extra bytes, layered)
     laz = str(tmp_path / "out.laz")
     dh.save_as_las(laz)
     assert os.path.getsize(laz) < os.path.getsize(out)
     hz, _ = las.read_las(laz)
-    assert hz.compressed and hz.version == (1, 2) and hz.point_count == n and hz.laszip["items"][0] == (6, 20, 2) and hz.laszip["items"][-1][0] == 0
+    assert hz.compressed and hz.version == (1, 4) and hz.point_format == 6 and hz.point_count == n
+    assert hz.laszip["compressor"] == 3 and hz.laszip["items"][0] == (10, 30, 3) and hz.laszip["items"][-1][0] == 14
     again = DataHandler(laz)
     again.load_las_files()
     for c in "XYZ":
         assert np.abs(again.df[c].to_numpy() - df[c].to_numpy()).max() <= 0.000125 + 1e-9
     for c in ("intensity", "classification", "return_number"):
         np.testing.assert_array_equal(again.df[c].to_numpy(), df[c].to_numpy())
-    np.testing.assert_array_equal(again.df["gps_time"].to_numpy(), df["gps_time"].to_numpy())  # a float64 extra dimension
+    np.testing.assert_array_equal(again.df["gps_time"].to_numpy(), df["gps_time"].to_numpy())
     for c in ("point_count", "cov_xx"):
         np.testing.assert_array_equal(again.df[c].to_numpy(), df[c].to_numpy().astype(np.float32).astype(np.float64))
     plain = str(tmp_path / "plain.laz")
@@ -195,3 +196,54 @@ def test_command_line_templates_schema():
         assert set(cfg["vapc_command"]) == {"tool", "args"}
         tools.add(cfg["vapc_command"]["tool"])
     assert tools == {"compute", "statistics", "filter_and_compute", "filter", "mask", "subsample"}  # vapc_tools.py:376-411
+
+
+def test_save_as_laz_with_colours_uses_point_format_2(tmp_path):
+    """Frames with red / green / blue are written as LAS 1.2 point format 2 + extra bytes (POINT10 v2 + RGB12 v2 + BYTE v2)."""
+    rng = np.random.default_rng(2)
+    n = 5000
+    df = pd.DataFrame({"X": np.round(rng.random(n) * 30, 3), "Y": np.round(rng.random(n) * 30, 3), "Z": np.round(rng.random(n) * 5, 3),
+                       "intensity": rng.integers(0, 4000, n).astype(float), "classification": rng.integers(0, 20, n).astype(float),
+                       "red": rng.integers(0, 65536, n).astype(float), "green": rng.integers(0, 65536, n).astype(float),
+                       "blue": rng.integers(0, 65536, n).astype(float), "gps_time": 3e5 + np.arange(n) * 1e-5, "point_count": rng.integers(1, 9, n).astype(float)})
+    dh = DataHandler("")
+    dh.df = df.copy()
+    path = str(tmp_path / "rgb.laz")
+    dh.save_as_las(path)
+    h, _ = las.read_las(path)
+    assert h.compressed and h.version == (1, 2) and h.point_format == 2 and h.laszip["items"][:2] == [(6, 20, 2), (8, 6, 2)] and h.laszip["items"][2][0] == 0
+    back = DataHandler(path)
+    back.load_las_files()
+    for c in ("intensity", "classification", "red", "green", "blue", "gps_time", "point_count"):
+        np.testing.assert_array_equal(back.df[c].to_numpy(), df[c].to_numpy(), err_msg=c)
+    for c in "XYZ":
+        assert np.abs(back.df[c].to_numpy() - df[c].to_numpy()).max() <= 0.000125 + 1e-9
+
+
+def test_las_to_laz_conversion_of_the_command_line(tmp_path):
+    """What main.do_vapc_on_files does for save_as=".laz" (main.py:154-168 of the reference): the tool's LAS 1.4 / format 7 result is
+    loaded again and saved as .laz.  Its colour dimensions are all zero (the cloud had none), so the LAZ file is LAS 1.4 point
+    format 6 + extra bytes; every other column survives."""
+    rng = np.random.default_rng(4)
+    n = 3000
+    df = pd.DataFrame({"X": np.round(rng.random(n) * 30, 3), "Y": np.round(rng.random(n) * 30, 3), "Z": np.round(rng.random(n) * 5, 3),
+                       "intensity": rng.integers(0, 4000, n).astype(float), "point_count": rng.integers(1, 9, n).astype(float),
+                       "cog_x": rng.random(n), "cog_y": rng.random(n), "cog_z": rng.random(n)})
+    first = DataHandler("")
+    first.df = df.copy()
+    las_path = str(tmp_path / "compute.las")
+    first.save_as_las(las_path)
+    again = DataHandler(las_path)
+    again.load_las_files()
+    assert {"red", "green", "blue"} <= set(again.df.columns)  # format 7 always carries them
+    laz_path = str(tmp_path / "compute.laz")
+    again.save_as_las(laz_path)
+    h, _ = las.read_las(laz_path)
+    assert h.compressed and h.version == (1, 4) and h.point_format == 6 and os.path.getsize(laz_path) < os.path.getsize(las_path)
+    res = DataHandler(laz_path)
+    res.load_las_files()
+    assert len(res.df) == n and {"point_count", "cog_x", "cog_y", "cog_z", "intensity"} <= set(res.df.columns) and "red" not in res.df.columns
+    for c in ("point_count", "cog_x", "cog_y", "cog_z", "intensity"):
+        np.testing.assert_array_equal(res.df[c].to_numpy(), again.df[c].to_numpy(), err_msg=c)
+    for c in "XYZ":
+        assert np.abs(res.df[c].to_numpy() - df[c].to_numpy()).max() <= 2 * 0.000125 + 1e-9

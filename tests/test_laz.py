@@ -57,10 +57,11 @@ def test_vapc_in_multi_chunk_known_answers():
 
 
 @needs_fixtures
-@pytest.mark.parametrize("name", ["small_mask.laz", "vapc_in.laz"])
+@pytest.mark.parametrize("name", ["small_mask.laz", "vapc_in.laz", "tree_wind_condition.laz", "als_multichannel_leg000_points.laz"])
 def test_encoder_reproduces_laszip_byte_for_byte(name):
-    """Decode the reference's file, encode the records again: the point data of the file — 1 and 11 chunks of arithmetic-coded
-    POINT10 v2 + RGB12 v2 items and the chunk table — comes out identical to what LASzip wrote, byte for byte."""
+    """Decode the reference's file, encode the records again: the point data of the file comes out identical to what LASzip wrote,
+    byte for byte — 1 and 11 chunks of arithmetic-coded POINT10 v2 + RGB12 v2 items (LAS 1.2), 2 chunks each of layered POINT14 v3
+    (+ 44 BYTE14 v3 layers) with their layer sizes (LAS 1.4), and the chunk tables."""
     import ctypes as C
 
     from vapc_b200 import _lib as L
@@ -93,13 +94,38 @@ def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb):
     extra = dict(point_count=rng.integers(1, 60, n).astype(np.float32), noise=rng.random(n), small=rng.integers(-100, 100, n).astype(np.int16),
                  big=rng.integers(0, 2 ** 62, n).astype(np.int64))
     path = str(tmp_path / "t.laz")
-    las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk)
+    las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk, las14=False)
     h, c = las.read_las(path)
-    assert h.compressed and h.point_format == (2 if rgb else 0) and h.point_count == n and h.laszip["chunk_size"] == chunk
+    assert h.compressed and h.version == (1, 2) and h.point_format == (2 if rgb else 0) and h.point_count == n and h.laszip["chunk_size"] == chunk
     for k, v in (("x", x), ("y", y), ("z", z)):
         assert n == 0 or np.abs(c[k] - v).max() < 1e-9
     for k, v in std.items():
         np.testing.assert_array_equal(np.asarray(c[k]).astype(np.int64), np.asarray(v).astype(np.int64), err_msg=k)
+    for k, v in extra.items():
+        np.testing.assert_array_equal(c[k], v, err_msg=k)
+
+
+@pytest.mark.parametrize("n,chunk", [(0, 50000), (1, 50000), (2, 100), (1000, 100), (1001, 100), (120_001, 50000)])
+def test_laz14_write_read_roundtrip(tmp_path, n, chunk):
+    """LAS 1.4 point format 6 + extra bytes through the layered codec (runs anywhere): all four scanner channels in random
+    order (the per-channel contexts, which no fixture exercises), return numbers incl. r = 0 and r > n, GPS times that jump
+    between sequences, constant layers (omitted from the chunk) next to incompressible ones."""
+    rng = np.random.default_rng(n + chunk)
+    x, y, z = (np.round(rng.random(n) * s, 3) for s in (100.0, 50.0, 10.0))
+    gps = np.where(rng.random(n) < 0.02, rng.random(n) * 1e9, 5e5 + np.arange(n) * 1e-4 * rng.integers(1, 4, n))
+    std = dict(intensity=rng.integers(0, 65536, n), return_number=rng.integers(0, 16, n), number_of_returns=rng.integers(0, 16, n),
+               scan_direction_flag=rng.integers(0, 2, n), edge_of_flight_line=rng.integers(0, 2, n), classification=rng.integers(0, 256, n),
+               synthetic=rng.integers(0, 2, n), overlap=rng.integers(0, 2, n), scanner_channel=rng.integers(0, 4, n), scan_angle=rng.integers(-30000, 30001, n),
+               user_data=np.full(n, 7), point_source_id=np.full(n, 4711), gps_time=gps)
+    extra = dict(point_count=rng.integers(1, 60, n).astype(np.float32), noise=rng.random(n), constant=np.full(n, 3, np.int16))
+    path = str(tmp_path / "t14.laz")
+    las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk)
+    h, c = las.read_las(path)
+    assert h.compressed and h.version == (1, 4) and h.point_format == 6 and h.point_count == n and h.laszip["compressor"] == 3
+    for k, v in (("x", x), ("y", y), ("z", z)):
+        assert n == 0 or np.abs(c[k] - v).max() < 1e-9
+    for k, v in std.items():
+        np.testing.assert_array_equal(np.asarray(c[k]).astype(np.float64), np.asarray(v).astype(np.float64), err_msg=k)
     for k, v in extra.items():
         np.testing.assert_array_equal(c[k], v, err_msg=k)
 

@@ -1091,6 +1091,352 @@ struct Byte14V3 {
   }
 };
 
+
+// ---- encoder side of the layered items: the mirror of Point14V3 / Byte14V3 ------------------------------------------
+struct Point14V3Writer {
+  struct Ctx {
+    bool unused = true;
+    P14 last;
+    uint16_t last_intensity[8];
+    Median5 mx[12], my[12];
+    int32_t last_Z[8];
+    std::unique_ptr<SymbolModel> changed_values[8], scanner_channel, number_of_returns[16], return_number_gps_same, return_number[16];
+    std::unique_ptr<SymbolModel> classification[64], flags[64], user_data[64], gps_multi, gps_0diff;
+    std::unique_ptr<IntegerCompressor> ic_dx, ic_dy, ic_z, ic_intensity, ic_scan_angle, ic_source, ic_gps;
+    uint32_t gps_last = 0, gps_next = 0;
+    uint64_t last_gps[4];
+    int32_t last_gps_diff[4], multi_extreme[4];
+  };
+  std::vector<uint8_t> buf[kLayers14];
+  ArithmeticEncoder enc[kLayers14];
+  bool changed[kLayers14];
+  Ctx ctx[4];
+  uint32_t current = 0;
+
+  static SymbolModel& lazy(std::unique_ptr<SymbolModel>& m, uint32_t n) { return Point14V3::lazy(m, n); }
+  void create_and_init(uint32_t c, const P14& item) {
+    Ctx& x = ctx[c];
+    for (int i = 0; i < 8; ++i) lazy(x.changed_values[i], 128).init();
+    lazy(x.scanner_channel, 3).init();
+    for (int i = 0; i < 16; ++i) {
+      if (x.number_of_returns[i]) x.number_of_returns[i]->init();
+      if (x.return_number[i]) x.return_number[i]->init();
+    }
+    lazy(x.return_number_gps_same, 13).init();
+    if (!x.ic_dx) {
+      x.ic_dx.reset(new IntegerCompressor(&enc[kLayerXY], 32, 2));
+      x.ic_dy.reset(new IntegerCompressor(&enc[kLayerXY], 32, 22));
+      x.ic_z.reset(new IntegerCompressor(&enc[kLayerZ], 32, 20));
+      x.ic_intensity.reset(new IntegerCompressor(&enc[kLayerIntensity], 16, 4));
+      x.ic_scan_angle.reset(new IntegerCompressor(&enc[kLayerScanAngle], 16, 2));
+      x.ic_source.reset(new IntegerCompressor(&enc[kLayerSource], 16, 1));
+      x.ic_gps.reset(new IntegerCompressor(&enc[kLayerGps], 32, 9));
+    }
+    x.ic_dx->init(); x.ic_dy->init(); x.ic_z->init(); x.ic_intensity->init(); x.ic_scan_angle->init(); x.ic_source->init(); x.ic_gps->init();
+    for (int i = 0; i < 12; ++i) { x.mx[i].init(); x.my[i].init(); }
+    for (int i = 0; i < 8; ++i) { x.last_Z[i] = item.Z; x.last_intensity[i] = item.intensity; }
+    for (int i = 0; i < 64; ++i) {
+      if (x.classification[i]) x.classification[i]->init();
+      if (x.flags[i]) x.flags[i]->init();
+      if (x.user_data[i]) x.user_data[i]->init();
+    }
+    lazy(x.gps_multi, kGpsMultiTotal).init();
+    lazy(x.gps_0diff, 5).init();
+    x.gps_last = x.gps_next = 0;
+    for (int i = 0; i < 4; ++i) { x.last_gps[i] = 0; x.last_gps_diff[i] = 0; x.multi_extreme[i] = 0; }
+    memcpy(&x.last_gps[0], &item.gps_time, 8);
+    x.last = item;
+    x.last.gps_time_change = false;
+    x.unused = false;
+  }
+  uint32_t begin_chunk(const uint8_t* first_raw) {
+    for (int l = 0; l < kLayers14; ++l) {
+      buf[l].clear();
+      enc[l].init(&buf[l]);
+      changed[l] = false;
+    }
+    for (auto& c : ctx) c.unused = true;
+    P14 item;
+    item.unpack(first_raw);
+    current = item.scanner_channel;
+    create_and_init(current, item);
+    return current;
+  }
+  static int32_t quantize(float f) { return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f); }
+  void write_gps(Ctx& x, uint64_t gps) {
+    ArithmeticEncoder& e = enc[kLayerGps];
+    const int64_t d64 = (int64_t)(gps - x.last_gps[x.gps_last]);
+    const int32_t d32 = (int32_t)d64;
+    if (x.last_gps_diff[x.gps_last] == 0) {
+      if (d64 == (int64_t)d32) {
+        e.symbol(*x.gps_0diff, 0);
+        x.ic_gps->compress(0, d32, 0);
+        x.last_gps_diff[x.gps_last] = d32;
+        x.multi_extreme[x.gps_last] = 0;
+      } else {
+        for (uint32_t i = 1; i < 4; ++i) {
+          const int64_t o64 = (int64_t)(gps - x.last_gps[(x.gps_last + i) & 3]);
+          if (o64 == (int64_t)(int32_t)o64) {
+            e.symbol(*x.gps_0diff, i + 1);
+            x.gps_last = (x.gps_last + i) & 3;
+            write_gps(x, gps);
+            return;
+          }
+        }
+        e.symbol(*x.gps_0diff, 1);
+        x.ic_gps->compress((int32_t)(x.last_gps[x.gps_last] >> 32), (int32_t)(gps >> 32), 8);
+        e.write_bits(32, (uint32_t)gps);
+        x.gps_next = (x.gps_next + 1) & 3;
+        x.gps_last = x.gps_next;
+        x.last_gps_diff[x.gps_last] = 0;
+        x.multi_extreme[x.gps_last] = 0;
+      }
+      x.last_gps[x.gps_last] = gps;
+    } else {
+      if (d64 == (int64_t)d32) {
+        const int32_t ld = x.last_gps_diff[x.gps_last];
+        const int32_t multi = quantize((float)d32 / (float)ld);
+        if (multi == 1) {
+          e.symbol(*x.gps_multi, 1);
+          x.ic_gps->compress(ld, d32, 1);
+          x.multi_extreme[x.gps_last] = 0;
+        } else if (multi > 0) {
+          if (multi < kGpsMulti) {
+            e.symbol(*x.gps_multi, (uint32_t)multi);
+            x.ic_gps->compress((int32_t)((uint32_t)multi * (uint32_t)ld), d32, multi < 10 ? 2 : 3);
+          } else {
+            e.symbol(*x.gps_multi, kGpsMulti);
+            x.ic_gps->compress((int32_t)((uint32_t)kGpsMulti * (uint32_t)ld), d32, 4);
+            if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = d32; x.multi_extreme[x.gps_last] = 0; }
+          }
+        } else if (multi < 0) {
+          if (multi > kGpsMultiMinus) {
+            e.symbol(*x.gps_multi, (uint32_t)(kGpsMulti - multi));
+            x.ic_gps->compress((int32_t)((uint32_t)multi * (uint32_t)ld), d32, 5);
+          } else {
+            e.symbol(*x.gps_multi, (uint32_t)(kGpsMulti - kGpsMultiMinus));
+            x.ic_gps->compress((int32_t)((uint32_t)kGpsMultiMinus * (uint32_t)ld), d32, 6);
+            if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = d32; x.multi_extreme[x.gps_last] = 0; }
+          }
+        } else {
+          e.symbol(*x.gps_multi, 0);
+          x.ic_gps->compress(0, d32, 7);
+          if (++x.multi_extreme[x.gps_last] > 3) { x.last_gps_diff[x.gps_last] = d32; x.multi_extreme[x.gps_last] = 0; }
+        }
+      } else {
+        for (uint32_t i = 1; i < 4; ++i) {
+          const int64_t o64 = (int64_t)(gps - x.last_gps[(x.gps_last + i) & 3]);
+          if (o64 == (int64_t)(int32_t)o64) {
+            e.symbol(*x.gps_multi, (uint32_t)kGpsMultiCodeFull + i);
+            x.gps_last = (x.gps_last + i) & 3;
+            write_gps(x, gps);
+            return;
+          }
+        }
+        e.symbol(*x.gps_multi, kGpsMultiCodeFull);
+        x.ic_gps->compress((int32_t)(x.last_gps[x.gps_last] >> 32), (int32_t)(gps >> 32), 8);
+        e.write_bits(32, (uint32_t)gps);
+        x.gps_next = (x.gps_next + 1) & 3;
+        x.gps_last = x.gps_next;
+        x.last_gps_diff[x.gps_last] = 0;
+        x.multi_extreme[x.gps_last] = 0;
+      }
+      x.last_gps[x.gps_last] = gps;
+    }
+  }
+  uint32_t write(const uint8_t* raw) {
+    P14 item;
+    item.unpack(raw);
+    Ctx* x = &ctx[current];
+    const int lpr = (x->last.return_number == 1 ? 1 : 0) + (x->last.return_number >= x->last.number_of_returns ? 2 : 0) + (x->last.gps_time_change ? 4 : 0);
+    const uint32_t sc = item.scanner_channel;
+    const P14* ref = &x->last;  // what the point is compared with: the last point of ITS channel when that channel is alive
+    if (sc != current && !ctx[sc].unused) ref = &ctx[sc].last;
+    uint64_t gps_bits, ref_bits;
+    memcpy(&gps_bits, &item.gps_time, 8);
+    memcpy(&ref_bits, &ref->gps_time, 8);
+    const bool source_change = item.psid != ref->psid, gps_change = gps_bits != ref_bits, angle_change = item.scan_angle != ref->scan_angle;
+    const uint32_t last_n = ref->number_of_returns, last_r = ref->return_number, n = item.number_of_returns, r = item.return_number;
+    uint32_t cv = ((uint32_t)(sc != current) << 6) | ((uint32_t)source_change << 5) | ((uint32_t)gps_change << 4) | ((uint32_t)angle_change << 3) |
+                  ((uint32_t)(n != last_n) << 2);
+    if (r != last_r) cv |= r == (last_r + 1) % 16 ? 1u : (r == (last_r + 15) % 16 ? 2u : 3u);
+    enc[kLayerXY].symbol(*x->changed_values[lpr], cv);
+    if (cv & 64) {
+      const int diff = (int)sc - (int)current;
+      enc[kLayerXY].symbol(*x->scanner_channel, (uint32_t)(diff > 0 ? diff - 1 : diff + 4 - 1));
+      if (ctx[sc].unused) create_and_init(sc, x->last);
+      current = sc;
+      x = &ctx[current];
+    }
+    if (cv & 4) enc[kLayerXY].symbol(lazy(x->number_of_returns[last_n], 16), n);
+    if ((cv & 3) == 3) {
+      if (gps_change) {
+        enc[kLayerXY].symbol(lazy(x->return_number[last_r], 16), r);
+      } else {
+        const int diff = (int)r - (int)last_r;
+        enc[kLayerXY].symbol(*x->return_number_gps_same, (uint32_t)(diff > 1 ? diff - 2 : diff + 16 - 2));
+      }
+    }
+    const uint32_t m = return_map6(n, r), l = return_level8(n, r);
+    const int cpr = (r == 1 ? 2 : 0) + (r >= n ? 1 : 0);
+    const uint32_t mi = (m << 1) | (gps_change ? 1u : 0u);
+    int32_t diff = (int32_t)((uint32_t)item.X - (uint32_t)x->last.X);
+    x->ic_dx->compress(x->mx[mi].get(), diff, n == 1);
+    x->mx[mi].add(diff);
+    uint32_t kb = x->ic_dx->k;
+    diff = (int32_t)((uint32_t)item.Y - (uint32_t)x->last.Y);
+    x->ic_dy->compress(x->my[mi].get(), diff, (n == 1) + (kb < 20 ? (kb & ~1u) : 20));
+    x->my[mi].add(diff);
+    kb = (x->ic_dx->k + x->ic_dy->k) / 2;
+    x->ic_z->compress(x->last_Z[l], item.Z, (n == 1) + (kb < 18 ? (kb & ~1u) : 18));
+    if (x->last_Z[l] != item.Z) changed[kLayerZ] = true;
+    x->last_Z[l] = item.Z;
+    const int ccc = ((x->last.classification & 0x1F) << 1) + (cpr == 3 ? 1 : 0);
+    enc[kLayerClass].symbol(lazy(x->classification[ccc], 256), item.classification);
+    if (x->last.classification != item.classification) changed[kLayerClass] = true;
+    const uint32_t lf = ((uint32_t)x->last.edge << 5) | ((uint32_t)x->last.scan_dir << 4) | x->last.class_flags;
+    const uint32_t f = ((uint32_t)item.edge << 5) | ((uint32_t)item.scan_dir << 4) | item.class_flags;
+    enc[kLayerFlags].symbol(lazy(x->flags[lf], 64), f);
+    if (lf != f) changed[kLayerFlags] = true;
+    const uint32_t ii = ((uint32_t)cpr << 1) | (gps_change ? 1u : 0u);
+    x->ic_intensity->compress(x->last_intensity[ii], item.intensity, (uint32_t)cpr);
+    if (x->last_intensity[ii] != item.intensity) changed[kLayerIntensity] = true;
+    x->last_intensity[ii] = item.intensity;
+    if (angle_change) {
+      x->ic_scan_angle->compress((int32_t)(uint16_t)x->last.scan_angle, (int32_t)(uint16_t)item.scan_angle, gps_change ? 1 : 0);
+      changed[kLayerScanAngle] = true;
+    }
+    enc[kLayerUserData].symbol(lazy(x->user_data[x->last.user_data / 4], 256), item.user_data);
+    if (x->last.user_data != item.user_data) changed[kLayerUserData] = true;
+    if (source_change) {
+      x->ic_source->compress(x->last.psid, item.psid, 0);
+      changed[kLayerSource] = true;
+    }
+    if (gps_change) {
+      write_gps(*x, gps_bits);
+      changed[kLayerGps] = true;
+    }
+    x->last = item;
+    x->last.gps_time_change = gps_change;
+    return current;
+  }
+  void end_chunk() {
+    for (int l = 0; l < kLayers14; ++l) enc[l].done();
+  }
+  uint32_t layer_bytes(int l) const { return (l == kLayerXY || changed[l]) ? (uint32_t)buf[l].size() : 0u; }
+};
+
+struct Byte14V3Writer {
+  int number;
+  struct Ctx {
+    bool unused = true;
+    std::vector<uint8_t> last;
+    std::vector<std::unique_ptr<SymbolModel>> m;
+  };
+  std::vector<std::vector<uint8_t>> buf;
+  std::vector<ArithmeticEncoder> enc;
+  std::vector<char> changed;
+  Ctx ctx[4];
+  uint32_t current = 0;
+  explicit Byte14V3Writer(int n) : number(n), buf((size_t)n), enc((size_t)n), changed((size_t)n) {}
+  void create_and_init(uint32_t c, const uint8_t* item) {
+    Ctx& x = ctx[c];
+    if (x.m.empty())
+      for (int i = 0; i < number; ++i) x.m.emplace_back(new SymbolModel(256));
+    for (auto& m : x.m) m->init();
+    x.last.assign(item, item + number);
+    x.unused = false;
+  }
+  void begin_chunk(const uint8_t* first_raw, uint32_t context) {
+    for (int i = 0; i < number; ++i) {
+      buf[(size_t)i].clear();
+      enc[(size_t)i].init(&buf[(size_t)i]);
+      changed[(size_t)i] = 0;
+    }
+    for (auto& c : ctx) c.unused = true;
+    current = context;
+    create_and_init(current, first_raw);
+  }
+  void write(const uint8_t* item, uint32_t context) {
+    if (context != current) {
+      if (ctx[context].unused) create_and_init(context, ctx[current].last.data());
+      current = context;
+    }
+    Ctx& x = ctx[current];
+    for (int i = 0; i < number; ++i) {
+      const int diff = (int)item[i] - (int)x.last[(size_t)i];
+      enc[(size_t)i].symbol(*x.m[(size_t)i], u8_fold(diff));
+      if (diff) {
+        changed[(size_t)i] = 1;
+        x.last[(size_t)i] = item[i];
+      }
+    }
+  }
+  void end_chunk() {
+    for (int i = 0; i < number; ++i) enc[(size_t)i].done();
+  }
+  uint32_t layer_bytes(int i) const { return changed[(size_t)i] ? (uint32_t)buf[(size_t)i].size() : 0u; }
+};
+
+void write_chunk_table(std::vector<uint8_t>& out, const std::vector<uint32_t>& chunk_bytes) {
+  const uint32_t version = 0, count = (uint32_t)chunk_bytes.size();
+  const uint8_t* v = reinterpret_cast<const uint8_t*>(&version);
+  const uint8_t* n = reinterpret_cast<const uint8_t*>(&count);
+  out.insert(out.end(), v, v + 4);
+  out.insert(out.end(), n, n + 4);
+  if (count == 0) return;
+  ArithmeticEncoder enc;
+  enc.init(&out);
+  IntegerCompressor ic(&enc, 32, 2);
+  int32_t prev = 0;
+  for (uint32_t b : chunk_bytes) {
+    ic.compress(prev, (int32_t)b, 1);
+    prev = (int32_t)b;
+  }
+  enc.done();
+}
+
+void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size, uint32_t chunk_size, int extra, std::vector<uint8_t>& out,
+                    std::vector<uint32_t>& chunk_bytes) {
+  std::unique_ptr<Point14V3Writer> p14(new Point14V3Writer());
+  std::unique_ptr<Byte14V3Writer> b14(extra ? new Byte14V3Writer(extra) : nullptr);
+  const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t first = c * (int64_t)chunk_size;
+    const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
+    const uint8_t* rec = records + first * point_size;
+    const size_t begin = out.size();
+    out.insert(out.end(), rec, rec + point_size);
+    const uint32_t context = p14->begin_chunk(rec);
+    if (b14) b14->begin_chunk(rec + 30, context);
+    for (int64_t p = 1; p < count; ++p) {
+      const uint8_t* r = rec + p * point_size;
+      const uint32_t cx = p14->write(r);
+      if (b14) b14->write(r + 30, cx);
+    }
+    p14->end_chunk();
+    if (b14) b14->end_chunk();
+    const uint32_t cnt = (uint32_t)count;
+    const uint8_t* cp = reinterpret_cast<const uint8_t*>(&cnt);
+    out.insert(out.end(), cp, cp + 4);
+    for (int l = 0; l < kLayers14; ++l) {
+      const uint32_t nb = p14->layer_bytes(l);
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
+      out.insert(out.end(), q, q + 4);
+    }
+    for (int i = 0; i < extra; ++i) {
+      const uint32_t nb = b14->layer_bytes(i);
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
+      out.insert(out.end(), q, q + 4);
+    }
+    for (int l = 0; l < kLayers14; ++l)
+      if (p14->layer_bytes(l)) out.insert(out.end(), p14->buf[l].begin(), p14->buf[l].end());
+    for (int i = 0; i < extra; ++i)
+      if (b14->layer_bytes(i)) out.insert(out.end(), b14->buf[(size_t)i].begin(), b14->buf[(size_t)i].end());
+    chunk_bytes.push_back((uint32_t)(out.size() - begin));
+  }
+}
+
 // chunk start positions from the chunk table (both compressors write the same table)
 int read_chunk_table(const char* who, const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t nchunks, std::vector<int64_t>& chunk_start) {
   int64_t table_pos;
@@ -1267,8 +1613,24 @@ extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int
                                int32_t nitems, int64_t stream_offset_host, uint8_t* out_host, int64_t out_cap, int64_t* out_bytes_host) {
   if (!items_host || !out_bytes_host || npoints < 0 || nitems < 1 || point_size < 1 || (npoints > 0 && !records_host))
     return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: bad arguments");
-  if (const int rc = check_items("vapc_laz_encode", items_host, nitems, point_size)) return rc;
   if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: a fixed chunk size is required");
+  if (items_host[0] == 10) {  // LAS 1.4: layered chunked (compressor 3), POINT14 v3 (+ BYTE14 v3)
+    int extra = 0;
+    const bool ok = items_host[1] == 30 && items_host[2] == 3 && (nitems == 1 || (nitems == 2 && items_host[3] == 14 && items_host[5] == 3));
+    if (nitems == 2) extra = items_host[4];
+    if (!ok || 30 + extra != point_size) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: layered items must be POINT14 v3 (+ BYTE14 v3) adding up to the point size");
+    std::vector<uint8_t> lay(8, 0);
+    std::vector<uint32_t> sizes;
+    encode_layered(records_host, npoints, point_size, chunk_size, extra, lay, sizes);
+    const int64_t tpos = stream_offset_host + (int64_t)lay.size();
+    memcpy(lay.data(), &tpos, 8);
+    write_chunk_table(lay, sizes);
+    *out_bytes_host = (int64_t)lay.size();
+    if (!out_host || out_cap < (int64_t)lay.size()) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_laz_encode: output buffer too small (%lld bytes needed)", (long long)lay.size());
+    memcpy(out_host, lay.data(), lay.size());
+    return VAPC_OK;
+  }
+  if (const int rc = check_items("vapc_laz_encode", items_host, nitems, point_size)) return rc;
   std::vector<uint8_t> out(8, 0);
   ArithmeticEncoder enc;
   std::vector<std::unique_ptr<ItemWriter>> writers;

@@ -109,14 +109,16 @@ class DataHandler:
             out.write(outfile)
             return
         if outfile.lower().endswith(".laz"):
-            # native LASzip encoder: LAS 1.2, point format 0 / 2, everything without a legacy field as float32 extra bytes
-            legacy = set(_las.dimension_names(2))
+            # native LASzip encoder: LAS 1.4 point format 6 + extra bytes (no colours), else LAS 1.2 point format 2 + extra bytes
+            rgb = [c for c in ("red", "green", "blue") if c in self.df.columns]
+            coloured = any(bool(self.df[c].to_numpy().any()) for c in rgb)  # all-zero colours (a point-format-7 file without colours) are dropped
+            known = set(_las.dimension_names(2 if coloured else 6))
             standard, extra = {}, {}
             for name in self.df.columns:
-                if name in _SKIP_ON_SAVE:
+                if name in _SKIP_ON_SAVE or (name in rgb and not coloured):
                     continue
                 col = self.df[name].to_numpy()
-                if name in legacy:
+                if name in known:
                     standard[name] = col
                 elif name == "gps_time":
                     extra[name] = np.asarray(col, dtype=np.float64)  # seconds of a GPS week need all 53 bits

@@ -201,10 +201,9 @@ def read_las_ints(path: str):
     return header, np.ascontiguousarray(cols["X"], dtype=np.int32), np.ascontiguousarray(cols["Y"], dtype=np.int32), np.ascontiguousarray(cols["Z"], dtype=np.int32)
 
 
-def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
-              point_format: int = 7, generating_software: str = "vapc_b200"):
-    """LAS 1.4, point format 6 / 7 / 8.  `standard`: values for standard dimensions by laspy name (cast to the field
-    type); `extra`: extra-byte dimensions (float32 / int16 / ... arrays)."""
+def _build_las14(x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales, offsets, point_format: int,
+                 generating_software: str, more_vlrs: bytes = b"", n_more_vlrs: int = 0, compressed: bool = False):
+    """(header, VLR bytes, point records) of a LAS 1.4 file of point format 6 / 7 / 8; shared by write_las and write_laz."""
     if point_format not in (6, 7, 8):
         raise ValueError("writer supports point formats 6, 7 and 8 (LAS 1.4)")
     x, y, z = (np.asarray(a, np.float64) for a in (x, y, z))
@@ -257,8 +256,9 @@ def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     sw = generating_software.encode("ascii", "replace")[:31]
     header[58:58 + len(sw)] = sw
     struct.pack_into("<HH", header, 90, 1, 2026)  # creation day / year
-    struct.pack_into("<HII", header, 94, 375, 375 + len(vlr), 1 if vlr else 0)
-    struct.pack_into("<BH", header, 104, point_format, dt.itemsize)
+    vlr = more_vlrs + vlr
+    struct.pack_into("<HII", header, 94, 375, 375 + len(vlr), n_more_vlrs + (1 if extra_fields else 0))
+    struct.pack_into("<BH", header, 104, point_format | (0x80 if compressed else 0), dt.itemsize)
     struct.pack_into("<I", header, 107, 0)  # legacy counts are 0 for formats >= 6
     mins = [float(c.min()) if n else 0.0 for c in (x, y, z)]
     maxs = [float(c.max()) if n else 0.0 for c in (x, y, z)]
@@ -267,30 +267,79 @@ def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     rn = (rec["return_byte"] & 0x0F).astype(np.int64)
     by_return = np.bincount(rn[(rn >= 1) & (rn <= 15)] - 1, minlength=15)[:15] if n else np.zeros(15, np.int64)
     struct.pack_into("<15Q", header, 255, *[int(v) for v in by_return])
+    return header, vlr, rec
+
+
+def write_las(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
+              point_format: int = 7, generating_software: str = "vapc_b200"):
+    """LAS 1.4, point format 6 / 7 / 8.  `standard`: values for standard dimensions by laspy name (cast to the field
+    type); `extra`: extra-byte dimensions (float32 / int16 / ... arrays)."""
+    header, vlr, rec = _build_las14(x, y, z, standard, extra, scales, offsets, point_format, generating_software)
     with open(path, "wb") as f:
         f.write(bytes(header))
         f.write(vlr)
         f.write(rec.tobytes())
 
 
+def _laz_encode(rec: np.ndarray, items, chunk_size: int, offset_to_points: int) -> bytes:
+    """Point records -> LASzip stream through vapc_laz_encode."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    raw = np.frombuffer(rec.tobytes(), dtype=np.uint8)
+    n, size = len(rec), rec.dtype.itemsize
+    item_arr = np.array(items, dtype=np.uint16).reshape(-1)
+    cap = int(raw.size + raw.size // 8 + 1024 * (n // max(1, chunk_size) + 2) + 4096)
+    nbytes = C.c_int64(0)
+    for _ in range(2):  # incompressible data: retry once with the size the encoder asked for
+        out = np.empty(cap, dtype=np.uint8)
+        rc = L.raw("vapc_laz_encode")(raw.ctypes.data_as(C.c_void_p), n, size, int(chunk_size), item_arr.ctypes.data_as(C.c_void_p), len(items),
+                                      int(offset_to_points), out.ctypes.data_as(C.c_void_p), cap, C.byref(nbytes))
+        if rc != L.VAPC_E_WORKSPACE:
+            break
+        cap = int(nbytes.value)
+    L.check(rc)
+    return out[: nbytes.value].tobytes()
+
+
 def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
-              chunk_size: int = 50000, generating_software: str = "vapc_b200"):
-    """LASzip-compressed LAS 1.2 through the library's own encoder (vapc_laz_encode): point format 2 when red / green / blue are
-    given, else 0, every other dimension as extra bytes; "pointwise chunked" compression of the items POINT10 v2 (+ RGB12 v2)
-    (+ BYTE v2) — the layout of the reference's vapc_in.laz fixture, whose point data the encoder reproduces byte for byte
-    (tests/test_laz.py).  Values that do not fit the legacy fields (return numbers above 7, classes above 31) are masked as
-    in any point-format-0 file; pass them as extra dimensions to keep them."""
+              chunk_size: int = 50000, generating_software: str = "vapc_b200", las14=None):
+    """LASzip-compressed output through the library's own encoder (vapc_laz_encode).
+    las14 (default: whenever there are no colours): LAS 1.4 point format 6 + extra bytes, "layered chunked" compression of the
+    items POINT14 v3 (+ BYTE14 v3) — the layout of the reference's LAS 1.4 fixtures.  Otherwise LAS 1.2: point format 2 when red /
+    green / blue are given, else 0, every other dimension as extra bytes, "pointwise chunked" compression of POINT10 v2 (+ RGB12 v2)
+    (+ BYTE v2) — the layout of the reference's vapc_in.laz; values that do not fit the legacy fields (return numbers above 7,
+    classes above 31) are masked as in any point-format-0 file.  The encoder reproduces the point data of all four fixtures byte
+    for byte (tests/test_laz.py)."""
     import ctypes as C
 
     from . import _lib as L
 
     x, y, z = (np.asarray(a, np.float64) for a in (x, y, z))
     n = len(x)
+    coloured = any(c in standard for c in ("red", "green", "blue"))
+    if las14 is None:
+        las14 = not coloured
+    if las14:
+        if coloured:
+            raise NotImplementedError("LAZ with colours is written as LAS 1.2 point format 2 (the LASzip item RGB14 is not implemented)")
+        extra_size = sum(np.dtype(_EXTRA_TYPES[_EXTRA_CODES.get(np.asarray(a).dtype.str.lstrip("<|"), 9)]).itemsize for a in extra.values())
+        items = [(10, 30, 3)] + ([(14, extra_size, 3)] if extra_size else [])
+        body = struct.pack("<HHBBHIIqqH", 3, 0, 3, 4, 3, 0, int(chunk_size), -1, -1, len(items)) + b"".join(struct.pack("<HHH", *it) for it in items)
+        lvlr = struct.pack("<H16sHH32s", 0, b"laszip encoded", 22204, len(body), b"vapc_b200 LASzip-compatible") + body
+        header, vlr, rec = _build_las14(x, y, z, standard, extra, scales, offsets, 6, generating_software, more_vlrs=lvlr, n_more_vlrs=1, compressed=True)
+        stream = _laz_encode(rec, items, int(chunk_size), 375 + len(vlr))
+        with open(path, "wb") as f:
+            f.write(bytes(header))
+            f.write(vlr)
+            f.write(stream)
+        return
     scales = np.asarray([0.00025] * 3 if scales is None else scales, np.float64)
     if offsets is None:
         offsets = np.array([x.min(), y.min(), z.min()]) if n else np.zeros(3)
     offsets = np.asarray(offsets, np.float64)
-    point_format = 2 if any(c in standard for c in ("red", "green", "blue")) else 0
+    point_format = 2 if coloured else 0
     fields = list(POINT_FORMATS[point_format])
     core_size = np.dtype(fields).itemsize
     known = set(dimension_names(point_format))
@@ -355,20 +404,8 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     mins = [float(c.min()) if n else 0.0 for c in (x, y, z)]
     maxs = [float(c.max()) if n else 0.0 for c in (x, y, z)]
     struct.pack_into("<12d", header, 131, *scales, *offsets, maxs[0], mins[0], maxs[1], mins[1], maxs[2], mins[2])
-    raw = np.frombuffer(rec.tobytes(), dtype=np.uint8)
-    item_arr = np.array(items, dtype=np.uint16).reshape(-1)
-    cap = int(raw.size + raw.size // 8 + 64 * (n // max(1, chunk_size) + 2) + 1024)
-    out = np.empty(cap, dtype=np.uint8)
-    nbytes = C.c_int64(0)
-    rc = L.raw("vapc_laz_encode")(raw.ctypes.data_as(C.c_void_p), n, dt.itemsize, int(chunk_size), item_arr.ctypes.data_as(C.c_void_p), len(items),
-                                  offset_to_points, out.ctypes.data_as(C.c_void_p), cap, C.byref(nbytes))
-    if rc == L.VAPC_E_WORKSPACE:  # incompressible data: retry with the size the encoder asked for
-        cap = int(nbytes.value)
-        out = np.empty(cap, dtype=np.uint8)
-        rc = L.raw("vapc_laz_encode")(raw.ctypes.data_as(C.c_void_p), n, dt.itemsize, int(chunk_size), item_arr.ctypes.data_as(C.c_void_p), len(items),
-                                      offset_to_points, out.ctypes.data_as(C.c_void_p), cap, C.byref(nbytes))
-    L.check(rc)
+    stream = _laz_encode(rec, items, int(chunk_size), offset_to_points)
     with open(path, "wb") as f:
         f.write(bytes(header))
         f.write(vlrs)
-        f.write(out[: nbytes.value].tobytes())
+        f.write(stream)
