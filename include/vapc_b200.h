@@ -440,7 +440,7 @@ VAPC_API int vapc_selftest_mahalanobis_host(const double* cov6_host, const doubl
  * records_out_host.  compressor / chunk_size / items (nitems triples type, size, version) come from the
  * "laszip encoded" VLR (record id 22204).  Supported: compressor 2 (pointwise chunked) with POINT10 v2, RGB12 v2 and BYTE v2
  * items, i.e. LAS point formats 0 and 2 (+ extra bytes) — the layout of the reference's vapc_in.laz / small_mask.laz — and
- * compressor 3 (layered chunked) with POINT14 v3 (+ BYTE14 v3), i.e. LAS 1.4 point format 6 (+ extra bytes) — the layout of its
+ * compressor 3 (layered chunked) with POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3), i.e. LAS 1.4 point formats 6 / 7 (+ extra bytes) — the layout of its
  * tree_wind_condition.laz / als_multichannel_leg000_points.laz; anything else returns VAPC_E_INVALID with a message naming
  * the item.  A layered chunk whose layer decoders do not end exactly on their streams' last bytes is reported as corrupt. */
 VAPC_API int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64_t offset_to_points, int64_t npoints,
@@ -448,7 +448,7 @@ VAPC_API int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64
                     int32_t nitems, uint8_t* records_out_host);
 
 /* The mirror: npoints records -> LASzip stream with a fixed chunk_size; items POINT10 v2 / RGB12 v2 / BYTE v2 (compressor 2,
- * pointwise chunked) or POINT14 v3 (+ BYTE14 v3) (compressor 3, layered chunked: layers that never change inside a chunk are
+ * pointwise chunked) or POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) (compressor 3, layered chunked: layers that never change inside a chunk are
  * omitted).  The stream starts with the 8-byte position of its chunk table, counted from the start of the file:
  * stream_offset_host = the header's offset to point data.  *out_bytes_host receives the stream length (also when out_cap is too
  * small: VAPC_E_WORKSPACE).  Pinned: re-encoding the decoded records of each of the reference's four LAZ fixtures reproduces the

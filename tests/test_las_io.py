@@ -198,8 +198,9 @@ def test_command_line_templates_schema():
     assert tools == {"compute", "statistics", "filter_and_compute", "filter", "mask", "subsample"}  # vapc_tools.py:376-411
 
 
-def test_save_as_laz_with_colours_uses_point_format_2(tmp_path):
-    """Frames with red / green / blue are written as LAS 1.2 point format 2 + extra bytes (POINT10 v2 + RGB12 v2 + BYTE v2)."""
+def test_save_as_laz_with_colours_uses_point_format_7(tmp_path):
+    """Frames with red / green / blue are written as LAS 1.4 point format 7 + extra bytes (POINT14 v3 + RGB14 v3 + BYTE14 v3):
+    the reference's own output format (datahandler.py:99-165)."""
     rng = np.random.default_rng(2)
     n = 5000
     df = pd.DataFrame({"X": np.round(rng.random(n) * 30, 3), "Y": np.round(rng.random(n) * 30, 3), "Z": np.round(rng.random(n) * 5, 3),
@@ -211,7 +212,7 @@ def test_save_as_laz_with_colours_uses_point_format_2(tmp_path):
     path = str(tmp_path / "rgb.laz")
     dh.save_as_las(path)
     h, _ = las.read_las(path)
-    assert h.compressed and h.version == (1, 2) and h.point_format == 2 and h.laszip["items"][:2] == [(6, 20, 2), (8, 6, 2)] and h.laszip["items"][2][0] == 0
+    assert h.compressed and h.version == (1, 4) and h.point_format == 7 and h.laszip["items"][:2] == [(10, 30, 3), (11, 6, 3)] and h.laszip["items"][2][0] == 14
     back = DataHandler(path)
     back.load_las_files()
     for c in ("intensity", "classification", "red", "green", "blue", "gps_time", "point_count"):

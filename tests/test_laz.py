@@ -106,7 +106,8 @@ def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb):
 
 
 @pytest.mark.parametrize("n,chunk", [(0, 50000), (1, 50000), (2, 100), (1000, 100), (1001, 100), (120_001, 50000)])
-def test_laz14_write_read_roundtrip(tmp_path, n, chunk):
+@pytest.mark.parametrize("rgb", [False, True])
+def test_laz14_write_read_roundtrip(tmp_path, n, chunk, rgb):
     """LAS 1.4 point format 6 + extra bytes through the layered codec (runs anywhere): all four scanner channels in random
     order (the per-channel contexts, which no fixture exercises), return numbers incl. r = 0 and r > n, GPS times that jump
     between sequences, constant layers (omitted from the chunk) next to incompressible ones."""
@@ -117,11 +118,15 @@ def test_laz14_write_read_roundtrip(tmp_path, n, chunk):
                scan_direction_flag=rng.integers(0, 2, n), edge_of_flight_line=rng.integers(0, 2, n), classification=rng.integers(0, 256, n),
                synthetic=rng.integers(0, 2, n), overlap=rng.integers(0, 2, n), scanner_channel=rng.integers(0, 4, n), scan_angle=rng.integers(-30000, 30001, n),
                user_data=np.full(n, 7), point_source_id=np.full(n, 4711), gps_time=gps)
+    if rgb:  # point format 7: RGB14 v3 in a layer of its own (grey runs, one constant channel)
+        grey = rng.integers(0, 65536, n)
+        std.update(red=grey, green=np.where(rng.random(n) < 0.5, grey, rng.integers(0, 65536, n)), blue=np.full(n, 513))
     extra = dict(point_count=rng.integers(1, 60, n).astype(np.float32), noise=rng.random(n), constant=np.full(n, 3, np.int16))
     path = str(tmp_path / "t14.laz")
     las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk)
     h, c = las.read_las(path)
-    assert h.compressed and h.version == (1, 4) and h.point_format == 6 and h.point_count == n and h.laszip["compressor"] == 3
+    assert h.compressed and h.version == (1, 4) and h.point_format == (7 if rgb else 6) and h.point_count == n and h.laszip["compressor"] == 3
+    assert [it[0] for it in h.laszip["items"]] == ([10, 11, 14] if rgb else [10, 14])
     for k, v in (("x", x), ("y", y), ("z", z)):
         assert n == 0 or np.abs(c[k] - v).max() < 1e-9
     for k, v in std.items():

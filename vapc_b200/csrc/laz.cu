@@ -1092,6 +1092,72 @@ struct Byte14V3 {
 };
 
 
+// RGB14 v3 (LAS 1.4 point formats 7 / 8): the colour coder of RGB12 v2 in a layer of its own, one context per scanner channel.
+// No fixture of the reference holds this item: round-trip tested, and guarded like every layer by the end-of-stream check.
+struct Rgb14V3 {
+  ByteReader br;
+  ArithmeticDecoder dec;
+  bool changed = false;
+  std::unique_ptr<Rgb12V2> ctx[4];
+  bool unused[4];
+  uint32_t current = 0;
+  void create_and_init(uint32_t c, const uint8_t* item) {
+    if (!ctx[c]) ctx[c].reset(new Rgb12V2(&dec));
+    ctx[c]->init(item);
+    unused[c] = false;
+  }
+  int64_t begin_chunk(const uint8_t* first_raw, uint32_t context, const uint8_t* sizes, const uint8_t* layers, const uint8_t* limit) {
+    uint32_t nb;
+    memcpy(&nb, sizes, 4);
+    br = ByteReader{layers, layers + nb <= limit ? layers + nb : limit};
+    changed = nb > 0;
+    if (changed) dec.init(&br);
+    for (auto& u : unused) u = true;
+    current = context;
+    create_and_init(current, first_raw);
+    return nb;
+  }
+  void read(uint8_t* out, uint32_t context) {
+    if (context != current) {
+      if (unused[context]) create_and_init(context, reinterpret_cast<const uint8_t*>(ctx[current]->last));
+      current = context;
+    }
+    if (changed) ctx[current]->read(out);
+    else memcpy(out, ctx[current]->last, 6);
+  }
+};
+struct Rgb14V3Writer {
+  std::vector<uint8_t> buf;
+  ArithmeticEncoder enc;
+  bool changed = false;
+  std::unique_ptr<Rgb12V2Writer> ctx[4];
+  bool unused[4];
+  uint32_t current = 0;
+  void create_and_init(uint32_t c, const uint8_t* item) {
+    if (!ctx[c]) ctx[c].reset(new Rgb12V2Writer(&enc));
+    ctx[c]->init(item);
+    unused[c] = false;
+  }
+  void begin_chunk(const uint8_t* first_raw, uint32_t context) {
+    buf.clear();
+    enc.init(&buf);
+    changed = false;
+    for (auto& u : unused) u = true;
+    current = context;
+    create_and_init(current, first_raw);
+  }
+  void write(const uint8_t* item, uint32_t context) {
+    if (context != current) {
+      if (unused[context]) create_and_init(context, reinterpret_cast<const uint8_t*>(ctx[current]->last));
+      current = context;
+    }
+    if (memcmp(ctx[current]->last, item, 6) != 0) changed = true;
+    ctx[current]->write(item);
+  }
+  void end_chunk() { enc.done(); }
+  uint32_t layer_bytes() const { return changed ? (uint32_t)buf.size() : 0u; }
+};
+
 // ---- encoder side of the layered items: the mirror of Point14V3 / Byte14V3 ------------------------------------------
 struct Point14V3Writer {
   struct Ctx {
@@ -1396,9 +1462,10 @@ void write_chunk_table(std::vector<uint8_t>& out, const std::vector<uint32_t>& c
   enc.done();
 }
 
-void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size, uint32_t chunk_size, int extra, std::vector<uint8_t>& out,
+void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size, uint32_t chunk_size, int rgb, int extra, std::vector<uint8_t>& out,
                     std::vector<uint32_t>& chunk_bytes) {
   std::unique_ptr<Point14V3Writer> p14(new Point14V3Writer());
+  std::unique_ptr<Rgb14V3Writer> c14(rgb ? new Rgb14V3Writer() : nullptr);
   std::unique_ptr<Byte14V3Writer> b14(extra ? new Byte14V3Writer(extra) : nullptr);
   const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
   for (int64_t c = 0; c < nchunks; ++c) {
@@ -1408,19 +1475,27 @@ void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size,
     const size_t begin = out.size();
     out.insert(out.end(), rec, rec + point_size);
     const uint32_t context = p14->begin_chunk(rec);
-    if (b14) b14->begin_chunk(rec + 30, context);
+    if (c14) c14->begin_chunk(rec + 30, context);
+    if (b14) b14->begin_chunk(rec + 30 + rgb, context);
     for (int64_t p = 1; p < count; ++p) {
       const uint8_t* r = rec + p * point_size;
       const uint32_t cx = p14->write(r);
-      if (b14) b14->write(r + 30, cx);
+      if (c14) c14->write(r + 30, cx);
+      if (b14) b14->write(r + 30 + rgb, cx);
     }
     p14->end_chunk();
+    if (c14) c14->end_chunk();
     if (b14) b14->end_chunk();
     const uint32_t cnt = (uint32_t)count;
     const uint8_t* cp = reinterpret_cast<const uint8_t*>(&cnt);
     out.insert(out.end(), cp, cp + 4);
     for (int l = 0; l < kLayers14; ++l) {
       const uint32_t nb = p14->layer_bytes(l);
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
+      out.insert(out.end(), q, q + 4);
+    }
+    if (c14) {
+      const uint32_t nb = c14->layer_bytes();
       const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
       out.insert(out.end(), q, q + 4);
     }
@@ -1431,11 +1506,13 @@ void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size,
     }
     for (int l = 0; l < kLayers14; ++l)
       if (p14->layer_bytes(l)) out.insert(out.end(), p14->buf[l].begin(), p14->buf[l].end());
+    if (c14 && c14->layer_bytes()) out.insert(out.end(), c14->buf.begin(), c14->buf.end());
     for (int i = 0; i < extra; ++i)
       if (b14->layer_bytes(i)) out.insert(out.end(), b14->buf[(size_t)i].begin(), b14->buf[(size_t)i].end());
     chunk_bytes.push_back((uint32_t)(out.size() - begin));
   }
 }
+
 
 // chunk start positions from the chunk table (both compressors write the same table)
 int read_chunk_table(const char* who, const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t nchunks, std::vector<int64_t>& chunk_start) {
@@ -1462,30 +1539,42 @@ int read_chunk_table(const char* who, const uint8_t* file, int64_t file_bytes, i
   return VAPC_OK;
 }
 
+// items of a layered file: POINT14 v3 [+ RGB14 v3] [+ BYTE14 v3]
+int layered_items(const char* who, const uint16_t* items, int nitems, int point_size, int* rgb, int* extra) {
+  *rgb = *extra = 0;
+  bool ok = nitems >= 1 && nitems <= 3 && items[0] == 10 && items[1] == 30 && items[2] == 3;
+  int bad = 0;
+  for (int i = 1; ok && i < nitems; ++i) {
+    const int type = items[3 * i], size = items[3 * i + 1], version = items[3 * i + 2];
+    if (type == 11 && size == 6 && version == 3 && i == 1) *rgb = 6;
+    else if (type == 14 && size > 0 && version == 3 && i == nitems - 1) *extra = size;
+    else { ok = false; bad = i; }
+  }
+  if (!ok)
+    return vapc_set_error(VAPC_E_INVALID, "%s: layered LASzip item type %d (size %d, version %d) is not supported (POINT14 v3, RGB14 v3 and BYTE14 v3 are)", who,
+                          items[3 * bad], items[3 * bad + 1], items[3 * bad + 2]);
+  if (30 + *rgb + *extra != point_size) return vapc_set_error(VAPC_E_INVALID, "%s: item sizes (%d) do not add up to the point size (%d)", who, 30 + *rgb + *extra, point_size);
+  return VAPC_OK;
+}
+
 int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t npoints, int32_t point_size, uint32_t chunk_size,
                    const uint16_t* items, int32_t nitems, uint8_t* out) {
   const char* who = "vapc_laz_decode";
-  int extra = 0;
-  if (nitems < 1 || items[0] != 10 || items[1] != 30 || items[2] != 3)
-    return vapc_set_error(VAPC_E_INVALID, "%s: layered LASzip item type %d (size %d, version %d) is not supported (POINT14 v3 + BYTE14 v3 are)", who, items[0],
-                          items[1], items[2]);
-  if (nitems == 2 && items[3] == 14 && items[5] == 3) extra = items[4];
-  else if (nitems != 1)
-    return vapc_set_error(VAPC_E_INVALID, "%s: layered LASzip item type %d (size %d, version %d) is not supported (POINT14 v3 + BYTE14 v3 are)", who, items[3],
-                          items[4], items[5]);
-  if (30 + extra != point_size) return vapc_set_error(VAPC_E_INVALID, "%s: item sizes (%d) do not add up to the point size (%d)", who, 30 + extra, point_size);
+  int extra = 0, rgb = 0;
+  if (const int rc = layered_items(who, items, nitems, point_size, &rgb, &extra)) return rc;
   if (npoints == 0) return VAPC_OK;
   if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "%s: variable chunk sizes are not supported", who);
   const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
   std::vector<int64_t> chunk_start;
   if (const int rc = read_chunk_table(who, file, file_bytes, offset_to_points, nchunks, chunk_start)) return rc;
   std::unique_ptr<Point14V3> p14(new Point14V3());
+  std::unique_ptr<Rgb14V3> c14(rgb ? new Rgb14V3() : nullptr);
   std::unique_ptr<Byte14V3> b14(extra ? new Byte14V3(extra) : nullptr);
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
     const int64_t begin = chunk_start[(size_t)c], limit = chunk_start[(size_t)c + 1];
-    const int64_t head = point_size + 4 + 4 * (kLayers14 + extra);
+    const int64_t head = point_size + 4 + 4 * (kLayers14 + (rgb ? 1 : 0) + extra);
     if (limit > file_bytes || begin + head > limit) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld outside the file", who, (long long)c);
     uint8_t* rec = out + first * point_size;
     memcpy(rec, file + begin, (size_t)point_size);  // the first point of a chunk is stored raw
@@ -1494,16 +1583,19 @@ int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_po
     if ((int64_t)stored != count) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld holds %u points, expected %lld", who, (long long)c, stored, (long long)count);
     const uint8_t* sizes = file + begin + point_size + 4;
     const uint8_t* layers = file + begin + head;
-    const int64_t used = p14->begin_chunk(rec, sizes, layers, file + limit);
-    if (b14) b14->begin_chunk(rec + 30, p14->current, sizes + 4 * kLayers14, layers + used, file + limit);
+    int64_t used = p14->begin_chunk(rec, sizes, layers, file + limit);
+    if (c14) used += c14->begin_chunk(rec + 30, p14->current, sizes + 4 * kLayers14, layers + used, file + limit);
+    if (b14) b14->begin_chunk(rec + 30 + rgb, p14->current, sizes + 4 * (kLayers14 + (rgb ? 1 : 0)), layers + used, file + limit);
     for (int64_t p = 1; p < count; ++p) {
       uint8_t* r = rec + p * point_size;
       const uint32_t context = p14->read(r);
-      if (b14) b14->read(r + 30, context);
+      if (c14) c14->read(r + 30, context);
+      if (b14) b14->read(r + 30 + rgb, context);
     }
     // a correct decode ends every layer on the last byte of its stream
     bool exact = !p14->overrun();
     for (int l = 0; l < kLayers14 && exact; ++l) exact = !p14->changed[l] || p14->br[l].p == p14->br[l].end;
+    if (c14 && c14->changed) exact = exact && !c14->br.overrun && c14->br.p == c14->br.end;
     if (b14) {
       exact = exact && !b14->overrun();
       for (int i = 0; i < b14->number && exact; ++i) exact = !b14->changed[(size_t)i] || b14->br[(size_t)i].p == b14->br[(size_t)i].end;
@@ -1615,13 +1707,11 @@ extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int
     return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: bad arguments");
   if (chunk_size == 0 || chunk_size == 0xFFFFFFFFu) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: a fixed chunk size is required");
   if (items_host[0] == 10) {  // LAS 1.4: layered chunked (compressor 3), POINT14 v3 (+ BYTE14 v3)
-    int extra = 0;
-    const bool ok = items_host[1] == 30 && items_host[2] == 3 && (nitems == 1 || (nitems == 2 && items_host[3] == 14 && items_host[5] == 3));
-    if (nitems == 2) extra = items_host[4];
-    if (!ok || 30 + extra != point_size) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_encode: layered items must be POINT14 v3 (+ BYTE14 v3) adding up to the point size");
+    int extra = 0, rgb = 0;
+    if (const int rc = layered_items("vapc_laz_encode", items_host, nitems, point_size, &rgb, &extra)) return rc;
     std::vector<uint8_t> lay(8, 0);
     std::vector<uint32_t> sizes;
-    encode_layered(records_host, npoints, point_size, chunk_size, extra, lay, sizes);
+    encode_layered(records_host, npoints, point_size, chunk_size, rgb, extra, lay, sizes);
     const int64_t tpos = stream_offset_host + (int64_t)lay.size();
     memcpy(lay.data(), &tpos, 8);
     write_chunk_table(lay, sizes);

@@ -109,10 +109,10 @@ class DataHandler:
             out.write(outfile)
             return
         if outfile.lower().endswith(".laz"):
-            # native LASzip encoder: LAS 1.4 point format 6 + extra bytes (no colours), else LAS 1.2 point format 2 + extra bytes
+            # native LASzip encoder: LAS 1.4 point format 6 + extra bytes, 7 when the cloud has colours (the reference's default)
             rgb = [c for c in ("red", "green", "blue") if c in self.df.columns]
             coloured = any(bool(self.df[c].to_numpy().any()) for c in rgb)  # all-zero colours (a point-format-7 file without colours) are dropped
-            known = set(_las.dimension_names(2 if coloured else 6))
+            known = set(_las.dimension_names(7 if coloured else 6))
             standard, extra = {}, {}
             for name in self.df.columns:
                 if name in _SKIP_ON_SAVE or (name in rgb and not coloured):

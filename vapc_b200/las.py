@@ -12,9 +12,9 @@ needs from it for plain `.las` files and mirrors laspy's conventions:
 
 LAZ: the library's own LASzip codec (vapc_b200/csrc/laz.cu, host entry points `vapc_laz_decode` / `vapc_laz_encode`) reads
 all four fixtures of the reference — "pointwise chunked" POINT10 v2 (+ RGB12 v2, + BYTE v2 extra bytes): point formats 0 and 2
-(`vapc_in.laz`, `small_mask.laz`), and the "layered chunked" POINT14 v3 (+ BYTE14 v3) of LAS 1.4 point format 6
-(`tree_wind_condition.laz`, `als_multichannel_leg000_points.laz`) — and writes `.laz` as LAS 1.2 point format 0 / 2 + extra bytes
-(`write_laz`).  Other items (GPSTIME11, RGB14, wave packets) raise NotImplementedError naming the item; `laspy` with a LAZ
+(`vapc_in.laz`, `small_mask.laz`), and the "layered chunked" POINT14 v3 (+ RGB14 v3, + BYTE14 v3) of LAS 1.4 point formats 6 / 7
+(`tree_wind_condition.laz`, `als_multichannel_leg000_points.laz`) — and writes `.laz` as LAS 1.4 point format 6 / 7 + extra bytes
+(`write_laz`).  Other items (GPSTIME11, RGBNIR14, wave packets) raise NotImplementedError naming the item; `laspy` with a LAZ
 backend reads them when it is installed.
 """
 from __future__ import annotations
@@ -306,8 +306,9 @@ def _laz_encode(rec: np.ndarray, items, chunk_size: int, offset_to_points: int) 
 def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
               chunk_size: int = 50000, generating_software: str = "vapc_b200", las14=None):
     """LASzip-compressed output through the library's own encoder (vapc_laz_encode).
-    las14 (default: whenever there are no colours): LAS 1.4 point format 6 + extra bytes, "layered chunked" compression of the
-    items POINT14 v3 (+ BYTE14 v3) — the layout of the reference's LAS 1.4 fixtures.  Otherwise LAS 1.2: point format 2 when red /
+    las14 (default): LAS 1.4 point format 6 (7 with colours: the reference's own output format, datahandler.py:99-165) + extra
+    bytes, "layered chunked" compression of the items POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) — the layout of the reference's LAS 1.4
+    fixtures (RGB14 is round-trip tested only: no fixture holds colours in LAS 1.4).  las14=False: LAS 1.2, point format 2 when red /
     green / blue are given, else 0, every other dimension as extra bytes, "pointwise chunked" compression of POINT10 v2 (+ RGB12 v2)
     (+ BYTE v2) — the layout of the reference's vapc_in.laz; values that do not fit the legacy fields (return numbers above 7,
     classes above 31) are masked as in any point-format-0 file.  The encoder reproduces the point data of all four fixtures byte
@@ -320,15 +321,14 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     n = len(x)
     coloured = any(c in standard for c in ("red", "green", "blue"))
     if las14 is None:
-        las14 = not coloured
+        las14 = True
     if las14:
-        if coloured:
-            raise NotImplementedError("LAZ with colours is written as LAS 1.2 point format 2 (the LASzip item RGB14 is not implemented)")
         extra_size = sum(np.dtype(_EXTRA_TYPES[_EXTRA_CODES.get(np.asarray(a).dtype.str.lstrip("<|"), 9)]).itemsize for a in extra.values())
-        items = [(10, 30, 3)] + ([(14, extra_size, 3)] if extra_size else [])
+        items = [(10, 30, 3)] + ([(11, 6, 3)] if coloured else []) + ([(14, extra_size, 3)] if extra_size else [])
         body = struct.pack("<HHBBHIIqqH", 3, 0, 3, 4, 3, 0, int(chunk_size), -1, -1, len(items)) + b"".join(struct.pack("<HHH", *it) for it in items)
         lvlr = struct.pack("<H16sHH32s", 0, b"laszip encoded", 22204, len(body), b"vapc_b200 LASzip-compatible") + body
-        header, vlr, rec = _build_las14(x, y, z, standard, extra, scales, offsets, 6, generating_software, more_vlrs=lvlr, n_more_vlrs=1, compressed=True)
+        header, vlr, rec = _build_las14(x, y, z, standard, extra, scales, offsets, 7 if coloured else 6, generating_software, more_vlrs=lvlr, n_more_vlrs=1,
+                                        compressed=True)
         stream = _laz_encode(rec, items, int(chunk_size), 375 + len(vlr))
         with open(path, "wb") as f:
             f.write(bytes(header))
