@@ -438,8 +438,8 @@ VAPC_API int vapc_selftest_mahalanobis_host(const double* cov6_host, const doubl
 /* ---- (f)1 LASzip decoding on the host (file I/O in front of the hot path; datahandler.py:72-73 gets it from
  * laspy[lazrs]).  Decodes npoints records of point_size bytes from a LAZ file image in host memory into
  * records_out_host.  compressor / chunk_size / items (nitems triples type, size, version) come from the
- * "laszip encoded" VLR (record id 22204).  Supported: compressor 2 (pointwise chunked) with POINT10 v2, RGB12 v2 and BYTE v2
- * items, i.e. LAS point formats 0 and 2 (+ extra bytes) — the layout of the reference's vapc_in.laz / small_mask.laz — and
+ * "laszip encoded" VLR (record id 22204).  Supported: compressor 2 (pointwise chunked) with POINT10 v2, GPSTIME11 v2, RGB12 v2 and BYTE v2
+ * items, i.e. LAS point formats 0 - 3 (+ extra bytes) — the layout of the reference's vapc_in.laz / small_mask.laz — and
  * compressor 3 (layered chunked) with POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3), i.e. LAS 1.4 point formats 6 / 7 (+ extra bytes) — the layout of its
  * tree_wind_condition.laz / als_multichannel_leg000_points.laz; anything else returns VAPC_E_INVALID with a message naming
  * the item.  A layered chunk whose layer decoders do not end exactly on their streams' last bytes is reported as corrupt. */
@@ -447,7 +447,7 @@ VAPC_API int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int64
                     int32_t point_size, int32_t compressor, uint32_t chunk_size, const uint16_t* items_host,
                     int32_t nitems, uint8_t* records_out_host);
 
-/* The mirror: npoints records -> LASzip stream with a fixed chunk_size; items POINT10 v2 / RGB12 v2 / BYTE v2 (compressor 2,
+/* The mirror: npoints records -> LASzip stream with a fixed chunk_size; items POINT10 v2 / GPSTIME11 v2 / RGB12 v2 / BYTE v2 (compressor 2,
  * pointwise chunked) or POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) (compressor 3, layered chunked: layers that never change inside a chunk are
  * omitted).  The stream starts with the 8-byte position of its chunk table, counted from the start of the file:
  * stream_offset_host = the header's offset to point data.  *out_bytes_host receives the stream length (also when out_cap is too

@@ -81,7 +81,8 @@ def test_encoder_reproduces_laszip_byte_for_byte(name):
 
 @pytest.mark.parametrize("n,chunk", [(0, 50000), (1, 50000), (2, 50000), (1000, 100), (1001, 100), (120_001, 50000)])
 @pytest.mark.parametrize("rgb", [False, True])
-def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb):
+@pytest.mark.parametrize("gps", [False, True])
+def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb, gps):
     """write_laz -> read_las on synthetic clouds (runs anywhere): single points, exact chunk multiples, several chunks, with and
     without colours, extra bytes of four types; constant and incompressible columns."""
     rng = np.random.default_rng(n + chunk + rgb)
@@ -91,16 +92,22 @@ def test_laz_write_read_roundtrip(tmp_path, n, chunk, rgb):
                withheld=rng.integers(0, 2, n), scan_angle_rank=rng.integers(-90, 91, n), user_data=np.full(n, 7), point_source_id=rng.integers(0, 65536, n))
     if rgb:
         std.update(red=rng.integers(0, 65536, n), green=rng.integers(0, 256, n) * 256, blue=np.zeros(n, np.int64))
+    if gps:  # GPSTIME11 v2: regular pulses, repeated times, multiples, backward steps, jumps to other sequences
+        t = 3e5 + np.cumsum(rng.choice([0.0, 1e-5, 1e-5, 1e-5, 3e-5, 7e-4, -2e-5], n))
+        std["gps_time"] = np.where(rng.random(n) < 0.01, rng.random(n) * 1e9, t)
     extra = dict(point_count=rng.integers(1, 60, n).astype(np.float32), noise=rng.random(n), small=rng.integers(-100, 100, n).astype(np.int16),
                  big=rng.integers(0, 2 ** 62, n).astype(np.int64))
     path = str(tmp_path / "t.laz")
     las.write_laz(path, x, y, z, std, extra, scales=[0.001] * 3, offsets=[0.0, 0.0, 0.0], chunk_size=chunk, las14=False)
     h, c = las.read_las(path)
-    assert h.compressed and h.version == (1, 2) and h.point_format == (2 if rgb else 0) and h.point_count == n and h.laszip["chunk_size"] == chunk
+    assert h.compressed and h.version == (1, 2) and h.point_format == (2 if rgb else 0) + (1 if gps else 0) and h.point_count == n and h.laszip["chunk_size"] == chunk
     for k, v in (("x", x), ("y", y), ("z", z)):
         assert n == 0 or np.abs(c[k] - v).max() < 1e-9
     for k, v in std.items():
-        np.testing.assert_array_equal(np.asarray(c[k]).astype(np.int64), np.asarray(v).astype(np.int64), err_msg=k)
+        if k == "gps_time":
+            np.testing.assert_array_equal(c[k], v)
+        else:
+            np.testing.assert_array_equal(np.asarray(c[k]).astype(np.int64), np.asarray(v).astype(np.int64), err_msg=k)
     for k, v in extra.items():
         np.testing.assert_array_equal(c[k], v, err_msg=k)
 

@@ -1605,13 +1605,212 @@ int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_po
   return VAPC_OK;
 }
 
+
+// GPSTIME11 version 2 (LAS point formats 1 / 3): the GPS time coder of the layered format (pinned byte for byte by the LAS 1.4
+// fixtures) with the two extra "unchanged" symbols version 2 needs, there being no separate change flag.  No fixture of the
+// reference holds this item: round-trip tested, and guarded by the end-of-chunk check of the pointwise decoder.
+constexpr int kGps2Unchanged = kGpsMulti - kGpsMultiMinus + 1, kGps2CodeFull = kGpsMulti - kGpsMultiMinus + 2, kGps2Total = kGpsMulti - kGpsMultiMinus + 6;
+struct GpsState {
+  uint32_t last = 0, next = 0;
+  uint64_t time[4];
+  int32_t diff[4], extreme[4];
+  void init(const uint8_t* first) {
+    last = next = 0;
+    for (int i = 0; i < 4; ++i) { time[i] = 0; diff[i] = 0; extreme[i] = 0; }
+    memcpy(&time[0], first, 8);
+  }
+  void bump(int32_t d) {
+    if (++extreme[last] > 3) { diff[last] = d; extreme[last] = 0; }
+  }
+};
+struct GpsTime11V2 : ItemReader {
+  ArithmeticDecoder* dec;
+  GpsState g;
+  SymbolModel multi_model{(uint32_t)kGps2Total}, zero_model{6};
+  IntegerDecompressor ic;
+  explicit GpsTime11V2(ArithmeticDecoder* d) : dec(d), ic(d, 32, 9) {}
+  void init(const uint8_t* first) override {
+    g.init(first);
+    multi_model.init();
+    zero_model.init();
+    ic.init();
+  }
+  void new_sequence() {
+    g.next = (g.next + 1) & 3;
+    uint64_t v = (uint64_t)(uint32_t)ic.decompress((int32_t)(g.time[g.last] >> 32), 8);
+    v = (v << 32) | dec->read_bits(32);
+    g.time[g.next] = v;
+    g.last = g.next;
+    g.diff[g.last] = 0;
+    g.extreme[g.last] = 0;
+  }
+  void step() {
+    if (g.diff[g.last] == 0) {
+      const int multi = (int)dec->symbol(zero_model);
+      if (multi == 1) {
+        g.diff[g.last] = ic.decompress(0, 0);
+        g.time[g.last] += (uint64_t)(int64_t)g.diff[g.last];
+        g.extreme[g.last] = 0;
+      } else if (multi == 2) {
+        new_sequence();
+      } else if (multi > 2) {
+        g.last = (g.last + (uint32_t)multi - 2) & 3;
+        step();
+      }  // 0: unchanged
+    } else {
+      int multi = (int)dec->symbol(multi_model);
+      const int32_t ld = g.diff[g.last];
+      if (multi == 1) {
+        g.time[g.last] += (uint64_t)(int64_t)ic.decompress(ld, 1);
+        g.extreme[g.last] = 0;
+      } else if (multi < kGps2Unchanged) {
+        int32_t d;
+        if (multi == 0) {
+          d = ic.decompress(0, 7);
+          g.bump(d);
+        } else if (multi < kGpsMulti) {
+          d = ic.decompress((int32_t)((uint32_t)multi * (uint32_t)ld), multi < 10 ? 2 : 3);
+        } else if (multi == kGpsMulti) {
+          d = ic.decompress((int32_t)((uint32_t)kGpsMulti * (uint32_t)ld), 4);
+          g.bump(d);
+        } else {
+          multi = kGpsMulti - multi;
+          if (multi > kGpsMultiMinus) {
+            d = ic.decompress((int32_t)((uint32_t)multi * (uint32_t)ld), 5);
+          } else {
+            d = ic.decompress((int32_t)((uint32_t)kGpsMultiMinus * (uint32_t)ld), 6);
+            g.bump(d);
+          }
+        }
+        g.time[g.last] += (uint64_t)(int64_t)d;
+      } else if (multi == kGps2CodeFull) {
+        new_sequence();
+      } else if (multi > kGps2CodeFull) {
+        g.last = (g.last + (uint32_t)multi - (uint32_t)kGps2CodeFull) & 3;
+        step();
+      }  // kGps2Unchanged: unchanged
+    }
+  }
+  void read(uint8_t* out) override {
+    step();
+    memcpy(out, &g.time[g.last], 8);
+  }
+};
+struct GpsTime11V2Writer : ItemWriter {
+  ArithmeticEncoder* enc;
+  GpsState g;
+  SymbolModel multi_model{(uint32_t)kGps2Total}, zero_model{6};
+  IntegerCompressor ic;
+  explicit GpsTime11V2Writer(ArithmeticEncoder* e) : enc(e), ic(e, 32, 9) {}
+  void init(const uint8_t* first) override {
+    g.init(first);
+    multi_model.init();
+    zero_model.init();
+    ic.init();
+  }
+  void new_sequence(uint64_t t) {
+    ic.compress((int32_t)(g.time[g.last] >> 32), (int32_t)(t >> 32), 8);
+    enc->write_bits(32, (uint32_t)t);
+    g.next = (g.next + 1) & 3;
+    g.last = g.next;
+    g.diff[g.last] = 0;
+    g.extreme[g.last] = 0;
+  }
+  void write(const uint8_t* item) override {
+    uint64_t t;
+    memcpy(&t, item, 8);
+    step(t);
+  }
+  void step(uint64_t t) {
+    if (g.diff[g.last] == 0) {
+      if (t == g.time[g.last]) {
+        enc->symbol(zero_model, 0);  // unchanged
+        return;
+      }
+      const int64_t d64 = (int64_t)(t - g.time[g.last]);
+      const int32_t d32 = (int32_t)d64;
+      if (d64 == (int64_t)d32) {
+        enc->symbol(zero_model, 1);
+        ic.compress(0, d32, 0);
+        g.diff[g.last] = d32;
+        g.extreme[g.last] = 0;
+      } else {
+        for (uint32_t i = 1; i < 4; ++i) {
+          const int64_t o64 = (int64_t)(t - g.time[(g.last + i) & 3]);
+          if (o64 == (int64_t)(int32_t)o64) {
+            enc->symbol(zero_model, i + 2);
+            g.last = (g.last + i) & 3;
+            step(t);
+            return;
+          }
+        }
+        enc->symbol(zero_model, 2);
+        new_sequence(t);
+      }
+      g.time[g.last] = t;
+    } else {
+      if (t == g.time[g.last]) {
+        enc->symbol(multi_model, kGps2Unchanged);
+        return;
+      }
+      const int64_t d64 = (int64_t)(t - g.time[g.last]);
+      const int32_t d32 = (int32_t)d64;
+      if (d64 == (int64_t)d32) {
+        const int32_t ld = g.diff[g.last];
+        const int32_t multi = Point14V3Writer::quantize((float)d32 / (float)ld);
+        if (multi == 1) {
+          enc->symbol(multi_model, 1);
+          ic.compress(ld, d32, 1);
+          g.extreme[g.last] = 0;
+        } else if (multi > 0) {
+          if (multi < kGpsMulti) {
+            enc->symbol(multi_model, (uint32_t)multi);
+            ic.compress((int32_t)((uint32_t)multi * (uint32_t)ld), d32, multi < 10 ? 2 : 3);
+          } else {
+            enc->symbol(multi_model, kGpsMulti);
+            ic.compress((int32_t)((uint32_t)kGpsMulti * (uint32_t)ld), d32, 4);
+            g.bump(d32);
+          }
+        } else if (multi < 0) {
+          if (multi > kGpsMultiMinus) {
+            enc->symbol(multi_model, (uint32_t)(kGpsMulti - multi));
+            ic.compress((int32_t)((uint32_t)multi * (uint32_t)ld), d32, 5);
+          } else {
+            enc->symbol(multi_model, (uint32_t)(kGpsMulti - kGpsMultiMinus));
+            ic.compress((int32_t)((uint32_t)kGpsMultiMinus * (uint32_t)ld), d32, 6);
+            g.bump(d32);
+          }
+        } else {
+          enc->symbol(multi_model, 0);
+          ic.compress(0, d32, 7);
+          g.bump(d32);
+        }
+      } else {
+        for (uint32_t i = 1; i < 4; ++i) {
+          const int64_t o64 = (int64_t)(t - g.time[(g.last + i) & 3]);
+          if (o64 == (int64_t)(int32_t)o64) {
+            enc->symbol(multi_model, (uint32_t)kGps2CodeFull + i);
+            g.last = (g.last + i) & 3;
+            step(t);
+            return;
+          }
+        }
+        enc->symbol(multi_model, kGps2CodeFull);
+        new_sequence(t);
+      }
+      g.time[g.last] = t;
+    }
+  }
+};
+
 int check_items(const char* who, const uint16_t* items, int nitems, int point_size) {
   int total = 0;
   for (int i = 0; i < nitems; ++i) {
     const int type = items[3 * i], size = items[3 * i + 1], version = items[3 * i + 2];
-    const bool ok = (type == 6 && size == 20 && version == 2) || (type == 8 && size == 6 && version == 2) || (type == 0 && size > 0 && version == 2);
+    const bool ok = (type == 6 && size == 20 && version == 2) || (type == 7 && size == 8 && version == 2) || (type == 8 && size == 6 && version == 2) ||
+                    (type == 0 && size > 0 && version == 2);
     if (!ok)
-      return vapc_set_error(VAPC_E_INVALID, "%s: LASzip item type %d (size %d, version %d) is not supported (POINT10 v2, RGB12 v2 and BYTE v2 are)", who, type,
+      return vapc_set_error(VAPC_E_INVALID, "%s: LASzip item type %d (size %d, version %d) is not supported (POINT10 v2, GPSTIME11 v2, RGB12 v2 and BYTE v2 are)", who, type,
                             size, version);
     total += size;
   }
@@ -1662,6 +1861,7 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
   std::vector<int> sizes;
   for (int i = 0; i < nitems; ++i) {
     if (items_host[3 * i] == 6) readers.emplace_back(new Point10V2(&dec));
+    else if (items_host[3 * i] == 7) readers.emplace_back(new GpsTime11V2(&dec));
     else if (items_host[3 * i] == 8) readers.emplace_back(new Rgb12V2(&dec));
     else readers.emplace_back(new ByteV2(&dec, items_host[3 * i + 1]));
     sizes.push_back(items_host[3 * i + 1]);
@@ -1670,7 +1870,8 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
     const int64_t begin = chunk_start[(size_t)c];
-    const int64_t limit = nchunks > 1 && c + 1 < nchunks ? chunk_start[(size_t)c + 1] : file_bytes;
+    const bool has_table = table_pos >= chunk_start[0] && table_pos + 8 <= file_bytes;
+    const int64_t limit = nchunks > 1 && c + 1 < nchunks ? chunk_start[(size_t)c + 1] : (has_table ? table_pos : file_bytes);
     if (begin + point_size > file_bytes || limit > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld outside the file", (long long)c);
     uint8_t* out = records_out_host + first * point_size;
     memcpy(out, file_host + begin, (size_t)point_size);  // the first point of a chunk is stored raw
@@ -1690,7 +1891,9 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
           off += sizes[i];
         }
       }
-      if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld is truncated or corrupt", (long long)c);
+      // a correct decode ends on the last byte of the chunk (the chunk table marks the end of the last one)
+      if (br.overrun || ((nchunks > 1 || has_table) && br.p != br.end))
+        return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld is truncated or corrupt", (long long)c);
     }
   }
   return VAPC_OK;
@@ -1727,6 +1930,7 @@ extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int
   std::vector<int> sizes;
   for (int i = 0; i < nitems; ++i) {
     if (items_host[3 * i] == 6) writers.emplace_back(new Point10V2Writer(&enc));
+    else if (items_host[3 * i] == 7) writers.emplace_back(new GpsTime11V2Writer(&enc));
     else if (items_host[3 * i] == 8) writers.emplace_back(new Rgb12V2Writer(&enc));
     else writers.emplace_back(new ByteV2Writer(&enc, items_host[3 * i + 1]));
     sizes.push_back(items_host[3 * i + 1]);

@@ -11,10 +11,10 @@ needs from it for plain `.las` files and mirrors laspy's conventions:
   dimensions as float32 (`datahandler.py:99-165`).
 
 LAZ: the library's own LASzip codec (vapc_b200/csrc/laz.cu, host entry points `vapc_laz_decode` / `vapc_laz_encode`) reads
-all four fixtures of the reference — "pointwise chunked" POINT10 v2 (+ RGB12 v2, + BYTE v2 extra bytes): point formats 0 and 2
-(`vapc_in.laz`, `small_mask.laz`), and the "layered chunked" POINT14 v3 (+ RGB14 v3, + BYTE14 v3) of LAS 1.4 point formats 6 / 7
+all four fixtures of the reference — "pointwise chunked" POINT10 v2 (+ GPSTIME11 v2, + RGB12 v2, + BYTE v2 extra bytes): point formats 0 - 3
+(`vapc_in.laz`, `small_mask.laz` are format 2), and the "layered chunked" POINT14 v3 (+ RGB14 v3, + BYTE14 v3) of LAS 1.4 point formats 6 / 7
 (`tree_wind_condition.laz`, `als_multichannel_leg000_points.laz`) — and writes `.laz` as LAS 1.4 point format 6 / 7 + extra bytes
-(`write_laz`).  Other items (GPSTIME11, RGBNIR14, wave packets) raise NotImplementedError naming the item; `laspy` with a LAZ
+(`write_laz`).  Other items (RGBNIR14, wave packets, version-1 items) raise NotImplementedError naming the item; `laspy` with a LAZ
 backend reads them when it is installed.
 """
 from __future__ import annotations
@@ -308,9 +308,8 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     """LASzip-compressed output through the library's own encoder (vapc_laz_encode).
     las14 (default): LAS 1.4 point format 6 (7 with colours: the reference's own output format, datahandler.py:99-165) + extra
     bytes, "layered chunked" compression of the items POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) — the layout of the reference's LAS 1.4
-    fixtures (RGB14 is round-trip tested only: no fixture holds colours in LAS 1.4).  las14=False: LAS 1.2, point format 2 when red /
-    green / blue are given, else 0, every other dimension as extra bytes, "pointwise chunked" compression of POINT10 v2 (+ RGB12 v2)
-    (+ BYTE v2) — the layout of the reference's vapc_in.laz; values that do not fit the legacy fields (return numbers above 7,
+    fixtures (RGB14 is round-trip tested only: no fixture holds colours in LAS 1.4).  las14=False: LAS 1.2, point format 0 - 3 (GPS time and / or colours),
+    every other dimension as extra bytes, "pointwise chunked" compression of POINT10 v2 (+ GPSTIME11 v2) (+ RGB12 v2) (+ BYTE v2) — the layout of the reference's vapc_in.laz; values that do not fit the legacy fields (return numbers above 7,
     classes above 31) are masked as in any point-format-0 file.  The encoder reproduces the point data of all four fixtures byte
     for byte (tests/test_laz.py)."""
     import ctypes as C
@@ -339,7 +338,7 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     if offsets is None:
         offsets = np.array([x.min(), y.min(), z.min()]) if n else np.zeros(3)
     offsets = np.asarray(offsets, np.float64)
-    point_format = 2 if coloured else 0
+    point_format = (2 if coloured else 0) + (1 if "gps_time" in standard else 0)  # 0, 1 (GPS time), 2 (colours), 3 (both)
     fields = list(POINT_FORMATS[point_format])
     core_size = np.dtype(fields).itemsize
     known = set(dimension_names(point_format))
@@ -373,7 +372,8 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
                 rec[name] = arr.astype(dt[name])
     for (name, arr, _), field in zip(extra_fields, dt.names[len(POINT_FORMATS[point_format]):]):
         rec[field] = arr
-    items = [(6, 20, 2)] + ([(8, 6, 2)] if point_format == 2 else []) + ([(0, dt.itemsize - core_size, 2)] if dt.itemsize > core_size else [])
+    items = ([(6, 20, 2)] + ([(7, 8, 2)] if point_format in (1, 3) else []) + ([(8, 6, 2)] if point_format in (2, 3) else [])
+             + ([(0, dt.itemsize - core_size, 2)] if dt.itemsize > core_size else []))
     # VLRs: laszip description, extra-bytes description
     body = struct.pack("<HHBBHIIqqH", 2, 0, 3, 4, 3, 0, int(chunk_size), -1, -1, len(items)) + b"".join(struct.pack("<HHH", *it) for it in items)
     vlrs = struct.pack("<H16sHH32s", 0, b"laszip encoded", 22204, len(body), b"vapc_b200 LASzip-compatible") + body
