@@ -9,14 +9,61 @@
 // LAS 1.4: the layered POINT14 v3 + BYTE14 v3 items (compressor 3) of the reference's other two fixtures are decoded as well
 // (second half of this file).  Other items (GPSTIME11, WAVEPACKET13, RGB14, ...) are reported as unsupported.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
 
 namespace {
+// Chunks are independent streams: decode / encode them on the host's cores.  make() builds one set of coder objects per thread,
+// body(chunk, state) returns a status whose message lives in the worker's thread-local slot; the first failure wins and is
+// re-raised in the caller's thread.  VAPC_LAZ_THREADS overrides the thread count.
+template <typename Make, typename Body>
+int parallel_chunks(int64_t nchunks, Make make, Body body) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char* env = getenv("VAPC_LAZ_THREADS")) hw = (unsigned)atoi(env);
+  if (hw < 1) hw = 1;
+  const int64_t nthreads = std::min<int64_t>(std::min<int64_t>(hw, 32), nchunks);
+  std::atomic<int64_t> next{0};
+  std::atomic<int> failed{0};
+  std::mutex mu;
+  std::string msg;
+  int code = VAPC_OK;
+  auto worker = [&]() {
+    auto st = make();
+    for (;;) {
+      const int64_t c = next.fetch_add(1);
+      if (c >= nchunks || failed.load()) break;
+      const int rc = body(c, *st);
+      if (rc != VAPC_OK) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed.load()) {
+          code = rc;
+          msg = vapc_last_error();
+          failed.store(1);
+        }
+        break;
+      }
+    }
+  };
+  if (nthreads <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (int64_t t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+  }
+  if (failed.load()) return vapc_set_error(code, "%s", msg.c_str());
+  return VAPC_OK;
+}
+
 // ---- byte source --------------------------------------------------------------------------------------------
 struct ByteReader {
   const uint8_t* p;
@@ -1462,18 +1509,31 @@ void write_chunk_table(std::vector<uint8_t>& out, const std::vector<uint32_t>& c
   enc.done();
 }
 
-void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size, uint32_t chunk_size, int rgb, int extra, std::vector<uint8_t>& out,
-                    std::vector<uint32_t>& chunk_bytes) {
-  std::unique_ptr<Point14V3Writer> p14(new Point14V3Writer());
-  std::unique_ptr<Rgb14V3Writer> c14(rgb ? new Rgb14V3Writer() : nullptr);
-  std::unique_ptr<Byte14V3Writer> b14(extra ? new Byte14V3Writer(extra) : nullptr);
+int encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size, uint32_t chunk_size, int rgb, int extra, std::vector<uint8_t>& out,
+                   std::vector<uint32_t>& chunk_bytes) {
+  struct State {
+    std::unique_ptr<Point14V3Writer> p14;
+    std::unique_ptr<Rgb14V3Writer> c14;
+    std::unique_ptr<Byte14V3Writer> b14;
+  };
+  auto make = [&]() {
+    std::unique_ptr<State> st(new State());
+    st->p14.reset(new Point14V3Writer());
+    if (rgb) st->c14.reset(new Rgb14V3Writer());
+    if (extra) st->b14.reset(new Byte14V3Writer(extra));
+    return st;
+  };
   const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
-  for (int64_t c = 0; c < nchunks; ++c) {
+  std::vector<std::vector<uint8_t>> parts((size_t)nchunks);
+  auto one_chunk = [&](int64_t c, State& st) -> int {
+    Point14V3Writer* p14 = st.p14.get();
+    Rgb14V3Writer* c14 = st.c14.get();
+    Byte14V3Writer* b14 = st.b14.get();
+    std::vector<uint8_t>& o = parts[(size_t)c];
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
     const uint8_t* rec = records + first * point_size;
-    const size_t begin = out.size();
-    out.insert(out.end(), rec, rec + point_size);
+    o.insert(o.end(), rec, rec + point_size);
     const uint32_t context = p14->begin_chunk(rec);
     if (c14) c14->begin_chunk(rec + 30, context);
     if (b14) b14->begin_chunk(rec + 30 + rgb, context);
@@ -1486,33 +1546,29 @@ void encode_layered(const uint8_t* records, int64_t npoints, int32_t point_size,
     p14->end_chunk();
     if (c14) c14->end_chunk();
     if (b14) b14->end_chunk();
-    const uint32_t cnt = (uint32_t)count;
-    const uint8_t* cp = reinterpret_cast<const uint8_t*>(&cnt);
-    out.insert(out.end(), cp, cp + 4);
-    for (int l = 0; l < kLayers14; ++l) {
-      const uint32_t nb = p14->layer_bytes(l);
-      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
-      out.insert(out.end(), q, q + 4);
-    }
-    if (c14) {
-      const uint32_t nb = c14->layer_bytes();
-      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
-      out.insert(out.end(), q, q + 4);
-    }
-    for (int i = 0; i < extra; ++i) {
-      const uint32_t nb = b14->layer_bytes(i);
-      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nb);
-      out.insert(out.end(), q, q + 4);
-    }
+    auto put32 = [&](uint32_t v) {
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&v);
+      o.insert(o.end(), q, q + 4);
+    };
+    put32((uint32_t)count);
+    for (int l = 0; l < kLayers14; ++l) put32(p14->layer_bytes(l));
+    if (c14) put32(c14->layer_bytes());
+    for (int i = 0; i < extra; ++i) put32(b14->layer_bytes(i));
     for (int l = 0; l < kLayers14; ++l)
-      if (p14->layer_bytes(l)) out.insert(out.end(), p14->buf[l].begin(), p14->buf[l].end());
-    if (c14 && c14->layer_bytes()) out.insert(out.end(), c14->buf.begin(), c14->buf.end());
+      if (p14->layer_bytes(l)) o.insert(o.end(), p14->buf[l].begin(), p14->buf[l].end());
+    if (c14 && c14->layer_bytes()) o.insert(o.end(), c14->buf.begin(), c14->buf.end());
     for (int i = 0; i < extra; ++i)
-      if (b14->layer_bytes(i)) out.insert(out.end(), b14->buf[(size_t)i].begin(), b14->buf[(size_t)i].end());
-    chunk_bytes.push_back((uint32_t)(out.size() - begin));
+      if (b14->layer_bytes(i)) o.insert(o.end(), b14->buf[(size_t)i].begin(), b14->buf[(size_t)i].end());
+    return VAPC_OK;
+  };
+  if (const int rc = parallel_chunks(nchunks, make, one_chunk)) return rc;
+  for (auto& part : parts) {
+    out.insert(out.end(), part.begin(), part.end());
+    chunk_bytes.push_back((uint32_t)part.size());
+    std::vector<uint8_t>().swap(part);
   }
+  return VAPC_OK;
 }
-
 
 // chunk start positions from the chunk table (both compressors write the same table)
 int read_chunk_table(const char* who, const uint8_t* file, int64_t file_bytes, int64_t offset_to_points, int64_t nchunks, std::vector<int64_t>& chunk_start) {
@@ -1567,10 +1623,22 @@ int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_po
   const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
   std::vector<int64_t> chunk_start;
   if (const int rc = read_chunk_table(who, file, file_bytes, offset_to_points, nchunks, chunk_start)) return rc;
-  std::unique_ptr<Point14V3> p14(new Point14V3());
-  std::unique_ptr<Rgb14V3> c14(rgb ? new Rgb14V3() : nullptr);
-  std::unique_ptr<Byte14V3> b14(extra ? new Byte14V3(extra) : nullptr);
-  for (int64_t c = 0; c < nchunks; ++c) {
+  struct State {
+    std::unique_ptr<Point14V3> p14;
+    std::unique_ptr<Rgb14V3> c14;
+    std::unique_ptr<Byte14V3> b14;
+  };
+  auto make = [&]() {
+    std::unique_ptr<State> st(new State());
+    st->p14.reset(new Point14V3());
+    if (rgb) st->c14.reset(new Rgb14V3());
+    if (extra) st->b14.reset(new Byte14V3(extra));
+    return st;
+  };
+  auto one_chunk = [&](int64_t c, State& st) -> int {
+    Point14V3* p14 = st.p14.get();
+    Rgb14V3* c14 = st.c14.get();
+    Byte14V3* b14 = st.b14.get();
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
     const int64_t begin = chunk_start[(size_t)c], limit = chunk_start[(size_t)c + 1];
@@ -1601,8 +1669,9 @@ int decode_layered(const uint8_t* file, int64_t file_bytes, int64_t offset_to_po
       for (int i = 0; i < b14->number && exact; ++i) exact = !b14->changed[(size_t)i] || b14->br[(size_t)i].p == b14->br[(size_t)i].end;
     }
     if (!exact) return vapc_set_error(VAPC_E_INVALID, "%s: chunk %lld is truncated or corrupt (a layer's decoder did not end with its stream)", who, (long long)c);
-  }
-  return VAPC_OK;
+    return VAPC_OK;
+  };
+  return parallel_chunks(nchunks, make, one_chunk);
 }
 
 
@@ -1803,6 +1872,7 @@ struct GpsTime11V2Writer : ItemWriter {
   }
 };
 
+
 int check_items(const char* who, const uint16_t* items, int nitems, int point_size) {
   int total = 0;
   for (int i = 0; i < nitems; ++i) {
@@ -1856,38 +1926,44 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
     }
     if (br.overrun) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk table truncated");
   }
-  ArithmeticDecoder dec;
-  std::vector<std::unique_ptr<ItemReader>> readers;
+  struct State {
+    ArithmeticDecoder dec;
+    std::vector<std::unique_ptr<ItemReader>> readers;
+  };
   std::vector<int> sizes;
-  for (int i = 0; i < nitems; ++i) {
-    if (items_host[3 * i] == 6) readers.emplace_back(new Point10V2(&dec));
-    else if (items_host[3 * i] == 7) readers.emplace_back(new GpsTime11V2(&dec));
-    else if (items_host[3 * i] == 8) readers.emplace_back(new Rgb12V2(&dec));
-    else readers.emplace_back(new ByteV2(&dec, items_host[3 * i + 1]));
-    sizes.push_back(items_host[3 * i + 1]);
-  }
-  for (int64_t c = 0; c < nchunks; ++c) {
+  for (int i = 0; i < nitems; ++i) sizes.push_back(items_host[3 * i + 1]);
+  auto make = [&]() {
+    std::unique_ptr<State> st(new State());
+    for (int i = 0; i < nitems; ++i) {
+      if (items_host[3 * i] == 6) st->readers.emplace_back(new Point10V2(&st->dec));
+      else if (items_host[3 * i] == 7) st->readers.emplace_back(new GpsTime11V2(&st->dec));
+      else if (items_host[3 * i] == 8) st->readers.emplace_back(new Rgb12V2(&st->dec));
+      else st->readers.emplace_back(new ByteV2(&st->dec, items_host[3 * i + 1]));
+    }
+    return st;
+  };
+  const bool has_table = table_pos >= chunk_start[0] && table_pos + 8 <= file_bytes;
+  auto one_chunk = [&](int64_t c, State& st) -> int {
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
     const int64_t begin = chunk_start[(size_t)c];
-    const bool has_table = table_pos >= chunk_start[0] && table_pos + 8 <= file_bytes;
     const int64_t limit = nchunks > 1 && c + 1 < nchunks ? chunk_start[(size_t)c + 1] : (has_table ? table_pos : file_bytes);
     if (begin + point_size > file_bytes || limit > file_bytes) return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld outside the file", (long long)c);
     uint8_t* out = records_out_host + first * point_size;
     memcpy(out, file_host + begin, (size_t)point_size);  // the first point of a chunk is stored raw
     int off = 0;
-    for (size_t i = 0; i < readers.size(); ++i) {
-      readers[i]->init(out + off);
+    for (size_t i = 0; i < st.readers.size(); ++i) {
+      st.readers[i]->init(out + off);
       off += sizes[i];
     }
     if (count > 1) {
       ByteReader br{file_host + begin + point_size, file_host + limit};
-      dec.init(&br);
+      st.dec.init(&br);
       for (int64_t p = 1; p < count; ++p) {
         uint8_t* rec = out + p * point_size;
         off = 0;
-        for (size_t i = 0; i < readers.size(); ++i) {
-          readers[i]->read(rec + off);
+        for (size_t i = 0; i < st.readers.size(); ++i) {
+          st.readers[i]->read(rec + off);
           off += sizes[i];
         }
       }
@@ -1895,8 +1971,9 @@ extern "C" int vapc_laz_decode(const uint8_t* file_host, int64_t file_bytes, int
       if (br.overrun || ((nchunks > 1 || has_table) && br.p != br.end))
         return vapc_set_error(VAPC_E_INVALID, "vapc_laz_decode: chunk %lld is truncated or corrupt", (long long)c);
     }
-  }
-  return VAPC_OK;
+    return VAPC_OK;
+  };
+  return parallel_chunks(nchunks, make, one_chunk);
 }
 
 // Encode `npoints` records into a LASzip "pointwise chunked" stream (compressor 2): [int64 position of the chunk table,
@@ -1914,7 +1991,7 @@ extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int
     if (const int rc = layered_items("vapc_laz_encode", items_host, nitems, point_size, &rgb, &extra)) return rc;
     std::vector<uint8_t> lay(8, 0);
     std::vector<uint32_t> sizes;
-    encode_layered(records_host, npoints, point_size, chunk_size, rgb, extra, lay, sizes);
+    if (const int rc = encode_layered(records_host, npoints, point_size, chunk_size, rgb, extra, lay, sizes)) return rc;
     const int64_t tpos = stream_offset_host + (int64_t)lay.size();
     memcpy(lay.data(), &tpos, 8);
     write_chunk_table(lay, sizes);
@@ -1925,60 +2002,57 @@ extern "C" int vapc_laz_encode(const uint8_t* records_host, int64_t npoints, int
   }
   if (const int rc = check_items("vapc_laz_encode", items_host, nitems, point_size)) return rc;
   std::vector<uint8_t> out(8, 0);
-  ArithmeticEncoder enc;
-  std::vector<std::unique_ptr<ItemWriter>> writers;
+  struct State {
+    ArithmeticEncoder enc;
+    std::vector<std::unique_ptr<ItemWriter>> writers;
+  };
   std::vector<int> sizes;
-  for (int i = 0; i < nitems; ++i) {
-    if (items_host[3 * i] == 6) writers.emplace_back(new Point10V2Writer(&enc));
-    else if (items_host[3 * i] == 7) writers.emplace_back(new GpsTime11V2Writer(&enc));
-    else if (items_host[3 * i] == 8) writers.emplace_back(new Rgb12V2Writer(&enc));
-    else writers.emplace_back(new ByteV2Writer(&enc, items_host[3 * i + 1]));
-    sizes.push_back(items_host[3 * i + 1]);
-  }
+  for (int i = 0; i < nitems; ++i) sizes.push_back(items_host[3 * i + 1]);
+  auto make = [&]() {
+    std::unique_ptr<State> st(new State());
+    for (int i = 0; i < nitems; ++i) {
+      if (items_host[3 * i] == 6) st->writers.emplace_back(new Point10V2Writer(&st->enc));
+      else if (items_host[3 * i] == 7) st->writers.emplace_back(new GpsTime11V2Writer(&st->enc));
+      else if (items_host[3 * i] == 8) st->writers.emplace_back(new Rgb12V2Writer(&st->enc));
+      else st->writers.emplace_back(new ByteV2Writer(&st->enc, items_host[3 * i + 1]));
+    }
+    return st;
+  };
   const int64_t nchunks = (npoints + chunk_size - 1) / chunk_size;
-  std::vector<uint32_t> chunk_bytes;
-  for (int64_t c = 0; c < nchunks; ++c) {
+  std::vector<std::vector<uint8_t>> parts((size_t)nchunks);
+  auto one_chunk = [&](int64_t c, State& st) -> int {
+    std::vector<uint8_t>& o = parts[(size_t)c];
     const int64_t first = c * (int64_t)chunk_size;
     const int64_t count = std::min<int64_t>(chunk_size, npoints - first);
-    const size_t begin = out.size();
     const uint8_t* rec = records_host + first * point_size;
-    out.insert(out.end(), rec, rec + point_size);  // the first point of a chunk is stored raw
+    o.insert(o.end(), rec, rec + point_size);  // the first point of a chunk is stored raw
     int off = 0;
-    for (size_t i = 0; i < writers.size(); ++i) {
-      writers[i]->init(rec + off);
+    for (size_t i = 0; i < st.writers.size(); ++i) {
+      st.writers[i]->init(rec + off);
       off += sizes[i];
     }
-    enc.init(&out);
+    st.enc.init(&o);
     for (int64_t p = 1; p < count; ++p) {
       const uint8_t* r = rec + p * point_size;
       off = 0;
-      for (size_t i = 0; i < writers.size(); ++i) {
-        writers[i]->write(r + off);
+      for (size_t i = 0; i < st.writers.size(); ++i) {
+        st.writers[i]->write(r + off);
         off += sizes[i];
       }
     }
-    enc.done();
-    chunk_bytes.push_back((uint32_t)(out.size() - begin));
+    st.enc.done();
+    return VAPC_OK;
+  };
+  if (const int rc = parallel_chunks(nchunks, make, one_chunk)) return rc;
+  std::vector<uint32_t> chunk_bytes;
+  for (auto& part : parts) {
+    out.insert(out.end(), part.begin(), part.end());
+    chunk_bytes.push_back((uint32_t)part.size());
+    std::vector<uint8_t>().swap(part);
   }
   const int64_t table_pos = stream_offset_host + (int64_t)out.size();
   memcpy(out.data(), &table_pos, 8);
-  {
-    const uint32_t version = 0, count = (uint32_t)nchunks;
-    const uint8_t* v = reinterpret_cast<const uint8_t*>(&version);
-    const uint8_t* n = reinterpret_cast<const uint8_t*>(&count);
-    out.insert(out.end(), v, v + 4);
-    out.insert(out.end(), n, n + 4);
-    if (nchunks > 0) {
-      enc.init(&out);
-      IntegerCompressor ic(&enc, 32, 2);
-      int32_t prev = 0;
-      for (int64_t i = 0; i < nchunks; ++i) {
-        ic.compress(prev, (int32_t)chunk_bytes[(size_t)i], 1);
-        prev = (int32_t)chunk_bytes[(size_t)i];
-      }
-      enc.done();
-    }
-  }
+  write_chunk_table(out, chunk_bytes);
   *out_bytes_host = (int64_t)out.size();
   if (!out_host || out_cap < (int64_t)out.size()) return vapc_set_error(VAPC_E_WORKSPACE, "vapc_laz_encode: output buffer too small (%lld bytes needed)", (long long)out.size());
   memcpy(out_host, out.data(), out.size());
