@@ -1,14 +1,14 @@
-// LASzip decoder for the point layout of the reference's fixtures (tests/test_data/vapc_in.laz, small_mask.laz):
-// "pointwise chunked" compression (compressor 2) of POINT10 (version 2) + RGB12 (version 2) items, i.e. LAS point
-// format 2 written by LASzip 2.x / 3.x without layering.  Host code (file decoding sits in front of the hot path,
-// SURVEY.md section 8(f) row 1): the reference gets this from laspy[lazrs] (src/vapc/datahandler.py:72-73), which is
-// not installable offline.  Written from the published LASzip format description (Isenburg, "LASzip: lossless
-// compression of LiDAR data", PE&RS 2013) — an adaptive arithmetic coder (Said's FastAC scheme), integer
-// "corrector" coders with k-bit contexts, and the per-item predictors of version 2.
-//
-// LAS 1.4: the layered POINT14 v3 + BYTE14 v3 items (compressor 3) of the reference's other two fixtures are decoded as well
-// (second half of this file).  Other items (GPSTIME11, WAVEPACKET13, RGB14, ...) are reported as unsupported.
-#include <stdint.h>
+// LASzip codec (host code; file decoding / encoding sits next to the hot path).  The reference
+// gets this from laspy[lazrs] (src/vapc/datahandler.py:72-73, :99-165), which is not installable offline.  Written from the
+// published LASzip format description (Isenburg, "LASzip: lossless compression of LiDAR data", PE&RS 2013): an adaptive
+// arithmetic coder (Said's FastAC scheme), integer "corrector" coders with k-bit contexts and the per-item predictors.
+//   compressor 2, "pointwise chunked":  POINT10 v2, GPSTIME11 v2, RGB12 v2, BYTE v2          LAS point formats 0 - 3
+//   compressor 3, "layered chunked":    POINT14 v3, RGB14 v3, BYTE14 v3                       LAS 1.4 point formats 6 / 7
+// Decoder pins: the reference's four fixtures decode to their headers' bounding boxes and by-return counts, and every chunk /
+// layer decoder ends on the last byte of its stream (enforced for every file).  Encoder pin: re-encoding the decoded records
+// reproduces the point data of all four files byte for byte (tests/test_laz.py).  GPSTIME11 v2 and RGB14 v3 occur in none of
+// the fixtures: they reuse pinned coders (the GPS coder of POINT14 v3, the colour coder of RGB12 v2) and are round-trip tested.
+// Chunks are independent: they are decoded / encoded on all host cores.
 #include <stdlib.h>
 #include <string.h>
 
