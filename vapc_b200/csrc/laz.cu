@@ -9,9 +9,11 @@
 // reproduces the point data of all four files byte for byte (tests/test_laz.py).  GPSTIME11 v2 and RGB14 v3 occur in none of
 // the fixtures: they reuse pinned coders (the GPS coder of POINT14 v3, the colour coder of RGB12 v2) and are round-trip tested.
 // Chunks are independent: they are decoded / encoded on all host cores.
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <memory>
 #include <mutex>
