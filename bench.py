@@ -3,19 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl reference]
 
-A step is one pass of the hot path over one synthetic cloud: bounding box -> packed voxel keys ->
-stable radix sort -> run-length segmentation -> FP64 (count, mean, M2) moments -> density, centroid,
-std, covariance, eigenvalues, 8 eigen-features (+ the point->voxel map).  At N = 1 the workload is
-BASELINE.json configs[1]: a 100M-point uniform cloud, voxel 0.1 m, full attribute set.
+A step is one pass of the hot path over one synthetic cloud: packed voxel keys + records grouped by key prefix -> grouping inside
+the buckets (cell table on dense grids, else stable radix passes) -> FP64 (count, mean, M2) moments -> density, centroid, std,
+covariance, eigenvalues, 8 eigen-features (+ the point->voxel map).
+  N = 1: BASELINE.json configs[1], a 100M-point uniform cloud, voxel 0.1 m, full attribute set.
+  N > 1: configs[2], a clustered terrain + trees cloud of 1.25e8 points per GPU sharded in scan-line order, voxel 0.25 m; the same
+         cloud shuffled and round 1's slab layout are measured too (extra), and the sharded table is CHECKED after the timed region
+         against plain torch on the ranks' own points ("check"; a failed check exits non-zero).
 
 value   whole-job points/s with the inputs already resident in HBM (CUDA events, max over ranks)
-e2e     the same metric through the public API with HOST buffers: pinned host -> device copies of X, Y, Z
-        and the device -> pinned-host read of the complete voxel table inside the timed region
-roofline  the dominant C-ABI call: algorithmic bytes / CUDA-event time on the launching stream, against
-        MEASURED_PEAKS.json
-cpu_baseline  the CPU port of the reference's pandas path (oracle/ref_port.py, "port": the reference is pure
-        Python and /root/reference does not exist on the GPU box) on a bounded spatial crop, 1 core
---impl reference  times that CPU port alone and prints the same line with "impl": "reference"
+e2e     the same metric through the public API with HOST buffers: pinned host -> device copies of the coordinates and the
+        device -> pinned-host read of the voxel table inside the timed region; platform_gbs = what plain concurrent copies
+        reach on this box, frac_of_platform = the e2e's PCIe traffic against it; e2e.facade = the drop-in `Vapc` class
+        (DataFrame in, reduced DataFrame out)
+roofline  the kernel with the largest share of the step: algorithmic bytes / CUDA-event time on the launching stream,
+        against MEASURED_PEAKS.json; traffic = its DRAM bytes in the committed ncu capture (profiles/r2_ncu_traffic.json)
+cpu_baseline  the unmodified reference (oracle/_ref, kind "reference"; oracle/ref_port.py, kind "port", where that copy is absent)
+        on a bounded spatial crop, 1 core
+--impl reference  times the reference alone on all host cores and prints the same line with "impl": "reference"
 """
 import argparse
 import json
@@ -31,15 +36,10 @@ sys.path.insert(0, ROOT)
 METRIC = "points/sec voxelise+stats"
 UNIT = "points/s"
 VOXEL_SIZE = 0.1
+VOXEL_SIZE_MULTI = 0.25  # configs[2]
 ORIGIN = [0.0, 0.0, 0.0]
 EXTENT = (50.0, 50.0, 4.0)  # metres: 500 x 500 x 40 voxels = 1e7 cells -> ~10 points per voxel at 1e8 points
 QUANT = 1e-4  # LAS-like coordinate quantisation
-# DRAM traffic per launch of the big kernels at the default workload, from the committed `ncu --set full` capture
-# (profiles/README.md says which file); reported next to the algorithmic bytes of the dominant kernel
-NCU_TRAFFIC_GB = {  # profiles/r1_f_ncu_full.csv (1e8 points, 9 999 543 voxels, 24-bit keys)
-    "bucket_scatter_kernel": 6.42, "reduce_moments_kernel": 5.27, "onesweep_kernel": 1.40, "voxel_stats_kernel": 2.90,
-    "keys_hist_kernel": 2.75, "p2v_lookup_kernel": 0.76, "minmax_partial": 2.40, "digit_hist_kernel": 0.40, "count_heads_kernel": 0.40,
-}
 
 
 def parse():
@@ -47,7 +47,11 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--points", type=int, default=100_000_000, help="points per GPU")
+    ap.add_argument("--points", type=int, default=0, help="points per GPU (default: 1e8 at N = 1 = configs[1], 1.25e8 at N > 1 = configs[2])")
+    ap.add_argument("--bounds", default="header", choices=["header", "computed"],
+                    help="N = 1: the cloud's bounding box comes with the data, as a LAS header gives it (default), or is computed by one more pass")
+    ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the shuffled and slab layouts")
+    ap.add_argument("--no-facade", action="store_true", help="skip the drop-in facade e2e (DataFrame in, reduced DataFrame out)")
     ap.add_argument("--no-las-e2e", action="store_true", help="skip the LAS-integer-input variant of the e2e measurement")
     ap.add_argument("--impl", default="vapc_b200", choices=["vapc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -59,23 +63,6 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 # synthetic data
 # ------------------------------------------------------------------------------------------------
-def gen_cloud_device(n, seed, device, x_shift=0.0):
-    """n quantised uniform points in EXTENT (x shifted by x_shift metres), fp64 device columns."""
-    import torch
-
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    cols = []
-    for k, ext in enumerate(EXTENT):
-        q = torch.randint(0, int(round(ext / QUANT)), (n,), generator=g, device=device, dtype=torch.int64)
-        c = q.to(torch.float64) * QUANT
-        if k == 0 and x_shift:
-            c += x_shift
-        cols.append(c)
-        del q
-    return cols
-
-
 def gen_crop_host(n_sample, seed=2):
     """A spatial crop of the same cloud law at the same density (10 points per voxel at 1e8 points): the box
     [0, lx) x [0, 0.5) x [0, 4) holding n_sample points.  Generated on the host (numpy), used by the CPU legs."""
@@ -93,25 +80,45 @@ def gen_crop_host(n_sample, seed=2):
 # ------------------------------------------------------------------------------------------------
 # CPU legs
 # ------------------------------------------------------------------------------------------------
-def cpu_port_once(x, y, z):
-    from oracle import ref_port
+CPU_KIND_TEXT = {
+    "reference": "the UNMODIFIED reference (oracle/_ref = its package directory copied unchanged by oracle/build_ref.py) through its own API: "
+                 "Vapc(...).compute_requested_attributes() with point_count, point_density, center_of_gravity, std_of_cog, covariance_matrix, "
+                 "eigenvalues, geometric_features; single-threaded pandas/numpy incl. its per-voxel Python eigen step",
+    "port": "oracle/ref_port.py (the reference package is not on this box): keeps the reference's single-threaded pandas data flow incl. its "
+            "per-voxel Python eigen step",
+}
 
-    t0 = time.perf_counter()
-    df = ref_port.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN, with_eigen=True)
-    dt = time.perf_counter() - t0
+
+def cpu_reference_once(x, y, z):
+    """One pass of the reference's CPU path over host columns: (kind, seconds, voxels).  kind "reference" = the unmodified reference
+    (oracle/ref_harness.py over oracle/_ref), "port" = oracle/ref_port.py when the reference package is not there."""
+    from oracle import ref_harness
+
+    if ref_harness.available():
+        ref_harness.import_reference()
+        t0 = time.perf_counter()
+        v = ref_harness.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN)
+        dt = time.perf_counter() - t0
+        df, kind = v.df, "reference"
+    else:
+        from oracle import ref_port
+
+        t0 = time.perf_counter()
+        df = ref_port.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN, with_eigen=True)
+        dt = time.perf_counter() - t0
+        kind = "port"
     nvox = int(df[["voxel_x", "voxel_y", "voxel_z"]].drop_duplicates().shape[0])
-    return dt, nvox
+    return kind, dt, nvox
 
 
 def _cpu_worker(job):
     n_sample, seed = job
     x, y, z, _ = gen_crop_host(n_sample, seed=seed)
-    dt, nvox = cpu_port_once(x, y, z)
-    return dt, nvox
+    return cpu_reference_once(x, y, z)
 
 
 def run_reference_arm(args):
-    """The reference's CPU path (oracle/ref_port.py keeps its pandas data flow) on the host cores.  The reference itself is
+    """The reference's CPU path (the unmodified reference from oracle/_ref; oracle/ref_port.py where that is absent) on the host cores.  The reference itself is
     single-threaded; its own way to use more cores is to cut the cloud into spatial tiles and process them independently
     (main.py:97-137), so every host core gets its own crop of the workload here and the throughput is the sum."""
     rank = int(os.environ.get("RANK", "0"))
@@ -124,40 +131,63 @@ def run_reference_arm(args):
     n_sample = args.cpu_sample or int(min(200_000, max(2_000, budget * 5_000)))
     _, _, _, what = gen_crop_host(n_sample)
     what = what.replace(f"{n_sample} points", f"{n_sample} points per core")
-    nvox = 0
+    nvox, kind = 0, "port"
     with ProcessPoolExecutor(max_workers=cores) as pool:
         for _ in range(args.warmup):
             list(pool.map(_cpu_worker, [(n_sample, 100 + c) for c in range(cores)]))
         t0 = time.perf_counter()
         for k in range(args.steps):
             res = list(pool.map(_cpu_worker, [(n_sample, 1000 * (k + 1) + c) for c in range(cores)]))
-            nvox = sum(r[1] for r in res)
+            nvox = sum(r[2] for r in res)
+            kind = res[0][0]
         total = time.perf_counter() - t0
     value = n_sample * cores * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.points, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": workload_config(args.points or 100_000_000, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": what + f" ({nvox} voxels per step over {cores} processes, one independent crop each: tiling is the reference's "
-                                          "own scaling mechanism); the reference is single-threaded pandas/numpy; per-voxel Python eigen step included"},
+                                          "own scaling mechanism, main.py:97-137); " + CPU_KIND_TEXT[kind]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(points_per_gpu, gpus):
+def workload_config(points_per_gpu, gpus, bounds="header"):
     return {
         "workload": f"configs[1]: {points_per_gpu / 1e6:g}M-point synthetic uniform cloud per GPU, voxel_size={VOXEL_SIZE} m, "
                     "full attribute set (count, density, centroid, std, covariance, eigenvalues, 8 eigen-features) + point->voxel map",
         "points_per_gpu": points_per_gpu, "voxel_size": VOXEL_SIZE, "extent_m": list(EXTENT),
+        "bounds": ("the cloud's bounding box is an input (the LAS header states it; the reference's DataHandler reads the same header): no "
+                   "min/max pass; extra.bounds_computed is the step with that pass" if bounds == "header" else
+                   "computed: one more pass over x, y, z (vapc_minmax_f64)"),
         "l2": "inputs (24 B/point, 2.4 GB at 1e8 points) are larger than the 126 MB L2; no flush needed",
-        "parallelism": f"points sharded in contiguous chunks over {gpus} GPU(s)" + ("" if gpus == 1 else
-                       "; rank r holds the x-slab [0.9 r L, 0.9 r L + L) (10 % overlap with its neighbour); partial voxel tables "
-                       "exchanged by key range with one NCCL all-to-all, then merged"),
+        "parallelism": "one GPU",
     }
+
+
+def workload_config_multi(points_per_gpu, gpus, vs):
+    return {
+        "workload": f"configs[2]: {points_per_gpu * gpus / 1e9:g}B-point synthetic clustered (terrain sheet + trees) cloud sharded over {gpus} GPUs in "
+                    f"scan-line order ({points_per_gpu / 1e6:g}M points per GPU: rank r holds the strip y in [r W, (r+1) W) of a 1000 m wide cloud, W = "
+                    f"{125.0 * points_per_gpu / 1.25e8:g} m), voxel_size={vs} m, full attribute set; partial voxel tables exchanged by key range, then merged",
+        "points_per_gpu": points_per_gpu, "voxel_size": vs,
+        "l2": "inputs (24 B/point, 3 GB per GPU) are larger than the 126 MB L2; no flush needed",
+        "parallelism": f"points sharded in contiguous chunks over {gpus} GPUs; every rank voxelises its chunk alone (local bounds by a min/max pass), "
+                       "the key space is cut by a global histogram, the partial rows that leave a rank are written into the owner's receive buffer over "
+                       "NVLink (peer memory), the owner merges; extra.shuffled = the same cloud dealt at random, extra.slab_configs1 = round 1's layout",
+    }
+
+
+def cpu_baseline_leg(args):
+    n_sample = args.cpu_sample or 100_000
+    cx, cy, cz, what = gen_crop_host(n_sample)
+    kind, dt, cv = cpu_reference_once(cx, cy, cz)
+    return {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": kind, "seconds": round(dt, 2),
+            "sample": what + f" ({cv} voxels); " + CPU_KIND_TEXT[kind] + "; host has %d logical cores" % (os.cpu_count() or 0)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -230,6 +260,7 @@ def algorithmic_bytes(name, n, v, key_bytes, passes, low_passes):
         "vapc_pack_records_bucketed": (24 + k) * n + (k + 24 + k + 32) * n,
         "vapc_sort_pairs": (k + passes * (2 * k + 8) - 4) * n,
         "vapc_sort_pairs_segmented": (k + low_passes * (2 * k + 8) - 4) * n,
+        "vapc_sort_cells_segmented": (2 * k + 8) * n,
         "vapc_count_voxels": k * n,
         "vapc_reduce_moments": (k + 4 + 32 + 4) * n + (k + 12 + 72) * v,
         "vapc_point2voxel_dense": (k + 4) * n + (k + 4) * v,
@@ -248,6 +279,8 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
         ("digit_hist_kernel", k * n),
         # one radix pass: keys + payload in and out; the first pass of a sort takes the payload from the position
         ("onesweep_kernel", (2 * k + 8) * n - (4 * n) / max(1.0, launches_per_step)),
+        # dense grids: the bucketed keys in twice (count, place), sorted keys and positions out
+        ("cell_sort_kernel", (2 * k + 8) * n),
         ("count_heads_kernel", k * n),
         ("reduce_moments_kernel", (k + 4 + 32 + 4) * n + (k + 12 + 72) * v),
         ("p2v_lookup_kernel", (k + 4) * n),
@@ -260,6 +293,89 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
     return kernel, 0.0
 
 
+def time_steps(step, steps, barrier, world, device, dist, profile=False, L=None):
+    """K calls of step() between CUDA events (max over ranks).  profile: per-kernel / per-call CUDA events inside the same region."""
+    import torch
+
+    records = []
+
+    def observer(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        records.append((name, phase, ev))
+
+    launches0 = L.raw("vapc_launch_count")() if L is not None else 0
+    barrier()
+    t0 = time.perf_counter()
+    if profile:
+        L.observer = observer
+        L.call("vapc_profile_enable", 1)  # CUDA events around every kernel launch, on the launching stream
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    out = None
+    for _ in range(steps):
+        out = None
+        out = step()
+    t_end.record()
+    if profile:
+        L.observer = None
+        L.call("vapc_profile_enable", 0)
+    barrier()
+    t1 = time.perf_counter()
+    kernel_times = L.profile_collect() if profile else {}
+    launches = (L.raw("vapc_launch_count")() - launches0) if L is not None else 0
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    return {"ms_per_step": ms_total / steps, "out": out, "records": records, "kernel_times": kernel_times, "launches": launches,
+            "window": [t0, t1]}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel of the committed `ncu --set full` capture
+    of this bench (profiles/r2_ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep): {kernel: GB}, or {} ."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d
+    except Exception:
+        return {}
+
+
+def platform_copy_bandwidth(device, world, dist, barrier, nbytes=1 << 30, reps=3):
+    """What the box gives: every rank copies nbytes host -> device and nbytes device -> host at once (plain pinned cudaMemcpyAsync on
+    two streams), all ranks together.  Aggregate GB/s over all ranks (both directions added), wall clock between barriers."""
+    import torch
+
+    hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    dout = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    best = 0.0
+    for r in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if r:
+            best = max(best, 2 * nbytes * world / dt / 1e9)
+    if world > 1:
+        t = torch.tensor([best], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        best = float(t.item())
+    return best
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -270,10 +386,11 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
+    from tools import synth
     from vapc_b200 import _lib as L
     from vapc_b200 import engine as E
 
@@ -288,28 +405,43 @@ def main():
     sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    n = args.points
-
-    if world > 1:
         from vapc_b200 import dist as D
-
-        x, y, z = gen_cloud_device(n, seed=2 + rank, device=device, x_shift=D.bench_slab_shift(rank, EXTENT[0]))
-    else:
-        x, y, z = gen_cloud_device(n, seed=2, device=device)
-
-    def step_device():
-        if world > 1:
-            return D.voxel_statistics(x, y, z, VOXEL_SIZE, ORIGIN)
-        cloud = E.VoxelCloud.build(x, y, z, VOXEL_SIZE, ORIGIN, keep_columns=False)
-        st = cloud.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
-        return cloud, st
+    multi = world > 1
+    n = args.points or (125_000_000 if multi else 100_000_000)
+    vs = VOXEL_SIZE_MULTI if multi else VOXEL_SIZE
+    FULL = dict(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
 
     def barrier():
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ------------------------------------------------------------------------------
+    windows = []
+    extra = {}
+    check = None
+    if not multi:
+        # ---- N = 1: configs[1] -----------------------------------------------------------------------------------------
+        x, y, z = synth.uniform_cloud(n, seed=2, device=device, extent=EXTENT)
+        # the cloud's bounding box as the header of its LAS file states it (the reference's DataHandler reads the same header)
+        header_bounds = [0.0, 0.0, 0.0] + [e - QUANT for e in EXTENT]
+
+        def make_step(bounds):
+            def step():
+                cloud = E.VoxelCloud.build(x, y, z, vs, ORIGIN, keep_columns=False, bounds=bounds)
+                return cloud, cloud.stats(**FULL)
+            return step
+
+        step_device = make_step(header_bounds if args.bounds == "header" else None)
+        workload = workload_config(n, world, args.bounds)
+    else:
+        # ---- N > 1: configs[2], scan-line order ----------------------------------------------------------------------------
+        x, y, z = synth.clustered_chunk(n, rank, world, device, seed=3, scan_order=True)
+
+        def step_device():
+            return D.voxel_statistics(x, y, z, vs, ORIGIN)
+
+        workload = workload_config_multi(n, world, vs)
+
     for _ in range(max(args.warmup, 3)):
         cloud, st = step_device()
     torch.cuda.synchronize()
@@ -317,47 +449,28 @@ def main():
     exchange_kind = getattr(cloud, "exchange", None)
     key_bytes = cloud.grid.key_bytes
     total_bits = cloud.grid.total_bits
+    sorted_by = getattr(cloud, "sorted_by", None)
     passes = (total_bits + 7) // 8
     low_passes = (total_bits - min(8, cloud.grid.bits[0]) + 7) // 8  # inside the key-prefix buckets
 
     # ---- timed region: K steps, CUDA events, per-call events for the roofline -----------------
-    records = []
-
-    def observer(name, phase):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        records.append((name, phase, ev))
-
-    launches0 = L.raw("vapc_launch_count")()
-    barrier()
-    windows = [[time.perf_counter(), None]]
-    L.observer = observer
-    L.call("vapc_profile_enable", 1)  # CUDA events around every kernel launch, on the launching stream
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        cloud, st = step_device()
-    t_end.record()
-    L.observer = None
-    L.call("vapc_profile_enable", 0)
-    barrier()
-    kernel_times = L.profile_collect()
-    launches = L.raw("vapc_launch_count")() - launches0
-    windows[0][1] = time.perf_counter()
-    ms_total = t_start.elapsed_time(t_end)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    timed = time_steps(step_device, args.steps, barrier, world, device, dist, profile=True, L=L)
+    windows.append(timed["window"])
+    ms_per_step = timed["ms_per_step"]
     value = n * world / (ms_per_step * 1e-3)
+    cloud, st = timed["out"]
+    launches = timed["launches"]
+    kernel_times = timed["kernel_times"]
+    if multi:
+        nv_t = torch.tensor([cloud.nvoxels, cloud.partial_rows_sent], dtype=torch.int64, device=device)
+        dist.all_reduce(nv_t)
+        nvox_global, rows_exchanged = int(nv_t[0]), int(nv_t[1])
 
     per_call = {}
     pending = {}
     gaps = {}
     last_after = None
-    for name, phase, ev in records:
+    for name, phase, ev in timed["records"]:
         if phase == "before":
             pending[name] = ev
             if last_after is not None:
@@ -366,25 +479,25 @@ def main():
             per_call.setdefault(name, []).append(pending.pop(name).elapsed_time(ev))
             last_after = (name, ev)
     gaps = {k: round(sum(v) / len(v), 4) for k, v in gaps.items()}
-    del records
+    timed["records"] = None
 
-    # ---- roofline of the dominant call --------------------------------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    n_local_vox = getattr(cloud, "local_voxels", nvox)
     breakdown = {}
     for name, ts in per_call.items():
         calls_per_step = len(ts) / args.steps
         avg = sum(ts) / len(ts)
-        b = algorithmic_bytes(name, n, nvox, key_bytes, passes, low_passes)
+        b = algorithmic_bytes(name, n, n_local_vox, key_bytes, passes, low_passes)
         breakdown[name] = {"ms_per_call": round(avg, 4), "calls_per_step": calls_per_step, "ms_per_step": round(avg * calls_per_step, 4),
                            "algorithmic_GB": round(b / 1e9, 4), "GBps": round(b / 1e9 / (avg * 1e-3), 1) if b else None}
-    # per kernel (CUDA events around every launch inside the timed region): the dominant one gives the roofline
     per_kernel = {}
     for kname, (cnt, ms) in kernel_times.items():
-        short, b = kernel_algorithmic_bytes(kname, n, nvox, key_bytes, cnt / args.steps)
+        short, b = kernel_algorithmic_bytes(kname, n, n_local_vox, key_bytes, cnt / args.steps)
         e = per_kernel.setdefault(short, {"launches_per_step": 0.0, "ms_per_step": 0.0, "algorithmic_GB_per_launch": round(b / 1e9, 4)})
         e["launches_per_step"] += cnt / args.steps
         e["ms_per_step"] += ms / args.steps
@@ -394,41 +507,132 @@ def main():
         e["GBps"] = round(e["algorithmic_GB_per_launch"] / (e["ms_per_launch"] * 1e-3), 1) if e["algorithmic_GB_per_launch"] and e["ms_per_launch"] else None
     dom = max((k for k in per_kernel if per_kernel[k]["GBps"]), key=lambda k: per_kernel[k]["ms_per_step"])
     achieved = per_kernel[dom]["GBps"]
+    traffic_tab = ncu_traffic()
+    tkey = "n1" if not multi else "multi"
+    traffic = (traffic_tab.get(tkey) or {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": NCU_TRAFFIC_GB.get(dom) if (n == 100_000_000 and world == 1) else None, "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
+                "traffic": traffic, "traffic_unit": "GB per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, read from "
+                "profiles/r2_ncu_traffic.json (the committed --set full capture of this command" + ("" if not multi else "'s per-GPU workload on one GPU") + ")",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_kernel[dom]["algorithmic_GB_per_launch"] * 1e9),
                 "ms_per_launch": per_kernel[dom]["ms_per_launch"], "launches_per_step": per_kernel[dom]["launches_per_step"],
                 "share_of_step": round(per_kernel[dom]["ms_per_step"] / ms_per_step, 3)}
     gpu_ms = sum(v["ms_per_step"] for v in breakdown.values())
 
+    # ---- N = 1 extra: the same step when nobody knows the bounding box (one more pass over x, y, z) ----------------------------
+    if not multi and args.bounds == "header":
+        step_nb = make_step(None)
+        step_nb()
+        t2 = time_steps(step_nb, args.steps, barrier, world, device, dist, L=L)
+        windows.append(t2["window"])
+        extra["bounds_computed"] = {"ms_per_step": t2["ms_per_step"], "value": n / (t2["ms_per_step"] * 1e-3),
+                                    "what": "the same step without caller bounds: vapc_minmax_f64 reads x, y, z once more (24 B/point)"}
+        t2 = None
+
+    # ---- N > 1: correctness of the sharded table, then the other layouts ------------------------------------------------------
+    if multi:
+        from tools.dist_check import verify_sharded_table
+
+        check = verify_sharded_table(cloud, st, x, y, z)
+        check["voxels_table"] = nvox_global
+        check["ok"] = bool(check["ok"] and check["voxels_torch_unique"] == nvox_global)
+        # the per-GPU share of the same workload WITHOUT the other ranks: local pipeline only (N = 1 on this rank's chunk)
+        def step_local():
+            c = E.VoxelCloud.build(x, y, z, vs, ORIGIN, keep_columns=False, want_point2voxel=False)
+            return c, c.stats(**FULL)
+        step_local()
+        tl = time_steps(step_local, args.steps, barrier, world, device, dist, L=L)
+        windows.append(tl["window"])
+        extra["one_gpu_same_workload"] = {"ms_per_step": tl["ms_per_step"], "value_per_gpu": n / (tl["ms_per_step"] * 1e-3),
+                                          "what": "every rank's own chunk voxelised alone (no exchange, no merge), max over ranks: the N = 1 "
+                                                  "figure of THIS workload; value / (N x value_per_gpu) is its scaling efficiency"}
+        tl = None
+        nvlink_bytes = rows_exchanged * 88
+        extra["exchange"] = {"partial_rows_sent_all_ranks": rows_exchanged, "bytes_over_nvlink_per_step": nvlink_bytes,
+                             "share_of_rows": round(rows_exchanged / max(1, nvox_global), 4)}
+        del cloud, st, x, y, z
+        torch.cuda.empty_cache()
+        if not args.no_extra:
+            # shuffled: every rank holds a random sample of the whole cloud -> every rank touches every voxel
+            xs, ys, zs = synth.clustered_chunk(n, rank, world, device, seed=3, scan_order=False)
+
+            def step_shuffled():
+                return D.voxel_statistics(xs, ys, zs, vs, ORIGIN)
+            for _ in range(2):
+                step_shuffled()
+            tsh = time_steps(step_shuffled, max(3, args.steps // 2), barrier, world, device, dist, profile=True, L=L)
+            windows.append(tsh["window"])
+            tab = tsh["out"][0]
+            sent = torch.tensor([tab.partial_rows_sent, tab.nvoxels], dtype=torch.int64, device=device)
+            dist.all_reduce(sent)
+            chk = verify_sharded_table(tab, tsh["out"][1], xs, ys, zs)
+            ex_ms = sum(ms for k, (c_, ms) in tsh["kernel_times"].items() if "pack_partial_rows" in k) / max(3, args.steps // 2)
+            extra["shuffled"] = {"ms_per_step": tsh["ms_per_step"], "value": n * world / (tsh["ms_per_step"] * 1e-3),
+                                 "voxels": int(sent[1]), "partial_rows_sent_all_ranks": int(sent[0]),
+                                 "bytes_over_nvlink_per_step": int(sent[0]) * 88,
+                                 "nvlink_GBps_per_gpu_during_pack": round(int(sent[0]) * 88 / world / 1e9 / (ex_ms * 1e-3), 1) if ex_ms else None,
+                                 "nvlink_peak_GBps_per_direction": 900, "check_ok": bool(chk["ok"] and chk["voxels_torch_unique"] == int(sent[1])),
+                                 "what": "the same cloud with the points dealt to the ranks at random: every rank holds partial rows of (almost) every "
+                                         "voxel, the exchange carries (N-1)/N of all partial rows; limiter = exchange volume + the merge of N partial rows per voxel"}
+            tsh = tab = None
+            del xs, ys, zs
+            torch.cuda.empty_cache()
+            # the slab layout of round 1 (configs[1] boxes overlapping by 10 %), for continuity with SCALE_r01
+            n_slab = 100_000_000 if n == 125_000_000 else n
+            xb, yb, zb = synth.uniform_cloud(n_slab, seed=2 + rank, device=device, extent=EXTENT, x_shift=D.bench_slab_shift(rank, EXTENT[0]))
+
+            def step_slab():
+                return D.voxel_statistics(xb, yb, zb, VOXEL_SIZE, ORIGIN)
+            for _ in range(2):
+                step_slab()
+            tsl = time_steps(step_slab, args.steps, barrier, world, device, dist, L=L)
+            windows.append(tsl["window"])
+            extra["slab_configs1"] = {"ms_per_step": tsl["ms_per_step"], "value": n_slab * world / (tsl["ms_per_step"] * 1e-3), "points_per_gpu": n_slab,
+                                      "what": "round 1's N > 1 layout: rank r holds the configs[1] box shifted to x in [0.9 r L, 0.9 r L + L), voxel 0.1 m"}
+            tsl = None
+            del xb, yb, zb
+            torch.cuda.empty_cache()
+        x, y, z = synth.clustered_chunk(n, rank, world, device, seed=3, scan_order=True)
+    else:
+        del cloud, st
+
     # ---- e2e: host buffers in, host voxel table out -------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hx, hy, hz = (c.cpu().pin_memory() for c in (x, y, z))
-        del x, y, z, cloud, st
-        torch.cuda.empty_cache()
         from vapc_b200.pipeline import HostStreamPipeline, STAT_NAMES
 
-        def compute_fn(dx, dy, dz):
-            if world > 1:
-                c, s_ = D.voxel_statistics(dx, dy, dz, VOXEL_SIZE, ORIGIN)
-            else:
-                c = E.VoxelCloud.build(dx, dy, dz, VOXEL_SIZE, ORIGIN, keep_columns=False)
-                s_ = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
-            out = {"voxel_keys": c.voxel_keys, "count": c.count}
-            out.update({k: getattr(s_, k) for k in STAT_NAMES})
-            return out
+        platform = platform_copy_bandwidth(device, world, dist, barrier)
+        e_steps = max(5, args.steps)
+        if not multi:
+            hx, hy, hz = (c.cpu().pin_memory() for c in (x, y, z))
+            del x, y, z
+            torch.cuda.empty_cache()
+            pipe = HostStreamPipeline(vs, ORIGIN, device, bounds=header_bounds if args.bounds == "header" else None)
+            cols_in = (hx, hy, hz)
+        else:
+            # N > 1: the chunk as the int32 X, Y, Z of its LAS file (12 B/point over PCIe); the table comes back without the
+            # Eigenvalue_n columns (a left-over of the reference, vapc.py:1132)
+            lasq = [torch.round(c / QUANT).to(torch.int32).cpu().pin_memory() for c in (x, y, z)]
+            del x, y, z
+            torch.cuda.empty_cache()
+            e2e_cols = tuple(k for k in STAT_NAMES if k != "eig_n")
 
-        pipe = HostStreamPipeline(VOXEL_SIZE, ORIGIN, device, compute_fn=compute_fn)
-        for _res in pipe.run([(hx, hy, hz)] * 2):  # warm-up: allocates device / pinned buffers
+            def compute_fn(dx, dy, dz):
+                fx, fy, fz = E.las_coordinates(dx, dy, dz, [QUANT] * 3, [0.0] * 3, device)
+                c, s_ = D.voxel_statistics(fx, fy, fz, vs, ORIGIN, stats_columns=e2e_cols)
+                out = {"voxel_keys": c.voxel_keys, "count": c.count}
+                out.update({k: getattr(s_, k) for k in e2e_cols})
+                return out
+
+            pipe = HostStreamPipeline(vs, ORIGIN, device, compute_fn=compute_fn)
+            cols_in = tuple(lasq)
+        for _res in pipe.run([cols_in] * 2):  # warm-up: allocates device / pinned buffers
             pass
         torch.cuda.synchronize()
-        e_steps = max(5, args.steps)
         pipe.h2d_bytes = pipe.d2h_bytes = 0
         barrier()
         t0 = time.perf_counter()
         nres = 0
-        for _res in pipe.run([(hx, hy, hz)] * e_steps):
+        for _res in pipe.run([cols_in] * e_steps):
             nres += 1
         torch.cuda.synchronize()
         barrier()
@@ -436,26 +640,32 @@ def main():
         dt = (windows[-1][1] - t0) / e_steps
         assert nres == e_steps
         h2d, d2h = pipe.h2d_bytes // e_steps, pipe.d2h_bytes // e_steps
-        if world > 1:
+        if multi:
             t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=device)
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             dt, h2d, d2h = float(tmax[0].item()), int(t[1].item()), int(t[2].item())
         e2e = {"value": n * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
-               "steps": e_steps,
-               "api": "vapc_b200.pipeline.HostStreamPipeline over VoxelCloud.build + .stats (N = 1) / dist.voxel_statistics (N > 1): every step "
-                      "copies its X, Y, Z from pinned host memory and its complete voxel table back to pinned host memory; H2D of step k+1, "
-                      "compute of step k and D2H of step k-1 overlap on three streams; wall clock over all steps incl. pipeline fill and "
-                      "drain, max over ranks"}
+               "steps": e_steps, "platform_gbs": round(platform, 1), "pcie_gbs": round((h2d + d2h) / dt / 1e9, 1),
+               "frac_of_platform": round((h2d + d2h) / dt / 1e9 / platform, 3) if platform else None,
+               "platform_what": "aggregate GB/s of all ranks each copying 1 GiB host -> device and 1 GiB device -> host at once (plain pinned "
+                                "cudaMemcpyAsync, two streams per GPU, wall clock between barriers): what this box's PCIe / host memory gives",
+               "api": ("vapc_b200.pipeline.HostStreamPipeline over VoxelCloud.build + .stats: every step copies its fp64 X, Y, Z from pinned host "
+                       "memory and its complete voxel table (224 B/voxel) back to pinned host memory" if not multi else
+                       "vapc_b200.pipeline.HostStreamPipeline over dist.voxel_statistics: every step copies the rank's chunk as int32 LAS X, Y, Z "
+                       "(12 B/point) from pinned host memory and its key range of the voxel table (count, density, centroid, std, covariance, "
+                       "eigenvalues, 8 features: 200 B/voxel) back to pinned host memory") +
+                      "; H2D of step k+1, compute of step k and D2H of step k-1 overlap on three streams; wall clock over all steps incl. "
+                      "pipeline fill and drain, max over ranks"}
 
         # the same cloud as the int32 coordinates of a LAS file (scale 1e-4, offset 0): 12 B/point over PCIe; reported next to e2e
-        if world == 1 and not args.no_las_e2e:
+        if not multi and not args.no_las_e2e:
             lasq = [torch.round(c / QUANT).to(torch.int32) for c in (hx, hy, hz)]
             assert all(bool((q.to(torch.float64) * QUANT + 0.0 == c).all()) for q, c in zip(lasq, (hx, hy, hz))), "not the same cloud"
             lasq = [q.pin_memory() for q in lasq]
             del hx, hy, hz
-            lpipe = HostStreamPipeline(VOXEL_SIZE, ORIGIN, device, las=([QUANT] * 3, [0.0] * 3))
+            lpipe = HostStreamPipeline(vs, ORIGIN, device, las=([QUANT] * 3, [0.0] * 3), bounds=header_bounds if args.bounds == "header" else None)
             for _res in lpipe.run([tuple(lasq)] * 2):
                 pass
             torch.cuda.synchronize()
@@ -466,37 +676,46 @@ def main():
             torch.cuda.synchronize()
             windows.append([t0, time.perf_counter()])
             ldt = (windows[-1][1] - t0) / e_steps
-            e2e["las_int32"] = {"value": n / ldt, "unit": UNIT, "ms_per_step": ldt * 1e3, "h2d_bytes_per_step": lpipe.h2d_bytes // e_steps,
-                                "d2h_bytes_per_step": lpipe.d2h_bytes // e_steps,
+            lh, ld = lpipe.h2d_bytes // e_steps, lpipe.d2h_bytes // e_steps
+            e2e["las_int32"] = {"value": n / ldt, "unit": UNIT, "ms_per_step": ldt * 1e3, "h2d_bytes_per_step": lh, "d2h_bytes_per_step": ld,
+                                "frac_of_platform": round((lh + ld) / ldt / 1e9 / platform, 3) if platform else None,
                                 "what": "the same cloud entering as the int32 X, Y, Z of a LAS file (scale 1e-4, offset 0; identical doubles, "
                                         "identical voxel table): vapc_pack_records_bucketed_i32 forms X * scale + offset in the key kernels"}
+            del lasq
+        # the drop-in facade: DataFrame in -> reduced DataFrame out
+        if not multi and not args.no_facade:
+            try:
+                from tools.facade_bench import facade_e2e
+
+                e2e["facade"] = facade_e2e(sizes=(10_000_000, 100_000_000) if n >= 100_000_000 else (n,))
+            except Exception as exc:  # noqa: BLE001
+                e2e["facade"] = {"error": repr(exc)}
 
     clocks = sampler.stop(windows)
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and rank == 0:
-        n_sample = args.cpu_sample or 100_000
-        cx, cy, cz, what = gen_crop_host(n_sample)
-        dt, cv = cpu_port_once(cx, cy, cz)
-        cpu_baseline = {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": round(dt, 2),
-                        "sample": what + f" ({cv} voxels); oracle/ref_port.py keeps the reference's single-threaded pandas data flow "
-                                         "incl. its per-voxel Python eigen step; host has %d logical cores" % (os.cpu_count() or 0)}
+        cpu_baseline = cpu_baseline_leg(args)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(workload_config(n, world), voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes,
-                                                 **({"exchange": exchange_kind} if world > 1 else {})),
+            "data": "synthetic", "config": dict(workload, voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes,
+                                                 **({"grouping": sorted_by} if sorted_by else {}),
+                                                 **({"exchange": exchange_kind, "voxels_all_gpus": nvox_global} if multi else {})),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": per_kernel, "abi_calls": breakdown, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3),
-            "gaps_between_calls_ms": gaps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check, "extra": extra, "kernels": per_kernel, "abi_calls": breakdown,
+            "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3), "gaps_between_calls_ms": gaps,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
+    if multi:
+        ok = check is None or check["ok"]
         dist.destroy_process_group()
+        if not ok:
+            raise SystemExit("bench.py: the sharded voxel table failed its check: " + json.dumps(check))
 
 
 if __name__ == "__main__":

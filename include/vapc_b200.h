@@ -175,6 +175,20 @@ VAPC_API int vapc_sort_pairs_segmented(void* keys, void* keys_alt, uint32_t* idx
                               const uint32_t* seg_start, int32_t nseg, void* ws, size_t ws_bytes,
                               int32_t* result_location_host, void* stream);
 
+/* ---- dense grids: the buckets sorted through a per-bucket cell table instead of radix passes -------------
+ * Replaces vapc_sort_pairs_segmented + vapc_count_voxels when the key bits below the bucket digit number 7..16 (grids of up
+ * to 24 key bits: 2^low_bits cells of one bucket fit 16-bit counters in one SM's shared memory) and the keys are 32-bit:
+ * per bucket count -> scan -> place -> put every cell's positions in ascending order.  keys_bucketed / bucket_start: as
+ * written by vapc_pack_records_bucketed (not modified).  keys_sorted, pos_sorted: the same contents
+ * vapc_sort_pairs_segmented would produce (stable: input order inside a voxel), bit for bit.  *nvoxels (device int64)
+ * and ws: as vapc_count_voxels leaves them (vapc_reduce_moments runs next on the same ws).  status (device int32, caller-
+ * zeroed): bit 2 is set when the method does not apply to this cloud — a cell holding more than 128 points — and the
+ * outputs are then undefined: fall back to vapc_sort_pairs_segmented + vapc_count_voxels.  (The pandas groupby this
+ * stands for: vapc.py:724, :843, :959.) */
+VAPC_API int vapc_sort_cells_segmented(const void* keys_bucketed, int64_t n, int32_t key_bytes, int32_t low_bits,
+                              const uint32_t* bucket_start, int32_t nseg, void* keys_sorted, uint32_t* pos_sorted,
+                              int64_t* nvoxels, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- run-length segmentation of sorted keys into the voxel table ----------------------
  * Step 1: count voxels.  Writes per-tile head counts + their exclusive scan into ws and the
  * number of voxels into *nvoxels (device int64).  Step 2 (vapc_reduce_moments) needs the same
@@ -205,6 +219,9 @@ VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_so
                         void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
                         double* mean3, double* m2, uint32_t* row_sorted, uint32_t* idx_sorted,
                         void* ws, size_t ws_bytes, void* stream);
+/* idx_sorted[p] = original index of the point at sorted position p, read back from its record (vapc_reduce_moments writes the same
+ * array when given idx_sorted; callers that only need it for the per-attribute statistics, vapc.py:393-406, form it on demand). */
+VAPC_API int vapc_record_indices(const double* xyzw, const uint32_t* pos_sorted, int64_t n, uint32_t* idx_sorted, void* stream);
 /* out[index[i]] = values[i] */
 VAPC_API int vapc_scatter_u32(const uint32_t* index, const uint32_t* values, int64_t n, uint32_t* out, void* stream);
 

@@ -1,0 +1,41 @@
+"""Recipe: make the UNMODIFIED reference importable where /root/reference does not exist (the GPU box).
+
+TEST / MEASUREMENT INFRASTRUCTURE.  The reference (3dgeo-heidelberg/vapc) is pure Python, so "building" it is copying its
+package directory /root/reference/src/vapc, file for file and unchanged, to oracle/_ref/vapc — a directory that is git-ignored
+(never in this repository's history) but not gpurun-ignored, so it travels to the GPU box like the built .so files.  There
+`bench.py --impl reference` and the `cpu_baseline` leg time it through oracle/ref_harness.py (kind "reference"); without it they
+fall back to oracle/ref_port.py (kind "port").  Run by __graft_entry__.build() whenever /root/reference is present.
+
+    python oracle/build_ref.py
+"""
+import filecmp
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.environ.get("VAPC_REFERENCE_SRC", "/root/reference/src")
+DST = os.path.join(HERE, "_ref")
+
+
+def build(verbose=True) -> bool:
+    src = os.path.join(SRC, "vapc")
+    if not os.path.isdir(src):
+        if verbose:
+            print(f"oracle/build_ref.py: {src} not present; keeping oracle/_ref as it is")
+        return os.path.isdir(os.path.join(DST, "vapc"))
+    dst = os.path.join(DST, "vapc")
+    os.makedirs(dst, exist_ok=True)
+    for name in sorted(os.listdir(src)):
+        if not name.endswith(".py"):
+            continue
+        a, b = os.path.join(src, name), os.path.join(dst, name)
+        if not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
+            shutil.copyfile(a, b)
+    if verbose:
+        print(f"oracle/build_ref.py: reference package at {dst}")
+    return True
+
+
+if __name__ == "__main__":
+    sys.exit(0 if build() else 1)

@@ -359,9 +359,88 @@ def clusters_nn():
     save("clusters_nn", store)
 
 
+def label_change():
+    """label_by_mask (vapc.py:614-677) and the in-memory core of extract_areas_with_change_using_mahalanobis_distance
+    (vapc_tools.py:625-660: two-epoch change -> voxels with change_type >= 1 as the mask -> select_by_mask + label_by_mask of both
+    epochs, vapc_tools.py:589-622) of the unmodified reference, frames handed over directly instead of through LAS files.
+      lab_unique_*   scene of 3000 points labelled by a mask of unique voxels carrying two attributes;
+      lab_dup_*      the same with a mask holding several rows per voxel (the left join multiplies rows);
+      chg_*          epochs of 6000 / 6200 points, voxel 0.5, alpha 0.005: the mask frame and, per epoch, the selected + labelled frame."""
+    store = {}
+    rng = np.random.default_rng(2024)
+    scene = uniform_cloud(3000, 31, (0.0, 0.0, 0.0), (8.0, 6.0, 3.0))[["X", "Y", "Z"]].assign(_row=np.arange(3000, dtype=np.float64))
+    mpts = uniform_cloud(400, 32, (1.0, 1.0, 0.0), (6.0, 5.0, 2.0))[["X", "Y", "Z"]]
+    mpts["label"] = rng.integers(0, 5, len(mpts)).astype(np.float64)
+    mpts["score"] = np.round(rng.random(len(mpts)), 3)
+    vs = 0.5
+    for c in scene.columns:
+        store[f"in_scene_{c}"] = scene[c].to_numpy()
+    for c in mpts.columns:
+        store[f"in_mask_{c}"] = mpts[c].to_numpy()
+    store["in_voxel_size"] = np.float64(vs)
+    # unique mask voxels: the mask reduced to voxel centres first
+    m = new_vapc(mpts, vs, return_at="center_of_voxel")
+    m.reduce_to_voxels()
+    store["lab_unique_mask__columns"] = np.array(m.df.columns.tolist())
+    cols_to(store, "lab_unique_mask_", m.df)
+    m = new_vapc(m.df, vs)  # a fresh object over the reduced frame, as point_cloud_to_vapc gives after reading the mask file
+    p = new_vapc(scene, vs)
+    p.label_by_mask(m, label_attributes=["label", "score"])
+    store["lab_unique__columns"] = np.array(p.df.columns.tolist())
+    cols_to(store, "lab_unique_", p.df.reset_index(drop=True))
+    store["lab_unique_index_names"] = np.array([str(n) for n in p.df.index.names])
+    # several mask rows per voxel
+    m = new_vapc(mpts, vs)
+    p = new_vapc(scene, vs)
+    p.label_by_mask(m, label_attributes=["label"])
+    store["lab_dup__columns"] = np.array(p.df.columns.tolist())
+    cols_to(store, "lab_dup_", p.df.reset_index(drop=True))
+    # default arguments: the join refuses the overlapping voxel columns
+    try:
+        new_vapc(scene, vs).label_by_mask(new_vapc(mpts, vs))
+        store["lab_default_raises"] = np.array("")
+    except Exception as exc:  # noqa: BLE001
+        store["lab_default_raises"] = np.array(type(exc).__name__)
+    # change areas
+    e1 = np.round(rng.random((6000, 3)) * [12.0, 10.0, 3.0], 4)
+    moved = e1[:5200].copy()
+    moved[(moved[:, 0] > 5.0) & (moved[:, 0] < 7.0)] += [0.15, 0.0, 0.1]
+    e2 = np.concatenate([np.round(moved + rng.normal(0, 0.01, moved.shape), 4), np.round(rng.random((1000, 3)) * [12.0, 10.0, 3.0] + [3.0, 0, 0], 4)])
+    alpha = 0.005
+    for k, e in (("1", e1), ("2", e2)):
+        for j, c in enumerate("XYZ"):
+            store[f"in_chg_e{k}_{c}"] = e[:, j]
+    store["in_chg_alpha"] = np.float64(alpha)
+    frames = [pd.DataFrame(e, columns=list("XYZ")) for e in (e1, e2)]
+    bi = vapc.BiTemporalVapc([new_vapc(frames[0], vs), new_vapc(frames[1], vs)])
+    bi.prepare_data_for_mahalanobis_distance()
+    bi.merge_vapcs_with_same_voxel_index()
+    bi.compute_mahalanobis_distance(alpha=alpha)
+    bi.compute_voxels_occupied_in_single_epoch()
+    bi.prepare_data_for_export()
+    bi.df = bi.df[(bi.df["change_type"] >= 1)]
+    mask_frame = bi.df.reset_index(drop=True)
+    store["chg_mask__columns"] = np.array(mask_frame.columns.tolist())
+    cols_to(store, "chg_mask_", mask_frame)
+    for k, f in (("1", frames[0]), ("2", frames[1])):
+        vm = vapc.Vapc(vs)
+        vm.df = mask_frame.copy()
+        sc = vapc.Vapc(vs)
+        sc.df = f.assign(_row=np.arange(len(f), dtype=np.float64))
+        sc.select_by_mask(vm, segment_in_or_out="in")
+        sc.label_by_mask(vm, ["mahalanobi_significance", "p_value", "change_type"])
+        out = sc.df.reset_index(drop=True)
+        store[f"chg_out{k}__columns"] = np.array(out.columns.tolist())
+        cols_to(store, f"chg_out{k}_", out)
+    save("label_change", store)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "clusters_nn":
         clusters_nn()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "label_change":
+        label_change()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "real_file":
         real_file()
@@ -375,3 +454,4 @@ if __name__ == "__main__":
     grid8()
     real_file()
     clusters_nn()
+    label_change()

@@ -52,7 +52,7 @@ def load_golden(name):
 
 
 def cloud_cases():
-    return [n for n in golden_names() if n not in ("kat_voxelize", "clusters_nn")]
+    return [n for n in golden_names() if n not in ("kat_voxelize", "clusters_nn", "label_change")]
 
 
 def per_voxel(gold, point2voxel, nvox, col):

@@ -402,6 +402,55 @@ def test_reproducible_bitwise(E):
         assert torch.equal(getattr(a, name), getattr(c, name)), name + " (bucketed vs input-order records)"
 
 
+def _cell_sort_cloud(kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "low9":  # 8 + 5 + 4 = 17 key bits: 9 below the bucket digit, the smallest cell tables
+        ext, n = (25.6, 3.2, 1.6), 150_000
+    elif kind == "low13":
+        ext, n = (25.6, 25.6, 3.2), 400_000
+    elif kind == "low16":  # 9 + 9 + 6 = 24 key bits like the benchmark grid: 2^16 cells per bucket
+        ext, n = (50.0, 50.0, 4.0), 1_500_000
+    else:
+        raise ValueError(kind)
+    pts = np.stack([rng.integers(0, int(e / 1e-4), n) * 1e-4 for e in ext], axis=1)
+    # hot cells of 17 .. ~120 points (the 32-wide network and the warp-ranked cells), scattered through the input
+    hot = []
+    for cnt in (17, 20, 31, 32, 33, 40, 64, 96, 100, 110):
+        for _ in range(6):
+            c = np.floor(rng.uniform(0, 1, 3) * np.array(ext) / 0.1) * 0.1 + 0.05
+            hot.append(c + rng.uniform(-0.04, 0.04, (cnt, 3)))
+    pts = np.vstack([pts] + hot)
+    pts = np.round(pts[rng.permutation(len(pts))], 4)
+    return tuple(np.ascontiguousarray(pts[:, k]) for k in range(3))
+
+
+@pytest.mark.parametrize("kind", ["low9", "low13", "low16"])
+def test_cell_sort_equals_radix(E, kind):
+    """vapc_sort_cells_segmented (dense grids) gives what the stable radix passes give, bit for bit: sorted keys, positions
+    (input order inside a voxel), voxel count, and with them every table column."""
+    x, y, z = _cell_sort_cloud(kind, 7)
+    a = E.VoxelCloud.build(x, y, z, 0.1, [0, 0, 0], cell_sort=True)
+    b = E.VoxelCloud.build(x, y, z, 0.1, [0, 0, 0], cell_sort=False)
+    assert a.sorted_by == "cells" and b.sorted_by == "radix"
+    assert a.nvoxels == b.nvoxels
+    assert int(_u32(a.count).max()) >= 100
+    for name in ("keys_sorted", "pos_sorted", "idx_sorted", "voxel_keys", "start", "count", "first_idx", "mean3", "m2", "point2voxel"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    c = E.VoxelCloud.build(x, y, z, 0.1, [0, 0, 0], cell_sort=True)  # and run to run (the atomics only hand out slots)
+    assert torch.equal(a.pos_sorted, c.pos_sorted) and torch.equal(a.m2, c.m2)
+
+
+def test_cell_sort_falls_back_on_crowded_cells(E):
+    """A cell with more than 128 points: the per-cell ordering is not the cell sort's job, status bit 2 -> radix passes."""
+    x, y, z = _cell_sort_cloud("low13", 8)
+    x[:500], y[:500], z[:500] = 3.33, 4.44, 1.11
+    a = E.VoxelCloud.build(x, y, z, 0.1, [0, 0, 0], cell_sort=True)
+    b = E.VoxelCloud.build(x, y, z, 0.1, [0, 0, 0], cell_sort=False)
+    assert a.sorted_by == "radix"
+    for name in ("keys_sorted", "pos_sorted", "voxel_keys", "count", "m2", "point2voxel"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
 def test_bucketed_records(E):
     """vapc_pack_records_bucketed: buckets are the leading key bits in order, stable inside a bucket, every record
     carries its point and its original index."""

@@ -95,10 +95,12 @@ SIGNATURES = {
     "vapc_segment_workspace_bytes": (SZ, [I64]),
     "vapc_count_voxels": (C.c_int, [P, I64, I32, P, P, SZ, P]),
     "vapc_reduce_moments": (C.c_int, [P, P, I64, GP, P, I64, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "vapc_record_indices": (C.c_int, [P, P, I64, P, P]),
     "vapc_bucket_workspace_bytes": (SZ, [I64]),
     "vapc_pack_records_bucketed": (C.c_int, [P, P, P, I64, GP, P, P, P, P, C.POINTER(I32), C.POINTER(I32), P, P, SZ, P]),
     "vapc_expand_bucket_keys": (C.c_int, [P, I64, P, I32, I32, P, P]),
     "vapc_sort_pairs_segmented": (C.c_int, [P, P, P, P, I32, I64, I32, I32, P, I32, P, SZ, C.POINTER(I32), P]),
+    "vapc_sort_cells_segmented": (C.c_int, [P, I64, I32, I32, P, I32, P, P, P, P, P, SZ, P]),
     "vapc_point2voxel_table_bytes": (SZ, [I32]),
     "vapc_point2voxel_dense": (C.c_int, [P, I64, P, I64, I32, I32, P, SZ, P, P]),
     "vapc_voxel_stats": (C.c_int, [P, P, P, P, I64, GP, P, P, P, P, P, P, P, P]),

@@ -24,45 +24,17 @@
 
 #include "common.cuh"
 #include "math3.cuh"
+#include "segment_ws.cuh"
 
 namespace {
+using namespace segws;
 constexpr int kThreads = 256;
 constexpr int kItems = 4;
-constexpr int kSegTile = kThreads * kItems;  // 1024
+static_assert(kSegTile == kThreads * kItems, "tile = 4 positions per thread");
 constexpr int kPartialRowWords = 11;         // exchanged partial voxel row: key, count, mean[3], M2[6] (8 bytes each)
 #ifndef VAPC_REDUCE_MINB
 #define VAPC_REDUCE_MINB 4
 #endif
-
-struct SegWs {  // layout of the segmentation workspace
-  uint32_t* tile_heads;       // [ntiles]   heads per tile, then (in place) exclusive scan = first voxel row of the tile
-  unsigned long long* total;  // [1]        number of voxels
-  void* scan_ws;              // scan scratch
-  uint32_t* carry_cnt;        // [ntiles]   points in the leading partial segment (0 = none)
-  double* carry;              // [ntiles][10] its partial moments (or other per-op payload)
-  uint32_t* long_chains;      // [ntiles]   first tile of every carry chain longer than one tile
-  uint32_t* n_long;           // [1]
-};
-inline int64_t seg_tiles(int64_t n) { return (n + kSegTile - 1) / kSegTile; }
-inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
-inline size_t seg_ws_bytes(int64_t n) {
-  const int64_t nt = seg_tiles(n < 1 ? 1 : n);
-  return align_up(nt * 4) + align_up(8) + align_up(scan_u32_workspace_bytes(nt)) + align_up(nt * 4) + align_up(nt * 10 * 8) +
-         align_up(nt * 4) + align_up(4);
-}
-inline SegWs carve(void* ws, int64_t n) {
-  const int64_t nt = seg_tiles(n < 1 ? 1 : n);
-  unsigned char* p = static_cast<unsigned char*>(ws);
-  SegWs w;
-  w.tile_heads = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
-  w.total = reinterpret_cast<unsigned long long*>(p); p += align_up(8);
-  w.scan_ws = p; p += align_up(scan_u32_workspace_bytes(nt));
-  w.carry_cnt = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
-  w.carry = reinterpret_cast<double*>(p); p += align_up(nt * 10 * 8);
-  w.long_chains = reinterpret_cast<uint32_t*>(p); p += align_up(nt * 4);
-  w.n_long = reinterpret_cast<uint32_t*>(p);
-  return w;
-}
 
 // ---- load one tile's keys (blocked, 4 per thread) + the predecessor of the first ---------------
 template <typename KeyT>
@@ -507,6 +479,14 @@ __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const uint32_t* 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[__ldcs(index + i)] = __ldcs(row + i);
 }
 
+// original index of every sorted position, read from the fourth slot of its record (8 of the record's 32 bytes = one sector)
+__global__ void __launch_bounds__(kThreads) record_indices_kernel(const double* __restrict__ xyzw, const uint32_t* __restrict__ pos_sorted, int64_t n,
+                                                                  uint32_t* __restrict__ idx_sorted) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    idx_sorted[p] = (uint32_t)__double_as_longlong(__ldg(xyzw + 4 * (int64_t)__ldcs(pos_sorted + p) + 3));
+}
+
 // ---- closest to centroid ----------------------------------------------------------------------------
 // distance = sqrt((X-cog_x)^2 + (Y-cog_y)^2 + (Z-cog_z)^2), numpy evaluation order, no FMA.
 __device__ __forceinline__ double ref_distance(double px, double py, double pz, double cx, double cy, double cz) {
@@ -808,6 +788,16 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_
               nvoxels_host, count, mean3, m2, w.long_chains, w.n_long);
   VAPC_LAUNCH(fixup_long_chains_kernel, kNumSMs, kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt, nvoxels_host, count, mean3, m2,
               w.long_chains, w.n_long);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
+extern "C" int vapc_record_indices(const double* xyzw, const uint32_t* pos_sorted, int64_t n, uint32_t* idx_sorted, void* stream) {
+  if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_record_indices: n < 0");
+  if (n == 0) return VAPC_OK;
+  if (!xyzw || !pos_sorted || !idx_sorted) return vapc_set_error(VAPC_E_INVALID, "vapc_record_indices: null buffer");
+  const int grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16);
+  VAPC_LAUNCH(record_indices_kernel, grid, kThreads, 0, as_stream(stream), xyzw, pos_sorted, n, idx_sorted);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -121,6 +121,7 @@ class ShardedVoxelTable:
     partial_rows_sent: int
     partial_rows_received: int
     exchange: str = "nccl"  # "peer": rows written straight into the owner's symmetric receive buffer over NVLink
+    local_voxels: int = 0  # rows of this rank's own partial table before the exchange
 
     def stats(self, density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True):
         from . import engine as E
@@ -284,7 +285,7 @@ def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: tor
 
 
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
-                     thresholds=None, keep_local=False):
+                     thresholds=None, keep_local=False, stats_columns=None):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
@@ -389,7 +390,13 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     table = ShardedVoxelTable(grid=g, nvoxels=vm, voxel_keys=out_keys, count=out_count, mean3=out_mean, m2=out_m2,
                               thresholds=host[world * world:].tolist(), partial_rows_sent=int(sum(send_remote)),
                               partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl")
-    st = table.stats() if with_stats else None
+    table.local_voxels = v
+    if not with_stats:
+        st = None
+    elif stats_columns is not None:  # only these columns (a host that wants the table back pays PCIe time per column)
+        st = table.stats(**{k: (k in stats_columns) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")})
+    else:
+        st = table.stats()
     if keep_local:
         # keep_local: a third value, the LocalShard for rows_from_owner / point_distance / closest_to_cog below
         recv_keys = in_rows[:, 0].contiguous().view(torch.int64).clone() if n_in else torch.empty(0, dtype=torch.int64, device=dev)

@@ -10,6 +10,7 @@ This is what `vapc_b200.Vapc` / `BiTemporalVapc` (the reference-shaped facade) d
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -211,6 +212,9 @@ def _tune_device(device):
             L.call("vapc_set_l2_fetch_granularity", g)
 
 
+CELL_SORT = os.environ.get("VAPC_CELL_SORT", "1") != "0"  # dense grids: counting sort through a per-bucket cell table
+CELL_SORT_MIN_BITS = 9   # fewer key bits below the bucket digit: a single radix pass is as cheap
+CELL_SORT_MAX_MEAN = 16  # mean points per cell of the key space beyond which the per-cell ordering would dominate
 DENSE_P2V_MAX_BITS = 29  # rank-bitmap point->voxel table: 2^bits / 4 bytes, <= 128 MB stays L2-resident on B200
 
 
@@ -237,7 +241,7 @@ class VoxelCloud:
         self.xyzw = None  # 32-byte records {x, y, z, original index}, in bucket order (or input order)
         self.keys_sorted = None
         self.pos_sorted = None  # position of each sorted point's record in xyzw
-        self.idx_sorted = None  # original index of each sorted point
+        self._idx_sorted = None  # original index of each sorted point (formed on first use)
         self.voxel_keys = None
         self.start = None
         self.count = None
@@ -246,12 +250,13 @@ class VoxelCloud:
         self.m2 = None
         self.point2voxel = None
         self._seg_ws = None
+        self.sorted_by = "radix"  # or "cells" (vapc_sort_cells_segmented)
         self._stats_cache: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------
     @classmethod
     def build(cls, x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), *, bounds=None, want_point2voxel=True,
-              keep_columns=True, device=None, bucketed=True, las=None) -> "VoxelCloud":
+              keep_columns=True, device=None, bucketed=True, las=None, cell_sort=None) -> "VoxelCloud":
         """voxelize + groupby of the reference (vapc.py:188-207 and the groupby at :724, :843, :959)
         as: bounds -> packed keys + xyzw records in key-prefix bucket order -> stable radix sort of the remaining key
         bits inside the buckets -> segmentation -> moments.  bucketed=False keeps the records in input order and
@@ -259,6 +264,8 @@ class VoxelCloud:
         las = (X, Y, Z, scales, offsets): the cloud as the int32 coordinates of a LAS file (x, y, z are then ignored and may be
         None): the key kernels read 12 B/point and form X * scale + offset themselves — the same doubles, the same results."""
         _require_cuda()
+        if cell_sort is None:
+            cell_sort = CELL_SORT
         if las is not None:
             if not bucketed:
                 raise ValueError("LAS integer input needs the bucketed path")
@@ -297,6 +304,10 @@ class VoxelCloud:
         status = torch.zeros(1, dtype=torch.int32, device=device)
         _tune_device(device)
         dense_p2v = want_point2voxel and g.total_bits <= DENSE_P2V_MAX_BITS
+        ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
+        self._seg_ws = _empty(ws_bytes, torch.uint8, device)
+        nv = torch.zeros(2, dtype=torch.int64, device=device)
+        host = None
         if bucketed:
             keys = _empty(n, kdtype, device)  # keys in input order
             keys_b = _empty(n, kdtype, device)
@@ -312,14 +323,29 @@ class VoxelCloud:
                        C.byref(bucket_bits), C.byref(bkey_bytes), _ptr(status), _ptr(bws), bws_bytes, _stream())
             del bws
             low_bits = g.total_bits - bucket_bits.value
-            if bkey_bytes.value == 4 and g.key_bytes == 8:
-                # 64-bit grid, but the bits below the bucket digit fit 32: sort 4-byte keys, then rebuild the full sorted keys
-                low_sorted, self.pos_sorted = sort_pairs_segmented(keys_b.view(torch.int32)[:n], low_bits, bucket_start, 1 << bucket_bits.value)
-                self.keys_sorted = _empty(n, torch.int64, device)
-                L.call("vapc_expand_bucket_keys", _ptr(low_sorted), n, _ptr(bucket_start), bucket_bits.value, low_bits, _ptr(self.keys_sorted), _stream())
-                del low_sorted
-            else:
-                self.keys_sorted, self.pos_sorted = sort_pairs_segmented(keys_b, low_bits, bucket_start, 1 << bucket_bits.value)
+            nbuckets = 1 << bucket_bits.value
+            # dense grids: the cells of a bucket fit a shared-memory table -> counting sort instead of radix passes (csrc/cell_sort.cu)
+            if (cell_sort and g.key_bytes == 4 and bucket_bits.value == 8 and CELL_SORT_MIN_BITS <= low_bits <= 16
+                    and n <= (CELL_SORT_MAX_MEAN << g.total_bits)):
+                self.keys_sorted = _empty(n, kdtype, device)
+                self.pos_sorted = _empty(n, torch.int32, device)
+                L.call("vapc_sort_cells_segmented", _ptr(keys_b), n, 4, low_bits, _ptr(bucket_start), nbuckets, _ptr(self.keys_sorted),
+                       _ptr(self.pos_sorted), _ptr(nv), _ptr(status), _ptr(self._seg_ws), ws_bytes, _stream())
+                host = torch.cat([nv[:1], status.to(torch.int64)]).cpu()  # the one sync of the pipeline
+                if int(host[1]) & 4:  # a cell with too many points for the per-cell ordering: the radix sort takes over
+                    host = None
+                    self.keys_sorted = self.pos_sorted = None
+                else:
+                    self.sorted_by = "cells"
+            if host is None:
+                if bkey_bytes.value == 4 and g.key_bytes == 8:
+                    # 64-bit grid, but the bits below the bucket digit fit 32: sort 4-byte keys, then rebuild the full sorted keys
+                    low_sorted, self.pos_sorted = sort_pairs_segmented(keys_b.view(torch.int32)[:n], low_bits, bucket_start, nbuckets)
+                    self.keys_sorted = _empty(n, torch.int64, device)
+                    L.call("vapc_expand_bucket_keys", _ptr(low_sorted), n, _ptr(bucket_start), bucket_bits.value, low_bits, _ptr(self.keys_sorted), _stream())
+                    del low_sorted
+                else:
+                    self.keys_sorted, self.pos_sorted = sort_pairs_segmented(keys_b, low_bits, bucket_start, nbuckets)
             del keys_b
             if not dense_p2v:
                 del keys
@@ -329,11 +355,9 @@ class VoxelCloud:
             self.keys_sorted, self.pos_sorted = sort_pairs(keys, g.total_bits, preserve_keys=dense_p2v)
             if not dense_p2v:
                 del keys
-        ws_bytes = L.raw("vapc_segment_workspace_bytes")(n)
-        self._seg_ws = _empty(ws_bytes, torch.uint8, device)
-        nv = torch.zeros(2, dtype=torch.int64, device=device)
-        L.call("vapc_count_voxels", _ptr(self.keys_sorted), n, g.key_bytes, _ptr(nv), _ptr(self._seg_ws), ws_bytes, _stream())
-        host = torch.cat([nv[:1], status.to(torch.int64)]).cpu()  # the one sync of the pipeline
+        if host is None:
+            L.call("vapc_count_voxels", _ptr(self.keys_sorted), n, g.key_bytes, _ptr(nv), _ptr(self._seg_ws), ws_bytes, _stream())
+            host = torch.cat([nv[:1], status.to(torch.int64)]).cpu()  # the one sync of the pipeline
         if int(host[1]) & 1:
             raise L.VapcError(L.VAPC_E_RANGE, "a point fell outside the voxel grid bounds (NaN / inf coordinate or wrong bounds)")
         self.nvoxels = V = int(host[0])
@@ -344,15 +368,16 @@ class VoxelCloud:
         self.mean3 = torch.empty((3, V), dtype=torch.float64, device=device)
         self.m2 = torch.empty((6, V), dtype=torch.float64, device=device)
         self.point2voxel = _empty(n, torch.int32, device) if want_point2voxel else None
-        self.idx_sorted = _empty(n, torch.int32, device)
         row_sorted = _empty(n, torch.int32, device) if (want_point2voxel and not dense_p2v) else None
+        if row_sorted is not None:
+            self._idx_sorted = _empty(n, torch.int32, device)
         L.call("vapc_reduce_moments", _ptr(self.keys_sorted), _ptr(self.pos_sorted), n, C.byref(g), _ptr(self.xyzw), V,
                _ptr(self.voxel_keys), _ptr(self.start), _ptr(self.count), _ptr(self.first_idx), _ptr(self.mean3), _ptr(self.m2),
-               _ptr(row_sorted), _ptr(self.idx_sorted), _ptr(self._seg_ws), ws_bytes, _stream())
+               _ptr(row_sorted), _ptr(self._idx_sorted), _ptr(self._seg_ws), ws_bytes, _stream())
         if row_sorted is not None:
             # (index, row) pairs grouped by the leading byte of the index, then scattered inside L2-sized windows
             nbits = max(1, int(n - 1).bit_length())
-            grouped_idx, grouped_row = sort_pairs(self.idx_sorted, nbits, idx=row_sorted, preserve_keys=True, begin_bit=max(0, nbits - 8))
+            grouped_idx, grouped_row = sort_pairs(self._idx_sorted, nbits, idx=row_sorted, preserve_keys=True, begin_bit=max(0, nbits - 8))
             L.call("vapc_scatter_u32", _ptr(grouped_idx), _ptr(grouped_row), n, _ptr(self.point2voxel), _stream())
             del grouped_idx, grouped_row, row_sorted
         if dense_p2v:
@@ -366,6 +391,15 @@ class VoxelCloud:
     @property
     def device(self):
         return self.voxel_keys.device
+
+    @property
+    def idx_sorted(self):
+        """Original index of every sorted position (int32 storage of uint32).  Only the per-attribute statistics and the grouped
+        point->voxel scatter read it, so it is formed on first use from the records (4 B/point written) instead of by every build."""
+        if self._idx_sorted is None:
+            self._idx_sorted = _empty(self.n, torch.int32, self.device)
+            L.call("vapc_record_indices", _ptr(self.xyzw), _ptr(self.pos_sorted), self.n, _ptr(self._idx_sorted), _stream())
+        return self._idx_sorted
 
     # ------------------------------------------------------------------------------------
     def stats(self, density=False, cog=False, std=False, cov=False, eig=False, eig_n=False, feat=False) -> VoxelStats:
@@ -512,18 +546,18 @@ def attribute_statistics(cloud: VoxelCloud, attr, median=True) -> Dict[str, torc
     return out
 
 
-def lexsort_unique_rows(x, y, z, device=None) -> np.ndarray:
+def lexsort_unique_rows(x, y, z, device=None, as_tensor=False):
     """Row numbers that `df.drop_duplicates(subset=[X, Y, Z])` followed by `df.groupby([X, Y, Z]).<agg>()` visits, in the
     order of the result (vapc.py:1208-1209): rows sorted lexicographically by (X, Y, Z), of rows with identical coordinates only
     the first (lowest row number), rows with a NaN coordinate dropped.  Three stable 64-bit radix sorts on the GPU (Z, then
-    Y, then X) instead of pandas' hash + sort on the host."""
+    Y, then X) instead of pandas' hash + sort on the host.  as_tensor: the rows as an int64 device tensor instead of a host array."""
     _require_cuda()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     cols = [_dev_f64(a, device) + 0.0 for a in (x, y, z)]  # + 0.0: -0.0 and 0.0 are one group, as in pandas
     n = cols[0].numel()
     if n == 0:
-        return np.zeros(0, dtype=np.int64)
+        return torch.zeros(0, dtype=torch.int64, device=device) if as_tensor else np.zeros(0, dtype=np.int64)
     order = None
     for c in reversed(cols):
         keys = _empty(n, torch.int64, device)
@@ -535,7 +569,7 @@ def lexsort_unique_rows(x, y, z, device=None) -> np.ndarray:
     keep = torch.ones(n, dtype=torch.bool, device=device)
     keep[1:] = (sx[1:] != sx[:-1]) | (sy[1:] != sy[:-1]) | (sz[1:] != sz[:-1])
     keep &= ~(torch.isnan(sx) | torch.isnan(sy) | torch.isnan(sz))
-    return rows[keep].cpu().numpy()
+    return rows[keep] if as_tensor else rows[keep].cpu().numpy()
 
 
 # ----------------------------------------------------------------------------------------

@@ -27,26 +27,32 @@ from . import engine as E
 STAT_NAMES = ("density", "cog", "std", "cov", "eig", "eig_n", "feat")
 
 
-def full_statistics(dx, dy, dz, voxel_size, origin, las=None) -> Dict[str, torch.Tensor]:
+def full_statistics(dx, dy, dz, voxel_size, origin, las=None, bounds=None, columns=STAT_NAMES) -> Dict[str, torch.Tensor]:
     """The whole single-GPU hot path on device columns -> dict of device tensors (the voxel table).  las = (scales, offsets):
-    dx, dy, dz are int32 LAS coordinates."""
+    dx, dy, dz are int32 LAS coordinates.  bounds: [min x, min y, min z, max x, max y, max z] when the caller knows them (a LAS
+    header does): the bounding-box pass over the coordinates is skipped.  columns: the statistics to compute and return."""
     if las is not None:
-        c = E.VoxelCloud.build(None, None, None, voxel_size, origin, keep_columns=False, las=(dx, dy, dz, las[0], las[1]))
+        c = E.VoxelCloud.build(None, None, None, voxel_size, origin, keep_columns=False, las=(dx, dy, dz, las[0], las[1]), bounds=bounds)
     else:
-        c = E.VoxelCloud.build(dx, dy, dz, voxel_size, origin, keep_columns=False)
-    s = c.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+        c = E.VoxelCloud.build(dx, dy, dz, voxel_size, origin, keep_columns=False, bounds=bounds)
+    s = c.stats(**{k: True for k in columns})
     out = {"voxel_keys": c.voxel_keys, "count": c.count}
-    out.update({k: getattr(s, k) for k in STAT_NAMES})
+    out.update({k: getattr(s, k) for k in columns})
     out["_grid"] = c.grid
     return out
 
 
 class HostStreamPipeline:
-    def __init__(self, voxel_size, origin, device=None, compute_fn: Optional[Callable] = None, depth: int = 2, las=None):
+    def __init__(self, voxel_size, origin, device=None, compute_fn: Optional[Callable] = None, depth: int = 2, las=None, bounds=None,
+                 columns=STAT_NAMES):
+        """las = (scales, offsets): the clouds are int32 LAS coordinates.  bounds: coordinate bounds valid for every cloud of the
+        run (the header of the LAS file the clouds are chunks of).  columns: which statistics come back (every column costs PCIe time:
+        the full table is 224 B per voxel)."""
         E._require_cuda()
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.voxel_size, self.origin = voxel_size, list(origin)
-        self.compute_fn = compute_fn or (lambda x, y, z: full_statistics(x, y, z, self.voxel_size, self.origin, las=las))
+        self.compute_fn = compute_fn or (lambda x, y, z: full_statistics(x, y, z, self.voxel_size, self.origin, las=las, bounds=bounds,
+                                                                         columns=columns))
         self.depth = depth
         self.s_in = torch.cuda.Stream(self.device)
         self.s_compute = torch.cuda.Stream(self.device)

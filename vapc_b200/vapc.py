@@ -2,13 +2,20 @@
 B200 engine.
 
 Same constructor, attributes, state flags, method names and DataFrame column names as the
-reference; `self.df` stays a host pandas DataFrame (callers read and assign it directly,
-tests/test_voxel.py:82-83) while every per-point computation runs on the GPU through
-`vapc_b200.engine` (C ABI calls) and only the resulting columns are copied back.
+reference; `self.df` is a host pandas DataFrame whenever a caller looks at it (callers read and
+assign it directly, tests/test_voxel.py:82-83) while every per-point computation runs on the GPU
+through `vapc_b200.engine` (C ABI calls).
+
+The reference materialises every per-voxel value per point (16+ float64 columns x N rows).
+Here a computed column stays on the device as its [V] voxel column + the point -> voxel map until somebody
+reads `.df`: the `df` property then broadcasts the pending columns into the frame, in the reference's
+column order.  `compute_requested_attributes()` followed by `reduce_to_voxels()` — what the command-line
+tools do — never builds the N-row columns at all: the reduced frame is formed from the V-row table.
+A caller that has been handed the frame may edit it in place, so every read of `.df` also drops the device
+copy of the cloud; it is rebuilt from the frame's X, Y, Z on the next computation.
 
 Host-side work is limited to what the DataFrame container itself requires (adding / dropping /
-reordering columns, row selection with a mask computed on the GPU, and — on the V-row reduced
-frame only — the reference's final `drop_duplicates` + `groupby(XYZ).median()` formatting).
+reordering columns, row selection with a mask computed on the GPU, the voxel MultiIndex).
 """
 from __future__ import annotations
 
@@ -60,7 +67,11 @@ class Vapc:
         if not isinstance(self.origin, list) or len(self.origin) != 3:
             raise ValueError("origin must be a list of three coordinates [x, y, z].")
         self.AVAILABLE_COMPUTATIONS = list(Vapc.AVAILABLE_COMPUTATIONS)
-        self.df = None
+        self._df = None      # the host frame: original columns + whatever has been materialised
+        self._lazy = {}      # column name -> (kind, device tensor, cloud); kind "voxel": [V] column to broadcast, "point": [N] column
+        self._cols = None    # logical column order (frame columns + pending ones), None = the frame's own
+        self._exposed = True  # a caller holds the frame (and may have edited it) since the cloud was built
+        self._pinned = {}    # (dtype, device index) -> reusable pinned staging buffer of THIS object
         self.original_attributes = None
         # state flags of the lazy-dependency protocol (vapc.py:90-110)
         self.attributes_up_to_data = False
@@ -89,89 +100,148 @@ class Vapc:
         self.closest_ties = "all"
         self._cloud = None
         self._cloud_sig = None
-        # name -> ([V] device column, cloud it belongs to): per-voxel columns this class broadcast into the frame itself;
-        # reduce_to_voxels takes them from the device instead of gathering N-row host columns
-        self._voxel_cols = {}
+
+    # ------------------------------------------------------------------------------------
+    # the frame: host columns + columns still pending on the device
+    # ------------------------------------------------------------------------------------
+    @property
+    def df(self):
+        """The per-point (or reduced) pandas DataFrame, every computed column present.  Reading it hands the frame to the caller:
+        pending device columns are broadcast into it first, and the device copy of the cloud is dropped afterwards (the caller may
+        edit the frame in place; the next computation re-reads X, Y, Z)."""
+        if self._df is not None:
+            self._materialise()
+            self._exposed = True
+        return self._df
+
+    @df.setter
+    def df(self, value):
+        self._df = value
+        self._lazy = {}
+        self._cols = None
+        self._cloud = None
+        self._exposed = True
+
+    def _columns(self):
+        return list(self._df.columns) if self._cols is None else list(self._cols)
+
+    def _has(self, name):
+        return name in self._lazy or (self._df is not None and name in self._df.columns)
+
+    def _add_lazy(self, name, kind, tensor, cloud):
+        if self._cols is None:
+            self._cols = list(self._df.columns)
+        if name not in self._cols:
+            self._cols.append(name)
+        self._lazy[name] = (kind, tensor, cloud)
+
+    def _lazy_host(self, name) -> np.ndarray:
+        """A pending column as a fresh host array of N rows."""
+        kind, t, cloud = self._lazy[name]
+        if kind == "voxel":
+            if t.dtype in (torch.float64, torch.int32):
+                t = cloud.broadcast(t.contiguous())
+            else:
+                t = t[_u32(cloud.point2voxel)]
+        return self._host(t).copy()
+
+    def _materialise(self, only=None):
+        """Broadcast pending columns (all, or the named ones) into the host frame, keeping the logical column order."""
+        if not self._lazy:
+            if self._cols is not None and list(self._df.columns) == self._cols:
+                self._cols = None
+            return
+        names = [c for c in self._cols if c in self._lazy and (only is None or c in only)]
+        if not names:
+            return
+        new = {c: self._lazy_host(c) for c in names}
+        fresh = [c for c in names if c not in self._df.columns]
+        for c in names:
+            if c not in fresh:
+                self._df[c] = new[c]
+        if fresh:
+            # one concat instead of one frame insertion per column (39 of them for the full attribute set)
+            add = pd.DataFrame({c: new[c] for c in fresh}, index=self._df.index, copy=False)
+            self._df = pd.concat([self._df, add], axis=1, copy=False)
+        for c in names:
+            del self._lazy[c]
+        if not self._lazy:
+            if list(self._df.columns) != self._cols:
+                self._df = self._df[self._cols]
+            self._cols = None
+        self._resign()  # same points, possibly a new frame object
+
+    def _host_column(self, name, dtype=None) -> np.ndarray:
+        """Column `name` as a host array whether it is pending or in the frame."""
+        if name in self._lazy:
+            a = self._lazy_host(name)
+        else:
+            a = self._df[name].to_numpy()
+        return a if dtype is None else np.asarray(a, dtype=dtype)
+
+    def _assign_host(self, name, array):
+        """A host-computed column into the frame (and into the logical order while other columns are pending)."""
+        self._lazy.pop(name, None)
+        self._df[name] = array
+        if self._cols is not None and name not in self._cols:
+            self._cols.append(name)
+
+    def _drop_device_state(self):
+        """The frame's rows or coordinates changed: pending columns and the device cloud no longer describe it."""
+        self._lazy = {}
+        self._cols = None
+        self._cloud = None
 
     # ------------------------------------------------------------------------------------
     # device cloud cache
     # ------------------------------------------------------------------------------------
     def _signature(self):
-        x = self.df["X"].to_numpy()
-        n = len(x)
-        sig = [id(self.df), n, float(self.voxel_size), tuple(float(o) for o in self.origin)]
-        for c in ("X", "Y", "Z"):
-            a = self.df[c].to_numpy()
-            sig.append(a.__array_interface__["data"][0])
-            if n:
-                sig += [float(a[0]), float(a[n // 2]), float(a[-1])]
-        return tuple(sig)
+        return (id(self._df), len(self._df), float(self.voxel_size), tuple(float(o) for o in self.origin))
 
     def _get_cloud(self) -> E.VoxelCloud:
-        """The device-side voxelisation of the current X, Y, Z columns (rebuilt when they change)."""
-        if self.df is None:
+        """The device-side voxelisation of the frame's X, Y, Z columns.  Rebuilt when the frame was handed out since the last
+        build (the caller may have edited it), was replaced, or voxel_size / origin changed."""
+        if self._df is None:
             raise AttributeError("no point cloud loaded: assign `df` or call get_data_from_data_handler()")
         sig = self._signature()
-        if self._cloud is None or sig != self._cloud_sig:
-            self._voxel_cols = {}
-            self._cloud = E.VoxelCloud.build(self.df["X"].to_numpy(np.float64), self.df["Y"].to_numpy(np.float64),
-                                             self.df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
-            self._cloud_sig = sig
+        if self._cloud is None or self._exposed or sig != self._cloud_sig:
+            self._materialise()  # pending columns belong to the old cloud
+            self._cloud = E.VoxelCloud.build(self._df["X"].to_numpy(np.float64), self._df["Y"].to_numpy(np.float64),
+                                             self._df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
+            self._cloud_sig = self._signature()
+            self._exposed = False
         return self._cloud
 
     def _resign(self):
-        """Re-take the cache signature after this class itself touched the frame (added columns)."""
-        if self._cloud is not None:
-            self._cloud_sig = self._signature()
-
-    def _per_point(self, voxel_column: torch.Tensor) -> np.ndarray:
-        """Broadcast a [V] voxel column to the points on the device, copy the result to the host."""
-        return self._host(self._get_cloud().broadcast(voxel_column.contiguous())).copy()
+        """Re-take the cache signature after this class itself replaced the frame object (reset_index, reordering)."""
+        if self._cloud is not None and self._cloud_sig is not None:
+            self._cloud_sig = (id(self._df), len(self._df)) + tuple(self._cloud_sig[2:])  # grid parameters as they were at build time
 
     def _set_per_point(self, name: str, voxel_column: torch.Tensor):
-        """df[name] = the [V] voxel column broadcast to the points."""
-        cloud = self._get_cloud()
-        self._set_col(name, cloud.broadcast(voxel_column.contiguous()))
-        self._voxel_cols[name] = (voxel_column, cloud)
-
-    def _voxel_column(self, name: str, cloud, probe_rows: np.ndarray, probe_voxels: torch.Tensor):
-        """The [V] device column behind the per-point frame column `name`, if this class put it there for `cloud` and the
-        frame still shows it (a few probed rows are compared bit for bit: callers own `df` and may have rewritten it)."""
-        hit = self._voxel_cols.get(name)
-        if hit is None or hit[1] is not cloud or cloud is None:
-            return None
-        col = hit[0]
-        if col.dtype != torch.float64 or col.numel() != cloud.nvoxels:
-            return None
-        a = self.df[name].to_numpy()
-        if a.dtype != np.float64 or len(a) != cloud.n:
-            return None
-        want = col[probe_voxels].cpu().numpy()
-        if not np.array_equal(a[probe_rows].view(np.int64), want.view(np.int64)):
-            return None
-        return col
-
-    _pinned = {}  # (dtype, device index) -> reusable pinned staging buffer
-
-    def _host(self, t: torch.Tensor) -> np.ndarray:
-        """Device column -> fresh host array through a reusable pinned staging buffer (a pageable copy of an 80 MB column
-        runs at ~2.5 GB/s, the pinned one at PCIe speed)."""
-        key = (t.dtype, t.device.index)
-        buf = Vapc._pinned.get(key)
-        if buf is None or buf.numel() < t.numel():
-            buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
-            Vapc._pinned[key] = buf
-        view = buf[: t.numel()]
-        view.copy_(t, non_blocking=False)
-        return view.numpy()  # a view of the staging buffer: valid until the next _host call
+        """Column `name` = the [V] voxel column broadcast to the points (pending until `.df` is read)."""
+        self._add_lazy(name, "voxel", voxel_column, self._get_cloud())
 
     def _set_col(self, name: str, t: torch.Tensor):
-        """df[name] = device column.  pandas copies an array that is assigned as a column; should a version ever keep a view,
-        the staging buffer must not be handed out."""
-        staged = self._host(t)
-        self.df[name] = staged
-        if len(staged) and np.may_share_memory(self.df[name].to_numpy(), staged):
-            self.df[name] = staged.copy()
+        """Column `name` = an [N] device column (pending until `.df` is read)."""
+        self._add_lazy(name, "point", t, self._get_cloud())
+
+    def _host(self, t: torch.Tensor) -> np.ndarray:
+        """Device column -> host array through a reusable pinned staging buffer of this object (a pageable copy of an 80 MB column
+        runs at ~2.5 GB/s, the pinned one at PCIe speed).  The result is a view of the staging buffer: valid until the next call."""
+        key = (t.dtype, t.device.index)
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < t.numel():
+            buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+            self._pinned[key] = buf
+        view = buf[: t.numel()]
+        view.copy_(t.contiguous(), non_blocking=False)
+        return view.numpy()
+
+    def release(self):
+        """Free the pinned staging buffers and the device copy of the cloud (they are re-created on demand)."""
+        self._materialise() if self._df is not None else None
+        self._pinned = {}
+        self._cloud = None
 
     def _validate_compute_list(self):
         invalid = [c for c in self.compute if c not in self.AVAILABLE_COMPUTATIONS]
@@ -188,7 +258,7 @@ class Vapc:
             raise AttributeError("The provided data_handler does not have a 'df' attribute.")
         self.df = data_handler.df
         data_handler.df = None
-        self.original_attributes = self.df.columns.tolist()
+        self.original_attributes = self._df.columns.tolist()
 
     @trace
     @timeit
@@ -196,7 +266,7 @@ class Vapc:
         """[int(min X), int(min Y), int(min Z)] (vapc.py:153-162); the minima come from the GPU bbox kernel."""
         dev = torch.device("cuda", torch.cuda.current_device())
         E._require_cuda()
-        cols = [E._dev_f64(self.df[c].to_numpy(np.float64), dev) for c in ("X", "Y", "Z")]
+        cols = [E._dev_f64(self._df[c].to_numpy(np.float64), dev) for c in ("X", "Y", "Z")]
         mm = E.coordinate_bounds(*cols)
         self.reduction_point = [int(mm[0]), int(mm[1]), int(mm[2])]
 
@@ -207,20 +277,28 @@ class Vapc:
         if self.reduction_point is None:
             self.compute_reduction_point()
         sign = 1 if self.offset_applied else -1
+        self._materialise()
         for c, r in zip(("X", "Y", "Z"), self.reduction_point):
-            self.df[c] = self.df[c] + sign * r
+            self._df[c] = self._df[c] + sign * r
+        self._drop_device_state()  # the coordinates changed
         self.offset_applied = not self.offset_applied
+
+    def _voxelize(self):
+        """voxel_x / voxel_y / voxel_z = floor((coord - origin) / voxel_size) as int64 (vapc.py:188-207): the voxel table's triples
+        broadcast to the points (pending until `.df` is read)."""
+        cloud = self._get_cloud()
+        for name, col in zip(("voxel_x", "voxel_y", "voxel_z"), cloud.voxel_coords()):
+            self._add_lazy(name, "voxel", col, cloud)
+        self._voxelized_cloud = cloud
+        self.voxelized = True
 
     @trace
     @timeit
     def voxelize(self):
-        """voxel_x / voxel_y / voxel_z = floor((coord - origin) / voxel_size) as int64 (vapc.py:188-207)."""
-        vx, vy, vz = E.voxel_coords(self.df["X"].to_numpy(np.float64), self.df["Y"].to_numpy(np.float64),
-                                    self.df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
-        for name, col in zip(("voxel_x", "voxel_y", "voxel_z"), (vx, vy, vz)):
-            self._set_col(name, col)
-        self.voxelized = True
-        self._resign()
+        """voxel_x / voxel_y / voxel_z = floor((coord - origin) / voxel_size) as int64; returns the frame like the reference
+        (vapc.py:188-207)."""
+        self._voxelize()
+        return self.df
 
     @trace
     @timeit
@@ -263,12 +341,12 @@ class Vapc:
             print("No attributes specified for computation. Skipping.")
             return
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         if not self.attributes_up_to_data:
             self.update_attribute_dictionary()
         required = ["voxel_x", "voxel_y", "voxel_z"] + list(self.attributes.keys())
-        missing = [c for c in required if c not in self.df.columns]
+        missing = [c for c in required if not self._has(c)]
         if missing:
             raise KeyError(f"Missing columns in `self.df`: {missing}")
         cloud = self._get_cloud()
@@ -276,7 +354,7 @@ class Vapc:
         for attr, stats_list in self.attributes.items():
             if not isinstance(stats_list, list):
                 stats_list = [stats_list]
-            values = self.df[attr].to_numpy(np.float64)
+            values = self._host_column(attr, np.float64)
             thresholds, want_mode = [], False
             for stat in stats_list:
                 if stat == "mode":
@@ -304,20 +382,16 @@ class Vapc:
                     new_cols[col] = count_res[dict(thresholds)[stat]]
                 elif stat in ("mean", "std", "var", "median", "min", "max", "sum"):
                     if simple is None:
-                        simple = E.attribute_statistics(cloud, values)
+                        simple = E.attribute_statistics(cloud, values, median="median" in stats_list)
                     new_cols[col] = simple[stat]
                 else:
                     print(f"Unknown aggregation type '{stat}' for attribute '{attr}'. Skipping.")
         # the reference merges the aggregated frame back with how="left" (index reset, vapc.py:468-470)
-        self.df = self.df.reset_index(drop=True)
+        self._df = self._df.reset_index(drop=True)
         self._resign()  # same points in a new frame object: keep the device cloud
-        p2v = _u32(cloud.point2voxel)
         for col, table in new_cols.items():
-            self.df[col] = table[p2v].cpu().numpy()
-            if table.dtype == torch.float64:
-                self._voxel_cols[col] = (table, cloud)
+            self._add_lazy(col, "voxel", table, cloud)
         self.attributes_per_voxel = True
-        self._cloud_sig = self._signature()
 
     # ------------------------------------------------------------------------------------
     @trace
@@ -327,10 +401,11 @@ class Vapc:
         if self.voxel_index:
             return
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
-        self.df.set_index(["voxel_x", "voxel_y", "voxel_z"], inplace=True, drop=False)
-        self.df.index.set_names(["idx_voxel_x", "idx_voxel_y", "idx_voxel_z"], inplace=True)
+        self._materialise(only=("voxel_x", "voxel_y", "voxel_z"))  # the MultiIndex lives in the frame
+        self._df.set_index(["voxel_x", "voxel_y", "voxel_z"], inplace=True, drop=False)
+        self._df.index.set_names(["idx_voxel_x", "idx_voxel_y", "idx_voxel_z"], inplace=True)
         self.voxel_index = True
         self._resign()
 
@@ -341,72 +416,123 @@ class Vapc:
         first-occurrence order; overwrites `self.df` with that mask frame and returns it
         (vapc.py:495-541, including its X/Y/Z = (v + vs/2) * vs quirk)."""
         if not self.voxelized:
-            self.voxelize()
-        v = [self.df[c].to_numpy(np.int64) for c in ("voxel_x", "voxel_y", "voxel_z")]
-        uniq = E.unique_voxels_first_occurrence(*v)
+            self._voxelize()
+        if all(c in self._lazy for c in ("voxel_x", "voxel_y", "voxel_z")):
+            # the voxel table IS the unique triples; first-occurrence order = ascending first point index
+            cloud = self._lazy["voxel_x"][2]
+            order = torch.argsort(_u32(cloud.first_idx))
+            uniq = [c[order] for c in cloud.voxel_coords()]
+        else:
+            uniq = E.unique_voxels_first_occurrence(*[self._host_column(c, np.int64) for c in ("voxel_x", "voxel_y", "voxel_z")])
         expanded = E.buffer_expand(uniq[0], uniq[1], uniq[2], int(buffer_size))
         buf = E.unique_voxels_first_occurrence(expanded[0], expanded[1], expanded[2])
         self.df = pd.DataFrame({n: c.cpu().numpy() for n, c in zip(("voxel_x", "voxel_y", "voxel_z"), buf)})
         self.voxelized = True
         self.voxel_index = False
         self.compute_voxel_index()
-        self.df["Y"] = (self.df["voxel_y"] + self.voxel_size / 2) * self.voxel_size
-        self.df["Z"] = (self.df["voxel_z"] + self.voxel_size / 2) * self.voxel_size
-        self.df["X"] = (self.df["voxel_x"] + self.voxel_size / 2) * self.voxel_size
-        self.buffer_df = self.df
-        self._cloud = None
-        self._voxel_cols = {}
-        return self.df
+        self._df["Y"] = (self._df["voxel_y"] + self.voxel_size / 2) * self.voxel_size
+        self._df["Z"] = (self._df["voxel_z"] + self.voxel_size / 2) * self.voxel_size
+        self._df["X"] = (self._df["voxel_x"] + self.voxel_size / 2) * self.voxel_size
+        self.buffer_df = self._df
+        self._drop_device_state()
+        return self._df
+
+    def _cloud_if_current(self):
+        """The device cloud if it still describes the frame (not handed out, not replaced, same grid), else None."""
+        if self._cloud is None or self._exposed or self._df is None or self._signature() != self._cloud_sig:
+            return None
+        return self._cloud
+
+    def _own_voxel_cloud(self):
+        """The device cloud if the frame's voxel_x / voxel_y / voxel_z are its own voxelisation (set by this class, frame not
+        handed out since): per-voxel answers can then be formed on the V-row table and broadcast."""
+        cloud = self._cloud_if_current()
+        return cloud if cloud is not None and getattr(self, "_voxelized_cloud", None) is cloud else None
 
     def _mask_voxels(self, vapc_mask):
-        if self.df is None or vapc_mask.df is None:
+        if self._df is None or vapc_mask._df is None:
             raise AttributeError("Both `self.df` and `vapc_mask.df` must exist.")
         if self.voxelized is False:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         if vapc_mask.voxelized is False:
-            vapc_mask.voxelize()
+            vapc_mask._voxelize()
         if vapc_mask.voxel_index is False:
             vapc_mask.compute_voxel_index()
         if self.voxel_index is False:
             self.compute_voxel_index()
-        idx = vapc_mask.df.index
+        idx = vapc_mask._df.index
         return [np.asarray(idx.get_level_values(k), dtype=np.int64) for k in range(3)]
+
+    def _per_point_of_voxels(self, cloud, voxel_values: torch.Tensor) -> np.ndarray:
+        """[V] int32 device values -> host array of N rows (broadcast through the point -> voxel map)."""
+        return self._host(cloud.broadcast(voxel_values.to(torch.int32).contiguous())).copy()
 
     @trace
     @timeit
     def select_by_mask(self, vapc_mask, segment_in_or_out="in"):
         """Keep ("in") or remove ("out") the points whose voxel triple is in the mask's voxel set
-        (vapc.py:545-609).  Membership is a GPU hash-set probe; original order is kept, the voxel
-        columns are dropped afterwards and `voxelized` is reset, as in the reference."""
+        (vapc.py:545-609).  Membership is a GPU hash-set probe — of the V voxel rows when the voxel columns are this object's own
+        voxelisation, else of the frame's index; original order is kept, the voxel columns are dropped afterwards and
+        `voxelized` is reset, as in the reference."""
         mv = self._mask_voxels(vapc_mask)
         if segment_in_or_out not in ("in", "out"):
             raise ValueError("Parameter 'segment_in_or_out' must be either 'in' or 'out'.")
         mask = E.VoxelMask(mv[0], mv[1], mv[2], float(self.voxel_size), self.origin)
-        own = [np.asarray(self.df.index.get_level_values(k), dtype=np.int64) for k in range(3)]
-        member = mask.contains_voxels(*own).cpu().numpy().astype(bool)
-        self.df = self.df.loc[member if segment_in_or_out == "in" else ~member]
+        cloud = self._own_voxel_cloud()
+        if cloud is not None:
+            member = self._per_point_of_voxels(cloud, mask.contains_voxels(*cloud.voxel_coords())).astype(bool)
+        else:
+            own = [np.asarray(self._df.index.get_level_values(k), dtype=np.int64) for k in range(3)]
+            member = mask.contains_voxels(*own).cpu().numpy().astype(bool)
+        self._materialise()
+        frame = self._df.loc[member if segment_in_or_out == "in" else ~member]
         for attr in ["voxel_x", "voxel_y", "voxel_z"]:
-            if attr in self.df.columns:
-                self.df = self.df.drop([attr], axis=1)
+            if attr in frame.columns:
+                frame = frame.drop([attr], axis=1)
+        self._df = frame
         self.voxelized = False
-        self._cloud = None
-        self._voxel_cols = {}
+        self._drop_device_state()
 
     @trace
     @timeit
     def label_by_mask(self, vapc_mask, label_attributes=["voxel_x", "voxel_y", "voxel_z"]):
-        """Left-join selected mask columns onto the points by voxel triple (vapc.py:614-677)."""
+        """Left-join selected mask columns onto the points by voxel triple (vapc.py:614-677).  With a mask of unique voxels the
+        join runs on the GPU: sorted-key join of the two voxel tables -> mask row of every voxel -> broadcast to the points; the
+        mask's columns are then gathered by that row (NaN where the voxel is not in the mask, as the left join gives).  A mask
+        with repeated voxels multiplies rows in the reference: that case goes through pandas' own join."""
         self._mask_voxels(vapc_mask)
-        common = [c for c in label_attributes if c in vapc_mask.df.columns]
+        mask_df = vapc_mask._df
+        common = [c for c in label_attributes if c in mask_df.columns]
+        self._materialise(only=("voxel_x", "voxel_y", "voxel_z"))
         if common:
-            self.df = self.df.join(vapc_mask.df[common], how="left")
+            overlap = [c for c in common if self._has(c)]
+            if overlap:  # pandas' join refuses equal column names without a suffix (the reference's default arguments end here)
+                raise ValueError(f"columns overlap but no suffix specified: {pd.Index(overlap)}")
+            cloud = self._own_voxel_cloud()
+            if cloud is not None and mask_df.index.is_unique:
+                mv = [np.asarray(mask_df.index.get_level_values(k), dtype=np.int64) for k in range(3)]
+                dev = cloud.device
+                i1, i2, _, _ = E.join_voxel_tables(cloud.voxel_coords(), [torch.from_numpy(a).to(dev) for a in mv])
+                row_of_voxel = torch.full((cloud.nvoxels,), -1, dtype=torch.int32, device=dev)
+                row_of_voxel[i1] = i2.to(torch.int32)
+                mrow = self._per_point_of_voxels(cloud, row_of_voxel).astype(np.int64)
+                found = mrow >= 0
+                taken = mask_df[common].take(np.where(found, mrow, 0))
+                if not found.all():
+                    taken = taken.where(np.broadcast_to(found[:, None], taken.shape))  # NaN (and the dtype promotion of the join)
+                self._materialise()
+                for c in common:
+                    self._df[c] = taken[c].to_numpy()
+            else:
+                self._materialise()
+                self._df = self._df.join(mask_df[common], how="left")
+        self._materialise()
         for attr in ["voxel_x", "voxel_y", "voxel_z"]:
-            if attr in self.df.columns:
-                self.df = self.df.drop([attr], axis=1)
+            if attr in self._df.columns:
+                self._df = self._df.drop([attr], axis=1)
         self.voxelized = False
-        self._cloud = None
-        self._voxel_cols = {}
+        self._drop_device_state()
 
     # ------------------------------------------------------------------------------------
     @trace
@@ -414,11 +540,10 @@ class Vapc:
     def compute_point_count(self):
         """point_count = points in the point's voxel, int64 (vapc.py:715-726)."""
         if self.voxelized is False:
-            self.voxelize()
+            self._voxelize()
         cloud = self._get_cloud()
-        self._set_col("point_count", _u32(cloud.broadcast(cloud.count)))
+        self._set_per_point("point_count", _u32(cloud.count))
         self.point_count = True
-        self._resign()
 
     @trace
     @timeit
@@ -431,7 +556,6 @@ class Vapc:
         cloud = self._get_cloud()
         self._set_per_point("point_density", cloud.stats(density=True).density)
         self.point_density = True
-        self._resign()
 
     @trace
     @timeit
@@ -449,7 +573,6 @@ class Vapc:
                 self.drop_columns += ["cog_x", "cog_y", "cog_z"]
         self._set_col("distance", self._get_cloud().point_distance())
         self.distance_to_center_of_gravity = True
-        self._resign()
 
     @trace
     @timeit
@@ -467,65 +590,60 @@ class Vapc:
         cloud = self._get_cloud()
         min_dist, argmin = cloud.closest_to_cog()
         self._closest_argmin = _u32(argmin)
-        self.df = self.df.reset_index(drop=True)
+        self._df = self._df.reset_index(drop=True)
         self._resign()  # same points in a new frame object: keep the device cloud
         self._set_per_point("min_distance", min_dist)
         self.closest_to_center_of_gravity = True
-        self._cloud_sig = self._signature()
 
     @trace
     @timeit
     def compute_center_of_gravity(self):
         """cog_x / cog_y / cog_z = per-voxel mean of X, Y, Z (vapc.py:829-852)."""
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         cloud = self._get_cloud()
         cog = cloud.stats(cog=True).cog
         for k, name in enumerate(("cog_x", "cog_y", "cog_z")):
             self._set_per_point(name, cog[k])
         self.center_of_gravity = True
-        self._resign()
 
     @trace
     @timeit
     def compute_std_of_cog(self):
         """std_x / std_y / std_z = per-voxel sample standard deviation, ddof = 1 (vapc.py:856-887)."""
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         cloud = self._get_cloud()
         std = cloud.stats(std=True).std
         for k, name in enumerate(("std_x", "std_y", "std_z")):
             self._set_per_point(name, std[k])
         self.std_of_cog = True
-        self._resign()
 
     @trace
     @timeit
     def compute_center_of_voxel(self):
         """center_* = ((voxel * vs) + vs / 2) + origin (vapc.py:891-907)."""
         if self.voxelized is False:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         center, _ = self._get_cloud().center_corner(center=True, corner=False)
         for k, name in enumerate(("center_x", "center_y", "center_z")):
             self._set_per_point(name, center[k])
         self.center_of_voxel = True
-        self._resign()
 
     @trace
     @timeit
     def compute_corner_of_voxel(self):
         """corner_* = (voxel * vs) + origin (vapc.py:911-925)."""
         if self.voxelized is False:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         _, corner = self._get_cloud().center_corner(center=False, corner=True)
         for k, name in enumerate(("corner_x", "corner_y", "corner_z")):
             self._set_per_point(name, corner[k])
         self.corner_of_voxel = True
-        self._resign()
 
     @trace
     @timeit
@@ -534,17 +652,13 @@ class Vapc:
         single-point voxels.  Sets `covariance_matrix_computed` — like the reference it does NOT set
         the `covariance_matrix` flag."""
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
         cloud = self._get_cloud()
         cov = cloud.stats(cov=True).cov
-        six = [self._per_point(cov[k]) for k in range(6)]
         for name, k in zip(_COV_NAMES, _COV9_FROM6):
-            self.df[name] = six[k]
-            self._voxel_cols[name] = (cov[k], cloud)
-        other = [c for c in self.df.columns if c not in _COV_NAMES]
-        self.df = self.df[_COV_NAMES + other]
+            self._add_lazy(name, "voxel", cov[k], cloud)
+        self._cols = _COV_NAMES + [c for c in self._cols if c not in _COV_NAMES]  # the reference moves them to the front
         self.covariance_matrix_computed = True
-        self._cloud_sig = self._signature()
 
     @trace
     @timeit
@@ -557,12 +671,11 @@ class Vapc:
                 self.drop_columns += list(_COV_NAMES)
         cloud = self._get_cloud()
         eig = cloud.stats(eig=True).eig
-        self.df = self.df.reset_index(drop=True)
+        self._df = self._df.reset_index(drop=True)
         self._resign()  # same points in a new frame object: keep the device cloud
         for k, name in enumerate(("Eigenvalue_1", "Eigenvalue_2", "Eigenvalue_3")):
             self._set_per_point(name, eig[k])
         self.eigenvalues = True
-        self._cloud_sig = self._signature()
 
     @trace
     @timeit
@@ -580,7 +693,6 @@ class Vapc:
         for k, name in enumerate(E.FEATURE_NAMES):
             self._set_per_point(name, st.feat[k])
         self.geometric_features = True
-        self._resign()
 
     # ------------------------------------------------------------------------------------
     @trace
@@ -588,7 +700,7 @@ class Vapc:
     def reduce_to_voxels(self):
         """One row per voxel at the centre / corner / centroid / closest point(s) (vapc.py:1150-1210)."""
         if self.return_at == "center_of_voxel":
-            if self.center_of_voxel is False or not hasattr(self.df, "center_x"):
+            if self.center_of_voxel is False or not self._has("center_x"):
                 self.compute_center_of_voxel()
                 self.drop_columns += ["center_x", "center_y", "center_z"]
             self.new_column_names.update({"X": "center_x", "Y": "center_y", "Z": "center_z"})
@@ -609,69 +721,97 @@ class Vapc:
             if not self.closest_to_center_of_gravity:
                 self.compute_closest_to_center_of_gravity()
                 self.drop_columns += ["min_distance"]
-            if self.closest_ties == "first" and getattr(self, "_closest_argmin", None) is not None:
-                sel = np.sort(_u32(self._closest_argmin).cpu().numpy())
-            else:
-                sel = np.nonzero(self.df["distance"].to_numpy() == self.df["min_distance"].to_numpy())[0]
         else:
             print(f"Voxels cannot be reduced to {self.return_at},\n \
                     try 'center_of_gravity', 'center_of_voxel', 'closest_to_center_of_gravity', or 'corner_of_voxel'")
             return
-        if self.return_at != "closest_to_center_of_gravity":
-            # one row per voxel: its first point (what drop_duplicates(subset=XYZ) keeps, vapc.py:1208);
-            # picking those V rows first is equivalent and avoids formatting N rows
-            cloud = self._get_cloud() if self._cloud is not None and len(self.df) == self._cloud.n else None
-            sel = np.sort(_u32(cloud.first_idx).cpu().numpy()) if cloud is not None else None
-        # From here on the reference works on the frame (vapc.py:1200-1209): copy the new coordinates into X, Y, Z, drop the
-        # helper columns, drop_duplicates(subset=XYZ), groupby(XYZ, as_index=False).median(numeric_only=True).  After the drop
-        # every group is ONE row, so the result is: the first row of each distinct (X, Y, Z), sorted by (X, Y, Z), key columns
-        # first, every other numeric column as float64.  It is built column by column from the selected rows (pandas needed
-        # 8 s for 6e6 voxels x 39 columns), the row order comes from three radix sorts on the GPU.
+        # From here on the reference works on the frame (vapc.py:1195-1209): [closest: keep the rows with distance == min_distance,]
+        # copy the new coordinates into X, Y, Z, drop the helper columns, drop_duplicates(subset=XYZ),
+        # groupby(XYZ, as_index=False).median(numeric_only=True).  After the drop every group is ONE row, so the result is: the first
+        # row of each distinct (X, Y, Z), sorted by (X, Y, Z), key columns first, every other numeric column as float64.  Here:
+        # candidate rows (one per voxel: its first point; or the closest points) -> their X, Y, Z -> three radix sorts on the GPU for
+        # the row order -> every output column gathered for those rows only — from its [V] voxel column on the device when it is
+        # still pending, from the host column otherwise — into one float64 block that the frame wraps without a copy.
         dropped = set(self.drop_columns)
-        missing = [c for c in dropped if c not in self.df.columns]
+        missing = [c for c in dropped if not self._has(c)]
         if missing:
             raise KeyError(f"{missing} not found in axis")
-        def xyz(c):
-            a = self.df[self.new_column_names.get(c, c)].to_numpy(np.float64)
-            return a if sel is None else a[sel]
+        cloud = self._cloud_if_current()
+        n = len(self._df)
+        dev = cloud.device if cloud is not None else torch.device("cuda", torch.cuda.current_device())
+        p2v = _u32(cloud.point2voxel) if cloud is not None else None
 
-        rows = E.lexsort_unique_rows(xyz("X"), xyz("Y"), xyz("Z"))
-        final_np = rows if sel is None else sel[rows]  # source row of every output row
-        final = torch.from_numpy(final_np)
-        names = [c for c in ["X", "Y", "Z"] + [c for c in self.df.columns if c not in ("X", "Y", "Z")] if c not in dropped]
-        keep = []
-        for c in names:
-            src = self.df[self.new_column_names.get(c, c)]
-            if c in ("X", "Y", "Z") or pd.api.types.is_bool_dtype(src.dtype) or pd.api.types.is_numeric_dtype(src.dtype):
-                keep.append(c)
-        # columns this class broadcast from the voxel table come straight from the device ([V] column -> output rows); the
-        # others (original attributes: the value of the voxel's first point) are gathered from the N-row host columns.  All
-        # outputs are float64, written into one block that the frame wraps without the copy pandas makes when it
-        # consolidates 39 separate columns.
-        cloud = self._cloud if self._cloud is not None and len(self.df) == self._cloud.n and self._cloud.point2voxel is not None else None
-        out_voxel = probe_rows = probe_voxels = None
-        if cloud is not None and len(final_np):
-            p2v = _u32(cloud.point2voxel)
-            out_voxel = p2v[final.to(p2v.device)]
-            probe_rows = final_np[np.linspace(0, len(final_np) - 1, num=min(256, len(final_np)), dtype=np.int64)]
-            probe_voxels = p2v[torch.from_numpy(probe_rows).to(p2v.device)]
-        block = np.empty((len(keep), len(final_np)), dtype=np.float64)
-        for i, c in enumerate(keep):
-            srcname = self.new_column_names.get(c, c)
-            vcol = self._voxel_column(srcname, cloud, probe_rows, probe_voxels) if out_voxel is not None else None
-            if vcol is not None:
-                block[i] = self._host(vcol[out_voxel])
-                continue
-            a = np.ascontiguousarray(self.df[srcname].to_numpy())
+        def gather(name, rows_dev, rows_np):
+            """Column `name` at the given point rows: a device tensor when the column is pending, else a host array."""
+            hit = self._lazy.get(name)
+            if hit is not None:
+                kind, t, c = hit
+                return t[_u32(c.point2voxel)[rows_dev]] if kind == "voxel" else t[rows_dev]
+            a = np.ascontiguousarray(self._df[name].to_numpy())
             if a.dtype not in (np.float64, np.float32, np.int64, np.int32, np.int16, np.int8, np.uint8):
                 a = a.astype(np.float64)  # bool, unsigned 16 / 32 / 64 bit: not gatherable through torch
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")  # read-only numpy views are only read here
-                block[i] = torch.from_numpy(a).index_select(0, final).numpy()  # multi-threaded gather
+                return torch.from_numpy(a).index_select(0, rows_np()).numpy()  # multi-threaded gather
+
+        # ---- candidate rows -------------------------------------------------------------------------------------------
+        if self.return_at == "closest_to_center_of_gravity":
+            if self.closest_ties == "first" and getattr(self, "_closest_argmin", None) is not None and cloud is not None:
+                sel = torch.sort(self._closest_argmin.to(dev)).values
+            else:
+                allrows = torch.arange(n, device=dev)
+                d, m = (gather(c, allrows, lambda: torch.arange(n)) for c in ("distance", "min_distance"))
+                d, m = (torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dev) if isinstance(v, np.ndarray) else v for v in (d, m))
+                sel = torch.nonzero(d == m).flatten()
+                del allrows, d, m
+        elif cloud is not None:
+            # one row per voxel: its first point (what drop_duplicates(subset=XYZ) keeps, vapc.py:1208)
+            sel = torch.sort(_u32(cloud.first_idx)).values
+        else:
+            sel = torch.arange(n, device=dev)
+        sel_np_cache = []
+
+        def sel_np():
+            if not sel_np_cache:
+                sel_np_cache.append(sel.cpu())
+            return sel_np_cache[0]
+
+        xyz = []
+        for c in ("X", "Y", "Z"):
+            v = gather(self.new_column_names.get(c, c), sel, sel_np)
+            xyz.append(torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dev) if isinstance(v, np.ndarray) else v.to(torch.float64))
+        rows = E.lexsort_unique_rows(*xyz, device=dev, as_tensor=True)
+        final = sel[rows]  # source row of every output row
+        final_np_cache = []
+
+        def final_np():
+            if not final_np_cache:
+                final_np_cache.append(final.cpu())
+            return final_np_cache[0]
+
+        # ---- output columns -------------------------------------------------------------------------------------------
+        names = [c for c in ["X", "Y", "Z"] + [c for c in self._columns() if c not in ("X", "Y", "Z")] if c not in dropped]
+        keep = []
+        for c in names:
+            src = self.new_column_names.get(c, c)
+            if c in ("X", "Y", "Z") or src in self._lazy:
+                keep.append(c)
+                continue
+            dt = self._df[src].dtype
+            if pd.api.types.is_bool_dtype(dt) or pd.api.types.is_numeric_dtype(dt):
+                keep.append(c)
+        block = np.empty((len(keep), final.numel()), dtype=np.float64)
+        for i, c in enumerate(keep):
+            if c in ("X", "Y", "Z"):
+                v = xyz["XYZ".index(c)][rows]
+            else:
+                v = gather(self.new_column_names.get(c, c), final, final_np)
+            if isinstance(v, np.ndarray):
+                block[i] = v
+            else:
+                torch.from_numpy(block[i]).copy_(v.to(torch.float64))
         self.df = pd.DataFrame(block.T, columns=keep, copy=False)
         self.reduced = True
-        self._cloud = None
-        self._voxel_cols = {}
 
     @trace
     @timeit
@@ -680,23 +820,35 @@ class Vapc:
         valid_strings = ["equal_to", "==", "not_equal_to", "!=", "greater_than", ">", "greater_than_or_equal_to", ">=",
                          "less_than", "<", "less_than_or_equal_to", "<="]
         op = min_max_eq.lower()
-        col = self.df[filter_attribute]  # KeyError on a missing column, as in the reference
-        if op in ["equal_to", "=="]:
-            self.df = self.df[col == filter_value]
-        elif op in ["not_equal_to", "!="]:
-            self.df = self.df[col != filter_value]
-        elif op in ["greater_than", ">"]:
-            self.df = self.df[col > filter_value]
-        elif op in ["greater_than_or_equal_to", ">="]:
-            self.df = self.df[col >= filter_value]
-        elif op in ["less_than", "<"]:
-            self.df = self.df[col < filter_value]
-        elif op in ["less_than_or_equal_to", "<="]:
-            self.df = self.df[col <= filter_value]
-        else:
+        ops = {"equal_to": "eq", "==": "eq", "not_equal_to": "ne", "!=": "ne", "greater_than": "gt", ">": "gt", "greater_than_or_equal_to": "ge",
+               ">=": "ge", "less_than": "lt", "<": "lt", "less_than_or_equal_to": "le", "<=": "le"}
+        if not self._has(filter_attribute):
+            raise KeyError(filter_attribute)  # a missing column, as in the reference
+        if op not in ops:
             raise ValueError(f"Filter invalid, use only one of the following:\n\n{', '.join(valid_strings)}.")
-        self._cloud = None
-        self._voxel_cols = {}
+        hit = self._lazy.get(filter_attribute)
+        numeric = isinstance(filter_value, (int, float, np.integer, np.floating)) and not isinstance(filter_value, (bool, np.bool_))
+        if hit is not None and numeric:
+            # the column is still on the device: compare there ([V] voxel values, or [N] point values), compact every pending column
+            # to the surviving rows on the device and bring only those back
+            kind, t, cloud = hit
+            cond = getattr(torch, ops[op])(t, filter_value)
+            p2v = _u32(cloud.point2voxel)
+            rows = torch.nonzero(cond[p2v] if kind == "voxel" else cond).flatten()
+            frame = self._df.iloc[rows.cpu().numpy()]
+            new = {}
+            for name in self._cols:
+                if name in self._lazy:
+                    k2, t2, c2 = self._lazy[name]
+                    new[name] = self._host(t2[_u32(c2.point2voxel)[rows]] if k2 == "voxel" else t2[rows]).copy()
+            order = list(self._cols)
+            frame = pd.concat([frame, pd.DataFrame(new, index=frame.index, copy=False)], axis=1, copy=False)
+            self._df = frame if list(frame.columns) == order else frame[order]
+        else:
+            self._materialise()
+            col = self._df[filter_attribute]
+            self._df = self._df[getattr(col, ops[op])(filter_value)]
+        self._drop_device_state()
 
     def compute_mode_count(self, attribute: str, percentage: float):
         """Convenience alias named by the north_star: the statistic string "mode_count,<p>" of the
@@ -720,9 +872,13 @@ class Vapc:
         if cluster_by is None:
             cluster_by = ["voxel_x", "voxel_y", "voxel_z"]
         if not self.voxelized:
-            self.voxelize()
+            self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
-        cols = self.df[cluster_by]  # KeyError for unknown columns, like the reference
+        missing = [c for c in cluster_by if not self._has(c)]
+        if missing:
+            raise KeyError(f"{missing} not in index")  # unknown columns, like the reference
+        self._materialise(only=tuple(cluster_by))
+        cols = self._df[cluster_by]
         if not 1 <= cols.shape[1] <= 3:
             raise NotImplementedError("compute_clusters: one to three cluster_by columns")
         dtype0 = cols.dtypes.iloc[0]
@@ -732,8 +888,7 @@ class Vapc:
         label, size, openings = E.cluster_components(*arrays, cluster_distance, integer_rows=integer)
         self.objectCounter = float(openings + 1)
         # np.zeros_like(df[cluster_by[0]]) holds the ids; the sizes come back through a merge (index reset)
-        self.df["cluster_id"] = self._host(label).astype(dtype0)
-        self.df = self.df.reset_index(drop=True)
+        self._assign_host("cluster_id", self._host(label).astype(dtype0))
+        self._df = self._df.reset_index(drop=True)
         self._resign()  # same points in a new frame object: keep the device cloud
-        self.df["cluster_size"] = self._host(size).astype(np.result_type(dtype0, np.int64))
-        self._resign()
+        self._assign_host("cluster_size", self._host(size).astype(np.result_type(dtype0, np.int64)))

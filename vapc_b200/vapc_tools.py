@@ -5,7 +5,9 @@ returns False for an operator outside its list instead of raising (vapc_tools.py
 recognises `.las` / `.ply` outputs (vapc_tools.py:413-419) — so pipelines and notebooks written against the
 reference run unchanged; the per-point work happens in the CUDA library through `Vapc`.
 
-Mesh (OBJ) tools (vapc_tools.py:451-659) are outside the hot-path scope.
+Mesh (OBJ) tools (vapc_tools.py:451-587) are outside the hot-path scope; the point-cloud
+change-detection tools `extract_point_cloud_by_3D_mask_and_label` and `extract_areas_with_change_using_mahalanobis_distance`
+(vapc_tools.py:589-660) are here.
 """
 from __future__ import annotations
 
@@ -154,3 +156,45 @@ def extract_point_cloud_by_3D_mask(scene_file, mask_file, outfile, voxel_size=1,
     vp_scene.select_by_mask(vp_mask, segment_in_or_out=segment_mode)
     dh_scene.df = vp_scene.df
     dh_scene.save_as_las(outfile)
+
+
+def extract_point_cloud_by_3D_mask_and_label(scene_file, mask_file, outfile, voxel_size=1, segment_mode="in", mode="p", skiprows=2):
+    """Points of `scene_file` inside / outside the voxels occupied by `mask_file`, labelled with the mask's change attributes
+    `mahalanobi_significance`, `p_value`, `change_type` (vapc_tools.py:589-622; point-cloud masks only — mesh masks, mode "m", are
+    outside the hot-path scope).  Selection and label join run on the GPU (Vapc.select_by_mask / label_by_mask)."""
+    if mode == "m":
+        raise NotImplementedError("OBJ mesh masks are outside the scope of vapc_b200 (DESIGN.md section 7)")
+    if mode != "p":
+        raise ValueError("mode must be either 'm' or 'p', seperated by '_'")
+    dh_scene = DataHandler(scene_file)
+    dh_scene.load_las_files()
+    vp_mask = point_cloud_to_vapc(mask_file, voxel_size=voxel_size)
+    vp_scene = Vapc(voxel_size)
+    vp_scene.df = dh_scene.df
+    vp_scene.select_by_mask(vp_mask, segment_in_or_out=segment_mode)
+    vp_scene.label_by_mask(vp_mask, ["mahalanobi_significance", "p_value", "change_type"])
+    dh_scene.df = vp_scene.df
+    dh_scene.save_as_las(outfile)
+
+
+def extract_areas_with_change_using_mahalanobis_distance(point_cloud_1_path, point_cloud_2_path, mask_file, point_cloud_out_1_path,
+                                                         point_cloud_out_2_path, voxel_size, alpha_value, delete_mask_file=True):
+    """Two-epoch change detection from file to file (vapc_tools.py:625-660): per-voxel centroid + covariance of both epochs, voxel
+    join, Mahalanobis test, appearing / disappearing voxels; the voxels with change_type >= 1 are written to `mask_file`, and both
+    epochs are clipped to them and labelled (extract_point_cloud_by_3D_mask_and_label).  Returns False (and writes nothing) when no
+    voxel changed; the mask file is kept, like the reference keeps it (its removal is commented out there)."""
+    vapc_1 = point_cloud_to_vapc(point_cloud_file=point_cloud_1_path, voxel_size=voxel_size)
+    vapc_2 = point_cloud_to_vapc(point_cloud_file=point_cloud_2_path, voxel_size=voxel_size)
+    bi_vapc = BiTemporalVapc([vapc_1, vapc_2])
+    bi_vapc.prepare_data_for_mahalanobis_distance()
+    bi_vapc.merge_vapcs_with_same_voxel_index()
+    bi_vapc.compute_mahalanobis_distance(alpha=alpha_value)
+    bi_vapc.compute_voxels_occupied_in_single_epoch()
+    bi_vapc.prepare_data_for_export()
+    bi_vapc.df = bi_vapc.df[(bi_vapc.df["change_type"] >= 1)]
+    if bi_vapc.df.shape[0] == 0:
+        print("No change detected in the area")
+        return False
+    bi_vapc.save_to_las(mask_file)
+    extract_point_cloud_by_3D_mask_and_label(point_cloud_1_path, mask_file, point_cloud_out_1_path, voxel_size)
+    extract_point_cloud_by_3D_mask_and_label(point_cloud_2_path, mask_file, point_cloud_out_2_path, voxel_size)
