@@ -249,6 +249,12 @@ VAPC_API int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, con
                      const double* m2, int64_t nvoxels, const vapc_grid_t* grid_host,
                      double* density, double* cog3, double* std3, double* cov6, double* eig3,
                      double* eign3, double* feat8, void* stream);
+/* The same for a table whose keys and moments live in a PERMUTED axis order (multi-GPU tables: the axis the ranks' chunks are
+ * separated along leads the key, so that contiguous key ranges follow the chunks): axis_order_host[i] = the coordinate axis (0 x, 1 y,
+ * 2 z) that internal axis i stands for.  cog3 / std3 / cov6 are written in x, y, z order; NULL = identity = vapc_voxel_stats. */
+VAPC_API int vapc_voxel_stats_axes(const void* voxel_keys, const uint32_t* count, const double* mean3, const double* m2,
+                          int64_t nvoxels, const vapc_grid_t* grid_host, const int32_t* axis_order_host, double* density,
+                          double* cog3, double* std3, double* cov6, double* eig3, double* eign3, double* feat8, void* stream);
 
 /* ---- a11 centre / corner of voxel (vapc.py:891-925): ((v*vs) + vs/2) + origin and
  * (v*vs) + origin, in the reference's operation order (bit-exact). out: [3][n]. */
@@ -433,6 +439,17 @@ VAPC_API int vapc_merge_partial_rows(const void* keys_sorted, const uint32_t* or
                             int64_t local_first, int64_t n_local, int64_t nvoxels_host, void* voxel_keys,
                             uint32_t* count, double* mean3, double* m2, void* ws, size_t ws_bytes,
                             void* stream);
+/* The owner's merge WITHOUT re-sorting its own rows: own = rows [own_first, own_first + n_own) of the local table (SoA, column stride
+ * own_stride) with their global keys own_keys[n_own]; u = the received rows, already sorted and combined per key (SoA, stride nu,
+ * 64-bit keys; e.g. by vapc_sort_pairs + vapc_merge_partial_rows with n_local = 0).  Both key-sorted, keys unique.  u_new_before
+ * (device int64 [nu + 1]): exclusive prefix of "the own rows do not hold this key".  Output: the merged table of
+ * nvoxels_host = n_own + u_new_before[nu] rows in key order; rows with equal keys are combined with Chan's update (own first).
+ * One pass over the own rows instead of a radix sort of all keys (the rows a rank keeps are the bulk: SURVEY 8(e)). */
+VAPC_API int vapc_merge_sorted_tables(const uint64_t* own_keys, const uint32_t* own_count, const double* own_mean3, const double* own_m2,
+                             int64_t own_stride, int64_t own_first, int64_t n_own, const uint64_t* u_keys,
+                             const uint32_t* u_count, const double* u_mean3, const double* u_m2, int64_t nu,
+                             const int64_t* u_new_before, int32_t key_bytes, int64_t nvoxels_host, void* out_keys,
+                             uint32_t* out_count, double* out_mean3, double* out_m2, void* stream);
 /* Multi-GPU closest-to-centroid: every rank proposes, per partial voxel row, its nearest point to the FINAL
  * centroid; the owner reduces the n candidates (rows[i] = merged voxel row, dist[i] >= 0, idx[i] = global point index >= 0)
  * to the lexicographic minimum (distance, index) per row — the single-GPU tie-break "lowest original index".  Rows without a

@@ -84,6 +84,17 @@ def per_point_outputs(rank, world, dev, pts, rng, vs, origin):
     cnt_pt = D.broadcast_to_points(table, shard, table.count.to(torch.float64)[None, :])[0].cpu().numpy()
     ref_cnt = ref.broadcast(ref.count).cpu().numpy()[a:b]
     assert np.array_equal(cnt_pt.astype(np.int64), ref_cnt.astype(np.int64)), "global point_count per point"
+    # the same per-point outputs with another axis leading the key (z, x, y): results do not depend on the internal order
+    t2, s2, sh2 = D.voxel_statistics(x, y, z, vs, origin, keep_local=True, axis_order=(2, 0, 1))
+    d2 = D.point_distance(t2, sh2, s2.cog).cpu().numpy()
+    assert np.all(np.abs(d2 - ref_pt) <= 1e-9 * ref_pt + 1e-12), "distance to the global centroid, z-leading key"
+    md2, gi2 = D.closest_to_cog(t2, sh2, s2.cog)
+    v2 = gather_cat(torch.stack(t2.voxel_coords()).cpu().numpy())
+    o2 = np.lexsort((v2[2], v2[1], v2[0]))
+    rmd2 = ref.closest_to_cog()[0].cpu().numpy()
+    md2 = gather_cat(md2.cpu().numpy())[o2]
+    assert np.all(np.abs(md2 - rmd2) <= 1e-9 * rmd2 + 1e-12), "min_distance, z-leading key"
+    del t2, s2, sh2
     # closest-to-centroid subsample
     md, gi = D.closest_to_cog(table, shard, st.cog)
     md, gi = gather_cat(md.cpu().numpy()), gather_cat(gi.cpu().numpy())
@@ -92,7 +103,21 @@ def per_point_outputs(rank, world, dev, pts, rng, vs, origin):
     assert len(md) == ref.nvoxels
     assert np.all(np.abs(md - rmd) <= 1e-9 * rmd + 1e-12), "min_distance"
     same = gi == ram
-    assert same.mean() > 0.999, float(same.mean())  # a last-bit centroid difference may flip an exact tie
+    # H5: the winner must lie in the single-GPU run's tied set of its voxel (distance <= min * (1 + 1e-12) + the
+    # rounding scale of a last-bit centroid difference); where the runner-up is clearly farther it must be the same point
+    p2v = (ref.point2voxel.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    full_d = ref.point_distance().cpu().numpy()
+    scale = 8 * np.finfo(np.float64).eps * max(vs, float(np.abs(cloud).max()))
+    rows = np.arange(ref.nvoxels)
+    assert np.array_equal(p2v[gi], rows), "the winner belongs to its voxel"
+    assert np.all(full_d[gi] <= rmd * (1 + 1e-12) + scale), "the winner is in the tied set"
+    far = np.where(full_d <= rmd[p2v] * (1 + 1e-12) + scale, np.inf, full_d)
+    second = np.full(ref.nvoxels, np.inf)
+    np.minimum.at(second, p2v, far)
+    near_count = np.bincount(p2v, weights=(far == np.inf).astype(np.float64), minlength=ref.nvoxels)
+    clear = (near_count == 1) & (second > rmd * (1 + 1e-9) + 1e-12)
+    assert np.array_equal(gi[clear], ram[clear]), "clear winners are identical"
+    near_ties = int((~clear).sum())
     # mode / mode_count of an integer attribute: (voxel, value, count) runs merged at the owners == one GPU, exactly
     cls_all = rng.integers(0, 9, n).astype(np.float64)
     cls_all[cloud[:, 0] > 20] = np.minimum(cls_all[cloud[:, 0] > 20], 3)  # skewed classes in half of the scene
@@ -102,7 +127,7 @@ def per_point_outputs(rank, world, dev, pts, rng, vs, origin):
     for p in (0.1, 0.3):
         assert np.array_equal(gather_cat(counts[p].cpu().numpy()), rcounts[p].cpu().numpy()), f"mode_count,{p}"
     if rank == 0:
-        print(f"[per-point] world={world}: {len(md)} voxels, subsample identical for {int(same.sum())}, "
+        print(f"[per-point] world={world}: {len(md)} voxels, subsample identical for {int(same.sum())} ({near_ties} near-tie voxels), "
               f"partial rows answered by owners: {sum(shard.send_remote)}", flush=True)
 
 
@@ -118,39 +143,55 @@ def main():
     n, vs, origin = 600_000, 0.2, [0.5, -1.0, 0.25]
     pts = np.round(np.concatenate([rng.uniform([-20, -5, 0], [60, 45, 6], (n // 2, 3)),
                                    rng.normal([20, 20, 3], [3, 3, 0.5], (n - n // 2, 3))]), 3)
-    for mode, exchange in (("coherent", "peer"), ("shuffled", "peer"), ("coherent", "nccl")):
-        order = np.argsort(pts[:, 0], kind="stable") if mode == "coherent" else rng.permutation(n)
+    ref = E.VoxelCloud.build(pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), vs, origin)  # single-GPU table of the whole cloud
+    rs = ref.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
+    ref_vox = torch.stack(ref.voxel_coords()).cpu().numpy()
+
+    def close(name, a, b, mode):
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        ok = ~np.isnan(b)
+        scale = np.abs(b[ok]) if name in ("density", "cog") else np.maximum(np.abs(b[ok]), 1e-12)
+        err = np.abs(a[ok] - b[ok])
+        if name in ("cov", "eig", "std"):  # norm-wise per voxel (H1 / H7)
+            big = np.nanmax(np.abs(b), axis=0, keepdims=True) * np.ones_like(b)
+            scale = np.maximum(big[ok], 1e-300)
+        assert np.all(err <= 1e-9 * scale + 1e-18), (mode, name, float(np.max(err / scale)))
+
+    for mode, exchange in (("coherent", "peer"), ("shuffled", "peer"), ("coherent", "nccl"), ("coherent_y", "peer")):
+        if mode == "shuffled":
+            order = rng.permutation(n)
+        else:  # contiguous chunks of the cloud sorted along x — or along y: the key then leads with y (choose_axis_order)
+            order = np.argsort(pts[:, 1 if mode == "coherent_y" else 0], kind="stable")
         chunk = pts[order[rank * n // world:(rank + 1) * n // world]]
         x, y, z = (torch.from_numpy(np.ascontiguousarray(chunk[:, k])).to(dev) for k in range(3))
         table, st = D.voxel_statistics(x, y, z, vs, origin, exchange=exchange)
         assert table.exchange == exchange, f"asked for the {exchange} exchange, got {table.exchange}"
-        # single-GPU reference of the whole cloud on every rank
-        ref = E.VoxelCloud.build(pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), vs, origin)
-        rs = ref.stats(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
-        assert table.grid.total_bits == ref.grid.total_bits and list(table.grid.vmin) == list(ref.grid.vmin)
+        assert table.axis_order == ((1, 0, 2) if mode == "coherent_y" and world > 1 else (0, 1, 2)), table.axis_order
         counts = torch.tensor([table.nvoxels], device=dev)
         allc = [torch.zeros_like(counts) for _ in range(world)]
         dist.all_gather(allc, counts)
         allc = [int(c.item()) for c in allc]
         assert sum(allc) == ref.nvoxels, (allc, ref.nvoxels)
-        lo = sum(allc[:rank])
-        sl = slice(lo, lo + table.nvoxels)
-        assert torch.equal(table.voxel_keys, ref.voxel_keys[sl]), "keys: ranks in rank order = global key order"
-        assert torch.equal(table.count, ref.count[sl]), "counts are exact"
-        for name in ("density", "cog", "std", "cov", "eig", "eig_n", "feat"):
-            a, b = getattr(st, name).cpu().numpy(), getattr(rs, name).cpu().numpy()[..., sl]
-            assert np.array_equal(np.isnan(a), np.isnan(b)), name
-            ok = ~np.isnan(b)
-            scale = np.abs(b[ok]) if name in ("density", "cog") else np.maximum(np.abs(b[ok]), 1e-12)
-            err = np.abs(a[ok] - b[ok])
-            if name in ("cov", "eig", "std"):  # norm-wise per voxel (H1 / H7)
-                big = np.nanmax(np.abs(b), axis=0, keepdims=True) * np.ones_like(b)
-                scale = np.maximum(big[ok], 1e-300)
-            if name in ("eig_n", "feat"):
-                continue  # ratios of noise on rank-deficient voxels; covered through eig
-            assert np.all(err <= 1e-9 * scale + 1e-18), (mode, name, float(np.max(err / scale)))
+        # order-free comparison: every rank's rows by voxel triple against the single-GPU table (lexicographic x, y, z)
+        vox = gather_cat(torch.stack(table.voxel_coords()).cpu().numpy())
+        by_voxel = np.lexsort((vox[2], vox[1], vox[0]))
+        assert np.array_equal(vox[:, by_voxel], ref_vox), "the voxel set"
+        assert np.array_equal(gather_cat(table.count.cpu().numpy())[by_voxel], ref.count.cpu().numpy()), "counts are exact"
+        for name in ("density", "cog", "std", "cov", "eig"):
+            close(name, gather_cat(getattr(st, name).cpu().numpy())[..., by_voxel], getattr(rs, name).cpu().numpy(), mode)
+        if table.axis_order == (0, 1, 2):
+            assert table.grid.total_bits == ref.grid.total_bits and list(table.grid.vmin) == list(ref.grid.vmin)
+            lo = sum(allc[:rank])
+            sl = slice(lo, lo + table.nvoxels)
+            assert torch.equal(table.voxel_keys, ref.voxel_keys[sl]), "keys: ranks in rank order = global key order"
+            assert torch.equal(table.count, ref.count[sl]), "counts are exact"
+        else:
+            sent = torch.tensor([table.partial_rows_sent], device=dev)
+            dist.all_reduce(sent)
+            assert int(sent.item()) < 0.2 * ref.nvoxels, "chunks separated along y keep their rows under a y-leading key"
         if rank == 0:
-            print(f"[{mode}, {exchange}] world={world}: owned voxels {allc}, partial rows sent by rank 0: {table.partial_rows_sent}", flush=True)
+            print(f"[{mode}, {exchange}] world={world}: axis order {table.axis_order}, owned voxels {allc}, partial rows sent by rank 0: "
+                  f"{table.partial_rows_sent}", flush=True)
     two_epoch(rank, world, dev, pts, rng, vs, origin)
     per_point_outputs(rank, world, dev, pts, rng, vs, origin)
     dist.barrier()

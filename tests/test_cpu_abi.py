@@ -205,3 +205,26 @@ def test_facade_argument_validation_matches_reference():
             df = None
         vapc.Vapc(1.0).get_data_from_data_handler(DH())
     assert callable(vapc.enable_trace) and callable(vapc.enable_timeit)
+
+
+def test_histogram_mode_restatement_matches_reference():
+    """vapc_b200.utilities.compute_mode_continuous (the fallback of `mode` for values np.bincount rejects) against the unmodified
+    reference's function (utilities.py:114-159), values and exceptions."""
+    from oracle import ref_harness
+
+    if not ref_harness.available():
+        pytest.skip("reference package not present")
+    ref_harness.import_reference()
+    from vapc.utilities import compute_mode_continuous as ref_mode
+
+    from vapc_b200.utilities import compute_mode_continuous as ours
+
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        d = np.round(rng.normal(-5, 4, rng.integers(5, 300)), 1)
+        assert ours(d) == ref_mode(d)
+    for bad in (np.array([-1.0]), np.array([-2.0, -2.0, -2.0]), np.array([-1.0, np.nan, 3.0])):
+        with pytest.raises(ValueError):
+            ref_mode(bad)
+        with pytest.raises(ValueError):
+            ours(bad)

@@ -215,3 +215,66 @@ def test_plan_exchange_arithmetic_matches_host_planner():
             edges = [0] + [t >> shift for t in thresholds] + [nb]
             for r in range(world):
                 assert out[r * world:(r + 1) * world].tolist() == [int(hist_all[r, a:b].sum()) for a, b in zip(edges[:-1], edges[1:])]
+
+
+# ---- the independent check bench.py --gpus N runs on its sharded table (tools/dist_check.py), world_size 2 over gloo ----------------
+def _check_worker(rank, world, port, ret):
+    from types import SimpleNamespace
+
+    from tools.dist_check import verify_sharded_table
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        n, vs = 30000, 0.5
+        pts = np.round(rng.uniform([0, 0, 0], [20, 12, 3], (n, 3)), 3)
+        mine = pts[rank::world]  # every rank holds points of (almost) every voxel
+        vmin = np.floor(pts.min(0) / vs).astype(np.int64)
+        vmax = np.floor(pts.max(0) / vs).astype(np.int64)
+        bits = [int(int(b - a).bit_length()) for a, b in zip(vmin, vmax)]
+        grid = SimpleNamespace(voxel_size=vs, origin=[0.0, 0.0, 0.0], vmin=vmin.tolist(), bits=bits, total_bits=sum(bits))
+        v = np.floor(pts / vs).astype(np.int64) - vmin
+        key = (v[:, 0] << (bits[1] + bits[2])) | (v[:, 1] << bits[2]) | v[:, 2]
+        uk, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        inv = inv.ravel()
+        threshold = int(uk[len(uk) // 2])
+        sel = (uk < threshold) if rank == 0 else (uk >= threshold)
+        mean = np.stack([np.bincount(inv, weights=pts[:, k], minlength=len(uk)) / cnt for k in range(3)], 1)
+        d = pts - mean[inv]
+        prod = [d[:, a] * d[:, b] for a, b in ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cov = np.stack([np.bincount(inv, weights=p, minlength=len(uk)) / (cnt - 1) for p in prod], 1)
+
+        def table_and_stats(count):
+            t = SimpleNamespace(grid=grid, voxel_keys=torch.from_numpy(uk[sel]), count=torch.from_numpy(count.astype(np.int32)), thresholds=[threshold])
+            s = SimpleNamespace(cog=torch.from_numpy(np.ascontiguousarray(mean[sel].T)), cov=torch.from_numpy(np.ascontiguousarray(cov[sel].T)))
+            return t, s
+
+        x, y, z = (torch.from_numpy(np.ascontiguousarray(mine[:, k])) for k in range(3))
+        good = verify_sharded_table(*table_and_stats(cnt[sel]), x, y, z, sample_rows=500)
+        assert good["ok"], good
+        assert good["voxels"] == len(uk) == good["voxels_torch_unique"] and good["points"] == n
+        wrong = cnt[sel].copy()
+        wrong[len(wrong) // 2] += 1
+        bad = verify_sharded_table(*table_and_stats(wrong), x, y, z, sample_rows=500)
+        assert not bad["ok"] and not bad["points_ok"]
+        t, s = table_and_stats(cnt[sel])
+        t.voxel_keys = t.voxel_keys[:-1]  # a voxel is missing
+        t.count = t.count[:-1]
+        s.cog, s.cov = s.cog[:, :-1], s.cov[:, :-1]
+        bad = verify_sharded_table(t, s, x, y, z, sample_rows=500)
+        assert not bad["ok"] and not bad["key_set_ok"]
+        ret[rank] = good["voxels"]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_table_check_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_check_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world and len(set(ret.values())) == 1

@@ -260,6 +260,33 @@ def test_mode_count_vs_oracle(E):
         cloud.mode_count(attr - 3.0, [0.1])
 
 
+def test_mode_falls_back_to_histogram_mode_per_voxel(E):
+    """vapc.py:407-412: a voxel whose values np.bincount rejects (negative scan angles) gets the Freedman-Diaconis histogram mode
+    (utilities.py:114-159) — that voxel only; the others keep argmax(bincount).  The column then holds floats."""
+    from vapc_b200.utilities import compute_mode_continuous
+
+    rng = np.random.default_rng(12)
+    n = 6000
+    pts = rng.uniform(0, 3, (n, 3))
+    x, y, z = (np.ascontiguousarray(pts[:, k]) for k in range(3))
+    attr = rng.integers(0, 6, n).astype(np.float64)
+    neg = pts[:, 0] < 1.0  # the voxels of the first metre hold negative, spread-out values
+    attr[neg] = np.round(rng.normal(-5.0, 4.0, neg.sum()), 1)
+    cloud = E.VoxelCloud.build(x, y, z, 1.0, [0, 0, 0])
+    g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], 1.0))
+    mode, _ = cloud.mode_count(attr, [], want_mode=True)
+    assert mode.dtype == torch.float64
+    got = _np(mode)
+    for v in range(g.nvoxels):
+        vals = attr[g.order[g.starts[v]:g.starts[v] + g.counts[v]]]
+        if (vals < 0).any():
+            assert got[v] == compute_mode_continuous(vals)
+        else:
+            assert got[v] == np.argmax(np.bincount(vals.astype(int)))
+    with pytest.raises(ValueError):
+        cloud.mode_count(attr, [0.1])  # mode_count has no fallback in the reference (vapc.py:423-428)
+
+
 def test_attribute_statistics_vs_oracle(E):
     x, y, z = make_cloud("uniform", 30000, 6)
     rng = np.random.default_rng(7)
@@ -332,7 +359,7 @@ def test_two_epoch_join_and_mahalanobis_vs_oracle(E):
         well = (cond < 1e2) & (cond2 < 1e2)  # well-conditioned voxels: plain 1e-9-level agreement
         p, pr = _np(res["p_value"]), ref["p_value"]
         assert np.all(np.isnan(p) == np.isnan(pr))
-        assert np.all(np.abs(p[well] - pr[well]) <= 1e-15 + 1e-7 * np.abs(pr[well]))
+        assert np.all(np.abs(p[well] - pr[well]) <= 1e-15 + 1e-9 * np.abs(pr[well])), float(np.max(np.abs(p[well] - pr[well]) / (1e-15 + 1e-9 * np.abs(pr[well]))))
         stable = well & (np.abs(pr - alpha) > 1e-6)
         np.testing.assert_array_equal(_np(res["significance"])[stable], ref["significance"][stable])
         np.testing.assert_array_equal(_np(res["change_type"])[stable], ref["change_type"][stable])

@@ -64,7 +64,7 @@ def check_against_torch(E, x, y, z, vs, full_stats=True):
     first = _u32(cloud.first_idx)
     lowest = torch.full((cnt.numel(),), n, dtype=torch.int64, device=x.device).scatter_reduce_(0, inv, torch.arange(n, device=x.device), reduce="amin")
     assert torch.equal(first, lowest), "first point of a voxel = lowest original index (stable sort)"
-    st = cloud.stats(cog=True, cov=True, eig=True, feat=full_stats)
+    st = cloud.stats(cog=True, std=True, cov=True, eig=True, feat=full_stats)
     scale = torch.stack([c.abs().max() for c in (x, y, z)])[:, None]
     assert bool(((st.cog - cog).abs() <= 1e-9 * scale).all()), "centroid within 1e-9"
     multi = cnt > 1
@@ -77,6 +77,29 @@ def check_against_torch(E, x, y, z, vs, full_stats=True):
     trace = st.cov[0, multi] + st.cov[3, multi] + st.cov[5, multi]
     assert bool(((eig.sum(0) - trace).abs() <= 1e-9 * trace.abs() + 1e-18).all()), "sum of eigenvalues = trace"
     assert bool((eig[0] >= eig[1]).all()) and bool((eig[1] >= eig[2]).all()) and bool((eig[2] >= 0).all())
+    # std (ddof = 1) = sqrt of the covariance diagonal of the independent two-pass result
+    var = torch.stack([cov[0], cov[3], cov[5]])[:, multi]
+    assert bool(((st.std[:, multi] - var.sqrt()).abs() <= 1e-9 * var.sqrt() + 8 * 2.2e-16 * scale).all()), "std within 1e-9"
+    assert bool(torch.isnan(st.std[:, ~multi]).all())
+    # eigenvalues and the 8 features against torch.linalg.eigvalsh of the independent covariance (H7 rules), on a sample of voxels
+    pick = torch.nonzero(multi).flatten()
+    pick = pick[:: max(1, pick.numel() // 1_000_000)]
+    c6 = cov[:, pick]
+    mat = torch.stack([torch.stack([c6[0], c6[1], c6[2]], 1), torch.stack([c6[1], c6[3], c6[4]], 1), torch.stack([c6[2], c6[4], c6[5]], 1)], 1)
+    lam = torch.linalg.eigvalsh(mat).flip(1).clamp(min=0.0).t()  # descending, PSD
+    l1 = lam[0]
+    efloor = 64 * 2.2e-16 * (scale.max() ** 2)  # rounding floor of forming a covariance from coordinates of this size
+    assert bool(((st.eig[:, pick] - lam).abs() <= 1e-9 * l1 + efloor).all()), "eigenvalues within 1e-9 of the largest"
+    if full_stats:
+        well = lam[2] > 1e6 * efloor  # full-rank voxels well above the rounding floor: ratio features carry 1e-9 absolute
+        f = st.feat[:, pick][:, well]
+        a, b, c = lam[0][well], lam[1][well], lam[2][well]
+        tot = a + b + c
+        e = torch.stack([a, b, c]) / tot
+        ref = torch.stack([tot, (a * b * c) ** (1.0 / 3.0), -(e * torch.log(e)).sum(0), (a - c) / a, (b - c) / a, (a - b) / a, c / tot, c / a])
+        assert bool(((f[0] - ref[0]).abs() <= 1e-9 * ref[0]).all()), "Sum_of_Eigenvalues"
+        assert bool(((f[1] ** 3 - a * b * c).abs() <= 1e-9 * a ** 3).all()), "Omnivariance through its cube"
+        assert bool(((f[2:] - ref[2:]).abs() <= 1e-9 + 1e-9 * ref[2:].abs()).all()), "ratio features within 1e-9"
     return cloud
 
 
@@ -147,6 +170,76 @@ def test_config4_two_epoch_join_and_change(E):
     assert float(sig[~in_moved & dense & (v1[0][i1].to(torch.float64) * vs < 149.0)].float().mean()) < 0.05, "the static part is not"
     ct = out["change_type"]
     assert bool((ct[~sig] == 0).all()) and bool(((ct[sig] == 1) | (ct[sig] == 2)).all())
+    torch.cuda.empty_cache()
+
+
+def test_config4_full_size_two_epochs_vs_torch(E):
+    """BASELINE configs[3] at its full size — two epochs of 2e8 points — against the independent torch implementation: the joined /
+    appeared / disappeared voxel SETS are identical, the centroid distance agrees to 1e-9, d1 / d2 to the conditioning-aware rule
+    on well-conditioned voxels, and the classes follow from the p-values (bi_vapc.py:92-138)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs 100 GiB of free device memory")
+    n, vs, alpha = 200_000_000, 0.5, 0.005
+    x, y, _ = quantised_uniform(n, (700.0, 700.0, 10.0), 14)
+    g = torch.Generator(device="cuda").manual_seed(15)
+    z = torch.round((2.2 + 0.05 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)) * 1e4) * 1e-4
+    keep = ~((y > 300.0) & (y < 310.0))  # a strip disappears in epoch 2, another one appears
+    x2 = x[keep] + torch.where(x[keep] > 500.0, 0.1, 0.0)
+    y2, z2 = y[keep], z[keep] + torch.randn(int(keep.sum()), device="cuda", generator=g, dtype=torch.float64) * 0.002
+    z2 = torch.round(z2 * 1e4) * 1e-4
+    del keep
+    tabs, refs = [], []
+    for cols in ((x, y, z), (x2, y2, z2)):
+        c = E.VoxelCloud.build(*cols, vs, [0.0, 0.0, 0.0], want_point2voxel=False, keep_columns=False)
+        st = c.stats(cog=True, cov=True)
+        tabs.append((c.voxel_coords(), st.cog, st.cov, _u32(c.count)))
+        del c
+        (vx, vy, vz), _, cnt, cog, cov = torch_voxel_table(*cols, vs)
+        refs.append(((vx, vy, vz), cog, cov, cnt))
+        torch.cuda.empty_cache()
+    for (v, cog, cov, cnt), (rv, rcog, rcov, rcnt) in zip(tabs, refs):
+        assert all(torch.equal(a, b) for a, b in zip(v, rv)) and torch.equal(cnt, rcnt)
+    i1, i2, only1, only2 = E.join_voxel_tables(tabs[0][0], tabs[1][0])
+    # the same join in torch: pack both tables over the common bounding box, intersect
+    lo = [min(int(a.min()), int(b.min())) for a, b in zip(refs[0][0], refs[1][0])]
+    ext = [max(int(a.max()), int(b.max())) - l + 1 for a, b, l in zip(refs[0][0], refs[1][0], lo)]
+    pk = [((v[0] - lo[0]) * ext[1] + (v[1] - lo[1])) * ext[2] + (v[2] - lo[2]) for v in (refs[0][0], refs[1][0])]
+    in2 = torch.isin(pk[0], pk[1])
+    in1 = torch.isin(pk[1], pk[0])
+    assert torch.equal(i1, torch.nonzero(in2).flatten()), "joined voxels (epoch-1 rows)"
+    assert torch.equal(pk[1][i2], pk[0][i1]), "pairs are the same voxel"
+    assert torch.equal(torch.sort(only1).values, torch.nonzero(~in2).flatten()), "disappeared voxels"
+    assert torch.equal(torch.sort(only2).values, torch.nonzero(~in1).flatten()), "appeared voxels"
+    assert only1.numel() > 1000 and only2.numel() >= 0
+    out = E.mahalanobis(tabs[0][1], tabs[0][2], tabs[1][1], tabs[1][2], i1, i2, alpha=alpha)
+    d = refs[0][1][:, i1] - refs[1][1][:, i2]
+    dist = d.pow(2).sum(0).sqrt()
+    assert bool(((out["distance"] - dist).abs() <= 1e-9 * dist + 1e-12).all()), "centroid distance"
+
+    def quad(c6, dd):
+        m = torch.stack([torch.stack([c6[0], c6[1], c6[2]], 1), torch.stack([c6[1], c6[3], c6[4]], 1), torch.stack([c6[2], c6[4], c6[5]], 1)], 1)
+        m = m + 1e-10 * torch.eye(3, dtype=torch.float64, device="cuda")
+        sol = torch.linalg.solve(m, dd.t().unsqueeze(2)).squeeze(2)
+        return (sol * dd.t()).sum(1), torch.linalg.cond(m)
+
+    ok = (tabs[0][3][i1] >= 8) & (tabs[1][3][i2] >= 8)  # voxels with enough points for a full-rank covariance
+    sel = torch.nonzero(ok).flatten()[:2_000_000]
+    d1, k1 = quad(refs[1][2][:, i2[sel]], d[:, sel])
+    d2, k2 = quad(refs[0][2][:, i1[sel]], d[:, sel])
+    for got, ref, cond in ((out["d1"][sel], d1, k1), (out["d2"][sel], d2, k2)):
+        well = cond < 1e4
+        assert int(well.sum()) > 1000
+        assert bool(((got[well] - ref[well]).abs() <= ref[well].abs() * (1e-9 + 1e-12 * cond[well]) + 1e-12).all()), "Mahalanobis distance"
+    p = out["p_value"]
+    sig = out["significance"].bool()
+    okp = ~torch.isnan(p)
+    assert bool((sig[okp] == (p[okp] < alpha)).all()), "significance follows from the p-value"
+    ct = out["change_type"]
+    assert bool((ct[~sig] == 0).all()) and bool(((ct[sig] == 1) | (ct[sig] == 2)).all()) and bool((ct[okp & (p == 0)] == 2).all())
+    moved = (tabs[0][0][0][i1].to(torch.float64) * vs > 502.0) & ok
+    still = (tabs[0][0][0][i1].to(torch.float64) * vs < 498.0) & ok
+    assert float(sig[moved].float().mean()) > 0.9 and float(sig[still].float().mean()) < 0.05
     torch.cuda.empty_cache()
 
 

@@ -82,7 +82,8 @@ def verify_sharded_table(table, stats, x, y, z, group=None, sample_rows=100_000)
     out["order_ok"] = bool(flag.item())
 
     # ---- key set -----------------------------------------------------------------------------------------------------
-    pk = _global_keys(x, y, z, g)
+    order = tuple(getattr(table, "axis_order", (0, 1, 2)))  # the table's grid is expressed in its internal axis order
+    pk = _global_keys(*[(x, y, z)[a] for a in order], g)
     uk = torch.unique(pk)
     dest = torch.searchsorted(th, uk, right=True) if world > 1 else torch.zeros_like(uk)
     cuts = torch.searchsorted(dest, torch.arange(world + 1, device=dev)).cpu().tolist()
@@ -124,14 +125,15 @@ def verify_sharded_table(table, stats, x, y, z, group=None, sample_rows=100_000)
         prod = torch.stack([d[:, 0] * d[:, 0], d[:, 0] * d[:, 1], d[:, 0] * d[:, 2], d[:, 1] * d[:, 1], d[:, 1] * d[:, 2], d[:, 2] * d[:, 2]], dim=1)
         cov = torch.zeros((m, 6), dtype=torch.float64, device=dev).index_add_(0, row, prod) / (n_ref[:, None] - 1).clamp(min=1)
         cog = stats.cog[:, a:a + m].t()
-        err = ((cog - mean).abs() / mean.abs().clamp(min=1e-300)).max()
+        # 1e-9 relative, norm-wise per voxel (a coordinate that happens to be ~0 has no relative scale of its own)
+        err = ((cog - mean).abs().max(dim=1).values / mean.abs().max(dim=1).values.clamp(min=1e-3 * float(g.voxel_size))).max()
         worst_cog = float(err)
         ok_cog = worst_cog <= 1e-9
         multi = n_ref > 1
         if bool(multi.any()):
             gc = stats.cov[:, a:a + m].t()[multi]
             rc = cov[multi]
-            scale = rc.abs().max(dim=1, keepdim=True).values.clamp(min=1e-300)
+            scale = rc.abs().max(dim=1, keepdim=True).values + 1e-3 * float(g.voxel_size) ** 2  # degenerate voxels: relative to the voxel
             worst_cov = float(((gc - rc).abs() / scale).max())
             ok_cov = worst_cov <= 1e-9
     flag = torch.tensor([int(ok_cnt), int(ok_cog), int(ok_cov)], dtype=torch.int64, device=dev)

@@ -104,6 +104,7 @@ SIGNATURES = {
     "vapc_point2voxel_table_bytes": (SZ, [I32]),
     "vapc_point2voxel_dense": (C.c_int, [P, I64, P, I64, I32, I32, P, SZ, P, P]),
     "vapc_voxel_stats": (C.c_int, [P, P, P, P, I64, GP, P, P, P, P, P, P, P, P]),
+    "vapc_voxel_stats_axes": (C.c_int, [P, P, P, P, I64, GP, C.POINTER(I32), P, P, P, P, P, P, P, P]),
     "vapc_voxel_center_corner": (C.c_int, [P, I64, GP, P, P, P]),
     "vapc_closest_to_cog": (C.c_int, [P, P, I64, I32, P, P, I64, P, P, P, SZ, P]),
     "vapc_point_distance": (C.c_int, [P, P, P, I64, P, P, I64, P, P]),
@@ -137,6 +138,7 @@ SIGNATURES = {
     "vapc_global_keys": (C.c_int, [P, I64, GP, GP, I32, P, P, P]),
     "vapc_pack_partial_rows": (C.c_int, [P, P, P, P, I64, I64, I64, P, P]),
     "vapc_merge_partial_rows": (C.c_int, [P, P, I64, I32, P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, SZ, P]),
+    "vapc_merge_sorted_tables": (C.c_int, [P, P, P, P, I64, I64, I64, P, P, P, P, I64, P, I32, I64, P, P, P, P, P]),
     "vapc_reduce_candidates": (C.c_int, [P, P, P, I64, I64, P, P, P]),
     "vapc_key_histogram": (C.c_int, [P, I64, I32, I32, I32, P, P]),
     "vapc_laz_decode": (C.c_int, [P, I64, I64, I64, I32, I32, C.c_uint32, P, I32, P]),

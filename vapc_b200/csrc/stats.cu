@@ -12,6 +12,13 @@
 
 namespace {
 constexpr int kThreads = 128;
+// Output rows of the axis-indexed tables.  The table's keys / moments may live in a permuted axis order (multi-GPU: the axis the
+// chunks are separated along leads the key, vapc_b200/dist.py); the outputs are always x, y, z: internal axis i -> row axis[i] of
+// cog / std, internal covariance component k -> component cov[k].
+struct StatsAxes {
+  int axis[3];
+  int cov[6];
+};
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ count,
@@ -19,7 +26,7 @@ __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __res
                                                                int64_t nvox, Grid g, double* __restrict__ density,
                                                                double* __restrict__ cog3, double* __restrict__ std3,
                                                                double* __restrict__ cov6, double* __restrict__ eig3,
-                                                               double* __restrict__ eign3, double* __restrict__ feat8) {
+                                                               double* __restrict__ eign3, double* __restrict__ feat8, StatsAxes ax) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvox) return;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -28,9 +35,9 @@ __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __res
   if (cog3) {
     long long vx, vy, vz;
     unpack_key((unsigned long long)keys[v], g, vx, vy, vz);
-    cog3[v] = shift_center(vx, g.ox, g.vs) + mean3[v];
-    cog3[nvox + v] = shift_center(vy, g.oy, g.vs) + mean3[nvox + v];
-    cog3[2 * nvox + v] = shift_center(vz, g.oz, g.vs) + mean3[2 * nvox + v];
+    cog3[ax.axis[0] * nvox + v] = shift_center(vx, g.ox, g.vs) + mean3[v];
+    cog3[ax.axis[1] * nvox + v] = shift_center(vy, g.oy, g.vs) + mean3[nvox + v];
+    cog3[ax.axis[2] * nvox + v] = shift_center(vz, g.oz, g.vs) + mean3[2 * nvox + v];
   }
   if (!(std3 || cov6 || eig3 || eign3 || feat8)) return;
   double c[6];
@@ -44,13 +51,13 @@ __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __res
   }
   if (cov6) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) cov6[(int64_t)k * nvox + v] = c[k];
+    for (int k = 0; k < 6; ++k) cov6[(int64_t)ax.cov[k] * nvox + v] = c[k];
   }
   if (std3) {
     // fmax(NaN, 0) would hide the n == 1 NaN, so clamp only real values (rounding can leave -1e-33)
-    std3[v] = c[0] < 0.0 ? 0.0 : sqrt(c[0]);
-    std3[nvox + v] = c[3] < 0.0 ? 0.0 : sqrt(c[3]);
-    std3[2 * nvox + v] = c[5] < 0.0 ? 0.0 : sqrt(c[5]);
+    std3[ax.axis[0] * nvox + v] = c[0] < 0.0 ? 0.0 : sqrt(c[0]);
+    std3[ax.axis[1] * nvox + v] = c[3] < 0.0 ? 0.0 : sqrt(c[3]);
+    std3[ax.axis[2] * nvox + v] = c[5] < 0.0 ? 0.0 : sqrt(c[5]);
   }
   if (!(eig3 || eign3 || feat8)) return;
   double l1 = nan, l2 = nan, l3 = nan;
@@ -107,22 +114,42 @@ inline int grid_for(int64_t n, int threads, int per_thread = 1) {
 }
 }  // namespace
 
-extern "C" int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, const double* mean3, const double* m2,
-                                int64_t nvoxels, const vapc_grid_t* grid_host, double* density, double* cog3, double* std3,
-                                double* cov6, double* eig3, double* eign3, double* feat8, void* stream) {
+extern "C" int vapc_voxel_stats_axes(const void* voxel_keys, const uint32_t* count, const double* mean3, const double* m2,
+                                     int64_t nvoxels, const vapc_grid_t* grid_host, const int32_t* axis_order_host, double* density,
+                                     double* cog3, double* std3, double* cov6, double* eig3, double* eign3, double* feat8, void* stream) {
   if (!grid_host || nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats: bad arguments");
+  StatsAxes ax = {{0, 1, 2}, {0, 1, 2, 3, 4, 5}};
+  if (axis_order_host) {
+    int seen = 0;
+    for (int i = 0; i < 3; ++i) {
+      if (axis_order_host[i] < 0 || axis_order_host[i] > 2) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats_axes: axis_order must be a permutation of 0, 1, 2");
+      ax.axis[i] = axis_order_host[i];
+      seen |= 1 << axis_order_host[i];
+    }
+    if (seen != 7) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats_axes: axis_order must be a permutation of 0, 1, 2");
+    static const int pair[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};  // (a, b) -> xx xy xz yy yz zz
+    int k = 0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) ax.cov[k++] = pair[ax.axis[i]][ax.axis[j]];
+  }
   if (nvoxels == 0) return VAPC_OK;
   if (!voxel_keys || !count || !mean3 || !m2) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats: null input");
   const Grid g = to_device_grid(grid_host);
   const unsigned blocks = (unsigned)((nvoxels + kThreads - 1) / kThreads);
   if (grid_host->key_bytes == 4)
     VAPC_LAUNCH(voxel_stats_kernel<uint32_t>, blocks, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(voxel_keys), count, mean3, m2,
-                                                                             nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8);
+                                                                             nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8, ax);
   else
     VAPC_LAUNCH(voxel_stats_kernel<unsigned long long>, blocks, kThreads, 0, as_stream(stream), 
-        static_cast<const unsigned long long*>(voxel_keys), count, mean3, m2, nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8);
+        static_cast<const unsigned long long*>(voxel_keys), count, mean3, m2, nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8, ax);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
+}
+
+extern "C" int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, const double* mean3, const double* m2,
+                                int64_t nvoxels, const vapc_grid_t* grid_host, double* density, double* cog3, double* std3,
+                                double* cov6, double* eig3, double* eign3, double* feat8, void* stream) {
+  return vapc_voxel_stats_axes(voxel_keys, count, mean3, m2, nvoxels, grid_host, nullptr, density, cog3, std3, cov6, eig3, eign3, feat8, stream);
 }
 
 extern "C" int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream) {

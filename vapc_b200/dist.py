@@ -47,6 +47,22 @@ def bench_slab_shift(rank: int, extent_x: float) -> float:
     return 0.9 * rank * extent_x
 
 
+def choose_axis_order(all_bounds) -> tuple:
+    """Which coordinate axis leads the packed key (most significant first).  The key space is cut into contiguous key ranges, one
+    per rank, so a rank keeps the rows of its own chunk exactly when the chunks are separated along the LEADING axis: chunks that
+    are strips along y under an x-major key would send (world - 1) / world of their rows away.  all_bounds: [world, 6] local
+    bounding boxes (min x, y, z, max x, y, z).  Measure per axis = sum of the ranks' extents / global extent (1 = the chunks tile the
+    axis, world = every chunk spans it), compared in eighths of its range so that chunks which all span everything (shuffled points)
+    keep the x, y, z order whatever the last digits of their bounding boxes say; axes in ascending measure, ties in x, y, z order."""
+    b = np.asarray(all_bounds, dtype=np.float64).reshape(-1, 6)
+    measure = []
+    for a in range(3):
+        ext = float(b[:, 3 + a].max() - b[:, a].min())
+        measure.append(float((b[:, 3 + a] - b[:, a]).sum()) / ext if ext > 0 else float(len(b)))
+    world = max(len(b), 1)
+    return tuple(sorted(range(3), key=lambda a: (int(round(8.0 * measure[a] / world)), a)))
+
+
 def plan_splitters(global_hist: np.ndarray, world: int, total_bits: int, hist_bits: int = HIST_BITS) -> List[int]:
     """Key thresholds t_1 <= ... <= t_{world-1}: rank g owns keys in [t_g, t_{g+1}) (t_0 = 0, t_world = inf).
     Chosen on histogram-bin boundaries so that every range holds about the same number of partial rows."""
@@ -122,20 +138,33 @@ class ShardedVoxelTable:
     partial_rows_received: int
     exchange: str = "nccl"  # "peer": rows written straight into the owner's symmetric receive buffer over NVLink
     local_voxels: int = 0  # rows of this rank's own partial table before the exchange
+    # Internal axis order: axis_order[0] is the coordinate axis that leads the packed key (choose_axis_order).  grid, voxel_keys,
+    # mean3 and m2 are expressed in THAT order; stats() and voxel_coords() hand everything back in x, y, z order.
+    axis_order: tuple = (0, 1, 2)
 
     def stats(self, density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True):
         from . import engine as E
 
         c = E.VoxelCloud()
         c.grid, c.nvoxels, c.voxel_keys, c.count, c.mean3, c.m2 = self.grid, self.nvoxels, self.voxel_keys, self.count, self.mean3, self.m2
+        c.axis_order = tuple(self.axis_order)  # the kernel writes centroid / std / covariance rows in x, y, z order
         return c.stats(density=density, cog=cog, std=std, cov=cov, eig=eig, eig_n=eig_n, feat=feat)
 
     def voxel_coords(self):
+        """(vx, vy, vz) int64 [V] of this rank's rows."""
         from . import engine as E
 
         c = E.VoxelCloud()
         c.grid, c.nvoxels, c.voxel_keys = self.grid, self.nvoxels, self.voxel_keys
-        return c.voxel_coords()
+        v = c.voxel_coords()
+        out = [None, None, None]
+        for i, a in enumerate(self.axis_order):
+            out[a] = v[i]
+        return out
+
+    def internal_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """[3, ...] rows given in x, y, z order -> the table's internal axis order."""
+        return t if tuple(self.axis_order) == (0, 1, 2) else t[list(self.axis_order)]
 
 
 @dataclass
@@ -284,8 +313,23 @@ def merge_partial_rows(grid, keys: torch.Tensor, count: torch.Tensor, mean3: tor
     return out_keys, out_count, out_mean, out_m2
 
 
+def gather_bounds(x, y, z, group=None) -> np.ndarray:
+    """[world, 6] local bounding boxes of all ranks (one min/max kernel + one all-gather of 6 doubles per rank)."""
+    from . import _lib as L
+    from . import engine as E
+
+    world = dist.get_world_size(group)
+    out = torch.empty(6, dtype=torch.float64, device=x.device)
+    ws_bytes = L.raw("vapc_minmax_workspace_bytes")()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.call("vapc_minmax_f64", E._ptr(x), E._ptr(y), E._ptr(z), x.numel(), E._ptr(out), E._ptr(ws), ws_bytes, E._stream())
+    allb = torch.empty(6 * world, dtype=torch.float64, device=x.device)
+    dist.all_gather_into_tensor(allb, out, group=group)
+    return allb.cpu().numpy().reshape(world, 6)
+
+
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
-                     thresholds=None, keep_local=False, stats_columns=None):
+                     thresholds=None, keep_local=False, stats_columns=None, axis_order="auto"):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
@@ -295,7 +339,10 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     (in place) with the received ones.  Five small device -> host copies synchronise the host: local bounds, local voxel
     count, global bounds, the all-gathered send-count matrix, the merged voxel count.
 
-    bounds (optional): global coordinate bounds every rank already agrees on (no all-reduce); thresholds (optional): the
+    axis_order: "auto" (choose_axis_order from the ranks' bounding boxes) or a permutation of (0, 1, 2): the coordinate axis that
+    leads the packed key.  Results come back in x, y, z order (ShardedVoxelTable.stats / voxel_coords); only the ROW order of the
+    sharded table follows the internal order.
+    bounds (optional): global coordinate bounds every rank already agrees on; thresholds (optional): the
     world - 1 key thresholds of an earlier table over the SAME grid — the rows are then sent to the owners of those key
     ranges instead of re-balancing, so that two tables (two epochs) are range-aligned rank by rank (two_epoch_change)."""
     from . import _lib as L
@@ -304,13 +351,27 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = x.device
-    if bounds is None:
-        local_b, finish_bounds = start_bounds(x, y, z, group)
-    else:
-        local_b, finish_bounds = None, (lambda: bounds)
+    # the local bounding boxes of all ranks: the global bounds, and which axis leads the key (the one the chunks are separated along)
+    local_b = None
+    if bounds is None or axis_order == "auto":
+        allb = gather_bounds(x, y, z, group)
+        local_b = allb[rank]
+        if bounds is None:
+            bounds = np.concatenate([allb[:, :3].min(0), allb[:, 3:].max(0)])
+        if axis_order == "auto":
+            axis_order = choose_axis_order(allb)
+    axis_order = tuple(int(a) for a in axis_order)
+    if sorted(axis_order) != [0, 1, 2]:
+        raise ValueError("axis_order must be a permutation of (0, 1, 2)")
+    if axis_order != (0, 1, 2):  # from here on everything lives in the internal axis order
+        perm6 = list(axis_order) + [3 + a for a in axis_order]
+        x, y, z = [(x, y, z)[a] for a in axis_order]
+        origin = [origin[a] for a in axis_order]
+        bounds = np.asarray(bounds, dtype=np.float64)[perm6]
+        local_b = local_b[perm6] if local_b is not None else None
     local = E.VoxelCloud.build(x, y, z, voxel_size, origin, bounds=local_b, want_point2voxel=keep_local, keep_columns=keep_local)
     lg = local.grid
-    g = E.grid_from_bounds(voxel_size, origin, finish_bounds())  # the key layout every rank agrees on
+    g = E.grid_from_bounds(voxel_size, origin, bounds)  # the key layout every rank agrees on
     if g.total_bits > 63:
         raise L.VapcError(L.VAPC_E_KEYSPACE, "multi-GPU key ranges need at most 63 key bits")
     v = local.nvoxels
@@ -369,27 +430,44 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
                        C.c_void_p(out_rows.data_ptr() + at * 88), E._stream())
         in_rows = torch.empty((n_in, 11), dtype=torch.float64, device=dev)
         dist.all_to_all_single(in_rows, out_rows, output_split_sizes=recv_remote, input_split_sizes=send_remote, group=group)
-    # merge: own rows (sources 0 .. n_own-1, read in place from the local table) + received rows (sources n_own ..)
-    r = n_own + n_in
-    keys = torch.empty(r, dtype=torch.int32 if g.key_bytes == 4 else torch.int64, device=dev)
-    L.call("vapc_merge_keys", E._ptr(gkeys), lo, n_own, E._ptr(in_rows), n_in, g.key_bytes, E._ptr(keys), E._stream())
-    ks, order = E.sort_pairs(keys, g.total_bits)
-    ws_bytes = L.raw("vapc_segment_workspace_bytes")(r)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    nv = torch.zeros(1, dtype=torch.int64, device=dev)
-    L.call("vapc_count_voxels", E._ptr(ks), r, g.key_bytes, E._ptr(nv), E._ptr(ws), ws_bytes, E._stream())
-    vm = int(nv.item())
-    out_keys = torch.empty(vm, dtype=ks.dtype, device=dev)
+    # merge WITHOUT re-sorting the own rows (they are the bulk and already key-sorted): the few received rows are sorted and combined
+    # per key on their own (n_in rows), then merged by rank into the own rows in ONE pass (vapc_merge_sorted_tables)
+    kdt = torch.int32 if g.key_bytes == 4 else torch.int64
+    own_keys = gkeys[lo:hi]
+    if n_in:
+        rkeys = torch.empty(n_in, dtype=kdt, device=dev)
+        L.call("vapc_merge_keys", E._ptr(gkeys), 0, 0, E._ptr(in_rows), n_in, g.key_bytes, E._ptr(rkeys), E._stream())
+        ks, order = E.sort_pairs(rkeys, g.total_bits)
+        ws_bytes = L.raw("vapc_segment_workspace_bytes")(n_in)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        nv = torch.zeros(1, dtype=torch.int64, device=dev)
+        L.call("vapc_count_voxels", E._ptr(ks), n_in, g.key_bytes, E._ptr(nv), E._ptr(ws), ws_bytes, E._stream())
+        nu = int(nv.item())
+        u_keys = torch.empty(nu, dtype=kdt, device=dev)
+        u_count = torch.empty(nu, dtype=torch.int32, device=dev)
+        u_mean = torch.empty((3, nu), dtype=torch.float64, device=dev)
+        u_m2 = torch.empty((6, nu), dtype=torch.float64, device=dev)
+        L.call("vapc_merge_partial_rows", E._ptr(ks), E._ptr(order), n_in, g.key_bytes, E._ptr(in_rows), None, None, None, 0, 0, 0, nu,
+               E._ptr(u_keys), E._ptr(u_count), E._ptr(u_mean), E._ptr(u_m2), E._ptr(ws), ws_bytes, E._stream())
+        u_keys64 = keys_as_int64(u_keys).contiguous()
+        at = torch.searchsorted(own_keys, u_keys64) if n_own else torch.zeros(nu, dtype=torch.int64, device=dev)
+        held = (own_keys[at.clamp(max=max(n_own - 1, 0))] == u_keys64) & (at < n_own) if n_own else torch.zeros(nu, dtype=torch.bool, device=dev)
+        new_before = torch.zeros(nu + 1, dtype=torch.int64, device=dev)
+        torch.cumsum((~held).to(torch.int64), 0, out=new_before[1:])
+        vm = n_own + int(new_before[-1].item())
+    else:
+        nu, u_keys64, u_count, u_mean, u_m2, new_before, vm = 0, None, None, None, None, None, n_own
+    out_keys = torch.empty(vm, dtype=kdt, device=dev)
     out_count = torch.empty(vm, dtype=torch.int32, device=dev)
     out_mean = torch.empty((3, vm), dtype=torch.float64, device=dev)
     out_m2 = torch.empty((6, vm), dtype=torch.float64, device=dev)
-    if r:
-        L.call("vapc_merge_partial_rows", E._ptr(ks), E._ptr(order), r, g.key_bytes, E._ptr(in_rows), E._ptr(local.count), E._ptr(local.mean3),
-               E._ptr(local.m2), v, lo, n_own, vm, E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), E._ptr(ws), ws_bytes,
-               E._stream())
+    if vm:
+        L.call("vapc_merge_sorted_tables", E._ptr(own_keys.contiguous()), E._ptr(local.count), E._ptr(local.mean3), E._ptr(local.m2), v, lo, n_own,
+               E._ptr(u_keys64), E._ptr(u_count), E._ptr(u_mean), E._ptr(u_m2), nu, E._ptr(new_before), g.key_bytes, vm,
+               E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), E._stream())
     table = ShardedVoxelTable(grid=g, nvoxels=vm, voxel_keys=out_keys, count=out_count, mean3=out_mean, m2=out_m2,
                               thresholds=host[world * world:].tolist(), partial_rows_sent=int(sum(send_remote)),
-                              partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl")
+                              partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl", axis_order=axis_order)
     table.local_voxels = v
     if not with_stats:
         st = None
@@ -419,11 +497,12 @@ def two_epoch_change(epoch1: Sequence[torch.Tensor], epoch2: Sequence[torch.Tens
     from . import _lib as L
     from . import engine as E
 
-    (_, fin1), (_, fin2) = start_bounds(*epoch1, group), start_bounds(*epoch2, group)
-    b1, b2 = fin1(), fin2()
-    gb = np.concatenate([np.minimum(b1[:3], b2[:3]), np.maximum(b1[3:], b2[3:])])
-    t1, _ = voxel_statistics(*epoch1, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb)
-    t2, _ = voxel_statistics(*epoch2, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb, thresholds=t1.thresholds)
+    a1, a2 = gather_bounds(*epoch1, group), gather_bounds(*epoch2, group)
+    gb = np.concatenate([np.minimum(a1[:, :3].min(0), a2[:, :3].min(0)), np.maximum(a1[:, 3:].max(0), a2[:, 3:].max(0))])
+    order = choose_axis_order(a1)  # both epochs share the key layout AND the key ranges, planned on epoch 1
+    t1, _ = voxel_statistics(*epoch1, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb, axis_order=order)
+    t2, _ = voxel_statistics(*epoch2, voxel_size, origin, group=group, with_stats=False, exchange=exchange, bounds=gb, thresholds=t1.thresholds,
+                             axis_order=order)
     dev = t1.voxel_keys.device
     k1, k2 = keys_as_int64(t1.voxel_keys).contiguous(), keys_as_int64(t2.voxel_keys).contiguous()
     m1 = torch.empty(t1.nvoxels, dtype=torch.int32, device=dev)
@@ -478,7 +557,7 @@ def point_distance(table: ShardedVoxelTable, shard: LocalShard, cog: torch.Tenso
     from . import engine as E
 
     c = shard.cloud
-    per_row = rows_from_owner(table, shard, cog)
+    per_row = rows_from_owner(table, shard, table.internal_rows(cog))  # the shard's cloud lives in the internal axis order
     out = torch.empty(c.n, dtype=torch.float64, device=cog.device)
     L.call("vapc_point_distance", E._ptr(c.x), E._ptr(c.y), E._ptr(c.z), c.n, E._ptr(c.point2voxel), E._ptr(per_row), c.nvoxels, E._ptr(out), E._stream())
     return out
@@ -501,7 +580,7 @@ def closest_to_cog(table: ShardedVoxelTable, shard: LocalShard, cog: torch.Tenso
         sizes[dist.get_rank(shard.group)] = c.n
         dist.all_reduce(sizes, group=shard.group)
         point_offset = int(sizes[: dist.get_rank(shard.group)].sum().item())
-    md, am = c.closest_to_cog(cog=rows_from_owner(table, shard, cog))
+    md, am = c.closest_to_cog(cog=rows_from_owner(table, shard, table.internal_rows(cog)))
     gidx = (am.to(torch.int64) & 0xFFFFFFFF) + point_offset
     lo, hi = shard.lo, shard.lo + shard.n_own
     cand = torch.stack([md, gidx.view(torch.float64)], dim=1)  # the index travels as a bit pattern

@@ -48,6 +48,11 @@ def _dev_f64(a, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
 
 
+def _u32_t(t: torch.Tensor) -> torch.Tensor:
+    """uint32 values stored in an int32 tensor -> int64."""
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
 def _empty(n, dtype, device):
     return torch.empty(int(n), dtype=dtype, device=device)
 
@@ -212,7 +217,7 @@ def _tune_device(device):
             L.call("vapc_set_l2_fetch_granularity", g)
 
 
-CELL_SORT = os.environ.get("VAPC_CELL_SORT", "1") != "0"  # dense grids: counting sort through a per-bucket cell table
+CELL_SORT = os.environ.get("VAPC_CELL_SORT", "0") != "0"  # dense grids: counting sort through a per-bucket cell table
 CELL_SORT_MIN_BITS = 9   # fewer key bits below the bucket digit: a single radix pass is as cheap
 CELL_SORT_MAX_MEAN = 16  # mean points per cell of the key space beyond which the per-cell ordering would dominate
 DENSE_P2V_MAX_BITS = 29  # rank-bitmap point->voxel table: 2^bits / 4 bytes, <= 128 MB stays L2-resident on B200
@@ -252,18 +257,26 @@ class VoxelCloud:
         self._seg_ws = None
         self.sorted_by = "radix"  # or "cells" (vapc_sort_cells_segmented)
         self._stats_cache: Dict[str, torch.Tensor] = {}
+        self.axis_order = (0, 1, 2)  # coordinate axis behind every internal axis of the keys / moments (multi-GPU tables permute them)
 
     # ------------------------------------------------------------------------------------
     @classmethod
     def build(cls, x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), *, bounds=None, want_point2voxel=True,
-              keep_columns=True, device=None, bucketed=True, las=None, cell_sort=None) -> "VoxelCloud":
+              keep_columns=True, device=None, bucketed=True, las=None, cell_sort=None, voxels=None) -> "VoxelCloud":
         """voxelize + groupby of the reference (vapc.py:188-207 and the groupby at :724, :843, :959)
         as: bounds -> packed keys + xyzw records in key-prefix bucket order -> stable radix sort of the remaining key
         bits inside the buckets -> segmentation -> moments.  bucketed=False keeps the records in input order and
         sorts all key bits (same results; the per-voxel gathers then miss the L2).
         las = (X, Y, Z, scales, offsets): the cloud as the int32 coordinates of a LAS file (x, y, z are then ignored and may be
-        None): the key kernels read 12 B/point and form X * scale + offset themselves — the same doubles, the same results."""
+        None): the key kernels read 12 B/point and form X * scale + offset themselves — the same doubles, the same results.
+        voxels = (vx, vy, vz): the voxel triple of every point GIVEN by the caller (int64 columns) instead of derived from the
+        coordinates — the reference groups by the frame's voxel_x / voxel_y / voxel_z columns whatever they hold (vapc.py:724, :843,
+        :959), e.g. after the caller edited them or the coordinates.  Moments stay relative to c(v) of the given voxel."""
         _require_cuda()
+        if voxels is not None:
+            bucketed = False
+            if las is not None:
+                raise ValueError("given voxel triples and LAS integer input exclude each other")
         if cell_sort is None:
             cell_sort = CELL_SORT
         if las is not None:
@@ -299,6 +312,16 @@ class VoxelCloud:
         if bounds is None:
             bounds = coordinate_bounds(x, y, z)
         self.grid = g = grid_from_bounds(voxel_size, origin, bounds)
+        if voxels is not None:
+            gv = [torch.as_tensor(np.asarray(a, dtype=np.int64) if not isinstance(a, torch.Tensor) else a).to(device=device, dtype=torch.int64).contiguous()
+                  for a in voxels]
+            if any(a.numel() != n for a in gv):
+                raise ValueError("voxel columns must have the length of the cloud")
+            coord_grid = g  # records are written with the coordinates' own grid; the keys below replace its keys
+            self.grid = g = grid_from_voxel_bounds(voxel_size, origin, [int(a.min().item()) for a in gv], [int(a.max().item()) for a in gv])
+            g.key_bytes = 8  # vapc_pack_triples_i64 writes 64-bit keys
+            if g.total_bits > 63:
+                raise L.VapcError(L.VAPC_E_KEYSPACE, "given voxel triples need more than 63 key bits")
         kdtype = torch.int32 if g.key_bytes == 4 else torch.int64
         self.xyzw = torch.empty((n, 4), dtype=torch.float64, device=device)
         status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -351,7 +374,14 @@ class VoxelCloud:
                 del keys
         else:
             keys = _empty(n, kdtype, device)
-            L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
+            if voxels is not None:
+                scratch = _empty(n, torch.int32 if coord_grid.key_bytes == 4 else torch.int64, device)
+                L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(coord_grid), _ptr(scratch), _ptr(self.xyzw), _ptr(status), _stream())
+                del scratch
+                L.call("vapc_pack_triples_i64", _ptr(gv[0]), _ptr(gv[1]), _ptr(gv[2]), n, C.byref(g), _ptr(keys), _ptr(status), _stream())
+                del gv
+            else:
+                L.call("vapc_pack_keys_f64", _ptr(x), _ptr(y), _ptr(z), n, C.byref(g), _ptr(keys), _ptr(self.xyzw), _ptr(status), _stream())
             self.keys_sorted, self.pos_sorted = sort_pairs(keys, g.total_bits, preserve_keys=dense_p2v)
             if not dense_p2v:
                 del keys
@@ -409,7 +439,8 @@ class VoxelCloud:
         shapes = dict(density=(V,), cog=(3, V), std=(3, V), cov=(6, V), eig=(3, V), eig_n=(3, V), feat=(8, V))
         new = {k: torch.empty(shapes[k], dtype=torch.float64, device=dev) for k, w in want.items() if w and k not in self._stats_cache}
         if new:
-            L.call("vapc_voxel_stats", _ptr(self.voxel_keys), _ptr(self.count), _ptr(self.mean3), _ptr(self.m2), V, C.byref(self.grid),
+            order = (C.c_int32 * 3)(*self.axis_order)
+            L.call("vapc_voxel_stats_axes", _ptr(self.voxel_keys), _ptr(self.count), _ptr(self.mean3), _ptr(self.m2), V, C.byref(self.grid), order,
                    *[_ptr(new.get(k)) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")], _stream())
             self._stats_cache.update(new)
         return VoxelStats(**{k: self._stats_cache[k] for k, w in want.items() if w})
@@ -465,6 +496,15 @@ class VoxelCloud:
         a = _dev_f64(attr, dev)
         if a.numel() != self.n:
             raise ValueError("attribute length differs from the cloud")
+        # values np.bincount(x.astype(int)) rejects — negative, NaN, infinite (vapc.py:409, :423): `mode_count` raises for such a
+        # voxel, `mode` falls back to the histogram mode of that voxel alone (vapc.py:411-412); the other voxels are not affected
+        rejected = ~(a >= 0) | torch.isinf(a)
+        flagged_rows = None
+        if bool(rejected.any()):
+            if list(thresholds):
+                raise ValueError("Cannot compute 'mode_count' for negative or non-finite attribute values")
+            flagged_rows = torch.unique(_u32_t(self.point2voxel)[rejected])
+            a_all, a = a, torch.where(rejected, torch.zeros_like(a), a)
         amax = float(a.max().item()) if self.n else 0.0
         attr_bits = max(1, int(max(amax, 0.0)).bit_length())
         if attr_bits > 32:
@@ -497,6 +537,17 @@ class VoxelCloud:
                    _ptr(mode if i == 0 else None), _ptr(mc), _stream())
             if p is not None:
                 counts[p] = mc
+        if flagged_rows is not None and mode is not None:
+            # the reference's per-voxel fallback, on the host, for the flagged voxels only (their points come out of the sorted order)
+            from .utilities import compute_mode_continuous
+
+            mode = mode.to(torch.float64)  # a column holding histogram modes is a float column
+            start = _u32_t(self.start).cpu().numpy()
+            idx = _u32_t(self.idx_sorted)
+            vals = []
+            for r in flagged_rows.cpu().tolist():
+                vals.append(compute_mode_continuous(a_all[idx[start[r]:start[r + 1]]].cpu().numpy()))
+            mode[flagged_rows] = torch.tensor(vals, dtype=torch.float64, device=dev)
         return mode, counts
 
     def percentage_occupied(self) -> float:

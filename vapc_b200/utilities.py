@@ -54,3 +54,20 @@ def timeit(func):
         return result
 
     return wrapper
+
+
+def compute_mode_continuous(data):
+    """Mode of a continuous sample as the centre of the fullest bin of a Freedman-Diaconis histogram (the reference's
+    utilities.py:114-159, which `mode` falls back to for voxels whose values np.bincount rejects, vapc.py:407-412).  Raises like the
+    reference when the bin width degenerates (a single value, zero inter-quartile range, NaN): int(ceil(nan)) / int(ceil(inf))."""
+    import numpy as np
+
+    data = np.asarray(data, dtype=np.float64)
+    n = len(data)
+    iqr = np.subtract(*np.percentile(data, [75, 25]))
+    with np.errstate(all="ignore"):
+        bin_width = 2 * iqr / n ** (1 / 3)
+        bins = int(np.ceil((np.max(data) - np.min(data)) / bin_width))
+    counts, bin_edges = np.histogram(data, bins=bins, density=True)
+    k = int(np.argmax(counts))
+    return (bin_edges[k] + bin_edges[k + 1]) / 2

@@ -19,7 +19,9 @@ reordering columns, row selection with a mask computed on the GPU, the voxel Mul
 """
 from __future__ import annotations
 
+import threading
 import warnings
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pandas as pd
@@ -27,6 +29,45 @@ import torch
 
 from . import engine as E
 from .utilities import timeit, trace
+
+_STAGING = {}  # device index -> [pinned buffer, pinned buffer]: double-buffered device -> host staging shared by all Vapc objects
+_STAGING_LOCK = threading.Lock()
+
+
+def _download_rows(block: np.ndarray, rows, make):
+    """block[i] = make(i) (a float64 device column) for every i in rows.  Device -> pinned staging copies alternate between two
+    buffers while worker threads move the previous column into the (pageable) block: the block is filled at the speed of the host
+    memcpy instead of a pageable cudaMemcpy.  The module-wide staging buffers are used under a lock (one download at a time)."""
+    if not len(rows):
+        return
+    width = block.shape[1]
+    dev = torch.cuda.current_device()
+    with _STAGING_LOCK:
+        bufs = _STAGING.get(dev)
+        if bufs is None or bufs[0].numel() < width:
+            bufs = [torch.empty(max(width, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+            _STAGING[dev] = bufs
+
+        def land(ev, buf, i):
+            ev.synchronize()
+            np.copyto(block[i], buf.numpy()[:width])
+
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            pending = [None, None]
+            for j, i in enumerate(rows):
+                k = j & 1
+                if pending[k] is not None:
+                    pending[k].result()
+                t = make(i)
+                bufs[k][:width].copy_(t.to(torch.float64), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending[k] = pool.submit(land, ev, bufs[k], i)
+                del t
+            for f in pending:
+                if f is not None:
+                    f.result()
+
 
 _COV_NAMES = ["cov_xx", "cov_xy", "cov_xz", "cov_yx", "cov_yy", "cov_yz", "cov_zx", "cov_zy", "cov_zz"]
 _COV9_FROM6 = [0, 1, 2, 1, 3, 4, 2, 4, 5]
@@ -162,7 +203,7 @@ class Vapc:
         if fresh:
             # one concat instead of one frame insertion per column (39 of them for the full attribute set)
             add = pd.DataFrame({c: new[c] for c in fresh}, index=self._df.index, copy=False)
-            self._df = pd.concat([self._df, add], axis=1, copy=False)
+            self._df = pd.concat([self._df, add], axis=1)
         for c in names:
             del self._lazy[c]
         if not self._lazy:
@@ -206,10 +247,17 @@ class Vapc:
         sig = self._signature()
         if self._cloud is None or self._exposed or sig != self._cloud_sig:
             self._materialise()  # pending columns belong to the old cloud
+            given = None
+            if self.voxelized and all(c in self._df.columns for c in ("voxel_x", "voxel_y", "voxel_z")):
+                # the frame carries voxel columns (handed out, assigned or edited by the caller): the reference groups by THOSE,
+                # whatever the coordinates say now (vapc.py:724, :843, :959)
+                given = [self._df[c].to_numpy(np.int64) for c in ("voxel_x", "voxel_y", "voxel_z")]
             self._cloud = E.VoxelCloud.build(self._df["X"].to_numpy(np.float64), self._df["Y"].to_numpy(np.float64),
-                                             self._df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin)
+                                             self._df["Z"].to_numpy(np.float64), float(self.voxel_size), self.origin, voxels=given)
             self._cloud_sig = self._signature()
             self._exposed = False
+            self._voxelized_cloud = self._cloud if given is not None else None
+            self._cloud_given = given is not None
         return self._cloud
 
     def _resign(self):
@@ -286,6 +334,9 @@ class Vapc:
     def _voxelize(self):
         """voxel_x / voxel_y / voxel_z = floor((coord - origin) / voxel_size) as int64 (vapc.py:188-207): the voxel table's triples
         broadcast to the points (pending until `.df` is read)."""
+        self.voxelized = False  # (re-)voxelise from the coordinates, not from voxel columns the frame may carry
+        if getattr(self, "_cloud_given", False):
+            self._cloud = None
         cloud = self._get_cloud()
         for name, col in zip(("voxel_x", "voxel_y", "voxel_z"), cloud.voxel_coords()):
             self._add_lazy(name, "voxel", col, cloud)
@@ -801,15 +852,16 @@ class Vapc:
             if pd.api.types.is_bool_dtype(dt) or pd.api.types.is_numeric_dtype(dt):
                 keep.append(c)
         block = np.empty((len(keep), final.numel()), dtype=np.float64)
+        on_device = [i for i, c in enumerate(keep) if c in ("X", "Y", "Z") or self.new_column_names.get(c, c) in self._lazy]
+
+        def device_column(i):
+            c = keep[i]
+            return xyz["XYZ".index(c)][rows] if c in ("X", "Y", "Z") else gather(self.new_column_names.get(c, c), final, final_np)
+
+        _download_rows(block, on_device, device_column)
         for i, c in enumerate(keep):
-            if c in ("X", "Y", "Z"):
-                v = xyz["XYZ".index(c)][rows]
-            else:
-                v = gather(self.new_column_names.get(c, c), final, final_np)
-            if isinstance(v, np.ndarray):
-                block[i] = v
-            else:
-                torch.from_numpy(block[i]).copy_(v.to(torch.float64))
+            if i not in on_device:
+                block[i] = gather(self.new_column_names.get(c, c), final, final_np)
         self.df = pd.DataFrame(block.T, columns=keep, copy=False)
         self.reduced = True
 
@@ -842,7 +894,7 @@ class Vapc:
                     k2, t2, c2 = self._lazy[name]
                     new[name] = self._host(t2[_u32(c2.point2voxel)[rows]] if k2 == "voxel" else t2[rows]).copy()
             order = list(self._cols)
-            frame = pd.concat([frame, pd.DataFrame(new, index=frame.index, copy=False)], axis=1, copy=False)
+            frame = pd.concat([frame, pd.DataFrame(new, index=frame.index, copy=False)], axis=1)
             self._df = frame if list(frame.columns) == order else frame[order]
         else:
             self._materialise()
