@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--points", type=int, default=0, help="points per GPU (default: 1e8 at N = 1 = configs[1], 1.25e8 at N > 1 = configs[2])")
     ap.add_argument("--bounds", default="header", choices=["header", "computed"],
                     help="N = 1: the cloud's bounding box comes with the data, as a LAS header gives it (default), or is computed by one more pass")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "configs2"],
+                    help="N = 1 only: configs1 (the bench line) or configs2 = one GPU's chunk of the N > 1 workload, voxelised alone (for profiles)")
     ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the shuffled and slab layouts")
     ap.add_argument("--no-facade", action="store_true", help="skip the drop-in facade e2e (DataFrame in, reduced DataFrame out)")
     ap.add_argument("--no-las-e2e", action="store_true", help="skip the LAS-integer-input variant of the e2e measurement")
@@ -262,7 +264,7 @@ def algorithmic_bytes(name, n, v, key_bytes, passes, low_passes):
         "vapc_sort_pairs_segmented": (k + low_passes * (2 * k + 8) - 4) * n,
         "vapc_sort_cells_segmented": (2 * k + 8) * n,
         "vapc_count_voxels": k * n,
-        "vapc_reduce_moments": (k + 4 + 32 + 4) * n + (k + 12 + 72) * v,
+        "vapc_reduce_moments": (k + 4 + 32) * n + (k + 12 + 72) * v,
         "vapc_point2voxel_dense": (k + 4) * n + (k + 4) * v,
         "vapc_voxel_stats": (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v,
     }.get(name, 0)
@@ -282,7 +284,7 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
         # dense grids: the bucketed keys in twice (count, place), sorted keys and positions out
         ("cell_sort_kernel", (2 * k + 8) * n),
         ("count_heads_kernel", k * n),
-        ("reduce_moments_kernel", (k + 4 + 32 + 4) * n + (k + 12 + 72) * v),
+        ("reduce_moments_kernel", (k + 4 + 32) * n + (k + 12 + 72) * v),  # sorted keys + positions + records in, the voxel rows out
         ("p2v_lookup_kernel", (k + 4) * n),
         ("p2v_fill_kernel", (k + 4) * v),
         ("voxel_stats_kernel", (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v),
@@ -407,8 +409,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
         from vapc_b200 import dist as D
     multi = world > 1
-    n = args.points or (125_000_000 if multi else 100_000_000)
-    vs = VOXEL_SIZE_MULTI if multi else VOXEL_SIZE
+    chunk_alone = not multi and args.workload == "configs2"
+    n = args.points or (125_000_000 if (multi or chunk_alone) else 100_000_000)
+    vs = VOXEL_SIZE_MULTI if (multi or chunk_alone) else VOXEL_SIZE
     FULL = dict(density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True)
 
     def barrier():
@@ -419,7 +422,21 @@ def main():
     windows = []
     extra = {}
     check = None
-    if not multi:
+    if chunk_alone:
+        # ---- N = 1, one GPU's chunk of configs[2] voxelised alone (what every rank of the N > 1 run does before the exchange) ----
+        x, y, z = synth.clustered_chunk(n, 0, 1, device, seed=3, scan_order=True)
+        header_bounds = None
+        args.bounds = "computed"
+
+        def make_step(bounds):
+            def step():
+                cloud = E.VoxelCloud.build(x, y, z, vs, ORIGIN, keep_columns=False, bounds=bounds)
+                return cloud, cloud.stats(**FULL)
+            return step
+
+        step_device = make_step(None)
+        workload = dict(workload_config_multi(n, 1, vs), parallelism="one GPU: the chunk voxelised alone, no exchange (bounds computed)")
+    elif not multi:
         # ---- N = 1: configs[1] -----------------------------------------------------------------------------------------
         x, y, z = synth.uniform_cloud(n, seed=2, device=device, extent=EXTENT)
         # the cloud's bounding box as the header of its LAS file states it (the reference's DataHandler reads the same header)
@@ -508,7 +525,7 @@ def main():
     dom = max((k for k in per_kernel if per_kernel[k]["GBps"]), key=lambda k: per_kernel[k]["ms_per_step"])
     achieved = per_kernel[dom]["GBps"]
     traffic_tab = ncu_traffic()
-    tkey = "n1" if not multi else "multi"
+    tkey = "n1" if not (multi or chunk_alone) else "multi"
     traffic = (traffic_tab.get(tkey) or {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "traffic_unit": "GB per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, read from "

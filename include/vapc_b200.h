@@ -450,6 +450,16 @@ VAPC_API int vapc_merge_sorted_tables(const uint64_t* own_keys, const uint32_t* 
                              const uint32_t* u_count, const double* u_mean3, const double* u_m2, int64_t nu,
                              const int64_t* u_new_before, int32_t key_bytes, int64_t nvoxels_host, void* out_keys,
                              uint32_t* out_count, double* out_mean3, double* out_m2, void* stream);
+/* The same merge with the per-voxel statistics of vapc_voxel_stats_axes formed in the same pass from the merged moments while they
+ * are in registers: out_mean3 / out_m2 may then be NULL (the merged moments are neither written nor read back: 72 B per voxel each
+ * way).  Statistic outputs nullable as in vapc_voxel_stats, column stride nvoxels_host. */
+VAPC_API int vapc_merge_sorted_tables_stats(const uint64_t* own_keys, const uint32_t* own_count, const double* own_mean3,
+                                   const double* own_m2, int64_t own_stride, int64_t own_first, int64_t n_own,
+                                   const uint64_t* u_keys, const uint32_t* u_count, const double* u_mean3, const double* u_m2,
+                                   int64_t nu, const int64_t* u_new_before, int32_t key_bytes, int64_t nvoxels_host,
+                                   void* out_keys, uint32_t* out_count, double* out_mean3, double* out_m2,
+                                   const vapc_grid_t* grid_host, const int32_t* axis_order_host, double* density, double* cog3,
+                                   double* std3, double* cov6, double* eig3, double* eign3, double* feat8, void* stream);
 /* Multi-GPU closest-to-centroid: every rank proposes, per partial voxel row, its nearest point to the FINAL
  * centroid; the owner reduces the n candidates (rows[i] = merged voxel row, dist[i] >= 0, idx[i] = global point index >= 0)
  * to the lexicographic minimum (distance, index) per row — the single-GPU tie-break "lowest original index".  Rows without a

@@ -81,12 +81,13 @@ def check_against_torch(E, x, y, z, vs, full_stats=True):
     var = torch.stack([cov[0], cov[3], cov[5]])[:, multi]
     assert bool(((st.std[:, multi] - var.sqrt()).abs() <= 1e-9 * var.sqrt() + 8 * 2.2e-16 * scale).all()), "std within 1e-9"
     assert bool(torch.isnan(st.std[:, ~multi]).all())
-    # eigenvalues and the 8 features against torch.linalg.eigvalsh of the independent covariance (H7 rules), on a sample of voxels
+    # eigenvalues and the 8 features against LAPACK (torch.linalg.eigvalsh on the host) of the independent covariance (H7 rules), on a
+    # sample of voxels
     pick = torch.nonzero(multi).flatten()
-    pick = pick[:: max(1, pick.numel() // 1_000_000)]
-    c6 = cov[:, pick]
+    pick = pick[:: max(1, pick.numel() // 200_000)]
+    c6 = cov[:, pick].cpu()
     mat = torch.stack([torch.stack([c6[0], c6[1], c6[2]], 1), torch.stack([c6[1], c6[3], c6[4]], 1), torch.stack([c6[2], c6[4], c6[5]], 1)], 1)
-    lam = torch.linalg.eigvalsh(mat).flip(1).clamp(min=0.0).t()  # descending, PSD
+    lam = torch.linalg.eigvalsh(mat).flip(1).clamp(min=0.0).t().to(x.device)  # descending, PSD
     l1 = lam[0]
     efloor = 64 * 2.2e-16 * (scale.max() ** 2)  # rounding floor of forming a covariance from coordinates of this size
     assert bool(((st.eig[:, pick] - lam).abs() <= 1e-9 * l1 + efloor).all()), "eigenvalues within 1e-9 of the largest"
@@ -185,8 +186,8 @@ def test_config4_full_size_two_epochs_vs_torch(E):
     g = torch.Generator(device="cuda").manual_seed(15)
     z = torch.round((2.2 + 0.05 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)) * 1e4) * 1e-4
     keep = ~((y > 300.0) & (y < 310.0))  # a strip disappears in epoch 2, another one appears
-    x2 = x[keep] + torch.where(x[keep] > 500.0, 0.1, 0.0)
-    y2, z2 = y[keep], z[keep] + torch.randn(int(keep.sum()), device="cuda", generator=g, dtype=torch.float64) * 0.002
+    x2, y2 = x[keep], y[keep]  # the part x > 500 m is lifted by 15 cm inside its voxel layer: the centroids move, the voxels stay
+    z2 = z[keep] + torch.where(x2 > 500.0, 0.15, 0.0) + torch.randn(int(keep.sum()), device="cuda", generator=g, dtype=torch.float64) * 0.002
     z2 = torch.round(z2 * 1e4) * 1e-4
     del keep
     tabs, refs = [], []

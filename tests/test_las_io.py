@@ -248,3 +248,14 @@ def test_las_to_laz_conversion_of_the_command_line(tmp_path):
         np.testing.assert_array_equal(res.df[c].to_numpy(), again.df[c].to_numpy(), err_msg=c)
     for c in "XYZ":
         assert np.abs(res.df[c].to_numpy() - df[c].to_numpy()).max() <= 2 * 0.000125 + 1e-9
+
+
+def test_writer_refuses_coordinates_that_do_not_fit_int32(tmp_path):
+    """laspy raises OverflowError where the int32 record cannot hold (c - offset) / scale; so does the native writer (no silent wrap)."""
+    from vapc_b200 import las
+
+    x = np.array([0.0, 600_000.0])  # 600 km at the default 0.25 mm scale: 2.4e9 units
+    with pytest.raises(OverflowError):
+        las.write_las(str(tmp_path / "far.las"), x, x * 0, x * 0, {}, {})
+    with pytest.raises(OverflowError):
+        las.write_las(str(tmp_path / "nan.las"), np.array([0.0, np.nan]), np.zeros(2), np.zeros(2), {}, {})

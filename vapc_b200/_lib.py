@@ -139,6 +139,7 @@ SIGNATURES = {
     "vapc_pack_partial_rows": (C.c_int, [P, P, P, P, I64, I64, I64, P, P]),
     "vapc_merge_partial_rows": (C.c_int, [P, P, I64, I32, P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, SZ, P]),
     "vapc_merge_sorted_tables": (C.c_int, [P, P, P, P, I64, I64, I64, P, P, P, P, I64, P, I32, I64, P, P, P, P, P]),
+    "vapc_merge_sorted_tables_stats": (C.c_int, [P, P, P, P, I64, I64, I64, P, P, P, P, I64, P, I32, I64, P, P, P, P, GP, C.POINTER(I32), P, P, P, P, P, P, P, P]),
     "vapc_reduce_candidates": (C.c_int, [P, P, P, I64, I64, P, P, P]),
     "vapc_key_histogram": (C.c_int, [P, I64, I32, I32, I32, P, P]),
     "vapc_laz_decode": (C.c_int, [P, I64, I64, I64, I32, I32, C.c_uint32, P, I32, P]),

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "math3.cuh"
 #include "segment_ws.cuh"
+#include "stats_row.cuh"
 
 namespace {
 using namespace segws;
@@ -664,8 +665,9 @@ __global__ void __launch_bounds__(kThreads) merge_partials_kernel(const KeyT* __
 // Both tables are key-sorted with unique keys: `own` = rows [own_first, own_first + n_own) of the local table (global keys given
 // separately), `u` = the received rows, sorted and combined per key beforehand.  u_new_before[j] = number of u rows in front of j
 // whose key the own rows do NOT hold (exclusive prefix, [nu + 1]); the merged table has n_own + u_new_before[nu] rows.
-//   own row i  -> output row i + u_new_before[lower_bound(u, key_i)], combined (Chan) with the u row of the same key if there is one
-//   u row j with a new key -> output row lower_bound(own, key_j) + u_new_before[j]
+//   own row i whose key u does not hold -> output row i + u_new_before[lower_bound(u, key_i)]        (merge_own_rows_kernel: the bulk)
+//   u row j -> output row lower_bound(own, key_j) + u_new_before[j]; combined (Chan: own first) with the own row of the same key if
+//   there is one                                                                                   (merge_u_rows_kernel: few rows)
 // One pass over the own rows (84 B read + written per row) instead of a radix sort of all keys + a gather-merge.
 __device__ __forceinline__ int64_t lower_bound_u64(const unsigned long long* __restrict__ keys, int64_t n, unsigned long long k) {
   int64_t lo = 0, hi = n;
@@ -683,53 +685,89 @@ __global__ void __launch_bounds__(kThreads) merge_own_rows_kernel(const unsigned
                                                                   const double* __restrict__ u_mean3, const double* __restrict__ u_m2, int64_t nu,
                                                                   const int64_t* __restrict__ u_new_before, int64_t nvox, KeyT* __restrict__ out_keys,
                                                                   uint32_t* __restrict__ out_count, double* __restrict__ out_mean3,
-                                                                  double* __restrict__ out_m2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                                  double* __restrict__ out_m2, Grid g, StatsOut so, int with_stats) {
+  // The own keys ascend with the thread, so do their positions in u: two threads of the CTA bracket the CTA's slice of u
+  // (a full binary search per row was a chain of ~18 dependent L2 reads in front of every row: 1.2 ms for 3.9e7 rows,
+  // twice what its 84 B per row cost), every row then searches only inside that bracket (usually 0-2 keys).
+  __shared__ int64_t bracket[2];
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+  if (nu > 0 && threadIdx.x < 2) {
+    const int64_t edge = threadIdx.x == 0 ? i0 : min(n_own, i0 + (int64_t)blockDim.x) - 1;
+    bracket[threadIdx.x] = lower_bound_u64(u_keys, nu, own_keys[edge]);
+  }
+  __syncthreads();
+  const int64_t i = i0 + threadIdx.x;
   if (i >= n_own) return;
   const unsigned long long key = own_keys[i];
   const int64_t src = own_first + i;
-  double na = (double)own_count[src], ma[3], Ma[6];
+  int64_t row = i;
+  if (nu > 0) {
+    const int64_t r = bracket[0] + lower_bound_u64(u_keys + bracket[0], bracket[1] - bracket[0], key);
+    if (r < nu && __ldg(u_keys + r) == key) return;  // u holds the key too: merge_u_rows_kernel combines the two rows (keeps this kernel lean)
+    row += u_new_before[r];
+  }
+  const unsigned na = own_count[src];
+  double ma[3], Ma[6];
 #pragma unroll
   for (int k = 0; k < 3; ++k) ma[k] = own_mean3[(int64_t)k * own_stride + src];
 #pragma unroll
   for (int k = 0; k < 6; ++k) Ma[k] = own_m2[(int64_t)k * own_stride + src];
-  int64_t row = i;
-  if (nu > 0) {
-    const int64_t r = lower_bound_u64(u_keys, nu, key);
-    row += u_new_before[r];
-    if (r < nu && __ldg(u_keys + r) == key) {
-      double mb[3], Mb[6];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) mb[k] = u_mean3[(int64_t)k * nu + r];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) Mb[k] = u_m2[(int64_t)k * nu + r];
-      chan_combine(na, ma, Ma, (double)u_count[r], mb, Mb);
-    }
-  }
   out_keys[row] = (KeyT)key;
-  out_count[row] = (uint32_t)na;
+  out_count[row] = na;
+  if (out_mean3) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) out_mean3[(int64_t)k * nvox + row] = ma[k];
+    for (int k = 0; k < 3; ++k) out_mean3[(int64_t)k * nvox + row] = ma[k];
+  }
+  if (out_m2) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) out_m2[(int64_t)k * nvox + row] = Ma[k];
+    for (int k = 0; k < 6; ++k) out_m2[(int64_t)k * nvox + row] = Ma[k];
+  }
+  if (with_stats) emit_voxel_stats(key, na, ma, Ma, g, row, so);
 }
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) merge_new_rows_kernel(const unsigned long long* __restrict__ own_keys, int64_t n_own,
+__global__ void __launch_bounds__(kThreads) merge_u_rows_kernel(const unsigned long long* __restrict__ own_keys, const uint32_t* __restrict__ own_count,
+                                                                const double* __restrict__ own_mean3, const double* __restrict__ own_m2,
+                                                                int64_t own_stride, int64_t own_first, int64_t n_own,
                                                                   const unsigned long long* __restrict__ u_keys, const uint32_t* __restrict__ u_count,
                                                                   const double* __restrict__ u_mean3, const double* __restrict__ u_m2, int64_t nu,
                                                                   const int64_t* __restrict__ u_new_before, int64_t nvox, KeyT* __restrict__ out_keys,
                                                                   uint32_t* __restrict__ out_count, double* __restrict__ out_mean3,
-                                                                  double* __restrict__ out_m2) {
+                                                                  double* __restrict__ out_m2, Grid g, StatsOut so, int with_stats) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nu || u_new_before[j + 1] == u_new_before[j]) return;  // the own rows hold this key: merged there
+  if (j >= nu) return;
   const unsigned long long key = u_keys[j];
-  const int64_t row = lower_bound_u64(own_keys, n_own, key) + u_new_before[j];
+  const int64_t at = lower_bound_u64(own_keys, n_own, key);
+  const int64_t row = at + u_new_before[j];
+  double nb = (double)u_count[j], mb[3], Mb[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) mb[k] = u_mean3[(int64_t)k * nu + j];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Mb[k] = u_m2[(int64_t)k * nu + j];
+  if (u_new_before[j + 1] == u_new_before[j]) {  // the own rows hold this key: own row first, then the received one (Chan)
+    const int64_t src = own_first + at;
+    double na = (double)own_count[src], ma[3], Ma[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ma[k] = own_mean3[(int64_t)k * own_stride + src];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Ma[k] = own_m2[(int64_t)k * own_stride + src];
+    chan_combine(na, ma, Ma, nb, mb, Mb);
+    nb = na;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mb[k] = ma[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Mb[k] = Ma[k];
+  }
   out_keys[row] = (KeyT)key;
-  out_count[row] = u_count[j];
+  out_count[row] = (uint32_t)nb;
+  if (out_mean3) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) out_mean3[(int64_t)k * nvox + row] = u_mean3[(int64_t)k * nu + j];
+    for (int k = 0; k < 3; ++k) out_mean3[(int64_t)k * nvox + row] = mb[k];
+  }
+  if (out_m2) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) out_m2[(int64_t)k * nvox + row] = u_m2[(int64_t)k * nu + j];
+    for (int k = 0; k < 6; ++k) out_m2[(int64_t)k * nvox + row] = Mb[k];
+  }
+  if (with_stats) emit_voxel_stats(key, (unsigned)nb, mb, Mb, g, row, so);
 }
 
 // local voxel keys -> keys in the GLOBAL layout (unpack with the local grid, repack with the global one) + the histogram of
@@ -1052,17 +1090,25 @@ extern "C" int vapc_merge_partial_rows(const void* keys_sorted, const uint32_t* 
   return VAPC_OK;
 }
 
-extern "C" int vapc_merge_sorted_tables(const uint64_t* own_keys, const uint32_t* own_count, const double* own_mean3, const double* own_m2,
-                                        int64_t own_stride, int64_t own_first, int64_t n_own, const uint64_t* u_keys, const uint32_t* u_count,
-                                        const double* u_mean3, const double* u_m2, int64_t nu, const int64_t* u_new_before, int32_t key_bytes,
-                                        int64_t nvoxels_host, void* out_keys, uint32_t* out_count, double* out_mean3, double* out_m2, void* stream) {
+extern "C" int vapc_merge_sorted_tables_stats(const uint64_t* own_keys, const uint32_t* own_count, const double* own_mean3, const double* own_m2,
+                                              int64_t own_stride, int64_t own_first, int64_t n_own, const uint64_t* u_keys, const uint32_t* u_count,
+                                              const double* u_mean3, const double* u_m2, int64_t nu, const int64_t* u_new_before, int32_t key_bytes,
+                                              int64_t nvoxels_host, void* out_keys, uint32_t* out_count, double* out_mean3, double* out_m2,
+                                              const vapc_grid_t* grid_host, const int32_t* axis_order_host, double* density, double* cog3,
+                                              double* std3, double* cov6, double* eig3, double* eign3, double* feat8, void* stream) {
   if (n_own < 0 || nu < 0 || nvoxels_host < n_own || own_first < 0 || own_stride < own_first + n_own)
     return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables: bad arguments");
   if (key_bytes != 4 && key_bytes != 8) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables: key_bytes must be 4 or 8");
+  StatsOut so{density, cog3, std3, cov6, eig3, eign3, feat8, nvoxels_host, {}};
+  const int with_stats = density || cog3 || so.needs_m2();
+  if (with_stats && !grid_host) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables_stats: statistics need the grid");
+  if (!stats_axes_from_order(axis_order_host, &so.ax)) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables_stats: axis_order must be a permutation of 0, 1, 2");
   if (nvoxels_host == 0) return VAPC_OK;
-  if (!out_keys || !out_count || !out_mean3 || !out_m2 || (n_own > 0 && (!own_keys || !own_count || !own_mean3 || !own_m2)) ||
+  if (!out_keys || !out_count || (n_own > 0 && (!own_keys || !own_count || !own_mean3 || !own_m2)) ||
       (nu > 0 && (!u_keys || !u_count || !u_mean3 || !u_m2 || !u_new_before)))
     return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables: null buffer");
+  Grid g{};
+  if (grid_host) g = to_device_grid(grid_host);
   cudaStream_t s = as_stream(stream);
   typedef unsigned long long u64;
   const u64* ok = reinterpret_cast<const u64*>(own_keys);
@@ -1070,15 +1116,25 @@ extern "C" int vapc_merge_sorted_tables(const uint64_t* own_keys, const uint32_t
   const unsigned g1 = (unsigned)((n_own + kThreads - 1) / kThreads), g2 = (unsigned)((nu + kThreads - 1) / kThreads);
   if (key_bytes == 4) {
     if (n_own) VAPC_LAUNCH(merge_own_rows_kernel<uint32_t>, g1, kThreads, 0, s, ok, own_count, own_mean3, own_m2, own_stride, own_first, n_own, uk, u_count, u_mean3, u_m2,
-                           nu, u_new_before, nvoxels_host, static_cast<uint32_t*>(out_keys), out_count, out_mean3, out_m2);
-    if (nu) VAPC_LAUNCH(merge_new_rows_kernel<uint32_t>, g2, kThreads, 0, s, ok, n_own, uk, u_count, u_mean3, u_m2, nu, u_new_before, nvoxels_host,
-                        static_cast<uint32_t*>(out_keys), out_count, out_mean3, out_m2);
+                           nu, u_new_before, nvoxels_host, static_cast<uint32_t*>(out_keys), out_count, out_mean3, out_m2, g, so, with_stats);
+    if (nu) VAPC_LAUNCH(merge_u_rows_kernel<uint32_t>, g2, kThreads, 0, s, ok, own_count, own_mean3, own_m2, own_stride, own_first, n_own, uk, u_count, u_mean3, u_m2, nu, u_new_before, nvoxels_host,
+                        static_cast<uint32_t*>(out_keys), out_count, out_mean3, out_m2, g, so, with_stats);
   } else {
     if (n_own) VAPC_LAUNCH(merge_own_rows_kernel<u64>, g1, kThreads, 0, s, ok, own_count, own_mean3, own_m2, own_stride, own_first, n_own, uk, u_count, u_mean3, u_m2, nu,
-                           u_new_before, nvoxels_host, static_cast<u64*>(out_keys), out_count, out_mean3, out_m2);
-    if (nu) VAPC_LAUNCH(merge_new_rows_kernel<u64>, g2, kThreads, 0, s, ok, n_own, uk, u_count, u_mean3, u_m2, nu, u_new_before, nvoxels_host,
-                        static_cast<u64*>(out_keys), out_count, out_mean3, out_m2);
+                           u_new_before, nvoxels_host, static_cast<u64*>(out_keys), out_count, out_mean3, out_m2, g, so, with_stats);
+    if (nu) VAPC_LAUNCH(merge_u_rows_kernel<u64>, g2, kThreads, 0, s, ok, own_count, own_mean3, own_m2, own_stride, own_first, n_own, uk, u_count, u_mean3, u_m2, nu, u_new_before, nvoxels_host,
+                        static_cast<u64*>(out_keys), out_count, out_mean3, out_m2, g, so, with_stats);
   }
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
+}
+
+extern "C" int vapc_merge_sorted_tables(const uint64_t* own_keys, const uint32_t* own_count, const double* own_mean3, const double* own_m2,
+                                        int64_t own_stride, int64_t own_first, int64_t n_own, const uint64_t* u_keys, const uint32_t* u_count,
+                                        const double* u_mean3, const double* u_m2, int64_t nu, const int64_t* u_new_before, int32_t key_bytes,
+                                        int64_t nvoxels_host, void* out_keys, uint32_t* out_count, double* out_mean3, double* out_m2, void* stream) {
+  if (nvoxels_host > 0 && (!out_mean3 || !out_m2)) return vapc_set_error(VAPC_E_INVALID, "vapc_merge_sorted_tables: null buffer");
+  return vapc_merge_sorted_tables_stats(own_keys, own_count, own_mean3, own_m2, own_stride, own_first, n_own, u_keys, u_count, u_mean3, u_m2, nu, u_new_before,
+                                        key_bytes, nvoxels_host, out_keys, out_count, out_mean3, out_m2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, nullptr, stream);
 }

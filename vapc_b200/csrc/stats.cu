@@ -9,81 +9,26 @@
 
 #include "common.cuh"
 #include "math3.cuh"
+#include "stats_row.cuh"
 
 namespace {
 constexpr int kThreads = 128;
-// Output rows of the axis-indexed tables.  The table's keys / moments may live in a permuted axis order (multi-GPU: the axis the
-// chunks are separated along leads the key, vapc_b200/dist.py); the outputs are always x, y, z: internal axis i -> row axis[i] of
-// cog / std, internal covariance component k -> component cov[k].
-struct StatsAxes {
-  int axis[3];
-  int cov[6];
-};
-
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) voxel_stats_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ count,
                                                                const double* __restrict__ mean3, const double* __restrict__ m2,
-                                                               int64_t nvox, Grid g, double* __restrict__ density,
-                                                               double* __restrict__ cog3, double* __restrict__ std3,
-                                                               double* __restrict__ cov6, double* __restrict__ eig3,
-                                                               double* __restrict__ eign3, double* __restrict__ feat8, StatsAxes ax) {
+                                                               int64_t nvox, Grid g, StatsOut o) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvox) return;
-  const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  const unsigned n = count[v];
-  if (density) density[v] = (double)n / (g.vs * g.vs * g.vs);  // point_count / voxel_size**3
-  if (cog3) {
-    long long vx, vy, vz;
-    unpack_key((unsigned long long)keys[v], g, vx, vy, vz);
-    cog3[ax.axis[0] * nvox + v] = shift_center(vx, g.ox, g.vs) + mean3[v];
-    cog3[ax.axis[1] * nvox + v] = shift_center(vy, g.oy, g.vs) + mean3[nvox + v];
-    cog3[ax.axis[2] * nvox + v] = shift_center(vz, g.oz, g.vs) + mean3[2 * nvox + v];
-  }
-  if (!(std3 || cov6 || eig3 || eign3 || feat8)) return;
-  double c[6];
-  if (n > 1) {
-    const double d = 1.0 / (double)(n - 1);  // one reciprocal instead of six divisions (<= 1 ulp apart)
+  double mean[3] = {0, 0, 0}, M[6] = {0, 0, 0, 0, 0, 0};
+  if (o.cog3) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c[k] = m2[(int64_t)k * nvox + v] * d;
-  } else {
+    for (int k = 0; k < 3; ++k) mean[k] = mean3[(int64_t)k * nvox + v];
+  }
+  if (o.needs_m2()) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c[k] = nan;
+    for (int k = 0; k < 6; ++k) M[k] = m2[(int64_t)k * nvox + v];
   }
-  if (cov6) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cov6[(int64_t)ax.cov[k] * nvox + v] = c[k];
-  }
-  if (std3) {
-    // fmax(NaN, 0) would hide the n == 1 NaN, so clamp only real values (rounding can leave -1e-33)
-    std3[ax.axis[0] * nvox + v] = c[0] < 0.0 ? 0.0 : sqrt(c[0]);
-    std3[ax.axis[1] * nvox + v] = c[3] < 0.0 ? 0.0 : sqrt(c[3]);
-    std3[ax.axis[2] * nvox + v] = c[5] < 0.0 ? 0.0 : sqrt(c[5]);
-  }
-  if (!(eig3 || eign3 || feat8)) return;
-  double l1 = nan, l2 = nan, l3 = nan;
-  if (n > 1) {
-    eig3_sym(c[0], c[1], c[2], c[3], c[4], c[5], l1, l2, l3);
-    // a covariance is positive semi-definite: rounding noise below zero is clamped (the reference's
-    // dgeev returns +-1e-18-sized noise of either sign there; see DESIGN.md, parity rule H7)
-    l2 = fmax(l2, 0.0);
-    l3 = fmax(l3, 0.0);
-  }
-  if (eig3) { eig3[v] = l1; eig3[nvox + v] = l2; eig3[2 * nvox + v] = l3; }
-  if (!(eign3 || feat8)) return;
-  const double total = l1 + l2 + l3;
-  const double inv_total = 1.0 / total, inv_l1 = 1.0 / l1;  // 0 / 0 = NaN and x / 0 = inf behave the same through the reciprocal
-  const double e1 = l1 * inv_total, e2 = l2 * inv_total, e3 = l3 * inv_total;
-  if (eign3) { eign3[v] = e1; eign3[nvox + v] = e2; eign3[2 * nvox + v] = e3; }
-  if (feat8) {
-    feat8[v] = total;                                                                       // Sum_of_Eigenvalues
-    feat8[nvox + v] = cbrt(l1 * l2 * l3);                                                   // Omnivariance ((.) ** (1/3), non-negative argument)
-    feat8[2 * nvox + v] = -(e1 * safe_log(e1) + e2 * safe_log(e2) + e3 * safe_log(e3));     // Eigenentropy
-    feat8[3 * nvox + v] = (l1 - l3) * inv_l1;                                               // Anisotropy
-    feat8[4 * nvox + v] = (l2 - l3) * inv_l1;                                               // Planarity
-    feat8[5 * nvox + v] = (l1 - l2) * inv_l1;                                               // Linearity
-    feat8[6 * nvox + v] = e3;                                                               // Surface_Variation
-    feat8[7 * nvox + v] = l3 * inv_l1;                                                      // Sphericity
-  }
+  emit_voxel_stats((unsigned long long)keys[v], count[v], mean, M, g, v, o);
 }
 
 // out[i] = table[index[i]]
@@ -118,30 +63,18 @@ extern "C" int vapc_voxel_stats_axes(const void* voxel_keys, const uint32_t* cou
                                      int64_t nvoxels, const vapc_grid_t* grid_host, const int32_t* axis_order_host, double* density,
                                      double* cog3, double* std3, double* cov6, double* eig3, double* eign3, double* feat8, void* stream) {
   if (!grid_host || nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats: bad arguments");
-  StatsAxes ax = {{0, 1, 2}, {0, 1, 2, 3, 4, 5}};
-  if (axis_order_host) {
-    int seen = 0;
-    for (int i = 0; i < 3; ++i) {
-      if (axis_order_host[i] < 0 || axis_order_host[i] > 2) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats_axes: axis_order must be a permutation of 0, 1, 2");
-      ax.axis[i] = axis_order_host[i];
-      seen |= 1 << axis_order_host[i];
-    }
-    if (seen != 7) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats_axes: axis_order must be a permutation of 0, 1, 2");
-    static const int pair[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};  // (a, b) -> xx xy xz yy yz zz
-    int k = 0;
-    for (int i = 0; i < 3; ++i)
-      for (int j = i; j < 3; ++j) ax.cov[k++] = pair[ax.axis[i]][ax.axis[j]];
-  }
+  StatsOut o{density, cog3, std3, cov6, eig3, eign3, feat8, nvoxels, {}};
+  if (!stats_axes_from_order(axis_order_host, &o.ax)) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats_axes: axis_order must be a permutation of 0, 1, 2");
   if (nvoxels == 0) return VAPC_OK;
   if (!voxel_keys || !count || !mean3 || !m2) return vapc_set_error(VAPC_E_INVALID, "vapc_voxel_stats: null input");
   const Grid g = to_device_grid(grid_host);
   const unsigned blocks = (unsigned)((nvoxels + kThreads - 1) / kThreads);
   if (grid_host->key_bytes == 4)
     VAPC_LAUNCH(voxel_stats_kernel<uint32_t>, blocks, kThreads, 0, as_stream(stream), static_cast<const uint32_t*>(voxel_keys), count, mean3, m2,
-                                                                             nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8, ax);
+                                                                             nvoxels, g, o);
   else
     VAPC_LAUNCH(voxel_stats_kernel<unsigned long long>, blocks, kThreads, 0, as_stream(stream), 
-        static_cast<const unsigned long long*>(voxel_keys), count, mean3, m2, nvoxels, g, density, cog3, std3, cov6, eig3, eign3, feat8, ax);
+        static_cast<const unsigned long long*>(voxel_keys), count, mean3, m2, nvoxels, g, o);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }

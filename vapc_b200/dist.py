@@ -141,9 +141,17 @@ class ShardedVoxelTable:
     # Internal axis order: axis_order[0] is the coordinate axis that leads the packed key (choose_axis_order).  grid, voxel_keys,
     # mean3 and m2 are expressed in THAT order; stats() and voxel_coords() hand everything back in x, y, z order.
     axis_order: tuple = (0, 1, 2)
+    fused_stats: object = None  # VoxelStats formed inside the owner merge (the merged moments were then not written: mean3 / m2 None)
 
     def stats(self, density=True, cog=True, std=True, cov=True, eig=True, eig_n=True, feat=True):
         from . import engine as E
+
+        want = dict(density=density, cog=cog, std=std, cov=cov, eig=eig, eig_n=eig_n, feat=feat)
+        if self.fused_stats is not None and all(getattr(self.fused_stats, k) is not None for k, w in want.items() if w):
+            return E.VoxelStats(**{k: getattr(self.fused_stats, k) for k, w in want.items() if w})
+        if self.mean3 is None:
+            raise ValueError("this table was built with its statistics fused into the merge (keep_moments=False): ask voxel_statistics for "
+                             "the columns up front, or pass keep_moments=True")
 
         c = E.VoxelCloud()
         c.grid, c.nvoxels, c.voxel_keys, c.count, c.mean3, c.m2 = self.grid, self.nvoxels, self.voxel_keys, self.count, self.mean3, self.m2
@@ -329,7 +337,7 @@ def gather_bounds(x, y, z, group=None) -> np.ndarray:
 
 
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
-                     thresholds=None, keep_local=False, stats_columns=None, axis_order="auto"):
+                     thresholds=None, keep_local=False, stats_columns=None, axis_order="auto", keep_moments=None):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
@@ -339,6 +347,9 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     (in place) with the received ones.  Five small device -> host copies synchronise the host: local bounds, local voxel
     count, global bounds, the all-gathered send-count matrix, the merged voxel count.
 
+    keep_moments: keep the merged (mean3, m2) moments in the table (needed to merge it again or to ask for other statistics later).
+    Default: only when no statistics are asked for here; otherwise the statistics are formed inside the owner's merge pass and the
+    merged moments are never written (72 B per voxel each way saved).
     axis_order: "auto" (choose_axis_order from the ranks' bounding boxes) or a permutation of (0, 1, 2): the coordinate axis that
     leads the packed key.  Results come back in x, y, z order (ShardedVoxelTable.stats / voxel_coords); only the ROW order of the
     sharded table follows the internal order.
@@ -457,24 +468,30 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
         vm = n_own + int(new_before[-1].item())
     else:
         nu, u_keys64, u_count, u_mean, u_m2, new_before, vm = 0, None, None, None, None, None, n_own
+    if keep_moments is None:
+        keep_moments = not with_stats
     out_keys = torch.empty(vm, dtype=kdt, device=dev)
     out_count = torch.empty(vm, dtype=torch.int32, device=dev)
-    out_mean = torch.empty((3, vm), dtype=torch.float64, device=dev)
-    out_m2 = torch.empty((6, vm), dtype=torch.float64, device=dev)
+    out_mean = torch.empty((3, vm), dtype=torch.float64, device=dev) if keep_moments else None
+    out_m2 = torch.empty((6, vm), dtype=torch.float64, device=dev) if keep_moments else None
+    fused = None
+    if with_stats:
+        names = ("density", "cog", "std", "cov", "eig", "eig_n", "feat")
+        cols = names if stats_columns is None else tuple(k for k in names if k in stats_columns)
+        shapes = dict(density=(vm,), cog=(3, vm), std=(3, vm), cov=(6, vm), eig=(3, vm), eig_n=(3, vm), feat=(8, vm))
+        fused = E.VoxelStats(**{k: torch.empty(shapes[k], dtype=torch.float64, device=dev) for k in cols})
+    order_c = (C.c_int32 * 3)(*axis_order)
     if vm:
-        L.call("vapc_merge_sorted_tables", E._ptr(own_keys.contiguous()), E._ptr(local.count), E._ptr(local.mean3), E._ptr(local.m2), v, lo, n_own,
+        stat_ptrs = [E._ptr(getattr(fused, k) if fused is not None else None) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")]
+        L.call("vapc_merge_sorted_tables_stats", E._ptr(own_keys.contiguous()), E._ptr(local.count), E._ptr(local.mean3), E._ptr(local.m2), v, lo, n_own,
                E._ptr(u_keys64), E._ptr(u_count), E._ptr(u_mean), E._ptr(u_m2), nu, E._ptr(new_before), g.key_bytes, vm,
-               E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), E._stream())
+               E._ptr(out_keys), E._ptr(out_count), E._ptr(out_mean), E._ptr(out_m2), C.byref(g), order_c, *stat_ptrs, E._stream())
     table = ShardedVoxelTable(grid=g, nvoxels=vm, voxel_keys=out_keys, count=out_count, mean3=out_mean, m2=out_m2,
                               thresholds=host[world * world:].tolist(), partial_rows_sent=int(sum(send_remote)),
                               partial_rows_received=n_in, exchange="peer" if peer is not None else "nccl", axis_order=axis_order)
     table.local_voxels = v
-    if not with_stats:
-        st = None
-    elif stats_columns is not None:  # only these columns (a host that wants the table back pays PCIe time per column)
-        st = table.stats(**{k: (k in stats_columns) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")})
-    else:
-        st = table.stats()
+    table.fused_stats = fused
+    st = fused
     if keep_local:
         # keep_local: a third value, the LocalShard for rows_from_owner / point_distance / closest_to_cog below
         recv_keys = in_rows[:, 0].contiguous().view(torch.int64).clone() if n_in else torch.empty(0, dtype=torch.int64, device=dev)

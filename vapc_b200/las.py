@@ -225,14 +225,20 @@ def _build_las14(x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.n
     dt = np.dtype(fields)
     rec = np.zeros(n, dtype=dt)
     for k, (c, up) in enumerate(((x, "X"), (y, "Y"), (z, "Z"))):
-        rec[up] = np.round((c - offsets[k]) / scales[k]).astype(np.int64).astype(np.int32)
+        q = np.round((c - offsets[k]) / scales[k])
+        # laspy refuses what does not fit the record's int32 (OverflowError) instead of wrapping silently; NaN / inf likewise
+        if n and not (np.isfinite(q).all() and q.min() >= -2147483648.0 and q.max() <= 2147483647.0):
+            raise OverflowError(f"{up} coordinates do not fit int32 records with scale {scales[k]} and offset {offsets[k]} "
+                                "(non-finite values, or an extent beyond 2^31 scale units)")
+        rec[up] = q.astype(np.int64).astype(np.int32)
     subs = _sub_fields(point_format)
     sub_lookup = {s[0]: (byte, s[1], s[2]) for byte, lst in subs.items() for s in lst}
     for name, arr in standard.items():
         arr = np.asarray(arr)
         if name in sub_lookup:
             byte, shift, mask = sub_lookup[name]
-            rec[byte] |= ((arr.astype(np.int64) & mask) << shift).astype(np.uint8)
+            with np.errstate(invalid="ignore"):
+                rec[byte] |= ((arr.astype(np.int64) & mask) << shift).astype(np.uint8)
         elif name in dt.names:
             with np.errstate(invalid="ignore"):
                 rec[name] = arr.astype(dt[name])
@@ -359,7 +365,12 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     dt = np.dtype(fields)
     rec = np.zeros(n, dtype=dt)
     for k, (c, up) in enumerate(((x, "X"), (y, "Y"), (z, "Z"))):
-        rec[up] = np.round((c - offsets[k]) / scales[k]).astype(np.int64).astype(np.int32)
+        q = np.round((c - offsets[k]) / scales[k])
+        # laspy refuses what does not fit the record's int32 (OverflowError) instead of wrapping silently; NaN / inf likewise
+        if n and not (np.isfinite(q).all() and q.min() >= -2147483648.0 and q.max() <= 2147483647.0):
+            raise OverflowError(f"{up} coordinates do not fit int32 records with scale {scales[k]} and offset {offsets[k]} "
+                                "(non-finite values, or an extent beyond 2^31 scale units)")
+        rec[up] = q.astype(np.int64).astype(np.int32)
     sub_lookup = {s_[0]: (byte, s_[1], s_[2]) for byte, lst in _sub_fields(point_format).items() for s_ in lst}
     for name, arr in standard.items():
         arr = np.asarray(arr)
