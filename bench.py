@@ -464,6 +464,7 @@ def main():
     torch.cuda.synchronize()
     nvox = cloud.nvoxels
     exchange_kind = getattr(cloud, "exchange", None)
+    cloud_axis_order = tuple(getattr(cloud, "axis_order", (0, 1, 2)))
     key_bytes = cloud.grid.key_bytes
     total_bits = cloud.grid.total_bits
     sorted_by = getattr(cloud, "sorted_by", None)
@@ -544,6 +545,30 @@ def main():
         extra["bounds_computed"] = {"ms_per_step": t2["ms_per_step"], "value": n / (t2["ms_per_step"] * 1e-3),
                                     "what": "the same step without caller bounds: vapc_minmax_f64 reads x, y, z once more (24 B/point)"}
         t2 = None
+
+    # ---- N = 1 extra: one GPU's chunk of configs[2] (the N > 1 workload) voxelised alone: the N = 1 point of THAT scaling curve -------
+    if not multi and not chunk_alone and not args.no_extra:
+        keep = (x, y, z)
+        del x, y, z
+        cx, cy, cz = synth.clustered_chunk(125_000_000, 0, 1, device, seed=3, scan_order=True)
+
+        def step_chunk():
+            c = E.VoxelCloud.build(cx, cy, cz, VOXEL_SIZE_MULTI, ORIGIN, keep_columns=False, want_point2voxel=False)
+            return c, c.stats(**FULL)
+        for _ in range(2):
+            step_chunk()
+        tc = time_steps(step_chunk, args.steps, barrier, world, device, dist, L=L)
+        windows.append(tc["window"])
+        extra["configs2_one_gpu"] = {"ms_per_step": tc["ms_per_step"], "value": 125_000_000 / (tc["ms_per_step"] * 1e-3), "points": 125_000_000,
+                                     "voxel_size": VOXEL_SIZE_MULTI, "voxels": tc["out"][0].nvoxels, "key_bits": tc["out"][0].grid.total_bits,
+                                     "what": "configs[2] at N = 1: the 1.25e8-point clustered chunk one rank of the N > 1 run holds, voxelised alone with "
+                                             "the calls every rank issues before the exchange (bounds computed, no point->voxel map).  `bench.py --gpus N` "
+                                             "(N > 1) reports configs[2]: its value / (N x this value) is that workload's scaling efficiency"}
+        tc = None
+        del cx, cy, cz
+        torch.cuda.empty_cache()
+        x, y, z = keep
+        del keep
 
     # ---- N > 1: correctness of the sharded table, then the other layouts ------------------------------------------------------
     if multi:
@@ -721,7 +746,12 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload, voxels_per_gpu=nvox, key_bits=total_bits, radix_passes=passes,
                                                  **({"grouping": sorted_by} if sorted_by else {}),
-                                                 **({"exchange": exchange_kind, "voxels_all_gpus": nvox_global} if multi else {})),
+                                                 **({"exchange": exchange_kind, "voxels_all_gpus": nvox_global,
+                                                     "key_axis_order": list(cloud_axis_order)} if multi else {})),
+            **({"n1_same_workload": {"value_per_gpu": extra["one_gpu_same_workload"]["value_per_gpu"],
+                                     "efficiency_inputs": "this line's value / (n_gpus x value_per_gpu): every rank's chunk voxelised alone in the same "
+                                                          "run; the N = 1 bench line measures configs[1] (a different cloud) and carries the same figure as "
+                                                          "extra.configs2_one_gpu"}} if multi else {}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check, "extra": extra, "kernels": per_kernel, "abi_calls": breakdown,
             "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3), "gaps_between_calls_ms": gaps,
