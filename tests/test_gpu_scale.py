@@ -184,7 +184,8 @@ def test_config4_full_size_two_epochs_vs_torch(E):
     n, vs, alpha = 200_000_000, 0.5, 0.005
     x, y, _ = quantised_uniform(n, (700.0, 700.0, 10.0), 14)
     g = torch.Generator(device="cuda").manual_seed(15)
-    z = torch.round((2.2 + 0.05 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)) * 1e4) * 1e-4
+    # a surface of 2 cm thickness: the test statistic is the shift against the spread of the POINTS (bi_vapc.py:112-117), 0.15 m / 0.02 m
+    z = torch.round((2.2 + 0.02 * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)) * 1e4) * 1e-4
     keep = ~((y > 300.0) & (y < 310.0))  # a strip disappears in epoch 2, another one appears
     x2, y2 = x[keep], y[keep]  # the part x > 500 m is lifted by 15 cm inside its voxel layer: the centroids move, the voxels stay
     z2 = z[keep] + torch.where(x2 > 500.0, 0.15, 0.0) + torch.randn(int(keep.sum()), device="cuda", generator=g, dtype=torch.float64) * 0.002

@@ -176,18 +176,25 @@ class Vapc:
             self._cols.append(name)
         self._lazy[name] = (kind, tensor, cloud)
 
-    def _lazy_host(self, name) -> np.ndarray:
-        """A pending column as a fresh host array of N rows."""
+    def _lazy_device(self, name) -> torch.Tensor:
+        """A pending column as an [N] device tensor (the voxel column broadcast through the point -> voxel map)."""
         kind, t, cloud = self._lazy[name]
         if kind == "voxel":
             if t.dtype in (torch.float64, torch.int32):
                 t = cloud.broadcast(t.contiguous())
             else:
                 t = t[_u32(cloud.point2voxel)]
-        return self._host(t).copy()
+        return t
+
+    def _lazy_host(self, name) -> np.ndarray:
+        """A pending column as a fresh host array of N rows."""
+        return self._host(self._lazy_device(name)).copy()
 
     def _materialise(self, only=None):
-        """Broadcast pending columns (all, or the named ones) into the host frame, keeping the logical column order."""
+        """Broadcast pending columns (all, or the named ones) into the host frame, keeping the logical column order.  The 8-byte
+        columns (float64, and int64 carried as bit patterns) land in two [k, N] blocks through the double-buffered pinned staging of
+        _download_rows; when everything pending is materialised the frame is rebuilt from column views in the final order, so that
+        neither pandas' consolidation nor a re-ordering copy touches the N x 39 values again."""
         if not self._lazy:
             if self._cols is not None and list(self._df.columns) == self._cols:
                 self._cols = None
@@ -195,21 +202,46 @@ class Vapc:
         names = [c for c in self._cols if c in self._lazy and (only is None or c in only)]
         if not names:
             return
-        new = {c: self._lazy_host(c) for c in names}
-        fresh = [c for c in names if c not in self._df.columns]
+        n = len(self._df)
+        new = {}
+        for dt_t, dt_n in ((torch.float64, np.float64), (torch.int64, np.int64)):
+            group = [c for c in names if self._lazy[c][1].dtype == dt_t]
+            if group and n:
+                block = np.empty((len(group), n), dtype=dt_n)
+                _download_rows(block.view(np.float64), list(range(len(group))), lambda i: self._lazy_device(group[i]).view(torch.float64))
+                new.update({c: block[i] for i, c in enumerate(group)})
         for c in names:
-            if c not in fresh:
-                self._df[c] = new[c]
-        if fresh:
-            # one concat instead of one frame insertion per column (39 of them for the full attribute set)
-            add = pd.DataFrame({c: new[c] for c in fresh}, index=self._df.index, copy=False)
-            self._df = pd.concat([self._df, add], axis=1)
+            if c not in new:
+                new[c] = self._lazy_host(c)
         for c in names:
             del self._lazy[c]
-        if not self._lazy:
-            if list(self._df.columns) != self._cols:
-                self._df = self._df[self._cols]
+        plain = all(isinstance(self._df[c].dtype, np.dtype) for c in self._df.columns)
+        if not self._lazy and plain:
+            # final order in one go: every column its own array (existing ones as views), no block consolidation, no reorder copy
+            def existing(c):
+                a = self._df[c].to_numpy()
+                if not a.flags.writeable:  # pandas hands out read-only views (copy-on-write); the new frame takes the column over
+                    try:
+                        a.flags.writeable = True
+                    except ValueError:
+                        a = a.copy()
+                return a
+
+            cols = {c: (new[c] if c in new else existing(c)) for c in self._cols}
+            self._df = pd.DataFrame(cols, index=self._df.index, copy=False)
             self._cols = None
+        else:
+            fresh = [c for c in names if c not in self._df.columns]
+            for c in names:
+                if c not in fresh:
+                    self._df[c] = new[c]
+            if fresh:
+                add = pd.DataFrame({c: new[c] for c in fresh}, index=self._df.index, copy=False)
+                self._df = pd.concat([self._df, add], axis=1)
+            if not self._lazy:
+                if list(self._df.columns) != self._cols:
+                    self._df = self._df[self._cols]
+                self._cols = None
         self._resign()  # same points, possibly a new frame object
 
     def _host_column(self, name, dtype=None) -> np.ndarray:
