@@ -91,32 +91,60 @@ CPU_KIND_TEXT = {
 }
 
 
-def cpu_reference_once(x, y, z):
+def cpu_reference_once(x, y, z, voxel_size=None):
     """One pass of the reference's CPU path over host columns: (kind, seconds, voxels).  kind "reference" = the unmodified reference
     (oracle/ref_harness.py over oracle/_ref), "port" = oracle/ref_port.py when the reference package is not there."""
     from oracle import ref_harness
 
+    voxel_size = VOXEL_SIZE if voxel_size is None else voxel_size
     if ref_harness.available():
         ref_harness.import_reference()
         t0 = time.perf_counter()
-        v = ref_harness.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN)
+        v = ref_harness.full_attribute_set(x, y, z, voxel_size, ORIGIN)
         dt = time.perf_counter() - t0
         df, kind = v.df, "reference"
     else:
         from oracle import ref_port
 
         t0 = time.perf_counter()
-        df = ref_port.full_attribute_set(x, y, z, VOXEL_SIZE, ORIGIN, with_eigen=True)
+        df = ref_port.full_attribute_set(x, y, z, voxel_size, ORIGIN, with_eigen=True)
         dt = time.perf_counter() - t0
         kind = "port"
     nvox = int(df[["voxel_x", "voxel_y", "voxel_z"]].drop_duplicates().shape[0])
     return kind, dt, nvox
 
 
+def gen_crop_host_clustered(n_sample, seed=3):
+    """A square crop of the configs[2] cloud law (tools/synth.py: terrain sheet + trees, 1e6 points per 1000 m2) holding n_sample points.
+    numpy only: the CPU legs fork worker processes, and torch's thread pools do not survive a fork."""
+    import numpy as np
+
+    side = float(np.sqrt(n_sample / 1000.0))
+    rng = np.random.default_rng(seed)
+    terrain = lambda x, y: 5.0 * np.sin(x / 37.0) * np.cos(y / 53.0) + 0.02 * x  # noqa: E731
+    nt = int(0.6 * n_sample)
+    tx, ty = rng.random(nt) * side, rng.random(nt) * side
+    tz = terrain(tx, ty) + (rng.random(nt) - 0.5) * 0.1
+    ntrees = max(1, int(round(0.2 * side * side)))
+    cx, cy, ch = rng.random(ntrees) * side, rng.random(ntrees) * side, 5.0 + 20.0 * rng.random(ntrees)
+    nb = n_sample - nt
+    t = rng.integers(0, ntrees, nb)
+    r = rng.standard_normal((nb, 3))
+    crown = rng.random(nb) < 0.8
+    h = rng.random(nb)
+    bx = cx[t] + np.where(crown, r[:, 0] * 1.5, r[:, 0] * 0.1)
+    by = cy[t] + np.where(crown, r[:, 1] * 1.5, r[:, 1] * 0.1)
+    bz = terrain(cx[t], cy[t]) + np.where(crown, ch[t] * (0.6 + 0.4 * h) + r[:, 2] * 0.8, ch[t] * 0.6 * h)
+    x, y, z = (np.round(np.concatenate(c) / QUANT) * QUANT for c in ((tx, bx), (ty, by), (tz, bz)))
+    order = np.lexsort((x, np.floor(y / 2.0)))  # scan lines: 2 m strips in y, x ascending inside a strip
+    return x[order], y[order], z[order], (f"square crop of {side:.1f} m x {side:.1f} m of the configs[2] cloud law at its density: "
+                                          f"{n_sample} points")
+
+
 def _cpu_worker(job):
-    n_sample, seed = job
-    x, y, z, _ = gen_crop_host(n_sample, seed=seed)
-    return cpu_reference_once(x, y, z)
+    n_sample, seed, clustered = job
+    x, y, z, _ = gen_crop_host_clustered(n_sample, seed=seed) if clustered else gen_crop_host(n_sample, seed=seed)
+    return cpu_reference_once(x, y, z, VOXEL_SIZE_MULTI if clustered else VOXEL_SIZE)
 
 
 def run_reference_arm(args):
@@ -130,16 +158,17 @@ def run_reference_arm(args):
 
     cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     budget = 150.0 / max(1, args.steps + args.warmup)  # seconds per step
-    n_sample = args.cpu_sample or int(min(200_000, max(2_000, budget * 5_000)))
-    _, _, _, what = gen_crop_host(n_sample)
+    clustered = args.gpus > 1  # the arm follows the GPU arm's config: configs[1] at N = 1, configs[2] at N > 1
+    n_sample = args.cpu_sample or int(min(200_000, max(2_000, budget * (2_000 if clustered else 5_000))))
+    _, _, _, what = gen_crop_host_clustered(n_sample) if clustered else gen_crop_host(n_sample)
     what = what.replace(f"{n_sample} points", f"{n_sample} points per core")
     nvox, kind = 0, "port"
     with ProcessPoolExecutor(max_workers=cores) as pool:
         for _ in range(args.warmup):
-            list(pool.map(_cpu_worker, [(n_sample, 100 + c) for c in range(cores)]))
+            list(pool.map(_cpu_worker, [(n_sample, 100 + c, clustered) for c in range(cores)]))
         t0 = time.perf_counter()
         for k in range(args.steps):
-            res = list(pool.map(_cpu_worker, [(n_sample, 1000 * (k + 1) + c) for c in range(cores)]))
+            res = list(pool.map(_cpu_worker, [(n_sample, 1000 * (k + 1) + c, clustered) for c in range(cores)]))
             nvox = sum(r[2] for r in res)
             kind = res[0][0]
         total = time.perf_counter() - t0
@@ -148,7 +177,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.points or 100_000_000, args.gpus),
+        "config": (workload_config_multi(args.points or 125_000_000, args.gpus, VOXEL_SIZE_MULTI) if clustered
+                   else workload_config(args.points or 100_000_000, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": what + f" ({nvox} voxels per step over {cores} processes, one independent crop each: tiling is the reference's "
                                           "own scaling mechanism, main.py:97-137); " + CPU_KIND_TEXT[kind]},
