@@ -259,3 +259,32 @@ def test_writer_refuses_coordinates_that_do_not_fit_int32(tmp_path):
         las.write_las(str(tmp_path / "far.las"), x, x * 0, x * 0, {}, {})
     with pytest.raises(OverflowError):
         las.write_las(str(tmp_path / "nan.las"), np.array([0.0, np.nan]), np.zeros(2), np.zeros(2), {}, {})
+
+
+def test_extra_bytes_description_in_an_evlr(tmp_path):
+    """LAS 1.4 allows the extra-bytes description (LASF_Spec / 4) to live in an EXTENDED VLR behind the points: the reader finds it there."""
+    import struct
+
+    from vapc_b200 import las
+
+    rng = np.random.default_rng(3)
+    n = 50
+    x, y, z = (np.round(rng.uniform(0, 10, n), 3) for _ in range(3))
+    amp = rng.normal(size=n).astype(np.float32)
+    path = str(tmp_path / "vlr.las")
+    las.write_las(path, x, y, z, {}, {"amplitude": amp})
+    buf = bytearray(open(path, "rb").read())
+    header_size, offset_to_points, n_vlr = struct.unpack_from("<HII", buf, 94)
+    assert n_vlr == 1
+    vlr = bytes(buf[header_size:offset_to_points])  # the 54-byte VLR header + the 192-byte description
+    body = vlr[54:]
+    evlr = struct.pack("<H16sHQ32s", 0, b"LASF_Spec", 4, len(body), b"extra bytes") + body
+    points = bytes(buf[offset_to_points:])
+    head = bytearray(buf[:header_size])
+    struct.pack_into("<HII", head, 94, header_size, header_size, 0)  # no VLRs: the points follow the header
+    struct.pack_into("<QI", head, 235, header_size + len(points), 1)  # one EVLR behind the points
+    moved = str(tmp_path / "evlr.las")
+    open(moved, "wb").write(bytes(head) + points + evlr)
+    h, rec = las.read_las(moved)
+    assert ("amplitude", "<f4") in [(name, np.dtype(dt).str) for name, dt in h.extra_dims]
+    np.testing.assert_array_equal(rec["amplitude"], amp)

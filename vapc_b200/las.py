@@ -117,16 +117,34 @@ def read_header(buf: bytes) -> LasHeader:
             comp, _coder, _vmaj, _vmin, _vrev, _opt, chunk, _nse, _ose, nitems = struct.unpack_from("<HHBBHIIqqH", body, 0)
             h.laszip = {"compressor": comp, "chunk_size": chunk, "items": [struct.unpack_from("<HHH", body, 34 + 6 * k) for k in range(nitems)]}
         if user == "LASF_Spec" and rec_id == 4:
-            for k in range(len(body) // 192):
-                e = body[k * 192:(k + 1) * 192]
-                dtype_code, options = e[2], e[3]
-                name = e[4:36].split(b"\0")[0].decode("ascii", "replace")
-                if dtype_code == 0:  # undocumented bytes: `options` holds the size
-                    h.extra_dims.append((name or f"ExtraBytes{k}", f"V{options}"))
-                elif dtype_code in _EXTRA_TYPES:
-                    h.extra_dims.append((name, _EXTRA_TYPES[dtype_code]))
+            _parse_extra_bytes(h, body)
         pos += 54 + length
+    # LAS 1.4 may keep the extra-bytes description in an EXTENDED VLR behind the points (start at header offset 235, count at 243;
+    # 60-byte EVLR headers with a 64-bit length)
+    if h.version >= (1, 4) and header_size >= 375 and not h.extra_dims:
+        start, n_evlr = struct.unpack_from("<QI", buf, 235)
+        pos = start
+        for _ in range(n_evlr):
+            if not start or pos + 60 > len(buf):
+                break
+            user = buf[pos + 2:pos + 18].split(b"\0")[0].decode("ascii", "replace")
+            rec_id, length = struct.unpack_from("<HQ", buf, pos + 18)
+            if user == "LASF_Spec" and rec_id == 4:
+                _parse_extra_bytes(h, buf[pos + 60:pos + 60 + length])
+            pos += 60 + length
     return h
+
+
+def _parse_extra_bytes(h: LasHeader, body: bytes):
+    """The extra-bytes description record (LASF_Spec / 4): 192 bytes per extra dimension."""
+    for k in range(len(body) // 192):
+        e = body[k * 192:(k + 1) * 192]
+        dtype_code, options = e[2], e[3]
+        name = e[4:36].split(b"\0")[0].decode("ascii", "replace")
+        if dtype_code == 0:  # undocumented bytes: `options` holds the size
+            h.extra_dims.append((name or f"ExtraBytes{k}", f"V{options}"))
+        elif dtype_code in _EXTRA_TYPES:
+            h.extra_dims.append((name, _EXTRA_TYPES[dtype_code]))
 
 
 def record_dtype(h: LasHeader) -> np.dtype:
