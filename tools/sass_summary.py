@@ -54,7 +54,7 @@ print("\n## whole library: the 40 most frequent opcodes")
 for op, v in total.most_common(40):
     print(f"{op:32s} {v}")
 print("\n## per kernel (functions of the benchmarked path and the cell sort)")
-want = ("keys_hist_kernel", "bucket_scatter_kernel", "digit_hist_kernel", "onesweep_kernel", "count_heads_kernel", "reduce_moments_kernel",
+want = ("tile_digits_kernel", "tile_scatter_kernel", "digit_hist_kernel", "onesweep_kernel", "count_heads_kernel", "reduce_moments_kernel",
         "p2v_lookup_kernel", "p2v_fill_kernel", "voxel_stats_kernel", "minmax_partial", "cell_sort_kernel", "pack_partial_rows_kernel", "merge_runs_kernel")
 for name, c in kernels.items():
     if not any(w in name for w in want):

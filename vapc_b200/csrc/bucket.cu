@@ -9,15 +9,17 @@
 // segments that vapc_sort_pairs_segmented sorts by the REMAINING key bits, which saves the radix pass over
 // the leading digit.
 //
-//   keys_hist_kernel      reads x, y, z; writes the packed keys in input order and counts the bucket digit
-//                         (shared-memory atomics)                                              24 + K B/pt
-//   bucket_scatter_kernel reads the keys of a 4096-point tile, ranks the bucket digit (radix_rank.cuh, stable),
-//                         decoupled look-back for the global offsets, then reads x, y, z and writes key and
-//                         record {x, y, z, index} at the bucketed position, records straight from registers as one
-//                         256-bit store each (a full sector)                              K + 24 + K + 32 B/pt
-// (One fused kernel was tried first: with the three IEEE divisions of the key in front of the count publication
-// every tile waited on its predecessors' look-back words — 34 % of all stall samples on that poll, 4.4 ms per 1e8
-// points.  Keys first, then a scatter pass whose tiles publish right after a 16 KB key load, is 2x faster.)
+// Round 2 layout (no ticket, no decoupled look-back: 25 % of the stall samples of the round-1 scatter kernel were its poll):
+//   tile_digits_kernel    a tile = 1536 consecutive points.  Reads x ONLY (the bucket digit is the leading bits of the voxel x
+//                         index), writes one digit byte per point and the tile's 256 digit counts        8 B/pt in, 1.3 B/pt out
+//   tile_chunk_sums / tile_chunk_scan / tile_offsets
+//                         column scan of the [tiles][256] count matrix -> first output slot of every (tile, digit),
+//                         bucket_start[]                                                                  ~2 B/pt
+//   tile_scatter_kernel   reads the digits of its tile, ranks them (radix_rank.cuh, stable), reads x, y, z, forms the packed key
+//                         (three IEEE divisions per point — hidden under the shared-memory reorder), writes the key in input order,
+//                         and key + record {x, y, z, index} at the bucketed position as whole lines       25.7 B/pt in, 40 B/pt out
+// (Round 1: keys first in a pass of their own over x, y, z (28 B/pt), then a scatter pass with tickets and look-back (64 B/pt);
+// a kernel that published its counts only after the three divisions had spent 34 % of its samples polling predecessors.)
 // Stable: inside a bucket the points keep their input order, so after the (stable) segmented sort the points
 // of a voxel are still in original index order.
 #include <algorithm>
@@ -34,108 +36,109 @@ using namespace rr;
 #endif
 constexpr int kItems = VAPC_BUCKET_ITEMS;
 constexpr int kTile = kThreads * kItems;  // 1536 points: the reordered records of a tile take 48 KB of shared memory (6 vs 8 items: 2.22 vs 2.42 ms)
+constexpr int kChunkTiles = 512;          // tiles per chunk of the column scan
 
 template <typename KeyT>
 __device__ __forceinline__ unsigned bucket_of(KeyT key, int shift, unsigned mask) { return (unsigned)(key >> shift) & mask; }
 
-// keys in input order + histogram of the bucket digit
-template <typename KeyT, int VEC, typename Src>
-__global__ void __launch_bounds__(kThreads) keys_hist_kernel(Src src, int64_t n, Grid g, int shift, unsigned mask, KeyT* __restrict__ keys,
-                                                             uint32_t* __restrict__ hist, int* __restrict__ status) {
+// digit byte of every point + the digit counts of every tile.  dshift = bits of the voxel x index below the bucket digit.
+template <typename Src>
+__global__ void __launch_bounds__(kThreads) tile_digits_kernel(Src src, int64_t n, Grid g, int dshift, unsigned mask, uint8_t* __restrict__ digits,
+                                                               uint16_t* __restrict__ tile_counts, int* __restrict__ status) {
   __shared__ unsigned sh[kRadix];
   sh[threadIdx.x] = 0;
   __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kTile + (threadIdx.x >> 5) * (32 * kItems) + (threadIdx.x & 31);
+  double px[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) px[k] = base + k * 32 < n ? src.cx(base + k * 32) : 0.0;
   int bad = 0;
-  const int64_t nvec = n / VEC;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    if (VEC == 2) {
-      double a[2], b[2], c[2];
-      src.pair(v, a, b, c);
-      const KeyT k0 = pack_one<KeyT>(a[0], b[0], c[0], g, bad);
-      const KeyT k1 = pack_one<KeyT>(a[1], b[1], c[1], g, bad);
-      if (sizeof(KeyT) == 4) {
-        reinterpret_cast<uint2*>(keys)[v] = make_uint2((unsigned)k0, (unsigned)k1);
-      } else {
-        reinterpret_cast<ulonglong2*>(keys)[v] = make_ulonglong2(k0, k1);
-      }
-      atomicAdd(&sh[bucket_of(k0, shift, mask)], 1u);
-      atomicAdd(&sh[bucket_of(k1, shift, mask)], 1u);
-    } else {
-      const KeyT k = pack_one<KeyT>(src.cx(v), src.cy(v), src.cz(v), g, bad);
-      keys[v] = k;
-      atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    if (base + k * 32 < n) {
+      const unsigned long long rx = (unsigned long long)(voxel_of(px[k], g.ox, g.vs) - g.minx);
+      bad |= g.bx < 64 && (rx >> g.bx);
+      const unsigned d = (unsigned)(rx >> dshift) & mask;  // an out-of-grid point gets SOME digit: the caller raises on the status bit
+      digits[base + k * 32] = (uint8_t)d;
+      atomicAdd(&sh[d], 1u);
     }
   }
-  if (VEC == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const KeyT k = pack_one<KeyT>(src.cx(n - 1), src.cy(n - 1), src.cz(n - 1), g, bad);
-    keys[n - 1] = k;
-    atomicAdd(&sh[bucket_of(k, shift, mask)], 1u);
-  }
   __syncthreads();
-  const unsigned c = sh[threadIdx.x];
-  if (c) atomicAdd(&hist[threadIdx.x], c);
+  tile_counts[(int64_t)blockIdx.x * kRadix + threadIdx.x] = (uint16_t)sh[threadIdx.x];
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
 }
 
-// bucket_start[b] = first slot of bucket b, [nb] = n   (digit_base = exclusive scan of the histogram)
-__global__ void bucket_start_kernel(const uint32_t* __restrict__ digit_base, int nb, uint32_t n, uint32_t* __restrict__ bucket_start) {
-  const int t = threadIdx.x;
-  if (t < nb) bucket_start[t] = digit_base[t];
-  if (t == 0) bucket_start[nb] = n;
+// column scan of tile_counts[tiles][256], thread == digit: chunk sums -> exclusive over chunks + digits -> per-tile offsets
+__global__ void __launch_bounds__(kThreads) tile_chunk_sums_kernel(const uint16_t* __restrict__ tile_counts, int64_t ntiles, uint32_t* __restrict__ chunk_sums) {
+  const int64_t t0 = (int64_t)blockIdx.x * kChunkTiles, t1 = min(ntiles, t0 + kChunkTiles);
+  unsigned sum = 0;
+#pragma unroll 8
+  for (int64_t t = t0; t < t1; ++t) sum += tile_counts[t * kRadix + threadIdx.x];
+  chunk_sums[(int64_t)blockIdx.x * kRadix + threadIdx.x] = sum;
+}
+__global__ void __launch_bounds__(kThreads) tile_chunk_scan_kernel(uint32_t* __restrict__ chunk_sums, int nchunks, int nb, uint32_t n,
+                                                                   uint32_t* __restrict__ bucket_start) {
+  __shared__ unsigned warp_s[33];
+  unsigned total = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const unsigned v = chunk_sums[(int64_t)c * kRadix + threadIdx.x];
+    chunk_sums[(int64_t)c * kRadix + threadIdx.x] = total;
+    total += v;
+  }
+  unsigned all;
+  const unsigned base = block_exclusive_scan(total, warp_s, &all);  // first slot of the digit's bucket
+  for (int c = 0; c < nchunks; ++c) chunk_sums[(int64_t)c * kRadix + threadIdx.x] += base;
+  if ((int)threadIdx.x < nb) bucket_start[threadIdx.x] = base;
+  if (threadIdx.x == 0) bucket_start[nb] = n;
+}
+__global__ void __launch_bounds__(kThreads) tile_offsets_kernel(const uint16_t* __restrict__ tile_counts, const uint32_t* __restrict__ chunk_base,
+                                                                int64_t ntiles, uint32_t* __restrict__ tile_offsets) {
+  const int64_t t0 = (int64_t)blockIdx.x * kChunkTiles, t1 = min(ntiles, t0 + kChunkTiles);
+  unsigned run = chunk_base[(int64_t)blockIdx.x * kRadix + threadIdx.x];
+#pragma unroll 8
+  for (int64_t t = t0; t < t1; ++t) {
+    tile_offsets[t * kRadix + threadIdx.x] = run;
+    run += tile_counts[t * kRadix + threadIdx.x];
+  }
 }
 
 // The tile's records reordered by bucket, as columns: coordinates, key and the 16-bit input slot of every point (64-bit
 // shared-memory stores per column measured 4 % faster than one 32-byte record store; a fourth CTA per SM — 55 KB each —
 // needs 64 registers per thread and loses more to spills than it gains).
-#ifndef VAPC_BUCKET_TMA
-#define VAPC_BUCKET_TMA 0
-#endif
 template <typename KeyT>
 struct BucketSmem {
   RankSmem r;
   alignas(32) union {
     MaskBuffers masks;
-#if VAPC_BUCKET_TMA
-    struct {
-      double4 rec[kTile];  // whole records in bucket order: a bucket's run leaves as ONE bulk copy (TMA) instead of 32-byte stores
-      KeyT key[kTile];
-    } rec;
-#else
     struct {
       double x[kTile], y[kTile], z[kTile];
       KeyT key[kTile];
       unsigned short slot[kTile];
     } rec;
-#endif
   } u;
 };
 
 // KeyOutT: the bucketed keys are written as 32-bit words holding the key bits BELOW the bucket digit when those fit
 // (64-bit keys of up to 40 bits): the segmented sort then moves 4-byte keys; vapc_expand_bucket_keys restores the full keys.
-template <typename KeyT, typename KeyOutT, typename LookT, typename Src>
-__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) bucket_scatter_kernel(
-    const KeyT* __restrict__ keys, Src src, int64_t n, int shift,
-    unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket, KeyOutT* __restrict__ keys_b,
-    double4* __restrict__ rec_b) {
+template <typename KeyT, typename KeyOutT, typename Src>
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) tile_scatter_kernel(
+    const uint8_t* __restrict__ digits, Src src, int64_t n, Grid g, int shift, unsigned mask, const uint32_t* __restrict__ tile_offsets,
+    KeyT* __restrict__ keys_orig, KeyOutT* __restrict__ keys_b, double4* __restrict__ rec_b, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BucketSmem<KeyT>& sm = *reinterpret_cast<BucketSmem<KeyT>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) sm.r.tile = atomicAdd(ticket, 1u);
   rank_init(sm.r, sm.u.masks);
-  __syncthreads();
-  const unsigned tile = sm.r.tile;
+  const unsigned tile = blockIdx.x;
   const int64_t tile_base = (int64_t)tile * kTile;
   const bool full = tile_base + kTile <= n;
-
+  const unsigned my_offset = tile_offsets[(int64_t)tile * kRadix + tid];  // thread == digit: first output slot of the tile's run
   // warp-striped: warp w owns points [w*32*kItems, (w+1)*32*kItems) of the tile, lane l takes point k*32 + l in step k.
-  // Slots past the end of the input (last tile) hold all-ones keys: highest bucket, last ranks, never written.
+  // Slots past the end of the input (last tile) take the highest digit: last ranks of it, never written.
   const int slot0 = warp * (32 * kItems) + lane;
   const int64_t wbase = tile_base + slot0;
-  KeyT key[kItems];
+  unsigned dig[kItems];
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) key[k] = (full || wbase + k * 32 < n) ? __ldcs(keys + wbase + k * 32) : (KeyT)~(KeyT)0;
-  // the coordinates are only needed once the positions are known; their loads overlap the ranking
+  for (int k = 0; k < kItems; ++k) dig[k] = (full || wbase + k * 32 < n) ? (unsigned)digits[wbase + k * 32] : (unsigned)(kRadix - 1);
   double px[kItems], py[kItems], pz[kItems];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
@@ -144,65 +147,59 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
     py[k] = valid ? src.cy(wbase + k * 32) : 0.0;
     pz[k] = valid ? src.cz(wbase + k * 32) : 0.0;
   }
+  __syncthreads();  // rank_init
 
   unsigned rank2[kItems / 2];
-  warp_rank<kItems>([&](int k) { return bucket_of(key[k], shift, mask); }, sm.r, sm.u.masks, rank2);
+  warp_rank<kItems>([&](int k) { return dig[k]; }, sm.r, sm.u.masks, rank2);
+
+  // the packed keys (three IEEE divisions per point) while the other warps rank; the key goes out in input order at once
+  KeyT key[kItems];
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    int b = 0;
+    const bool valid = full || wbase + k * 32 < n;
+    key[k] = pack_one<KeyT>(px[k], py[k], pz[k], g, b);
+    // out of the grid (status bit) or past the end of the input: keep the key consistent with the digit it was ranked by
+    if (b || !valid) key[k] = (KeyT)dig[k] << shift;
+    bad |= valid && b;
+    if (valid) keys_orig[wbase + k * 32] = key[k];
+  }
   __syncthreads();
 
-  LookT* mine = look + (int64_t)tile * kRadix + tid;
-  unsigned bstart;
-  const unsigned run = digit_offsets<LookT>(sm.r, mine, tile == 0, &bstart);
+  // first slot of every digit inside the tile, and of every warp's keys of it
+  {
+    unsigned cnt[kWarps], run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      cnt[w] = sm.r.warp_cnt[w][tid];
+      run += cnt[w];
+    }
+    unsigned total;
+    const unsigned b = block_exclusive_scan(run, sm.r.warp_s, &total);
+    unsigned acc = b;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      sm.r.warp_cnt[w][tid] = acc;
+      acc += cnt[w];
+    }
+    sm.r.delta[tid] = my_offset - b;
+    __syncthreads();
+  }
 
   // reorder the records inside shared memory (the mask words are dead: every warp passed the barriers above), so
   // that a bucket's run leaves as whole 128-byte lines: scattered single-sector stores were measured at a quarter of
   // the HBM write bandwidth (profiles/).
   const unsigned* wc = sm.r.warp_cnt[warp];
-#if VAPC_BUCKET_TMA
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
-    unsigned long long w = (uint32_t)tile_base + (uint32_t)(slot0 + k * 32);
-    if (sizeof(KeyT) == 4) w |= (unsigned long long)key[k] << 32;
-    sm.u.rec.rec[pos] = make_double4(px[k], py[k], pz[k], __longlong_as_double((long long)w));
-    sm.u.rec.key[pos] = key[k];
-  }
-  const LookT excl = look_back<LookT>(mine, (int64_t)tile, run);
-  sm.r.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
-  // the records were written through the generic proxy; the bulk copies read them through the async proxy
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  const int tile_n = (int)min((int64_t)kTile, n - tile_base);
-  {
-    // thread == bucket: its run [bstart, bstart + run) of the tile goes to rec_b[digit_base + excl ...] as one bulk copy
-    const int end = min((int)(bstart + run), tile_n);
-    if (end > (int)bstart) {
-      const unsigned bytes = (unsigned)(end - (int)bstart) * 32u;
-      const unsigned src = (unsigned)__cvta_generic_to_shared(&sm.u.rec.rec[bstart]);
-      double4* dst = rec_b + (digit_base[tid] + (unsigned)excl);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  }
-#pragma unroll 3
-  for (int p = tid; p < tile_n; p += kThreads) {
-    const KeyT k = sm.u.rec.key[p];
-    const unsigned dst = (unsigned)p + sm.r.delta[bucket_of(k, shift, mask)];
-    keys_b[dst] = sizeof(KeyOutT) < sizeof(KeyT) ? (KeyOutT)(k & (((KeyT)1 << shift) - 1)) : (KeyOutT)k;
-  }
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the copies
-#else
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const unsigned pos = wc[bucket_of(key[k], shift, mask)] + rank_of(rank2, k);
+    const unsigned pos = wc[dig[k]] + rank_of(rank2, k);
     sm.u.rec.x[pos] = px[k];
     sm.u.rec.y[pos] = py[k];
     sm.u.rec.z[pos] = pz[k];
     sm.u.rec.key[pos] = key[k];
     sm.u.rec.slot[pos] = (unsigned short)(slot0 + k * 32);
   }
-
-  const LookT excl = look_back<LookT>(mine, (int64_t)tile, run);
-  sm.r.delta[tid] = digit_base[tid] + (unsigned)excl - bstart;
   __syncthreads();
 
   // 32-bit keys also ride in the upper half of the record's index slot (readers only look at the lower half)
@@ -216,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
     st_record(rec_b + dst, sm.u.rec.x[p], sm.u.rec.y[p], sm.u.rec.z[p], __longlong_as_double((long long)w));
     keys_b[dst] = sizeof(KeyOutT) < sizeof(KeyT) ? (KeyOutT)(k & (((KeyT)1 << shift) - 1)) : (KeyOutT)k;
   }
-#endif
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, 1);
 }
 
 // full sorted keys from the sorted low parts: key = bucket << low_bits | low, the bucket of a position from bucket_start
@@ -237,39 +234,52 @@ __global__ void __launch_bounds__(kThreads) expand_keys_kernel(const uint32_t* _
 }
 
 inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
-// workspace: [bucket histogram -> first slots, 256 u32][ticket (256 B)][look-back ntiles x 256 x 8 B]
-constexpr size_t kHistBytes = kRadix * sizeof(uint32_t);
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+// workspace: [digits n x 1][tile_counts tiles x 256 x 2][tile_offsets tiles x 256 x 4][chunk sums chunks x 256 x 4]
+struct BucketWs {
+  uint8_t* digits;
+  uint16_t* tile_counts;
+  uint32_t* tile_offsets;
+  uint32_t* chunk_sums;
+};
+inline int64_t num_chunks(int64_t ntiles) { return (ntiles + kChunkTiles - 1) / kChunkTiles; }
+inline size_t bucket_ws_bytes(int64_t n) {
+  const int64_t nt = num_tiles(n < 1 ? 1 : n);
+  return align256((size_t)n) + align256((size_t)nt * kRadix * 2) + align256((size_t)nt * kRadix * 4) + align256((size_t)num_chunks(nt) * kRadix * 4);
+}
+inline BucketWs carve_bucket_ws(void* ws, int64_t n) {
+  const int64_t nt = num_tiles(n);
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  BucketWs w;
+  w.digits = p; p += align256((size_t)n);
+  w.tile_counts = reinterpret_cast<uint16_t*>(p); p += align256((size_t)nt * kRadix * 2);
+  w.tile_offsets = reinterpret_cast<uint32_t*>(p); p += align256((size_t)nt * kRadix * 4);
+  w.chunk_sums = reinterpret_cast<uint32_t*>(p);
+  return w;
+}
 
-template <typename KeyT, typename KeyOutT, typename LookT, typename Src>
+template <typename KeyT, typename KeyOutT, typename Src>
 int bucket_impl(const Src& src, int64_t n, const Grid& g, int mb, KeyOutT* keys_b, double4* rec_b, KeyT* keys_orig,
                 uint32_t* bucket_start, int32_t* status, void* ws, cudaStream_t s) {
-  const int shift = g.bx + g.by + g.bz - mb;  // the bucket digit = the leading mb bits of the key
+  const int shift = g.bx + g.by + g.bz - mb;  // the bucket digit = the leading mb bits of the key = of the voxel x index
   const unsigned mask = (1u << mb) - 1u;
   const int64_t ntiles = num_tiles(n);
-  unsigned char* base = static_cast<unsigned char*>(ws);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(base);
-  unsigned* ticket = reinterpret_cast<unsigned*>(base + kHistBytes);
-  LookT* look = reinterpret_cast<LookT*>(base + kHistBytes + 256);
-  VAPC_RETURN_IF_CUDA(cudaMemsetAsync(base, 0, kHistBytes + 256 + (size_t)ntiles * kRadix * sizeof(LookT), s));
-  const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16));
-  const bool vec = src.aligned() && (reinterpret_cast<uintptr_t>(keys_orig) & 15u) == 0;
-  if (vec) VAPC_LAUNCH((keys_hist_kernel<KeyT, 2, Src>), hgrid, kThreads, 0, s, src, n, g, shift, mask, keys_orig, hist, status);
-  else VAPC_LAUNCH((keys_hist_kernel<KeyT, 1, Src>), hgrid, kThreads, 0, s, src, n, g, shift, mask, keys_orig, hist, status);
-  VAPC_LAUNCH(digit_scan_kernel, 1, kThreads, 0, s, hist, nullptr, 1);
-  VAPC_LAUNCH(bucket_start_kernel, 1, kThreads, 0, s, hist, 1 << mb, (uint32_t)n, bucket_start);
+  const int nchunks = (int)num_chunks(ntiles);
+  const BucketWs w = carve_bucket_ws(ws, n);
+  VAPC_LAUNCH((tile_digits_kernel<Src>), (unsigned)ntiles, kThreads, 0, s, src, n, g, g.bx - mb, mask, w.digits, w.tile_counts, status);
+  VAPC_LAUNCH(tile_chunk_sums_kernel, (unsigned)nchunks, kThreads, 0, s, w.tile_counts, ntiles, w.chunk_sums);
+  VAPC_LAUNCH(tile_chunk_scan_kernel, 1, kThreads, 0, s, w.chunk_sums, nchunks, 1 << mb, (uint32_t)n, bucket_start);
+  VAPC_LAUNCH(tile_offsets_kernel, (unsigned)nchunks, kThreads, 0, s, w.tile_counts, w.chunk_sums, ntiles, w.tile_offsets);
   const size_t smem = sizeof(BucketSmem<KeyT>);
-  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel<KeyT, KeyOutT, LookT, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VAPC_LAUNCH((bucket_scatter_kernel<KeyT, KeyOutT, LookT, Src>), (unsigned)ntiles, kThreads, smem, s, keys_orig, src, n, shift, mask, hist, look, ticket, keys_b,
-              rec_b);
+  VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(tile_scatter_kernel<KeyT, KeyOutT, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAPC_LAUNCH((tile_scatter_kernel<KeyT, KeyOutT, Src>), (unsigned)ntiles, kThreads, smem, s, w.digits, src, n, g, shift, mask, w.tile_offsets, keys_orig, keys_b,
+              rec_b, status);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;
 }
 }  // namespace
 
-extern "C" size_t vapc_bucket_workspace_bytes(int64_t n) {
-  if (n < 1) n = 1;
-  return kHistBytes + 256 + (size_t)num_tiles(n) * kRadix * sizeof(unsigned long long);
-}
+extern "C" size_t vapc_bucket_workspace_bytes(int64_t n) { return bucket_ws_bytes(n < 1 ? 1 : n); }
 
 namespace {
 template <typename Src>
@@ -291,20 +301,16 @@ int pack_bucketed(const char* who, const Src& src, int64_t n, const vapc_grid_t*
   if (!ws || ws_bytes < vapc_bucket_workspace_bytes(n)) return vapc_set_error(VAPC_E_WORKSPACE, "%s: workspace too small", who);
   cudaStream_t s = as_stream(stream);
   double4* rec = reinterpret_cast<double4*>(xyzw_bucketed);
-  const bool wide = n >= ((int64_t)1 << 30);
   typedef unsigned long long u64;
   typedef uint32_t u32;
   if (grid_host->key_bytes == 4) {
-    if (!wide) return bucket_impl<u32, u32, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<u32, u32, u64>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u32, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u32*>(keys_orig), bucket_start, status, ws, s);
   }
   if (grid_host->key_bytes == 8) {
     if (narrow) {
-      if (!wide) return bucket_impl<u64, u32, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
-      return bucket_impl<u64, u32, u64>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+      return bucket_impl<u64, u32>(src, n, g, mb, static_cast<u32*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
     }
-    if (!wide) return bucket_impl<u64, u64, u32>(src, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
-    return bucket_impl<u64, u64, u64>(src, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
+    return bucket_impl<u64, u64>(src, n, g, mb, static_cast<u64*>(keys_bucketed), rec, static_cast<u64*>(keys_orig), bucket_start, status, ws, s);
   }
   return vapc_set_error(VAPC_E_INVALID, "%s: key_bytes must be 4 or 8", who);
 }
