@@ -236,6 +236,10 @@ VAPC_API size_t vapc_point2voxel_table_bytes(int32_t total_bits);
 VAPC_API int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys,
                            int64_t nvoxels, int32_t key_bytes, int32_t total_bits, void* table,
                            size_t table_bytes, uint32_t* point2voxel, void* stream);
+/* CTAs per SM of the lookup kernel of vapc_point2voxel_dense (1..32, default 16).  The lookup is bound by the rate of uncoalesced
+ * 8-byte gathers, not by issue slots or DRAM: a host that runs it on a side stream beside vapc_voxel_stats (both only read the voxel
+ * table of vapc_reduce_moments) lowers the residency so that both kernels share every SM.  Process-wide. */
+VAPC_API int vapc_point2voxel_set_ctas_per_sm(int32_t ctas);
 
 /* ---- a5, a7, a8, a12, a13, a14: per-voxel outputs from the moments ---------------------
  * (vapc.py:730-741 density, 829-852 centroid, 856-887 std ddof=1, 929-1040 covariance,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "vapc_last_error": (C.c_char_p, []),
     "vapc_launch_count": (C.c_uint64, []),
     "vapc_set_l2_fetch_granularity": (C.c_int, [I32]),
+    "vapc_point2voxel_set_ctas_per_sm": (C.c_int, [I32]),
     "vapc_profile_enable": (C.c_int, [I32]),
     "vapc_profile_collect": (C.c_int64, [C.c_char_p, I64]),
     "vapc_minmax_workspace_bytes": (SZ, []),

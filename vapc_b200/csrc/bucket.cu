@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) tile_digits_kernel(Src src, int64_t 
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     if (base + k * 32 < n) {
-      const unsigned long long rx = (unsigned long long)(voxel_of(px[k], g.ox, g.vs) - g.minx);
+      const unsigned long long rx = (unsigned long long)(voxel_of_fast(px[k], g.ox, g.vs, g.ivs) - g.minx);
       bad |= g.bx < 64 && (rx >> g.bx);
       const unsigned d = (unsigned)(rx >> dshift) & mask;  // an out-of-grid point gets SOME digit: the caller raises on the status bit
       digits[base + k * 32] = (uint8_t)d;

@@ -38,6 +38,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 // ---- packed-key layout, passed by value to kernels -------------------------------------
 struct Grid {
   double ox, oy, oz, vs;
+  double ivs;  // 1 / vs, correctly rounded (host): the fast path of voxel_of_fast
   long long minx, miny, minz;
   int bx, by, bz;
 };
@@ -45,6 +46,7 @@ static inline Grid to_device_grid(const vapc_grid_t* g) {
   Grid d;
   d.ox = g->origin[0]; d.oy = g->origin[1]; d.oz = g->origin[2];
   d.vs = g->voxel_size;
+  d.ivs = 1.0 / g->voxel_size;
   d.minx = g->vmin[0]; d.miny = g->vmin[1]; d.minz = g->vmin[2];
   d.bx = g->bits[0]; d.by = g->bits[1]; d.bz = g->bits[2];
   return d;
@@ -54,6 +56,21 @@ static inline Grid to_device_grid(const vapc_grid_t* g) {
 // floor, convert.  Bit-exact with numpy's np.floor((X - o) / vs).astype(int)  (vapc.py:199-201).
 __device__ __forceinline__ long long voxel_of(double c, double o, double vs) {
   return __double2ll_rd(__ddiv_rn(__dsub_rn(c, o), vs));
+}
+
+// The same integer without the division for almost every point (an IEEE fp64 division is ~30 instructions, and the key kernels
+// form three per point).  With d = c - o (IEEE), Q = d / vs (real) and ivs = fl(1 / vs):
+//   |fl(d / vs) - Q| <= 2^-53 |Q|   and   q' = fl(d * ivs) = Q (1 + e1)(1 + e2), |e| <= 2^-53   =>   |q' - fl(d / vs)| < 2^-51 |q'|.
+// So when no integer lies within 2^-50 |q'| of q', fl(d / vs) lies strictly between the same two integers as q' and
+// floor(q') == floor(fl(d / vs)).  Otherwise (a coordinate on a voxel face within rounding — LAS-quantised clouds have ~0.1 % of
+// those —, q' == 0, |q'| >= 2^52) the division itself decides.  NaN / inf fall through to the conversion, which treats them like
+// the division's result.  Bit-exact with voxel_of by construction; tests/test_gpu_kernels.py::test_voxel_coords_bit_exact checks
+// 80 000 face-adjacent values per grid through the key kernels.
+__device__ __forceinline__ long long voxel_of_fast(double c, double o, double vs, double ivs) {
+  const double d = __dsub_rn(c, o);
+  const double q = __dmul_rn(d, ivs);
+  if (fabs(__dsub_rn(q, rint(q))) <= __dmul_rn(fabs(q), 8.8817841970012523e-16 /* 2^-50 */)) return __double2ll_rd(__ddiv_rn(d, vs));
+  return __double2ll_rd(q);
 }
 
 __device__ __forceinline__ void unpack_key(unsigned long long key, const Grid& g, long long& vx,
@@ -77,9 +94,9 @@ __device__ __forceinline__ double shift_center(long long v, double o, double vs)
 // not fit its bit field (NaN / out-of-box point).
 template <typename KeyT>
 __device__ __forceinline__ KeyT pack_one(double px, double py, double pz, const Grid& g, int& bad, unsigned long long* rx_out = nullptr) {
-  const unsigned long long rx = (unsigned long long)(voxel_of(px, g.ox, g.vs) - g.minx);
-  const unsigned long long ry = (unsigned long long)(voxel_of(py, g.oy, g.vs) - g.miny);
-  const unsigned long long rz = (unsigned long long)(voxel_of(pz, g.oz, g.vs) - g.minz);
+  const unsigned long long rx = (unsigned long long)(voxel_of_fast(px, g.ox, g.vs, g.ivs) - g.minx);
+  const unsigned long long ry = (unsigned long long)(voxel_of_fast(py, g.oy, g.vs, g.ivs) - g.miny);
+  const unsigned long long rz = (unsigned long long)(voxel_of_fast(pz, g.oz, g.vs, g.ivs) - g.minz);
   // (unsigned) relative coordinates must fit their bit fields; NaN / out-of-box points do not
   bad |= (g.bx < 64 && (rx >> g.bx)) || (g.by < 64 && (ry >> g.by)) || (g.bz < 64 && (rz >> g.bz));
   const int sxy = g.by + g.bz;

@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(kThreads) voxel_coords_kernel(const double* __
                                                                 long long* __restrict__ vz) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    __stcs(vx + i, voxel_of(ld_stream(x + i), g.ox, g.vs));
-    __stcs(vy + i, voxel_of(ld_stream(y + i), g.oy, g.vs));
-    __stcs(vz + i, voxel_of(ld_stream(z + i), g.oz, g.vs));
+    __stcs(vx + i, voxel_of_fast(ld_stream(x + i), g.ox, g.vs, g.ivs));
+    __stcs(vy + i, voxel_of_fast(ld_stream(y + i), g.oy, g.vs, g.ivs));
+    __stcs(vz + i, voxel_of_fast(ld_stream(z + i), g.oz, g.vs, g.ivs));
   }
 }
 

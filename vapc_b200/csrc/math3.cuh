@@ -19,31 +19,27 @@ VAPC_HD double vapc_rsqrt(double v) {
 
 // One Jacobi rotation annihilating a_pq of a symmetric 3x3 held in scalars.
 // (app, aqq, apq) is the 2x2 pivot block, (arp, arq) the remaining off-diagonal pair.
-// t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = (aqq - app) / (2 apq), written as
-// 2 apq / (h + sgn(h) sqrt(h^2 + 4 apq^2)): one square root and two divisions per rotation (fp64 division is ~30
-// instructions on the GPU and this runs ~15 times per voxel).  The matrix is pre-scaled to max |entry| = 1, so h^2 cannot
-// overflow.
+// The rotation angle (|angle| <= pi/4) comes from its double angle, with two reciprocal square roots and no division or square
+// root (an fp64 division is ~30 instructions on the GPU, a square root ~20, rsqrt ~10, and the kernel running this ~8 times per
+// voxel is bound by issue slots):  with h = aqq - app and rho = 1 / sqrt(h^2 + 4 apq^2)
+//   cos 2a = |h| rho,  sin 2a = sgn(h) 2 apq rho,  cos^2 a = (1 + cos 2a) / 2,  cos a = cos^2 a * rsqrt(cos^2 a),
+//   sin a = sin 2a / (2 cos a),  tan a = sin a / cos a.
+// The matrix is pre-scaled to max |entry| = 1 and the caller only rotates pivots above its convergence threshold, so
+// h^2 + 4 apq^2 neither overflows nor underflows.
 VAPC_HD void jacobi_rotate(double& app, double& aqq, double& apq, double& arp, double& arq) {
-  if (apq == 0.0) return;
   const double h = aqq - app;
-  const double g = 100.0 * fabs(apq);
-  double t;
-  if (fabs(h) + g == fabs(h)) {
-    t = apq / h;
-  } else {
-    const double r = sqrt(fma(h, h, 4.0 * apq * apq));
-    t = 2.0 * apq / (h + copysign(r, h));
-  }
-  const double c = vapc_rsqrt(fma(t, t, 1.0));
-  const double s = t * c;
-  const double tau = s / (1.0 + c);
-  const double hh = t * apq;
+  const double rho = vapc_rsqrt(fma(h, h, 4.0 * apq * apq));
+  const double c2 = fma(0.5 * fabs(h), rho, 0.5);  // cos^2 in [1/2, 1]
+  const double ic = vapc_rsqrt(c2);                // 1 / cos
+  const double c = c2 * ic;
+  const double s = copysign(apq * rho, apq * copysign(1.0, h)) * ic;
+  const double hh = (s * ic) * apq;                // tan * apq
   app -= hh;
   aqq += hh;
   apq = 0.0;
   const double gp = arp, hq = arq;
-  arp = gp - s * (hq + gp * tau);
-  arq = hq + s * (gp - hq * tau);
+  arp = fma(c, gp, -s * hq);
+  arq = fma(s, gp, c * hq);
 }
 
 // Eigenvalues of the symmetric matrix [[a00 a01 a02][a01 a11 a12][a02 a12 a22]], descending.

@@ -926,6 +926,15 @@ extern "C" size_t vapc_point2voxel_table_bytes(int32_t total_bits) {
   return total_bits < 0 || total_bits > 32 ? 0 : (sizeof(uint2) << (total_bits > 5 ? total_bits - 5 : 0));
 }
 
+// CTAs per SM of p2v_lookup_kernel (a grid-stride kernel).  A caller that runs the lookup on a side stream next to another kernel
+// lowers it so that the lookup leaves threads and registers of every SM to its neighbour.
+static int g_p2v_ctas_per_sm = 16;
+extern "C" int vapc_point2voxel_set_ctas_per_sm(int32_t ctas) {
+  if (ctas < 1 || ctas > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_set_ctas_per_sm: 1..32");
+  g_p2v_ctas_per_sm = ctas;
+  return VAPC_OK;
+}
+
 extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, const void* voxel_keys, int64_t nvoxels, int32_t key_bytes,
                                       int32_t total_bits, void* table, size_t table_bytes, uint32_t* point2voxel, void* stream) {
   if (n < 0 || nvoxels < 0 || total_bits < 0 || total_bits > 32) return vapc_set_error(VAPC_E_INVALID, "vapc_point2voxel_dense: bad arguments");
@@ -933,7 +942,7 @@ extern "C" int vapc_point2voxel_dense(const void* keys_unsorted, int64_t n, cons
   if (n == 0) return VAPC_OK;
   cudaStream_t s = as_stream(stream);
   const int g1 = (int)std::min<int64_t>((nvoxels + kThreads - 1) / kThreads, (int64_t)kNumSMs * 16);
-  const int g2 = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * 16);
+  const int g2 = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)kNumSMs * g_p2v_ctas_per_sm);
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(table, 0, vapc_point2voxel_table_bytes(total_bits), s));
   if (key_bytes == 4) {
     VAPC_LAUNCH(p2v_fill_kernel<uint32_t>, g1 < 1 ? 1 : g1, kThreads, 0, s, static_cast<const uint32_t*>(voxel_keys), nvoxels, static_cast<uint2*>(table));

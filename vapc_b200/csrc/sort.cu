@@ -55,12 +55,16 @@ __device__ __forceinline__ int segment_of_tile(const unsigned* first, int nseg, 
 // ghist[p][s][d] = number of keys of segment s whose p-th 8-bit digit is d.  Shared-memory atomics (no
 // return value needed for counting); a CTA walks a contiguous range of tiles and flushes its non-zero
 // counters when the segment changes.
-template <typename KeyT, bool SEG>
-__global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int begin_bit, int end_bit,
+// PASSES > 0: the number of passes as a compile-time constant (the kernel is bound by issue slots, not by the shared-memory
+// atomics: with a run-time pass loop it spent 47 instructions per key and warp); 0: any number of passes.
+template <typename KeyT, bool SEG, int PASSES>
+__global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __restrict__ keys, int64_t n, int passes_rt, int begin_bit, int end_bit,
                                                               uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_start,
                                                               const uint32_t* __restrict__ seg_first_tile, int nseg, int tiles_per_cta) {
-  __shared__ unsigned sh[kMaxPasses][kRadix];
+  __shared__ unsigned sh[PASSES ? PASSES : kMaxPasses][kRadix];
   __shared__ unsigned first[kMaxSegments + 1];
+  const int passes = PASSES ? PASSES : passes_rt;
+#pragma unroll
   for (int p = 0; p < passes; ++p) sh[p][threadIdx.x] = 0;
   if (SEG) {
     if (threadIdx.x <= nseg) first[threadIdx.x] = seg_first_tile[threadIdx.x];
@@ -102,12 +106,24 @@ __global__ void __launch_bounds__(kThreads) digit_hist_kernel(const KeyT* __rest
       const int64_t i = base + j * kThreads + threadIdx.x;
       k[j] = i < end ? __ldcs(keys + i) : (KeyT)0;
     }
+    if (end - base == kTile) {  // a full tile: no per-key bound test
 #pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-      if (base + j * kThreads + threadIdx.x < end) {
+      for (int j = 0; j < kItems; ++j) {
+#pragma unroll
         for (int p = 0; p < passes; ++p) {
           const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
           atomicAdd(&sh[p][digit_of(k[j], begin_bit + p * kRadixBits, m)], 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        if (base + j * kThreads + threadIdx.x < end) {
+#pragma unroll
+          for (int p = 0; p < passes; ++p) {
+            const unsigned m = p == passes - 1 ? last_mask : (unsigned)(kRadix - 1);
+            atomicAdd(&sh[p][digit_of(k[j], begin_bit + p * kRadixBits, m)], 1u);
+          }
         }
       }
     }
@@ -254,7 +270,15 @@ int sweep_passes(KeyT* keys, KeyT* keys_alt, KeyT* keys_alt2, uint32_t* idx, uin
   if (SEG) VAPC_LAUNCH(seg_tiles_kernel, 1, kThreads, 0, s, seg_start, nseg, seg_first_tile);
   const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)kNumSMs * 8));
   const int tiles_per_cta = (int)((ntiles + hgrid - 1) / hgrid);
-  VAPC_LAUNCH((digit_hist_kernel<KeyT, SEG>), hgrid, kThreads, 0, s, keys, n, passes, begin_bit, end_bit, ghist, seg_start, seg_first_tile, hseg, tiles_per_cta);
+#define VAPC_HIST(P) VAPC_LAUNCH((digit_hist_kernel<KeyT, SEG, P>), hgrid, kThreads, 0, s, keys, n, passes, begin_bit, end_bit, ghist, seg_start, seg_first_tile, hseg, tiles_per_cta)
+  switch (passes) {
+    case 1: VAPC_HIST(1); break;
+    case 2: VAPC_HIST(2); break;
+    case 3: VAPC_HIST(3); break;
+    case 4: VAPC_HIST(4); break;
+    default: VAPC_HIST(0); break;
+  }
+#undef VAPC_HIST
   VAPC_LAUNCH(digit_scan_kernel, passes * hseg, kThreads, 0, s, ghist, SEG ? seg_start : nullptr, hseg);
   // key buffers: keys -> alt -> (alt2 | keys) -> alt -> ...; with alt2 the caller's keys stay intact
   KeyT* src_k = keys; KeyT* dst_k = keys_alt;

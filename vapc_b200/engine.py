@@ -220,6 +220,20 @@ def _tune_device(device):
 CELL_SORT = os.environ.get("VAPC_CELL_SORT", "0") != "0"  # dense grids: counting sort through a per-bucket cell table
 CELL_SORT_MIN_BITS = 9   # fewer key bits below the bucket digit: a single radix pass is as cheap
 CELL_SORT_MAX_MEAN = 16  # mean points per cell of the key space beyond which the per-cell ordering would dominate
+P2V_SIDE_STREAM = os.environ.get("VAPC_P2V_SIDE_STREAM", "1") != "0"  # point->voxel lookups beside the next kernel of the caller's stream
+P2V_SIDE_CTAS = int(os.environ.get("VAPC_P2V_SIDE_CTAS", "4"))             # their CTAs per SM there (alone: 16)
+P2V_SIDE_PRIORITY = os.environ.get("VAPC_P2V_SIDE_PRIORITY", "1") != "0"
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device):
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i not in _SIDE_STREAMS:
+        # high priority: its CTAs are placed as soon as the kernel in front on the caller's stream frees a slot, not behind that kernel's queue
+        _SIDE_STREAMS[i] = torch.cuda.Stream(device=i, priority=-1 if P2V_SIDE_PRIORITY else 0)
+    return _SIDE_STREAMS[i]
+
+
 DENSE_P2V_MAX_BITS = 29  # rank-bitmap point->voxel table: 2^bits / 4 bytes, <= 128 MB stays L2-resident on B200
 
 
@@ -253,7 +267,8 @@ class VoxelCloud:
         self.first_idx = None
         self.mean3 = None
         self.m2 = None
-        self.point2voxel = None
+        self._point2voxel = None
+        self._p2v_event = None  # set while the point->voxel map is still being formed on the side stream
         self._seg_ws = None
         self.sorted_by = "radix"  # or "cells" (vapc_sort_cells_segmented)
         self._stats_cache: Dict[str, torch.Tensor] = {}
@@ -412,11 +427,41 @@ class VoxelCloud:
             del grouped_idx, grouped_row, row_sorted
         if dense_p2v:
             tbytes = L.raw("vapc_point2voxel_table_bytes")(g.total_bits)
-            table = _empty(tbytes, torch.uint8, device)
-            L.call("vapc_point2voxel_dense", _ptr(keys), n, _ptr(self.voxel_keys), V, g.key_bytes, g.total_bits, _ptr(table), tbytes,
-                   _ptr(self.point2voxel), _stream())
+            if P2V_SIDE_STREAM:
+                # The lookups are bound by the rate of uncoalesced gathers (few issue slots, little DRAM traffic); whatever the caller
+                # launches next on its own stream — normally vapc_voxel_stats, bound by issue slots and the FP64 pipe — shares the SMs
+                # with them.  Reading .point2voxel joins the streams.
+                cur, side = torch.cuda.current_stream(device), _side_stream(device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    table = _empty(tbytes, torch.uint8, device)
+                    L.call("vapc_point2voxel_set_ctas_per_sm", P2V_SIDE_CTAS)
+                    L.call("vapc_point2voxel_dense", _ptr(keys), n, _ptr(self.voxel_keys), V, g.key_bytes, g.total_bits, _ptr(table), tbytes,
+                           _ptr(self._point2voxel), _stream())
+                    L.call("vapc_point2voxel_set_ctas_per_sm", 16)
+                    self._p2v_event = side.record_event()
+                for t in (keys, self.voxel_keys, self._point2voxel):
+                    t.record_stream(side)
+            else:
+                table = _empty(tbytes, torch.uint8, device)
+                L.call("vapc_point2voxel_dense", _ptr(keys), n, _ptr(self.voxel_keys), V, g.key_bytes, g.total_bits, _ptr(table), tbytes,
+                       _ptr(self._point2voxel), _stream())
             del keys, table
         return self
+
+    @property
+    def point2voxel(self):
+        """uint32 voxel row of every point (int32 storage).  Formed on a side stream by build(); the first read makes the caller's
+        stream wait for it."""
+        if self._p2v_event is not None:
+            torch.cuda.current_stream(self._point2voxel.device).wait_event(self._p2v_event)
+            self._p2v_event = None
+        return self._point2voxel
+
+    @point2voxel.setter
+    def point2voxel(self, t):
+        self._p2v_event = None
+        self._point2voxel = t
 
     @property
     def device(self):
