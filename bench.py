@@ -289,7 +289,7 @@ def algorithmic_bytes(name, n, v, key_bytes, passes, low_passes):
     return {
         "vapc_minmax_f64": 24 * n,
         "vapc_pack_keys_f64": (24 + k + 32) * n,
-        "vapc_pack_records_bucketed": (8 + 1) * n + (1 + 24 + k + k + 32) * n + 2 * n,
+        "vapc_pack_records_bucketed": 8 * n + (24 + k + k + 32) * n + 2 * n,
         "vapc_sort_pairs": (k + passes * (2 * k + 8) - 4) * n,
         "vapc_sort_pairs_segmented": (k + low_passes * (2 * k + 8) - 4) * n,
         "vapc_sort_cells_segmented": (2 * k + 8) * n,
@@ -305,8 +305,8 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
     k = key_bytes
     table = [
         ("minmax_partial", 24 * n),
-        ("tile_digits_kernel", (8 + 1) * n + n / 3),               # x in; digit byte + the tile's 256 16-bit counts (per 1536 points) out
-        ("tile_scatter_kernel", (1 + 24 + k + k + 32) * n + 2 * n / 3),  # digits + offsets + x, y, z in; keys (input order), bucketed keys + records out
+        ("tile_digits_kernel", 8 * n + n / 3),                     # x in; the tile's 256 16-bit digit counts (per 1536 points) out
+        ("tile_scatter_kernel", (24 + k + k + 32) * n + 2 * n / 3),  # x, y, z + the tile's offsets in; keys (input order), bucketed keys + records out
         ("tile_offsets_kernel", n),                               # tile counts in, per-(tile, digit) first slots out: 6 B per 1.5 points
         ("pack_keys_kernel", (24 + k + 32) * n),
         ("digit_hist_kernel", k * n),

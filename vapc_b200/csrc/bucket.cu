@@ -11,15 +11,17 @@
 //
 // Round 2 layout (no ticket, no decoupled look-back: 25 % of the stall samples of the round-1 scatter kernel were its poll):
 //   tile_digits_kernel    a tile = 1536 consecutive points.  Reads x ONLY (the bucket digit is the leading bits of the voxel x
-//                         index), writes one digit byte per point and the tile's 256 digit counts        8 B/pt in, 1.3 B/pt out
+//                         index) and writes the tile's 256 digit counts                                  8 B/pt in, 0.33 B/pt out
 //   tile_chunk_sums / tile_chunk_scan / tile_offsets
 //                         column scan of the [tiles][256] count matrix -> first output slot of every (tile, digit),
-//                         bucket_start[]                                                                  ~2 B/pt
-//   tile_scatter_kernel   reads the digits of its tile, ranks them (radix_rank.cuh, stable), reads x, y, z, forms the packed key
-//                         (three IEEE divisions per point — hidden under the shared-memory reorder), writes the key in input order,
-//                         and key + record {x, y, z, index} at the bucketed position as whole lines       25.7 B/pt in, 40 B/pt out
+//                         bucket_start[]                                                                  ~1.3 B/pt
+//   tile_scatter_kernel   reads x, y, z, forms the packed key (floor((c - o) / vs) per axis, bit-exact without the division for almost
+//                         every point: voxel_of_fast), takes the digit from the voxel x index, ranks the digits (radix_rank.cuh,
+//                         stable), writes the key in input order, and key + record {x, y, z, index} at the bucketed position as
+//                         whole lines                                                                     24.7 B/pt in, 40 B/pt out
 // (Round 1: keys first in a pass of their own over x, y, z (28 B/pt), then a scatter pass with tickets and look-back (64 B/pt);
-// a kernel that published its counts only after the three divisions had spent 34 % of its samples polling predecessors.)
+// a kernel that published its counts only after the three divisions had spent 34 % of its samples polling predecessors.  A digit
+// byte per point written by the counting pass and read back by the scatter pass — VAPC_BUCKET_DIGIT_BYTES=1 — cost 0.1 ms more.)
 // Stable: inside a bucket the points keep their input order, so after the (stable) segmented sort the points
 // of a voxel are still in original index order.
 #include <algorithm>
@@ -34,9 +36,15 @@ using namespace rr;
 #ifndef VAPC_BUCKET_MINB
 #define VAPC_BUCKET_MINB 3
 #endif
+#ifndef VAPC_BUCKET_DIGIT_BYTES
+#define VAPC_BUCKET_DIGIT_BYTES 0  // 1: the counting pass also writes a digit byte per point that the scatter pass reads back (2 B/point more traffic;
+                                   // the scatter kernel forms the voxel x index for the key anyway, so it takes the digit from there)
+#endif
+constexpr bool kDigitBytes = VAPC_BUCKET_DIGIT_BYTES != 0;
 constexpr int kItems = VAPC_BUCKET_ITEMS;
 constexpr int kTile = kThreads * kItems;  // 1536 points: the reordered records of a tile take 48 KB of shared memory (6 vs 8 items: 2.22 vs 2.42 ms)
-constexpr int kChunkTiles = 512;          // tiles per chunk of the column scan
+constexpr int kChunkTiles = 128;          // tiles per chunk of the column scan (512: 128 CTAs, each a serial loop of 512 loads — 0.04 ms per kernel)
+constexpr int kScanGroups = 4;            // the chunk scan runs 4 column scans side by side, each over a quarter of the chunks
 
 template <typename KeyT>
 __device__ __forceinline__ unsigned bucket_of(KeyT key, int shift, unsigned mask) { return (unsigned)(key >> shift) & mask; }
@@ -49,20 +57,22 @@ __global__ void __launch_bounds__(kThreads) tile_digits_kernel(Src src, int64_t 
   sh[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * kTile + (threadIdx.x >> 5) * (32 * kItems) + (threadIdx.x & 31);
+  const bool full = (int64_t)(blockIdx.x + 1) * kTile <= n;  // all but the last tile: no per-point bound test
   double px[kItems];
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) px[k] = base + k * 32 < n ? src.cx(base + k * 32) : 0.0;
-  int bad = 0;
+  for (int k = 0; k < kItems; ++k) px[k] = (full || base + k * 32 < n) ? src.cx(base + k * 32) : 0.0;
+  unsigned long long over = 0;  // bits of any relative x index beyond the grid's bx bits
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    if (base + k * 32 < n) {
+    if (full || base + k * 32 < n) {
       const unsigned long long rx = (unsigned long long)(voxel_of_fast(px[k], g.ox, g.vs, g.ivs) - g.minx);
-      bad |= g.bx < 64 && (rx >> g.bx);
+      over |= rx;
       const unsigned d = (unsigned)(rx >> dshift) & mask;  // an out-of-grid point gets SOME digit: the caller raises on the status bit
-      digits[base + k * 32] = (uint8_t)d;
+      if (kDigitBytes) digits[base + k * 32] = (uint8_t)d;
       atomicAdd(&sh[d], 1u);
     }
   }
+  const int bad = g.bx < 64 && (over >> g.bx) != 0;
   __syncthreads();
   tile_counts[(int64_t)blockIdx.x * kRadix + threadIdx.x] = (uint16_t)sh[threadIdx.x];
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
@@ -72,30 +82,58 @@ __global__ void __launch_bounds__(kThreads) tile_digits_kernel(Src src, int64_t 
 __global__ void __launch_bounds__(kThreads) tile_chunk_sums_kernel(const uint16_t* __restrict__ tile_counts, int64_t ntiles, uint32_t* __restrict__ chunk_sums) {
   const int64_t t0 = (int64_t)blockIdx.x * kChunkTiles, t1 = min(ntiles, t0 + kChunkTiles);
   unsigned sum = 0;
-#pragma unroll 8
+#pragma unroll 16
   for (int64_t t = t0; t < t1; ++t) sum += tile_counts[t * kRadix + threadIdx.x];
   chunk_sums[(int64_t)blockIdx.x * kRadix + threadIdx.x] = sum;
 }
-__global__ void __launch_bounds__(kThreads) tile_chunk_scan_kernel(uint32_t* __restrict__ chunk_sums, int nchunks, int nb, uint32_t n,
-                                                                   uint32_t* __restrict__ bucket_start) {
+// chunk_sums[c][d] -> exclusive prefix over the chunks of the thread's GROUP (a quarter of the chunks, scanned side by side by the four
+// groups of the CTA); group_add[g][d] = first slot of digit d's bucket + the keys of d in the groups in front of g.  The first slot of
+// (chunk c, digit d) is chunk_sums[c][d] + group_add[c / per][d]: tile_offsets_kernel adds the two.  Loads are issued eight chunks
+// ahead of the stores (a load - store - load chain through one pointer is a DRAM round trip per chunk).
+__global__ void __launch_bounds__(kThreads * kScanGroups) tile_chunk_scan_kernel(uint32_t* __restrict__ chunk_sums, int nchunks, int per, int nb, uint32_t n,
+                                                                                 uint32_t* __restrict__ group_add, uint32_t* __restrict__ bucket_start) {
   __shared__ unsigned warp_s[33];
+  __shared__ unsigned group_total[kScanGroups][kRadix];
+  const int d = threadIdx.x & (kRadix - 1), grp = threadIdx.x >> kRadixBits;
+  const int c0 = min(nchunks, grp * per), c1 = min(nchunks, c0 + per);
   unsigned total = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const unsigned v = chunk_sums[(int64_t)c * kRadix + threadIdx.x];
-    chunk_sums[(int64_t)c * kRadix + threadIdx.x] = total;
-    total += v;
+  for (int c = c0; c < c1; c += 8) {
+    unsigned v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = c + q < c1 ? chunk_sums[(int64_t)(c + q) * kRadix + d] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (c + q < c1) chunk_sums[(int64_t)(c + q) * kRadix + d] = total;
+      total += v[q];
+    }
   }
+  group_total[grp][d] = total;
+  __syncthreads();
+  unsigned before = 0, all_groups = 0;  // keys of digit d in the groups in front / in all chunks
+#pragma unroll
+  for (int q = 0; q < kScanGroups; ++q) {
+    const unsigned t = group_total[q][d];
+    if (q < grp) before += t;
+    all_groups += t;
+  }
+  // first slot of the digit's bucket: exclusive scan over the digits (the threads of the other groups add zeros)
+  __shared__ unsigned digit_base[kRadix];
   unsigned all;
-  const unsigned base = block_exclusive_scan(total, warp_s, &all);  // first slot of the digit's bucket
-  for (int c = 0; c < nchunks; ++c) chunk_sums[(int64_t)c * kRadix + threadIdx.x] += base;
-  if ((int)threadIdx.x < nb) bucket_start[threadIdx.x] = base;
-  if (threadIdx.x == 0) bucket_start[nb] = n;
+  const unsigned base = block_exclusive_scan(grp == 0 ? all_groups : 0u, warp_s, &all);
+  if (grp == 0) digit_base[d] = base;
+  __syncthreads();
+  group_add[grp * kRadix + d] = digit_base[d] + before;
+  if (grp == 0) {
+    if (d < nb) bucket_start[d] = digit_base[d];
+    if (d == 0) bucket_start[nb] = n;
+  }
 }
 __global__ void __launch_bounds__(kThreads) tile_offsets_kernel(const uint16_t* __restrict__ tile_counts, const uint32_t* __restrict__ chunk_base,
-                                                                int64_t ntiles, uint32_t* __restrict__ tile_offsets) {
+                                                                const uint32_t* __restrict__ group_add, int per, int64_t ntiles,
+                                                                uint32_t* __restrict__ tile_offsets) {
   const int64_t t0 = (int64_t)blockIdx.x * kChunkTiles, t1 = min(ntiles, t0 + kChunkTiles);
-  unsigned run = chunk_base[(int64_t)blockIdx.x * kRadix + threadIdx.x];
-#pragma unroll 8
+  unsigned run = chunk_base[(int64_t)blockIdx.x * kRadix + threadIdx.x] + group_add[(blockIdx.x / per) * kRadix + threadIdx.x];
+#pragma unroll 16
   for (int64_t t = t0; t < t1; ++t) {
     tile_offsets[t * kRadix + threadIdx.x] = run;
     run += tile_counts[t * kRadix + threadIdx.x];
@@ -122,7 +160,7 @@ struct BucketSmem {
 // (64-bit keys of up to 40 bits): the segmented sort then moves 4-byte keys; vapc_expand_bucket_keys restores the full keys.
 template <typename KeyT, typename KeyOutT, typename Src>
 __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB : 3) tile_scatter_kernel(
-    const uint8_t* __restrict__ digits, Src src, int64_t n, Grid g, int shift, unsigned mask, const uint32_t* __restrict__ tile_offsets,
+    const uint8_t* __restrict__ digits, Src src, int64_t n, Grid g, int shift, int dshift, unsigned mask, const uint32_t* __restrict__ tile_offsets,
     KeyT* __restrict__ keys_orig, KeyOutT* __restrict__ keys_b, double4* __restrict__ rec_b, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BucketSmem<KeyT>& sm = *reinterpret_cast<BucketSmem<KeyT>*>(smem_raw);
@@ -137,8 +175,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
   const int slot0 = warp * (32 * kItems) + lane;
   const int64_t wbase = tile_base + slot0;
   unsigned dig[kItems];
+  if (kDigitBytes) {
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) dig[k] = (full || wbase + k * 32 < n) ? (unsigned)digits[wbase + k * 32] : (unsigned)(kRadix - 1);
+    for (int k = 0; k < kItems; ++k) dig[k] = (full || wbase + k * 32 < n) ? (unsigned)digits[wbase + k * 32] : (unsigned)(kRadix - 1);
+  }
   double px[kItems], py[kItems], pz[kItems];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
@@ -147,24 +187,26 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_BUCKET_MINB
     py[k] = valid ? src.cy(wbase + k * 32) : 0.0;
     pz[k] = valid ? src.cz(wbase + k * 32) : 0.0;
   }
-  __syncthreads();  // rank_init
-
-  unsigned rank2[kItems / 2];
-  warp_rank<kItems>([&](int k) { return dig[k]; }, sm.r, sm.u.masks, rank2);
-
-  // the packed keys (three IEEE divisions per point) while the other warps rank; the key goes out in input order at once
+  // the packed keys; the bucket digit = the leading bits of the voxel x index (the same expression tile_digits_kernel counted).
+  // The key goes out in input order at once.
   KeyT key[kItems];
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     int b = 0;
+    unsigned long long rx;
     const bool valid = full || wbase + k * 32 < n;
-    key[k] = pack_one<KeyT>(px[k], py[k], pz[k], g, b);
-    // out of the grid (status bit) or past the end of the input: keep the key consistent with the digit it was ranked by
+    key[k] = pack_one<KeyT>(px[k], py[k], pz[k], g, b, &rx);
+    if (!kDigitBytes) dig[k] = valid ? (unsigned)(rx >> dshift) & mask : (unsigned)(kRadix - 1);
+    // out of the grid (status bit) or past the end of the input: keep the key consistent with the digit it is ranked by
     if (b || !valid) key[k] = (KeyT)dig[k] << shift;
     bad |= valid && b;
     if (valid) keys_orig[wbase + k * 32] = key[k];
   }
+  __syncthreads();  // rank_init
+
+  unsigned rank2[kItems / 2];
+  warp_rank<kItems>([&](int k) { return dig[k]; }, sm.r, sm.u.masks, rank2);
   __syncthreads();
 
   // first slot of every digit inside the tile, and of every warp's keys of it
@@ -235,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) expand_keys_kernel(const uint32_t* _
 
 inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-// workspace: [digits n x 1][tile_counts tiles x 256 x 2][tile_offsets tiles x 256 x 4][chunk sums chunks x 256 x 4]
+// workspace: [digits n x 1, only with VAPC_BUCKET_DIGIT_BYTES][tile_counts tiles x 256 x 2][tile_offsets tiles x 256 x 4][chunk sums (chunks + 4 groups) x 256 x 4]
 struct BucketWs {
   uint8_t* digits;
   uint16_t* tile_counts;
@@ -245,13 +287,13 @@ struct BucketWs {
 inline int64_t num_chunks(int64_t ntiles) { return (ntiles + kChunkTiles - 1) / kChunkTiles; }
 inline size_t bucket_ws_bytes(int64_t n) {
   const int64_t nt = num_tiles(n < 1 ? 1 : n);
-  return align256((size_t)n) + align256((size_t)nt * kRadix * 2) + align256((size_t)nt * kRadix * 4) + align256((size_t)num_chunks(nt) * kRadix * 4);
+  return align256(kDigitBytes ? (size_t)n : 0) + align256((size_t)nt * kRadix * 2) + align256((size_t)nt * kRadix * 4) + align256(((size_t)num_chunks(nt) + kScanGroups) * kRadix * 4);
 }
 inline BucketWs carve_bucket_ws(void* ws, int64_t n) {
   const int64_t nt = num_tiles(n);
   unsigned char* p = static_cast<unsigned char*>(ws);
   BucketWs w;
-  w.digits = p; p += align256((size_t)n);
+  w.digits = p; p += align256(kDigitBytes ? (size_t)n : 0);
   w.tile_counts = reinterpret_cast<uint16_t*>(p); p += align256((size_t)nt * kRadix * 2);
   w.tile_offsets = reinterpret_cast<uint32_t*>(p); p += align256((size_t)nt * kRadix * 4);
   w.chunk_sums = reinterpret_cast<uint32_t*>(p);
@@ -268,11 +310,13 @@ int bucket_impl(const Src& src, int64_t n, const Grid& g, int mb, KeyOutT* keys_
   const BucketWs w = carve_bucket_ws(ws, n);
   VAPC_LAUNCH((tile_digits_kernel<Src>), (unsigned)ntiles, kThreads, 0, s, src, n, g, g.bx - mb, mask, w.digits, w.tile_counts, status);
   VAPC_LAUNCH(tile_chunk_sums_kernel, (unsigned)nchunks, kThreads, 0, s, w.tile_counts, ntiles, w.chunk_sums);
-  VAPC_LAUNCH(tile_chunk_scan_kernel, 1, kThreads, 0, s, w.chunk_sums, nchunks, 1 << mb, (uint32_t)n, bucket_start);
-  VAPC_LAUNCH(tile_offsets_kernel, (unsigned)nchunks, kThreads, 0, s, w.tile_counts, w.chunk_sums, ntiles, w.tile_offsets);
+  const int per = (nchunks + kScanGroups - 1) / kScanGroups;  // chunks per scan group
+  uint32_t* group_add = w.chunk_sums + (size_t)nchunks * kRadix;
+  VAPC_LAUNCH(tile_chunk_scan_kernel, 1, kThreads * kScanGroups, 0, s, w.chunk_sums, nchunks, per, 1 << mb, (uint32_t)n, group_add, bucket_start);
+  VAPC_LAUNCH(tile_offsets_kernel, (unsigned)nchunks, kThreads, 0, s, w.tile_counts, w.chunk_sums, group_add, per, ntiles, w.tile_offsets);
   const size_t smem = sizeof(BucketSmem<KeyT>);
   VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(tile_scatter_kernel<KeyT, KeyOutT, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VAPC_LAUNCH((tile_scatter_kernel<KeyT, KeyOutT, Src>), (unsigned)ntiles, kThreads, smem, s, w.digits, src, n, g, shift, mask, w.tile_offsets, keys_orig, keys_b,
+  VAPC_LAUNCH((tile_scatter_kernel<KeyT, KeyOutT, Src>), (unsigned)ntiles, kThreads, smem, s, w.digits, src, n, g, shift, g.bx - mb, mask, w.tile_offsets, keys_orig, keys_b,
               rec_b, status);
   VAPC_CHECK_LAUNCH();
   return VAPC_OK;

@@ -226,6 +226,17 @@ P2V_SIDE_PRIORITY = os.environ.get("VAPC_P2V_SIDE_PRIORITY", "1") != "0"
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
+_PINNED_SCALARS: Dict[int, tuple] = {}
+
+
+def _pinned_scalars(device):
+    """(int64[2], int32[1]) pinned host words per device for the voxel count / status read-back of build()."""
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i not in _PINNED_SCALARS:
+        _PINNED_SCALARS[i] = (torch.zeros(2, dtype=torch.int64).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory())
+    return _PINNED_SCALARS[i]
+
+
 def _side_stream(device):
     i = device.index if device.index is not None else torch.cuda.current_device()
     if i not in _SIDE_STREAMS:
@@ -402,7 +413,13 @@ class VoxelCloud:
                 del keys
         if host is None:
             L.call("vapc_count_voxels", _ptr(self.keys_sorted), n, g.key_bytes, _ptr(nv), _ptr(self._seg_ws), ws_bytes, _stream())
-            host = torch.cat([nv[:1], status.to(torch.int64)]).cpu()  # the one sync of the pipeline
+            # the one sync of the pipeline: two small copies into pinned memory, no kernel in between (the GPU idles until the host
+            # has read V and queued the next call, so every microsecond here is on the step)
+            hv, hs = _pinned_scalars(device)
+            hv.copy_(nv, non_blocking=True)
+            hs.copy_(status, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            host = (int(hv[0]), int(hs[0]))
         if int(host[1]) & 1:
             raise L.VapcError(L.VAPC_E_RANGE, "a point fell outside the voxel grid bounds (NaN / inf coordinate or wrong bounds)")
         self.nvoxels = V = int(host[0])
