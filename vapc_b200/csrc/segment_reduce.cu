@@ -117,6 +117,10 @@ struct TileSmem {
 constexpr int kLongSeg = 64;
 __device__ __forceinline__ int sw(int p) { return p + (p >> 4); }
 
+template <typename KeyT>
+__device__ __forceinline__ void tile_prologue_loaded(TileSmem<KeyT>& sm, int64_t n, int64_t base, KeyT (&key)[kItems], KeyT prev,
+                                                     bool (&valid)[kItems], bool (&head)[kItems], unsigned (&inc)[kItems], unsigned& nheads,
+                                                     int& tile_n);
 // Common prologue: flags, scan, segment tables, voxel-table bookkeeping.
 // On return inc[j] = number of heads at tile positions <= this one (local segment id; 0 = continuation).
 template <typename KeyT>
@@ -125,6 +129,14 @@ __device__ __forceinline__ void tile_prologue(TileSmem<KeyT>& sm, const KeyT* __
                                               unsigned (&inc)[kItems], unsigned& nheads, int& tile_n) {
   KeyT prev;
   load_tile_keys(keys, n, base, key, prev, valid);
+  tile_prologue_loaded(sm, n, base, key, prev, valid, head, inc, nheads, tile_n);
+}
+// The same for keys the caller has loaded already (load_tile_keys): a kernel that also gathers through a second array issues both
+// loads first and runs this scan while the gathers are in flight.
+template <typename KeyT>
+__device__ __forceinline__ void tile_prologue_loaded(TileSmem<KeyT>& sm, int64_t n, int64_t base, KeyT (&key)[kItems], KeyT prev,
+                                                     bool (&valid)[kItems], bool (&head)[kItems], unsigned (&inc)[kItems], unsigned& nheads,
+                                                     int& tile_n) {
   const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
   const unsigned local = head_flags(key, prev, valid, p0, head);
   const unsigned excl = block_exclusive_scan(local, sm.scan_s, &nheads);
@@ -195,7 +207,11 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
   unsigned inc[kItems], nheads;
   int tile_n;
 
-  // issue the record-position loads + gathers first so that they overlap the scan
+  // the keys, the tile's first row and the record positions are requested together (one memory latency, not two: the scan below
+  // then runs while the gathers that depend on the positions are in flight)
+  KeyT prev;
+  load_tile_keys(keys, n, base, key, prev, valid);
+  const uint32_t first_row = tile_first[blockIdx.x];  // voxel row of the first head in this tile
   const int64_t p0 = base + (int64_t)threadIdx.x * kItems;
   uint32_t idx[kItems];
   if (p0 + kItems <= n) {
@@ -227,8 +243,7 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     }
   }
 
-  tile_prologue(sm, keys, n, base, key, valid, head, inc, nheads, tile_n);
-  const uint32_t first_row = tile_first[blockIdx.x];  // voxel row of the first head in this tile
+  tile_prologue_loaded(sm, n, base, key, prev, valid, head, inc, nheads, tile_n);
 
   uint32_t rows[kItems];
 #pragma unroll

@@ -19,7 +19,13 @@
 
 namespace {
 using namespace rr;
-constexpr int kItems = 16;
+#ifndef VAPC_SORT_ITEMS
+#define VAPC_SORT_ITEMS 16
+#endif
+#ifndef VAPC_SORT_MINB
+#define VAPC_SORT_MINB 4
+#endif
+constexpr int kItems = VAPC_SORT_ITEMS;
 constexpr int kTile = kThreads * kItems;  // 4096
 constexpr int kMaxPasses = 8;             // 64-bit keys
 constexpr int kMaxSegments = 256;
@@ -153,7 +159,7 @@ struct SweepSmem {
 };
 
 template <typename KeyT, typename LookT, bool IOTA, bool SEG>
-__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) onesweep_kernel(
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? VAPC_SORT_MINB : 3) onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, KeyT* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
     int64_t n, int shift, unsigned mask, const uint32_t* __restrict__ digit_base, LookT* __restrict__ look, unsigned* __restrict__ ticket,
     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_first_tile, int nseg) {
