@@ -201,14 +201,16 @@ def workload_config(points_per_gpu, gpus, bounds="header"):
     }
 
 
-def workload_config_multi(points_per_gpu, gpus, vs):
+def workload_config_multi(points_per_gpu, gpus, vs, bounds="computed"):
     return {
         "workload": f"configs[2]: {points_per_gpu * gpus / 1e9:g}B-point synthetic clustered (terrain sheet + trees) cloud sharded over {gpus} GPUs in "
                     f"scan-line order ({points_per_gpu / 1e6:g}M points per GPU: rank r holds the strip y in [r W, (r+1) W) of a 1000 m wide cloud, W = "
                     f"{125.0 * points_per_gpu / 1.25e8:g} m), voxel_size={vs} m, full attribute set; partial voxel tables exchanged by key range, then merged",
         "points_per_gpu": points_per_gpu, "voxel_size": vs,
         "l2": "inputs (24 B/point, 3 GB per GPU) are larger than the 126 MB L2; no flush needed",
-        "parallelism": f"points sharded in contiguous chunks over {gpus} GPUs; every rank voxelises its chunk alone (local bounds by a min/max pass), "
+        "parallelism": f"points sharded in contiguous chunks over {gpus} GPUs; every rank voxelises its chunk alone (" +
+                       ("the chunks' bounding boxes are an input, as their LAS headers state them: no min/max pass and no collective for the bounds; "
+                        "extra.bounds_computed is the step without them" if bounds == "header" else "local bounds by a min/max pass, all-gathered") + "), "
                        "the key space is cut by a global histogram, the partial rows that leave a rank are written into the owner's receive buffer over "
                        "NVLink (peer memory), the owner merges; extra.shuffled = the same cloud dealt at random, extra.slab_configs1 = round 1's layout",
     }
@@ -326,11 +328,19 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, launches_per_step):
     return kernel, 0.0
 
 
-def time_steps(step, steps, barrier, world, device, dist, profile=False, L=None):
-    """K calls of step() between CUDA events (max over ranks).  profile: per-kernel / per-call CUDA events inside the same region."""
+def time_steps(step, steps, barrier, world, device, dist, profile=False, L=None, settle=3):
+    """K calls of step() between CUDA events (max over ranks).  profile: per-kernel / per-call CUDA events inside the same region.
+    settle: untimed calls in front, in the SAME loop as the timed ones (the result of the previous call released before the next one
+    starts): the caching allocator and the side stream's deferred frees reach the state the timed calls then repeat.  One event per
+    step lands in step_ms (the spread of the K steps; the headline is the whole region / K)."""
     import torch
 
     records = []
+    out = None
+    for _ in range(settle):
+        out = None
+        out = step()
+    out = None
 
     def observer(name, phase):
         ev = torch.cuda.Event(enable_timing=True)
@@ -346,10 +356,13 @@ def time_steps(step, steps, barrier, world, device, dist, profile=False, L=None)
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
-    out = None
+    marks = []
     for _ in range(steps):
         out = None
         out = step()
+        if not profile:
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
     t_end.record()
     if profile:
         L.observer = None
@@ -359,12 +372,13 @@ def time_steps(step, steps, barrier, world, device, dist, profile=False, L=None)
     kernel_times = L.profile_collect() if profile else {}
     launches = (L.raw("vapc_launch_count")() - launches0) if L is not None else 0
     ms_total = t_start.elapsed_time(t_end)
+    step_ms = [round(a.elapsed_time(b), 4) for a, b in zip([t_start] + marks[:-1], marks)]
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     return {"ms_per_step": ms_total / steps, "out": out, "records": records, "kernel_times": kernel_times, "launches": launches,
-            "window": [t0, t1]}
+            "window": [t0, t1], "step_ms": step_ms}
 
 
 def ncu_traffic():
@@ -456,8 +470,7 @@ def main():
     if chunk_alone:
         # ---- N = 1, one GPU's chunk of configs[2] voxelised alone (what every rank of the N > 1 run does before the exchange) ----
         x, y, z = synth.clustered_chunk(n, 0, 1, device, seed=3, scan_order=True)
-        header_bounds = None
-        args.bounds = "computed"
+        header_bounds = [float(c.min()) for c in (x, y, z)] + [float(c.max()) for c in (x, y, z)]  # what the chunk's LAS header states
 
         def make_step(bounds):
             def step():
@@ -467,8 +480,8 @@ def main():
                 return cloud, st
             return step
 
-        step_device = make_step(None)
-        workload = dict(workload_config_multi(n, 1, vs), parallelism="one GPU: the chunk voxelised alone, no exchange (bounds computed)")
+        step_device = make_step(header_bounds if args.bounds == "header" else None)
+        workload = dict(workload_config_multi(n, 1, vs, args.bounds), parallelism=f"one GPU: the chunk voxelised alone, no exchange (bounds: {args.bounds})")
     elif not multi:
         # ---- N = 1: configs[1] -----------------------------------------------------------------------------------------
         x, y, z = synth.uniform_cloud(n, seed=2, device=device, extent=EXTENT)
@@ -489,10 +502,13 @@ def main():
         # ---- N > 1: configs[2], scan-line order ----------------------------------------------------------------------------
         x, y, z = synth.clustered_chunk(n, rank, world, device, seed=3, scan_order=True)
 
-        def step_device():
-            return D.voxel_statistics(x, y, z, vs, ORIGIN)
+        # every chunk's bounding box as the header of its LAS file states it, exchanged once at load time (outside the step)
+        chunk_bounds = D.gather_bounds(x, y, z) if args.bounds == "header" else None
 
-        workload = workload_config_multi(n, world, vs)
+        def step_device():
+            return D.voxel_statistics(x, y, z, vs, ORIGIN, all_bounds=chunk_bounds)
+
+        workload = workload_config_multi(n, world, vs, args.bounds)
 
     for _ in range(max(args.warmup, 3)):
         cloud, st = step_device()
@@ -512,6 +528,7 @@ def main():
     ms_per_step = plain["ms_per_step"]
     value = n * world / (ms_per_step * 1e-3)
     launches = plain["launches"]
+    step_ms = plain["step_ms"]
     plain = None
     # ---- the same K steps once more, instrumented: CUDA events around every kernel launch (on the launching stream) and every C-ABI
     # call, for the roofline and the kernel table.  The ~40 event records per step cost 0.1-0.2 ms of a 5.5 ms step, which is why the
@@ -600,8 +617,10 @@ def main():
         del x, y, z
         cx, cy, cz = synth.clustered_chunk(125_000_000, 0, 1, device, seed=3, scan_order=True)
 
+        chunk_hdr = ([float(c.min()) for c in (cx, cy, cz)] + [float(c.max()) for c in (cx, cy, cz)]) if args.bounds == "header" else None
+
         def step_chunk():
-            c = E.VoxelCloud.build(cx, cy, cz, VOXEL_SIZE_MULTI, ORIGIN, keep_columns=False, want_point2voxel=False)
+            c = E.VoxelCloud.build(cx, cy, cz, VOXEL_SIZE_MULTI, ORIGIN, keep_columns=False, want_point2voxel=False, bounds=chunk_hdr)
             return c, c.stats(**FULL)
         for _ in range(2):
             step_chunk()
@@ -610,7 +629,7 @@ def main():
         extra["configs2_one_gpu"] = {"ms_per_step": tc["ms_per_step"], "value": 125_000_000 / (tc["ms_per_step"] * 1e-3), "points": 125_000_000,
                                      "voxel_size": VOXEL_SIZE_MULTI, "voxels": tc["out"][0].nvoxels, "key_bits": tc["out"][0].grid.total_bits,
                                      "what": "configs[2] at N = 1: the 1.25e8-point clustered chunk one rank of the N > 1 run holds, voxelised alone with "
-                                             "the calls every rank issues before the exchange (bounds computed, no point->voxel map).  `bench.py --gpus N` "
+                                             "the calls every rank issues before the exchange (bounds as in config.bounds, no point->voxel map).  `bench.py --gpus N` "
                                              "(N > 1) reports configs[2]: its value / (N x this value) is that workload's scaling efficiency"}
         tc = None
         del cx, cy, cz
@@ -626,8 +645,10 @@ def main():
         check["voxels_table"] = nvox_global
         check["ok"] = bool(check["ok"] and check["voxels_torch_unique"] == nvox_global)
         # the per-GPU share of the same workload WITHOUT the other ranks: local pipeline only (N = 1 on this rank's chunk)
+        own_bounds = chunk_bounds[rank] if chunk_bounds is not None else None
+
         def step_local():
-            c = E.VoxelCloud.build(x, y, z, vs, ORIGIN, keep_columns=False, want_point2voxel=False)
+            c = E.VoxelCloud.build(x, y, z, vs, ORIGIN, keep_columns=False, want_point2voxel=False, bounds=own_bounds)
             return c, c.stats(**FULL)
         step_local()
         tl = time_steps(step_local, args.steps, barrier, world, device, dist, L=L)
@@ -636,6 +657,16 @@ def main():
                                           "what": "every rank's own chunk voxelised alone (no exchange, no merge), max over ranks: the N = 1 "
                                                   "figure of THIS workload; value / (N x value_per_gpu) is its scaling efficiency"}
         tl = None
+        if chunk_bounds is not None:
+            def step_nb():
+                return D.voxel_statistics(x, y, z, vs, ORIGIN)
+            step_nb()
+            t2 = time_steps(step_nb, args.steps, barrier, world, device, dist, L=L)
+            windows.append(t2["window"])
+            extra["bounds_computed"] = {"ms_per_step": t2["ms_per_step"], "value": n * world / (t2["ms_per_step"] * 1e-3),
+                                        "what": "the same step when nobody knows the chunks' bounding boxes: a min/max pass over x, y, z (24 B/point) and an "
+                                                "all-gather of the boxes inside the step"}
+            t2 = None
         nvlink_bytes = rows_exchanged * 88
         extra["exchange"] = {"partial_rows_sent_all_ranks": rows_exchanged, "bytes_over_nvlink_per_step": nvlink_bytes,
                              "share_of_rows": round(rows_exchanged / max(1, nvox_global), 4)}
@@ -708,7 +739,7 @@ def main():
 
             def compute_fn(dx, dy, dz):
                 fx, fy, fz = E.las_coordinates(dx, dy, dz, [QUANT] * 3, [0.0] * 3, device)
-                c, s_ = D.voxel_statistics(fx, fy, fz, vs, ORIGIN, stats_columns=e2e_cols)
+                c, s_ = D.voxel_statistics(fx, fy, fz, vs, ORIGIN, stats_columns=e2e_cols, all_bounds=chunk_bounds)
                 out = {"voxel_keys": c.voxel_keys, "count": c.count}
                 out.update({k: getattr(s_, k) for k in e2e_cols})
                 return out
@@ -802,7 +833,7 @@ def main():
                                                           "extra.configs2_one_gpu"}} if multi else {}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check, "extra": extra, "kernels": per_kernel, "abi_calls": breakdown,
-            "ms_per_step_instrumented": ms_instrumented, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3), "gaps_between_calls_ms": gaps,
+            "step_ms": step_ms, "ms_per_step_instrumented": ms_instrumented, "gpu_ms_in_abi_calls_per_step": round(gpu_ms, 3), "gaps_between_calls_ms": gaps,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

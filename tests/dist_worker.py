@@ -191,6 +191,13 @@ def main():
             sent = torch.tensor([table.partial_rows_sent, forced.partial_rows_sent], device=dev)
             dist.all_reduce(sent)
             assert int(sent[0]) < 0.6 * int(sent[1]), ("rows sent with the y-leading / x-leading key", sent.tolist())
+        # the chunks' bounding boxes as an input (LAS headers: no min/max pass, no collective for the bounds): the same table bit for bit
+        hdr = D.gather_bounds(x, y, z)
+        t_h, s_h = D.voxel_statistics(x, y, z, vs, origin, exchange=exchange, all_bounds=hdr)
+        assert t_h.axis_order == table.axis_order and t_h.nvoxels == table.nvoxels
+        assert torch.equal(t_h.voxel_keys, table.voxel_keys) and torch.equal(t_h.count, table.count), "all_bounds= changes the table"
+        for name in ("cog", "cov", "eig"):
+            assert torch.equal(torch.nan_to_num(getattr(s_h, name)), torch.nan_to_num(getattr(st, name))), ("all_bounds=", name)
         if rank == 0:
             print(f"[{mode}, {exchange}] world={world}: axis order {table.axis_order}, owned voxels {allc}, partial rows sent by rank 0: "
                   f"{table.partial_rows_sent}", flush=True)

@@ -337,14 +337,14 @@ def gather_bounds(x, y, z, group=None) -> np.ndarray:
 
 
 def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, with_stats=True, exchange="peer", bounds=None,
-                     thresholds=None, keep_local=False, stats_columns=None, axis_order="auto", keep_moments=None):
+                     thresholds=None, keep_local=False, stats_columns=None, axis_order="auto", keep_moments=None, all_bounds=None):
     """The multi-GPU hot path.  x, y, z: this rank's chunk (CUDA fp64).  Returns (ShardedVoxelTable, VoxelStats).
 
     Every rank voxelises its chunk with its OWN grid (keys relative to its own lowest voxel: fewer key bits and radix passes
     than the global layout, and no dependence on the global bounds, whose all-reduce overlaps the local pipeline).  The
     sorted local table is then re-keyed in the global layout (same order), splitters and destinations are planned on the
     device, only the rows that leave the rank are packed and exchanged (ONE all-to-all), and the owner merges its own rows
-    (in place) with the received ones.  Five small device -> host copies synchronise the host: local bounds, local voxel
+    (in place) with the received ones.  Small device -> host copies synchronise the host: the ranks' bounds (not with all_bounds=), local voxel
     count, global bounds, the all-gathered send-count matrix, the merged voxel count.
 
     keep_moments: keep the merged (mean3, m2) moments in the table (needed to merge it again or to ask for other statistics later).
@@ -353,6 +353,9 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     axis_order: "auto" (choose_axis_order from the ranks' bounding boxes) or a permutation of (0, 1, 2): the coordinate axis that
     leads the packed key.  Results come back in x, y, z order (ShardedVoxelTable.stats / voxel_coords); only the ROW order of the
     sharded table follows the internal order.
+    all_bounds (optional): [world, 6] bounding boxes of every rank's chunk as their LAS headers state them (gather_bounds once at load
+    time, or the headers themselves): no min/max pass over the points and no collective for the bounds inside the step; a point outside
+    its rank's stated box raises VAPC_E_RANGE.
     bounds (optional): global coordinate bounds every rank already agrees on; thresholds (optional): the
     world - 1 key thresholds of an earlier table over the SAME grid — the rows are then sent to the owners of those key
     ranges instead of re-balancing, so that two tables (two epochs) are range-aligned rank by rank (two_epoch_change)."""
@@ -364,8 +367,11 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
     dev = x.device
     # the local bounding boxes of all ranks: the global bounds, and which axis leads the key (the one the chunks are separated along)
     local_b = None
-    if bounds is None or axis_order == "auto":
-        allb = gather_bounds(x, y, z, group)
+    if all_bounds is not None or bounds is None or axis_order == "auto":
+        if all_bounds is not None:
+            allb = np.asarray(all_bounds, dtype=np.float64).reshape(world, 6)
+        else:
+            allb = gather_bounds(x, y, z, group)
         local_b = allb[rank]
         if bounds is None:
             bounds = np.concatenate([allb[:, :3].min(0), allb[:, 3:].max(0)])
@@ -453,19 +459,30 @@ def voxel_statistics(x, y, z, voxel_size, origin=(0.0, 0.0, 0.0), group=None, wi
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         nv = torch.zeros(1, dtype=torch.int64, device=dev)
         L.call("vapc_count_voxels", E._ptr(ks), n_in, g.key_bytes, E._ptr(nv), E._ptr(ws), ws_bytes, E._stream())
-        nu = int(nv.item())
-        u_keys = torch.empty(nu, dtype=kdt, device=dev)
-        u_count = torch.empty(nu, dtype=torch.int32, device=dev)
-        u_mean = torch.empty((3, nu), dtype=torch.float64, device=dev)
-        u_m2 = torch.empty((6, nu), dtype=torch.float64, device=dev)
-        L.call("vapc_merge_partial_rows", E._ptr(ks), E._ptr(order), n_in, g.key_bytes, E._ptr(in_rows), None, None, None, 0, 0, 0, nu,
+        # the number of distinct received keys (nu) and of those the own rows do not hold (-> vm) reach the host in ONE read: the
+        # combined rows are formed at the upper bound n_in (column stride n_in; slots past nu keep the all-ones key, which no own row
+        # holds and which the validity mask keeps out of the prefix), then cut to nu
+        u_keys = torch.full((n_in,), -1, dtype=kdt, device=dev)
+        u_count = torch.empty(n_in, dtype=torch.int32, device=dev)
+        u_mean = torch.empty((3, n_in), dtype=torch.float64, device=dev)
+        u_m2 = torch.empty((6, n_in), dtype=torch.float64, device=dev)
+        L.call("vapc_merge_partial_rows", E._ptr(ks), E._ptr(order), n_in, g.key_bytes, E._ptr(in_rows), None, None, None, 0, 0, 0, n_in,
                E._ptr(u_keys), E._ptr(u_count), E._ptr(u_mean), E._ptr(u_m2), E._ptr(ws), ws_bytes, E._stream())
         u_keys64 = keys_as_int64(u_keys).contiguous()
-        at = torch.searchsorted(own_keys, u_keys64) if n_own else torch.zeros(nu, dtype=torch.int64, device=dev)
-        held = (own_keys[at.clamp(max=max(n_own - 1, 0))] == u_keys64) & (at < n_own) if n_own else torch.zeros(nu, dtype=torch.bool, device=dev)
-        new_before = torch.zeros(nu + 1, dtype=torch.int64, device=dev)
-        torch.cumsum((~held).to(torch.int64), 0, out=new_before[1:])
-        vm = n_own + int(new_before[-1].item())
+        valid = torch.arange(n_in, device=dev) < nv
+        if n_own:
+            at = torch.searchsorted(own_keys, u_keys64)
+            held = (own_keys[at.clamp(max=n_own - 1)] == u_keys64) & (at < n_own)
+            fresh = valid & ~held
+        else:
+            fresh = valid
+        new_before = torch.zeros(n_in + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(fresh.to(torch.int64), 0, out=new_before[1:])
+        nu, n_new = torch.stack([nv[0], new_before[-1]]).cpu().tolist()
+        vm = n_own + n_new
+        if nu < n_in:
+            u_keys64, u_count, new_before = u_keys64[:nu], u_count[:nu], new_before[: nu + 1]
+            u_mean, u_m2 = u_mean[:, :nu].contiguous(), u_m2[:, :nu].contiguous()
     else:
         nu, u_keys64, u_count, u_mean, u_m2, new_before, vm = 0, None, None, None, None, None, n_own
     if keep_moments is None:
