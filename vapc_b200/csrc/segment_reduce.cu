@@ -100,6 +100,19 @@ __global__ void __launch_bounds__(kThreads) count_heads_kernel(const KeyT* __res
 }
 
 // ---- shared tile state ----------------------------------------------------------------------------
+#ifndef VAPC_LONG_SEG
+#define VAPC_LONG_SEG 64
+#endif
+#ifndef VAPC_MID_SEG
+#define VAPC_MID_SEG 16
+#endif
+#ifndef VAPC_MID_MEAN
+#define VAPC_MID_MEAN 8
+#endif
+constexpr int kLongSeg = VAPC_LONG_SEG;  // local segments of this many points or more are reduced by a warp instead of one thread
+constexpr int kMidSeg = VAPC_MID_SEG;    // ... and, in the kernel for clouds of fewer than VAPC_MID_MEAN points per voxel, those of kMidSeg ..
+                                         // kLongSeg - 1 points by a group of 8 lanes
+constexpr int kQueueSeg = kMidSeg;
 template <typename KeyT>
 struct TileSmem {
   unsigned scan_s[33];
@@ -112,9 +125,10 @@ struct TileSmem {
   double x[kSegTile + kSegTile / 16], y[kSegTile + kSegTile / 16], z[kSegTile + kSegTile / 16];
   // local segments of >= kLongSeg points are not walked by one thread but handed to a warp each
   unsigned n_long;
-  unsigned short long_seg[kSegTile / 64 + 2];
+  unsigned short long_seg[kSegTile / kLongSeg + 2];
+  unsigned n_mid;
+  unsigned short mid_seg[kSegTile / kQueueSeg + 2];
 };
-constexpr int kLongSeg = 64;
 __device__ __forceinline__ int sw(int p) { return p + (p >> 4); }
 
 template <typename KeyT>
@@ -193,7 +207,10 @@ __global__ void __launch_bounds__(kThreads) run_lengths_kernel(const KeyT* __res
 }
 
 // ---- step 2: moments ------------------------------------------------------------------------------
-template <typename KeyT>
+// MID: the middle tier is compiled in.  Clouds of few points per voxel on average are the ones where single voxels stand out (measured,
+// 1.25e8 clustered points, 3.2 per voxel: 2.31 -> 1.97 ms); on a uniform cloud of 10 points per voxel the tier has nothing to do and its
+// mere presence cost 0.06 ms of 1.08, so the host picks the kernel from n / V.
+template <typename KeyT, bool MID>
 __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_kernel(
     const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
     const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[nvox] = (uint32_t)n;
-  if (threadIdx.x == 0) sm.n_long = 0;
+  if (threadIdx.x == 0) sm.n_long = sm.n_mid = 0;
   __syncthreads();
 
   // sums about the segment's first point q0 -> (n, mean of p - c, M2) -> voxel row, or the tile's carry slot for s == 0
@@ -293,12 +310,20 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
       carry_cnt[blockIdx.x] = (uint32_t)cnt;
     }
   };
-  // one thread per local segment; segments of >= kLongSeg points (large voxels) are queued for a warp each
+  // one thread per local segment; segments of >= kLongSeg points (large voxels) are queued for a warp each, and segments that are
+  // long for THIS tile — at least kMidSeg points and twice the tile's mean — for a group of 8 lanes: a uniform cloud (10 +- 3 points
+  // per voxel) keeps the balanced one-thread walk, a clustered one (most voxels 1-2 points, the terrain sheet 20-60) does not leave
+  // 31 lanes waiting for the one that walks 40 points.  The threshold depends on the sorted keys only: results stay reproducible.
+  const int mid_thr = max(kMidSeg, 2 * tile_n / (int)(nheads + 1));
   for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
     const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
     if (b <= a) continue;  // only s == 0 can be empty (tile starts with a head)
     if (b - a >= kLongSeg) {
       sm.long_seg[atomicAdd(&sm.n_long, 1u)] = (unsigned short)s;
+      continue;
+    }
+    if (MID && b - a >= mid_thr) {
+      sm.mid_seg[atomicAdd(&sm.n_mid, 1u)] = (unsigned short)s;
       continue;
     }
     long long vx, vy, vz;
@@ -316,6 +341,39 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     emit(s, b - a, q0x, q0y, q0z, sx, sy, sz, xx, xy, xz, yy, yz, zz);
   }
   __syncthreads();
+  // middle segments (clustered clouds: a few voxels of the terrain sheet hold 20-60 points each while most voxels hold one or two —
+  // walked by one thread each, such a voxel kept its whole warp waiting): a group of 8 lanes each, four per warp at a time; lane l of
+  // the group sums points a + 1 + l, a + 1 + l + 8, ..., folded with a fixed xor butterfly inside the group
+  if (MID) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane & 7;
+    const unsigned nm = sm.n_mid;
+    // a warp takes four consecutive segments of the queue at a time (spreading the queue over all warps costs more issue slots than
+    // the shorter tail wins: every warp then runs the butterfly for one or two active groups)
+    for (unsigned i0 = warp * 4; i0 < nm; i0 += (kThreads / 32) * 4) {
+      const unsigned i = i0 + (lane >> 3);
+      const bool act = i < nm;
+      const unsigned s = act ? sm.mid_seg[i] : 0u;
+      const int a = act ? sm.seg_start[s] : 0, b = act ? sm.seg_start[s + 1] : 0;
+      long long vx, vy, vz;
+      unpack_key((unsigned long long)sm.seg_key[s], g, vx, vy, vz);
+      const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
+      const double q0x = sm.x[sw(a)] - cx, q0y = sm.y[sw(a)] - cy, q0z = sm.z[sw(a)] - cz;
+      double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = a + 1 + gl; p < b; p += 8) {
+        const int q = sw(p);
+        const double dx = (sm.x[q] - cx) - q0x, dy = (sm.y[q] - cy) - q0y, dz = (sm.z[q] - cz) - q0z;
+        v[0] += dx; v[1] += dy; v[2] += dz;
+        v[3] = fma(dx, dx, v[3]); v[4] = fma(dx, dy, v[4]); v[5] = fma(dx, dz, v[5]);
+        v[6] = fma(dy, dy, v[6]); v[7] = fma(dy, dz, v[7]); v[8] = fma(dz, dz, v[8]);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      }
+      if (act && gl == 0) emit(s, b - a, q0x, q0y, q0z, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+    }
+  }
   // long segments: lane l sums points a + 1 + l, a + 1 + l + 32, ...; the nine sums are folded with a fixed xor butterfly
   // (every lane ends with the same bits), so the result does not depend on scheduling
   {
@@ -895,19 +953,21 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_
   const int64_t nt = seg_tiles(n);
   cudaStream_t s = as_stream(stream);
   const double4* rec = reinterpret_cast<const double4*>(xyzw);
+  const bool mid = n < (int64_t)VAPC_MID_MEAN * nvoxels_host;  // few points per voxel on average: see reduce_moments_kernel
+#define VAPC_REDUCE(K, MID)                                                                                                                  \
+  do {                                                                                                                                       \
+    const size_t smem = tile_smem_bytes<K>();                                                                                                \
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    VAPC_LAUNCH((reduce_moments_kernel<K, MID>), (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, \
+                w.tile_heads, nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted,         \
+                w.carry_cnt, w.carry);                                                                                                       \
+  } while (0)
   if (grid_host->key_bytes == 4) {
-    typedef uint32_t K;
-    const size_t smem = tile_smem_bytes<K>();
-    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted, w.carry_cnt, w.carry);
+    if (mid) VAPC_REDUCE(uint32_t, true); else VAPC_REDUCE(uint32_t, false);
   } else {
-    typedef unsigned long long K;
-    const size_t smem = tile_smem_bytes<K>();
-    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VAPC_LAUNCH(reduce_moments_kernel<K>, (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, w.tile_heads,
-        nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted, w.carry_cnt, w.carry);
+    if (mid) VAPC_REDUCE(unsigned long long, true); else VAPC_REDUCE(unsigned long long, false);
   }
+#undef VAPC_REDUCE
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.n_long, 0, sizeof(uint32_t), s));
   VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
               nvoxels_host, count, mean3, m2, w.long_chains, w.n_long);

@@ -280,6 +280,7 @@ class VoxelCloud:
         self.m2 = None
         self._point2voxel = None
         self._p2v_event = None  # set while the point->voxel map is still being formed on the side stream
+        self._p2v_hold = None   # (side stream, tensors the lookups there still read)
         self._seg_ws = None
         self.sorted_by = "radix"  # or "cells" (vapc_sort_cells_segmented)
         self._stats_cache: Dict[str, torch.Tensor] = {}
@@ -457,8 +458,12 @@ class VoxelCloud:
                            _ptr(self._point2voxel), _stream())
                     L.call("vapc_point2voxel_set_ctas_per_sm", 16)
                     self._p2v_event = side.record_event()
-                for t in (keys, self.voxel_keys, self._point2voxel):
-                    t.record_stream(side)
+                # The lookups read `keys` and the voxel keys and write the map on the side stream.  They are HELD here until the caller's
+                # stream has waited for the event (the first read of .point2voxel) instead of being handed to the allocator with
+                # record_stream: a block whose release waits for a side-stream event is not back in the pool when the next build asks for
+                # the same size a few microseconds later, and the cudaMalloc that follows stalls that step by 3-4 ms every now and then
+                # (bench step_ms).  Only a cloud that is dropped before anybody read the map falls back to record_stream (__del__).
+                self._p2v_hold = (side, keys)
             else:
                 table = _empty(tbytes, torch.uint8, device)
                 L.call("vapc_point2voxel_dense", _ptr(keys), n, _ptr(self.voxel_keys), V, g.key_bytes, g.total_bits, _ptr(table), tbytes,
@@ -473,12 +478,24 @@ class VoxelCloud:
         if self._p2v_event is not None:
             torch.cuda.current_stream(self._point2voxel.device).wait_event(self._p2v_event)
             self._p2v_event = None
+            self._p2v_hold = None
         return self._point2voxel
 
     @point2voxel.setter
     def point2voxel(self, t):
         self._p2v_event = None
         self._point2voxel = t
+
+    def __del__(self):
+        # dropped while the side stream may still be reading / writing: the allocator must not reuse these blocks before it is done
+        hold = getattr(self, "_p2v_hold", None)
+        if hold is not None and getattr(self, "_p2v_event", None) is not None:
+            try:
+                for t in (hold[1], self.voxel_keys, self._point2voxel):
+                    if t is not None:
+                        t.record_stream(hold[0])
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
 
     @property
     def device(self):
