@@ -417,6 +417,32 @@ def test_plan_exchange_kernel_matches_host_mirror(E):
         assert torch.equal(out.to(torch.int64) & (0xFFFFFFFF if kb == 4 else -1), expect & (0xFFFFFFFF if kb == 4 else -1))
 
 
+def test_global_keys_and_histogram(E):
+    """vapc_global_keys: the sorted local voxel keys re-expressed in a larger (global) key layout — same voxels, same order — and the
+    histogram of their leading bits (few bins: runs of thousands of rows per bin; many bins: several runs per warp round)."""
+    import ctypes as C
+
+    from vapc_b200 import _lib as L
+
+    for kind, n, vs, seed in (("uniform", 300_000, 0.1, 3), ("clustered", 200_000, 0.25, 4), ("uniform", 5_000, 2.0, 5)):
+        x, y, z = make_cloud(kind, n, seed)
+        cloud = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+        lo = [float(np.min(c)) - 37.0 for c in (x, y, z)]
+        hi = [float(np.max(c)) + 91.0 for c in (x, y, z)]
+        g = E.grid_from_bounds(vs, [0, 0, 0], lo + hi)
+        vx, vy, vz = (t.to(torch.int64) for t in cloud.voxel_coords())
+        expect = ((vx - g.vmin[0]) << (g.bits[1] + g.bits[2])) | ((vy - g.vmin[1]) << g.bits[2]) | (vz - g.vmin[2])
+        assert bool((expect[1:] > expect[:-1]).all()), "the global layout keeps the order"
+        for hb in (4, 12, 16):
+            hb = min(hb, g.total_bits)
+            keys = torch.empty(cloud.nvoxels, dtype=torch.int64, device="cuda")
+            hist = torch.empty(1 << hb, dtype=torch.int32, device="cuda")
+            L.call("vapc_global_keys", E._ptr(cloud.voxel_keys), cloud.nvoxels, C.byref(cloud.grid), C.byref(g), hb, E._ptr(keys), E._ptr(hist), E._stream())
+            assert torch.equal(keys, expect), (kind, hb)
+            ref = torch.bincount(expect >> (g.total_bits - hb), minlength=1 << hb)
+            assert torch.equal(hist.to(torch.int64), ref), (kind, hb)
+
+
 def test_reproducible_bitwise(E):
     """No atomics in the reductions: two runs give bit-identical tables — and so does the path that keeps the
     records in input order and sorts all key bits (bucketed=False)."""
