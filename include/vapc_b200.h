@@ -219,6 +219,10 @@ VAPC_API int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_so
                         void* voxel_keys, uint32_t* start, uint32_t* count, uint32_t* first_idx,
                         double* mean3, double* m2, uint32_t* row_sorted, uint32_t* idx_sorted,
                         void* ws, size_t ws_bytes, void* stream);
+/* How a tile's voxels are summed follows the mean number of points per voxel (n / nvoxels_host): below 8 one thread per voxel with
+ * groups of 8 lanes for voxels that are long for their tile, from 32 on four lanes per voxel (and a warp for voxels of 64 points or
+ * more inside a tile, always) — in a fixed order, so results are reproducible run to run.  Test hook: force 1, 2 or 4 lanes per voxel (0: back to the rule). */
+VAPC_API int vapc_reduce_debug_lanes(int32_t lanes);
 /* idx_sorted[p] = original index of the point at sorted position p, read back from its record (vapc_reduce_moments writes the same
  * array when given idx_sorted; callers that only need it for the per-attribute statistics, vapc.py:393-406, form it on demand). */
 VAPC_API int vapc_record_indices(const double* xyzw, const uint32_t* pos_sorted, int64_t n, uint32_t* idx_sorted, void* stream);

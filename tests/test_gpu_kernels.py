@@ -417,6 +417,30 @@ def test_plan_exchange_kernel_matches_host_mirror(E):
         assert torch.equal(out.to(torch.int64) & (0xFFFFFFFF if kb == 4 else -1), expect & (0xFFFFFFFF if kb == 4 else -1))
 
 
+def test_reduce_lanes_per_voxel(E):
+    """vapc_reduce_moments sums a voxel with 1, 2 or 4 lanes (chosen from n / V; forced here): integers identical, moments equal to
+    rounding, and every variant bit-reproducible."""
+    from vapc_b200 import _lib as L
+
+    try:
+        for kind, n, vs, seed in (("uniform", 400_000, 0.5, 21), ("clustered", 300_000, 0.25, 22), ("duplicates", 50_000, 1.0, 23)):
+            x, y, z = make_cloud(kind, n, seed)
+            L.call("vapc_reduce_debug_lanes", 1)
+            ref = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+            for lanes in (2, 4):
+                L.call("vapc_reduce_debug_lanes", lanes)
+                a = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+                b = E.VoxelCloud.build(x, y, z, vs, [0, 0, 0])
+                for name in ("count", "first_idx", "voxel_keys", "start", "point2voxel"):
+                    assert torch.equal(getattr(a, name), getattr(ref, name)), (kind, lanes, name)
+                assert torch.equal(a.mean3, b.mean3) and torch.equal(a.m2, b.m2), (kind, lanes, "reproducible")
+                assert torch.allclose(a.mean3, ref.mean3, rtol=0, atol=1e-13 * vs), (kind, lanes)
+                scale = ref.m2.abs().amax(0, keepdim=True).clamp(min=1e-300)
+                assert bool(((a.m2 - ref.m2).abs() <= 1e-12 * scale + 1e-24).all()), (kind, lanes)
+    finally:
+        L.call("vapc_reduce_debug_lanes", 0)
+
+
 def test_global_keys_and_histogram(E):
     """vapc_global_keys: the sorted local voxel keys re-expressed in a larger (global) key layout — same voxels, same order — and the
     histogram of their leading bits (few bins: runs of thousands of rows per bin; many bins: several runs per warp round)."""

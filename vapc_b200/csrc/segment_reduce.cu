@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) run_lengths_kernel(const KeyT* __res
 // MID: the middle tier is compiled in.  Clouds of few points per voxel on average are the ones where single voxels stand out (measured,
 // 1.25e8 clustered points, 3.2 per voxel: 2.31 -> 1.97 ms); on a uniform cloud of 10 points per voxel the tier has nothing to do and its
 // mere presence cost 0.06 ms of 1.08, so the host picks the kernel from n / V.
-template <typename KeyT, bool MID>
+template <typename KeyT, bool MID, int L>
 __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_kernel(
     const KeyT* __restrict__ keys, const uint32_t* __restrict__ pos_sorted, int64_t n, Grid g, const double4* __restrict__ xyzw,
     const uint32_t* __restrict__ tile_first, int64_t nvox, KeyT* __restrict__ voxel_keys, uint32_t* __restrict__ start,
@@ -315,15 +315,19 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
   // per voxel) keeps the balanced one-thread walk, a clustered one (most voxels 1-2 points, the terrain sheet 20-60) does not leave
   // 31 lanes waiting for the one that walks 40 points.  The threshold depends on the sorted keys only: results stay reproducible.
   const int mid_thr = max(kMidSeg, 2 * tile_n / (int)(nheads + 1));
-  for (unsigned s = threadIdx.x; s <= nheads; s += kThreads) {
+  // L lanes per segment (L = 2, 4: clouds of many points per voxel — a tile of 1024 points then holds fewer segments than the CTA has
+  // threads, and with one thread per segment half of the warps waited at the barrier below while the others walked ~10 points each):
+  // lane l of the group sums points a + 1 + l, a + 1 + l + L, ..., folded by an xor butterfly inside the group (fixed order).
+  for (unsigned s = threadIdx.x / L; s <= nheads; s += kThreads / L) {
+    const int l = threadIdx.x & (L - 1);
     const int a = sm.seg_start[s], b = sm.seg_start[s + 1];
     if (b <= a) continue;  // only s == 0 can be empty (tile starts with a head)
     if (b - a >= kLongSeg) {
-      sm.long_seg[atomicAdd(&sm.n_long, 1u)] = (unsigned short)s;
+      if (l == 0) sm.long_seg[atomicAdd(&sm.n_long, 1u)] = (unsigned short)s;
       continue;
     }
     if (MID && b - a >= mid_thr) {
-      sm.mid_seg[atomicAdd(&sm.n_mid, 1u)] = (unsigned short)s;
+      if (l == 0) sm.mid_seg[atomicAdd(&sm.n_mid, 1u)] = (unsigned short)s;
       continue;
     }
     long long vx, vy, vz;
@@ -331,12 +335,23 @@ __global__ void __launch_bounds__(kThreads, VAPC_REDUCE_MINB) reduce_moments_ker
     const double cx = shift_center(vx, g.ox, g.vs), cy = shift_center(vy, g.oy, g.vs), cz = shift_center(vz, g.oz, g.vs);
     const double q0x = sm.x[sw(a)] - cx, q0y = sm.y[sw(a)] - cy, q0z = sm.z[sw(a)] - cz;
     double sx = 0, sy = 0, sz = 0, xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
-    for (int p = a + 1; p < b; ++p) {
+    for (int p = a + 1 + l; p < b; p += L) {
       const int q = sw(p);
       const double dx = (sm.x[q] - cx) - q0x, dy = (sm.y[q] - cy) - q0y, dz = (sm.z[q] - cz) - q0z;
       sx += dx; sy += dy; sz += dz;
       xx = fma(dx, dx, xx); xy = fma(dx, dy, xy); xz = fma(dx, dz, xz);
       yy = fma(dy, dy, yy); yz = fma(dy, dz, yz); zz = fma(dz, dz, zz);
+    }
+    if (L > 1) {
+      // the lanes of a group share s, a and b: they are here together (other groups of the warp may have left the loop)
+      const unsigned gmask = ((1u << L) - 1u) << ((threadIdx.x & 31) & ~(L - 1));
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(gmask, sx, o); sy += __shfl_xor_sync(gmask, sy, o); sz += __shfl_xor_sync(gmask, sz, o);
+        xx += __shfl_xor_sync(gmask, xx, o); xy += __shfl_xor_sync(gmask, xy, o); xz += __shfl_xor_sync(gmask, xz, o);
+        yy += __shfl_xor_sync(gmask, yy, o); yz += __shfl_xor_sync(gmask, yz, o); zz += __shfl_xor_sync(gmask, zz, o);
+      }
+      if (l != 0) continue;
     }
     emit(s, b - a, q0x, q0y, q0z, sx, sy, sz, xx, xy, xz, yy, yz, zz);
   }
@@ -970,6 +985,12 @@ extern "C" int vapc_count_voxels(const void* keys_sorted, int64_t n, int32_t key
   return VAPC_OK;
 }
 
+static int g_reduce_lanes = 0;  // 0: from n / V; 1, 2, 4: forced (tests, measurements)
+extern "C" int vapc_reduce_debug_lanes(int32_t lanes) {
+  g_reduce_lanes = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : 0;
+  return VAPC_OK;
+}
+
 extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_sorted, int64_t n, const vapc_grid_t* grid_host,
                                    const double* xyzw, int64_t nvoxels_host, void* voxel_keys, uint32_t* start, uint32_t* count,
                                    uint32_t* first_idx, double* mean3, double* m2, uint32_t* row_sorted, uint32_t* idx_sorted,
@@ -986,20 +1007,27 @@ extern "C" int vapc_reduce_moments(const void* keys_sorted, const uint32_t* pos_
   const int64_t nt = seg_tiles(n);
   cudaStream_t s = as_stream(stream);
   const double4* rec = reinterpret_cast<const double4*>(xyzw);
+  // the instantiation follows the mean number of points per voxel (a function of n and V only: results stay reproducible)
   const bool mid = n < (int64_t)VAPC_MID_MEAN * nvoxels_host;  // few points per voxel on average: see reduce_moments_kernel
-#define VAPC_REDUCE(K, MID)                                                                                                                  \
+  // measured at 1e8 points: 10 points per voxel 1.077 / 1.127 / 1.320 ms with 1 / 2 / 4 lanes, 80 points per voxel 1.584 / 1.511 / 1.472 ms
+  const int lanes = g_reduce_lanes > 0 ? g_reduce_lanes : (n >= 32 * nvoxels_host ? 4 : 1);
+#define VAPC_REDUCE(K, MID, L)                                                                                                               \
   do {                                                                                                                                       \
     const size_t smem = tile_smem_bytes<K>();                                                                                                \
-    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute(reduce_moments_kernel<K, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    VAPC_LAUNCH((reduce_moments_kernel<K, MID>), (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g, rec, \
-                w.tile_heads, nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted,         \
+    VAPC_RETURN_IF_CUDA(cudaFuncSetAttribute((reduce_moments_kernel<K, MID, L>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    VAPC_LAUNCH((reduce_moments_kernel<K, MID, L>), (unsigned)nt, kThreads, smem, s, static_cast<const K*>(keys_sorted), pos_sorted, n, g,   \
+                rec, w.tile_heads, nvoxels_host, static_cast<K*>(voxel_keys), start, count, first_idx, mean3, m2, row_sorted, idx_sorted,    \
                 w.carry_cnt, w.carry);                                                                                                       \
   } while (0)
-  if (grid_host->key_bytes == 4) {
-    if (mid) VAPC_REDUCE(uint32_t, true); else VAPC_REDUCE(uint32_t, false);
-  } else {
-    if (mid) VAPC_REDUCE(unsigned long long, true); else VAPC_REDUCE(unsigned long long, false);
-  }
+#define VAPC_REDUCE_K(K)                                  \
+  do {                                                    \
+    if (mid) VAPC_REDUCE(K, true, 1);                     \
+    else if (lanes == 4) VAPC_REDUCE(K, false, 4);        \
+    else if (lanes == 2) VAPC_REDUCE(K, false, 2);        \
+    else VAPC_REDUCE(K, false, 1);                        \
+  } while (0)
+  if (grid_host->key_bytes == 4) VAPC_REDUCE_K(uint32_t); else VAPC_REDUCE_K(unsigned long long);
+#undef VAPC_REDUCE_K
 #undef VAPC_REDUCE
   VAPC_RETURN_IF_CUDA(cudaMemsetAsync(w.n_long, 0, sizeof(uint32_t), s));
   VAPC_LAUNCH(fixup_moments_kernel, (unsigned)((nt + kThreads - 1) / kThreads), kThreads, 0, s, w.tile_heads, w.carry_cnt, w.carry, (int)nt,
