@@ -30,13 +30,14 @@ import torch
 from . import engine as E
 from .utilities import timeit, trace
 
-_STAGING = {}  # device index -> [pinned buffer, pinned buffer]: double-buffered device -> host staging shared by all Vapc objects
+_STAGING = {}  # device index -> pinned buffers: multi-buffered device -> host staging shared by all Vapc objects
 _STAGING_LOCK = threading.Lock()
+_STAGING_BUFFERS = 4  # the landing copies (pinned -> fresh pageable memory, i.e. page faults) run at ~10 GB/s per thread: four in flight
 
 
 def _download_rows(block: np.ndarray, rows, make):
-    """block[i] = make(i) (a float64 device column) for every i in rows.  Device -> pinned staging copies alternate between two
-    buffers while worker threads move the previous column into the (pageable) block: the block is filled at the speed of the host
+    """block[i] = make(i) (a float64 device column) for every i in rows.  Device -> pinned staging copies rotate through a few
+    buffers while worker threads move the previous columns into the (pageable) block: the block is filled at the speed of the host
     memcpy instead of a pageable cudaMemcpy.  The module-wide staging buffers are used under a lock (one download at a time)."""
     if not len(rows):
         return
@@ -45,17 +46,17 @@ def _download_rows(block: np.ndarray, rows, make):
     with _STAGING_LOCK:
         bufs = _STAGING.get(dev)
         if bufs is None or bufs[0].numel() < width:
-            bufs = [torch.empty(max(width, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+            bufs = [torch.empty(max(width, 1), dtype=torch.float64).pin_memory() for _ in range(_STAGING_BUFFERS)]
             _STAGING[dev] = bufs
 
         def land(ev, buf, i):
             ev.synchronize()
             np.copyto(block[i], buf.numpy()[:width])
 
-        with ThreadPoolExecutor(max_workers=2) as pool:
-            pending = [None, None]
+        with ThreadPoolExecutor(max_workers=_STAGING_BUFFERS) as pool:
+            pending = [None] * _STAGING_BUFFERS
             for j, i in enumerate(rows):
-                k = j & 1
+                k = j % _STAGING_BUFFERS
                 if pending[k] is not None:
                     pending[k].result()
                 t = make(i)
@@ -890,10 +891,20 @@ class Vapc:
             c = keep[i]
             return xyz["XYZ".index(c)][rows] if c in ("X", "Y", "Z") else gather(self.new_column_names.get(c, c), final, final_np)
 
-        _download_rows(block, on_device, device_column)
-        for i, c in enumerate(keep):
-            if i not in on_device:
-                block[i] = gather(self.new_column_names.get(c, c), final, final_np)
+        # the columns that live in the host frame (original attributes) are gathered by a host thread while the device columns come down
+        on_host = [i for i in range(len(keep)) if i not in on_device]
+        if on_host:
+            final_np()  # the row list reaches the host on this thread (its stream), the worker only reads it
+
+        def host_columns():
+            for i in on_host:
+                block[i] = gather(self.new_column_names.get(keep[i], keep[i]), final, final_np)
+
+        with ThreadPoolExecutor(max_workers=1) as side:
+            pending = side.submit(host_columns) if on_host else None
+            _download_rows(block, on_device, device_column)
+            if pending is not None:
+                pending.result()
         self.df = pd.DataFrame(block.T, columns=keep, copy=False)
         self.reduced = True
 
