@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kThreads) count_heads_kernel(const KeyT* __res
 #ifndef VAPC_LONG_SEG
 #define VAPC_LONG_SEG 64
 #endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef VAPC_MID_SEG
 #define VAPC_MID_SEG 16
 #endif
@@ -766,7 +767,6 @@ __device__ __forceinline__ int64_t lower_bound_u64(const unsigned long long* __r
   return lo;
 }
 constexpr int kMergeChunks = 4;
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) merge_own_rows_kernel(const unsigned long long* __restrict__ own_keys, const uint32_t* __restrict__ own_count,
                                                                   const double* __restrict__ own_mean3, const double* __restrict__ own_m2,
