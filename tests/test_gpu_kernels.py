@@ -41,6 +41,12 @@ def make_cloud(kind, n, seed):
         noise = rng.uniform(0, 40, (n - n // 2 - n // 4, 3))
         pts = np.round(np.vstack([blob, sheet, noise]), 4)
         pts = pts[rng.permutation(n)]
+    elif kind == "terrain":  # most voxels hold one or two points, the voxels of a thin sheet 20-60: the 8-lane tier of the reduction
+        sheet = np.stack([rng.uniform(0, 30, n // 2), rng.uniform(0, 30, n // 2), np.zeros(n // 2)], axis=1)
+        sheet[:, 2] = 2.0 + 0.2 * np.sin(sheet[:, 0] / 5) + rng.uniform(-0.03, 0.03, n // 2)
+        sparse = rng.uniform([0, 0, 0], [30, 30, 25], (n - n // 2, 3))
+        pts = np.round(np.vstack([sheet, sparse]), 4)
+        pts = pts[rng.permutation(n)]
     elif kind == "utm":  # large coordinates: 64-bit keys when the origin stays at 0
         pts = rng.uniform(0, 25, (n, 3)) + [476850.0, 5429100.0, 312.0]
         pts = np.round(pts, 3)
@@ -236,6 +242,8 @@ def check_cloud(E, x, y, z, vs, origin, eig_faithful=False, bucketed=True):
     ("uniform", 1, 1.0, [0, 0, 0]),
     ("uniform", 3, 1000.0, [0, 0, 0]),
     ("wide", 50000, 0.05, [0, 0, 0]),           # 2 km extent at 5 cm: 40 key bits -> 32-bit low keys inside the buckets
+    ("terrain", 400000, 0.25, [0, 0, 0]),       # < 8 points per voxel on average, sheet voxels of 20-60: groups of 8 lanes per voxel
+    ("uniform", 300000, 0.5, [0, 0, 0]),        # ~41 points per voxel: four lanes per voxel
 ])
 def test_voxel_table_vs_oracle(E, kind, n, vs, origin):
     x, y, z = make_cloud(kind, n, seed=n + int(vs * 100))
