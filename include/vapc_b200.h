@@ -282,6 +282,16 @@ VAPC_API int vapc_point_distance(const double* x, const double* y, const double*
                         const uint32_t* point2voxel, const double* cog3, int64_t nvoxels,
                         double* distance, void* stream);
 
+/* ---- a12, the reference's own numbers: cov_** exactly as vapc.py:947-1006 produces them -----------------------------------
+ * vapc_voxel_stats returns the covariance M2 / (n - 1) from centred moments (accurate to ~1e-13 at any coordinate offset).  The
+ * reference forms (S_ab - S_a S_b / n) / (n - 1) from raw sums, which loses every digit once |coordinate|^2 / variance nears
+ * 1e16 (UTM northings: O(1) errors).  For callers who must DIFF against the reference's output this entry point reproduces its
+ * columns bit for bit, noise included: per-point products rounded to fp64, per-voxel Kahan sums in row order (pandas' groupby
+ * sum), one rounding per operation of the closing formula.  xyzw / pos_sorted / start as vapc_reduce_moments reads and writes
+ * them; cov6 = [6][nvoxels] (xx xy xz yy yz zz), NaN for single-point voxels.  Pinned to the unmodified reference by
+ * tests/golden (assert_array_equal). */
+VAPC_API int vapc_cov_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start,
+                               int64_t nvoxels, double* cov6, void* stream);
 /* ---- broadcast / gather helpers: out[i] = table[index[i]]  (the per-point broadcast of
  * groupby.transform / merge(how="left"), vapc.py:724-726, 843-850, 1087-1089) ------------ */
 VAPC_API int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream);

@@ -182,6 +182,34 @@ def covariance_reference_formula(x, y, z, g: Grouping):
     return out
 
 
+def covariance_reference_bitwise(x, y, z, g: Grouping):
+    """The reference's cov_* columns bit for bit (vapc.py:947-1006): per-point products rounded to fp64 (:950-955), per-voxel
+    sums as pandas' groupby sum forms them (`grouped[...].transform("sum")`, :962-971: Kahan-compensated, rows in frame order),
+    then (S_ab - S_a S_b / n) / (n - 1), one rounding per operation (:977-1006).  [V, 6] in the order xx, xy, xz, yy, yz, zz.
+    Pure-Python loop over the points: small clouds only.  tests/test_oracle_golden.py pins it to the golden columns with
+    assert_array_equal."""
+    c = [np.asarray(a, np.float64) for a in (x, y, z)]
+    cols = c + [c[0] * c[0], c[1] * c[1], c[2] * c[2], c[0] * c[1], c[0] * c[2], c[1] * c[2]]
+    lab = np.asarray(g.point2voxel, np.int64)
+    s = np.zeros((9, g.nvoxels))
+    comp = np.zeros((9, g.nvoxels))
+    for j, col in enumerate(cols):
+        sj, cj = s[j], comp[j]
+        for v, l in zip(col.tolist(), lab.tolist()):
+            y_ = v - cj[l]
+            t = sj[l] + y_
+            cj[l] = (t - sj[l]) - y_
+            if cj[l] != cj[l]:
+                cj[l] = 0.0
+            sj[l] = t
+    n = g.counts.astype(np.float64)
+    out = np.full((g.nvoxels, 6), np.nan)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for k, (a, b, ab) in enumerate(((0, 0, 3), (0, 1, 6), (0, 2, 7), (1, 1, 4), (1, 2, 8), (2, 2, 5))):
+            out[:, k] = np.where(n > 1, (s[ab] - (s[a] * s[b]) / n) / (n - 1), np.nan)
+    return out
+
+
 def covariance_exact(x, y, z, g: Grouping):
     """Two-pass centred covariance in long double (what np.cov computes, vapc.py:1055-1056,
     evaluated in extended precision).  Independent 'truth' for the H1 parity rule."""

@@ -38,6 +38,32 @@ def new(vapc, gold, df=None, **kw):
 
 
 @pytest.mark.parametrize("name", P.cloud_cases())
+def test_covariance_formula_switch_reproduces_reference_columns(vapc, name):
+    """covariance_formula = "reference": the nine cov_** columns of the frame EQUAL the reference's, bit for bit (its raw-moment
+    formula over pandas' Kahan group sums) — for users who diff against the reference; the default stays the exact covariance."""
+    gold = P.load_golden(name)
+    v = new(vapc, gold)
+    assert v.covariance_formula == "exact"
+    v.covariance_formula = "reference"
+    v.compute = ["covariance_matrix", "eigenvalues"]
+    v.compute_requested_attributes()
+    df = v.df
+    for c in ("cov_xx", "cov_xy", "cov_xz", "cov_yx", "cov_yy", "cov_yz", "cov_zx", "cov_zy", "cov_zz"):
+        np.testing.assert_array_equal(df[c].to_numpy(), np.real(np.asarray(gold["pt_" + c])), err_msg=f"{name} {c}")
+    # the eigenvalues do not follow the switch (the reference takes them from np.cov, vapc.py:1055)
+    w = new(vapc, gold)
+    w.compute = ["eigenvalues"]
+    w.compute_requested_attributes()
+    for i in (1, 2, 3):
+        np.testing.assert_array_equal(df[f"Eigenvalue_{i}"].to_numpy(), w.df[f"Eigenvalue_{i}"].to_numpy())
+    bad = new(vapc, gold)
+    bad.covariance_formula = "raw"
+    bad.compute = ["covariance_matrix"]
+    with pytest.raises(ValueError):
+        bad.compute_requested_attributes()
+
+
+@pytest.mark.parametrize("name", P.cloud_cases())
 def test_full_attribute_set_matches_reference(vapc, name):
     gold = P.load_golden(name)
     v = new(vapc, gold)

@@ -425,6 +425,25 @@ def test_plan_exchange_kernel_matches_host_mirror(E):
         assert torch.equal(out.to(torch.int64) & (0xFFFFFFFF if kb == 4 else -1), expect & (0xFFFFFFFF if kb == 4 else -1))
 
 
+@pytest.mark.parametrize("name", ["utm_offset_vs0.25", "uniform5000_vs0.25", "plane500_vs1.0", "vapc_in_every50th_vs0.25", "shifted_origin_vs0.3"])
+def test_cov_reference_formula_bit_for_bit(E, name):
+    """vapc_cov_reference_formula == the cov_** columns of the unmodified reference, bit for bit (UTM-sized coordinates included,
+    where those columns are mostly rounding noise) — and == the oracle's Kahan restatement on a larger seeded cloud."""
+    gold = P.load_golden(name)
+    x, y, z = (np.asarray(gold[k], np.float64) for k in ("in_X", "in_Y", "in_Z"))
+    vs, origin = float(gold["in_voxel_size"]), np.asarray(gold["in_origin"], float).tolist()
+    for bucketed in (True, False):
+        cloud = E.VoxelCloud.build(x, y, z, vs, origin, bucketed=bucketed)
+        got = _np(cloud.covariance_reference_formula())[:, _u32(cloud.point2voxel)]
+        for k, c in enumerate(("cov_xx", "cov_xy", "cov_xz", "cov_yy", "cov_yz", "cov_zz")):
+            np.testing.assert_array_equal(got[k], np.real(np.asarray(gold["pt_" + c])), err_msg=f"{name} {c} bucketed={bucketed}")
+    if name == "utm_offset_vs0.25":
+        xs, ys, zs = make_cloud("utm", 30000, 77)
+        cloud = E.VoxelCloud.build(xs, ys, zs, 0.5, [0, 0, 0])
+        g = O.group_by_voxel(*O.voxelize(xs, ys, zs, [0, 0, 0], 0.5))
+        np.testing.assert_array_equal(_np(cloud.covariance_reference_formula()).T, O.covariance_reference_bitwise(xs, ys, zs, g))
+
+
 def test_reduce_lanes_per_voxel(E):
     """vapc_reduce_moments sums a voxel with 1, 2 or 4 lanes (chosen from n / V; forced here): integers identical, moments equal to
     rounding, and every variant bit-reproducible."""

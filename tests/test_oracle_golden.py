@@ -58,6 +58,9 @@ def test_float_columns(name):
     ssq = (O._group_sum(x * x, g) + O._group_sum(y * y, g) + O._group_sum(z * z, g)) / g.counts
     P.assert_cov_h1(O.covariance_reference_formula(x, y, z, g), ref6, g.counts, ssq, what="cov_ref")
     P.assert_cov_h1(O.covariance_exact(x, y, z, g), ref6, g.counts, ssq, what="cov_exact")
+    # ... and the restatement of pandas' Kahan group sums reproduces the reference's columns BIT FOR BIT, noise included
+    if len(x) <= 60000:
+        np.testing.assert_array_equal(O.covariance_reference_bitwise(x, y, z, g), ref6, err_msg="cov_** of the reference, bit for bit")
     for a, b in (("cov_xy", "cov_yx"), ("cov_xz", "cov_zx"), ("cov_yz", "cov_zy")):
         np.testing.assert_array_equal(gold["pt_" + a], gold["pt_" + b])
     # eigenvalues + features

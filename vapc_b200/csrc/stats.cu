@@ -85,6 +85,58 @@ extern "C" int vapc_voxel_stats(const void* voxel_keys, const uint32_t* count, c
   return vapc_voxel_stats_axes(voxel_keys, count, mean3, m2, nvoxels, grid_host, nullptr, density, cog3, std3, cov6, eig3, eign3, feat8, stream);
 }
 
+namespace {
+// The reference's OWN covariance columns, rounding for rounding (vapc.py:947-1006): products X*X, X*Y, ... rounded to fp64 per point,
+// per-voxel sums the way pandas' groupby sum forms them — Kahan-compensated, rows in frame order (inside a voxel the sorted
+// positions ARE in original row order: the sort is stable) — then (S_ab - S_a S_b / n) / (n - 1) with one rounding per operation.
+// One thread per voxel: the recurrence is sequential by definition.  No FMA anywhere.
+struct Kahan {
+  double s = 0.0, c = 0.0;
+  __device__ __forceinline__ void add(double v) {
+    const double y = __dsub_rn(v, c);
+    const double t = __dadd_rn(s, y);
+    c = __dsub_rn(__dsub_rn(t, s), y);
+    if (c != c) c = 0.0;  // pandas resets a NaN compensation (infinite sums)
+    s = t;
+  }
+};
+__global__ void __launch_bounds__(kThreads) cov_reference_kernel(const double4* __restrict__ xyzw, const uint32_t* __restrict__ pos_sorted,
+                                                                 const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ cov6) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const uint32_t a = start[v], b = start[v + 1];
+  Kahan sx, sy, sz, sxx, syy, szz, sxy, sxz, syz;
+  for (uint32_t p = a; p < b; ++p) {
+    const double4 r = ld_record(xyzw + pos_sorted[p]);
+    sx.add(r.x); sy.add(r.y); sz.add(r.z);
+    sxx.add(__dmul_rn(r.x, r.x)); syy.add(__dmul_rn(r.y, r.y)); szz.add(__dmul_rn(r.z, r.z));
+    sxy.add(__dmul_rn(r.x, r.y)); sxz.add(__dmul_rn(r.x, r.z)); syz.add(__dmul_rn(r.y, r.z));
+  }
+  const double n = (double)(b - a), n1 = (double)((long long)(b - a) - 1);
+  auto cov = [&](double sab, double sa, double sb) {
+    return b - a > 1 ? __ddiv_rn(__dsub_rn(sab, __ddiv_rn(__dmul_rn(sa, sb), n)), n1) : __longlong_as_double(0x7ff8000000000000LL);
+  };
+  cov6[0 * nvox + v] = cov(sxx.s, sx.s, sx.s);
+  cov6[1 * nvox + v] = cov(sxy.s, sx.s, sy.s);
+  cov6[2 * nvox + v] = cov(sxz.s, sx.s, sz.s);
+  cov6[3 * nvox + v] = cov(syy.s, sy.s, sy.s);
+  cov6[4 * nvox + v] = cov(syz.s, sy.s, sz.s);
+  cov6[5 * nvox + v] = cov(szz.s, sz.s, sz.s);
+}
+}  // namespace
+
+extern "C" int vapc_cov_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start, int64_t nvoxels, double* cov6,
+                                          void* stream) {
+  if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_cov_reference_formula: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  if (!xyzw || !pos_sorted || !start || !cov6) return vapc_set_error(VAPC_E_INVALID, "vapc_cov_reference_formula: null buffer");
+  if (reinterpret_cast<uintptr_t>(xyzw) & 31u) return vapc_set_error(VAPC_E_INVALID, "vapc_cov_reference_formula: xyzw must be 32-byte aligned");
+  VAPC_LAUNCH(cov_reference_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream),
+              reinterpret_cast<const double4*>(xyzw), pos_sorted, start, nvoxels, cov6);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
+
 extern "C" int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream) {
   if (n < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_gather_f64: n < 0");
   if (n == 0) return VAPC_OK;

@@ -510,6 +510,15 @@ class VoxelCloud:
             L.call("vapc_record_indices", _ptr(self.xyzw), _ptr(self.pos_sorted), self.n, _ptr(self._idx_sorted), _stream())
         return self._idx_sorted
 
+    def covariance_reference_formula(self) -> torch.Tensor:
+        """[6, V] covariance (xx xy xz yy yz zz) exactly as the reference's compute_covariance_matrix produces it (vapc.py:947-1006):
+        raw-moment formula over pandas' Kahan group sums, bit for bit — including its loss of digits at large coordinates.  For
+        diffing against the reference; `stats(cov=True)` is the accurate one."""
+        V = self.nvoxels
+        out = torch.empty((6, V), dtype=torch.float64, device=self.device)
+        L.call("vapc_cov_reference_formula", _ptr(self.xyzw), _ptr(self.pos_sorted), _ptr(self.start), V, _ptr(out), _stream())
+        return out
+
     # ------------------------------------------------------------------------------------
     def stats(self, density=False, cog=False, std=False, cov=False, eig=False, eig_n=False, feat=False) -> VoxelStats:
         """One launch of vapc_voxel_stats for whatever is not cached yet."""

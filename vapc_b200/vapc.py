@@ -109,6 +109,10 @@ class Vapc:
         if not isinstance(self.origin, list) or len(self.origin) != 3:
             raise ValueError("origin must be a list of three coordinates [x, y, z].")
         self.AVAILABLE_COMPUTATIONS = list(Vapc.AVAILABLE_COMPUTATIONS)
+        # not in the reference: which numbers the cov_* columns carry.  "exact" = M2 / (n - 1) from centred moments (~1e-13 of the true
+        # covariance at any coordinate offset); "reference" = the reference's raw-moment columns bit for bit (vapc.py:947-1006), which
+        # lose all digits at UTM-sized coordinates.  Eigenvalues and features never depend on it (the reference takes them from np.cov).
+        self.covariance_formula = "exact"
         self._df = None      # the host frame: original columns + whatever has been materialised
         self._lazy = {}      # column name -> (kind, device tensor, cloud); kind "voxel": [V] column to broadcast, "point": [N] column
         self._cols = None    # logical column order (frame columns + pending ones), None = the frame's own
@@ -745,7 +749,14 @@ class Vapc:
         if not self.voxelized:
             self._voxelize()
         cloud = self._get_cloud()
-        cov = cloud.stats(cov=True).cov
+        if self.covariance_formula == "reference":
+            # the reference's own columns, rounding for rounding (raw-moment formula over Kahan sums in row order): for diffing
+            # against its output; ill-conditioned at large coordinates (its errors are reproduced, not corrected)
+            cov = cloud.covariance_reference_formula()
+        elif self.covariance_formula == "exact":
+            cov = cloud.stats(cov=True).cov
+        else:
+            raise ValueError("covariance_formula must be 'exact' or 'reference'")
         for name, k in zip(_COV_NAMES, _COV9_FROM6):
             self._add_lazy(name, "voxel", cov[k], cloud)
         self._cols = _COV_NAMES + [c for c in self._cols if c not in _COV_NAMES]  # the reference moves them to the front
