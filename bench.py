@@ -328,6 +328,10 @@ def kernel_algorithmic_bytes(kernel, n, v, key_bytes, low_passes):
         ("p2v_lookup_kernel", (k + 4) * n, 1),
         ("p2v_fill_kernel", (k + 4) * v, 1),
         ("voxel_stats_kernel", (k + 4 + 72) * v + (8 + 24 + 24 + 48 + 24 + 24 + 64) * v, 1),
+        # N > 1, the owner's merge fused with the statistics: the own rows in (64-bit global key, count, 9 moments), key + count + the
+        # 27 statistic columns out (v = this rank's local voxels; all but ~1 % of them are rows it keeps)
+        ("merge_own_rows_kernel", (8 + 4 + 72) * v + (k + 4 + 8 + 24 + 24 + 48 + 24 + 24 + 64) * v, 1),
+        ("global_keys_kernel", (k + 8) * v, 1),
     ]
     for key, b, launches in table:
         if key in kernel:
