@@ -58,14 +58,18 @@ struct RankSmem {
   unsigned tile;
 };
 
+// Zeroes the running counters and the mask words with 128-bit stores: 8 instructions per thread instead of 32 (the word-wise version
+// showed up as MIO-queue throttle — 5.6 % of the scatter kernel's stall samples, as many store instructions as its whole ranking).
+// Both arrays start 16-byte aligned (warp_cnt leads RankSmem, the masks lead the aligned union of the kernels' shared structs).
 __device__ __forceinline__ void rank_init(RankSmem& sm, MaskBuffers& masks) {
   const int tid = threadIdx.x;
+  uint4* wc4 = reinterpret_cast<uint4*>(&sm.warp_cnt[0][0]);
+  uint4* mk4 = reinterpret_cast<uint4*>(&masks[0][0][0]);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) sm.warp_cnt[w][tid] = 0;
+  for (int i = 0; i < kWarps * kRadix / 4 / kThreads; ++i) wc4[i * kThreads + tid] = zero;
 #pragma unroll
-  for (int b = 0; b < 3; ++b)
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) masks[b][w][tid] = 0;
+  for (int i = 0; i < 3 * kWarps * kRadix / 4 / kThreads; ++i) mk4[i * kThreads + tid] = zero;
 }
 
 // Stable rank of ITEMS keys per lane inside the warp; digit(k) is the digit of the lane's k-th key and step k
