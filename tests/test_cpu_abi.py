@@ -228,3 +228,51 @@ def test_histogram_mode_restatement_matches_reference():
             ref_mode(bad)
         with pytest.raises(ValueError):
             ours(bad)
+
+
+def test_segmented_histogram_modes_equal_numpy_bit_for_bit():
+    """engine.segmented_histogram_modes (the batch form of the `mode` fallback, tensor ops only: the same code runs on the GPU)
+    against the per-sample numpy function — and through it the reference's (test above) — on samples of every kind the statistic
+    meets: rounded scan angles, small integers with ties between bins, wide dynamic range, values at UTM magnitude; batches holding a
+    sample the reference raises for are refused as a whole (the caller then takes the per-sample route and raises like numpy)."""
+    import torch
+
+    from vapc_b200 import engine as E
+    from vapc_b200.utilities import compute_mode_continuous
+
+    rng = np.random.default_rng(3)
+    compared = 0
+    for _ in range(12):
+        samples = []
+        for _s in range(int(rng.integers(1, 300))):
+            n = int(rng.integers(2, 200)) if rng.random() < 0.9 else int(rng.integers(200, 3000))
+            kind = rng.integers(0, 5)
+            if kind == 0:
+                v = np.round(rng.normal(-5, 4, n), 1)
+            elif kind == 1:
+                v = rng.integers(-30, 30, n).astype(np.float64)
+            elif kind == 2:
+                v = rng.normal(0, 1, n) * 10.0 ** rng.integers(-6, 6)
+            elif kind == 3:
+                v = np.round(rng.uniform(-90, 90, n))
+            else:
+                v = rng.integers(-3, 3, n) * 0.1 + 476850.0
+            samples.append(v)
+        ref, fine = [], []
+        for v in samples:
+            try:
+                with np.errstate(all="ignore"):
+                    ref.append(compute_mode_continuous(v))
+                fine.append(v)
+            except (ValueError, OverflowError):
+                pass
+        if fine:
+            got = E.segmented_histogram_modes(torch.from_numpy(np.concatenate(fine)), torch.tensor([len(v) for v in fine]))
+            np.testing.assert_array_equal(got.numpy(), np.array(ref))
+            compared += len(ref)
+        if len(fine) != len(samples):
+            assert E.segmented_histogram_modes(torch.from_numpy(np.concatenate(samples)), torch.tensor([len(v) for v in samples])) is None
+    assert compared > 1000
+    assert E.segmented_histogram_modes(torch.zeros(0, dtype=torch.float64), torch.zeros(0, dtype=torch.int64)).numel() == 0
+    assert E.segmented_histogram_modes(torch.tensor([-1.0, float("nan"), 3.0], dtype=torch.float64), torch.tensor([3])) is None
+    assert E.segmented_histogram_modes(torch.tensor([-2.0, -2.0, -2.0, 1.0, 5.0], dtype=torch.float64), torch.tensor([3, 2])) is None

@@ -293,6 +293,14 @@ def test_mode_falls_back_to_histogram_mode_per_voxel(E):
             assert got[v] == np.argmax(np.bincount(vals.astype(int)))
     with pytest.raises(ValueError):
         cloud.mode_count(attr, [0.1])  # mode_count has no fallback in the reference (vapc.py:423-428)
+    # a flagged voxel whose histogram the reference cannot build (all values equal: zero bin width) raises what numpy raises there
+    v0 = g.order[g.starts[0]:g.starts[0] + g.counts[0]]
+    flat = attr.copy()
+    flat[v0] = -2.0
+    with pytest.raises(ValueError):
+        compute_mode_continuous(flat[v0])
+    with pytest.raises(ValueError):
+        cloud.mode_count(flat, [], want_mode=True)
 
 
 def test_attribute_statistics_vs_oracle(E):

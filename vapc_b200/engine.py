@@ -626,16 +626,25 @@ class VoxelCloud:
             if p is not None:
                 counts[p] = mc
         if flagged_rows is not None and mode is not None:
-            # the reference's per-voxel fallback, on the host, for the flagged voxels only (their points come out of the sorted order)
-            from .utilities import compute_mode_continuous
-
+            # the reference's per-voxel fallback for the flagged voxels only: their points come out of the sorted order in one
+            # gather, all histogram modes in one batch of tensor ops (segmented_histogram_modes)
             mode = mode.to(torch.float64)  # a column holding histogram modes is a float column
-            start = _u32_t(self.start).cpu().numpy()
-            idx = _u32_t(self.idx_sorted)
-            vals = []
-            for r in flagged_rows.cpu().tolist():
-                vals.append(compute_mode_continuous(a_all[idx[start[r]:start[r + 1]]].cpu().numpy()))
-            mode[flagged_rows] = torch.tensor(vals, dtype=torch.float64, device=dev)
+            start = _u32_t(self.start)
+            lens = start[flagged_rows + 1] - start[flagged_rows]
+            seg = torch.repeat_interleave(torch.arange(flagged_rows.numel(), device=dev), lens)
+            within = torch.arange(int(lens.sum().item()), device=dev) - (torch.cumsum(lens, 0) - lens)[seg]
+            vals = a_all[_u32_t(self.idx_sorted)[start[flagged_rows][seg] + within]]
+            modes = segmented_histogram_modes(vals, lens)
+            if modes is None:
+                # a voxel the reference's histogram raises for (one value, zero inter-quartile range, NaN), or bins beyond the
+                # batch's memory bound: voxel by voxel on the host, in row order like the groupby, raising what numpy raises
+                from .utilities import compute_mode_continuous
+
+                host = vals.cpu().numpy()
+                cuts = np.concatenate([[0], np.cumsum(lens.cpu().numpy())])
+                modes = torch.tensor([compute_mode_continuous(host[cuts[i]:cuts[i + 1]]) for i in range(len(cuts) - 1)],
+                                     dtype=torch.float64, device=dev)
+            mode[flagged_rows] = modes
         return mode, counts
 
     def percentage_occupied(self) -> float:
@@ -643,6 +652,86 @@ class VoxelCloud:
         vx, vy, vz = self.voxel_coords()
         ext = [int(v.max().item()) - int(v.min().item()) + 1 for v in (vx, vy, vz)]
         return round(self.nvoxels / (ext[0] * ext[1] * ext[2]) * 100, 2)
+
+
+def segmented_histogram_modes(values: torch.Tensor, lengths: torch.Tensor, max_bins: int = 1 << 27) -> Optional[torch.Tensor]:
+    """compute_mode_continuous (the reference's utilities.py:114-159) of many samples at once: `values` holds the samples back to
+    back, `lengths` [S] their sizes; returns the S modes (fp64), or None when the batch cannot take this route (a non-finite value,
+    a degenerate bin width — the reference raises there, and the caller's per-sample route raises the same error —, or more than
+    `max_bins` bins in total).  Every step restates numpy's own arithmetic operation by operation in IEEE fp64 tensor ops, so the
+    result equals np.percentile / np.histogram / np.linspace bit for bit: the samples sorted inside their segments (two stable sorts),
+    the quartiles by numpy's `linear` rule (virtual index (n - 1) q, _lerp with its t >= 0.5 branch), bins = ceil(range / (2 iqr /
+    n ** (1/3))) — n ** (1/3) through Python's pow on the host, once per distinct n: the device's pow may differ in the last bit —,
+    edges = arange * (range / bins) + min with the last edge set to max, numpy's bin index with its one-ULP corrections, density =
+    counts / diff(edges) / n, first maximum, centre of that bin."""
+    dev = values.device
+    S = lengths.numel()
+    if S == 0:
+        return torch.empty(0, dtype=torch.float64, device=dev)
+    if not bool(torch.isfinite(values).all()):
+        return None
+    lengths = lengths.to(torch.int64)
+    off = torch.cumsum(lengths, 0) - lengths
+    seg = torch.repeat_interleave(torch.arange(S, device=dev), lengths)
+    # samples in ascending order inside their segments
+    o1 = torch.sort(values, stable=True).indices
+    o2 = torch.sort(seg[o1], stable=True).indices
+    sv = values[o1[o2]]
+    last = off + lengths - 1
+    vmin, vmax = sv[off], sv[last]
+    nf = lengths.to(torch.float64)
+
+    def quartile(q):
+        virt = (nf - 1.0) * q
+        prev = torch.floor(virt)
+        above = virt >= nf - 1.0
+        pi = torch.where(above, lengths - 1, prev.to(torch.int64))
+        ni = torch.where(above, lengths - 1, prev.to(torch.int64) + 1)
+        t = virt - torch.where(above, torch.full_like(prev, -1.0), prev)
+        a, b = sv[off + pi], sv[off + ni]
+        d = b - a
+        return torch.where(t >= 0.5, b - d * (1.0 - t), a + d * t)
+
+    iqr = quartile(0.75) - quartile(0.25)
+    uniq, inv = torch.unique(lengths, return_inverse=True)
+    cbrt = torch.tensor([int(c) ** (1 / 3) for c in uniq.cpu().tolist()], dtype=torch.float64).to(dev)[inv]
+    ratio = (vmax - vmin) / (2.0 * iqr / cbrt)
+    if not bool(torch.isfinite(ratio).all()):
+        return None
+    bins = torch.ceil(ratio).to(torch.int64)
+    if bool((bins < 1).any()) or int(bins.sum().item()) + S > max_bins:
+        return None
+    # bin edges of every segment back to back (bins + 1 each): np.linspace(min, max, bins + 1)
+    ne = bins + 1
+    eoff = torch.cumsum(ne, 0) - ne
+    eseg = torch.repeat_interleave(torch.arange(S, device=dev), ne)
+    j = (torch.arange(int(ne.sum().item()), device=dev) - eoff[eseg]).to(torch.float64)
+    delta = vmax - vmin
+    binsf = bins.to(torch.float64)
+    step = delta / binsf
+    edges = torch.where(step[eseg] == 0, j / binsf[eseg] * delta[eseg], j * step[eseg]) + vmin[eseg]
+    edges[eoff + bins] = vmax
+    # numpy's index of every sample: trunc((v - first) / (last - first) * bins), then the corrections around the edges
+    segs = seg  # the sorted samples keep the segment layout
+    f = (sv - vmin[segs]) / delta[segs] * binsf[segs]
+    idx = f.to(torch.int64)
+    nb = bins[segs]
+    idx = torch.where(idx == nb, idx - 1, idx)
+    eo = eoff[segs]
+    idx = torch.where(sv < edges[eo + idx], idx - 1, idx)
+    idx = torch.where((sv >= edges[eo + idx + 1]) & (idx != nb - 1), idx + 1, idx)
+    boff = eoff - torch.arange(S, device=dev)  # first bin of each segment among all bins
+    nbins_total = int(bins.sum().item())
+    counts = torch.bincount(boff[segs] + idx, minlength=nbins_total)
+    bseg = torch.repeat_interleave(torch.arange(S, device=dev), bins)
+    bj = torch.arange(nbins_total, device=dev) - boff[bseg]
+    lo, hi = edges[eoff[bseg] + bj], edges[eoff[bseg] + bj + 1]
+    dens = counts.to(torch.float64) / (hi - lo) / nf[bseg]
+    best = torch.full((S,), float("-inf"), dtype=torch.float64, device=dev).scatter_reduce(0, bseg, dens, "amax", include_self=True)
+    first = torch.full((S,), nbins_total, dtype=torch.int64, device=dev).scatter_reduce(
+        0, bseg, torch.where(dens == best[bseg], bj, torch.full_like(bj, nbins_total)), "amin", include_self=True)
+    k = eoff + first
+    return (edges[k] + edges[k + 1]) / 2.0
 
 
 def run_lengths(keys_sorted: torch.Tensor, weights: Optional[torch.Tensor] = None):
