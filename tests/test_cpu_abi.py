@@ -276,3 +276,33 @@ def test_segmented_histogram_modes_equal_numpy_bit_for_bit():
     assert E.segmented_histogram_modes(torch.zeros(0, dtype=torch.float64), torch.zeros(0, dtype=torch.int64)).numel() == 0
     assert E.segmented_histogram_modes(torch.tensor([-1.0, float("nan"), 3.0], dtype=torch.float64), torch.tensor([3])) is None
     assert E.segmented_histogram_modes(torch.tensor([-2.0, -2.0, -2.0, 1.0, 5.0], dtype=torch.float64), torch.tensor([3, 2])) is None
+
+
+def test_cloud_signature_sees_column_edits():
+    """Vapc._signature (what the cached device cloud is compared with): same frame -> same signature; a shifted, replaced or
+    re-assigned coordinate column, another voxel size or origin -> another one (host logic only, no GPU needed)."""
+    import pandas as pd
+
+    import vapc_b200 as vapc
+
+    rng = np.random.default_rng(5)
+    df = pd.DataFrame({"X": rng.uniform(0, 9, 5000), "Y": rng.uniform(0, 9, 5000), "Z": rng.uniform(0, 3, 5000), "intensity": 1.0})
+    v = vapc.Vapc(0.5)
+    v.df = df
+    s0 = v._signature()
+    assert v._signature() == s0
+    df["intensity"] = 2.0
+    assert v._signature() == s0  # not a coordinate
+    df["Y"] = df["Y"].to_numpy() * 2.0
+    s1 = v._signature()
+    assert s1 != s0
+    df.loc[:, "Z"] = df["Z"].to_numpy() + 1.0
+    assert v._signature() != s1
+    v.voxel_size = 0.25
+    s2 = v._signature()
+    v.origin = [1.0, 0.0, 0.0]
+    assert len({s0, s1, s2, v._signature()}) == 4
+    e = vapc.Vapc(0.5)
+    e.df = df.iloc[:0]
+    assert e._signature() == e._signature()
+    e.invalidate()  # nothing computed yet: a no-op

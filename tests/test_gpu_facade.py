@@ -393,6 +393,41 @@ def test_seeded_plane_known_answers(vapc):
             mock.assert_called_once()
 
 
+def test_edit_through_the_callers_own_reference(vapc):
+    """The caller assigns a frame, keeps the reference, and edits it in place WITHOUT reading `.df`: a shifted column changes the
+    fingerprint of X / Y / Z that `_get_cloud` compares, a single-cell edit is announced with `invalidate()`."""
+    gold = P.load_golden("uniform5000_vs0.25")
+    vs = float(gold["in_voxel_size"])
+    origin = gold["in_origin"].tolist()
+
+    def expected_counts(frame):
+        vox = np.floor((frame[["X", "Y", "Z"]].to_numpy() - np.asarray(origin)) / vs).astype(np.int64)
+        _, inv, cnt = np.unique(vox, axis=0, return_inverse=True, return_counts=True)
+        return cnt[inv.ravel()]
+
+    mine = input_frame(gold).copy()
+    v = vapc.Vapc(vs, origin=origin)
+    v.df = mine
+    v.compute_point_count()
+    assert v._lazy and not v._exposed  # computed, never handed out
+    mine["X"] = mine["X"].to_numpy() + 3.0 * vs * (np.arange(len(mine)) % 3)
+    v.point_count = v.voxelized = False
+    v.compute_point_count()
+    np.testing.assert_array_equal(v.df["point_count"].to_numpy(), expected_counts(mine))
+    # one cell, between two sampled rows of the fingerprint
+    w = vapc.Vapc(vs, origin=origin)
+    mine2 = input_frame(gold).copy()
+    w.df = mine2
+    w.compute_point_count()
+    mine2.loc[mine2.index[1], "Z"] = mine2["Z"].iloc[1] + 1000.0
+    w.invalidate()
+    w.point_count = w.voxelized = False
+    w.compute_point_count()
+    got = w.df["point_count"].to_numpy()
+    np.testing.assert_array_equal(got, expected_counts(mine2))
+    assert got[1] == 1
+
+
 # ---- lazily materialised frames, label_by_mask, the change-area flow ------------------------------------------------------------------
 def test_lazy_and_materialised_paths_agree(vapc):
     """Computed columns stay on the device until `.df` is read.  The frame built then, and the reduced frame built from the V-row

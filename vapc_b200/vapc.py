@@ -274,7 +274,23 @@ class Vapc:
     # device cloud cache
     # ------------------------------------------------------------------------------------
     def _signature(self):
-        return (id(self._df), len(self._df), float(self.voxel_size), tuple(float(o) for o in self.origin))
+        """What the device cloud was built from: the frame object, its length, voxel size, origin, and a fingerprint of X / Y / Z at
+        up to 1024 evenly spaced rows per axis (a few microseconds: it catches a column that was shifted, scaled or replaced through a
+        reference the caller kept to the frame they assigned).  An edit of single cells through such a reference is not seen — the
+        frame read from `.df` always is (`_exposed`) —: `invalidate()` states it explicitly."""
+        df = self._df
+        n = len(df)
+        rows = np.linspace(0, n - 1, min(n, 1024)).astype(np.int64) if n else None
+        probe = tuple(hash(df[c].to_numpy()[rows].tobytes()) if n and c in df.columns else None for c in ("X", "Y", "Z"))
+        return (id(df), n, float(self.voxel_size), tuple(float(o) for o in self.origin), probe)
+
+    def invalidate(self):
+        """Forget the device copy of the cloud: call after editing, in place, a frame this object already computed on through a
+        reference of your own (pending columns are written into the frame first; the next compute_* re-reads X, Y, Z)."""
+        if self._df is not None:
+            self._materialise()
+        self._drop_device_state()
+        self._exposed = True
 
     def _get_cloud(self) -> E.VoxelCloud:
         """The device-side voxelisation of the frame's X, Y, Z columns.  Rebuilt when the frame was handed out since the last
