@@ -116,6 +116,29 @@ def test_nearest_neighbours_equal_kdtree_at_scale(n, nq, h):
     np.testing.assert_array_equal(d.cpu().numpy(), rd)
 
 
+def test_module_level_helpers_of_bi_vapc():
+    """bi_vapc.mutual_nearest_neighbors / merge_with_suffix / compute_euclidean_distance (bi_vapc.py:171-207), which notebooks import
+    by name: pairs equal the reference's KD-tree statement, the distance is the reference's formula within one rounding."""
+    from vapc_b200 import bi_vapc as B
+
+    rng = np.random.default_rng(77)
+    a = rng.random((4000, 3)) * [30.0, 20.0, 3.0]
+    b = a[rng.permutation(4000)[:3500]] + rng.normal(0, 0.05, (3500, 3))
+    df1 = pd.DataFrame(a, columns=["cog_x", "cog_y", "cog_z"])
+    df2 = pd.DataFrame(b, columns=["cog_x", "cog_y", "cog_z"])
+    i1, i2 = B.mutual_nearest_neighbors(df1, df2)
+    r1, r2, rd = O.mutual_nearest_neighbors(a, b)
+    np.testing.assert_array_equal(i1, r1)
+    np.testing.assert_array_equal(i2, r2)
+    merged = B.merge_with_suffix(df1.iloc[i1].reset_index(drop=True), df2.iloc[i2].reset_index(drop=True))
+    assert merged.columns.tolist() == ["cog_x_x", "cog_y_x", "cog_z_x", "cog_x_y", "cog_y_y", "cog_z_y"]
+    dist = B.compute_euclidean_distance(merged)
+    assert isinstance(dist, pd.Series) and dist.index.equals(merged.index)
+    P.assert_close_rel(dist.to_numpy(), rd, rtol=1e-13, atol=0, what="distance")
+    with pytest.raises(ValueError):
+        B.mutual_nearest_neighbors(df1, df2, coord_cols=["cog_x", "cog_y"])
+
+
 @pytest.mark.parametrize("kind,n,d", [("grid", 300_000, 1.0), ("grid", 300_000, 1.8), ("float", 200_000, 0.12), ("dups", 100_000, 0.0)])
 def test_clusters_equal_components_at_scale(kind, n, d):
     """Against the closed form of the reference's sweep (oracle cluster_components, pinned to the reference by

@@ -174,3 +174,41 @@ class BiTemporalVapc:
         dh = DataHandler("")
         dh.df = self.df
         dh.save_as_las(output_file)
+
+
+# ---- the reference's module-level helpers (bi_vapc.py:171-207), for callers that import them ------------------------------------
+@trace
+@timeit
+def mutual_nearest_neighbors(df1, df2, coord_cols=["cog_x", "cog_y", "cog_z"]):
+    """Row numbers (idx1, idx2) of the MUTUAL nearest neighbours of two frames (bi_vapc.py:173-186): the reference's two KD-tree
+    queries as exact grid searches on the GPU (engine.mutual_nearest_neighbors -> vapc_cell_nn).  Three coordinate columns."""
+    if len(coord_cols) != 3:
+        raise ValueError("mutual_nearest_neighbors searches 3-D coordinates: give three columns")
+    sets = [[np.ascontiguousarray(d[c].to_numpy(np.float64)) for c in coord_cols] for d in (df1, df2)]
+    idx1, idx2, _ = E.mutual_nearest_neighbors(sets[0], sets[1])
+    return idx1.cpu().numpy(), idx2.cpu().numpy()
+
+
+@trace
+@timeit
+def merge_with_suffix(df1, df2, suffix1="_x", suffix2="_y"):
+    """Two frames side by side, columns suffixed (bi_vapc.py:190-194): frame bookkeeping, nothing to compute."""
+    return pd.concat([df1.add_suffix(suffix1), df2.add_suffix(suffix2)], axis=1)
+
+
+@trace
+@timeit
+def compute_euclidean_distance(df, coord_prefix="cog"):
+    """sqrt(dx^2 + dy^2 + dz^2) between the `<prefix>_?_x` and `<prefix>_?_y` columns of a merged frame (bi_vapc.py:198-207), by the
+    same kernel as BiTemporalVapc.compute_distance (vapc_mahalanobis' distance output, explicit round-to-nearest operations in the
+    reference's order).  Returns a Series on the frame's index like the reference."""
+    E._require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def tab(s):
+        return torch.from_numpy(np.ascontiguousarray(df[[f"{coord_prefix}_{a}_{s}" for a in "xyz"]].to_numpy(np.float64).T)).to(dev)
+
+    c1, c2 = tab("x"), tab("y")
+    rows = torch.arange(len(df), dtype=torch.int64, device=dev)
+    zeros = torch.zeros((6, len(df)), dtype=torch.float64, device=dev)
+    return pd.Series(E.mahalanobis(c1, zeros, c2, zeros, rows, rows)["distance"].cpu().numpy(), index=df.index)

@@ -71,3 +71,30 @@ def compute_mode_continuous(data):
     counts, bin_edges = np.histogram(data, bins=bins, density=True)
     k = int(np.argmax(counts))
     return (bin_edges[k] + bin_edges[k + 1]) / 2
+
+
+def get_version():
+    """The package version (the reference keeps this function here, utilities.py:11-12; `from vapc.utilities import *` exports it)."""
+    from .main import __version__
+
+    return __version__
+
+
+def optimal_bins(data, method="fd"):
+    """Number of histogram bins by the sqrt / Sturges / Rice / Freedman-Diaconis / Scott rule (the reference's helper, utilities.py:132-
+    159; host arithmetic on one small sample, used by nothing on the device path)."""
+    import numpy as np
+
+    n = len(data)
+    if method == "sqrt":
+        return int(np.sqrt(n))
+    if method == "sturges":
+        return int(np.ceil(np.log2(n) + 1))
+    if method == "rice":
+        return int(np.ceil(2 * n ** (1 / 3)))
+    if method == "fd":
+        iqr = np.subtract(*np.percentile(data, [75, 25]))
+        return int(np.ceil((np.max(data) - np.min(data)) / (2 * iqr / n ** (1 / 3))))
+    if method == "scott":
+        return int(np.ceil((np.max(data) - np.min(data)) / (3.5 * np.std(data) / n ** (1 / 3))))
+    raise ValueError(f"Unknown method: {method}")
