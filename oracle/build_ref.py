@@ -4,7 +4,8 @@ TEST / MEASUREMENT INFRASTRUCTURE.  The reference (3dgeo-heidelberg/vapc) is pur
 package directory /root/reference/src/vapc, file for file and unchanged, to oracle/_ref/vapc — a directory that is git-ignored
 (never in this repository's history) but not gpurun-ignored, so it travels to the GPU box like the built .so files.  There
 `bench.py --impl reference` and the `cpu_baseline` leg time it through oracle/ref_harness.py (kind "reference"); without it they
-fall back to oracle/ref_port.py (kind "port").  Run by __graft_entry__.build() whenever /root/reference is present.
+fall back to oracle/ref_port.py (kind "port").  The reference's two unit-test files (tests/test_voxel.py, tests/test_compute.py) are
+copied the same way to oracle/_ref/tests for tests/test_gpu_reference_suite.py.  Run by __graft_entry__.build() whenever /root/reference is present.
 
     python oracle/build_ref.py
 """
@@ -16,6 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("VAPC_REFERENCE_SRC", "/root/reference/src")
 DST = os.path.join(HERE, "_ref")
+REFERENCE_UNIT_TESTS = ("test_voxel.py", "test_compute.py")
 
 
 def build(verbose=True) -> bool:
@@ -32,6 +34,15 @@ def build(verbose=True) -> bool:
         a, b = os.path.join(src, name), os.path.join(dst, name)
         if not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
             shutil.copyfile(a, b)
+    # the reference's own unit tests (pure Python, no fixtures on disk), unchanged as well: tests/test_gpu_reference_suite.py replays
+    # them against the drop-in package (`import vapc` resolving to vapc_b200)
+    tsrc, tdst = os.path.join(os.path.dirname(SRC), "tests"), os.path.join(DST, "tests")
+    if os.path.isdir(tsrc):
+        os.makedirs(tdst, exist_ok=True)
+        for name in REFERENCE_UNIT_TESTS:
+            a, b = os.path.join(tsrc, name), os.path.join(tdst, name)
+            if os.path.exists(a) and not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
+                shutil.copyfile(a, b)
     if verbose:
         print(f"oracle/build_ref.py: reference package at {dst}")
     return True
