@@ -292,6 +292,14 @@ VAPC_API int vapc_point_distance(const double* x, const double* y, const double*
  * tests/golden (assert_array_equal). */
 VAPC_API int vapc_cov_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start,
                                int64_t nvoxels, double* cov6, void* stream);
+/* ---- a7 / a9 / a10, the reference's own numbers: cog_* exactly as vapc.py:843-850 produces them ---------------------------------
+ * pandas' groupby mean: the Kahan-compensated sum of the voxel's coordinates in row order, divided by the count.  It differs from
+ * the exact mean of vapc_voxel_stats in the last bit at most — but `distance`, `min_distance` and the rows the reference keeps in
+ * its closest-to-centroid reduction (`distance == min_distance`, vapc.py:1195) are functions of THIS double: with it as the cog3
+ * argument of vapc_point_distance / vapc_closest_to_cog the three columns and the selected rows (exact ties included) equal the
+ * reference's bit for bit.  cog3 = [3][nvoxels].  Pinned to the unmodified reference by tests/golden (assert_array_equal). */
+VAPC_API int vapc_cog_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start,
+                               int64_t nvoxels, double* cog3, void* stream);
 /* ---- broadcast / gather helpers: out[i] = table[index[i]]  (the per-point broadcast of
  * groupby.transform / merge(how="left"), vapc.py:724-726, 843-850, 1087-1089) ------------ */
 VAPC_API int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream);

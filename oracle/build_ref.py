@@ -4,8 +4,9 @@ TEST / MEASUREMENT INFRASTRUCTURE.  The reference (3dgeo-heidelberg/vapc) is pur
 package directory /root/reference/src/vapc, file for file and unchanged, to oracle/_ref/vapc — a directory that is git-ignored
 (never in this repository's history) but not gpurun-ignored, so it travels to the GPU box like the built .so files.  There
 `bench.py --impl reference` and the `cpu_baseline` leg time it through oracle/ref_harness.py (kind "reference"); without it they
-fall back to oracle/ref_port.py (kind "port").  The reference's two unit-test files (tests/test_voxel.py, tests/test_compute.py) are
-copied the same way to oracle/_ref/tests for tests/test_gpu_reference_suite.py.  Run by __graft_entry__.build() whenever /root/reference is present.
+fall back to oracle/ref_port.py (kind "port").  The reference's own test files (tests/test_voxel.py, tests/test_compute.py,
+tests/integration_tests/test_main.py and test_io.py) and the three LAZ fixtures they read are copied the same way to oracle/_ref/tests for
+tests/test_gpu_reference_suite.py.  Run by __graft_entry__.build() whenever /root/reference is present.
 
     python oracle/build_ref.py
 """
@@ -17,7 +18,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("VAPC_REFERENCE_SRC", "/root/reference/src")
 DST = os.path.join(HERE, "_ref")
-REFERENCE_UNIT_TESTS = ("test_voxel.py", "test_compute.py")
+REFERENCE_UNIT_TESTS = ("test_voxel.py", "test_compute.py", "integration_tests/test_main.py", "integration_tests/test_io.py",
+                        "test_data/vapc_in.laz", "test_data/small_mask.laz", "test_data/als_multichannel_leg000_points.laz")
 
 
 def build(verbose=True) -> bool:
@@ -41,6 +43,7 @@ def build(verbose=True) -> bool:
         os.makedirs(tdst, exist_ok=True)
         for name in REFERENCE_UNIT_TESTS:
             a, b = os.path.join(tsrc, name), os.path.join(tdst, name)
+            os.makedirs(os.path.dirname(b), exist_ok=True)
             if os.path.exists(a) and not (os.path.exists(b) and filecmp.cmp(a, b, shallow=False)):
                 shutil.copyfile(a, b)
     if verbose:

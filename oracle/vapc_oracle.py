@@ -210,6 +210,26 @@ def covariance_reference_bitwise(x, y, z, g: Grouping):
     return out
 
 
+def center_of_gravity_reference_bitwise(x, y, z, g: Grouping):
+    """The reference's cog_* columns bit for bit (vapc.py:843-850): pandas' groupby mean = the Kahan-compensated sum of the voxel's
+    values in frame order (the same recurrence as its groupby sum) divided by the count.  [V, 3].  Pure-Python loop over the points:
+    small clouds only.  tests/test_oracle_golden.py pins it — and the distance / min_distance columns that follow from it with numpy's
+    own operation order (vapc.py:790-825) — to the golden columns with assert_array_equal."""
+    lab = np.asarray(g.point2voxel, np.int64)
+    out = np.empty((g.nvoxels, 3))
+    for j, col in enumerate((x, y, z)):
+        sj, cj = np.zeros(g.nvoxels), np.zeros(g.nvoxels)
+        for v, l in zip(np.asarray(col, np.float64).tolist(), lab.tolist()):
+            y_ = v - cj[l]
+            t = sj[l] + y_
+            cj[l] = (t - sj[l]) - y_
+            if cj[l] != cj[l]:
+                cj[l] = 0.0
+            sj[l] = t
+        out[:, j] = sj / g.counts.astype(np.float64)
+    return out
+
+
 def covariance_exact(x, y, z, g: Grouping):
     """Two-pass centred covariance in long double (what np.cov computes, vapc.py:1055-1056,
     evaluated in extended precision).  Independent 'truth' for the H1 parity rule."""

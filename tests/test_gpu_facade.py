@@ -195,6 +195,37 @@ def test_reduce_to_voxels_matches_reference(vapc, name, mode):
             np.testing.assert_array_equal(v.df[others].to_numpy(), np.stack([gold[f"red_{mode}_{c}"] for c in others], 1))
 
 
+@pytest.mark.parametrize("name", P.cloud_cases())
+def test_centroid_columns_and_reduced_frames_equal_reference_bit_for_bit(vapc, name):
+    """centroid_formula = "reference" (the facade's default): the centroid is pandas' groupby mean to the bit, so cog_*, distance and
+    min_distance EQUAL the golden columns, and the centre-of-gravity / closest-to-centroid reductions return the reference's frames
+    row for row — same rows (every exactly tied point included), same order, every column: nothing left to the H5 tolerance.  With
+    "exact" (the reduction's own mean, no extra pass) the H5 rule holds as before."""
+    gold = P.load_golden(name)
+    v = new(vapc, gold)
+    assert v.centroid_formula == "reference"
+    v.compute = ["center_of_gravity", "distance_to_center_of_gravity", "closest_to_center_of_gravity"]
+    v.compute_requested_attributes()
+    df = v.df
+    for c in ("cog_x", "cog_y", "cog_z", "distance", "min_distance"):
+        np.testing.assert_array_equal(df[c].to_numpy(), gold["pt_" + c], err_msg=f"{name} {c}")
+    for mode in ("center_of_gravity", "closest_to_center_of_gravity"):
+        w = new(vapc, gold, return_at=mode)
+        w.reduce_to_voxels()
+        cols = gold[f"red_{mode}__columns"].tolist()
+        assert w.df.columns.tolist() == cols
+        ref = np.stack([gold[f"red_{mode}_{c}"] for c in cols], 1)
+        np.testing.assert_array_equal(w.df.to_numpy(), ref, err_msg=f"{name} {mode}")
+    e = new(vapc, gold, return_at="closest_to_center_of_gravity")
+    e.centroid_formula = "exact"
+    e.reduce_to_voxels()
+    check_closest_h5(e.df, gold)
+    bad = new(vapc, gold)
+    bad.centroid_formula = "kahan"
+    with pytest.raises(ValueError):
+        bad.compute_center_of_gravity()
+
+
 @pytest.mark.parametrize("name", [n for n in P.cloud_cases() if any(k.startswith("stat_") for k in P.load_golden(n))])
 def test_attribute_statistics_match_reference(vapc, name):
     gold = P.load_golden(name)

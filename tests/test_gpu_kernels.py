@@ -434,6 +434,43 @@ def test_plan_exchange_kernel_matches_host_mirror(E):
 
 
 @pytest.mark.parametrize("name", ["utm_offset_vs0.25", "uniform5000_vs0.25", "plane500_vs1.0", "vapc_in_every50th_vs0.25", "shifted_origin_vs0.3"])
+def test_cog_reference_formula_bit_for_bit(E, name):
+    """vapc_cog_reference_formula == the cog_* columns of the unmodified reference, bit for bit; with it as the cloud's centroid,
+    vapc_point_distance == `distance`, vapc_closest_to_cog == `min_distance` and the winner is the FIRST row of the reference's exactly
+    tied set — all assert_array_equal.  On a larger seeded cloud with duplicated points: == the oracle's Kahan restatement."""
+    gold = P.load_golden(name)
+    x, y, z = (np.asarray(gold[k], np.float64) for k in ("in_X", "in_Y", "in_Z"))
+    vs, origin = float(gold["in_voxel_size"]), np.asarray(gold["in_origin"], float).tolist()
+    for bucketed in (True, False):
+        cloud = E.VoxelCloud.build(x, y, z, vs, origin, bucketed=bucketed)
+        exact = _np(cloud.stats(cog=True).cog)
+        cloud.centroid_formula = "reference"
+        p2v = _u32(cloud.point2voxel)
+        got = _np(cloud.stats(cog=True).cog)
+        for k, c in enumerate(("cog_x", "cog_y", "cog_z")):
+            np.testing.assert_array_equal(got[k][p2v], gold["pt_" + c], err_msg=f"{name} {c} bucketed={bucketed}")
+        assert np.all(np.abs(got - exact) <= 8 * P.EPS * np.maximum(np.abs(got), vs))  # the two centroids differ in the last bits only
+        np.testing.assert_array_equal(_np(cloud.point_distance()), gold["pt_distance"])
+        md, am = cloud.closest_to_cog()
+        np.testing.assert_array_equal(_np(md)[p2v], gold["pt_min_distance"])
+        tied = gold["pt_distance"] == gold["pt_min_distance"]
+        first = np.full(cloud.nvoxels, len(x), np.int64)
+        np.minimum.at(first, p2v[tied], np.nonzero(tied)[0])
+        np.testing.assert_array_equal(_u32(am), first)
+        cloud.centroid_formula = "exact"
+        np.testing.assert_array_equal(_np(cloud.stats(cog=True).cog), exact)
+        with pytest.raises(ValueError):
+            cloud.centroid_formula = "kahan"
+    rng = np.random.default_rng(41)
+    pts = np.round(rng.uniform(0, 12, (30000, 3)), 3) + [476850.0, 5429100.0, 312.0]
+    pts[5000:9000] = pts[1000:5000]  # duplicated points: exact ties
+    x, y, z = (np.ascontiguousarray(pts[:, k]) for k in range(3))
+    cloud = E.VoxelCloud.build(x, y, z, 0.5, [0, 0, 0])
+    g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], 0.5))
+    np.testing.assert_array_equal(_np(cloud.centroid_reference_formula()).T, O.center_of_gravity_reference_bitwise(x, y, z, g))
+
+
+@pytest.mark.parametrize("name", ["utm_offset_vs0.25", "uniform5000_vs0.25", "plane500_vs1.0", "vapc_in_every50th_vs0.25", "shifted_origin_vs0.3"])
 def test_cov_reference_formula_bit_for_bit(E, name):
     """vapc_cov_reference_formula == the cov_** columns of the unmodified reference, bit for bit (UTM-sized coordinates included,
     where those columns are mostly rounding noise) — and == the oracle's Kahan restatement on a larger seeded cloud."""

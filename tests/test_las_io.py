@@ -117,13 +117,20 @@ def test_save_as_las_roundtrip(tmp_path):
     for c in ("point_count", "cov_xx"):  # extra dimensions are float32 (datahandler.py:157)
         np.testing.assert_array_equal(back.df[c].to_numpy(), df[c].to_numpy().astype(np.float32).astype(np.float64))
     assert back.df["scanner_channel"].eq(0).all() and back.df["overlap"].eq(0).all()  # not written (datahandler.py:152)
-    # .laz: the library's own LASzip encoder and decoder (no colours here: LAS 1.4 point format 6 + extra bytes, layered)
+    # .laz: the library's own LASzip encoder and decoder (LAS 1.4 point format 7 like the reference's default — colour fields present,
+    # all zero here — + extra bytes, layered; point format 6 on request)
     laz = str(tmp_path / "out.laz")
     dh.save_as_las(laz)
     assert os.path.getsize(laz) < os.path.getsize(out)
     hz, _ = las.read_las(laz)
-    assert hz.compressed and hz.version == (1, 4) and hz.point_format == 6 and hz.point_count == n
-    assert hz.laszip["compressor"] == 3 and hz.laszip["items"][0] == (10, 30, 3) and hz.laszip["items"][-1][0] == 14
+    assert hz.compressed and hz.version == (1, 4) and hz.point_format == 7 and hz.point_count == n
+    assert hz.laszip["compressor"] == 3 and hz.laszip["items"][:2] == [(10, 30, 3), (11, 6, 3)] and hz.laszip["items"][-1][0] == 14
+    laz6 = str(tmp_path / "out6.laz")
+    dh.save_as_las(laz6, las_point_format=6)
+    h6, c6 = las.read_las(laz6)
+    assert h6.compressed and h6.point_format == 6 and h6.laszip["items"][0] == (10, 30, 3) and h6.laszip["items"][1][0] == 14 and "red" not in c6
+    with pytest.raises(NotImplementedError):
+        dh.save_as_las(str(tmp_path / "out8.laz"), las_point_format=8)
     again = DataHandler(laz)
     again.load_las_files()
     for c in "XYZ":
@@ -223,8 +230,8 @@ def test_save_as_laz_with_colours_uses_point_format_7(tmp_path):
 
 def test_las_to_laz_conversion_of_the_command_line(tmp_path):
     """What main.do_vapc_on_files does for save_as=".laz" (main.py:154-168 of the reference): the tool's LAS 1.4 / format 7 result is
-    loaded again and saved as .laz.  Its colour dimensions are all zero (the cloud had none), so the LAZ file is LAS 1.4 point
-    format 6 + extra bytes; every other column survives."""
+    loaded again and saved as .laz: LAS 1.4 point format 7 again (colour dimensions all zero: the cloud had none) + extra bytes;
+    every column survives."""
     rng = np.random.default_rng(4)
     n = 3000
     df = pd.DataFrame({"X": np.round(rng.random(n) * 30, 3), "Y": np.round(rng.random(n) * 30, 3), "Z": np.round(rng.random(n) * 5, 3),
@@ -240,10 +247,11 @@ def test_las_to_laz_conversion_of_the_command_line(tmp_path):
     laz_path = str(tmp_path / "compute.laz")
     again.save_as_las(laz_path)
     h, _ = las.read_las(laz_path)
-    assert h.compressed and h.version == (1, 4) and h.point_format == 6 and os.path.getsize(laz_path) < os.path.getsize(las_path)
+    assert h.compressed and h.version == (1, 4) and h.point_format == 7 and os.path.getsize(laz_path) < os.path.getsize(las_path)
     res = DataHandler(laz_path)
     res.load_las_files()
-    assert len(res.df) == n and {"point_count", "cog_x", "cog_y", "cog_z", "intensity"} <= set(res.df.columns) and "red" not in res.df.columns
+    assert len(res.df) == n and {"point_count", "cog_x", "cog_y", "cog_z", "intensity", "red", "green", "blue"} <= set(res.df.columns)
+    assert not res.df[["red", "green", "blue"]].to_numpy().any()
     for c in ("point_count", "cog_x", "cog_y", "cog_z", "intensity"):
         np.testing.assert_array_equal(res.df[c].to_numpy(), again.df[c].to_numpy(), err_msg=c)
     for c in "XYZ":

@@ -85,6 +85,17 @@ def test_float_columns(name):
     # H5: the oracle's winner lies in the reference's tied set
     ref_min = gold["pt_min_distance"][winner]
     assert np.all(ref_d[winner] <= ref_min * (1 + 1e-12))
+    # ... and with the reference's own centroid double (pandas' Kahan group mean) nothing is left to tolerance: cog_*, distance,
+    # min_distance and the set of rows tied at the minimum equal the golden columns BIT FOR BIT
+    if len(x) <= 60000:
+        cog_b = O.center_of_gravity_reference_bitwise(x, y, z, g)
+        for k, c in enumerate(("cog_x", "cog_y", "cog_z")):
+            np.testing.assert_array_equal(cog_b[p2v, k], gold["pt_" + c], err_msg=c)
+        dist_b = O.distance_to_center_of_gravity(x, y, z, g, cog_b)
+        np.testing.assert_array_equal(dist_b, ref_d, err_msg="distance")
+        dmin_b, _, is_min_b = O.closest_to_center_of_gravity(dist_b, g)
+        np.testing.assert_array_equal(dmin_b[p2v], gold["pt_min_distance"], err_msg="min_distance")
+        np.testing.assert_array_equal(is_min_b, ref_d == gold["pt_min_distance"], err_msg="rows tied at the minimum")
 
 
 @pytest.mark.parametrize("name", P.cloud_cases())

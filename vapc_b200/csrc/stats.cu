@@ -123,7 +123,38 @@ __global__ void __launch_bounds__(kThreads) cov_reference_kernel(const double4* 
   cov6[4 * nvox + v] = cov(syz.s, sy.s, sz.s);
   cov6[5 * nvox + v] = cov(szz.s, sz.s, sz.s);
 }
+// The reference's OWN centroid columns, rounding for rounding (vapc.py:843-850): pandas' groupby mean = the Kahan-compensated sum of
+// the voxel's X (Y, Z) in frame order, divided by the count.  Equal to the exact mean to the last bit or two — but the reference selects
+// its closest-to-centroid rows by `distance == min_distance` on distances to THIS centroid, so ties and near-ties (duplicate points,
+// points mirrored about the centroid) only fall the same way when the centroid is the same double.
+__global__ void __launch_bounds__(kThreads) cog_reference_kernel(const double4* __restrict__ xyzw, const uint32_t* __restrict__ pos_sorted,
+                                                                 const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ cog3) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const uint32_t a = start[v], b = start[v + 1];
+  Kahan sx, sy, sz;
+  for (uint32_t p = a; p < b; ++p) {
+    const double4 r = ld_record(xyzw + pos_sorted[p]);
+    sx.add(r.x); sy.add(r.y); sz.add(r.z);
+  }
+  const double n = (double)(b - a);
+  cog3[0 * nvox + v] = __ddiv_rn(sx.s, n);
+  cog3[1 * nvox + v] = __ddiv_rn(sy.s, n);
+  cog3[2 * nvox + v] = __ddiv_rn(sz.s, n);
+}
 }  // namespace
+
+extern "C" int vapc_cog_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start, int64_t nvoxels, double* cog3,
+                                          void* stream) {
+  if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_cog_reference_formula: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  if (!xyzw || !pos_sorted || !start || !cog3) return vapc_set_error(VAPC_E_INVALID, "vapc_cog_reference_formula: null buffer");
+  if (reinterpret_cast<uintptr_t>(xyzw) & 31u) return vapc_set_error(VAPC_E_INVALID, "vapc_cog_reference_formula: xyzw must be 32-byte aligned");
+  VAPC_LAUNCH(cog_reference_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream),
+              reinterpret_cast<const double4*>(xyzw), pos_sorted, start, nvoxels, cog3);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
 
 extern "C" int vapc_cov_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start, int64_t nvoxels, double* cov6,
                                           void* stream) {

@@ -52,6 +52,9 @@ class DataHandler:
         if not isinstance(self.files, list):
             self.files = [self.files]
         for path in self.files:
+            if not isinstance(path, (str, os.PathLike)):
+                # what laspy.open raises for a source that is neither a path nor a stream (tests/integration_tests/test_io.py:134-144)
+                raise AttributeError(f"{type(path).__name__!r} object has no attribute 'seekable'")
             path = str(path)
             if _laspy is not None:  # pragma: no cover
                 with _laspy.open(path) as fh:
@@ -109,13 +112,14 @@ class DataHandler:
             out.write(outfile)
             return
         if outfile.lower().endswith(".laz"):
-            # native LASzip encoder: LAS 1.4 point format 6 + extra bytes, 7 when the cloud has colours (the reference's default)
-            rgb = [c for c in ("red", "green", "blue") if c in self.df.columns]
-            coloured = any(bool(self.df[c].to_numpy().any()) for c in rgb)  # all-zero colours (a point-format-7 file without colours) are dropped
-            known = set(_las.dimension_names(7 if coloured else 6))
+            # native LASzip encoder: LAS 1.4 point format 7 (the reference's default: colour fields always present, zero when the
+            # cloud has none — tests/integration_tests/test_io.py:162-180 asserts the format) or 6, + extra bytes
+            if str(las_version) != "1.4" or int(las_point_format) not in (6, 7):
+                raise NotImplementedError("the native LASzip writer produces LAS 1.4 point formats 6 and 7 (the reference's default is 1.4 / 7)")
+            known = set(_las.dimension_names(int(las_point_format)))
             standard, extra = {}, {}
             for name in self.df.columns:
-                if name in _SKIP_ON_SAVE or (name in rgb and not coloured):
+                if name in _SKIP_ON_SAVE:
                     continue
                 col = self.df[name].to_numpy()
                 if name in known:
@@ -124,7 +128,8 @@ class DataHandler:
                     extra[name] = np.asarray(col, dtype=np.float64)  # seconds of a GPS week need all 53 bits
                 else:
                     extra[name] = np.asarray(col, dtype=np.float64).astype(np.float32)
-            _las.write_laz(outfile, xyz[:, 0], xyz[:, 1], xyz[:, 2], standard, extra, scales=las_scales, offsets=las_offset)
+            _las.write_laz(outfile, xyz[:, 0], xyz[:, 1], xyz[:, 2], standard, extra, scales=las_scales, offsets=las_offset,
+                           point_format=int(las_point_format))
             return
         if str(las_version) != "1.4" or int(las_point_format) not in (6, 7, 8):
             raise NotImplementedError("the native writer produces LAS 1.4 point formats 6, 7, 8 (the reference's default is 1.4 / 7)")

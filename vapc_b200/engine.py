@@ -284,6 +284,7 @@ class VoxelCloud:
         self._seg_ws = None
         self.sorted_by = "radix"  # or "cells" (vapc_sort_cells_segmented)
         self._stats_cache: Dict[str, torch.Tensor] = {}
+        self._centroid_formula = "exact"
         self.axis_order = (0, 1, 2)  # coordinate axis behind every internal axis of the keys / moments (multi-GPU tables permute them)
 
     # ------------------------------------------------------------------------------------
@@ -519,6 +520,29 @@ class VoxelCloud:
         L.call("vapc_cov_reference_formula", _ptr(self.xyzw), _ptr(self.pos_sorted), _ptr(self.start), V, _ptr(out), _stream())
         return out
 
+    def centroid_reference_formula(self) -> torch.Tensor:
+        """[3, V] centroid exactly as the reference's compute_center_of_gravity produces it (vapc.py:843-850): pandas' groupby mean =
+        the Kahan sum of the voxel's coordinates in row order / count, bit for bit.  Distances to it, their per-voxel minimum and
+        the rows tied at that minimum are then the reference's own (vapc.py:790-825, :1195)."""
+        V = self.nvoxels
+        out = torch.empty((3, V), dtype=torch.float64, device=self.device)
+        L.call("vapc_cog_reference_formula", _ptr(self.xyzw), _ptr(self.pos_sorted), _ptr(self.start), V, _ptr(out), _stream())
+        return out
+
+    @property
+    def centroid_formula(self) -> str:
+        """Which double `stats(cog=True).cog` — and with it point_distance() / closest_to_cog() — carries: "exact" (the mean from the
+        shifted moments of the reduction, default) or "reference" (centroid_reference_formula: the drop-in facade's choice)."""
+        return self._centroid_formula
+
+    @centroid_formula.setter
+    def centroid_formula(self, value: str):
+        if value not in ("exact", "reference"):
+            raise ValueError("centroid_formula must be 'exact' or 'reference'")
+        if value != self._centroid_formula:
+            self._stats_cache.pop("cog", None)
+        self._centroid_formula = value
+
     # ------------------------------------------------------------------------------------
     def stats(self, density=False, cog=False, std=False, cov=False, eig=False, eig_n=False, feat=False) -> VoxelStats:
         """One launch of vapc_voxel_stats for whatever is not cached yet."""
@@ -527,9 +551,14 @@ class VoxelCloud:
         shapes = dict(density=(V,), cog=(3, V), std=(3, V), cov=(6, V), eig=(3, V), eig_n=(3, V), feat=(8, V))
         new = {k: torch.empty(shapes[k], dtype=torch.float64, device=dev) for k, w in want.items() if w and k not in self._stats_cache}
         if new:
-            order = (C.c_int32 * 3)(*self.axis_order)
-            L.call("vapc_voxel_stats_axes", _ptr(self.voxel_keys), _ptr(self.count), _ptr(self.mean3), _ptr(self.m2), V, C.byref(self.grid), order,
-                   *[_ptr(new.get(k)) for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")], _stream())
+            # the kernel forms everything from the (count, mean, M2) moments; a "reference" centroid comes from its own pass instead
+            outs = [new.get(k) if k != "cog" or self._centroid_formula == "exact" else None for k in ("density", "cog", "std", "cov", "eig", "eig_n", "feat")]
+            if any(o is not None for o in outs):
+                order = (C.c_int32 * 3)(*self.axis_order)
+                L.call("vapc_voxel_stats_axes", _ptr(self.voxel_keys), _ptr(self.count), _ptr(self.mean3), _ptr(self.m2), V, C.byref(self.grid), order,
+                       *[_ptr(o) for o in outs], _stream())
+            if "cog" in new and self._centroid_formula == "reference":
+                new["cog"] = self.centroid_reference_formula()
             self._stats_cache.update(new)
         return VoxelStats(**{k: self._stats_cache[k] for k, w in want.items() if w})
 

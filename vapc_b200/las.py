@@ -328,10 +328,10 @@ def _laz_encode(rec: np.ndarray, items, chunk_size: int, offset_to_points: int) 
 
 
 def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[str, np.ndarray], scales=None, offsets=None,
-              chunk_size: int = 50000, generating_software: str = "vapc_b200", las14=None):
+              chunk_size: int = 50000, generating_software: str = "vapc_b200", las14=None, point_format=None):
     """LASzip-compressed output through the library's own encoder (vapc_laz_encode).
-    las14 (default): LAS 1.4 point format 6 (7 with colours: the reference's own output format, datahandler.py:99-165) + extra
-    bytes, "layered chunked" compression of the items POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) — the layout of the reference's LAS 1.4
+    las14 (default): LAS 1.4 point format `point_format` (None: 6, or 7 when colours are given; the reference's own output format is
+    7, datahandler.py:99-165) + extra bytes, "layered chunked" compression of the items POINT14 v3 (+ RGB14 v3) (+ BYTE14 v3) — the layout of the reference's LAS 1.4
     fixtures (RGB14 is round-trip tested only: no fixture holds colours in LAS 1.4).  las14=False: LAS 1.2, point format 0 - 3 (GPS time and / or colours),
     every other dimension as extra bytes, "pointwise chunked" compression of POINT10 v2 (+ GPSTIME11 v2) (+ RGB12 v2) (+ BYTE v2) — the layout of the reference's vapc_in.laz; values that do not fit the legacy fields (return numbers above 7,
     classes above 31) are masked as in any point-format-0 file.  The encoder reproduces the point data of all four fixtures byte
@@ -345,6 +345,11 @@ def write_laz(path: str, x, y, z, standard: Dict[str, np.ndarray], extra: Dict[s
     coloured = any(c in standard for c in ("red", "green", "blue"))
     if las14 is None:
         las14 = True
+    if las14 and point_format is not None:
+        # the caller names the LAS 1.4 point format: 7 carries the colour fields (zero when the cloud has none), 6 does not
+        if int(point_format) not in (6, 7):
+            raise NotImplementedError(f"the LASzip writer produces LAS 1.4 point formats 6 and 7, not {point_format}")
+        coloured = int(point_format) == 7
     if las14:
         extra_size = sum(np.dtype(_EXTRA_TYPES[_EXTRA_CODES.get(np.asarray(a).dtype.str.lstrip("<|"), 9)]).itemsize for a in extra.values())
         items = [(10, 30, 3)] + ([(11, 6, 3)] if coloured else []) + ([(14, extra_size, 3)] if extra_size else [])

@@ -113,6 +113,11 @@ class Vapc:
         # covariance at any coordinate offset); "reference" = the reference's raw-moment columns bit for bit (vapc.py:947-1006), which
         # lose all digits at UTM-sized coordinates.  Eigenvalues and features never depend on it (the reference takes them from np.cov).
         self.covariance_formula = "exact"
+        # not in the reference either: which double the centroid is.  "reference" (default) = pandas' groupby mean bit for bit (Kahan sum
+        # in row order / count, vapc.py:843-850): cog_*, distance, min_distance and the rows kept by the closest-to-centroid reduction
+        # (exact ties included) then EQUAL the reference's; "exact" = the mean from the reduction's shifted moments (no extra pass; equal
+        # to within a bit, ties may fall differently).  Nothing is lost either way: both are correctly rounded to the last bit or two.
+        self.centroid_formula = "reference"
         self._df = None      # the host frame: original columns + whatever has been materialised
         self._lazy = {}      # column name -> (kind, device tensor, cloud); kind "voxel": [V] column to broadcast, "point": [N] column
         self._cols = None    # logical column order (frame columns + pending ones), None = the frame's own
@@ -311,6 +316,7 @@ class Vapc:
             self._exposed = False
             self._voxelized_cloud = self._cloud if given is not None else None
             self._cloud_given = given is not None
+        self._cloud.centroid_formula = self.centroid_formula  # drops a cached centroid of the other kind
         return self._cloud
 
     def _reset_index(self):
@@ -553,6 +559,7 @@ class Vapc:
         """The device cloud if it still describes the frame (not handed out, not replaced, same grid), else None."""
         if self._cloud is None or self._exposed or self._df is None or self._signature() != self._cloud_sig:
             return None
+        self._cloud.centroid_formula = self.centroid_formula
         return self._cloud
 
     def _own_voxel_cloud(self):
