@@ -300,6 +300,13 @@ VAPC_API int vapc_cov_reference_formula(const double* xyzw, const uint32_t* pos_
  * reference's bit for bit.  cog3 = [3][nvoxels].  Pinned to the unmodified reference by tests/golden (assert_array_equal). */
 VAPC_API int vapc_cog_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start,
                                int64_t nvoxels, double* cog3, void* stream);
+/* ---- a8, the reference's own numbers: std_* exactly as vapc.py:873-880 produces them ---------------------------------------------
+ * pandas' groupby std: Welford's recurrence over the voxel's coordinates in row order, M2 / (n - 1), square root — bit for bit,
+ * including the ~1e-7 relative error that recurrence has at UTM-sized coordinates (vapc_voxel_stats' std, from moments about a
+ * shift inside the voxel, does not have it).  For callers who DIFF against the reference's columns.  std3 = [3][nvoxels], NaN for
+ * single-point voxels.  Pinned to the unmodified reference by tests/golden (assert_array_equal). */
+VAPC_API int vapc_std_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start,
+                               int64_t nvoxels, double* std3, void* stream);
 /* ---- broadcast / gather helpers: out[i] = table[index[i]]  (the per-point broadcast of
  * groupby.transform / merge(how="left"), vapc.py:724-726, 843-850, 1087-1089) ------------ */
 VAPC_API int vapc_gather_f64(const double* table, const uint32_t* index, int64_t n, double* out, void* stream);

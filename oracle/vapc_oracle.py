@@ -230,6 +230,24 @@ def center_of_gravity_reference_bitwise(x, y, z, g: Grouping):
     return out
 
 
+def std_reference_bitwise(x, y, z, g: Grouping):
+    """The reference's std_* columns bit for bit (vapc.py:873-880): pandas' groupby std = Welford's recurrence over the voxel's values
+    in frame order, M2 / (n - 1), square root.  [V, 3], NaN for single-point voxels.  Pure-Python loop: small clouds only; pinned to
+    the golden columns with assert_array_equal (tests/test_oracle_golden.py)."""
+    lab = np.asarray(g.point2voxel, np.int64)
+    out = np.empty((g.nvoxels, 3))
+    for j, col in enumerate((x, y, z)):
+        n, mean, m2 = np.zeros(g.nvoxels), np.zeros(g.nvoxels), np.zeros(g.nvoxels)
+        for v, l in zip(np.asarray(col, np.float64).tolist(), lab.tolist()):
+            n[l] += 1.0
+            old = mean[l]
+            mean[l] = old + (v - old) / n[l]
+            m2[l] += (v - mean[l]) * (v - old)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out[:, j] = np.sqrt(np.where(n > 1, m2 / (n - 1), np.nan))
+    return out
+
+
 def covariance_exact(x, y, z, g: Grouping):
     """Two-pass centred covariance in long double (what np.cov computes, vapc.py:1055-1056,
     evaluated in extended precision).  Independent 'truth' for the H1 parity rule."""

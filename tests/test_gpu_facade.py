@@ -216,6 +216,16 @@ def test_centroid_columns_and_reduced_frames_equal_reference_bit_for_bit(vapc, n
         assert w.df.columns.tolist() == cols
         ref = np.stack([gold[f"red_{mode}_{c}"] for c in cols], 1)
         np.testing.assert_array_equal(w.df.to_numpy(), ref, err_msg=f"{name} {mode}")
+    s_ref = new(vapc, gold)
+    assert s_ref.std_formula == "exact"
+    s_ref.std_formula = "reference"
+    s_ref.compute_std_of_cog()
+    for c in ("std_x", "std_y", "std_z"):
+        np.testing.assert_array_equal(s_ref.df[c].to_numpy(), gold["pt_" + c], err_msg=f"{name} {c}")
+    s_bad = new(vapc, gold)
+    s_bad.std_formula = "welford"
+    with pytest.raises(ValueError):
+        s_bad.compute_std_of_cog()
     e = new(vapc, gold, return_at="closest_to_center_of_gravity")
     e.centroid_formula = "exact"
     e.reduce_to_voxels()

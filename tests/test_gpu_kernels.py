@@ -451,6 +451,9 @@ def test_cog_reference_formula_bit_for_bit(E, name):
             np.testing.assert_array_equal(got[k][p2v], gold["pt_" + c], err_msg=f"{name} {c} bucketed={bucketed}")
         assert np.all(np.abs(got - exact) <= 8 * P.EPS * np.maximum(np.abs(got), vs))  # the two centroids differ in the last bits only
         np.testing.assert_array_equal(_np(cloud.point_distance()), gold["pt_distance"])
+        std = _np(cloud.std_reference_formula())
+        for k, c in enumerate(("std_x", "std_y", "std_z")):  # pandas' Welford recurrence: std_* of the reference to the bit
+            np.testing.assert_array_equal(std[k][p2v], gold["pt_" + c], err_msg=f"{name} {c} bucketed={bucketed}")
         md, am = cloud.closest_to_cog()
         np.testing.assert_array_equal(_np(md)[p2v], gold["pt_min_distance"])
         tied = gold["pt_distance"] == gold["pt_min_distance"]
@@ -468,6 +471,7 @@ def test_cog_reference_formula_bit_for_bit(E, name):
     cloud = E.VoxelCloud.build(x, y, z, 0.5, [0, 0, 0])
     g = O.group_by_voxel(*O.voxelize(x, y, z, [0, 0, 0], 0.5))
     np.testing.assert_array_equal(_np(cloud.centroid_reference_formula()).T, O.center_of_gravity_reference_bitwise(x, y, z, g))
+    np.testing.assert_array_equal(_np(cloud.std_reference_formula()).T, O.std_reference_bitwise(x, y, z, g))
 
 
 @pytest.mark.parametrize("name", ["utm_offset_vs0.25", "uniform5000_vs0.25", "plane500_vs1.0", "vapc_in_every50th_vs0.25", "shifted_origin_vs0.3"])

@@ -96,6 +96,9 @@ def test_float_columns(name):
         dmin_b, _, is_min_b = O.closest_to_center_of_gravity(dist_b, g)
         np.testing.assert_array_equal(dmin_b[p2v], gold["pt_min_distance"], err_msg="min_distance")
         np.testing.assert_array_equal(is_min_b, ref_d == gold["pt_min_distance"], err_msg="rows tied at the minimum")
+        std_b = O.std_reference_bitwise(x, y, z, g)  # pandas' Welford recurrence: the reference's std_* to the bit
+        for k, c in enumerate(("std_x", "std_y", "std_z")):
+            np.testing.assert_array_equal(std_b[p2v, k], gold["pt_" + c], err_msg=c)
 
 
 @pytest.mark.parametrize("name", P.cloud_cases())

@@ -93,6 +93,7 @@ SIGNATURES = {
     "vapc_reduce_debug_lanes": (C.c_int, [I32]),
     "vapc_cov_reference_formula": (C.c_int, [P, P, P, I64, P, P]),
     "vapc_cog_reference_formula": (C.c_int, [P, P, P, I64, P, P]),
+    "vapc_std_reference_formula": (C.c_int, [P, P, P, I64, P, P]),
     "vapc_sort_pairs": (C.c_int, [P, P, P, P, P, I32, I64, I32, I32, P, SZ, C.POINTER(I32), P]),
     "vapc_sort_pairs_bits": (C.c_int, [P, P, P, P, P, I32, I64, I32, I32, I32, P, SZ, C.POINTER(I32), P]),
     "vapc_scatter_u32": (C.c_int, [P, P, I64, P, P]),

@@ -142,7 +142,46 @@ __global__ void __launch_bounds__(kThreads) cog_reference_kernel(const double4* 
   cog3[1 * nvox + v] = __ddiv_rn(sy.s, n);
   cog3[2 * nvox + v] = __ddiv_rn(sz.s, n);
 }
+// The reference's OWN std_* columns, rounding for rounding (vapc.py:873-880): pandas' groupby std = Welford's recurrence over the voxel's
+// values in frame order (mean += (v - mean) / k; M2 += (v - mean_new) * (v - mean_old)), M2 / (n - 1), square root.  At UTM-sized
+// coordinates the recurrence loses ~1e-7 of the value (the reason the default std comes from the shifted moments); this entry point is
+// for callers who diff against the reference's column.  NaN for single-point voxels.
+__global__ void __launch_bounds__(kThreads) std_reference_kernel(const double4* __restrict__ xyzw, const uint32_t* __restrict__ pos_sorted,
+                                                                 const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ std3) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const uint32_t a = start[v], b = start[v + 1];
+  double mean[3] = {0.0, 0.0, 0.0}, m2[3] = {0.0, 0.0, 0.0};
+  double k = 0.0;
+  for (uint32_t p = a; p < b; ++p) {
+    const double4 r = ld_record(xyzw + pos_sorted[p]);
+    const double val[3] = {r.x, r.y, r.z};
+    k = __dadd_rn(k, 1.0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double old = mean[c];
+      mean[c] = __dadd_rn(old, __ddiv_rn(__dsub_rn(val[c], old), k));
+      m2[c] = __dadd_rn(m2[c], __dmul_rn(__dsub_rn(val[c], mean[c]), __dsub_rn(val[c], old)));
+    }
+  }
+  const double n1 = (double)((long long)(b - a) - 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    std3[c * nvox + v] = b - a > 1 ? __dsqrt_rn(__ddiv_rn(m2[c], n1)) : __longlong_as_double(0x7ff8000000000000LL);
+}
 }  // namespace
+
+extern "C" int vapc_std_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start, int64_t nvoxels, double* std3,
+                                          void* stream) {
+  if (nvoxels < 0) return vapc_set_error(VAPC_E_INVALID, "vapc_std_reference_formula: bad arguments");
+  if (nvoxels == 0) return VAPC_OK;
+  if (!xyzw || !pos_sorted || !start || !std3) return vapc_set_error(VAPC_E_INVALID, "vapc_std_reference_formula: null buffer");
+  if (reinterpret_cast<uintptr_t>(xyzw) & 31u) return vapc_set_error(VAPC_E_INVALID, "vapc_std_reference_formula: xyzw must be 32-byte aligned");
+  VAPC_LAUNCH(std_reference_kernel, (unsigned)((nvoxels + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream),
+              reinterpret_cast<const double4*>(xyzw), pos_sorted, start, nvoxels, std3);
+  VAPC_CHECK_LAUNCH();
+  return VAPC_OK;
+}
 
 extern "C" int vapc_cog_reference_formula(const double* xyzw, const uint32_t* pos_sorted, const uint32_t* start, int64_t nvoxels, double* cog3,
                                           void* stream) {

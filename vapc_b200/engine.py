@@ -529,6 +529,15 @@ class VoxelCloud:
         L.call("vapc_cog_reference_formula", _ptr(self.xyzw), _ptr(self.pos_sorted), _ptr(self.start), V, _ptr(out), _stream())
         return out
 
+    def std_reference_formula(self) -> torch.Tensor:
+        """[3, V] standard deviation exactly as the reference's compute_std_of_cog produces it (vapc.py:873-880): pandas' groupby std =
+        Welford's recurrence in row order, / (n - 1), square root — bit for bit, its loss of digits at large coordinates included.
+        For diffing against the reference; `stats(std=True)` is the accurate one."""
+        V = self.nvoxels
+        out = torch.empty((3, V), dtype=torch.float64, device=self.device)
+        L.call("vapc_std_reference_formula", _ptr(self.xyzw), _ptr(self.pos_sorted), _ptr(self.start), V, _ptr(out), _stream())
+        return out
+
     @property
     def centroid_formula(self) -> str:
         """Which double `stats(cog=True).cog` — and with it point_distance() / closest_to_cog() — carries: "exact" (the mean from the

@@ -118,6 +118,9 @@ class Vapc:
         # (exact ties included) then EQUAL the reference's; "exact" = the mean from the reduction's shifted moments (no extra pass; equal
         # to within a bit, ties may fall differently).  Nothing is lost either way: both are correctly rounded to the last bit or two.
         self.centroid_formula = "reference"
+        # the std_* columns: "exact" = sqrt(M2 / (n - 1)) from the shifted moments; "reference" = pandas' groupby std bit for bit (Welford in
+        # row order, vapc.py:873-880), which is ~1e-7 off at UTM-sized coordinates — for users who diff against the reference
+        self.std_formula = "exact"
         self._df = None      # the host frame: original columns + whatever has been materialised
         self._lazy = {}      # column name -> (kind, device tensor, cloud); kind "voxel": [V] column to broadcast, "point": [N] column
         self._cols = None    # logical column order (frame columns + pending ones), None = the frame's own
@@ -734,7 +737,12 @@ class Vapc:
             self._voxelize()
             self.drop_columns += ["voxel_x", "voxel_y", "voxel_z"]
         cloud = self._get_cloud()
-        std = cloud.stats(std=True).std
+        if self.std_formula == "reference":
+            std = cloud.std_reference_formula()  # pandas' Welford recurrence in row order, bit for bit (for diffing)
+        elif self.std_formula == "exact":
+            std = cloud.stats(std=True).std
+        else:
+            raise ValueError("std_formula must be 'exact' or 'reference'")
         for k, name in enumerate(("std_x", "std_y", "std_z")):
             self._set_per_point(name, std[k])
         self.std_of_cog = True
