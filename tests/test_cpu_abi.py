@@ -306,3 +306,45 @@ def test_cloud_signature_sees_column_edits():
     e.df = df.iloc[:0]
     assert e._signature() == e._signature()
     e.invalidate()  # nothing computed yet: a no-op
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: include/vapc_b200.h compiles as strict C99 (no C++, no torch types), and a C program linked against
+    libvapc_b200.so alone calls it — the host-only entry points here (version, workspace sizes, the grid from a bounding box, the
+    argument check of a compute entry point), no GPU needed."""
+    import shutil
+    import subprocess
+
+    from vapc_b200 import _lib
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "vapc_b200.h"
+int main(void) {
+  vapc_grid_t g;
+  double mm[6] = {0.0, 0.0, 0.0, 49.9999, 49.9999, 3.9999};
+  memset(&g, 0, sizeof g);
+  g.voxel_size = 0.1;
+  if (vapc_abi_version() <= 0) return 1;
+  if (vapc_sort_workspace_bytes(100000000) == 0 || vapc_segment_workspace_bytes(100000000) == 0) return 2;
+  if (vapc_grid_from_bounds(&g, mm) != 0) return 3;
+  if (g.bits[0] != 9 || g.bits[1] != 9 || g.bits[2] != 6 || g.key_bytes != 4) return 4; /* 500 x 500 x 40 voxels: 24 key bits */
+  if (vapc_cog_reference_formula(NULL, NULL, NULL, -1, NULL, NULL) == 0) return 5;       /* bad arguments are refused ... */
+  if (strlen(vapc_last_error()) == 0) return 6;                                          /* ... with a message */
+  printf("abi %d bits %d %d %d\n", vapc_abi_version(), g.bits[0], g.bits[1], g.bits[2]);
+  return 0;
+}
+''')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("abi ")
