@@ -341,7 +341,10 @@ VAPC_API int vapc_mode_count_runs(const uint64_t* run_keys, const int64_t* run_w
  * (vapc.py:393-406).  order = point indices grouped by voxel ([start[v], start[v+1]) slices):
  * idx_sorted for vapc_attr_stats (original order inside a voxel), and the (voxel, value) order
  * produced by sorting vapc_f64_sort_keys by value, then stably by voxel row, for the median.
- * std = sqrt(var).  All outputs nullable. */
+ * std = sqrt(var).  All outputs nullable.  sum / mean / var are added the way numpy adds the reference's per-voxel slice (fewer
+ * than 8 values left to right, up to 128 in eight interleaved accumulators, beyond that numpy's pairwise halves; var as the
+ * pairwise sum of the rounded squared deviations from the rounded mean, no FMA): the columns equal the reference's bit for
+ * bit (tests/golden: assert_array_equal). */
 VAPC_API int vapc_attr_stats(const double* attr, const uint32_t* order, const uint32_t* start,
                              int64_t nvoxels, double* sum, double* mean, double* vmin, double* vmax,
                              double* var, void* stream);
