@@ -348,3 +348,39 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.startswith("abi ")
+
+
+def test_numpy_sum_order_of_the_attribute_kernel_on_the_host(tmp_path):
+    """csrc/np_sum.cuh — the summation order attr_stats_kernel uses for mean / sum / var — compiled for the host from the same text
+    (plain IEEE operations, -ffp-contract=off) equals ndarray.sum / mean / var bit for bit on slices of 1 to 1e6 values, contiguous
+    and as the strided field of a structured array (what the reference slices, vapc.py:387-399)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = tmp_path / "np_sum_host.cpp"
+    src.write_text('''
+#include "np_sum.cuh"
+extern "C" void stats(const double* x, long long stride, long long n, double* out) {
+  auto value = [&](int64_t p) { return x[p * stride]; };
+  const double s = np_pairwise_sum(value, 0, n);
+  const double m = s / (double)n;
+  auto sq = [&](int64_t p) { const double d = value(p) - m; return d * d; };
+  out[0] = s; out[1] = m; out[2] = np_pairwise_sum(sq, 0, n) / (double)n;
+}
+''')
+    so = tmp_path / "np_sum_host.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "vapc_b200", "csrc"), "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(5)
+    sizes = list(range(1, 300)) + [511, 512, 513, 1000, 1024, 4097, 8191, 8192, 8193, 10000, 65536, 100003, 1000000]
+    out = (ctypes.c_double * 3)()
+    for n in sizes:
+        a = rng.normal(-3, 5, n) * 10.0 ** rng.integers(-3, 6)
+        rec = np.zeros(n, dtype=[("voxel_x", "i8"), ("voxel_y", "i8"), ("voxel_z", "i8"), ("attr", "f8")])
+        rec["attr"] = a
+        for arr in (a, rec["attr"]):
+            lib.stats(ctypes.c_void_p(arr.ctypes.data), ctypes.c_longlong(arr.strides[0] // 8), ctypes.c_longlong(n), out)
+            assert tuple(out) == (float(arr.sum()), float(arr.mean()), float(arr.var())), n

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "np_sum.cuh"
 #include "common.cuh"
 
 namespace {
@@ -92,68 +93,8 @@ __global__ void __launch_bounds__(kThreads) mode_count_runs_kernel(const unsigne
 // ---- per-voxel statistics of an fp64 attribute (vapc.py:393-406) -----------------------------------------
 // One thread per voxel walks the voxel's points in original order (order = idx_sorted) — the order of the reference's slice
 // `sorted_data[attr][start:end]` (a stable lexsort by voxel) — and adds them the way numpy's `.sum()` / `.mean()` / `.var()` add a
-// 1-D fp64 slice, operation for operation, so that the columns equal the reference's bit for bit:
-//   fewer than 8 values: left to right;  up to 128: eight interleaved accumulators r[j] += a[i + j], combined as
-//   ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), then the tail left to right;  more: split at n / 2 rounded down to a multiple
-//   of 8 and add the two halves' sums (numpy's pairwise_sum, numpy/_core/src/umath/loops_utils.h.src).
+// 1-D fp64 slice (np_sum.cuh), so that the columns equal the reference's bit for bit:
 //   mean = sum / n;  var = pairwise sum of ((x - mean) * (x - mean)) / n  (ddof = 0, numpy/_core/_methods.py:_var);  no FMA anywhere.
-// The split recursion runs on an explicit stack (depth <= log2(n / 128) + 1 < 40): device recursion would need a stack-size guess.
-template <typename F>
-__device__ __forceinline__ double np_sum_block(F f, int64_t a, int64_t n) {
-  if (n < 8) {
-    double r = -0.0;
-    for (int64_t i = 0; i < n; ++i) r = __dadd_rn(r, f(a + i));
-    return r;
-  }
-  double r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = f(a + j);
-  int64_t i = 8;
-  for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(a + i + j));
-  }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, f(a + i));
-  return res;
-}
-template <typename F>
-__device__ double np_pairwise_sum(F f, int64_t a0, int64_t n0) {
-  if (n0 <= 128) return np_sum_block(f, a0, n0);
-  constexpr int kDepth = 48;
-  int64_t sa[kDepth], sn[kDepth];
-  double left[kDepth];
-  unsigned char state[kDepth];  // 0: not entered, 1: left half returned, 2: right half returned
-  int sp = 0;
-  sa[0] = a0; sn[0] = n0; state[0] = 0;
-  double ret = 0.0;
-  while (sp >= 0) {
-    if (state[sp] == 0) {
-      if (sn[sp] <= 128) {
-        ret = np_sum_block(f, sa[sp], sn[sp]);
-        --sp;
-      } else {
-        int64_t n2 = sn[sp] / 2;
-        n2 -= n2 % 8;
-        state[sp] = 1;
-        sa[sp + 1] = sa[sp]; sn[sp + 1] = n2; state[sp + 1] = 0;
-        ++sp;
-      }
-    } else if (state[sp] == 1) {
-      left[sp] = ret;
-      int64_t n2 = sn[sp] / 2;
-      n2 -= n2 % 8;
-      state[sp] = 2;
-      sa[sp + 1] = sa[sp] + n2; sn[sp + 1] = sn[sp] - n2; state[sp + 1] = 0;
-      ++sp;
-    } else {
-      ret = __dadd_rn(left[sp], ret);
-      --sp;
-    }
-  }
-  return ret;
-}
-
 __global__ void __launch_bounds__(kThreads) attr_stats_kernel(const double* __restrict__ attr, const uint32_t* __restrict__ order,
                                                               const uint32_t* __restrict__ start, int64_t nvox, double* __restrict__ sum,
                                                               double* __restrict__ mean, double* __restrict__ vmin, double* __restrict__ vmax,
