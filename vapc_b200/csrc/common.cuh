@@ -39,6 +39,8 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 struct Grid {
   double ox, oy, oz, vs;
   double ivs;  // 1 / vs, correctly rounded (host): the fast path of voxel_of_fast
+  double vs3;  // vs ** 3 as the host's pow forms it — what Python's `voxel_size ** 3` is (vapc.py:740); vs * vs * vs is one ulp off for
+               // a quarter of all voxel sizes (0.3 among them), and point_density would differ from the reference's in its last bit
   long long minx, miny, minz;
   int bx, by, bz;
 };
@@ -47,6 +49,7 @@ static inline Grid to_device_grid(const vapc_grid_t* g) {
   d.ox = g->origin[0]; d.oy = g->origin[1]; d.oz = g->origin[2];
   d.vs = g->voxel_size;
   d.ivs = 1.0 / g->voxel_size;
+  d.vs3 = pow(g->voxel_size, 3.0);
   d.minx = g->vmin[0]; d.miny = g->vmin[1]; d.minz = g->vmin[2];
   d.bx = g->bits[0]; d.by = g->bits[1]; d.bz = g->bits[2];
   return d;

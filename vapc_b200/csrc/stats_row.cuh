@@ -44,7 +44,7 @@ __device__ __forceinline__ void emit_voxel_stats(unsigned long long key, unsigne
                                                  int64_t v, const StatsOut& o) {
   const int64_t nvox = o.nvox;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  if (o.density) o.density[v] = (double)n / (g.vs * g.vs * g.vs);  // point_count / voxel_size**3
+  if (o.density) o.density[v] = __ddiv_rn((double)n, g.vs3);  // point_count / voxel_size ** 3, the cube as Python's pow gives it
   if (o.cog3) {
     long long vx, vy, vz;
     unpack_key(key, g, vx, vy, vz);
