@@ -313,6 +313,11 @@ def test_bitemporal_matches_reference(vapc, name):
     np.testing.assert_array_equal(got_vox[og], ref_vox[orf])
     assert (got_vox == ref_vox).mean() > 0.99
     P.assert_close_rel(md["distance"].to_numpy()[og], gold["bi_merged_distance"][orf], rtol=1e-9, atol=1e-13, what="distance")
+    # with the reference's centroid double (centroid_formula = "reference", the default) the joined rows come in the reference's order and
+    # the centroids and their distance are the reference's numbers
+    np.testing.assert_array_equal(got_vox, ref_vox)
+    for c in ("cog_x_x", "cog_y_x", "cog_z_x", "cog_x_y", "cog_y_y", "cog_z_y", "distance"):
+        np.testing.assert_array_equal(md[c].to_numpy(), gold["bi_merged_" + c], err_msg=c)
     six = ("cov_xx", "cov_xy", "cov_xz", "cov_yy", "cov_yz", "cov_zz")
     nine = ("cov_xx", "cov_xy", "cov_xz", "cov_yx", "cov_yy", "cov_yz", "cov_zx", "cov_zy", "cov_zz")
     eye = np.eye(3) * 1e-10
