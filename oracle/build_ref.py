@@ -19,7 +19,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("VAPC_REFERENCE_SRC", "/root/reference/src")
 DST = os.path.join(HERE, "_ref")
 REFERENCE_UNIT_TESTS = ("test_voxel.py", "test_compute.py", "integration_tests/test_main.py", "integration_tests/test_io.py",
-                        "test_data/vapc_in.laz", "test_data/small_mask.laz", "test_data/als_multichannel_leg000_points.laz")
+                        "test_data/vapc_in.laz", "test_data/small_mask.laz", "test_data/als_multichannel_leg000_points.laz",
+                        "test_data/tree_wind_condition.laz")
 
 
 def build(verbose=True) -> bool:

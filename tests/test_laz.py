@@ -1,7 +1,8 @@
 """The LASzip codec (vapc_laz_decode / vapc_laz_encode, host code in libvapc_b200.so) against the reference's own LAZ fixtures.
 
-The fixtures are read where the reference lies (/root/reference/tests/test_data, build container only); nothing is
-copied.  On a box without the reference these tests skip — the decoded real data still travels as the golden fixture
+The fixtures are read where the reference lies (/root/reference/tests/test_data) or, on a box without it, from the byte-identical
+copies oracle/build_ref.py keeps in the git-ignored oracle/_ref/tests/test_data; nothing of them is in this repository's history.
+With neither these tests skip — the decoded real data still travels as the golden fixture
 tests/golden/vapc_in_every50th_vs0.25.npz (oracle/make_golden.py real_file), which the GPU parity tests use.
 
 Pins: (1) the file headers' own bounding boxes, which the decoded points must reproduce exactly; (2) the reference's
@@ -18,6 +19,8 @@ from oracle import vapc_oracle as O
 from vapc_b200 import DataHandler, las
 
 DATA = "/root/reference/tests/test_data"
+if not os.path.exists(os.path.join(DATA, "vapc_in.laz")):  # the byte-identical copies oracle/build_ref.py makes (git-ignored, shipped to the GPU box)
+    DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "tests", "test_data")
 needs_fixtures = pytest.mark.skipif(not os.path.exists(os.path.join(DATA, "vapc_in.laz")), reason="reference fixtures not on this box")
 
 FMT2_ATTRS = ['intensity', 'return_number', 'number_of_returns', 'scan_direction_flag', 'edge_of_flight_line', 'classification', 'synthetic',
