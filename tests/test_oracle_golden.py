@@ -136,10 +136,8 @@ def test_attribute_statistics(name):
         attr = next(a for a in sorted((k[3:] for k in gold if k.startswith("in_")), key=len, reverse=True) if col.startswith(a + "_"))
         stat = col[len(attr) + 1:]
         got = O.attribute_statistic(gold["in_" + attr], g, stat)[g.point2voxel]
-        if stat == "mode" or "mode_count" in stat or stat in ("min", "max", "median"):
-            np.testing.assert_array_equal(got, gold[key], err_msg=col)
-        else:
-            np.testing.assert_allclose(got, gold[key], rtol=1e-12, atol=1e-12, err_msg=col)
+        # the oracle makes the reference's numpy calls on the reference's slices (vapc.py:393-406): every statistic is the golden column
+        np.testing.assert_array_equal(got, gold[key], err_msg=col)
 
 
 @pytest.mark.parametrize("name", [n for n in P.cloud_cases() if "mask_in_rows" in P.load_golden(n)])
