@@ -607,6 +607,7 @@ def main():
     tkey = "n1" if not (multi or chunk_alone) else "multi"
     traffic = (traffic_tab.get(tkey) or {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4),  # also against the nominal 8 TB/s of HBM3e
                 "traffic": traffic, "traffic_unit": "GB per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, read from "
                 "profiles/r2_ncu_traffic.json (the committed --set full capture of this command" + ("" if not multi else "'s per-GPU workload on one GPU") + ")",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_kernel[dom]["algorithmic_GB_per_launch"] * 1e9),
