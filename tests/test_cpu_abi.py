@@ -384,3 +384,35 @@ extern "C" void stats(const double* x, long long stride, long long n, double* ou
         for arr in (a, rec["attr"]):
             lib.stats(ctypes.c_void_p(arr.ctypes.data), ctypes.c_longlong(arr.strides[0] // 8), ctypes.c_longlong(n), out)
             assert tuple(out) == (float(arr.sum()), float(arr.mean()), float(arr.var())), n
+
+
+def test_module_level_helpers_match_reference_on_the_host():
+    """utilities.optimal_bins / get_version and bi_vapc.merge_with_suffix (names notebooks import from the reference) against the
+    unmodified reference's functions; compute_euclidean_distance / mutual_nearest_neighbors need the GPU (tests/test_gpu_neighbors.py)
+    and refuse to run without one."""
+    import pandas as pd
+
+    import vapc_b200
+    from vapc_b200 import bi_vapc as B
+    from vapc_b200 import utilities as U
+
+    assert U.get_version() == vapc_b200.get_version()
+    a, b = pd.DataFrame({"cog_x": [1.0, 2.0], "n": [3, 4]}), pd.DataFrame({"cog_x": [5.0, 6.0], "n": [7, 8]})
+    m = B.merge_with_suffix(a, b)
+    assert m.columns.tolist() == ["cog_x_x", "n_x", "cog_x_y", "n_y"] and m["n_y"].tolist() == [7, 8]
+    with pytest.raises(ValueError):
+        U.optimal_bins(np.arange(10.0), "doane")
+    with pytest.raises(RuntimeError):
+        B.compute_euclidean_distance(pd.DataFrame({f"cog_{c}_{s}": [0.0] for c in "xyz" for s in "xy"}))
+    from oracle import ref_harness
+
+    if not ref_harness.available():
+        pytest.skip("reference package not present")
+    ref_harness.import_reference()
+    from vapc.utilities import optimal_bins as ref_bins
+
+    rng = np.random.default_rng(2)
+    for n in (10, 100, 1000):
+        d = rng.normal(0, 3, n)
+        for method in ("sqrt", "sturges", "rice", "fd", "scott"):
+            assert U.optimal_bins(d, method) == ref_bins(d, method), (n, method)
